@@ -1,0 +1,141 @@
+"""Host-side batch plumbing for the 3D-graph path.
+
+* `Batch`            -- the attribute bag the model `forward(batch_data)` reads
+                        (`.z .pos .batch [.y .force .num_graphs .ptr]`), standing in for
+                        torch_geometric.data.Batch (reference run.py:121-124).
+* `collate` / `DataLoader` -- minimal replacement for torch_geometric.data.DataLoader
+                        (reference run.py:6,53-55): concatenates z/pos/force, stacks y, builds
+                        the sorted `batch` vector and `ptr`.
+* `synthetic_molecules` -- seeded synthetic QM9 / MD17 / OC20-shaped molecules;
+                        there is no network, so benchmarks and tests use these shapes.
+"""
+import math
+
+import torch
+
+
+class Batch:
+    def __init__(self, **kw):
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+    def to(self, device, non_blocking=False):
+        out = Batch()
+        for k, v in self.__dict__.items():
+            if isinstance(v, torch.Tensor):
+                v = v.to(device, non_blocking=non_blocking)
+            setattr(out, k, v)
+        return out
+
+    def pin_memory(self):
+        out = Batch()
+        for k, v in self.__dict__.items():
+            if isinstance(v, torch.Tensor):
+                v = v.pin_memory()
+            setattr(out, k, v)
+        return out
+
+    def keys(self):
+        return [k for k, v in self.__dict__.items() if isinstance(v, torch.Tensor)]
+
+    def __repr__(self):
+        parts = [f"{k}={tuple(v.shape)}" if isinstance(v, torch.Tensor) else f"{k}={v}"
+                 for k, v in self.__dict__.items()]
+        return "Batch(" + ", ".join(parts) + ")"
+
+
+def collate(items):
+    """List of per-molecule objects (attributes z, pos, optional y/force/...) -> Batch."""
+    out = Batch()
+    first = items[0]
+    keys = [k for k, v in vars(first).items() if isinstance(v, torch.Tensor)]
+    sizes = [int(it.z.size(0)) for it in items]
+    for k in keys:
+        vals = [getattr(it, k) for it in items]
+        if k == "y":
+            out.y = torch.cat([v.reshape(-1) for v in vals])
+        else:
+            setattr(out, k, torch.cat(vals, dim=0))
+    sz = torch.tensor(sizes, dtype=torch.long)
+    out.batch = torch.repeat_interleave(torch.arange(len(items)), sz)
+    ptr = torch.zeros(len(items) + 1, dtype=torch.long)
+    ptr[1:] = torch.cumsum(sz, 0)
+    out.ptr = ptr
+    out.num_graphs = len(items)
+    return out
+
+
+class DataLoader(torch.utils.data.DataLoader):
+    """`DataLoader(dataset, batch_size, shuffle)` as built at reference run.py:53-55."""
+
+    def __init__(self, dataset, batch_size=1, shuffle=False, **kw):
+        kw.pop("collate_fn", None)
+        super().__init__(dataset, batch_size, shuffle, collate_fn=collate, **kw)
+
+
+class Molecule:
+    def __init__(self, z, pos, y=None, force=None):
+        self.z, self.pos = z, pos
+        if y is not None:
+            self.y = y
+        if force is not None:
+            self.force = force
+
+
+def _sample_points(n, box, min_dist, gen):
+    """Rejection-sample n points uniform in `box` with pairwise distance >= min_dist."""
+    box_t = torch.tensor(box, dtype=torch.float32)
+    pts = torch.empty(0, 3)
+    tries = 0
+    while pts.size(0) < n:
+        cand = torch.rand(4 * n, 3, generator=gen) * box_t
+        for c in cand:
+            if pts.size(0) == 0 or float((pts - c).norm(dim=1).min()) >= min_dist:
+                pts = torch.cat([pts, c[None]], 0)
+                if pts.size(0) == n:
+                    break
+        tries += 1
+        if tries > 200:  # box too small for n points: relax by growing it
+            box_t = box_t * 1.1
+            tries = 0
+    return pts
+
+
+SHAPES = {
+    # name: (atoms, box in Angstrom, cutoff)   SURVEY.md §8d
+    "schnet-plumbing": (12, (4.0, 4.0, 4.0), 10.0),
+    "qm9": (18, (6.0, 5.0, 4.0), 5.0),
+    "md17-aspirin": (21, (7.0, 5.0, 3.5), 5.0),
+    "oc20-is2re": (73, (12.0, 12.0, 7.0), 6.0),
+}
+
+
+def synthetic_molecules(nmol, shape="qm9", seed=0, natoms=None, variable=False, min_dist=0.95):
+    """Seeded list of `Molecule`s of one of the SHAPES.  `variable=True` draws the atom count
+    per molecule around the nominal one (QM9: 9..29) and scales the box with it."""
+    n0, box, _ = SHAPES[shape]
+    if natoms is not None:
+        n0 = natoms
+    gen = torch.Generator().manual_seed(seed)
+    mols = []
+    for _ in range(nmol):
+        n = n0
+        b = box
+        if variable:
+            n = int(torch.clamp(torch.round(n0 + 0.25 * n0 * torch.randn(1, generator=gen)),
+                                max(2, n0 // 2), int(1.6 * n0) + 1).item())
+            s = (n / n0) ** (1.0 / 3.0)
+            b = tuple(x * s for x in box)
+        pos = _sample_points(n, b, min_dist, gen)
+        if shape == "md17-aspirin" and n == 21:
+            z = torch.tensor([6] * 9 + [8] * 4 + [1] * 8, dtype=torch.long)
+        else:
+            z = torch.randint(1, 10, (n,), generator=gen)
+        y = torch.randn(1, generator=gen)
+        force = torch.randn(n, 3, generator=gen)
+        mols.append(Molecule(z, pos, y, force))
+    return mols
+
+
+def synthetic_batch(nmol, shape="qm9", seed=0, **kw):
+    return collate(synthetic_molecules(nmol, shape, seed, **kw))
