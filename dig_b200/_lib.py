@@ -1,0 +1,89 @@
+"""ctypes binding of libdig3d.so (the C ABI declared in include/dig3d.h).
+
+The library is built in-tree by `__graft_entry__.build()` / `python -m dig_b200.build`.
+There is NO fallback: if the shared object is missing or a symbol is absent, importing the
+ops raises, and every op raises unless its tensors live on a CUDA device.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_int32, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdig3d.so")
+
+P = c_void_p
+
+
+class InitEWeights(Structure):
+    _fields_ = [(n, P) for n in ("emb", "w_rbf0", "b_rbf0", "w_lin", "b_lin", "w_rbf1")]
+
+
+class UpdateEWeights(Structure):
+    _fields_ = ([(n, P) for n in ("w_rbf1", "w_rbf2", "w_sbf2", "w_t2", "w_rbf",
+                                  "w_kj", "b_kj", "w_ji", "b_ji", "w_down", "w_up")]
+                + [("w_res", P * 6), ("b_res", P * 6), ("w_lin", P), ("b_lin", P)])
+
+
+class UpdateVWeights(Structure):
+    _fields_ = [("w_up", P), ("b_up", P), ("w_lins", P * 8), ("b_lins", P * 8), ("w_out", P),
+                ("n_lins", c_int32)]
+
+
+# name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/dig3d.h
+SIGNATURES = {
+    "dig3d_last_error": [],
+    "dig3d_abi_version": [],
+    "dig3d_graph_ptr": [P, c_int64, c_int64, P, P],
+    "dig3d_radius_neighbors": [P, P, P, c_int64, c_double, c_int32, P, P, P],
+    "dig3d_triplet_count": [P, P, c_int64, c_int32, P, P],
+    "dig3d_scan_counts": [P, P, c_int64, P, P, P, P],
+    "dig3d_edge_fill": [P, P, P, P, P, c_int64, c_int32, c_int64, P, P, P, P, P, P, P],
+    "dig3d_triplet_geometry": [P, P, P, P, P, c_int64, c_int32, P, P, P, P, P, P, P],
+    "dig3d_edge_basis": [P, c_int64, c_double, c_int32, P, c_int32, c_int32, P, P, P],
+    "dig3d_triplet_basis": [P, P, P, P, c_int64, c_int32, P, P, P],
+    "dig3d_triplet_basis_project": [P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int32, c_int32,
+                                    c_int32, P, P, P, P, P],
+    "dig3d_segment_sum": [P, P, c_int64, c_int64, P, P],
+    "dig3d_sphere_init_e": [P, P, P, P, c_int64, POINTER(InitEWeights), P, P, P],
+    "dig3d_sphere_update_e_a": [P, P, c_int64, POINTER(UpdateEWeights), P, P, P],
+    "dig3d_sphere_update_e_b": [P, P, P, P, P, P, c_int32, P, P, P, P, c_int64,
+                                POINTER(UpdateEWeights), P, P, P],
+    "dig3d_sphere_update_v": [P, c_int64, c_int32, POINTER(UpdateVWeights), P, P],
+    "dig3d_graph_readout": [P, P, c_int64, c_int64, c_int32, c_int32, P, P],
+}
+_RESTYPES = {"dig3d_last_error": c_char_p}
+
+_lib = None
+
+
+class Dig3dError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libdig3d.so and bind every declared symbol (raises if anything is missing)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Dig3dError(
+            f"{LIB_PATH} not found: build it with `python -m dig_b200.build` "
+            "(nvcc -gencode arch=compute_100a,code=sm_100a). There is no CPU/PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as exc:
+            raise Dig3dError(f"libdig3d.so does not export {name}") from exc
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, ctypes.c_int)
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.dig3d_last_error()
+        raise Dig3dError(f"{name} failed (rc={rc}): {msg.decode() if msg else ''}")

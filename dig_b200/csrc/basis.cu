@@ -1,0 +1,307 @@
+// Radial / angular basis evaluation (sm_100a).
+//
+//   dist_emb    spherenet/features.py:167-182   env(d/c) * sin(freq * d/c)
+//   angle_emb   spherenet/features.py:185-222   j~_ln(d_kj/c) * Y_l0(angle)          -> sbf [T, ns*nr]
+//               dimenetpp/features.py:183-220   same with env(d_kj/c) folded in
+//   torsion_emb spherenet/features.py:225-263   j~_bn(d_kj/c) * Y_f(angle, torsion)  -> tbf [T, ns*ns*nr]
+//
+// The closed forms are the generated headers (dig_b200/codegen.py): one correctly rounded fp32
+// op per node of the reference's lambdified expression.  The fused model path never materialises
+// sbf / tbf: dig3d_triplet_basis_project contracts them with lin_sbf1 / lin_t1 of ALL layers at
+// once, grouped by the (k->j) edge so the radial half of the contraction is done once per edge.
+#include "common.cuh"
+#include "generated/basis_dimenet_7_6.cuh"
+#include "generated/basis_dimenet_3_6.cuh"
+#include "generated/basis_gemnet_2_3.cuh"
+
+namespace dig3d {
+
+struct B76 {
+  static constexpr int NS = basis_dimenet_7_6::NS, NR = basis_dimenet_7_6::NR;
+  static constexpr int NB = NS * NR, NY = NS * NS;
+  __device__ static void bessel(float x, float (&o)[NB]) { basis_dimenet_7_6::bessel(x, o); }
+  __device__ static void yl0(float t, float (&o)[NS]) { basis_dimenet_7_6::yl0(t, o); }
+  __device__ static void ylm(float t, float p, float (&o)[NY]) { basis_dimenet_7_6::ylm(t, p, o); }
+};
+struct B36 {
+  static constexpr int NS = basis_dimenet_3_6::NS, NR = basis_dimenet_3_6::NR;
+  static constexpr int NB = NS * NR, NY = NS * NS;
+  __device__ static void bessel(float x, float (&o)[NB]) { basis_dimenet_3_6::bessel(x, o); }
+  __device__ static void yl0(float t, float (&o)[NS]) { basis_dimenet_3_6::yl0(t, o); }
+  __device__ static void ylm(float t, float p, float (&o)[NY]) { basis_dimenet_3_6::ylm(t, p, o); }
+};
+struct G23 {
+  static constexpr int NS = basis_gemnet_2_3::NS, NR = basis_gemnet_2_3::NR;
+  static constexpr int NB = NS * NR, NY = NS * NS;
+  __device__ static void bessel(float x, float (&o)[NB]) { basis_gemnet_2_3::bessel(x, o); }
+  __device__ static void yl0(float t, float (&o)[NS]) { basis_gemnet_2_3::yl0(t, o); }
+  __device__ static void ylm(float t, float p, float (&o)[NY]) { basis_gemnet_2_3::ylm(t, p, o); }
+};
+
+// Envelope.forward (features.py:159-164), ATen-CUDA op order:
+//   1./x -> reciprocal;  x.pow(p-1) -> powf (x*x / x*x*x for exponents 2 / 3)
+__device__ __forceinline__ float envelope(float x, int p, float a, float b, float c) {
+  const float rcp = __fdiv_rn(1.0f, x);
+  float p0;
+  const int q = p - 1;
+  if (q == 2) p0 = __fmul_rn(x, x);
+  else if (q == 3) p0 = __fmul_rn(__fmul_rn(x, x), x);
+  else if (q == 1) p0 = x;
+  else p0 = powf(x, (float)q);
+  const float p1 = __fmul_rn(p0, x);
+  const float p2 = __fmul_rn(p1, x);
+  float r = __fadd_rn(rcp, __fmul_rn(a, p0));
+  r = __fadd_rn(r, __fmul_rn(b, p1));
+  r = __fadd_rn(r, __fmul_rn(c, p2));
+  return r;
+}
+
+template <class BS>
+__global__ void edge_basis_kernel(const float* __restrict__ dist, int n_edges, float inv_cutoff, int p,
+                                  float ea, float eb, float ec, const float* __restrict__ freq,
+                                  int env_on_bessel, float* __restrict__ rbf0, float* __restrict__ bess) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  // dist / cutoff  ->  dist * (1.0f / cutoff)   (ATen CUDA div-by-scalar)
+  const float x = __fmul_rn(dist[e], inv_cutoff);
+  const float env = envelope(x, p, ea, eb, ec);
+  if (rbf0) {
+#pragma unroll
+    for (int n = 0; n < BS::NR; ++n)
+      rbf0[(size_t)e * BS::NR + n] = __fmul_rn(env, sinf(__fmul_rn(__ldg(freq + n), x)));
+  }
+  if (bess) {
+    float b[BS::NB];
+    BS::bessel(x, b);
+#pragma unroll
+    for (int c = 0; c < BS::NB; ++c)
+      bess[(size_t)e * BS::NB + c] = env_on_bessel ? __fmul_rn(env, b[c]) : b[c];
+  }
+}
+
+template <class BS>
+__global__ void triplet_basis_kernel(const float* __restrict__ bess, const float* __restrict__ angle,
+                                     const float* __restrict__ torsion, const int32_t* __restrict__ idx_kj,
+                                     int n_triplets, float* __restrict__ sbf, float* __restrict__ tbf) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_triplets) return;
+  const float* rb = bess + (size_t)idx_kj[t] * BS::NB;
+  const float th = angle[t];
+  if (sbf) {
+    float y0[BS::NS];
+    BS::yl0(th, y0);
+#pragma unroll
+    for (int l = 0; l < BS::NS; ++l)
+#pragma unroll
+      for (int n = 0; n < BS::NR; ++n)
+        sbf[(size_t)t * BS::NB + l * BS::NR + n] = __fmul_rn(__ldg(rb + l * BS::NR + n), y0[l]);
+  }
+  if (tbf) {
+    float y[BS::NY];
+    BS::ylm(th, torsion[t], y);
+    // (rbf[idx_kj].view(-1,1,n,k) * cbf.view(-1,n,n,1)): out[(a*n+b)*k+r] = rbf[b*k+r]*cbf[a*n+b]
+#pragma unroll
+    for (int ab = 0; ab < BS::NY; ++ab)
+#pragma unroll
+      for (int r = 0; r < BS::NR; ++r)
+        tbf[(size_t)t * (BS::NY * BS::NR) + ab * BS::NR + r] =
+            __fmul_rn(__ldg(rb + (ab % BS::NS) * BS::NR + r), y[ab]);
+  }
+}
+
+// ------------------------------------------------------------------ fused basis + projection
+// One warp per (k->j) edge.  Lane q = (layer l, basis row m), q = l*B + m, L*B == 32.
+//   R[ab]  = sum_r bess[kj][b*nr+r] * w_t1[l][m][(ab)*nr+r]        (ab = a*ns+b)   -- per edge
+//   Rs[l'] = sum_r bess[kj][l'*nr+r] * w_sbf1[l][m][l'*nr+r]                        -- per edge
+// then for every triplet (k->j->i) that uses this edge:
+//   t_p[t][q]   = sum_ab Y_ab(angle_t, torsion_t) * R[ab]
+//   sbf_p[t][q] = sum_l' Y_l'0(angle_t) * Rs[l']
+// The harmonics of up to 32 triplets are evaluated with lane == triplet, parked in shared
+// memory, then consumed with lane == (l, m).
+constexpr int PRJ_WARPS = 4;
+
+template <class BS, bool TORSION>
+__global__ void __launch_bounds__(PRJ_WARPS * 32)
+triplet_basis_project_kernel(const float* __restrict__ bess, const float* __restrict__ angle,
+                             const float* __restrict__ torsion, const int32_t* __restrict__ src,
+                             const int32_t* __restrict__ dst, const int32_t* __restrict__ row_ptr,
+                             const int32_t* __restrict__ trip_ptr, const int32_t* __restrict__ graph_ptr,
+                             const int64_t* __restrict__ batch, int n_edges,
+                             const float* __restrict__ w_sbf1, const float* __restrict__ w_t1,
+                             float* __restrict__ sbf_p, float* __restrict__ t_p) {
+  constexpr int NS = BS::NS, NR = BS::NR, NB = BS::NB, NY = BS::NY;
+  constexpr int NYT = TORSION ? NY : 1;
+  __shared__ float s_bess[PRJ_WARPS][NB];
+  __shared__ float s_y[PRJ_WARPS][32][NYT + NS + 1];
+  __shared__ int32_t s_trip[PRJ_WARPS][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int kj = blockIdx.x * PRJ_WARPS + w;
+  if (kj >= n_edges) return;
+  const int k = src[kj], j = dst[kj];
+  for (int c = lane; c < NB; c += 32) s_bess[w][c] = __ldg(bess + (size_t)kj * NB + c);
+  __syncwarp();
+  // per-edge radial contraction (weights streamed from L2; rows of this lane are contiguous)
+  float R[NYT], Rs[NS];
+  if (TORSION) {
+    const float* wt = w_t1 + (size_t)lane * (NY * NR);
+#pragma unroll
+    for (int ab = 0; ab < NY; ++ab) {
+      float acc = 0.f;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) acc = fmaf(s_bess[w][(ab % NS) * NR + r], __ldg(wt + ab * NR + r), acc);
+      R[ab] = acc;
+    }
+  }
+  {
+    const float* ws = w_sbf1 + (size_t)lane * NB;
+#pragma unroll
+    for (int l = 0; l < NS; ++l) {
+      float acc = 0.f;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) acc = fmaf(s_bess[w][l * NR + r], __ldg(ws + l * NR + r), acc);
+      Rs[l] = acc;
+    }
+  }
+  // enumerate the out-edges e = (j -> i), i != k, of j: candidates are the nodes of j's graph
+  const int jbase = row_ptr[j], dj = row_ptr[j + 1] - jbase;
+  const int rank_k = kj - jbase;  // position of k among j's in-neighbours
+  const int g = (int)batch[j];
+  const int lo = graph_ptr[g], hi = graph_ptr[g + 1];
+  for (int c0 = lo; c0 < hi; c0 += 32) {
+    const int i = c0 + lane;
+    int t = -1;
+    if (i < hi && i != k && i != j) {
+      const int ib = row_ptr[i], di = row_ptr[i + 1] - ib;
+      // binary search j among i's in-neighbour sources (ascending)
+      int a = 0, b = di;
+      while (a < b) { int mid = (a + b) >> 1; if (src[ib + mid] < j) a = mid + 1; else b = mid; }
+      if (a < di && src[ib + a] == j) {
+        const int e = ib + a;
+        // slot of k in e's triplet list: rank_k minus one if i precedes k in j's in-list
+        int a2 = 0, b2 = dj;
+        while (a2 < b2) { int mid = (a2 + b2) >> 1; if (src[jbase + mid] < i) a2 = mid + 1; else b2 = mid; }
+        const bool i_in = (a2 < dj && src[jbase + a2] == i);
+        t = trip_ptr[e] + rank_k - ((i_in && a2 < rank_k) ? 1 : 0);
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, t >= 0);
+    if (t >= 0) {
+      const int slot = __popc(m & ((1u << lane) - 1));
+      s_trip[w][slot] = t;
+      const float th = angle[t];
+      float y0[NS];
+      BS::yl0(th, y0);
+#pragma unroll
+      for (int l = 0; l < NS; ++l) s_y[w][slot][NYT + l] = y0[l];
+      if (TORSION) {
+        float y[NY];
+        BS::ylm(th, torsion[t], y);
+#pragma unroll
+        for (int ab = 0; ab < NY; ++ab) s_y[w][slot][ab] = y[ab];
+      }
+    }
+    __syncwarp();
+    const int cnt = __popc(m);
+    for (int s = 0; s < cnt; ++s) {
+      const int tt = s_trip[w][s];
+      float acc_s = 0.f;
+#pragma unroll
+      for (int l = 0; l < NS; ++l) acc_s = fmaf(s_y[w][s][NYT + l], Rs[l], acc_s);
+      sbf_p[(size_t)tt * 32 + lane] = acc_s;
+      if (TORSION) {
+        float acc_t = 0.f;
+#pragma unroll
+        for (int ab = 0; ab < NY; ++ab) acc_t = fmaf(s_y[w][s][ab], R[ab], acc_t);
+        t_p[(size_t)tt * 32 + lane] = acc_t;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <class BS>
+static int launch_edge_basis(const float* dist, int64_t n_edges, double cutoff, int exponent,
+                             const float* freq, int env_on_bessel, float* rbf0, float* bess,
+                             cudaStream_t st) {
+  const int p = exponent + 1;
+  const float a = (float)(-(p + 1) * (p + 2) / 2.0), b = (float)(p * (p + 2)), c = (float)(-p * (p + 1) / 2.0);
+  const float inv = 1.0f / (float)cutoff;
+  edge_basis_kernel<BS><<<ceil_div(n_edges, 128), 128, 0, st>>>(dist, (int)n_edges, inv, p, a, b, c, freq,
+                                                             env_on_bessel, rbf0, bess);
+  return 0;
+}
+
+}  // namespace dig3d
+
+using namespace dig3d;
+
+extern "C" {
+
+int dig3d_edge_basis(const float* dist, int64_t n_edges, double cutoff, int32_t envelope_exponent,
+                     const float* freq, int32_t basis_id, int32_t envelope_on_bessel, float* rbf0,
+                     float* bess, void* stream) {
+  DIG3D_REQUIRE(dist && (rbf0 || bess), "edge_basis: null pointer");
+  DIG3D_REQUIRE(!rbf0 || freq, "edge_basis: rbf0 requested without freq");
+  if (n_edges == 0) return DIG3D_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (basis_id) {
+    case 0: launch_edge_basis<B76>(dist, n_edges, cutoff, envelope_exponent, freq, envelope_on_bessel, rbf0, bess, st); break;
+    case 1: launch_edge_basis<B36>(dist, n_edges, cutoff, envelope_exponent, freq, envelope_on_bessel, rbf0, bess, st); break;
+    case 2: launch_edge_basis<G23>(dist, n_edges, cutoff, envelope_exponent, freq, envelope_on_bessel, rbf0, bess, st); break;
+    default: set_error("edge_basis: unknown basis_id %d", basis_id); return DIG3D_EUNSUPPORTED;
+  }
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_triplet_basis(const float* bess, const float* angle, const float* torsion, const int32_t* idx_kj,
+                        int64_t n_triplets, int32_t basis_id, float* sbf, float* tbf, void* stream) {
+  DIG3D_REQUIRE(bess && angle && idx_kj && (sbf || tbf), "triplet_basis: null pointer");
+  DIG3D_REQUIRE(!tbf || torsion, "triplet_basis: tbf requested without torsion");
+  if (n_triplets == 0) return DIG3D_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ceil_div(n_triplets, 128);
+  switch (basis_id) {
+    case 0: triplet_basis_kernel<B76><<<grid, 128, 0, st>>>(bess, angle, torsion, idx_kj, (int)n_triplets, sbf, tbf); break;
+    case 1: triplet_basis_kernel<B36><<<grid, 128, 0, st>>>(bess, angle, torsion, idx_kj, (int)n_triplets, sbf, tbf); break;
+    default: set_error("triplet_basis: unsupported basis_id %d", basis_id); return DIG3D_EUNSUPPORTED;
+  }
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_triplet_basis_project(const float* bess, const float* angle, const float* torsion,
+                                const int32_t* src, const int32_t* dst, const int32_t* row_ptr,
+                                const int32_t* trip_ptr, const int32_t* graph_ptr, const int64_t* batch,
+                                int64_t n_edges, int64_t n_triplets, int32_t basis_id, int32_t n_layers,
+                                int32_t basis_emb, const float* w_sbf1, const float* w_t1, float* sbf_p,
+                                float* t_p, void* stream) {
+  DIG3D_REQUIRE(bess && angle && src && dst && row_ptr && trip_ptr && graph_ptr && batch && w_sbf1 && sbf_p,
+                "triplet_basis_project: null pointer");
+  DIG3D_REQUIRE(n_layers * basis_emb == 32, "triplet_basis_project: n_layers*basis_emb must be 32, got %d*%d",
+                n_layers, basis_emb);
+  const bool tors = (t_p != nullptr);
+  DIG3D_REQUIRE(!tors || (torsion && w_t1), "triplet_basis_project: torsion path needs torsion and w_t1");
+  if (n_edges == 0 || n_triplets == 0) return DIG3D_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ceil_div(n_edges, PRJ_WARPS);
+#define DIG3D_PRJ(BS)                                                                                       \
+  if (tors)                                                                                                 \
+    triplet_basis_project_kernel<BS, true><<<grid, PRJ_WARPS * 32, 0, st>>>(                                \
+        bess, angle, torsion, src, dst, row_ptr, trip_ptr, graph_ptr, batch, (int)n_edges, w_sbf1, w_t1,    \
+        sbf_p, t_p);                                                                                        \
+  else                                                                                                      \
+    triplet_basis_project_kernel<BS, false><<<grid, PRJ_WARPS * 32, 0, st>>>(                               \
+        bess, angle, torsion, src, dst, row_ptr, trip_ptr, graph_ptr, batch, (int)n_edges, w_sbf1, w_t1,    \
+        sbf_p, t_p);
+  switch (basis_id) {
+    case 0: DIG3D_PRJ(B76); break;
+    case 1: DIG3D_PRJ(B36); break;
+    default: set_error("triplet_basis_project: unsupported basis_id %d", basis_id); return DIG3D_EUNSUPPORTED;
+  }
+#undef DIG3D_PRJ
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+}  // extern "C"

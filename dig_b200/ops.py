@@ -1,0 +1,259 @@
+"""Tensor-level wrappers over the C ABI (include/dig3d.h).
+
+PyTorch is used for device memory (caching allocator) and streams only; every computation below
+is a hand-written sm_100a kernel in libdig3d.so.  Inputs are validated here (dtype / device /
+contiguity / alignment), the C side only returns codes.  Nothing in this module has a CPU path.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import call
+
+BASIS_IDS = {("dimenet", 7, 6): 0, ("dimenet", 3, 6): 1, ("gemnet", 2, 3): 2}
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t, dtype=None, name="tensor", align=4):
+    """Device pointer of a validated tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t)}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: dig_b200 ops run on CUDA tensors only (got device {t.device}); "
+                           "there is no CPU fallback")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: tensor must be contiguous")
+    ptr = t.data_ptr()
+    if t.numel() and ptr % align != 0:
+        raise ValueError(f"{name}: storage must be {align}-byte aligned")
+    return ctypes.c_void_p(ptr)
+
+
+class Graph3D:
+    """Radius graph in CSR-by-target form plus the implicit triplet structure."""
+    __slots__ = ("n_nodes", "n_graphs", "n_edges", "n_triplets", "cap", "graph_ptr", "batch",
+                 "row_ptr", "src", "dst", "edge_index", "dist", "vec", "trip_ptr",
+                 "angle", "torsion", "idx_kj", "idx_ji", "idx_kj64", "idx_ji64")
+
+    def __init__(self):
+        for s in self.__slots__:
+            setattr(self, s, None)
+
+
+def build_graph(pos, batch, cutoff, num_graphs=None, max_num_neighbors=32, want_vec=False,
+                want_edge_index=True):
+    """radius_graph(pos, r=cutoff, batch) (reference spherenet.py:304 etc.) + triplet offsets.
+
+    One host<->device synchronisation: the edge and triplet totals (two ints) are read back to size
+    the per-edge / per-triplet buffers (the reference path has >= 10 implicit syncs)."""
+    if pos.dim() != 2 or pos.size(1) != 3:
+        raise ValueError(f"pos must be [N, 3], got {tuple(pos.shape)}")
+    n = pos.size(0)
+    if batch is None:
+        batch = torch.zeros(n, dtype=torch.long, device=pos.device)
+    if batch.shape != (n,):
+        raise ValueError("batch must be [N]")
+    pos = pos.detach()
+    dev = pos.device
+    st = _stream()
+    if num_graphs is None:
+        num_graphs = int(batch[-1].item()) + 1 if n else 0
+    g = Graph3D()
+    g.n_nodes, g.n_graphs, g.batch = n, int(num_graphs), batch
+    cap = int(max_num_neighbors) + 1
+    g.cap = cap
+    g.graph_ptr = torch.empty(g.n_graphs + 1, dtype=torch.int32, device=dev)
+    call("dig3d_graph_ptr", _p(batch, torch.int64, "batch"), n, g.n_graphs, _p(g.graph_ptr), st)
+    nbr = torch.empty(max(n, 1) * cap, dtype=torch.int32, device=dev)
+    deg = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    tcnt = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    call("dig3d_radius_neighbors", _p(pos, torch.float32, "pos"), _p(batch), _p(g.graph_ptr), n,
+         float(cutoff), cap, _p(nbr), _p(deg), st)
+    call("dig3d_triplet_count", _p(nbr), _p(deg), n, cap, _p(tcnt), st)
+    g.row_ptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    node_trip_ptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    totals = torch.empty(4, dtype=torch.int32, device=dev)
+    call("dig3d_scan_counts", _p(deg), _p(tcnt), n, _p(g.row_ptr), _p(node_trip_ptr), _p(totals), st)
+    tot = totals[:2].tolist()                      # the one sync of the forward pass
+    g.n_edges, g.n_triplets = int(tot[0]), int(tot[1])
+    e = g.n_edges
+    g.src = torch.empty(max(e, 1), dtype=torch.int32, device=dev)[:e]
+    g.dst = torch.empty(max(e, 1), dtype=torch.int32, device=dev)[:e]
+    g.dist = torch.empty(max(e, 1), dtype=torch.float32, device=dev)[:e]
+    g.trip_ptr = torch.zeros(e + 1, dtype=torch.int32, device=dev)
+    g.edge_index = torch.empty(2, e, dtype=torch.int64, device=dev) if want_edge_index else None
+    g.vec = torch.empty(e, 3, dtype=torch.float32, device=dev) if want_vec else None
+    if e:
+        call("dig3d_edge_fill", _p(pos), _p(nbr), _p(deg), _p(g.row_ptr), _p(node_trip_ptr), n, cap, e,
+             _p(g.edge_index) if want_edge_index else None, _p(g.src), _p(g.dst), _p(g.dist),
+             _p(g.vec) if want_vec else None, _p(g.trip_ptr), st)
+    return g
+
+
+def triplet_geometry(g, pos, use_torsion, want_idx=True, want_idx64=False):
+    """xyz_to_dat's angle / torsion / idx_kj / idx_ji (reference utils/geometric_computing.py:43-75)."""
+    dev = pos.device
+    t = g.n_triplets
+    g.angle = torch.empty(t, dtype=torch.float32, device=dev)
+    g.torsion = torch.empty(t, dtype=torch.float32, device=dev) if use_torsion else None
+    if want_idx:
+        g.idx_kj = torch.empty(t, dtype=torch.int32, device=dev)
+        g.idx_ji = torch.empty(t, dtype=torch.int32, device=dev)
+    if want_idx64:
+        g.idx_kj64 = torch.empty(t, dtype=torch.int64, device=dev)
+        g.idx_ji64 = torch.empty(t, dtype=torch.int64, device=dev)
+    if g.n_edges and t:
+        call("dig3d_triplet_geometry", _p(pos.detach(), torch.float32, "pos"), _p(g.src), _p(g.dst),
+             _p(g.row_ptr), _p(g.trip_ptr), g.n_edges, int(bool(use_torsion)), _p(g.angle),
+             _p(g.torsion) if use_torsion else None,
+             _p(g.idx_kj) if want_idx else None, _p(g.idx_ji) if want_idx else None,
+             _p(g.idx_kj64) if want_idx64 else None, _p(g.idx_ji64) if want_idx64 else None, _stream())
+    return g
+
+
+def edge_basis(dist, cutoff, envelope_exponent, freq, basis_id, envelope_on_bessel, num_radial,
+               n_bessel, want_rbf0=True, want_bessel=True):
+    e = dist.numel()
+    dev = dist.device
+    rbf0 = torch.empty(e, num_radial, dtype=torch.float32, device=dev) if want_rbf0 else None
+    bess = torch.empty(e, n_bessel, dtype=torch.float32, device=dev) if want_bessel else None
+    if e:
+        call("dig3d_edge_basis", _p(dist, torch.float32, "dist"), e, float(cutoff), int(envelope_exponent),
+             _p(freq.detach(), torch.float32, "freq") if freq is not None else None, int(basis_id),
+             int(bool(envelope_on_bessel)), _p(rbf0) if want_rbf0 else None,
+             _p(bess) if want_bessel else None, _stream())
+    return rbf0, bess
+
+
+def triplet_basis(bess, angle, torsion, idx_kj, basis_id, ns, nr, want_tbf):
+    """Materialised sbf [T, ns*nr] / tbf [T, ns*ns*nr] (API-parity / test path)."""
+    t = angle.numel()
+    dev = angle.device
+    sbf = torch.empty(t, ns * nr, dtype=torch.float32, device=dev)
+    tbf = torch.empty(t, ns * ns * nr, dtype=torch.float32, device=dev) if want_tbf else None
+    if t:
+        call("dig3d_triplet_basis", _p(bess, torch.float32), _p(angle, torch.float32),
+             _p(torsion, torch.float32) if want_tbf else None, _p(idx_kj, torch.int32), t, int(basis_id),
+             _p(sbf), _p(tbf) if want_tbf else None, _stream())
+    return sbf, tbf
+
+
+def triplet_basis_project(g, bess, basis_id, w_sbf1_rows, w_t1_rows):
+    """w_sbf1_rows: [32, ns*nr], w_t1_rows: [32, ns*ns*nr] or None.  Returns sbf_p [T,32], t_p [T,32]|None."""
+    t = g.n_triplets
+    dev = bess.device
+    sbf_p = torch.empty(max(t, 1), 32, dtype=torch.float32, device=dev)[:t]
+    t_p = torch.empty(max(t, 1), 32, dtype=torch.float32, device=dev)[:t] if w_t1_rows is not None else None
+    if t and g.n_edges:
+        call("dig3d_triplet_basis_project", _p(bess, torch.float32), _p(g.angle),
+             _p(g.torsion) if w_t1_rows is not None else None, _p(g.src), _p(g.dst), _p(g.row_ptr),
+             _p(g.trip_ptr), _p(g.graph_ptr), _p(g.batch, torch.int64), g.n_edges, t, int(basis_id), 4, 8,
+             _p(w_sbf1_rows, torch.float32, "w_sbf1"),
+             _p(w_t1_rows, torch.float32, "w_t1") if w_t1_rows is not None else None,
+             _p(sbf_p), _p(t_p) if t_p is not None else None, _stream())
+    return sbf_p, t_p
+
+
+def segment_sum(x, ptr):
+    """scatter(x, index, dim=0, reduce='sum') for a sorted index given as CSR pointers."""
+    if x.dim() != 2:
+        raise ValueError("segment_sum expects [rows, width]")
+    s = ptr.numel() - 1
+    out = torch.empty(s, x.size(1), dtype=torch.float32, device=x.device)
+    if s:
+        call("dig3d_segment_sum", _p(x, torch.float32, "x", align=16 if x.size(1) % 4 == 0 else 4), _p(ptr, torch.int32, "ptr"), s, x.size(1),
+             _p(out), _stream())
+    return out
+
+
+def graph_readout(v_all, graph_ptr, n_graphs, n_nodes):
+    """v_all: [n_blocks, N, C] -> u [n_graphs, C] (sum over nodes of each graph, then over blocks)."""
+    nb, _, c = v_all.shape
+    u = torch.empty(n_graphs, c, dtype=torch.float32, device=v_all.device)
+    if n_graphs:
+        call("dig3d_graph_readout", _p(v_all, torch.float32, align=4), _p(graph_ptr, torch.int32), n_graphs,
+             n_nodes, nb, c, _p(u, align=4), _stream())
+    return u
+
+
+# ----------------------------------------------------------------------------- SphereNet / DimeNet++
+def _wp(t, name):
+    return _p(t.detach(), torch.float32, name, align=16).value if t is not None else None
+
+
+def pack_init_e(m):
+    w = _lib.InitEWeights()
+    w.emb = _wp(m.emb.weight, "emb")
+    w.w_rbf0, w.b_rbf0 = _wp(m.lin_rbf_0.weight, "lin_rbf_0.w"), _wp(m.lin_rbf_0.bias, "lin_rbf_0.b")
+    w.w_lin, w.b_lin = _wp(m.lin.weight, "lin.w"), _wp(m.lin.bias, "lin.b")
+    w.w_rbf1 = _wp(m.lin_rbf_1.weight, "lin_rbf_1.w")
+    return w
+
+
+def pack_update_e(m, torsion):
+    w = _lib.UpdateEWeights()
+    w.w_rbf1, w.w_rbf2 = _wp(m.lin_rbf1.weight, "lin_rbf1"), _wp(m.lin_rbf2.weight, "lin_rbf2")
+    w.w_sbf2 = _wp(m.lin_sbf2.weight, "lin_sbf2")
+    w.w_t2 = _wp(m.lin_t2.weight, "lin_t2") if torsion else None
+    w.w_rbf = _wp(m.lin_rbf.weight, "lin_rbf")
+    w.w_kj, w.b_kj = _wp(m.lin_kj.weight, "lin_kj.w"), _wp(m.lin_kj.bias, "lin_kj.b")
+    w.w_ji, w.b_ji = _wp(m.lin_ji.weight, "lin_ji.w"), _wp(m.lin_ji.bias, "lin_ji.b")
+    w.w_down, w.w_up = _wp(m.lin_down.weight, "lin_down"), _wp(m.lin_up.weight, "lin_up")
+    res = list(m.layers_before_skip) + list(m.layers_after_skip)
+    for r, layer in enumerate(res):
+        w.w_res[2 * r], w.b_res[2 * r] = _wp(layer.lin1.weight, "res.lin1.w"), _wp(layer.lin1.bias, "res.lin1.b")
+        w.w_res[2 * r + 1], w.b_res[2 * r + 1] = _wp(layer.lin2.weight, "res.lin2.w"), _wp(layer.lin2.bias, "res.lin2.b")
+    w.w_lin, w.b_lin = _wp(m.lin.weight, "lin.w"), _wp(m.lin.bias, "lin.b")
+    return w
+
+
+def pack_update_v(m):
+    w = _lib.UpdateVWeights()
+    w.w_up, w.b_up = _wp(m.lin_up.weight, "lin_up.w"), _wp(m.lin_up.bias, "lin_up.b")
+    for l, lin in enumerate(m.lins):
+        w.w_lins[l], w.b_lins[l] = _wp(lin.weight, "lins.w"), _wp(lin.bias, "lins.b")
+    w.w_out = _wp(m.lin.weight, "lin.w")
+    w.n_lins = len(m.lins)
+    return w
+
+
+def sphere_init_e(z, g, rbf0, w, hidden):
+    e1 = torch.empty(max(g.n_edges, 1), hidden, dtype=torch.float32, device=rbf0.device)[:g.n_edges]
+    v_in = torch.zeros(g.n_nodes, hidden, dtype=torch.float32, device=rbf0.device)
+    if g.n_edges:
+        call("dig3d_sphere_init_e", _p(z, torch.int64, "z"), _p(g.src), _p(g.dst), _p(rbf0), g.n_edges,
+             ctypes.byref(w), _p(e1), _p(v_in), _stream())
+    return e1, v_in
+
+
+def sphere_update_e(e1, g, rbf0, sbf_p, t_p, col0, w, hidden, int_emb):
+    """One update_e block (parts A + B).  sbf_p/t_p: [T, 32] with this layer's 8 columns at col0."""
+    dev = e1.device
+    e = g.n_edges
+    x_ji = torch.empty(max(e, 1), hidden, dtype=torch.float32, device=dev)[:e]
+    x_down = torch.empty(max(e, 1), int_emb, dtype=torch.float32, device=dev)[:e]
+    e1_out = torch.empty(max(e, 1), hidden, dtype=torch.float32, device=dev)[:e]
+    v_in = torch.zeros(g.n_nodes, hidden, dtype=torch.float32, device=dev)
+    if e:
+        st = _stream()
+        call("dig3d_sphere_update_e_a", _p(e1), _p(rbf0), e, ctypes.byref(w), _p(x_ji), _p(x_down), st)
+        sp = ctypes.c_void_p(sbf_p.data_ptr() + 4 * col0)
+        tp = ctypes.c_void_p(t_p.data_ptr() + 4 * col0) if t_p is not None else None
+        call("dig3d_sphere_update_e_b", _p(e1), _p(x_ji), _p(x_down), _p(rbf0), sp, tp, 32, _p(g.src),
+             _p(g.dst), _p(g.row_ptr), _p(g.trip_ptr), e, ctypes.byref(w), _p(e1_out), _p(v_in), st)
+    return e1_out, v_in
+
+
+def sphere_update_v(v_in, w, out_channels, v_out):
+    n = v_in.size(0)
+    if n:
+        call("dig3d_sphere_update_v", _p(v_in), n, int(out_channels), ctypes.byref(w), _p(v_out, align=4), _stream())
+    return v_out

@@ -1,0 +1,272 @@
+"""SphereNet and DimeNet++ behind the reference's class API, running on fused sm_100a kernels.
+
+Mirrors (constructor kwargs, attribute / parameter names, forward(batch_data) -> [num_graphs, out]):
+    reference dig/threedgraph/method/spherenet/spherenet.py:228-320   (SphereNet)
+    reference dig/threedgraph/method/dimenetpp/dimenetpp.py:207-293    (DimeNetPP)
+
+The nn.Module tree below only HOLDS parameters under the reference's names (so state_dicts
+round-trip) and initialises them like the reference; the arithmetic of
+`forward` is the kernel pipeline in dig_b200/ops.py:
+
+    radius graph + triplet offsets -> triplet geometry (angle[, torsion]) -> edge basis ->
+    fused triplet basis x first basis projection (all layers) -> init_e -> update_v ->
+    [update_e (A, B) -> update_v] x L -> graph readout
+"""
+from math import sqrt
+
+import torch
+from torch import nn
+
+from ... import ops
+from ...basis import envelope_coefficients  # noqa: F401  (documented dependency)
+from ._common import ResidualLayer, glorot_orthogonal, require_cuda, swish
+
+_SUPPORTED = dict(hidden_channels=128, int_emb_size=64, out_emb_channels=256, num_radial=6,
+                  num_before_skip=1, num_after_skip=2)
+
+
+class dist_emb(nn.Module):
+    """Holder of the trainable Bessel frequencies (reference spherenet/features.py:167-182)."""
+
+    def __init__(self, num_radial, cutoff=5.0, envelope_exponent=5):
+        super().__init__()
+        self.cutoff = cutoff
+        self.envelope_exponent = envelope_exponent
+        self.freq = nn.Parameter(torch.Tensor(num_radial))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        from math import pi
+        self.freq.data = torch.arange(1, self.freq.numel() + 1).float().mul_(pi)
+
+
+class emb(nn.Module):
+    """reference spherenet.py:17-32 / dimenetpp.py:20-33: only dist_emb owns parameters."""
+
+    def __init__(self, num_spherical, num_radial, cutoff, envelope_exponent):
+        super().__init__()
+        self.dist_emb = dist_emb(num_radial, cutoff, envelope_exponent)
+        self.num_spherical, self.num_radial = num_spherical, num_radial
+
+    def reset_parameters(self):
+        self.dist_emb.reset_parameters()
+
+
+class init(nn.Module):
+    """reference spherenet.py:53-91 / dimenetpp.py:55-78."""
+
+    def __init__(self, num_radial, hidden_channels):
+        super().__init__()
+        self.emb = nn.Embedding(95, hidden_channels)
+        self.lin_rbf_0 = nn.Linear(num_radial, hidden_channels)
+        self.lin = nn.Linear(3 * hidden_channels, hidden_channels)
+        self.lin_rbf_1 = nn.Linear(num_radial, hidden_channels, bias=False)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        self.emb.weight.data.uniform_(-sqrt(3), sqrt(3))
+        self.lin_rbf_0.reset_parameters()
+        self.lin.reset_parameters()
+        glorot_orthogonal(self.lin_rbf_1.weight, scale=2.0)
+
+
+class update_e(nn.Module):
+    """reference spherenet.py:94-182 (torsion=True) / dimenetpp.py:81-161 (torsion=False)."""
+
+    def __init__(self, hidden_channels, int_emb_size, basis_emb_size_dist, basis_emb_size_angle,
+                 basis_emb_size_torsion, num_spherical, num_radial, num_before_skip, num_after_skip,
+                 torsion):
+        super().__init__()
+        self.torsion = torsion
+        self.lin_rbf1 = nn.Linear(num_radial, basis_emb_size_dist, bias=False)
+        self.lin_rbf2 = nn.Linear(basis_emb_size_dist, hidden_channels, bias=False)
+        self.lin_sbf1 = nn.Linear(num_spherical * num_radial, basis_emb_size_angle, bias=False)
+        self.lin_sbf2 = nn.Linear(basis_emb_size_angle, int_emb_size, bias=False)
+        if torsion:
+            self.lin_t1 = nn.Linear(num_spherical * num_spherical * num_radial, basis_emb_size_torsion, bias=False)
+            self.lin_t2 = nn.Linear(basis_emb_size_torsion, int_emb_size, bias=False)
+        self.lin_rbf = nn.Linear(num_radial, hidden_channels, bias=False)
+        self.lin_kj = nn.Linear(hidden_channels, hidden_channels)
+        self.lin_ji = nn.Linear(hidden_channels, hidden_channels)
+        self.lin_down = nn.Linear(hidden_channels, int_emb_size, bias=False)
+        self.lin_up = nn.Linear(int_emb_size, hidden_channels, bias=False)
+        self.layers_before_skip = nn.ModuleList([ResidualLayer(hidden_channels) for _ in range(num_before_skip)])
+        self.lin = nn.Linear(hidden_channels, hidden_channels)
+        self.layers_after_skip = nn.ModuleList([ResidualLayer(hidden_channels) for _ in range(num_after_skip)])
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        names = ["lin_rbf1", "lin_rbf2", "lin_sbf1", "lin_sbf2"] + (["lin_t1", "lin_t2"] if self.torsion else [])
+        for n in names:
+            glorot_orthogonal(getattr(self, n).weight, scale=2.0)
+        for n in ("lin_kj", "lin_ji"):
+            glorot_orthogonal(getattr(self, n).weight, scale=2.0)
+            getattr(self, n).bias.data.fill_(0)
+        glorot_orthogonal(self.lin_down.weight, scale=2.0)
+        glorot_orthogonal(self.lin_up.weight, scale=2.0)
+        for layer in self.layers_before_skip:
+            layer.reset_parameters()
+        glorot_orthogonal(self.lin.weight, scale=2.0)
+        self.lin.bias.data.fill_(0)
+        for layer in self.layers_after_skip:
+            layer.reset_parameters()
+        glorot_orthogonal(self.lin_rbf.weight, scale=2.0)
+
+
+class update_v(nn.Module):
+    """reference spherenet.py:185-216 / dimenetpp.py:164-195."""
+
+    def __init__(self, hidden_channels, out_emb_channels, out_channels, num_output_layers, output_init):
+        super().__init__()
+        self.output_init = output_init
+        self.lin_up = nn.Linear(hidden_channels, out_emb_channels, bias=True)
+        self.lins = nn.ModuleList([nn.Linear(out_emb_channels, out_emb_channels) for _ in range(num_output_layers)])
+        self.lin = nn.Linear(out_emb_channels, out_channels, bias=False)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        glorot_orthogonal(self.lin_up.weight, scale=2.0)
+        for lin in self.lins:
+            glorot_orthogonal(lin.weight, scale=2.0)
+            lin.bias.data.fill_(0)
+        if self.output_init == 'zeros':
+            self.lin.weight.data.fill_(0)
+        if self.output_init == 'GlorotOrthogonal':
+            glorot_orthogonal(self.lin.weight, scale=2.0)
+
+
+class update_u(nn.Module):
+    """reference spherenet.py:219-225 (parameter-free); folded into the graph readout kernel."""
+
+
+class _DimeNetFamily(nn.Module):
+    _torsion = False
+
+    def _build(self, energy_and_force, cutoff, num_layers, hidden_channels, out_channels, int_emb_size,
+               be_dist, be_angle, be_torsion, out_emb_channels, num_spherical, num_radial,
+               envelope_exponent, num_before_skip, num_after_skip, num_output_layers, act, output_init):
+        given = dict(hidden_channels=hidden_channels, int_emb_size=int_emb_size,
+                     out_emb_channels=out_emb_channels, num_radial=num_radial,
+                     num_before_skip=num_before_skip, num_after_skip=num_after_skip)
+        bad = {k: v for k, v in given.items() if _SUPPORTED[k] != v}
+        if bad or not (be_dist == be_angle == 8 and (be_torsion == 8 or not self._torsion)):
+            raise NotImplementedError(
+                f"{type(self).__name__}: the sm_100a kernels of this round are compiled for "
+                f"{_SUPPORTED} and basis_emb_size 8; got {bad or (be_dist, be_angle, be_torsion)}")
+        if ("dimenet", num_spherical, num_radial) not in ops.BASIS_IDS:
+            raise NotImplementedError(
+                f"no generated basis for num_spherical={num_spherical}, num_radial={num_radial}; "
+                f"available: {sorted(k[1:] for k in ops.BASIS_IDS if k[0] == 'dimenet')} "
+                "(add the pair to dig_b200/codegen.py:CONFIGS and rebuild)")
+        if act is not swish and getattr(act, "__name__", "") != "swish":
+            raise NotImplementedError("only the default swish activation is fused")
+        if num_output_layers > 8:
+            raise NotImplementedError("num_output_layers > 8")
+        self.cutoff = cutoff
+        self.energy_and_force = energy_and_force
+        self.num_layers = num_layers
+        self.hidden_channels, self.int_emb_size, self.out_channels = hidden_channels, int_emb_size, out_channels
+        self.num_spherical, self.num_radial, self.envelope_exponent = num_spherical, num_radial, envelope_exponent
+        self._basis_id = ops.BASIS_IDS[("dimenet", num_spherical, num_radial)]
+
+        self.init_e = init(num_radial, hidden_channels)
+        self.init_v = update_v(hidden_channels, out_emb_channels, out_channels, num_output_layers, output_init)
+        self.init_u = update_u()
+        self.emb = emb(num_spherical, num_radial, cutoff, envelope_exponent)
+        self.update_vs = nn.ModuleList([
+            update_v(hidden_channels, out_emb_channels, out_channels, num_output_layers, output_init)
+            for _ in range(num_layers)])
+        self.update_es = nn.ModuleList([
+            update_e(hidden_channels, int_emb_size, be_dist, be_angle, be_torsion, num_spherical, num_radial,
+                     num_before_skip, num_after_skip, self._torsion) for _ in range(num_layers)])
+        self.update_us = nn.ModuleList([update_u() for _ in range(num_layers)])
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        self.init_e.reset_parameters()
+        self.init_v.reset_parameters()
+        self.emb.reset_parameters()
+        for m in self.update_es:
+            m.reset_parameters()
+        for m in self.update_vs:
+            m.reset_parameters()
+
+    # ------------------------------------------------------------------ forward
+    def _projection_rows(self, first, count):
+        """Rows [32, C] of lin_sbf1 (and lin_t1) for layers first..first+count-1, zero padded."""
+        def rows(name):
+            ws = [getattr(self.update_es[l], name).weight.detach() for l in range(first, first + count)]
+            w = torch.cat(ws, 0)
+            if w.size(0) < 32:
+                w = torch.cat([w, w.new_zeros(32 - w.size(0), w.size(1))], 0)
+            return w.contiguous()
+        return rows("lin_sbf1"), (rows("lin_t1") if self._torsion else None)
+
+    def forward(self, batch_data):
+        z, pos, batch = batch_data.z, batch_data.pos, batch_data.batch
+        require_cuda(pos, type(self).__name__ + ".forward")
+        if self.energy_and_force:
+            # Forces need d(energy)/d(pos), i.e. the backward kernels: not built yet.
+            raise NotImplementedError(
+                "energy_and_force=True needs the backward kernels, which are not implemented in this "
+                "round (forward inference only)")
+        ns, nr = self.num_spherical, self.num_radial
+        g = ops.build_graph(pos, batch, self.cutoff, num_graphs=getattr(batch_data, "num_graphs", None))
+        ops.triplet_geometry(g, pos, use_torsion=self._torsion, want_idx=False)
+        rbf0, bess = ops.edge_basis(g.dist, self.cutoff, self.envelope_exponent, self.emb.dist_emb.freq,
+                                    self._basis_id, envelope_on_bessel=not self._torsion, num_radial=nr,
+                                    n_bessel=ns * nr)
+        L = self.num_layers
+        proj = []
+        for first in range(0, L, 4):
+            w_s, w_t = self._projection_rows(first, min(4, L - first))
+            proj.append(ops.triplet_basis_project(g, bess, self._basis_id, w_s, w_t))
+
+        e1, v_in = ops.sphere_init_e(z, g, rbf0, ops.pack_init_e(self.init_e), self.hidden_channels)
+        v_all = torch.empty(L + 1, g.n_nodes, self.out_channels, dtype=torch.float32, device=pos.device)
+        ops.sphere_update_v(v_in, ops.pack_update_v(self.init_v), self.out_channels, v_all[0])
+        for l in range(L):
+            sbf_p, t_p = proj[l // 4]
+            e1, v_in = ops.sphere_update_e(e1, g, rbf0, sbf_p, t_p, 8 * (l % 4),
+                                           ops.pack_update_e(self.update_es[l], self._torsion),
+                                           self.hidden_channels, self.int_emb_size)
+            ops.sphere_update_v(v_in, ops.pack_update_v(self.update_vs[l]), self.out_channels, v_all[l + 1])
+        return ops.graph_readout(v_all, g.graph_ptr, g.n_graphs, g.n_nodes)
+
+
+class SphereNet(_DimeNetFamily):
+    r"""Drop-in for dig.threedgraph.method.SphereNet (reference spherenet.py:228-320).
+
+    Same constructor arguments and defaults.  Restrictions of this round (raise at construction):
+    `use_extra_node_feature=True`, `use_node_features=False`, non-swish `act`, and channel sizes other
+    than the class defaults; `energy_and_force=True` raises at forward (no backward kernels yet)."""
+    _torsion = True
+
+    def __init__(self, energy_and_force=False, cutoff=5.0, num_layers=4, hidden_channels=128, out_channels=1,
+                 int_emb_size=64, basis_emb_size_dist=8, basis_emb_size_angle=8, basis_emb_size_torsion=8,
+                 out_emb_channels=256, num_spherical=7, num_radial=6, envelope_exponent=5, num_before_skip=1,
+                 num_after_skip=2, num_output_layers=3, act=swish, output_init='GlorotOrthogonal',
+                 use_node_features=True, use_extra_node_feature=False, extra_node_feature_dim=1):
+        super().__init__()
+        if use_extra_node_feature or not use_node_features:
+            raise NotImplementedError("use_extra_node_feature / use_node_features=False are not fused yet")
+        self.use_extra_node_feature = use_extra_node_feature
+        self._build(energy_and_force, cutoff, num_layers, hidden_channels, out_channels, int_emb_size,
+                    basis_emb_size_dist, basis_emb_size_angle, basis_emb_size_torsion, out_emb_channels,
+                    num_spherical, num_radial, envelope_exponent, num_before_skip, num_after_skip,
+                    num_output_layers, act, output_init)
+
+
+class DimeNetPP(_DimeNetFamily):
+    r"""Drop-in for dig.threedgraph.method.DimeNetPP (reference dimenetpp.py:207-293)."""
+    _torsion = False
+
+    def __init__(self, energy_and_force=False, cutoff=5.0, num_layers=4, hidden_channels=128, out_channels=1,
+                 int_emb_size=64, basis_emb_size=8, out_emb_channels=256, num_spherical=7, num_radial=6,
+                 envelope_exponent=5, num_before_skip=1, num_after_skip=2, num_output_layers=3, act=swish,
+                 output_init='GlorotOrthogonal'):
+        super().__init__()
+        self._build(energy_and_force, cutoff, num_layers, hidden_channels, out_channels, int_emb_size,
+                    basis_emb_size, basis_emb_size, basis_emb_size, out_emb_channels, num_spherical,
+                    num_radial, envelope_exponent, num_before_skip, num_after_skip, num_output_layers, act,
+                    output_init)

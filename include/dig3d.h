@@ -1,0 +1,170 @@
+/* dig3d.h -- C ABI of libdig3d.so, the sm_100a implementation of DIG's 3D-graph
+ * message-passing hot path (dig.threedgraph.method.{SchNet,SphereNet,DimeNetPP,ComENet}).
+ *
+ * The reference has NO native/FFI boundary for this path: every device op is a
+ * third-party wheel or ATen kernel launched from Python.  Each entry point below therefore cites
+ * the reference Python call site(s) whose device work it replaces.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers + sizes, no torch types; all pointers are DEVICE pointers unless named *_host;
+ *   - caller owns every buffer (no allocation, no synchronisation, no global state inside);
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - returns 0 on success, a negative DIG3D_E* code otherwise; dig3d_last_error() returns a
+ *     thread-local message for the last failing call;
+ *   - fp32 everywhere; indices are int32 inside kernels, int64 at the reference-facing API
+ *     (edge_index / idx_kj / idx_ji outputs).
+ */
+#ifndef DIG3D_H
+#define DIG3D_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIG3D_OK 0
+#define DIG3D_EINVAL (-1)
+#define DIG3D_ECUDA (-2)
+#define DIG3D_EUNSUPPORTED (-3)
+
+const char* dig3d_last_error(void);
+int dig3d_abi_version(void);
+
+/* ------------------------------------------------------------------ graph construction
+ * radius_graph(pos, r, batch)            schnet.py:156 dimenetpp.py:277 spherenet.py:304 comenet.py:294
+ * (torch_cluster 1.6.0 CUDA semantics: per-graph brute force, strict d2 < r*r, first
+ *  max_num_neighbors+1 hits in ascending source index incl. self, self removed afterwards)
+ * + SparseTensor / repeat_interleave triplet enumeration   utils/geometric_computing.py:27-41
+ */
+
+/* ptr[g] = first node of graph g, ptr[n_graphs] = n_nodes (batch is sorted ascending). */
+int dig3d_graph_ptr(const int64_t* batch, int64_t n_nodes, int64_t n_graphs, int32_t* ptr, void* stream);
+
+/* nbr[n*cap + s] = s-th in-neighbour (ascending) of node n, deg[n] = count (self excluded);
+ * cap = max_num_neighbors + 1. */
+int dig3d_radius_neighbors(const float* pos, const int64_t* batch, const int32_t* ptr, int64_t n_nodes,
+                           double cutoff, int32_t cap, int32_t* nbr, int32_t* deg, void* stream);
+
+/* tcnt[i] = number of triplets (k->j->i, k != i) over the in-edges of node i. */
+int dig3d_triplet_count(const int32_t* nbr, const int32_t* deg, int64_t n_nodes, int32_t cap,
+                        int32_t* tcnt, void* stream);
+
+/* Exclusive scans: row_ptr[0..n] of deg, node_trip_ptr[0..n] of tcnt; totals[0]=E, totals[1]=T. */
+int dig3d_scan_counts(const int32_t* deg, const int32_t* tcnt, int64_t n_nodes, int32_t* row_ptr,
+                      int32_t* node_trip_ptr, int32_t* totals, void* stream);
+
+/* Per-edge arrays, edges sorted by (target i, source j):
+ *   edge_index[2,E] int64 (row 0 = source j, row 1 = target i), src/dst int32, dist[E],
+ *   vec[E,3] = pos[j]-pos[i] (nullable), trip_ptr[E+1] (first triplet of each edge).
+ *   dist = sqrt(sum((pos_i-pos_j)^2)) with ATen-CUDA rounding (geometric_computing.py:25). */
+int dig3d_edge_fill(const float* pos, const int32_t* nbr, const int32_t* deg, const int32_t* row_ptr,
+                    const int32_t* node_trip_ptr, int64_t n_nodes, int32_t cap, int64_t n_edges,
+                    int64_t* edge_index, int32_t* src, int32_t* dst, float* dist, float* vec,
+                    int32_t* trip_ptr, void* stream);
+
+/* ------------------------------------------------------------------ geometry
+ * xyz_to_dat(pos, edge_index, N, use_torsion)     utils/geometric_computing.py:43-75
+ * angle[T], torsion[T] (nullable), idx_kj/idx_ji int32 (nullable) and int64 (nullable).
+ * Triplets ordered by (edge ji ascending, k ascending); torsion = min over k_n != i of the
+ * dihedral in (0, 2pi], the k_n == k self candidate included, cross products in ATen's
+ * fma(a,b,-rn(c*d)) form. */
+int dig3d_triplet_geometry(const float* pos, const int32_t* src, const int32_t* dst, const int32_t* row_ptr,
+                           const int32_t* trip_ptr, int64_t n_edges, int32_t use_torsion, float* angle,
+                           float* torsion, int32_t* idx_kj, int32_t* idx_ji, int64_t* idx_kj64,
+                           int64_t* idx_ji64, void* stream);
+
+/* ------------------------------------------------------------------ basis
+ * dist_emb / angle_emb / torsion_emb      spherenet/features.py:167-263, dimenetpp/features.py:149-220
+ * basis_id: 0 = dimenet flavour ns=7 nr=6, 1 = dimenet ns=3 nr=6, 2 = gemnet ns=2 nr=3 (ComENet).
+ */
+/* rbf0[E,nr] = env(d/c) * sin(freq*d/c); bess[E,ns*nr] = j~_ln(d/c) (times env(d/c) if envelope_on_bessel,
+ * the DimeNet++ angle_emb variant, dimenetpp/features.py:214). */
+int dig3d_edge_basis(const float* dist, int64_t n_edges, double cutoff, int32_t envelope_exponent,
+                     const float* freq, int32_t basis_id, int32_t envelope_on_bessel, float* rbf0,
+                     float* bess, void* stream);
+
+/* Materialise sbf[T, ns*nr] and (nullable) tbf[T, ns*ns*nr] exactly as the reference's angle_emb /
+ * torsion_emb do (test / API-parity path; the fused model path never materialises them). */
+int dig3d_triplet_basis(const float* bess, const float* angle, const float* torsion, const int32_t* idx_kj,
+                        int64_t n_triplets, int32_t basis_id, float* sbf, float* tbf, void* stream);
+
+/* Fused basis evaluation + first basis projection for ALL layers:
+ *   sbf_p[T, L*B] = lin_sbf1_l(sbf),  t_p[T, L*B] = lin_t1_l(tbf) (nullable => DimeNet++)
+ * w_sbf1: [L][B][ns*nr], w_t1: [L][B][ns*ns*nr] (PyTorch [out,in] per layer, layers concatenated).
+ * Requires L*B == 32.                                     spherenet.py:163,167  dimenetpp.py:146 */
+int dig3d_triplet_basis_project(const float* bess, const float* angle, const float* torsion,
+                                const int32_t* src, const int32_t* dst, const int32_t* row_ptr,
+                                const int32_t* trip_ptr, const int32_t* graph_ptr, const int64_t* batch,
+                                int64_t n_edges, int64_t n_triplets, int32_t basis_id, int32_t n_layers,
+                                int32_t basis_emb, const float* w_sbf1, const float* w_t1, float* sbf_p,
+                                float* t_p, void* stream);
+
+/* ------------------------------------------------------------------ segmented reductions
+ * scatter(src, index, dim=0, dim_size, reduce='sum') with a SORTED index given as CSR pointers
+ * (spherenet.py:211,224 schnet.py:55,81 comenet.py:398): out[s, :] = sum_{r in [ptr[s], ptr[s+1])} x[r, :].
+ * No atomics, deterministic. */
+int dig3d_segment_sum(const float* x, const int32_t* ptr, int64_t n_segments, int64_t width, float* out,
+                      void* stream);
+
+/* ------------------------------------------------------------------ SphereNet / DimeNet++ blocks
+ * All weights are PyTorch nn.Linear layout [out, in] row-major fp32; null bias pointer = no bias.
+ * H = hidden_channels (128), I = int_emb_size (64), B = basis_emb (8), nr = num_radial (6),
+ * O = out_emb_channels (256).  Only these sizes are compiled in round 1. */
+typedef struct {
+  const float* emb;        /* [95, H]   init_e.emb.weight */
+  const float* w_rbf0;     /* [H, nr]   init_e.lin_rbf_0.weight */
+  const float* b_rbf0;     /* [H] */
+  const float* w_lin;      /* [H, 3H]   init_e.lin.weight */
+  const float* b_lin;      /* [H] */
+  const float* w_rbf1;     /* [H, nr]   init_e.lin_rbf_1.weight */
+} dig3d_init_e_weights;
+
+typedef struct {
+  const float *w_rbf1, *w_rbf2;   /* [B, nr], [H, B] */
+  const float *w_sbf2, *w_t2;     /* [I, B], [I, B] (w_t2 null => DimeNet++) */
+  const float *w_rbf;             /* [H, nr] */
+  const float *w_kj, *b_kj, *w_ji, *b_ji;   /* [H, H], [H] */
+  const float *w_down, *w_up;     /* [I, H], [H, I] */
+  const float *w_res[6], *b_res[6]; /* before_skip.0.{lin1,lin2}, after_skip.{0,1}.{lin1,lin2}: [H,H],[H] */
+  const float *w_lin, *b_lin;     /* [H, H], [H] */
+} dig3d_update_e_weights;
+
+typedef struct {
+  const float *w_up, *b_up;       /* [O, H], [O] */
+  const float *w_lins[8], *b_lins[8]; /* [O, O], [O]; first n_lins used */
+  const float *w_out;             /* [out_channels, O] */
+  int32_t n_lins;                 /* num_output_layers */
+} dig3d_update_v_weights;
+
+/* init.forward (spherenet.py:79-91, dimenetpp.py:71-78) fused with the edge->node scatter of
+ * update_v (spherenet.py:211): writes e1[E,H] and ACCUMULATES e2 into v_in[N,H] (caller zeroes). */
+int dig3d_sphere_init_e(const int64_t* z, const int32_t* src, const int32_t* dst, const float* rbf0,
+                        int64_t n_edges, const dig3d_init_e_weights* w, float* e1, float* v_in,
+                        void* stream);
+
+/* update_e.forward part A (spherenet.py:154-161): x_ji[E,H], x_kj_down[E,I]. */
+int dig3d_sphere_update_e_a(const float* e1, const float* rbf0, int64_t n_edges,
+                            const dig3d_update_e_weights* w, float* x_ji, float* x_down, void* stream);
+
+/* update_e.forward part B (spherenet.py:163-180) fused with update_v's scatter (spherenet.py:211):
+ * triplet gather * basis, segmented sum over idx_ji, lin_up, residual stack; writes e1_out[E,H]
+ * and ACCUMULATES e2 into v_in[N,H].  sbf_p/t_p are the layer's [T, ld_p] slices (col offset
+ * applied by the caller), t_p null => DimeNet++. */
+int dig3d_sphere_update_e_b(const float* e1_in, const float* x_ji, const float* x_down, const float* rbf0,
+                            const float* sbf_p, const float* t_p, int32_t ld_p, const int32_t* src,
+                            const int32_t* dst, const int32_t* row_ptr, const int32_t* trip_ptr,
+                            int64_t n_edges, const dig3d_update_e_weights* w, float* e1_out, float* v_in,
+                            void* stream);
+
+/* update_v.forward after the scatter (spherenet.py:212-215): v_out[N, out_channels]. */
+int dig3d_sphere_update_v(const float* v_in, int64_t n_nodes, int32_t out_channels,
+                          const dig3d_update_v_weights* w, float* v_out, void* stream);
+
+/* update_u over all blocks (spherenet.py:223-225,313-318): u[g, c] = sum_l sum_{n in g} v[l][n][c],
+ * v: [n_blocks, N, C] contiguous. */
+int dig3d_graph_readout(const float* v, const int32_t* graph_ptr, int64_t n_graphs, int64_t n_nodes,
+                        int32_t n_blocks, int32_t channels, float* u, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
