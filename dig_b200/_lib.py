@@ -81,9 +81,40 @@ def load():
     return lib
 
 
+# Launch accounting (bench.py's `gpu_launches`) and optional per-kernel CUDA-event timing
+# (bench.py's roofline pass).  Every entry point except scan/ptr helpers launches exactly one kernel.
+launch_count = 0
+_timing = None            # None, or dict name -> list of (start_event, stop_event)
+
+
+def start_timing():
+    global _timing
+    _timing = {}
+
+
+def stop_timing():
+    """Returns {entry point: [ms, ...]} for the calls made since start_timing() (synchronises)."""
+    global _timing
+    import torch
+    torch.cuda.synchronize()
+    out = {k: [a.elapsed_time(b) for a, b in v] for k, v in (_timing or {}).items()}
+    _timing = None
+    return out
+
+
 def call(name, *args):
+    global launch_count
     lib = load()
-    rc = getattr(lib, name)(*args)
+    if _timing is not None:
+        import torch
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = getattr(lib, name)(*args)
+        b.record()
+        _timing.setdefault(name, []).append((a, b))
+    else:
+        rc = getattr(lib, name)(*args)
+    launch_count += 1
     if rc != 0:
         msg = lib.dig3d_last_error()
         raise Dig3dError(f"{name} failed (rc={rc}): {msg.decode() if msg else ''}")

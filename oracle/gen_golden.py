@@ -154,16 +154,30 @@ def notebook_example(utils):
     print("notebook:", idx_kj.tolist(), idx_ji.tolist(), torsion.tolist())
 
 
+def state_shapes(method):
+    """Key names + shapes of every fixture model's state_dict (SURVEY.md Appendix A contract), so
+    tests can rebuild formula weights and check the drop-in classes without the reference."""
+    out = {}
+    for name, (mn, kw, _, _) in CASES.items():
+        model = getattr(method, mn)(**kw)
+        out[mn + json.dumps(kw, sort_keys=True)] = {k: list(v.shape) for k, v in model.state_dict().items()}
+    with open(os.path.join(GOLD, "state_shapes.json"), "w") as fh:
+        json.dump(out, fh)
+    print("state shapes:", {k: len(v) for k, v in out.items()})
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     method = load_reference()
     utils = load_reference_utils()
-    which = sys.argv[1:] or list(CASES) + ["basis", "notebook"]
+    which = sys.argv[1:] or list(CASES) + ["basis", "notebook", "shapes"]
     for name in which:
         if name == "basis":
             basis_sources(method)
         elif name == "notebook":
             notebook_example(utils)
+        elif name == "shapes":
+            state_shapes(method)
         else:
             run_case(method, utils, name)
 

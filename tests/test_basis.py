@@ -1,0 +1,54 @@
+"""CPU tests for the product-side basis generator and the device-code generator."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN
+from dig_b200 import basis, codegen
+
+with open(os.path.join(GOLDEN, "basis_formulas.json")) as _fh:
+    GOLD = json.load(_fh)
+
+
+@pytest.mark.parametrize("tag,flavor,ns,nr", [("spherenet_7_6", "dimenet", 7, 6),
+                                             ("spherenet_3_6", "dimenet", 3, 6),
+                                             ("comenet_2_3", "gemnet", 2, 3)])
+def test_generator_reproduces_reference_formulas(tag, flavor, ns, nr):
+    """dig_b200/basis.py must emit exactly the strings the reference's sympy code lambdifies."""
+    mine = basis.basis_sources(flavor, ns, nr)
+    ref = GOLD[tag]
+    assert mine["bessel"] == ref["bessel"]
+    for key in ("yl0", "ylm"):
+        # the l = 0 entry is a constant the reference stores through a float32 tensor
+        assert np.float32(float(mine[key][0])) == np.float32(float(ref[key][0]))
+        assert mine[key][1:] == ref[key][1:]
+
+
+def test_dimenetpp_uses_the_same_forms_as_spherenet():
+    assert GOLD["dimenetpp_7_6"]["bessel"] == GOLD["spherenet_7_6"]["bessel"]
+    assert GOLD["dimenetpp_7_6"]["yl0"] == GOLD["spherenet_7_6"]["yl0"]
+
+
+def test_committed_headers_match_generator():
+    csrc = os.path.join(os.path.dirname(basis.__file__), "csrc", "generated")
+    for tag, (flavor, ns, nr) in codegen.CONFIGS.items():
+        want = codegen.emit_header(tag, flavor, ns, nr, basis.basis_sources(flavor, ns, nr))
+        with open(os.path.join(csrc, f"basis_{tag}.cuh")) as fh:
+            assert fh.read() == want, f"stale generated header for {tag}: run python -m dig_b200.codegen --force"
+
+
+def test_codegen_typing_rules():
+    src = codegen.emit_function("f", ["x"], ["2*x/5 + x**2 - 1/x + x**7 + (3/2)*x**0.5"])
+    assert "__fmul_rn(2.0f, x)" in src                     # python scalar rounded to fp32, one op per node
+    assert "0.200000003f" in src                           # t / c -> t * (1.0f / c)  (ATen CUDA)
+    assert "__fmul_rn(x, x)" in src                        # ** 2 -> x*x
+    assert "__fdiv_rn(1.0f, x)" in src                     # c / t -> reciprocal(t) * c
+    assert "powf(x, 7.0f)" in src and "sqrtf(x)" in src
+    assert "1.5f" in src                                   # (3/2) folded in python double first
+    assert "fmaf" not in src                               # never contracted
+
+
+def test_envelope_coefficients():
+    assert basis.envelope_coefficients(5) == (6, -28.0, 48, -21.0)
