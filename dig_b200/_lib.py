@@ -24,6 +24,10 @@ class UpdateEWeights(Structure):
                 + [("w_res", P * 6), ("b_res", P * 6), ("w_lin", P), ("b_lin", P)])
 
 
+class SchnetBlockWeights(Structure):
+    _fields_ = [(n, P) for n in ("w_lin", "w_mlp0", "b_mlp0", "w_mlp2", "b_mlp2", "w_v1", "b_v1", "w_v2", "b_v2")]
+
+
 class UpdateVWeights(Structure):
     _fields_ = [("w_up", P), ("b_up", P), ("w_lins", P * 8), ("b_lins", P * 8), ("w_out", P),
                 ("n_lins", c_int32)]
@@ -50,6 +54,9 @@ SIGNATURES = {
                                 POINTER(UpdateEWeights), P, P, P],
     "dig3d_sphere_update_v": [P, c_int64, c_int32, POINTER(UpdateVWeights), P, P],
     "dig3d_graph_readout": [P, P, c_int64, c_int64, c_int32, c_int32, P, P],
+    "dig3d_schnet_block": [P, c_int64, P, P, P, c_int64, P, c_int32, c_double, c_double, c_int32, c_int32,
+                           POINTER(SchnetBlockWeights), P, P, P, P],
+    "dig3d_schnet_readout": [P, c_int64, c_int32, P, P, P, P, c_int32, P, P],
 }
 _RESTYPES = {"dig3d_last_error": c_char_p}
 

@@ -118,8 +118,21 @@ __global__ void triplet_basis_kernel(const float* __restrict__ bess, const float
 //   sbf_p[t][q] = sum_l' Y_l'0(angle_t) * Rs[l']
 // The harmonics of up to 32 triplets are evaluated with lane == triplet, parked in shared
 // memory, then consumed with lane == (l, m).
-constexpr int PRJ_WARPS = 4;
+constexpr int PRJ_WARPS = 8;
+constexpr int PRJ_LD = 33;  // lane stride of the transposed weight tables (conflict-free both ways)
 
+template <class BS, bool TORSION>
+struct PrjSmem {
+  static constexpr int NYT = TORSION ? BS::NY : 1;
+  float wt[TORSION ? BS::NY * BS::NR * PRJ_LD : 1];   // [c][lane]: w_t1[lane][c]
+  float ws[BS::NB * PRJ_LD];                          // [c][lane]: w_sbf1[lane][c]
+  float bess[PRJ_WARPS][BS::NB];
+  float y[PRJ_WARPS][32][NYT + BS::NS + 1];
+  int32_t trip[PRJ_WARPS][32];
+};
+
+// Persistent CTAs (grid ~ 2 per SM): the first-projection weights of all layers are staged ONCE per
+// CTA into shared memory, transposed so that lane q reads row q without bank conflicts.
 template <class BS, bool TORSION>
 __global__ void __launch_bounds__(PRJ_WARPS * 32)
 triplet_basis_project_kernel(const float* __restrict__ bess, const float* __restrict__ angle,
@@ -131,91 +144,93 @@ triplet_basis_project_kernel(const float* __restrict__ bess, const float* __rest
                              float* __restrict__ sbf_p, float* __restrict__ t_p) {
   constexpr int NS = BS::NS, NR = BS::NR, NB = BS::NB, NY = BS::NY;
   constexpr int NYT = TORSION ? NY : 1;
-  __shared__ float s_bess[PRJ_WARPS][NB];
-  __shared__ float s_y[PRJ_WARPS][32][NYT + NS + 1];
-  __shared__ int32_t s_trip[PRJ_WARPS][32];
+  extern __shared__ __align__(16) unsigned char prj_smem_raw[];
+  PrjSmem<BS, TORSION>& sm = *reinterpret_cast<PrjSmem<BS, TORSION>*>(prj_smem_raw);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int kj = blockIdx.x * PRJ_WARPS + w;
-  if (kj >= n_edges) return;
-  const int k = src[kj], j = dst[kj];
-  for (int c = lane; c < NB; c += 32) s_bess[w][c] = __ldg(bess + (size_t)kj * NB + c);
-  __syncwarp();
-  // per-edge radial contraction (weights streamed from L2; rows of this lane are contiguous)
-  float R[NYT], Rs[NS];
-  if (TORSION) {
-    const float* wt = w_t1 + (size_t)lane * (NY * NR);
+  if (TORSION)
+    for (int id = threadIdx.x; id < 32 * NY * NR; id += PRJ_WARPS * 32)
+      sm.wt[(id % (NY * NR)) * PRJ_LD + id / (NY * NR)] = __ldg(w_t1 + id);
+  for (int id = threadIdx.x; id < 32 * NB; id += PRJ_WARPS * 32)
+    sm.ws[(id % NB) * PRJ_LD + id / NB] = __ldg(w_sbf1 + id);
+  __syncthreads();
+  for (int kj = blockIdx.x * PRJ_WARPS + w; kj < n_edges; kj += gridDim.x * PRJ_WARPS) {
+    const int k = src[kj], j = dst[kj];
+    __syncwarp();
+    for (int c = lane; c < NB; c += 32) sm.bess[w][c] = __ldg(bess + (size_t)kj * NB + c);
+    __syncwarp();
+    // per-edge radial contraction
+    float R[NYT], Rs[NS];
+    if (TORSION) {
 #pragma unroll
-    for (int ab = 0; ab < NY; ++ab) {
-      float acc = 0.f;
+      for (int ab = 0; ab < NY; ++ab) {
+        float acc = 0.f;
 #pragma unroll
-      for (int r = 0; r < NR; ++r) acc = fmaf(s_bess[w][(ab % NS) * NR + r], __ldg(wt + ab * NR + r), acc);
-      R[ab] = acc;
+        for (int r = 0; r < NR; ++r)
+          acc = fmaf(sm.bess[w][(ab % NS) * NR + r], sm.wt[(ab * NR + r) * PRJ_LD + lane], acc);
+        R[ab] = acc;
+      }
     }
-  }
-  {
-    const float* ws = w_sbf1 + (size_t)lane * NB;
 #pragma unroll
     for (int l = 0; l < NS; ++l) {
       float acc = 0.f;
 #pragma unroll
-      for (int r = 0; r < NR; ++r) acc = fmaf(s_bess[w][l * NR + r], __ldg(ws + l * NR + r), acc);
+      for (int r = 0; r < NR; ++r) acc = fmaf(sm.bess[w][l * NR + r], sm.ws[(l * NR + r) * PRJ_LD + lane], acc);
       Rs[l] = acc;
     }
-  }
-  // enumerate the out-edges e = (j -> i), i != k, of j: candidates are the nodes of j's graph
-  const int jbase = row_ptr[j], dj = row_ptr[j + 1] - jbase;
-  const int rank_k = kj - jbase;  // position of k among j's in-neighbours
-  const int g = (int)batch[j];
-  const int lo = graph_ptr[g], hi = graph_ptr[g + 1];
-  for (int c0 = lo; c0 < hi; c0 += 32) {
-    const int i = c0 + lane;
-    int t = -1;
-    if (i < hi && i != k && i != j) {
-      const int ib = row_ptr[i], di = row_ptr[i + 1] - ib;
-      // binary search j among i's in-neighbour sources (ascending)
-      int a = 0, b = di;
-      while (a < b) { int mid = (a + b) >> 1; if (src[ib + mid] < j) a = mid + 1; else b = mid; }
-      if (a < di && src[ib + a] == j) {
-        const int e = ib + a;
-        // slot of k in e's triplet list: rank_k minus one if i precedes k in j's in-list
-        int a2 = 0, b2 = dj;
-        while (a2 < b2) { int mid = (a2 + b2) >> 1; if (src[jbase + mid] < i) a2 = mid + 1; else b2 = mid; }
-        const bool i_in = (a2 < dj && src[jbase + a2] == i);
-        t = trip_ptr[e] + rank_k - ((i_in && a2 < rank_k) ? 1 : 0);
+    // enumerate the out-edges e = (j -> i), i != k, of j: candidates are the nodes of j's graph
+    const int jbase = row_ptr[j], dj = row_ptr[j + 1] - jbase;
+    const int rank_k = kj - jbase;  // position of k among j's in-neighbours
+    const int g = (int)batch[j];
+    const int lo = graph_ptr[g], hi = graph_ptr[g + 1];
+    for (int c0 = lo; c0 < hi; c0 += 32) {
+      const int i = c0 + lane;
+      int t = -1;
+      if (i < hi && i != k && i != j) {
+        const int ib = row_ptr[i], di = row_ptr[i + 1] - ib;
+        int a = 0, b = di;  // binary search j among i's in-neighbour sources (ascending)
+        while (a < b) { int mid = (a + b) >> 1; if (src[ib + mid] < j) a = mid + 1; else b = mid; }
+        if (a < di && src[ib + a] == j) {
+          const int e = ib + a;
+          // slot of k in e's triplet list: rank_k minus one if i precedes k in j's in-list
+          int a2 = 0, b2 = dj;
+          while (a2 < b2) { int mid = (a2 + b2) >> 1; if (src[jbase + mid] < i) a2 = mid + 1; else b2 = mid; }
+          const bool i_in = (a2 < dj && src[jbase + a2] == i);
+          t = trip_ptr[e] + rank_k - ((i_in && a2 < rank_k) ? 1 : 0);
+        }
       }
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, t >= 0);
-    if (t >= 0) {
-      const int slot = __popc(m & ((1u << lane) - 1));
-      s_trip[w][slot] = t;
-      const float th = angle[t];
-      float y0[NS];
-      BS::yl0(th, y0);
+      const unsigned m = __ballot_sync(0xffffffffu, t >= 0);
+      if (t >= 0) {
+        const int slot = __popc(m & ((1u << lane) - 1));
+        sm.trip[w][slot] = t;
+        const float th = angle[t];
+        float y0[NS];
+        BS::yl0(th, y0);
 #pragma unroll
-      for (int l = 0; l < NS; ++l) s_y[w][slot][NYT + l] = y0[l];
-      if (TORSION) {
-        float y[NY];
-        BS::ylm(th, torsion[t], y);
+        for (int l = 0; l < NS; ++l) sm.y[w][slot][NYT + l] = y0[l];
+        if (TORSION) {
+          float y[NY];
+          BS::ylm(th, torsion[t], y);
 #pragma unroll
-        for (int ab = 0; ab < NY; ++ab) s_y[w][slot][ab] = y[ab];
+          for (int ab = 0; ab < NY; ++ab) sm.y[w][slot][ab] = y[ab];
+        }
       }
-    }
-    __syncwarp();
-    const int cnt = __popc(m);
-    for (int s = 0; s < cnt; ++s) {
-      const int tt = s_trip[w][s];
-      float acc_s = 0.f;
+      __syncwarp();
+      const int cnt = __popc(m);
+      for (int s = 0; s < cnt; ++s) {
+        const int tt = sm.trip[w][s];
+        float acc_s = 0.f;
 #pragma unroll
-      for (int l = 0; l < NS; ++l) acc_s = fmaf(s_y[w][s][NYT + l], Rs[l], acc_s);
-      sbf_p[(size_t)tt * 32 + lane] = acc_s;
-      if (TORSION) {
-        float acc_t = 0.f;
+        for (int l = 0; l < NS; ++l) acc_s = fmaf(sm.y[w][s][NYT + l], Rs[l], acc_s);
+        sbf_p[(size_t)tt * 32 + lane] = acc_s;
+        if (TORSION) {
+          float acc_t = 0.f;
 #pragma unroll
-        for (int ab = 0; ab < NY; ++ab) acc_t = fmaf(s_y[w][s][ab], R[ab], acc_t);
-        t_p[(size_t)tt * 32 + lane] = acc_t;
+          for (int ab = 0; ab < NY; ++ab) acc_t = fmaf(sm.y[w][s][ab], R[ab], acc_t);
+          t_p[(size_t)tt * 32 + lane] = acc_t;
+        }
       }
+      __syncwarp();
     }
-    __syncwarp();
   }
 }
 
@@ -284,21 +299,30 @@ int dig3d_triplet_basis_project(const float* bess, const float* angle, const flo
   DIG3D_REQUIRE(!tors || (torsion && w_t1), "triplet_basis_project: torsion path needs torsion and w_t1");
   if (n_edges == 0 || n_triplets == 0) return DIG3D_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = ceil_div(n_edges, PRJ_WARPS);
-#define DIG3D_PRJ(BS)                                                                                       \
-  if (tors)                                                                                                 \
-    triplet_basis_project_kernel<BS, true><<<grid, PRJ_WARPS * 32, 0, st>>>(                                \
-        bess, angle, torsion, src, dst, row_ptr, trip_ptr, graph_ptr, batch, (int)n_edges, w_sbf1, w_t1,    \
-        sbf_p, t_p);                                                                                        \
-  else                                                                                                      \
-    triplet_basis_project_kernel<BS, false><<<grid, PRJ_WARPS * 32, 0, st>>>(                               \
-        bess, angle, torsion, src, dst, row_ptr, trip_ptr, graph_ptr, batch, (int)n_edges, w_sbf1, w_t1,    \
-        sbf_p, t_p);
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = (int)((n_edges + PRJ_WARPS - 1) / PRJ_WARPS < 2 * n_sm ? (n_edges + PRJ_WARPS - 1) / PRJ_WARPS
+                                                                          : 2 * n_sm);
+#define DIG3D_PRJ_ONE(BS, TORS)                                                                             \
+  {                                                                                                         \
+    auto kfn = triplet_basis_project_kernel<BS, TORS>;                                                      \
+    const size_t smem = sizeof(PrjSmem<BS, TORS>);                                                          \
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { \
+      set_error("triplet_basis_project: cannot reserve %zu bytes of shared memory", smem);                  \
+      return DIG3D_ECUDA;                                                                                   \
+    }                                                                                                       \
+    kfn<<<grid, PRJ_WARPS * 32, smem, st>>>(bess, angle, torsion, src, dst, row_ptr, trip_ptr, graph_ptr,   \
+                                            batch, (int)n_edges, w_sbf1, w_t1, sbf_p, t_p);                 \
+  }
+#define DIG3D_PRJ(BS) \
+  if (tors) DIG3D_PRJ_ONE(BS, true) else DIG3D_PRJ_ONE(BS, false)
   switch (basis_id) {
     case 0: DIG3D_PRJ(B76); break;
     case 1: DIG3D_PRJ(B36); break;
     default: set_error("triplet_basis_project: unsupported basis_id %d", basis_id); return DIG3D_EUNSUPPORTED;
   }
+#undef DIG3D_PRJ_ONE
 #undef DIG3D_PRJ
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;

@@ -257,3 +257,37 @@ def sphere_update_v(v_in, w, out_channels, v_out):
     if n:
         call("dig3d_sphere_update_v", _p(v_in), n, int(out_channels), ctypes.byref(w), _p(v_out, align=4), _stream())
     return v_out
+
+
+# ----------------------------------------------------------------------------- SchNet
+def pack_schnet_block(ue, uv):
+    w = _lib.SchnetBlockWeights()
+    w.w_lin = _wp(ue.lin.weight, "update_e.lin")
+    g = ue.mlp[0].weight.size(1)
+    w0 = torch.nn.functional.pad(ue.mlp[0].weight.detach(), (0, 64 - g)).contiguous()   # zero-pad G -> 64
+    w.w_mlp0, w.b_mlp0 = _wp(w0, "mlp.0.w"), _wp(ue.mlp[0].bias, "mlp.0.b")
+    w.w_mlp2, w.b_mlp2 = _wp(ue.mlp[2].weight, "mlp.2.w"), _wp(ue.mlp[2].bias, "mlp.2.b")
+    w.w_v1, w.b_v1 = _wp(uv.lin1.weight, "update_v.lin1.w"), _wp(uv.lin1.bias, "update_v.lin1.b")
+    w.w_v2, w.b_v2 = _wp(uv.lin2.weight, "update_v.lin2.w"), _wp(uv.lin2.bias, "update_v.lin2.b")
+    return w, w0          # keep the padded copy alive until the kernel has been enqueued
+
+
+def schnet_block(v, g, offset, coeff, cutoff, hidden, filters, w):
+    n = v.size(0)
+    dev = v.device
+    vlin = torch.empty(n, filters, dtype=torch.float32, device=dev)
+    agg = torch.zeros(n, filters, dtype=torch.float32, device=dev)
+    v_out = torch.empty(n, hidden, dtype=torch.float32, device=dev)
+    call("dig3d_schnet_block", _p(v, torch.float32, "v", 16), n, _p(g.dist), _p(g.src), _p(g.dst), g.n_edges,
+         _p(offset, torch.float32, "offset"), offset.numel(), float(coeff), float(cutoff), int(hidden),
+         int(filters), ctypes.byref(w), _p(vlin), _p(agg), _p(v_out), _stream())
+    return v_out
+
+
+def schnet_readout(v, lin1, lin2, out_channels):
+    n = v.size(0)
+    node_out = torch.empty(n, out_channels, dtype=torch.float32, device=v.device)
+    call("dig3d_schnet_readout", _p(v, torch.float32), n, v.size(1), _p(lin1.weight.detach(), torch.float32),
+         _p(lin1.bias.detach(), torch.float32), _p(lin2.weight.detach(), torch.float32),
+         _p(lin2.bias.detach(), torch.float32), int(out_channels), _p(node_out), _stream())
+    return node_out

@@ -192,6 +192,13 @@ class _DimeNetFamily(nn.Module):
             m.reset_parameters()
 
     # ------------------------------------------------------------------ forward
+    def _side_stream(self, device):
+        streams = self.__dict__.setdefault("_streams", {})
+        key = (device.type, device.index)
+        if key not in streams:
+            streams[key] = torch.cuda.Stream(device=device)
+        return streams[key]
+
     def _projection_rows(self, first, count):
         """Rows [32, C] of lin_sbf1 (and lin_t1) for layers first..first+count-1, zero padded."""
         def rows(name):
@@ -222,15 +229,30 @@ class _DimeNetFamily(nn.Module):
             w_s, w_t = self._projection_rows(first, min(4, L - first))
             proj.append(ops.triplet_basis_project(g, bess, self._basis_id, w_s, w_t))
 
-        e1, v_in = ops.sphere_init_e(z, g, rbf0, ops.pack_init_e(self.init_e), self.hidden_channels)
+        # The node MLP (update_v) of block l only feeds the readout, so it runs on a side stream and
+        # overlaps with the edge kernels of block l+1 (it fills SMs the 2-CTA/SM edge tiles leave idle).
+        main = torch.cuda.current_stream()
+        side = self._side_stream(pos.device)
         v_all = torch.empty(L + 1, g.n_nodes, self.out_channels, dtype=torch.float32, device=pos.device)
-        ops.sphere_update_v(v_in, ops.pack_update_v(self.init_v), self.out_channels, v_all[0])
+        v_all.record_stream(side)
+
+        def node_mlp(v_in, holder, out):
+            ready = torch.cuda.Event()
+            ready.record(main)
+            side.wait_event(ready)
+            v_in.record_stream(side)
+            with torch.cuda.stream(side):
+                ops.sphere_update_v(v_in, ops.pack_update_v(holder), self.out_channels, out)
+
+        e1, v_in = ops.sphere_init_e(z, g, rbf0, ops.pack_init_e(self.init_e), self.hidden_channels)
+        node_mlp(v_in, self.init_v, v_all[0])
         for l in range(L):
             sbf_p, t_p = proj[l // 4]
             e1, v_in = ops.sphere_update_e(e1, g, rbf0, sbf_p, t_p, 8 * (l % 4),
                                            ops.pack_update_e(self.update_es[l], self._torsion),
                                            self.hidden_channels, self.int_emb_size)
-            ops.sphere_update_v(v_in, ops.pack_update_v(self.update_vs[l]), self.out_channels, v_all[l + 1])
+            node_mlp(v_in, self.update_vs[l], v_all[l + 1])
+        main.wait_stream(side)
         return ops.graph_readout(v_all, g.graph_ptr, g.n_graphs, g.n_nodes)
 
 

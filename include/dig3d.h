@@ -164,6 +164,28 @@ int dig3d_sphere_update_v(const float* v_in, int64_t n_nodes, int32_t out_channe
 int dig3d_graph_readout(const float* v, const int32_t* graph_ptr, int64_t n_graphs, int64_t n_nodes,
                         int32_t n_blocks, int32_t channels, float* u, void* stream);
 
+/* ------------------------------------------------------------------ SchNet
+ * One interaction (update_e + update_v, schnet.py:29-35,53-59) for hidden_channels == num_filters in
+ * {32, 64, 128}:  vlin = lin(v);  agg[i] = sum_{j->i} vlin[j] * mlp(gauss(d)) * C(d);
+ *                 v_out = v + lin2(ssp(lin1(agg))).   agg must be zeroed by the caller.
+ * w_mlp0 is [F, 64]: mlp.0.weight zero padded from num_gaussians to 64 columns. */
+typedef struct {
+  const float *w_lin;                 /* [F, H]  update_es.l.lin.weight (no bias) */
+  const float *w_mlp0, *b_mlp0;       /* [F, 64 (padded G)], [F] */
+  const float *w_mlp2, *b_mlp2;       /* [F, F], [F] */
+  const float *w_v1, *b_v1;           /* [H, F], [H]   update_vs.l.lin1 */
+  const float *w_v2, *b_v2;           /* [H, H], [H]   update_vs.l.lin2 */
+} dig3d_schnet_block_weights;
+
+int dig3d_schnet_block(const float* v, int64_t n_nodes, const float* dist, const int32_t* src,
+                       const int32_t* dst, int64_t n_edges, const float* offset, int32_t n_gauss, double coeff,
+                       double cutoff, int32_t hidden, int32_t filters, const dig3d_schnet_block_weights* w,
+                       float* vlin, float* agg, float* v_out, void* stream);
+
+/* update_u before the graph scatter (schnet.py:78-80): node_out[N, out_channels] = lin2(ssp(lin1(v))). */
+int dig3d_schnet_readout(const float* v, int64_t n_nodes, int32_t hidden, const float* w1, const float* b1,
+                         const float* w2, const float* b2, int32_t out_channels, float* node_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -152,3 +152,24 @@ def test_full_size_config_properties():
     # edges associate differently: equal to fp32 rounding, not bitwise
     assert rel_err(shuffled.cpu().numpy(), full[perm].cpu().numpy()) < 2e-6
     assert rel_err(single[0].cpu().numpy(), full[5].cpu().numpy()) < 2e-6
+
+
+@pytest.mark.parametrize("hidden,layers", [(32, 2), (128, 3)])
+def test_schnet_parity(hidden, layers):
+    """BASELINE configs[0] (SchNet 2-layer h=32, 16 x 12 atoms, cutoff 10) + the class-default width."""
+    from dig_b200.threedgraph.method import SchNet
+    from oracle import restated
+    dev = torch.device("cuda:0")
+    g, z, pos, batch = case_inputs("schnet_cfg1", dev)
+    model = SchNet(num_layers=layers, hidden_channels=hidden, num_filters=hidden, cutoff=10.0)
+    sd = formula_state_dict(model.state_dict(), seed=1)
+    model.load_state_dict(sd)
+    model = model.to(dev)
+    with torch.no_grad():
+        u = model(_batch(z, pos, batch))
+    ref = restated.schnet_forward({k: v.to(dev) for k, v in sd.items()}, z, pos, batch, cutoff=10.0,
+                                  num_layers=layers)
+    assert u.shape == (16, 1)
+    assert rel_err(u.cpu().numpy(), ref.cpu().numpy()) < TOL
+    if hidden == 32 and layers == 2:      # the fixture case: vs the real reference on CPU
+        assert rel_err(u.cpu().numpy(), g["energy_f32"]) < TOL
