@@ -28,6 +28,19 @@ class SchnetBlockWeights(Structure):
     _fields_ = [(n, P) for n in ("w_lin", "w_mlp0", "b_mlp0", "w_mlp2", "b_mlp2", "w_v1", "b_v1", "w_v2", "b_v2")]
 
 
+class ComenetBlockWeights(Structure):
+    _fields_ = ([(n, P) for n in ("w_lin", "b_lin", "w_f1a", "w_f1b", "w_f2a", "w_f2b", "w_rel1", "b_rel1",
+                                  "w_root1", "w_rel2", "b_rel2", "w_root2", "w_lin1", "b_lin1", "w_lin2",
+                                  "b_lin2", "w_cat", "b_cat")]
+                + [("w_lins", P * 8), ("b_lins", P * 8)]
+                + [(n, P) for n in ("norm_w", "norm_b", "norm_ms", "w_final", "b_final")]
+                + [("n_lins", c_int32)])
+
+
+class ComenetHeadWeights(Structure):
+    _fields_ = [("w_lins", P * 8), ("b_lins", P * 8), ("w_out", P), ("b_out", P), ("n_lins", c_int32)]
+
+
 class UpdateVWeights(Structure):
     _fields_ = [("w_up", P), ("b_up", P), ("w_lins", P * 8), ("b_lins", P * 8), ("w_out", P),
                 ("n_lins", c_int32)]
@@ -57,6 +70,10 @@ SIGNATURES = {
     "dig3d_schnet_block": [P, c_int64, P, P, P, c_int64, P, c_int32, c_double, c_double, c_int32, c_int32,
                            POINTER(SchnetBlockWeights), P, P, P, P],
     "dig3d_schnet_readout": [P, c_int64, c_int32, P, P, P, P, c_int32, P, P],
+    "dig3d_comenet_geometry": [P, P, P, P, P, P, P, c_int64, c_int64, c_double, P, P, P, P, P],
+    "dig3d_comenet_embed": [P, P, c_int64, P, P],
+    "dig3d_comenet_block": [P, P, P, P, P, P, P, c_int64, c_int64, c_int64, POINTER(ComenetBlockWeights),
+                            POINTER(ComenetHeadWeights), c_int32, P, P, P, P, P, P, P, P],
 }
 _RESTYPES = {"dig3d_last_error": c_char_p}
 

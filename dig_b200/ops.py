@@ -291,3 +291,71 @@ def schnet_readout(v, lin1, lin2, out_channels):
          _p(lin1.bias.detach(), torch.float32), _p(lin2.weight.detach(), torch.float32),
          _p(lin2.bias.detach(), torch.float32), int(out_channels), _p(node_out), _stream())
     return node_out
+
+
+# ----------------------------------------------------------------------------- ComENet
+def comenet_geometry(g, pos, cutoff, want_angles=False):
+    dev = pos.device
+    e, n = g.n_edges, g.n_nodes
+    refs = torch.empty(4 * max(n, 1), dtype=torch.int32, device=dev)
+    f1 = torch.empty(max(e, 1), 12, dtype=torch.float32, device=dev)[:e]
+    f2 = torch.empty(max(e, 1), 6, dtype=torch.float32, device=dev)[:e]
+    angles = torch.empty(e, 3, dtype=torch.float32, device=dev) if want_angles else None
+    call("dig3d_comenet_geometry", _p(pos.detach(), torch.float32, "pos"), _p(g.dist), _p(g.src), _p(g.dst),
+         _p(g.row_ptr), _p(g.graph_ptr), _p(g.batch, torch.int64), n, e, float(cutoff), _p(refs), _p(f1), _p(f2),
+         _p(angles) if want_angles else None, _stream())
+    return f1, f2, angles
+
+
+def comenet_embed(z, emb_weight):
+    n = z.numel()
+    x = torch.empty(n, emb_weight.size(1), dtype=torch.float32, device=emb_weight.device)
+    call("dig3d_comenet_embed", _p(z, torch.int64, "z"), _p(emb_weight.detach(), torch.float32), n, _p(x), _stream())
+    return x
+
+
+def pack_comenet_block(m):
+    w = _lib.ComenetBlockWeights()
+    w.w_lin, w.b_lin = _wp(m.lin.weight, "lin.w"), _wp(m.lin.bias, "lin.b")
+    w.w_f1a, w.w_f1b = _wp(m.lin_feature1.lin1.weight, "f1.lin1"), _wp(m.lin_feature1.lin2.weight, "f1.lin2")
+    w.w_f2a, w.w_f2b = _wp(m.lin_feature2.lin1.weight, "f2.lin1"), _wp(m.lin_feature2.lin2.weight, "f2.lin2")
+    w.w_rel1, w.b_rel1, w.w_root1 = (_wp(m.conv1.lin_rel.weight, "c1.rel.w"), _wp(m.conv1.lin_rel.bias, "c1.rel.b"),
+                                     _wp(m.conv1.lin_root.weight, "c1.root"))
+    w.w_rel2, w.b_rel2, w.w_root2 = (_wp(m.conv2.lin_rel.weight, "c2.rel.w"), _wp(m.conv2.lin_rel.bias, "c2.rel.b"),
+                                     _wp(m.conv2.lin_root.weight, "c2.root"))
+    w.w_lin1, w.b_lin1 = _wp(m.lin1.weight, "lin1.w"), _wp(m.lin1.bias, "lin1.b")
+    w.w_lin2, w.b_lin2 = _wp(m.lin2.weight, "lin2.w"), _wp(m.lin2.bias, "lin2.b")
+    w.w_cat, w.b_cat = _wp(m.lin_cat.weight, "lin_cat.w"), _wp(m.lin_cat.bias, "lin_cat.b")
+    for l, lin in enumerate(m.lins):
+        w.w_lins[l], w.b_lins[l] = _wp(lin.weight, "lins.w"), _wp(lin.bias, "lins.b")
+    w.n_lins = len(m.lins)
+    w.norm_w, w.norm_b, w.norm_ms = _wp(m.norm.weight, "norm.w"), _wp(m.norm.bias, "norm.b"), _wp(m.norm.mean_scale, "norm.ms")
+    w.w_final, w.b_final = _wp(m.final.weight, "final.w"), _wp(m.final.bias, "final.b")
+    return w
+
+
+def pack_comenet_head(lins, lin_out):
+    h = _lib.ComenetHeadWeights()
+    for l, lin in enumerate(lins):
+        h.w_lins[l], h.b_lins[l] = _wp(lin.weight, "head.lins.w"), _wp(lin.bias, "head.lins.b")
+    h.n_lins = len(lins)
+    if lin_out is not None:
+        h.w_out, h.b_out = _wp(lin_out.weight, "lin_out.w"), _wp(lin_out.bias, "lin_out.b")
+    return h
+
+
+def comenet_block(x, f1, f2, g, w, head, out_channels, last):
+    """One SimpleInteractionBlock; returns x_next [N,256], or node_out [N,out_channels] when `last`."""
+    dev = x.device
+    n, hch = x.shape
+    xs = torch.empty(n, hch, dtype=torch.float32, device=dev)
+    h = torch.empty(n, hch, dtype=torch.float32, device=dev)
+    agg = torch.zeros(2, n, hch, dtype=torch.float32, device=dev)
+    stats = torch.empty(2, max(g.n_graphs, 1), hch, dtype=torch.float32, device=dev)
+    x_out = None if last else torch.empty(n, hch, dtype=torch.float32, device=dev)
+    node_out = torch.empty(n, out_channels, dtype=torch.float32, device=dev) if last else None
+    call("dig3d_comenet_block", _p(x, torch.float32, "x", 16), _p(f1), _p(f2), _p(g.src), _p(g.dst),
+         _p(g.graph_ptr), _p(g.batch, torch.int64), n, g.n_edges, g.n_graphs, ctypes.byref(w), ctypes.byref(head),
+         int(out_channels), _p(xs), _p(agg[0]), _p(agg[1]), _p(h), _p(stats), _p(x_out) if x_out is not None else None,
+         _p(node_out) if node_out is not None else None, _stream())
+    return node_out if last else x_out

@@ -1,0 +1,181 @@
+"""ComENet behind the reference's class API (reference dig/threedgraph/method/comenet/comenet.py:218-401),
+running on the fused sm_100a kernels of dig_b200/csrc/comenet.cu.
+
+The module tree only HOLDS parameters under the reference's names -- including the PyG names the
+shipped OC20 checkpoint pins (`conv{1,2}.lin_rel.{weight,bias}`, `conv{1,2}.lin_root.weight`,
+`norm.{weight,bias,mean_scale}`) -- and initialises them like the reference."""
+import math
+from math import sqrt
+
+import torch
+from torch import nn
+
+from ... import ops
+from ._common import glorot, require_cuda
+
+
+class Linear(nn.Module):
+    """reference comenet.py:29-84 (glorot weights, zero bias by default)."""
+
+    def __init__(self, in_channels, out_channels, bias=True, weight_initializer='glorot', bias_initializer='zeros'):
+        super().__init__()
+        assert in_channels > 0
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.weight_initializer, self.bias_initializer = weight_initializer, bias_initializer
+        self.weight = nn.Parameter(torch.Tensor(out_channels, in_channels))
+        if bias:
+            self.bias = nn.Parameter(torch.Tensor(out_channels))
+        else:
+            self.register_parameter('bias', None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        if self.weight_initializer == 'glorot':
+            glorot(self.weight)
+        elif self.weight_initializer is None or self.weight_initializer == 'kaiming_uniform':
+            bound = math.sqrt(6 / ((1 + 5) * self.in_channels))      # kaiming_uniform(fan=in, a=sqrt(5))
+            self.weight.data.uniform_(-bound, bound)
+        elif self.weight_initializer == 'zeros':
+            self.weight.data.fill_(0)
+        else:
+            raise RuntimeError(f"Linear layer weight initializer '{self.weight_initializer}' is not supported")
+        if self.bias is not None:
+            if self.bias_initializer == 'zeros':
+                self.bias.data.fill_(0)
+            elif self.bias_initializer is None:
+                bound = 1.0 / math.sqrt(self.in_channels)
+                self.bias.data.uniform_(-bound, bound)
+            else:
+                raise RuntimeError(f"Linear layer bias initializer '{self.bias_initializer}' is not supported")
+
+
+class TwoLayerLinear(nn.Module):
+    """reference comenet.py:87-112 (used with bias=False, act=False)."""
+
+    def __init__(self, in_channels, middle_channels, out_channels, bias=False, act=False):
+        super().__init__()
+        if bias or act:
+            raise NotImplementedError("the fused edge filter implements TwoLayerLinear(bias=False, act=False)")
+        self.lin1 = Linear(in_channels, middle_channels, bias=bias)
+        self.lin2 = Linear(middle_channels, out_channels, bias=bias)
+
+    def reset_parameters(self):
+        self.lin1.reset_parameters()
+        self.lin2.reset_parameters()
+
+
+class EmbeddingBlock(nn.Module):
+    def __init__(self, hidden_channels):
+        super().__init__()
+        self.emb = nn.Embedding(95, hidden_channels)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        self.emb.weight.data.uniform_(-sqrt(3), sqrt(3))
+
+
+class EdgeGraphConv(nn.Module):
+    """Holder with torch_geometric.nn.GraphConv's parameters (reference comenet.py:130-133):
+    out = lin_rel(sum_j w_e * x_j) + lin_root(x_i); PyG default initialisers."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.lin_rel = Linear(in_channels, out_channels, bias=True, weight_initializer=None, bias_initializer=None)
+        self.lin_root = Linear(in_channels, out_channels, bias=False, weight_initializer=None)
+
+    def reset_parameters(self):
+        self.lin_rel.reset_parameters()
+        self.lin_root.reset_parameters()
+
+
+class GraphNorm(nn.Module):
+    """Holder with torch_geometric.nn.GraphNorm's parameters (used at reference comenet.py:160)."""
+
+    def __init__(self, in_channels, eps=1e-5):
+        super().__init__()
+        self.eps = eps
+        self.weight = nn.Parameter(torch.Tensor(in_channels))
+        self.bias = nn.Parameter(torch.Tensor(in_channels))
+        self.mean_scale = nn.Parameter(torch.Tensor(in_channels))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        self.weight.data.fill_(1)
+        self.bias.data.fill_(0)
+        self.mean_scale.data.fill_(1)
+
+
+class SimpleInteractionBlock(nn.Module):
+    """reference comenet.py:136-215."""
+
+    def __init__(self, hidden_channels, middle_channels, num_radial, num_spherical, num_layers, output_channels):
+        super().__init__()
+        self.conv1 = EdgeGraphConv(hidden_channels, hidden_channels)
+        self.conv2 = EdgeGraphConv(hidden_channels, hidden_channels)
+        self.lin1 = Linear(hidden_channels, hidden_channels)
+        self.lin2 = Linear(hidden_channels, hidden_channels)
+        self.lin_cat = Linear(2 * hidden_channels, hidden_channels)
+        self.norm = GraphNorm(hidden_channels)
+        self.lin_feature1 = TwoLayerLinear(num_radial * num_spherical ** 2, middle_channels, hidden_channels)
+        self.lin_feature2 = TwoLayerLinear(num_radial * num_spherical, middle_channels, hidden_channels)
+        self.lin = Linear(hidden_channels, hidden_channels)
+        self.lins = nn.ModuleList([Linear(hidden_channels, hidden_channels) for _ in range(num_layers)])
+        self.final = Linear(hidden_channels, output_channels)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        for m in (self.conv1, self.conv2, self.norm, self.lin_feature1, self.lin_feature2, self.lin, self.lin1,
+                  self.lin2, self.lin_cat, *self.lins, self.final):
+            m.reset_parameters()
+
+
+class ComENet(nn.Module):
+    r"""Drop-in for dig.threedgraph.method.ComENet (same constructor arguments and defaults).
+    This round's kernels are compiled for hidden_channels=256, middle_channels=64, num_radial=3,
+    num_spherical=2 (the class defaults); other sizes raise at construction."""
+
+    def __init__(self, cutoff=8.0, num_layers=4, hidden_channels=256, middle_channels=64, out_channels=1,
+                 num_radial=3, num_spherical=2, num_output_layers=3):
+        super().__init__()
+        if (hidden_channels, middle_channels, num_radial, num_spherical) != (256, 64, 3, 2) or num_output_layers > 8:
+            raise NotImplementedError(
+                "ComENet kernels of this round are compiled for hidden_channels=256, middle_channels=64, "
+                f"num_radial=3, num_spherical=2; got {(hidden_channels, middle_channels, num_radial, num_spherical)}")
+        if num_layers < 1:
+            raise ValueError("num_layers must be >= 1")
+        self.out_channels = out_channels
+        self.cutoff = cutoff
+        self.num_layers = num_layers
+        self.emb = EmbeddingBlock(hidden_channels)
+        self.interaction_blocks = nn.ModuleList([
+            SimpleInteractionBlock(hidden_channels, middle_channels, num_radial, num_spherical, num_output_layers,
+                                   hidden_channels) for _ in range(num_layers)])
+        self.lins = nn.ModuleList([Linear(hidden_channels, hidden_channels) for _ in range(num_output_layers)])
+        self.lin_out = Linear(hidden_channels, out_channels)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        self.emb.reset_parameters()
+        for m in self.interaction_blocks:
+            m.reset_parameters()
+        for lin in self.lins:
+            lin.reset_parameters()
+        self.lin_out.reset_parameters()
+
+    def _forward(self, data):
+        batch, z, pos = data.batch, data.z.long(), data.pos
+        require_cuda(pos, "ComENet.forward")
+        g = ops.build_graph(pos, batch, self.cutoff, num_graphs=getattr(data, "num_graphs", None),
+                            want_edge_index=False)
+        f1, f2, _ = ops.comenet_geometry(g, pos, self.cutoff)
+        x = ops.comenet_embed(z, self.emb.emb.weight)
+        no_head = ops.pack_comenet_head([], None)
+        head = ops.pack_comenet_head(self.lins, self.lin_out)
+        for b, block in enumerate(self.interaction_blocks):
+            last = b == self.num_layers - 1
+            x = ops.comenet_block(x, f1, f2, g, ops.pack_comenet_block(block), head if last else no_head,
+                                  self.out_channels, last)
+        return ops.segment_sum(x, g.graph_ptr)          # energy = scatter(x, batch)   comenet.py:398
+
+    def forward(self, batch_data):
+        return self._forward(batch_data)

@@ -1,0 +1,139 @@
+"""Training / evaluation driver with the interface of reference dig/threedgraph/method/run.py:13-180.
+
+Same `run().run(...)`, `train(...)`, `val(...)` signatures, printed dictionaries, checkpoint
+contents and return values.  torch_geometric's DataLoader (reference run.py:6,53-55) is replaced by
+dig_b200.data.DataLoader (same constructor use, concatenating collate).
+
+Round-1 status: the sm_100a kernels are forward-only, so `val` (inference, the reference's eval
+loop) runs on the fused path, while `train` raises for the dig_b200 models until the backward
+kernels exist (any differentiable torch model still trains through this driver unchanged).
+"""
+import os
+
+import torch
+from torch.autograd import grad
+from torch.optim import Adam
+from torch.optim.lr_scheduler import StepLR
+
+from ...data import DataLoader
+
+try:                       # progress bars are optional plumbing (reference run.py:10)
+    from tqdm import tqdm
+except ImportError:        # pragma: no cover
+    def tqdm(x):
+        return x
+
+
+class run():
+    r"""The base script for running different 3DGN methods (reference run.py:13-18)."""
+
+    def __init__(self):
+        pass
+
+    def run(self, device, train_dataset, valid_dataset, test_dataset, model, loss_func, evaluation, epochs=500,
+            batch_size=32, vt_batch_size=32, lr=0.0005, lr_decay_factor=0.5, lr_decay_step_size=50, weight_decay=0,
+            energy_and_force=False, p=100, save_dir='', log_dir=''):
+        r"""reference run.py:20-101."""
+        model = model.to(device)
+        num_params = sum(p.numel() for p in model.parameters())
+        print(f'#Params: {num_params}')
+        optimizer = Adam(model.parameters(), lr=lr, weight_decay=weight_decay)
+        scheduler = StepLR(optimizer, step_size=lr_decay_step_size, gamma=lr_decay_factor)
+        train_loader = DataLoader(train_dataset, batch_size, shuffle=True)
+        valid_loader = DataLoader(valid_dataset, vt_batch_size, shuffle=False)
+        test_loader = DataLoader(test_dataset, vt_batch_size, shuffle=False)
+        best_valid = float('inf')
+        best_test = float('inf')
+        if save_dir != '' and not os.path.exists(save_dir):
+            os.makedirs(save_dir)
+        writer = None
+        if log_dir != '':
+            if not os.path.exists(log_dir):
+                os.makedirs(log_dir)
+            from torch.utils.tensorboard import SummaryWriter
+            writer = SummaryWriter(log_dir=log_dir)
+
+        for epoch in range(1, epochs + 1):
+            print("\n=====Epoch {}".format(epoch), flush=True)
+            print('\nTraining...', flush=True)
+            train_mae = self.train(model, optimizer, train_loader, energy_and_force, p, loss_func, device)
+            print('\n\nEvaluating...', flush=True)
+            valid_mae = self.val(model, valid_loader, energy_and_force, p, evaluation, device)
+            print('\n\nTesting...', flush=True)
+            test_mae = self.val(model, test_loader, energy_and_force, p, evaluation, device)
+            print()
+            print({'Train': train_mae, 'Validation': valid_mae, 'Test': test_mae})
+            if writer is not None:
+                writer.add_scalar('train_mae', train_mae, epoch)
+                writer.add_scalar('valid_mae', valid_mae, epoch)
+                writer.add_scalar('test_mae', test_mae, epoch)
+            if valid_mae < best_valid:
+                best_valid = valid_mae
+                best_test = test_mae
+                if save_dir != '':
+                    print('Saving checkpoint...')
+                    checkpoint = {'epoch': epoch, 'model_state_dict': model.state_dict(),
+                                  'optimizer_state_dict': optimizer.state_dict(),
+                                  'scheduler_state_dict': scheduler.state_dict(), 'best_valid_mae': best_valid,
+                                  'num_params': num_params}
+                    torch.save(checkpoint, os.path.join(save_dir, 'valid_checkpoint.pt'))
+            scheduler.step()
+
+        print(f'Best validation MAE so far: {best_valid}')
+        print(f'Test MAE when got best validation result: {best_test}')
+        if writer is not None:
+            writer.close()
+
+    def train(self, model, optimizer, train_loader, energy_and_force, p, loss_func, device):
+        r"""reference run.py:103-135; returns the mean training loss."""
+        model.train()
+        loss_accum = 0
+        step = -1
+        for step, batch_data in enumerate(tqdm(train_loader)):
+            optimizer.zero_grad()
+            batch_data = batch_data.to(device)
+            out = model(batch_data)
+            if not out.requires_grad:
+                raise NotImplementedError(
+                    "run.train: this model's forward is not differentiable -- the dig_b200 sm_100a kernels are "
+                    "forward-only in this round (backward kernels: DESIGN.md 'next'); use run.val for inference")
+            if energy_and_force:
+                force = -grad(outputs=out, inputs=batch_data.pos, grad_outputs=torch.ones_like(out),
+                              create_graph=True, retain_graph=True)[0]
+                e_loss = loss_func(out, batch_data.y.unsqueeze(1))
+                f_loss = loss_func(force, batch_data.force)
+                loss = e_loss + p * f_loss
+            else:
+                loss = loss_func(out, batch_data.y.unsqueeze(1))
+            loss.backward()
+            optimizer.step()
+            loss_accum += loss.detach().cpu().item()
+        return loss_accum / (step + 1)
+
+    def val(self, model, data_loader, energy_and_force, p, evaluation, device):
+        r"""reference run.py:137-180; returns the MAE (energy MAE + p * force MAE with forces).
+        Predictions are gathered in lists and concatenated once (the reference re-concatenates every
+        step); values are identical."""
+        model.eval()
+        preds, targets, preds_force, targets_force = [], [], [], []
+        for step, batch_data in enumerate(tqdm(data_loader)):
+            batch_data = batch_data.to(device)
+            if energy_and_force:
+                out = model(batch_data)
+                force = -grad(outputs=out, inputs=batch_data.pos, grad_outputs=torch.ones_like(out),
+                              create_graph=True, retain_graph=True)[0]
+                preds_force.append(force.detach_())
+                targets_force.append(batch_data.force)
+            else:
+                with torch.no_grad():
+                    out = model(batch_data)
+            preds.append(out.detach())
+            targets.append(batch_data.y.unsqueeze(1))
+        input_dict = {"y_true": torch.cat(targets, dim=0), "y_pred": torch.cat(preds, dim=0)}
+        if energy_and_force:
+            input_dict_force = {"y_true": torch.cat(targets_force, dim=0), "y_pred": torch.cat(preds_force, dim=0)}
+            energy_mae = evaluation.eval(input_dict)['mae']
+            force_mae = evaluation.eval(input_dict_force)['mae']
+            print({'Energy MAE': energy_mae, 'Force MAE': force_mae})
+            return energy_mae + p * force_mae
+        return evaluation.eval(input_dict)['mae']

@@ -186,6 +186,49 @@ int dig3d_schnet_block(const float* v, int64_t n_nodes, const float* dist, const
 int dig3d_schnet_readout(const float* v, int64_t n_nodes, int32_t hidden, const float* w1, const float* b1,
                          const float* w2, const float* b2, int32_t out_channels, float* node_out, void* stream);
 
+/* ------------------------------------------------------------------ ComENet (hidden 256, middle 64, nr=3, ns=2)
+ * dig3d_comenet_geometry: reference atoms (4x scatter_min, comenet.py:304-327), theta/phi/tau
+ * (comenet.py:365-385) and the basis features feature1[E,12] / feature2[E,6]
+ * (comenet/features.py:289-295,340-348).  refs: [4, N] int32 workspace (nearest / second-nearest
+ * in-edge, nearest / second-nearest out-edge of every node); angles: nullable [E,3] (theta,phi,tau). */
+int dig3d_comenet_geometry(const float* pos, const float* dist, const int32_t* src, const int32_t* dst,
+                           const int32_t* row_ptr, const int32_t* graph_ptr, const int64_t* batch,
+                           int64_t n_nodes, int64_t n_edges, double cutoff, int32_t* refs, float* feature1,
+                           float* feature2, float* angles, void* stream);
+
+/* x = act(emb(z))   EmbeddingBlock.forward, comenet.py:125-127 */
+int dig3d_comenet_embed(const int64_t* z, const float* emb, int64_t n_nodes, float* x, void* stream);
+
+typedef struct {
+  const float *w_lin, *b_lin;                 /* [256,256],[256]  interaction_blocks.b.lin */
+  const float *w_f1a, *w_f1b;                 /* lin_feature1.lin1 [64,12], .lin2 [256,64] (no bias) */
+  const float *w_f2a, *w_f2b;                 /* lin_feature2.lin1 [64,6],  .lin2 [256,64] */
+  const float *w_rel1, *b_rel1, *w_root1;     /* conv1.lin_rel (+bias), conv1.lin_root */
+  const float *w_rel2, *b_rel2, *w_root2;     /* conv2 */
+  const float *w_lin1, *b_lin1, *w_lin2, *b_lin2;
+  const float *w_cat, *b_cat;                 /* [256,512],[256] */
+  const float *w_lins[8], *b_lins[8];         /* lins.{l} */
+  const float *norm_w, *norm_b, *norm_ms;     /* GraphNorm weight, bias, mean_scale */
+  const float *w_final, *b_final;
+  int32_t n_lins;
+} dig3d_comenet_block_weights;
+
+typedef struct {                               /* output head, comenet.py:394-396 (n_lins == 0: no head) */
+  const float *w_lins[8], *b_lins[8];
+  const float *w_out, *b_out;                  /* [out_channels,256],[out_channels] */
+  int32_t n_lins;
+} dig3d_comenet_head_weights;
+
+/* One SimpleInteractionBlock (comenet.py:195-215): 5 kernels (entry lin, both edge convolutions with
+ * the edge->node scatter fused, node block, GraphNorm statistics, norm + final).  When head->n_lins > 0
+ * the output head is fused behind `final` and node_out[N,out_channels] is written instead of x_out.
+ * Workspaces: xs, h [N,256]; agg1, agg2 [N,256] ZEROED by the caller; stats [2, n_graphs, 256]. */
+int dig3d_comenet_block(const float* x_in, const float* feature1, const float* feature2, const int32_t* src,
+                        const int32_t* dst, const int32_t* graph_ptr, const int64_t* batch, int64_t n_nodes,
+                        int64_t n_edges, int64_t n_graphs, const dig3d_comenet_block_weights* w,
+                        const dig3d_comenet_head_weights* head, int32_t out_channels, float* xs, float* agg1,
+                        float* agg2, float* h, float* stats, float* x_out, float* node_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

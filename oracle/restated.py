@@ -268,3 +268,107 @@ def schnet_forward(sd, z, pos, batch, *, cutoff=10.0, num_layers=6, num_gaussian
         v = v + _lin(sd, q + ".lin2", ssp(_lin(sd, q + ".lin1", out)))     # :56-59
     h = _lin(sd, "update_u.lin2", ssp(_lin(sd, "update_u.lin1", v)))       # :78-80
     return shim.scatter(h, batch, dim=0, dim_size=num_graphs)
+
+
+# ----------------------------------------------------------------------------- ComENet
+def comenet_geometry(pos, edge_index, num_nodes, cutoff):
+    """comenet.py:295-385: nearest / second-nearest reference atoms and the angles theta, phi, tau."""
+    j, i = edge_index
+    vecs = pos[j] - pos[i]                                                 # :297
+    dist = vecs.norm(dim=-1)
+    n_e = i.numel()
+
+    def two_nearest(index):                                                # :304-327
+        _, a0 = shim.scatter_min(dist, index, dim_size=num_nodes)
+        a0[a0 >= n_e] = 0
+        add = torch.zeros_like(dist)
+        add[a0] = cutoff
+        _, a1 = shim.scatter_min(dist + add, index, dim_size=num_nodes)
+        a1[a1 >= n_e] = 0
+        return a0, a1
+
+    argmin0, argmin1 = two_nearest(i)
+    argmin0_j, argmin1_j = two_nearest(j)
+    n0, n1 = j[argmin0][i], j[argmin1][i]
+    n0_j, n1_j = i[argmin0_j][j], i[argmin1_j][j]
+    mask_iref = n0 == j                                                    # :344-354
+    idx_iref = argmin0[i].clone()
+    idx_iref[mask_iref] = argmin1[i][mask_iref]
+    mask_jref = n0_j == i
+    idx_jref = argmin0_j[j].clone()
+    idx_jref[mask_jref] = argmin1_j[j][mask_jref]
+    pos_ji, pos_in0, pos_in1 = vecs, vecs[argmin0][i], vecs[argmin1][i]
+    pos_iref, pos_jref_j = vecs[idx_iref], vecs[idx_jref]
+    cross = lambda a, b: torch.linalg.cross(a, b, dim=-1)
+
+    def fold(t):                                                           # x[x<0] += pi   :368,377,385
+        t = t.clone()
+        t[t < 0] = t[t < 0] + math.pi
+        return t
+
+    a = ((-pos_ji) * pos_in0).sum(dim=-1)
+    b = cross(-pos_ji, pos_in0).norm(dim=-1)
+    theta = fold(torch.atan2(b, a))
+    dist_ji = pos_ji.pow(2).sum(dim=-1).sqrt()
+    plane1, plane2 = cross(-pos_ji, pos_in0), cross(-pos_ji, pos_in1)
+    a = (plane1 * plane2).sum(dim=-1)
+    b = (cross(plane1, plane2) * pos_ji).sum(dim=-1) / dist_ji
+    phi = fold(torch.atan2(b, a))
+    plane1, plane2 = cross(pos_ji, pos_jref_j), cross(pos_ji, pos_iref)
+    a = (plane1 * plane2).sum(dim=-1)
+    b = (cross(plane1, plane2) * pos_ji).sum(dim=-1) / dist_ji
+    tau = fold(torch.atan2(b, a))
+    return dist, theta, phi, tau
+
+
+def comenet_features(dist, theta, phi, tau, cutoff, ns=2, nr=3):
+    """comenet/features.py:284-295 (angle_emb) and :340-348 (torsion_emb)."""
+    bs = basis(f"comenet_{ns}_{nr}", ns, nr)
+    rbf = bs.rbf(dist, cutoff)                                             # [E, ns*nr]
+    y0 = torch.stack([torch.zeros_like(tau) + bs.y0_const] + [fn(tau) for fn in bs.yl0], dim=1)
+    feature2 = (rbf.view(-1, ns, nr) * y0.view(-1, ns, 1)).view(-1, ns * nr)
+    ylm = torch.stack([torch.zeros_like(theta) + bs.ylm_const] + [fn(theta, phi) for fn in bs.ylm], dim=1)
+    degree = torch.arange(ns, device=dist.device) * 2 + 1
+    r = rbf.view(-1, ns, nr).repeat_interleave(degree, dim=1).view(-1, ns ** 2 * nr)
+    feature1 = r * ylm.repeat_interleave(nr, dim=1)
+    return feature1, feature2
+
+
+def comenet_forward(sd, z, pos, batch, *, cutoff=8.0, num_layers=4, num_radial=3, num_spherical=2,
+                    num_output_layers=3, num_graphs=None, return_intermediates=False):
+    """ComENet._forward (comenet.py:288-399)."""
+    n = z.size(0)
+    if num_graphs is None:
+        num_graphs = int(batch.max()) + 1
+    edge_index = radius_graph(pos, cutoff, batch)
+    j, i = edge_index
+    dist, theta, phi, tau = comenet_geometry(pos, edge_index, n, cutoff)
+    f1, f2 = comenet_features(dist, theta, phi, tau, cutoff, num_spherical, num_radial)
+    x = swish(F.embedding(z.long(), sd["emb.emb.weight"]))                  # comenet.py:125-127
+    for b in range(num_layers):                                            # comenet.py:195-215
+        p = f"interaction_blocks.{b}"
+        x = swish(_lin(sd, p + ".lin", x))
+        hs = []
+        for c, feat in ((1, f1), (2, f2)):
+            w = _lin(sd, f"{p}.lin_feature{c}.lin2", _lin(sd, f"{p}.lin_feature{c}.lin1", feat))
+            agg = torch.zeros_like(x).index_add_(0, i, w * x[j])           # EdgeGraphConv.message + add aggr
+            h = _lin(sd, f"{p}.conv{c}.lin_rel", agg) + _lin(sd, f"{p}.conv{c}.lin_root", x)
+            hs.append(swish(_lin(sd, f"{p}.lin{c}", h)))
+        h = _lin(sd, p + ".lin_cat", torch.cat(hs, 1)) + x
+        for l in range(num_output_layers):
+            h = swish(_lin(sd, f"{p}.lins.{l}", h)) + h
+        # GraphNorm (torch_geometric 2.1.0)
+        mean = shim.scatter(h, batch, dim=0, dim_size=num_graphs, reduce="mean")
+        out = h - mean.index_select(0, batch) * sd[p + ".norm.mean_scale"]
+        var = shim.scatter(out.pow(2), batch, dim=0, dim_size=num_graphs, reduce="mean")
+        std = (var + 1e-5).sqrt().index_select(0, batch)
+        h = sd[p + ".norm.weight"] * out / std + sd[p + ".norm.bias"]
+        x = _lin(sd, p + ".final", h)
+    for l in range(num_output_layers):
+        x = swish(_lin(sd, f"lins.{l}", x))
+    x = _lin(sd, "lin_out", x)
+    energy = shim.scatter(x, batch, dim=0, dim_size=num_graphs)
+    if return_intermediates:
+        return energy, dict(edge_index=edge_index, dist=dist, theta=theta, phi=phi, tau=tau,
+                            feature1=f1, feature2=f2)
+    return energy

@@ -58,12 +58,13 @@ def test_state_dict_contract():
     """Parameter names / shapes equal the reference's, from the fixture."""
     import json
     from helpers import GOLDEN
-    from dig_b200.threedgraph.method import SphereNet, DimeNetPP, SchNet
+    from dig_b200.threedgraph.method import SphereNet, DimeNetPP, SchNet, ComENet
     with open(os.path.join(GOLDEN, "state_shapes.json")) as fh:
         shapes = json.load(fh)
     for cls, kw in ((SphereNet, dict(cutoff=5.0)), (DimeNetPP, dict(cutoff=5.0)),
                     (SphereNet, dict(cutoff=5.0, num_spherical=3)),
-                    (SchNet, dict(num_layers=2, hidden_channels=32, num_filters=32, cutoff=10.0))):
+                    (SchNet, dict(num_layers=2, hidden_channels=32, num_filters=32, cutoff=10.0)),
+                    (ComENet, dict(cutoff=6.0, hidden_channels=256, middle_channels=64))):
         ref = shapes[cls.__name__ + json.dumps(kw, sort_keys=True)]
         mine = {k: list(v.shape) for k, v in cls(**kw).state_dict().items()}
         assert mine == ref
