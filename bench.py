@@ -266,12 +266,13 @@ def main():
     H, I = 128, 64
     kern = {k: sum(v) / len(v) for k, v in per.items()}
     step_kernel_ms = sum(sum(v) for v in per.values()) / min(args.steps, 10)
-    dom = "dig3d_sphere_update_e_b"
+    dom = "dig3d_sphere_update_e_b_tc" if "dig3d_sphere_update_e_b_tc" in kern else "dig3d_sphere_update_e_b"
     dom_ms = kern[dom]
     # algorithmic work of update_e part B per launch (DESIGN.md "kernels"):
     flops_b = E * (2 * I * H + 7 * 2 * H * H) + T * (2 * 2 * 8 * I + 2 * I)
     bytes_b = 4 * (E * (3 * H + 6 + 2) + T * (I + 16) + N * H)
-    roof = {"kernel": "sphere_update_e_b_kernel<true>", "bound": "tensor",
+    roof = {"kernel": dom.replace("dig3d_", "") + (" (triplet gather + tcgen05 3xTF32 chain)" if dom.endswith("_tc") else ""),
+            "bound": "tensor",
             "achieved": flops_b / (dom_ms * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
             "frac": flops_b / (dom_ms * 1e-3) / 1e12 / tf_peak, "traffic": None,
             "peak_source": f"{which} bf16_tflops_sustained (kernel timed inside the step)",
@@ -279,7 +280,8 @@ def main():
             "algorithmic_flops_per_launch": flops_b, "algorithmic_bytes_per_launch": bytes_b,
             "hbm_view": {"achieved": bytes_b / (dom_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                          "frac": bytes_b / (dom_ms * 1e-3) / 1e9 / hbm_peak},
-            "note": "fp32 FFMA tile engine (exact-fp32 parity path); tcgen05 3xTF32 is the planned replacement",
+            "note": "flops counted once per fp32 product; the tensor path issues 3 TF32 MMAs per product (3xTF32 split for 1e-5 parity), "
+                    "so the tensor pipe does 3x this work",
             "kernel_ms": {k.replace("dig3d_", ""): round(v, 5) for k, v in sorted(kern.items())}}
 
     # ---- scatter (segment-sum) HBM roofline: the second half of BASELINE.json's metric

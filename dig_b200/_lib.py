@@ -41,6 +41,12 @@ class ComenetHeadWeights(Structure):
     _fields_ = [("w_lins", P * 8), ("b_lins", P * 8), ("w_out", P), ("b_out", P), ("n_lins", c_int32)]
 
 
+class TcUpdateE(Structure):
+    _fields_ = ([(n, P) for n in ("p_ji", "b_ji", "p_kj", "b_kj", "p_down", "p_up")]
+                + [("p_res", P * 6), ("b_res", P * 6)]
+                + [(n, P) for n in ("p_lin", "b_lin", "w_rbf1", "w_rbf2", "w_rbf", "w_sbf2", "w_t2")])
+
+
 class UpdateVWeights(Structure):
     _fields_ = [("w_up", P), ("b_up", P), ("w_lins", P * 8), ("b_lins", P * 8), ("w_out", P),
                 ("n_lins", c_int32)]
@@ -67,6 +73,11 @@ SIGNATURES = {
                                 POINTER(UpdateEWeights), P, P, P],
     "dig3d_sphere_update_v": [P, c_int64, c_int32, POINTER(UpdateVWeights), P, P],
     "dig3d_graph_readout": [P, P, c_int64, c_int64, c_int32, c_int32, P, P],
+    "dig3d_tc_packed_floats": [c_int32, c_int32],
+    "dig3d_tc_pack": [P, P, P, P, c_int32, P],
+    "dig3d_tc_timeouts": [],
+    "dig3d_sphere_update_e_a_tc": [P, P, c_int64, POINTER(TcUpdateE), P, P, P],
+    "dig3d_sphere_update_e_b_tc": [P, P, P, P, P, P, c_int32, P, P, P, P, c_int64, POINTER(TcUpdateE), P, P, P, P],
     "dig3d_schnet_block": [P, c_int64, P, P, P, c_int64, P, c_int32, c_double, c_double, c_int32, c_int32,
                            POINTER(SchnetBlockWeights), P, P, P, P],
     "dig3d_schnet_readout": [P, c_int64, c_int32, P, P, P, P, c_int32, P, P],

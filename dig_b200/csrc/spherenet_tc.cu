@@ -1,0 +1,553 @@
+// SphereNet / DimeNet++ update_e on the 5th-generation tensor cores (tcgen05, sm_100a).
+//
+// The dense edge-MLP chain of update_e (spherenet.py:154-180: lin_ji, lin_kj, lin_down, lin_up, three
+// residual layers, lin) is ~96 % of the block's FLOPs.  Here each CTA owns 128 consecutive edges and runs
+// the whole chain with the activations resident on chip:
+//
+//   * MMA: tcgen05.mma.cta_group::1.kind::tf32, M = 128 (edges) x N = 128/64 (channels), fp32 accumulators
+//     in TMEM.  fp32 parity (1e-5) rules out plain TF32, so every product is the 3xTF32 split
+//     D = A_lo*W_hi + A_hi*W_lo + A_hi*W_hi with hi = rna_tf32(x), lo = rna_tf32(x - hi)
+//     (measured 3.7e-7 relative on the B200, tools/tc_test.cu).
+//   * A operand: the epilogue warps write the next layer's activations (already split into hi / lo planes)
+//     straight into the UMMA canonical K-major layout in shared memory; the fp32 residual / skip value
+//     of the row is parked in TMEM columns 128..255 (tcgen05.st/ld), so one A buffer (2 x 64 KB) suffices.
+//   * B operand: weights are pre-split and pre-arranged (dig3d_tc_pack) as [K/32][hi|lo][8][N][4] so that a
+//     K-chunk is ONE contiguous 32 KB block, streamed by cp.async.bulk (TMA engine) through a 2-stage
+//     mbarrier ring.
+//   * Warp roles: warp 0 = bulk-copy producer, warp 1 = MMA issuer (one elected thread), warps 2..9 =
+//     epilogue (TMEM -> registers -> bias / swish / residual -> split -> shared memory).
+//
+// The latency-bound triplet gather (spherenet.py:163-171) runs in its own high-occupancy SIMT kernel
+// (sphere_triplet_gather_kernel) and hands m[E,64] to the chain.
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace dig3d {
+using namespace tc05;
+
+constexpr int TC_M = 128;
+constexpr int TC_THREADS = 320;
+constexpr int TC_STAGES = 2;
+constexpr int TC_STAGE_FLOATS = 2 * 8 * 128 * 4;   // hi + lo planes of a K=32 chunk with N = 128
+
+struct TcSmem {
+  float a_hi[32 * TC_M * 4];
+  float a_lo[32 * TC_M * 4];
+  float w[TC_STAGES][TC_STAGE_FLOATS];
+  float bias[8][128];
+  float wr[128 * 8];      // lin_rbf (kernel B) or lin_rbf2 (kernel A) rows, padded to 8
+  float wr1[8 * 8];       // lin_rbf1 rows (kernel A), padded to 8
+  int dst[TC_M];
+  uint64_t full[TC_STAGES], empty[TC_STAGES], a_ready, d_ready;
+  uint32_t tmem_base;
+};
+
+struct TcGemm {
+  const float* w;     // packed [K/32][2][8][N][4]
+  const float* bias;  // [N] or null
+  int K, N;
+};
+
+__device__ __forceinline__ float swish_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+// ---- producer: stream every K-chunk of every GEMM of the chain through the ring
+template <int NG>
+__device__ __forceinline__ void tc_producer(TcSmem& s, const TcGemm (&g)[NG]) {
+  int it = 0;
+  for (int q = 0; q < NG; ++q) {
+    const int chunks = g[q].K / 32;
+    const uint32_t bytes = 2u * 8u * (uint32_t)g[q].N * 16u;
+    for (int c = 0; c < chunks; ++c, ++it) {
+      const int st = it % TC_STAGES;
+      mbar_wait(&s.empty[st], ((it / TC_STAGES) & 1) ^ 1);
+      mbar_arrive_expect_tx(&s.full[st], bytes);
+      bulk_g2s(s.w[st], g[q].w + (size_t)c * (bytes / 4), bytes, &s.full[st]);
+    }
+  }
+}
+
+// ---- MMA issuer
+template <int NG>
+__device__ __forceinline__ void tc_mma(TcSmem& s, const TcGemm (&g)[NG], uint32_t tmem_d) {
+  int it = 0;
+  const uint32_t a_hi = smem_u32(s.a_hi), a_lo = smem_u32(s.a_lo);
+  for (int q = 0; q < NG; ++q) {
+    const int chunks = g[q].K / 32, n = g[q].N;
+    const uint32_t idesc = idesc_tf32(TC_M, n);
+    mbar_wait(&s.a_ready, q & 1);
+    tc_fence_after();
+    for (int c = 0; c < chunks; ++c, ++it) {
+      const int st = it % TC_STAGES;
+      mbar_wait(&s.full[st], (it / TC_STAGES) & 1);
+      tc_fence_after();
+      const uint32_t w_hi = smem_u32(s.w[st]), w_lo = w_hi + 8u * n * 16u;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint32_t a_off = (uint32_t)((c * 4 + ks) * 2 * TC_M * 16);
+        const uint32_t b_off = (uint32_t)(ks * 2 * n * 16);
+        const uint64_t dah = smem_desc(a_hi + a_off, TC_M * 16, 128), dal = smem_desc(a_lo + a_off, TC_M * 16, 128);
+        const uint64_t dbh = smem_desc(w_hi + b_off, n * 16, 128), dbl = smem_desc(w_lo + b_off, n * 16, 128);
+        mma_tf32(tmem_d, dal, dbh, idesc, (c | ks) != 0);   // small terms first
+        mma_tf32(tmem_d, dah, dbl, idesc, 1);
+        mma_tf32(tmem_d, dah, dbh, idesc, 1);
+      }
+      mma_commit(&s.empty[st]);
+    }
+    mma_commit(&s.d_ready);
+  }
+}
+
+// ---- epilogue helpers (thread = one row, 64 or 32 columns in 16-column pieces)
+struct EpiCtx {
+  int row, half, lane_base;   // row in tile, column half (0/1), TMEM lane quarter base
+  uint32_t tm;                // TMEM base
+};
+__device__ __forceinline__ EpiCtx epi_ctx(const TcSmem& s) {
+  const int et = threadIdx.x - 64, we = et >> 5, lane = et & 31;
+  const int q = (we + 2) & 3;
+  return {32 * q + lane, we >> 2, 32 * q, s.tmem_base};
+}
+__device__ __forceinline__ void store_a(TcSmem& s, int row, int col, const float (&v)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; i += 4) {
+    float4 h, l;
+    split_tf32(v[i], h.x, l.x); split_tf32(v[i + 1], h.y, l.y); split_tf32(v[i + 2], h.z, l.z); split_tf32(v[i + 3], h.w, l.w);
+    const int o = (((col + i) >> 2) * TC_M + row) * 4;
+    *reinterpret_cast<float4*>(s.a_hi + o) = h;
+    *reinterpret_cast<float4*>(s.a_lo + o) = l;
+  }
+}
+__device__ __forceinline__ void epi_done(TcSmem& s) {
+  fence_async_smem();
+  tc_fence_before();
+  mbar_arrive(&s.a_ready);
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------- triplet gather (SIMT)
+// m[e] = sum_{t in trip(e)} x_down[kj(t)] * lin_sbf2(sbf_p[t]) * lin_t2(t_p[t])      spherenet.py:163-171
+template <bool TORSION>
+__global__ void __launch_bounds__(256)
+sphere_triplet_gather_kernel(const float* __restrict__ x_down, const float* __restrict__ sbf_p,
+                             const float* __restrict__ t_p, int ld_p, const int32_t* __restrict__ src,
+                             const int32_t* __restrict__ dst, const int32_t* __restrict__ row_ptr,
+                             const int32_t* __restrict__ trip_ptr, int n_edges, const float* __restrict__ w_sbf2,
+                             const float* __restrict__ w_t2, float* __restrict__ m) {
+  const int lane = threadIdx.x & 31;
+  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (e >= n_edges) return;
+  float ws2[2][8], wt2[2][8];
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      ws2[h][q] = __ldg(w_sbf2 + (lane + 32 * h) * 8 + q);
+      wt2[h][q] = TORSION ? __ldg(w_t2 + (lane + 32 * h) * 8 + q) : 0.f;
+    }
+  const int j = src[e], i = dst[e];
+  const int base = row_ptr[j], d = row_ptr[j + 1] - base;
+  int t = trip_ptr[e];
+  float a0 = 0.f, a1 = 0.f;
+  for (int sl = 0; sl < d; ++sl) {
+    const int kj = base + sl;
+    if (src[kj] == i) continue;
+    const float4* sp = reinterpret_cast<const float4*>(sbf_p + (size_t)t * ld_p);
+    const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
+    const float x0 = __ldg(x_down + (size_t)kj * 64 + lane), x1 = __ldg(x_down + (size_t)kj * 64 + lane + 32);
+    const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    float g0 = 0.f, g1 = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { g0 = fmaf(ws2[0][q], sv[q], g0); g1 = fmaf(ws2[1][q], sv[q], g1); }
+    float m0 = __fmul_rn(x0, g0), m1 = __fmul_rn(x1, g1);
+    if (TORSION) {
+      const float4* tp = reinterpret_cast<const float4*>(t_p + (size_t)t * ld_p);
+      const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1);
+      const float tv[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+      float h0 = 0.f, h1 = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { h0 = fmaf(wt2[0][q], tv[q], h0); h1 = fmaf(wt2[1][q], tv[q], h1); }
+      m0 = __fmul_rn(m0, h0); m1 = __fmul_rn(m1, h1);
+    }
+    a0 += m0; a1 += m1;
+    ++t;
+  }
+  m[(size_t)e * 64 + lane] = a0;
+  m[(size_t)e * 64 + lane + 32] = a1;
+}
+
+// ---------------------------------------------------------------------------------- weight packing
+// W [N, K] (nn.Linear layout) -> [K/32][hi|lo][8][N][4], hi/lo = TF32 split.  One launch packs up to 16 matrices.
+struct PackJob { const float* w; float* out; int N, K; };
+struct PackJobs { PackJob job[16]; int n; };
+__global__ void tc_pack_kernel(PackJobs jobs) {
+  const PackJob jb = jobs.job[blockIdx.y];
+  const int total = jb.N * jb.K;
+  for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < total; id += gridDim.x * blockDim.x) {
+    const int n = id / jb.K, k = id % jb.K;
+    float h, l;
+    split_tf32(__ldg(jb.w + id), h, l);
+    const int c = k >> 5, ku = (k & 31) >> 2, kk = k & 3;
+    const size_t blk = (size_t)c * (2 * 8 * jb.N * 4);
+    jb.out[blk + ((size_t)ku * jb.N + n) * 4 + kk] = h;
+    jb.out[blk + (size_t)8 * jb.N * 4 + ((size_t)ku * jb.N + n) * 4 + kk] = l;
+  }
+}
+
+// ---------------------------------------------------------------------------------- update_e part A (tensor)
+struct TcAParams {
+  TcGemm g[3];                 // lin_ji, lin_kj, lin_down
+  const float *w_rbf1, *w_rbf2;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+sphere_update_e_a_tc_kernel(const float* __restrict__ e1, const float* __restrict__ rbf0, int n_edges, TcAParams P,
+                            float* __restrict__ x_ji, float* __restrict__ x_down) {
+  extern __shared__ __align__(1024) unsigned char tc_raw[];
+  TcSmem& s = *reinterpret_cast<TcSmem*>(tc_raw);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int e0 = blockIdx.x * TC_M, rows = min(TC_M, n_edges - e0);
+  if (tid == 0) {
+    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    mbar_init(&s.a_ready, 256); mbar_init(&s.d_ready, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&s.tmem_base, 256);
+  for (int i = tid; i < 2 * 128; i += TC_THREADS) s.bias[i / 128][i % 128] = __ldg(P.g[i / 128].bias + i % 128);
+  for (int i = tid; i < 128 * 8; i += TC_THREADS) s.wr[i] = __ldg(P.w_rbf2 + i);      // [128][8]
+  for (int i = tid; i < 64; i += TC_THREADS) s.wr1[i] = (i % 8 < 6) ? __ldg(P.w_rbf1 + (i / 8) * 6 + i % 8) : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) {
+    if (tid == 0) tc_producer(s, P.g);
+  } else if (warp == 1) {
+    if (tid == 32) tc_mma(s, P.g, s.tmem_base);
+  } else {
+    const EpiCtx c = epi_ctx(s);
+    const bool valid = c.row < rows;
+    const size_t ge = (size_t)(e0 + c.row);
+    const uint32_t tl = c.tm + ((uint32_t)c.lane_base << 16);
+    // A0 = e1 tile
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const int col = c.half * 64 + cc * 16;
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        const float4 x = valid ? __ldg(reinterpret_cast<const float4*>(e1 + ge * 128 + col + i)) : make_float4(0, 0, 0, 0);
+        v[i] = x.x; v[i + 1] = x.y; v[i + 2] = x.z; v[i + 3] = x.w;
+      }
+      store_a(s, c.row, col, v);
+    }
+    // rbf gate coefficients of this row: r8 = lin_rbf1(rbf0[row])            spherenet.py:157
+    float r8[8];
+    {
+      float rb[6];
+#pragma unroll
+      for (int n = 0; n < 6; ++n) rb[n] = valid ? __ldg(rbf0 + ge * 6 + n) : 0.f;
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        float a = 0.f;
+#pragma unroll
+        for (int n = 0; n < 6; ++n) a = fmaf(s.wr1[m * 8 + n], rb[n], a);
+        r8[m] = a;
+      }
+    }
+    epi_done(s);
+    // G0: x_ji = act(lin_ji(e1))                                                spherenet.py:154
+    mbar_wait(&s.d_ready, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const int col = c.half * 64 + cc * 16;
+      uint32_t r[16];
+      tmem_ld16(tl + col, r);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          float4 o;
+          o.x = swish_fast(__uint_as_float(r[i]) + s.bias[0][col + i]);
+          o.y = swish_fast(__uint_as_float(r[i + 1]) + s.bias[0][col + i + 1]);
+          o.z = swish_fast(__uint_as_float(r[i + 2]) + s.bias[0][col + i + 2]);
+          o.w = swish_fast(__uint_as_float(r[i + 3]) + s.bias[0][col + i + 3]);
+          *reinterpret_cast<float4*>(x_ji + ge * 128 + col + i) = o;
+        }
+      }
+    }
+    epi_done(s);
+    // G1: x_kj = act(lin_kj(e1)) * lin_rbf2(r8)                                 spherenet.py:155-159
+    mbar_wait(&s.d_ready, 1);
+    tc_fence_after();
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const int col = c.half * 64 + cc * 16;
+      uint32_t r[16];
+      tmem_ld16(tl + col, r);
+      tmem_ld_wait();
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float gate = 0.f;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) gate = fmaf(s.wr[(col + i) * 8 + m], r8[m], gate);
+        v[i] = swish_fast(__uint_as_float(r[i]) + s.bias[1][col + i]) * gate;
+      }
+      store_a(s, c.row, col, v);
+    }
+    epi_done(s);
+    // G2: x_down = act(lin_down(x_kj)), N = 64                                  spherenet.py:161
+    mbar_wait(&s.d_ready, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      const int col = c.half * 32 + cc * 16;
+      uint32_t r[16];
+      tmem_ld16(tl + col, r);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          float4 o;
+          o.x = swish_fast(__uint_as_float(r[i])); o.y = swish_fast(__uint_as_float(r[i + 1]));
+          o.z = swish_fast(__uint_as_float(r[i + 2])); o.w = swish_fast(__uint_as_float(r[i + 3]));
+          *reinterpret_cast<float4*>(x_down + ge * 64 + col + i) = o;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(s.tmem_base, 256);
+}
+
+// ---------------------------------------------------------------------------------- update_e part B (tensor)
+struct TcBParams {
+  TcGemm g[8];                 // lin_up, res0.lin1, res0.lin2, lin, res1.lin1, res1.lin2, res2.lin1, res2.lin2
+  const float* w_rbf;          // [128, 6]
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+sphere_update_e_b_tc_kernel(const float* __restrict__ m, const float* __restrict__ x_ji,
+                            const float* __restrict__ e1_in, const float* __restrict__ rbf0,
+                            const int32_t* __restrict__ dst, int n_edges, TcBParams P, float* __restrict__ e1_out,
+                            float* __restrict__ v_in) {
+  extern __shared__ __align__(1024) unsigned char tc_raw[];
+  TcSmem& s = *reinterpret_cast<TcSmem*>(tc_raw);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int e0 = blockIdx.x * TC_M, rows = min(TC_M, n_edges - e0);
+  if (tid == 0) {
+    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    mbar_init(&s.a_ready, 256); mbar_init(&s.d_ready, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&s.tmem_base, 256);
+  for (int i = tid; i < 8 * 128; i += TC_THREADS) {
+    const float* b = P.g[i / 128].bias;
+    s.bias[i / 128][i % 128] = b ? __ldg(b + i % 128) : 0.f;
+  }
+  for (int i = tid; i < 128 * 8; i += TC_THREADS) s.wr[i] = (i % 8 < 6) ? __ldg(P.w_rbf + (i / 8) * 6 + i % 8) : 0.f;
+  for (int i = tid; i < TC_M; i += TC_THREADS) s.dst[i] = (i < rows) ? dst[e0 + i] : -1;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) {
+    if (tid == 0) tc_producer(s, P.g);
+  } else if (warp == 1) {
+    if (tid == 32) tc_mma(s, P.g, s.tmem_base);
+  } else {
+    const EpiCtx c = epi_ctx(s);
+    const bool valid = c.row < rows;
+    const size_t ge = (size_t)(e0 + c.row);
+    const uint32_t tl = c.tm + ((uint32_t)c.lane_base << 16);
+    // A0 = m tile (K = 64): this thread's 32 columns
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      const int col = c.half * 32 + cc * 16;
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        const float4 x = valid ? __ldg(reinterpret_cast<const float4*>(m + ge * 64 + col + i)) : make_float4(0, 0, 0, 0);
+        v[i] = x.x; v[i + 1] = x.y; v[i + 2] = x.z; v[i + 3] = x.w;
+      }
+      store_a(s, c.row, col, v);
+    }
+    epi_done(s);
+    // The eight epilogues of the chain (spherenet.py:172-179):
+    //   q=0: h = x_ji + act(lin_up(m))                       -> A, stash
+    //   q=1,4,6: t = act(lin1(h))                            -> A
+    //   q=2,5: h = stash + act(lin2(t))                      -> A, stash      (q=2: stash not needed afterwards)
+    //   q=3: h = act(lin(h)) + e1_in                         -> A, stash
+    //   q=7: h = stash + act(lin2(t))                        -> e1_out, e2 tile
+    for (int q = 0; q < 8; ++q) {
+      mbar_wait(&s.d_ready, q & 1);
+      tc_fence_after();
+      const bool add_stash = (q == 2 || q == 5 || q == 7);
+      const bool to_stash = (q == 0 || q == 3 || q == 5);
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const int col = c.half * 64 + cc * 16;
+        uint32_t r[16], st[16];
+        tmem_ld16(tl + col, r);
+        if (add_stash) tmem_ld16(tl + 128 + col, st);
+        tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = swish_fast(__uint_as_float(r[i]) + s.bias[q][col + i]);
+        if (add_stash) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += __uint_as_float(st[i]);
+        }
+        if (q == 0 || q == 3) {
+          const float* gsrc = (q == 0 ? x_ji : e1_in) + ge * 128 + col;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 x = valid ? __ldg(reinterpret_cast<const float4*>(gsrc + i)) : make_float4(0, 0, 0, 0);
+            v[i] += x.x; v[i + 1] += x.y; v[i + 2] += x.z; v[i + 3] += x.w;
+          }
+        }
+        if (q < 7) {
+          store_a(s, c.row, col, v);
+          if (to_stash) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) st[i] = __float_as_uint(v[i]);
+            tmem_st16(tl + 128 + col, st);
+          }
+        } else {
+          // e1_out and e2 = lin_rbf(rbf0) * e1 (tile staged over the A planes)   spherenet.py:180
+          float rb[6];
+#pragma unroll
+          for (int n = 0; n < 6; ++n) rb[n] = valid ? __ldg(rbf0 + ge * 6 + n) : 0.f;
+          float* e2t = s.a_hi;   // [128][132] floats overlay (a_hi + a_lo are contiguous, all MMAs are done)
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            if (valid) *reinterpret_cast<float4*>(e1_out + ge * 128 + col + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float gsum = 0.f;
+#pragma unroll
+              for (int n = 0; n < 6; ++n) gsum = fmaf(s.wr[(col + i + u) * 8 + n], rb[n], gsum);
+              e2t[c.row * 132 + col + i + u] = gsum * v[i + u];
+            }
+          }
+        }
+      }
+      if (q < 7) {
+        if (to_stash) tmem_st_wait();
+        epi_done(s);
+      }
+    }
+    tc_fence_before();
+    epi_bar();
+    // segmented edge -> node sums of the e2 tile (target-sorted rows)             spherenet.py:211
+    const int col = tid - 64;
+    if (col < 128 && rows > 0) {
+      const float* e2t = s.a_hi;
+      float run = 0.f;
+      int cur = s.dst[0];
+      bool first = true;
+      for (int r = 0; r < rows; ++r) {
+        const int d = s.dst[r];
+        if (d != cur) {
+          if (first) atomicAdd(v_in + (size_t)cur * 128 + col, run);
+          else v_in[(size_t)cur * 128 + col] = run;
+          first = false; run = 0.f; cur = d;
+        }
+        run += e2t[r * 132 + col];
+      }
+      atomicAdd(v_in + (size_t)cur * 128 + col, run);
+    }
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(s.tmem_base, 256);
+}
+
+static int tc_smem_attr(const void* fn, size_t bytes) {
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(%zu): %s", bytes, cudaGetErrorString(e));
+    return DIG3D_ECUDA;
+  }
+  return DIG3D_OK;
+}
+
+}  // namespace dig3d
+
+using namespace dig3d;
+
+extern "C" {
+
+int dig3d_tc_packed_floats(int32_t n, int32_t k) { return 2 * n * k; }
+
+int dig3d_tc_pack(const float* const* weights, const int32_t* n, const int32_t* k, float* const* outs, int32_t count,
+                  void* stream) {
+  DIG3D_REQUIRE(weights && n && k && outs && count >= 1 && count <= 16, "tc_pack: bad arguments");
+  PackJobs jobs;
+  jobs.n = count;
+  int max_total = 0;
+  for (int i = 0; i < count; ++i) {
+    DIG3D_REQUIRE(weights[i] && outs[i] && k[i] % 32 == 0 && n[i] % 8 == 0, "tc_pack: matrix %d has N=%d K=%d", i, n[i], k[i]);
+    jobs.job[i] = {weights[i], outs[i], n[i], k[i]};
+    max_total = max_total > n[i] * k[i] ? max_total : n[i] * k[i];
+  }
+  dim3 grid(ceil_div(max_total, 256), count);
+  tc_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(jobs);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_tc_timeouts(void) {
+  unsigned int v = 0;
+  cudaMemcpyFromSymbol(&v, tc05::g_mbar_timeout, sizeof(v));
+  return (int)v;
+}
+
+int dig3d_sphere_update_e_a_tc(const float* e1, const float* rbf0, int64_t n_edges, const dig3d_tc_update_e* w,
+                               float* x_ji, float* x_down, void* stream) {
+  DIG3D_REQUIRE(e1 && rbf0 && w && x_ji && x_down, "sphere_update_e_a_tc: null pointer");
+  if (n_edges == 0) return DIG3D_OK;
+  TcAParams P;
+  P.g[0] = {w->p_ji, w->b_ji, 128, 128};
+  P.g[1] = {w->p_kj, w->b_kj, 128, 128};
+  P.g[2] = {w->p_down, nullptr, 128, 64};
+  P.w_rbf1 = w->w_rbf1; P.w_rbf2 = w->w_rbf2;
+  int rc = tc_smem_attr((const void*)sphere_update_e_a_tc_kernel, sizeof(TcSmem));
+  if (rc) return rc;
+  sphere_update_e_a_tc_kernel<<<ceil_div(n_edges, TC_M), TC_THREADS, sizeof(TcSmem), (cudaStream_t)stream>>>(
+      e1, rbf0, (int)n_edges, P, x_ji, x_down);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_sphere_update_e_b_tc(const float* e1_in, const float* x_ji, const float* x_down, const float* rbf0,
+                               const float* sbf_p, const float* t_p, int32_t ld_p, const int32_t* src,
+                               const int32_t* dst, const int32_t* row_ptr, const int32_t* trip_ptr, int64_t n_edges,
+                               const dig3d_tc_update_e* w, float* m_ws, float* e1_out, float* v_in, void* stream) {
+  DIG3D_REQUIRE(e1_in && x_ji && x_down && rbf0 && sbf_p && src && dst && row_ptr && trip_ptr && w && m_ws && e1_out &&
+                    v_in, "sphere_update_e_b_tc: null pointer");
+  DIG3D_REQUIRE((t_p != nullptr) == (w->w_t2 != nullptr), "sphere_update_e_b_tc: t_p and w_t2 must agree");
+  if (n_edges == 0) return DIG3D_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int gblocks = ceil_div(n_edges * 32, 256);
+  if (t_p)
+    sphere_triplet_gather_kernel<true><<<gblocks, 256, 0, st>>>(x_down, sbf_p, t_p, ld_p, src, dst, row_ptr, trip_ptr,
+                                                               (int)n_edges, w->w_sbf2, w->w_t2, m_ws);
+  else
+    sphere_triplet_gather_kernel<false><<<gblocks, 256, 0, st>>>(x_down, sbf_p, t_p, ld_p, src, dst, row_ptr, trip_ptr,
+                                                                (int)n_edges, w->w_sbf2, w->w_t2, m_ws);
+  DIG3D_LAUNCH_CHECK();
+  TcBParams P;
+  P.g[0] = {w->p_up, nullptr, 64, 128};
+  for (int i = 0; i < 2; ++i) P.g[1 + i] = {w->p_res[i], w->b_res[i], 128, 128};
+  P.g[3] = {w->p_lin, w->b_lin, 128, 128};
+  for (int i = 2; i < 6; ++i) P.g[2 + i] = {w->p_res[i], w->b_res[i], 128, 128};
+  P.w_rbf = w->w_rbf;
+  int rc = tc_smem_attr((const void*)sphere_update_e_b_tc_kernel, sizeof(TcSmem));
+  if (rc) return rc;
+  sphere_update_e_b_tc_kernel<<<ceil_div(n_edges, TC_M), TC_THREADS, sizeof(TcSmem), st>>>(
+      m_ws, x_ji, e1_in, rbf0, dst, (int)n_edges, P, e1_out, v_in);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+}  // extern "C"

@@ -359,3 +359,71 @@ def comenet_block(x, f1, f2, g, w, head, out_channels, last):
          int(out_channels), _p(xs), _p(agg[0]), _p(agg[1]), _p(h), _p(stats), _p(x_out) if x_out is not None else None,
          _p(node_out) if node_out is not None else None, _stream())
     return node_out if last else x_out
+
+
+# ----------------------------------------------------------------------------- tcgen05 update_e
+_TC_MATS = ("lin_ji", "lin_kj", "lin_down", "lin_up", "lin")
+
+
+def tc_pack_update_e(m, torsion, cache):
+    """Packed (TF32 hi/lo split, UMMA layout) copies of the dense weights of one update_e block.
+    `cache` (a dict owned by the model) keeps them until a parameter changes (tensor._version)."""
+    mats = [m.lin_ji.weight, m.lin_kj.weight, m.lin_down.weight, m.lin_up.weight]
+    res = list(m.layers_before_skip) + list(m.layers_after_skip)
+    for layer in res:
+        mats += [layer.lin1.weight, layer.lin2.weight]
+    mats.append(m.lin.weight)
+    key = tuple((w.data_ptr(), w._version) for w in mats)
+    hit = cache.get(id(m))
+    if hit is None or hit[0] != key:
+        dev = mats[0].device
+        sizes = [2 * w.size(0) * w.size(1) for w in mats]
+        buf = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+        offs = [0]
+        for sz in sizes:
+            offs.append(offs[-1] + sz)
+        n = len(mats)
+        wp = (ctypes.c_void_p * n)(*[_p(w.detach(), torch.float32, "w", 16).value for w in mats])
+        op = (ctypes.c_void_p * n)(*[buf.data_ptr() + 4 * o for o in offs[:-1]])
+        ns = (ctypes.c_int32 * n)(*[w.size(0) for w in mats])
+        ks = (ctypes.c_int32 * n)(*[w.size(1) for w in mats])
+        call("dig3d_tc_pack", wp, ns, ks, op, n, _stream())
+        hit = (key, buf, offs)
+        cache[id(m)] = hit
+    _, buf, offs = hit
+    base = buf.data_ptr()
+    w = _lib.TcUpdateE()
+    w.p_ji, w.p_kj, w.p_down, w.p_up = (base + 4 * offs[0], base + 4 * offs[1], base + 4 * offs[2], base + 4 * offs[3])
+    for r in range(6):
+        w.p_res[r] = base + 4 * offs[4 + r]
+    w.p_lin = base + 4 * offs[10]
+    w.b_ji, w.b_kj, w.b_lin = _wp(m.lin_ji.bias, "b_ji"), _wp(m.lin_kj.bias, "b_kj"), _wp(m.lin.bias, "b_lin")
+    for r, layer in enumerate(res):
+        w.b_res[2 * r], w.b_res[2 * r + 1] = _wp(layer.lin1.bias, "res.b1"), _wp(layer.lin2.bias, "res.b2")
+    w.w_rbf1, w.w_rbf2, w.w_rbf = _wp(m.lin_rbf1.weight, "rbf1"), _wp(m.lin_rbf2.weight, "rbf2"), _wp(m.lin_rbf.weight, "rbf")
+    w.w_sbf2 = _wp(m.lin_sbf2.weight, "sbf2")
+    w.w_t2 = _wp(m.lin_t2.weight, "t2") if torsion else None
+    return w
+
+
+def sphere_update_e_tc(e1, g, rbf0, sbf_p, t_p, col0, w, hidden, int_emb):
+    """update_e (A + triplet gather + B) with the dense chain on tcgen05."""
+    dev = e1.device
+    e = g.n_edges
+    x_ji = torch.empty(max(e, 1), hidden, dtype=torch.float32, device=dev)[:e]
+    x_down = torch.empty(max(e, 1), int_emb, dtype=torch.float32, device=dev)[:e]
+    m_ws = torch.empty(max(e, 1), int_emb, dtype=torch.float32, device=dev)[:e]
+    e1_out = torch.empty(max(e, 1), hidden, dtype=torch.float32, device=dev)[:e]
+    v_in = torch.zeros(g.n_nodes, hidden, dtype=torch.float32, device=dev)
+    if e:
+        st = _stream()
+        call("dig3d_sphere_update_e_a_tc", _p(e1), _p(rbf0), e, ctypes.byref(w), _p(x_ji), _p(x_down), st)
+        sp = ctypes.c_void_p(sbf_p.data_ptr() + 4 * col0)
+        tp = ctypes.c_void_p(t_p.data_ptr() + 4 * col0) if t_p is not None else None
+        call("dig3d_sphere_update_e_b_tc", _p(e1), _p(x_ji), _p(x_down), _p(rbf0), sp, tp, 32, _p(g.src), _p(g.dst),
+             _p(g.row_ptr), _p(g.trip_ptr), e, ctypes.byref(w), _p(m_ws), _p(e1_out), _p(v_in), st)
+    return e1_out, v_in, x_ji, x_down
+
+
+def tc_timeouts():
+    return _lib.load().dig3d_tc_timeouts()

@@ -12,6 +12,7 @@ round-trip) and initialises them like the reference; the a
     fused triplet basis x first basis projection (all layers) -> init_e -> update_v ->
     [update_e (A, B) -> update_v] x L -> graph readout
 """
+import os
 from math import sqrt
 
 import torch
@@ -244,13 +245,20 @@ class _DimeNetFamily(nn.Module):
             with torch.cuda.stream(side):
                 ops.sphere_update_v(v_in, ops.pack_update_v(holder), self.out_channels, out)
 
+        dense_tc = os.environ.get("DIG3D_DENSE", "tc") != "simt"
+        tc_cache = self.__dict__.setdefault("_tc_cache", {})
         e1, v_in = ops.sphere_init_e(z, g, rbf0, ops.pack_init_e(self.init_e), self.hidden_channels)
         node_mlp(v_in, self.init_v, v_all[0])
         for l in range(L):
             sbf_p, t_p = proj[l // 4]
-            e1, v_in = ops.sphere_update_e(e1, g, rbf0, sbf_p, t_p, 8 * (l % 4),
-                                           ops.pack_update_e(self.update_es[l], self._torsion),
-                                           self.hidden_channels, self.int_emb_size)
+            if dense_tc:      # tcgen05 3xTF32 dense chain (csrc/spherenet_tc.cu)
+                wt = ops.tc_pack_update_e(self.update_es[l], self._torsion, tc_cache)
+                e1, v_in, _, _ = ops.sphere_update_e_tc(e1, g, rbf0, sbf_p, t_p, 8 * (l % 4), wt,
+                                                        self.hidden_channels, self.int_emb_size)
+            else:             # exact-fp32 FFMA tile engine (csrc/spherenet.cu), kept as the validation twin
+                e1, v_in = ops.sphere_update_e(e1, g, rbf0, sbf_p, t_p, 8 * (l % 4),
+                                               ops.pack_update_e(self.update_es[l], self._torsion),
+                                               self.hidden_channels, self.int_emb_size)
             node_mlp(v_in, self.update_vs[l], v_all[l + 1])
         main.wait_stream(side)
         return ops.graph_readout(v_all, g.graph_ptr, g.n_graphs, g.n_nodes)

@@ -164,6 +164,33 @@ int dig3d_sphere_update_v(const float* v_in, int64_t n_nodes, int32_t out_channe
 int dig3d_graph_readout(const float* v, const int32_t* graph_ptr, int64_t n_graphs, int64_t n_nodes,
                         int32_t n_blocks, int32_t channels, float* u, void* stream);
 
+/* ------------------------------------------------------------------ update_e on the tensor cores (tcgen05)
+ * Same math as dig3d_sphere_update_e_a/_b with the dense chain on tcgen05.mma kind::tf32 (3xTF32 split,
+ * fp32 TMEM accumulators).  Weights are pre-split / pre-arranged once per parameter update:
+ *   dig3d_tc_pack: W [N,K] (nn.Linear layout) -> [K/32][hi|lo][8][N][4] floats (2*N*K floats per matrix). */
+int dig3d_tc_packed_floats(int32_t n, int32_t k);
+int dig3d_tc_pack(const float* const* weights, const int32_t* n, const int32_t* k, float* const* outs,
+                  int32_t count, void* stream);
+/* number of mbarrier waits that hit the bounded-spin limit since library load (0 = healthy) */
+int dig3d_tc_timeouts(void);
+
+typedef struct {
+  const float *p_ji, *b_ji, *p_kj, *b_kj;     /* packed lin_ji / lin_kj [128,128] + fp32 biases */
+  const float *p_down, *p_up;                 /* packed lin_down [64,128], lin_up [128,64] */
+  const float *p_res[6], *b_res[6];           /* packed residual linears, order as dig3d_update_e_weights */
+  const float *p_lin, *b_lin;
+  const float *w_rbf1, *w_rbf2, *w_rbf;       /* small fp32 matrices, nn.Linear layout */
+  const float *w_sbf2, *w_t2;                 /* [64,8] (w_t2 null => DimeNet++) */
+} dig3d_tc_update_e;
+
+int dig3d_sphere_update_e_a_tc(const float* e1, const float* rbf0, int64_t n_edges, const dig3d_tc_update_e* w,
+                               float* x_ji, float* x_down, void* stream);
+/* m_ws: [E,64] workspace for the triplet-gathered messages. */
+int dig3d_sphere_update_e_b_tc(const float* e1_in, const float* x_ji, const float* x_down, const float* rbf0,
+                               const float* sbf_p, const float* t_p, int32_t ld_p, const int32_t* src,
+                               const int32_t* dst, const int32_t* row_ptr, const int32_t* trip_ptr, int64_t n_edges,
+                               const dig3d_tc_update_e* w, float* m_ws, float* e1_out, float* v_in, void* stream);
+
 /* ------------------------------------------------------------------ SchNet
  * One interaction (update_e + update_v, schnet.py:29-35,53-59) for hidden_channels == num_filters in
  * {32, 64, 128}:  vlin = lin(v);  agg[i] = sum_{j->i} vlin[j] * mlp(gauss(d)) * C(d);
