@@ -9,8 +9,13 @@
 //     D = A_lo*W_hi + A_hi*W_lo + A_hi*W_hi with hi = rna_tf32(x), lo = rna_tf32(x - hi)
 //     (measured 3.7e-7 relative on the B200, tools/tc_test.cu).
 //   * A operand: the epilogue warps write the next layer's activations (already split into hi / lo planes)
-//     straight into the UMMA canonical K-major layout in shared memory; the fp32 residual / skip value
-//     of the row is parked in TMEM columns 128..255 (tcgen05.st/ld), so one A buffer (2 x 64 KB) suffices.
+//     straight into the UMMA canonical K-major layout in shared memory; the fp32 residual / skip value of
+//     the row stays in the registers of the epilogue thread that owns it, so one A buffer (2 x 64 KB) suffices.
+//   * The tensor core ACCUMULATES WITH TRUNCATION (measured: mean signed relative error -4.7e-7 after 24
+//     accumulations, tools/tc_bias.cu), a systematic shrink that adds up coherently over the chain and over the
+//     nodes of a molecule (3.7e-5 on the energy with one accumulator).  So each K-quarter of the main
+//     hi*hi term gets its OWN accumulator (TMEM columns q*128), opened by that quarter's two small correction
+//     terms, and the epilogue adds the four partials with round-to-nearest.
 //   * B operand: weights are pre-split and pre-arranged (dig3d_tc_pack) as [K/32][hi|lo][8][N][4] so that a
 //     K-chunk is ONE contiguous 32 KB block, streamed by cp.async.bulk (TMA engine) through a 2-stage
 //     mbarrier ring.
@@ -48,7 +53,12 @@ struct TcGemm {
   int K, N;
 };
 
-__device__ __forceinline__ float swish_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// x * sigmoid(x).  Default: libdevice expf + IEEE division (as accurate as the SIMT twin); the MUFU-only
+// variant (ex2.approx / rcp.approx) is ~1e-6 less accurate per activation and selectable for experiments.
+__device__ int g_fast_swish = 0;
+__device__ __forceinline__ float swish_sel(float x, int fast) {
+  return fast ? __fdividef(x, 1.0f + __expf(-x)) : __fdiv_rn(x, 1.0f + expf(-x));
+}
 
 // ---- producer: stream every K-chunk of every GEMM of the chain through the ring
 template <int NG>
@@ -87,9 +97,17 @@ __device__ __forceinline__ void tc_mma(TcSmem& s, const TcGemm (&g)[NG], uint32_
         const uint32_t b_off = (uint32_t)(ks * 2 * n * 16);
         const uint64_t dah = smem_desc(a_hi + a_off, TC_M * 16, 128), dal = smem_desc(a_lo + a_off, TC_M * 16, 128);
         const uint64_t dbh = smem_desc(w_hi + b_off, n * 16, 128), dbl = smem_desc(w_lo + b_off, n * 16, 128);
-        mma_tf32(tmem_d, dal, dbh, idesc, (c | ks) != 0);   // small terms first
-        mma_tf32(tmem_d, dah, dbl, idesc, 1);
-        mma_tf32(tmem_d, dah, dbh, idesc, 1);
+        // this K-quarter's corrections (magnitude 2^-11 of the main term) open its accumulator ...
+        mma_tf32(tmem_d + 128u * c, dal, dbh, idesc, ks != 0);
+        mma_tf32(tmem_d + 128u * c, dah, dbl, idesc, 1);
+      }
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint32_t a_off = (uint32_t)((c * 4 + ks) * 2 * TC_M * 16);
+        const uint32_t b_off = (uint32_t)(ks * 2 * n * 16);
+        const uint64_t dah = smem_desc(a_hi + a_off, TC_M * 16, 128);
+        const uint64_t dbh = smem_desc(w_hi + b_off, n * 16, 128);
+        mma_tf32(tmem_d + 128u * c, dah, dbh, idesc, 1);   // ... then its four hi*hi steps are added on top
       }
       mma_commit(&s.empty[st]);
     }
@@ -115,6 +133,27 @@ __device__ __forceinline__ void store_a(TcSmem& s, int row, int col, const float
     const int o = (((col + i) >> 2) * TC_M + row) * 4;
     *reinterpret_cast<float4*>(s.a_hi + o) = h;
     *reinterpret_cast<float4*>(s.a_lo + o) = l;
+  }
+}
+// acc[i] = RN sum of the K-quarter accumulators (NQ = K/32 of them) for 16 columns starting at `col`
+template <int NQ>
+__device__ __forceinline__ void load_acc(uint32_t tl, int col, float (&acc)[16]) {
+  uint32_t r0[16], r1[16];
+  tmem_ld16(tl + col, r0);
+  tmem_ld16(tl + 128 + col, r1);
+  if (NQ == 4) {
+    uint32_t r2[16], r3[16];
+    tmem_ld16(tl + 256 + col, r2);
+    tmem_ld16(tl + 384 + col, r3);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      acc[i] = __fadd_rn(__fadd_rn(__uint_as_float(r0[i]), __uint_as_float(r1[i])),
+                         __fadd_rn(__uint_as_float(r2[i]), __uint_as_float(r3[i])));
+  } else {
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = __fadd_rn(__uint_as_float(r0[i]), __uint_as_float(r1[i]));
   }
 }
 __device__ __forceinline__ void epi_done(TcSmem& s) {
@@ -211,7 +250,7 @@ sphere_update_e_a_tc_kernel(const float* __restrict__ e1, const float* __restric
     mbar_init(&s.a_ready, 256); mbar_init(&s.d_ready, 1);
     mbar_fence_init();
   }
-  if (warp == 0) tmem_alloc(&s.tmem_base, 256);
+  if (warp == 0) tmem_alloc(&s.tmem_base, 512);
   for (int i = tid; i < 2 * 128; i += TC_THREADS) s.bias[i / 128][i % 128] = __ldg(P.g[i / 128].bias + i % 128);
   for (int i = tid; i < 128 * 8; i += TC_THREADS) s.wr[i] = __ldg(P.w_rbf2 + i);      // [128][8]
   for (int i = tid; i < 64; i += TC_THREADS) s.wr1[i] = (i % 8 < 6) ? __ldg(P.w_rbf1 + (i / 8) * 6 + i % 8) : 0.f;
@@ -224,6 +263,7 @@ sphere_update_e_a_tc_kernel(const float* __restrict__ e1, const float* __restric
     if (tid == 32) tc_mma(s, P.g, s.tmem_base);
   } else {
     const EpiCtx c = epi_ctx(s);
+    const int fast = g_fast_swish;
     const bool valid = c.row < rows;
     const size_t ge = (size_t)(e0 + c.row);
     const uint32_t tl = c.tm + ((uint32_t)c.lane_base << 16);
@@ -260,17 +300,16 @@ sphere_update_e_a_tc_kernel(const float* __restrict__ e1, const float* __restric
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) {
       const int col = c.half * 64 + cc * 16;
-      uint32_t r[16];
-      tmem_ld16(tl + col, r);
-      tmem_ld_wait();
+      float r[16];
+      load_acc<4>(tl, col, r);
       if (valid) {
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
           float4 o;
-          o.x = swish_fast(__uint_as_float(r[i]) + s.bias[0][col + i]);
-          o.y = swish_fast(__uint_as_float(r[i + 1]) + s.bias[0][col + i + 1]);
-          o.z = swish_fast(__uint_as_float(r[i + 2]) + s.bias[0][col + i + 2]);
-          o.w = swish_fast(__uint_as_float(r[i + 3]) + s.bias[0][col + i + 3]);
+          o.x = swish_sel(r[i] + s.bias[0][col + i], fast);
+          o.y = swish_sel(r[i + 1] + s.bias[0][col + i + 1], fast);
+          o.z = swish_sel(r[i + 2] + s.bias[0][col + i + 2], fast);
+          o.w = swish_sel(r[i + 3] + s.bias[0][col + i + 3], fast);
           *reinterpret_cast<float4*>(x_ji + ge * 128 + col + i) = o;
         }
       }
@@ -282,16 +321,15 @@ sphere_update_e_a_tc_kernel(const float* __restrict__ e1, const float* __restric
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) {
       const int col = c.half * 64 + cc * 16;
-      uint32_t r[16];
-      tmem_ld16(tl + col, r);
-      tmem_ld_wait();
+      float r[16];
+      load_acc<4>(tl, col, r);
       float v[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         float gate = 0.f;
 #pragma unroll
         for (int m = 0; m < 8; ++m) gate = fmaf(s.wr[(col + i) * 8 + m], r8[m], gate);
-        v[i] = swish_fast(__uint_as_float(r[i]) + s.bias[1][col + i]) * gate;
+        v[i] = swish_sel(r[i] + s.bias[1][col + i], fast) * gate;
       }
       store_a(s, c.row, col, v);
     }
@@ -302,15 +340,14 @@ sphere_update_e_a_tc_kernel(const float* __restrict__ e1, const float* __restric
 #pragma unroll
     for (int cc = 0; cc < 2; ++cc) {
       const int col = c.half * 32 + cc * 16;
-      uint32_t r[16];
-      tmem_ld16(tl + col, r);
-      tmem_ld_wait();
+      float r[16];
+      load_acc<4>(tl, col, r);
       if (valid) {
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
           float4 o;
-          o.x = swish_fast(__uint_as_float(r[i])); o.y = swish_fast(__uint_as_float(r[i + 1]));
-          o.z = swish_fast(__uint_as_float(r[i + 2])); o.w = swish_fast(__uint_as_float(r[i + 3]));
+          o.x = swish_sel(r[i], fast); o.y = swish_sel(r[i + 1], fast);
+          o.z = swish_sel(r[i + 2], fast); o.w = swish_sel(r[i + 3], fast);
           *reinterpret_cast<float4*>(x_down + ge * 64 + col + i) = o;
         }
       }
@@ -318,7 +355,7 @@ sphere_update_e_a_tc_kernel(const float* __restrict__ e1, const float* __restric
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 0) tmem_dealloc(s.tmem_base, 256);
+  if (warp == 0) tmem_dealloc(s.tmem_base, 512);
 }
 
 // ---------------------------------------------------------------------------------- update_e part B (tensor)
@@ -341,7 +378,7 @@ sphere_update_e_b_tc_kernel(const float* __restrict__ m, const float* __restrict
     mbar_init(&s.a_ready, 256); mbar_init(&s.d_ready, 1);
     mbar_fence_init();
   }
-  if (warp == 0) tmem_alloc(&s.tmem_base, 256);
+  if (warp == 0) tmem_alloc(&s.tmem_base, 512);
   for (int i = tid; i < 8 * 128; i += TC_THREADS) {
     const float* b = P.g[i / 128].bias;
     s.bias[i / 128][i % 128] = b ? __ldg(b + i % 128) : 0.f;
@@ -357,6 +394,7 @@ sphere_update_e_b_tc_kernel(const float* __restrict__ m, const float* __restrict
     if (tid == 32) tc_mma(s, P.g, s.tmem_base);
   } else {
     const EpiCtx c = epi_ctx(s);
+    const int fast = g_fast_swish;
     const bool valid = c.row < rows;
     const size_t ge = (size_t)(e0 + c.row);
     const uint32_t tl = c.tm + ((uint32_t)c.lane_base << 16);
@@ -379,6 +417,8 @@ sphere_update_e_b_tc_kernel(const float* __restrict__ m, const float* __restrict
     //   q=2,5: h = stash + act(lin2(t))                      -> A, stash      (q=2: stash not needed afterwards)
     //   q=3: h = act(lin(h)) + e1_in                         -> A, stash
     //   q=7: h = stash + act(lin2(t))                        -> e1_out, e2 tile
+    float stash[64];     // fp32 residual of this thread's (row, 64 columns), lives in registers
+#pragma unroll
     for (int q = 0; q < 8; ++q) {
       mbar_wait(&s.d_ready, q & 1);
       tc_fence_after();
@@ -387,16 +427,14 @@ sphere_update_e_b_tc_kernel(const float* __restrict__ m, const float* __restrict
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
         const int col = c.half * 64 + cc * 16;
-        uint32_t r[16], st[16];
-        tmem_ld16(tl + col, r);
-        if (add_stash) tmem_ld16(tl + 128 + col, st);
-        tmem_ld_wait();
+        float r[16];
+        if (q == 0) load_acc<2>(tl, col, r); else load_acc<4>(tl, col, r);
         float v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = swish_fast(__uint_as_float(r[i]) + s.bias[q][col + i]);
+        for (int i = 0; i < 16; ++i) v[i] = swish_sel(r[i] + s.bias[q][col + i], fast);
         if (add_stash) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += __uint_as_float(st[i]);
+          for (int i = 0; i < 16; ++i) v[i] += stash[cc * 16 + i];
         }
         if (q == 0 || q == 3) {
           const float* gsrc = (q == 0 ? x_ji : e1_in) + ge * 128 + col;
@@ -410,8 +448,7 @@ sphere_update_e_b_tc_kernel(const float* __restrict__ m, const float* __restrict
           store_a(s, c.row, col, v);
           if (to_stash) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) st[i] = __float_as_uint(v[i]);
-            tmem_st16(tl + 128 + col, st);
+            for (int i = 0; i < 16; ++i) stash[cc * 16 + i] = v[i];
           }
         } else {
           // e1_out and e2 = lin_rbf(rbf0) * e1 (tile staged over the A planes)   spherenet.py:180
@@ -432,10 +469,7 @@ sphere_update_e_b_tc_kernel(const float* __restrict__ m, const float* __restrict
           }
         }
       }
-      if (q < 7) {
-        if (to_stash) tmem_st_wait();
-        epi_done(s);
-      }
+      if (q < 7) epi_done(s);
     }
     tc_fence_before();
     epi_bar();
@@ -459,7 +493,7 @@ sphere_update_e_b_tc_kernel(const float* __restrict__ m, const float* __restrict
     }
   }
   __syncthreads();
-  if (warp == 0) tmem_dealloc(s.tmem_base, 256);
+  if (warp == 0) tmem_dealloc(s.tmem_base, 512);
 }
 
 static int tc_smem_attr(const void* fn, size_t bytes) {
@@ -496,6 +530,13 @@ int dig3d_tc_pack(const float* const* weights, const int32_t* n, const int32_t* 
   return DIG3D_OK;
 }
 
+int dig3d_tc_set_fast_swish(int32_t on) {
+  int v = on ? 1 : 0;
+  cudaError_t e = cudaMemcpyToSymbol(g_fast_swish, &v, sizeof(v));
+  if (e != cudaSuccess) { set_error("tc_set_fast_swish: %s", cudaGetErrorString(e)); return DIG3D_ECUDA; }
+  return DIG3D_OK;
+}
+
 int dig3d_tc_timeouts(void) {
   unsigned int v = 0;
   cudaMemcpyFromSymbol(&v, tc05::g_mbar_timeout, sizeof(v));
@@ -519,23 +560,32 @@ int dig3d_sphere_update_e_a_tc(const float* e1, const float* rbf0, int64_t n_edg
   return DIG3D_OK;
 }
 
-int dig3d_sphere_update_e_b_tc(const float* e1_in, const float* x_ji, const float* x_down, const float* rbf0,
-                               const float* sbf_p, const float* t_p, int32_t ld_p, const int32_t* src,
-                               const int32_t* dst, const int32_t* row_ptr, const int32_t* trip_ptr, int64_t n_edges,
-                               const dig3d_tc_update_e* w, float* m_ws, float* e1_out, float* v_in, void* stream) {
-  DIG3D_REQUIRE(e1_in && x_ji && x_down && rbf0 && sbf_p && src && dst && row_ptr && trip_ptr && w && m_ws && e1_out &&
-                    v_in, "sphere_update_e_b_tc: null pointer");
-  DIG3D_REQUIRE((t_p != nullptr) == (w->w_t2 != nullptr), "sphere_update_e_b_tc: t_p and w_t2 must agree");
+int dig3d_sphere_triplet_gather(const float* x_down, const float* sbf_p, const float* t_p, int32_t ld_p,
+                                const int32_t* src, const int32_t* dst, const int32_t* row_ptr,
+                                const int32_t* trip_ptr, int64_t n_edges, const float* w_sbf2, const float* w_t2,
+                                float* m, void* stream) {
+  DIG3D_REQUIRE(x_down && sbf_p && src && dst && row_ptr && trip_ptr && w_sbf2 && m, "sphere_triplet_gather: null pointer");
+  DIG3D_REQUIRE((t_p != nullptr) == (w_t2 != nullptr), "sphere_triplet_gather: t_p and w_t2 must agree");
+  DIG3D_REQUIRE(ld_p % 4 == 0, "sphere_triplet_gather: ld_p must be a multiple of 4");
   if (n_edges == 0) return DIG3D_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int gblocks = ceil_div(n_edges * 32, 256);
   if (t_p)
     sphere_triplet_gather_kernel<true><<<gblocks, 256, 0, st>>>(x_down, sbf_p, t_p, ld_p, src, dst, row_ptr, trip_ptr,
-                                                               (int)n_edges, w->w_sbf2, w->w_t2, m_ws);
+                                                               (int)n_edges, w_sbf2, w_t2, m);
   else
     sphere_triplet_gather_kernel<false><<<gblocks, 256, 0, st>>>(x_down, sbf_p, t_p, ld_p, src, dst, row_ptr, trip_ptr,
-                                                                (int)n_edges, w->w_sbf2, w->w_t2, m_ws);
+                                                                (int)n_edges, w_sbf2, w_t2, m);
   DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_sphere_update_e_b_tc(const float* m, const float* e1_in, const float* x_ji, const float* rbf0,
+                               const int32_t* dst, int64_t n_edges, const dig3d_tc_update_e* w, float* e1_out,
+                               float* v_in, void* stream) {
+  DIG3D_REQUIRE(m && e1_in && x_ji && rbf0 && dst && w && e1_out && v_in, "sphere_update_e_b_tc: null pointer");
+  if (n_edges == 0) return DIG3D_OK;
+  cudaStream_t st = (cudaStream_t)stream;
   TcBParams P;
   P.g[0] = {w->p_up, nullptr, 64, 128};
   for (int i = 0; i < 2; ++i) P.g[1 + i] = {w->p_res[i], w->b_res[i], 128, 128};
@@ -545,7 +595,7 @@ int dig3d_sphere_update_e_b_tc(const float* e1_in, const float* x_ji, const floa
   int rc = tc_smem_attr((const void*)sphere_update_e_b_tc_kernel, sizeof(TcSmem));
   if (rc) return rc;
   sphere_update_e_b_tc_kernel<<<ceil_div(n_edges, TC_M), TC_THREADS, sizeof(TcSmem), st>>>(
-      m_ws, x_ji, e1_in, rbf0, dst, (int)n_edges, P, e1_out, v_in);
+      m, x_ji, e1_in, rbf0, dst, (int)n_edges, P, e1_out, v_in);
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
 }

@@ -420,9 +420,15 @@ def sphere_update_e_tc(e1, g, rbf0, sbf_p, t_p, col0, w, hidden, int_emb):
         call("dig3d_sphere_update_e_a_tc", _p(e1), _p(rbf0), e, ctypes.byref(w), _p(x_ji), _p(x_down), st)
         sp = ctypes.c_void_p(sbf_p.data_ptr() + 4 * col0)
         tp = ctypes.c_void_p(t_p.data_ptr() + 4 * col0) if t_p is not None else None
-        call("dig3d_sphere_update_e_b_tc", _p(e1), _p(x_ji), _p(x_down), _p(rbf0), sp, tp, 32, _p(g.src), _p(g.dst),
-             _p(g.row_ptr), _p(g.trip_ptr), e, ctypes.byref(w), _p(m_ws), _p(e1_out), _p(v_in), st)
+        call("dig3d_sphere_triplet_gather", _p(x_down), sp, tp, 32, _p(g.src), _p(g.dst), _p(g.row_ptr),
+             _p(g.trip_ptr), e, w.w_sbf2, w.w_t2, _p(m_ws), st)
+        call("dig3d_sphere_update_e_b_tc", _p(m_ws), _p(e1), _p(x_ji), _p(rbf0), _p(g.dst), e, ctypes.byref(w),
+             _p(e1_out), _p(v_in), st)
     return e1_out, v_in, x_ji, x_down
+
+
+def tc_set_fast_swish(on):
+    call("dig3d_tc_set_fast_swish", int(bool(on)))
 
 
 def tc_timeouts():

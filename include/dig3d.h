@@ -185,11 +185,18 @@ typedef struct {
 
 int dig3d_sphere_update_e_a_tc(const float* e1, const float* rbf0, int64_t n_edges, const dig3d_tc_update_e* w,
                                float* x_ji, float* x_down, void* stream);
-/* m_ws: [E,64] workspace for the triplet-gathered messages. */
-int dig3d_sphere_update_e_b_tc(const float* e1_in, const float* x_ji, const float* x_down, const float* rbf0,
-                               const float* sbf_p, const float* t_p, int32_t ld_p, const int32_t* src,
-                               const int32_t* dst, const int32_t* row_ptr, const int32_t* trip_ptr, int64_t n_edges,
-                               const dig3d_tc_update_e* w, float* m_ws, float* e1_out, float* v_in, void* stream);
+/* m[e] = sum over the triplets of edge e of x_down[kj] * lin_sbf2(sbf_p) * lin_t2(t_p)   (spherenet.py:163-171);
+ * SIMT, one warp per edge, register accumulation over the contiguous triplet range (no atomics). */
+int dig3d_sphere_triplet_gather(const float* x_down, const float* sbf_p, const float* t_p, int32_t ld_p,
+                                const int32_t* src, const int32_t* dst, const int32_t* row_ptr,
+                                const int32_t* trip_ptr, int64_t n_edges, const float* w_sbf2, const float* w_t2,
+                                float* m, void* stream);
+/* lin_up + residual stack + lin (spherenet.py:172-180) on tcgen05; writes e1_out, ACCUMULATES e2 into v_in. */
+int dig3d_sphere_update_e_b_tc(const float* m, const float* e1_in, const float* x_ji, const float* rbf0,
+                               const int32_t* dst, int64_t n_edges, const dig3d_tc_update_e* w, float* e1_out,
+                               float* v_in, void* stream);
+/* 1: MUFU-only swish in the tensor-path epilogues (faster, ~1e-6 less accurate); default 0. */
+int dig3d_tc_set_fast_swish(int32_t on);
 
 /* ------------------------------------------------------------------ SchNet
  * One interaction (update_e + update_v, schnet.py:29-35,53-59) for hidden_channels == num_filters in

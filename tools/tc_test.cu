@@ -33,12 +33,12 @@ struct Smem {
 };
 
 __global__ void __launch_bounds__(192, 1) tc_kernel(const float* a, const float* w_hi, const float* w_lo, float* d1,
-                                                   float* d3, float* stash_out) {
+                                                   float* d3, float* stash_out, float* d4) {
   extern __shared__ __align__(1024) unsigned char raw[];
   Smem& s = *reinterpret_cast<Smem*>(raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) { mbar_init(&s.bar_w, 1); mbar_init(&s.bar_d, 1); mbar_fence_init(); }
-  if (warp == 4) tmem_alloc(&s.tmem_base, 256);
+  if (warp == 4) tmem_alloc(&s.tmem_base, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -82,6 +82,21 @@ __global__ void __launch_bounds__(192, 1) tc_kernel(const float* a, const float*
     }
     mma_commit(&s.bar_d);
   }
+  if (tid < 128) {   // A operand copies in TMEM: hi at columns [256, 256+K), lo at [384, 384+K)
+    const uint32_t lane_addr = tm + ((uint32_t)(warp * 32) << 16);
+    for (int k = 0; k < K; k += 16) {
+      uint32_t h[16], l[16];
+      for (int i = 0; i < 16; ++i) {
+        float hh, ll;
+        split_tf32(a[(size_t)tid * K + k + i], hh, ll);
+        h[i] = __float_as_uint(hh); l[i] = __float_as_uint(ll);
+      }
+      tmem_st16(lane_addr + 256 + k, h);
+      tmem_st16(lane_addr + 384 + k, l);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+  }
   if (tid < 128) {
     mbar_wait(&s.bar_d, 0);
     tc_fence_after();
@@ -104,7 +119,33 @@ __global__ void __launch_bounds__(192, 1) tc_kernel(const float* a, const float*
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tm, 256);
+  tc_fence_after();
+  // second round: 4-term product with the A operand read from TMEM (TS form) into columns [0,128)
+  if (tid == 160) {
+    for (int term = 0; term < 4; ++term) {
+      const uint32_t ta = tm + (term == 0 || term == 1 ? 384u : 256u);      // lo, lo, hi, hi
+      const float* pb = (term == 0 || term == 2) ? s.w_lo : s.w_hi;          // lo*lo, lo*hi, hi*lo, hi*hi
+      for (int ks = 0; ks < K / 8; ++ks) {
+        uint64_t db = smem_desc(smem_u32(pb) + ks * 2 * N * 16, N * 16, 128);
+        mma_tf32_ts(tm, ta + ks * 8, db, idesc, (term | ks) != 0);
+      }
+    }
+    mma_commit(&s.bar_d);
+  }
+  if (tid < 128) {
+    mbar_wait(&s.bar_d, 1);
+    tc_fence_after();
+    const uint32_t lane_addr = tm + ((uint32_t)(warp * 32) << 16);
+    for (int c = 0; c < 128; c += 16) {
+      uint32_t r[16];
+      tmem_ld16(lane_addr + c, r);
+      tmem_ld_wait();
+      for (int i = 0; i < 16; ++i) d4[(size_t)tid * N + c + i] = __uint_as_float(r[i]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tm, 512);
 }
 
 int main() {
@@ -112,24 +153,25 @@ int main() {
   srand(1);
   for (auto& x : a) x = (float)rand() / RAND_MAX * 2 - 1;
   for (auto& x : w) x = (float)rand() / RAND_MAX * 2 - 1;
-  float *da, *dw, *dhi, *dlo, *d1, *d3, *st;
+  float *da, *dw, *dhi, *dlo, *d1, *d3, *st, *d4;
   cudaMalloc(&da, M * K * 4); cudaMalloc(&dw, N * K * 4); cudaMalloc(&dhi, N * K * 4); cudaMalloc(&dlo, N * K * 4);
-  cudaMalloc(&d1, M * N * 4); cudaMalloc(&d3, M * N * 4); cudaMalloc(&st, 128 * 16 * 4);
+  cudaMalloc(&d1, M * N * 4); cudaMalloc(&d3, M * N * 4); cudaMalloc(&st, 128 * 16 * 4); cudaMalloc(&d4, M * N * 4);
   cudaMemcpy(da, a.data(), M * K * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(dw, w.data(), N * K * 4, cudaMemcpyHostToDevice);
   pack_w<<<(N * K + 255) / 256, 256>>>(dw, dhi, dlo);
   cudaFuncSetAttribute(tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-  tc_kernel<<<1, 192, sizeof(Smem)>>>(da, dhi, dlo, d1, d3, st);
+  tc_kernel<<<1, 192, sizeof(Smem)>>>(da, dhi, dlo, d1, d3, st, d4);
   cudaError_t e = cudaDeviceSynchronize();
   printf("kernel: %s\n", cudaGetErrorString(e));
   unsigned int to = 0;
   cudaMemcpyFromSymbol(&to, g_mbar_timeout, sizeof(to));
   printf("mbarrier timeouts: %u\n", to);
-  std::vector<float> h1(M * N), h3(M * N), hs(128 * 16);
+  std::vector<float> h1(M * N), h3(M * N), hs(128 * 16), h4(M * N);
+  cudaMemcpy(h4.data(), d4, M * N * 4, cudaMemcpyDeviceToHost);
   cudaMemcpy(h1.data(), d1, M * N * 4, cudaMemcpyDeviceToHost);
   cudaMemcpy(h3.data(), d3, M * N * 4, cudaMemcpyDeviceToHost);
   cudaMemcpy(hs.data(), st, 128 * 16 * 4, cudaMemcpyDeviceToHost);
-  double e1 = 0, e3 = 0, ref_max = 0;
+  double e1 = 0, e3 = 0, e4 = 0, ef = 0, ref_max = 0;
   for (int i = 0; i < M; ++i)
     for (int j = 0; j < N; ++j) {
       double r = 0;
@@ -137,11 +179,14 @@ int main() {
       ref_max = fmax(ref_max, fabs(r));
       e1 = fmax(e1, fabs(h1[i * N + j] - r));
       e3 = fmax(e3, fabs(h3[i * N + j] - r));
+      e4 = fmax(e4, fabs(h4[i * N + j] - r));
+      { float f = 0; for (int k = 0; k < K; ++k) f = fmaf(a[i * K + k], w[j * K + k], f); ef = fmax(ef, fabs(f - r)); }
     }
   int bad = 0;
   for (int t = 0; t < 128; ++t) for (int i = 0; i < 16; ++i) bad += hs[t * 16 + i] != (float)(t * 1000 + i);
   printf("ref max %.4f | 1xTF32 max abs err %.3e (rel %.3e) | 3xTF32 max abs err %.3e (rel %.3e) | stash mismatches %d\n",
          ref_max, e1, e1 / ref_max, e3, e3 / ref_max, bad);
+  printf("4-term TS (A in TMEM) max abs err %.3e (rel %.3e) | plain fp32 fma chain rel %.3e\n", e4, e4 / ref_max, ef / ref_max);
   printf("sample d3[0][0..3] = %f %f %f %f\n", h3[0], h3[1], h3[2], h3[3]);
   return (e == cudaSuccess && to == 0 && e3 / ref_max < 5e-6 && bad == 0) ? 0 : 1;
 }
