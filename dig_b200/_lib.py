@@ -80,6 +80,7 @@ SIGNATURES = {
     "dig3d_sphere_triplet_gather": [P, P, P, c_int32, P, P, P, P, c_int64, P, P, P, P],
     "dig3d_sphere_update_e_b_tc": [P, P, P, P, P, c_int64, POINTER(TcUpdateE), P, P, P],
     "dig3d_tc_set_fast_swish": [c_int32],
+    "dig3d_tc_trace": [c_int32, P],
     "dig3d_schnet_block": [P, c_int64, P, P, P, c_int64, P, c_int32, c_double, c_double, c_int32, c_int32,
                            POINTER(SchnetBlockWeights), P, P, P, P],
     "dig3d_schnet_readout": [P, c_int64, c_int32, P, P, P, P, c_int32, P, P],

@@ -19,8 +19,9 @@
 //   * B operand: weights are pre-split and pre-arranged (dig3d_tc_pack) as [K/32][hi|lo][8][N][4] so that a
 //     K-chunk is ONE contiguous 32 KB block, streamed by cp.async.bulk (TMA engine) through a 2-stage
 //     mbarrier ring.
-//   * Warp roles: warp 0 = bulk-copy producer, warp 1 = MMA issuer (one elected thread), warps 2..9 =
-//     epilogue (TMEM -> registers -> bias / swish / residual -> split -> shared memory).
+//   * Warp roles: warp 0 = bulk-copy producer, warp 1 = MMA issuer (one elected thread), warps 2..17 =
+//     epilogue (TMEM -> registers -> bias / swish / residual -> split -> shared memory); four warps share a
+//     TMEM lane quarter and take 32 columns each, so four warps per scheduler hide the epilogue's latencies.
 //
 // The latency-bound triplet gather (spherenet.py:163-171) runs in its own high-occupancy SIMT kernel
 // (sphere_triplet_gather_kernel) and hands m[E,64] to the chain.
@@ -31,7 +32,9 @@ namespace dig3d {
 using namespace tc05;
 
 constexpr int TC_M = 128;
-constexpr int TC_THREADS = 320;
+constexpr int TC_EPI_WARPS = 16;
+constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
+constexpr int TC_THREADS = 64 + TC_EPI_THREADS;   // warp 0 producer, warp 1 MMA issuer, 16 epilogue warps
 constexpr int TC_STAGES = 2;
 constexpr int TC_STAGE_FLOATS = 2 * 8 * 128 * 4;   // hi + lo planes of a K=32 chunk with N = 128
 
@@ -53,9 +56,13 @@ struct TcGemm {
   int K, N;
 };
 
-// x * sigmoid(x).  Default: libdevice expf + IEEE division (as accurate as the SIMT twin); the MUFU-only
-// variant (ex2.approx / rcp.approx) is ~1e-6 less accurate per activation and selectable for experiments.
-__device__ int g_fast_swish = 0;
+// x * sigmoid(x).  Default: MUFU ex2/rcp approximations (measured on the B200: no effect on the energy error,
+// 3.9e-6 vs 4.4e-6, and a much shorter epilogue); libdevice expf + IEEE division selectable for experiments.
+__device__ int g_fast_swish = 1;
+// optional timeline probe: CTA 0 of the tensor kernels records clock64() at protocol points (tools/gpu_tc_timeline.py)
+__device__ long long g_tc_trace[64];
+__device__ int g_tc_trace_on = 0;
+#define TC_TRACE(slot) do { if (g_tc_trace_on && blockIdx.x == 0) g_tc_trace[(slot)] = clock64(); } while (0)
 __device__ __forceinline__ float swish_sel(float x, int fast) {
   return fast ? __fdividef(x, 1.0f + __expf(-x)) : __fdiv_rn(x, 1.0f + expf(-x));
 }
@@ -70,6 +77,7 @@ __device__ __forceinline__ void tc_producer(TcSmem& s, const TcGemm (&g)[NG]) {
     for (int c = 0; c < chunks; ++c, ++it) {
       const int st = it % TC_STAGES;
       mbar_wait(&s.empty[st], ((it / TC_STAGES) & 1) ^ 1);
+      if (it < 12) TC_TRACE(40 + it);
       mbar_arrive_expect_tx(&s.full[st], bytes);
       bulk_g2s(s.w[st], g[q].w + (size_t)c * (bytes / 4), bytes, &s.full[st]);
     }
@@ -86,10 +94,12 @@ __device__ __forceinline__ void tc_mma(TcSmem& s, const TcGemm (&g)[NG], uint32_
     const uint32_t idesc = idesc_tf32(TC_M, n);
     mbar_wait(&s.a_ready, q & 1);
     tc_fence_after();
+    if (q < 4) TC_TRACE(8 + 4 * q);            // A ready
     for (int c = 0; c < chunks; ++c, ++it) {
       const int st = it % TC_STAGES;
       mbar_wait(&s.full[st], (it / TC_STAGES) & 1);
       tc_fence_after();
+      if (q < 4 && c == 0) TC_TRACE(9 + 4 * q);   // first weight chunk landed
       const uint32_t w_hi = smem_u32(s.w[st]), w_lo = w_hi + 8u * n * 16u;
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
@@ -112,17 +122,18 @@ __device__ __forceinline__ void tc_mma(TcSmem& s, const TcGemm (&g)[NG], uint32_
       mma_commit(&s.empty[st]);
     }
     mma_commit(&s.d_ready);
+    if (q < 4) TC_TRACE(10 + 4 * q);           // all MMAs of the GEMM issued
   }
 }
 
 // ---- epilogue helpers (thread = one row, 64 or 32 columns in 16-column pieces)
 struct EpiCtx {
-  int row, half, lane_base;   // row in tile, column half (0/1), TMEM lane quarter base
+  int row, part, lane_base;   // row in tile, column part (0..3), TMEM lane quarter base
   uint32_t tm;                // TMEM base
 };
 __device__ __forceinline__ EpiCtx epi_ctx(const TcSmem& s) {
   const int et = threadIdx.x - 64, we = et >> 5, lane = et & 31;
-  const int q = (we + 2) & 3;
+  const int q = (we + 2) & 3;   // a warp may only touch TMEM lanes [32*(warp%4), +32)
   return {32 * q + lane, we >> 2, 32 * q, s.tmem_base};
 }
 __device__ __forceinline__ void store_a(TcSmem& s, int row, int col, const float (&v)[16]) {
@@ -161,7 +172,7 @@ __device__ __forceinline__ void epi_done(TcSmem& s) {
   tc_fence_before();
   mbar_arrive(&s.a_ready);
 }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory"); }
 
 // ---------------------------------------------------------------------------------- triplet gather (SIMT)
 // m[e] = sum_{t in trip(e)} x_down[kj(t)] * lin_sbf2(sbf_p[t]) * lin_t2(t_p[t])      spherenet.py:163-171
@@ -185,30 +196,50 @@ sphere_triplet_gather_kernel(const float* __restrict__ x_down, const float* __re
     }
   const int j = src[e], i = dst[e];
   const int base = row_ptr[j], d = row_ptr[j + 1] - base;
-  int t = trip_ptr[e];
+  // position of i among j's in-neighbours (d if absent): triplet r of this edge uses slot r + (r >= p_i)
+  int p_i = d;
+  for (int s0 = 0; s0 < d; s0 += 32) {
+    const int sl = s0 + lane;
+    const unsigned hit = __ballot_sync(0xffffffffu, sl < d && src[base + sl] == i);
+    if (hit) p_i = s0 + __ffs(hit) - 1;
+  }
+  const int t0 = trip_ptr[e], nt = d - (p_i < d ? 1 : 0);
   float a0 = 0.f, a1 = 0.f;
-  for (int sl = 0; sl < d; ++sl) {
-    const int kj = base + sl;
-    if (src[kj] == i) continue;
-    const float4* sp = reinterpret_cast<const float4*>(sbf_p + (size_t)t * ld_p);
-    const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
-    const float x0 = __ldg(x_down + (size_t)kj * 64 + lane), x1 = __ldg(x_down + (size_t)kj * 64 + lane + 32);
-    const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    float g0 = 0.f, g1 = 0.f;
+  // independent iterations, four triplets in flight per warp
+  for (int r0 = 0; r0 < nt; r0 += 4) {
+    float4 s0[4], s1[4], q0[4], q1[4];
+    float x0[4], x1[4];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) { g0 = fmaf(ws2[0][q], sv[q], g0); g1 = fmaf(ws2[1][q], sv[q], g1); }
-    float m0 = __fmul_rn(x0, g0), m1 = __fmul_rn(x1, g1);
-    if (TORSION) {
-      const float4* tp = reinterpret_cast<const float4*>(t_p + (size_t)t * ld_p);
-      const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1);
-      const float tv[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-      float h0 = 0.f, h1 = 0.f;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) { h0 = fmaf(wt2[0][q], tv[q], h0); h1 = fmaf(wt2[1][q], tv[q], h1); }
-      m0 = __fmul_rn(m0, h0); m1 = __fmul_rn(m1, h1);
+    for (int u = 0; u < 4; ++u) {
+      const int r = min(r0 + u, nt - 1);
+      const int kj = base + r + (r >= p_i ? 1 : 0);
+      const float4* sp = reinterpret_cast<const float4*>(sbf_p + (size_t)(t0 + r) * ld_p);
+      s0[u] = __ldg(sp); s1[u] = __ldg(sp + 1);
+      if (TORSION) {
+        const float4* tp = reinterpret_cast<const float4*>(t_p + (size_t)(t0 + r) * ld_p);
+        q0[u] = __ldg(tp); q1[u] = __ldg(tp + 1);
+      }
+      x0[u] = __ldg(x_down + (size_t)kj * 64 + lane);
+      x1[u] = __ldg(x_down + (size_t)kj * 64 + lane + 32);
     }
-    a0 += m0; a1 += m1;
-    ++t;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (r0 + u < nt) {
+        const float sv[8] = {s0[u].x, s0[u].y, s0[u].z, s0[u].w, s1[u].x, s1[u].y, s1[u].z, s1[u].w};
+        float g0 = 0.f, g1 = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { g0 = fmaf(ws2[0][q], sv[q], g0); g1 = fmaf(ws2[1][q], sv[q], g1); }
+        float m0 = __fmul_rn(x0[u], g0), m1 = __fmul_rn(x1[u], g1);
+        if (TORSION) {
+          const float tv[8] = {q0[u].x, q0[u].y, q0[u].z, q0[u].w, q1[u].x, q1[u].y, q1[u].z, q1[u].w};
+          float h0 = 0.f, h1 = 0.f;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { h0 = fmaf(wt2[0][q], tv[q], h0); h1 = fmaf(wt2[1][q], tv[q], h1); }
+          m0 = __fmul_rn(m0, h0); m1 = __fmul_rn(m1, h1);
+        }
+        a0 += m0; a1 += m1;
+      }
+    }
   }
   m[(size_t)e * 64 + lane] = a0;
   m[(size_t)e * 64 + lane + 32] = a1;
@@ -247,7 +278,7 @@ sphere_update_e_a_tc_kernel(const float* __restrict__ e1, const float* __restric
   const int e0 = blockIdx.x * TC_M, rows = min(TC_M, n_edges - e0);
   if (tid == 0) {
     for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
-    mbar_init(&s.a_ready, 256); mbar_init(&s.d_ready, 1);
+    mbar_init(&s.a_ready, TC_EPI_THREADS); mbar_init(&s.d_ready, 1);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(&s.tmem_base, 512);
@@ -255,8 +286,10 @@ sphere_update_e_a_tc_kernel(const float* __restrict__ e1, const float* __restric
   for (int i = tid; i < 128 * 8; i += TC_THREADS) s.wr[i] = __ldg(P.w_rbf2 + i);      // [128][8]
   for (int i = tid; i < 64; i += TC_THREADS) s.wr1[i] = (i % 8 < 6) ? __ldg(P.w_rbf1 + (i / 8) * 6 + i % 8) : 0.f;
   tc_fence_before();
+  if (tid == 64) TC_TRACE(0);
   __syncthreads();
   tc_fence_after();
+  if (tid == 64) TC_TRACE(1);
   if (warp == 0) {
     if (tid == 0) tc_producer(s, P.g);
   } else if (warp == 1) {
@@ -269,8 +302,8 @@ sphere_update_e_a_tc_kernel(const float* __restrict__ e1, const float* __restric
     const uint32_t tl = c.tm + ((uint32_t)c.lane_base << 16);
     // A0 = e1 tile
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-      const int col = c.half * 64 + cc * 16;
+    for (int cc = 0; cc < 2; ++cc) {
+      const int col = c.part * 32 + cc * 16;
       float v[16];
 #pragma unroll
       for (int i = 0; i < 16; i += 4) {
@@ -293,13 +326,15 @@ sphere_update_e_a_tc_kernel(const float* __restrict__ e1, const float* __restric
         r8[m] = a;
       }
     }
+    if (tid == 64) TC_TRACE(2);
     epi_done(s);
     // G0: x_ji = act(lin_ji(e1))                                                spherenet.py:154
     mbar_wait(&s.d_ready, 0);
     tc_fence_after();
+    if (tid == 64) TC_TRACE(3);
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-      const int col = c.half * 64 + cc * 16;
+    for (int cc = 0; cc < 2; ++cc) {
+      const int col = c.part * 32 + cc * 16;
       float r[16];
       load_acc<4>(tl, col, r);
       if (valid) {
@@ -314,13 +349,15 @@ sphere_update_e_a_tc_kernel(const float* __restrict__ e1, const float* __restric
         }
       }
     }
+    if (tid == 64) TC_TRACE(4);
     epi_done(s);
     // G1: x_kj = act(lin_kj(e1)) * lin_rbf2(r8)                                 spherenet.py:155-159
     mbar_wait(&s.d_ready, 1);
     tc_fence_after();
+    if (tid == 64) TC_TRACE(5);
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-      const int col = c.half * 64 + cc * 16;
+    for (int cc = 0; cc < 2; ++cc) {
+      const int col = c.part * 32 + cc * 16;
       float r[16];
       load_acc<4>(tl, col, r);
       float v[16];
@@ -333,13 +370,14 @@ sphere_update_e_a_tc_kernel(const float* __restrict__ e1, const float* __restric
       }
       store_a(s, c.row, col, v);
     }
+    if (tid == 64) TC_TRACE(6);
     epi_done(s);
     // G2: x_down = act(lin_down(x_kj)), N = 64                                  spherenet.py:161
     mbar_wait(&s.d_ready, 0);
     tc_fence_after();
-#pragma unroll
-    for (int cc = 0; cc < 2; ++cc) {
-      const int col = c.half * 32 + cc * 16;
+    if (tid == 64) TC_TRACE(7);
+    {
+      const int col = c.part * 16;
       float r[16];
       load_acc<4>(tl, col, r);
       if (valid) {
@@ -375,7 +413,7 @@ sphere_update_e_b_tc_kernel(const float* __restrict__ m, const float* __restrict
   const int e0 = blockIdx.x * TC_M, rows = min(TC_M, n_edges - e0);
   if (tid == 0) {
     for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
-    mbar_init(&s.a_ready, 256); mbar_init(&s.d_ready, 1);
+    mbar_init(&s.a_ready, TC_EPI_THREADS); mbar_init(&s.d_ready, 1);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(&s.tmem_base, 512);
@@ -398,10 +436,9 @@ sphere_update_e_b_tc_kernel(const float* __restrict__ m, const float* __restrict
     const bool valid = c.row < rows;
     const size_t ge = (size_t)(e0 + c.row);
     const uint32_t tl = c.tm + ((uint32_t)c.lane_base << 16);
-    // A0 = m tile (K = 64): this thread's 32 columns
-#pragma unroll
-    for (int cc = 0; cc < 2; ++cc) {
-      const int col = c.half * 32 + cc * 16;
+    // A0 = m tile (K = 64): this thread's 16 columns
+    {
+      const int col = c.part * 16;
       float v[16];
 #pragma unroll
       for (int i = 0; i < 16; i += 4) {
@@ -417,16 +454,16 @@ sphere_update_e_b_tc_kernel(const float* __restrict__ m, const float* __restrict
     //   q=2,5: h = stash + act(lin2(t))                      -> A, stash      (q=2: stash not needed afterwards)
     //   q=3: h = act(lin(h)) + e1_in                         -> A, stash
     //   q=7: h = stash + act(lin2(t))                        -> e1_out, e2 tile
-    float stash[64];     // fp32 residual of this thread's (row, 64 columns), lives in registers
-#pragma unroll
+    float stash[32];     // fp32 residual of this thread's (row, 32 columns), lives in registers
+#pragma unroll 1
     for (int q = 0; q < 8; ++q) {
       mbar_wait(&s.d_ready, q & 1);
       tc_fence_after();
       const bool add_stash = (q == 2 || q == 5 || q == 7);
       const bool to_stash = (q == 0 || q == 3 || q == 5);
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        const int col = c.half * 64 + cc * 16;
+      for (int cc = 0; cc < 2; ++cc) {
+        const int col = c.part * 32 + cc * 16;
         float r[16];
         if (q == 0) load_acc<2>(tl, col, r); else load_acc<4>(tl, col, r);
         float v[16];
@@ -534,6 +571,13 @@ int dig3d_tc_set_fast_swish(int32_t on) {
   int v = on ? 1 : 0;
   cudaError_t e = cudaMemcpyToSymbol(g_fast_swish, &v, sizeof(v));
   if (e != cudaSuccess) { set_error("tc_set_fast_swish: %s", cudaGetErrorString(e)); return DIG3D_ECUDA; }
+  return DIG3D_OK;
+}
+
+int dig3d_tc_trace(int32_t on, long long* out64 /* host, 64 entries, nullable */) {
+  if (out64) cudaMemcpyFromSymbol(out64, g_tc_trace, sizeof(long long) * 64);
+  int v = on ? 1 : 0;
+  cudaMemcpyToSymbol(g_tc_trace_on, &v, sizeof(v));
   return DIG3D_OK;
 }
 

@@ -195,6 +195,8 @@ int dig3d_sphere_triplet_gather(const float* x_down, const float* sbf_p, const f
 int dig3d_sphere_update_e_b_tc(const float* m, const float* e1_in, const float* x_ji, const float* rbf0,
                                const int32_t* dst, int64_t n_edges, const dig3d_tc_update_e* w, float* e1_out,
                                float* v_in, void* stream);
+/* debugging probe: enable / read the clock64() timeline CTA 0 of the tensor kernels records (host buffer, 64 x i64) */
+int dig3d_tc_trace(int32_t on, long long* out64);
 /* 1: MUFU-only swish in the tensor-path epilogues (faster, ~1e-6 less accurate); default 0. */
 int dig3d_tc_set_fast_swish(int32_t on);
 
