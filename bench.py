@@ -269,9 +269,13 @@ def main():
     dom = "dig3d_sphere_update_e_b_tc" if "dig3d_sphere_update_e_b_tc" in kern else "dig3d_sphere_update_e_b"
     dom_ms = kern[dom]
     # algorithmic work of update_e part B per launch (DESIGN.md "kernels"):
-    flops_b = E * (2 * I * H + 7 * 2 * H * H) + T * (2 * 2 * 8 * I + 2 * I)
-    bytes_b = 4 * (E * (3 * H + 6 + 2) + T * (I + 16) + N * H)
-    roof = {"kernel": dom.replace("dig3d_", "") + (" (triplet gather + tcgen05 3xTF32 chain)" if dom.endswith("_tc") else ""),
+    if dom.endswith("_tc"):      # chain only: lin_up + 7 (128x128) linears; reads m, x_ji, e1_in, rbf0; writes e1_out, v_in
+        flops_b = E * (2 * I * H + 7 * 2 * H * H)
+        bytes_b = 4 * (E * (I + 3 * H + 6 + 1) + N * H)
+    else:
+        flops_b = E * (2 * I * H + 7 * 2 * H * H) + T * (2 * 2 * 8 * I + 2 * I)
+        bytes_b = 4 * (E * (3 * H + 6 + 2) + T * (I + 16) + N * H)
+    roof = {"kernel": dom.replace("dig3d_", "") + (" (tcgen05 3xTF32 dense chain)" if dom.endswith("_tc") else ""),
             "bound": "tensor",
             "achieved": flops_b / (dom_ms * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
             "frac": flops_b / (dom_ms * 1e-3) / 1e12 / tf_peak, "traffic": None,
@@ -306,6 +310,26 @@ def main():
                "input_mb": rep * E * H * 4 / 1e6}
     del x
 
+    # ---- GPU comparator: the reference's op sequence (oracle/restated.py == the
+    #      reference code over torch-native scatter) executed by ATen/cuBLAS on this same B200
+    gpu_cmp = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import restated
+        sd_dev = {k: v.detach() for k, v in model.state_dict().items()}
+        rb = resident[0]
+        with torch.no_grad():
+            restated.spherenet_forward(sd_dev, rb.z, rb.pos, rb.batch, num_graphs=MOLS_PER_GPU)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for s_ in range(3):
+                rb = resident[s_ % N_ROTATE]
+                restated.spherenet_forward(sd_dev, rb.z, rb.pos, rb.batch, num_graphs=MOLS_PER_GPU)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        gpu_cmp = {"value": 3 * MOLS_PER_GPU / dt, "unit": "molecules/s", "ms_per_step": 1e3 * dt / 3,
+                   "what": "reference op sequence (oracle/restated.py) on the same B200 through ATen/cuBLAS fp32, "
+                           "torch-native scatter; same batch size and weights"}
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         rate, dt, iters, threads = cpu_oracle_rate(32)
@@ -326,7 +350,8 @@ def main():
             "e2e": {"value": e2e, "unit": "molecules/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": wall_e2e / args.steps, "timing": "host wall clock incl. per-step stream sync"},
             "gpu_launches": launches, "wall_ms_per_step": wall_ms / args.steps,
-            "clocks": sampler.summary(), "roofline": roof, "scatter_roofline": scatter, "cpu_baseline": cpu}
+            "clocks": sampler.summary(), "roofline": roof, "scatter_roofline": scatter, "cpu_baseline": cpu,
+            "gpu_comparator": gpu_cmp}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -72,6 +72,7 @@ SIGNATURES = {
     "dig3d_sphere_update_e_b": [P, P, P, P, P, P, c_int32, P, P, P, P, c_int64,
                                 POINTER(UpdateEWeights), P, P, P],
     "dig3d_sphere_update_v": [P, c_int64, c_int32, POINTER(UpdateVWeights), P, P],
+    "dig3d_sphere_update_v_batched": [P, c_int64, c_int32, c_int32, P, P, P],
     "dig3d_graph_readout": [P, P, c_int64, c_int64, c_int32, c_int32, P, P],
     "dig3d_tc_packed_floats": [c_int32, c_int32],
     "dig3d_tc_pack": [P, P, P, P, c_int32, P],

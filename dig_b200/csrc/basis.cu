@@ -139,7 +139,7 @@ triplet_basis_project_kernel(const float* __restrict__ bess, const float* __rest
                              const float* __restrict__ torsion, const int32_t* __restrict__ src,
                              const int32_t* __restrict__ dst, const int32_t* __restrict__ row_ptr,
                              const int32_t* __restrict__ trip_ptr, const int32_t* __restrict__ graph_ptr,
-                             const int64_t* __restrict__ batch, int n_edges,
+                             const int64_t* __restrict__ batch, int n_edges, int n_triplets,
                              const float* __restrict__ w_sbf1, const float* __restrict__ w_t1,
                              float* __restrict__ sbf_p, float* __restrict__ t_p) {
   constexpr int NS = BS::NS, NR = BS::NR, NB = BS::NB, NY = BS::NY;
@@ -221,12 +221,14 @@ triplet_basis_project_kernel(const float* __restrict__ bess, const float* __rest
         float acc_s = 0.f;
 #pragma unroll
         for (int l = 0; l < NS; ++l) acc_s = fmaf(sm.y[w][s][NYT + l], Rs[l], acc_s);
-        sbf_p[(size_t)tt * 32 + lane] = acc_s;
+        // layer-major output [4][T][8]: each layer later streams its own contiguous 32 B per triplet
+        const size_t o = ((size_t)(lane >> 3) * n_triplets + tt) * 8 + (lane & 7);
+        sbf_p[o] = acc_s;
         if (TORSION) {
           float acc_t = 0.f;
 #pragma unroll
           for (int ab = 0; ab < NY; ++ab) acc_t = fmaf(sm.y[w][s][ab], R[ab], acc_t);
-          t_p[(size_t)tt * 32 + lane] = acc_t;
+          t_p[o] = acc_t;
         }
       }
       __syncwarp();
@@ -313,7 +315,7 @@ int dig3d_triplet_basis_project(const float* bess, const float* angle, const flo
       return DIG3D_ECUDA;                                                                                   \
     }                                                                                                       \
     kfn<<<grid, PRJ_WARPS * 32, smem, st>>>(bess, angle, torsion, src, dst, row_ptr, trip_ptr, graph_ptr,   \
-                                            batch, (int)n_edges, w_sbf1, w_t1, sbf_p, t_p);                 \
+                                            batch, (int)n_edges, (int)n_triplets, w_sbf1, w_t1, sbf_p, t_p);\
   }
 #define DIG3D_PRJ(BS) \
   if (tors) DIG3D_PRJ_ONE(BS, true) else DIG3D_PRJ_ONE(BS, false)

@@ -305,9 +305,32 @@ struct NodeSmem {
   float ws[2 * OE * LDW];
 };
 
+struct UpdateVBatch {
+  dig3d_update_v_weights w[8];
+};
+
+__device__ __forceinline__ void sphere_update_v_body(const float* __restrict__ v_in, int n_nodes, int out_channels,
+                                                     const dig3d_update_v_weights& W, float* __restrict__ v_out);
+
 __global__ void __launch_bounds__(DT, 1)
 sphere_update_v_kernel(const float* __restrict__ v_in, int n_nodes, int out_channels,
                        dig3d_update_v_weights W, float* __restrict__ v_out) {
+  sphere_update_v_body(v_in, n_nodes, out_channels, W, v_out);
+}
+
+// All (num_layers + 1) node MLPs of a forward pass in ONE launch (grid.y = block): they only feed the
+// readout, so they are deferred to the end where 5 x 72 CTAs fill the GPU instead of competing with
+// the edge kernels of the next block.
+__global__ void __launch_bounds__(DT, 1)
+sphere_update_v_batched_kernel(const float* __restrict__ v_in_all, int n_nodes, int out_channels,
+                               UpdateVBatch B, float* __restrict__ v_out_all) {
+  const int b = blockIdx.y;
+  sphere_update_v_body(v_in_all + (size_t)b * n_nodes * H, n_nodes, out_channels, B.w[b],
+                       v_out_all + (size_t)b * n_nodes * out_channels);
+}
+
+__device__ __forceinline__ void sphere_update_v_body(const float* __restrict__ v_in, int n_nodes, int out_channels,
+                                                     const dig3d_update_v_weights& W, float* __restrict__ v_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   NodeSmem& s = *reinterpret_cast<NodeSmem*>(smem_raw);
   const int n0 = blockIdx.x * TMV, rows = min(TMV, n_nodes - n0);
@@ -422,6 +445,25 @@ int dig3d_sphere_update_e_b(const float* e1_in, const float* x_ji, const float* 
         e1_in, x_ji, x_down, rbf0, sbf_p, t_p, ld_p, src, dst, row_ptr, trip_ptr, (int)n_edges, *w, e1_out,
         v_in);
   }
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_sphere_update_v_batched(const float* v_in_all, int64_t n_nodes, int32_t n_blocks, int32_t out_channels,
+                                  const dig3d_update_v_weights* w, float* v_out_all, void* stream) {
+  DIG3D_REQUIRE(v_in_all && w && v_out_all && out_channels > 0, "sphere_update_v_batched: bad arguments");
+  DIG3D_REQUIRE(n_blocks >= 1 && n_blocks <= 8, "sphere_update_v_batched: n_blocks=%d outside [1,8]", n_blocks);
+  if (n_nodes == 0) return DIG3D_OK;
+  UpdateVBatch B;
+  for (int b = 0; b < n_blocks; ++b) {
+    DIG3D_REQUIRE(w[b].n_lins >= 0 && w[b].n_lins <= 8, "sphere_update_v_batched: n_lins outside [0,8]");
+    B.w[b] = w[b];
+  }
+  int rc = set_smem(sphere_update_v_batched_kernel, sizeof(NodeSmem));
+  if (rc) return rc;
+  dim3 grid(ceil_div(n_nodes, TMV), n_blocks);
+  sphere_update_v_batched_kernel<<<grid, DT, sizeof(NodeSmem), (cudaStream_t)stream>>>(
+      v_in_all, (int)n_nodes, out_channels, B, v_out_all);
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
 }

@@ -147,11 +147,14 @@ def triplet_basis(bess, angle, torsion, idx_kj, basis_id, ns, nr, want_tbf):
 
 
 def triplet_basis_project(g, bess, basis_id, w_sbf1_rows, w_t1_rows):
-    """w_sbf1_rows: [32, ns*nr], w_t1_rows: [32, ns*ns*nr] or None.  Returns sbf_p [T,32], t_p [T,32]|None."""
+    """w_sbf1_rows: [32, ns*nr], w_t1_rows: [32, ns*ns*nr] or None.
+    Returns sbf_p [4, T, 8], t_p [4, T, 8] | None (layer-major: layer l's rows are contiguous)."""
     t = g.n_triplets
     dev = bess.device
-    sbf_p = torch.empty(max(t, 1), 32, dtype=torch.float32, device=dev)[:t]
-    t_p = torch.empty(max(t, 1), 32, dtype=torch.float32, device=dev)[:t] if w_t1_rows is not None else None
+    sbf_p = torch.empty(4, max(t, 1), 8, dtype=torch.float32, device=dev)
+    t_p = torch.empty(4, max(t, 1), 8, dtype=torch.float32, device=dev) if w_t1_rows is not None else None
+    if t == 0:
+        return sbf_p[:, :0], (t_p[:, :0] if t_p is not None else None)
     if t and g.n_edges:
         call("dig3d_triplet_basis_project", _p(bess, torch.float32), _p(g.angle),
              _p(g.torsion) if w_t1_rows is not None else None, _p(g.src), _p(g.dst), _p(g.row_ptr),
@@ -225,31 +228,43 @@ def pack_update_v(m):
     return w
 
 
-def sphere_init_e(z, g, rbf0, w, hidden):
+def sphere_init_e(z, g, rbf0, w, hidden, v_in=None):
     e1 = torch.empty(max(g.n_edges, 1), hidden, dtype=torch.float32, device=rbf0.device)[:g.n_edges]
-    v_in = torch.zeros(g.n_nodes, hidden, dtype=torch.float32, device=rbf0.device)
+    if v_in is None:
+        v_in = torch.zeros(g.n_nodes, hidden, dtype=torch.float32, device=rbf0.device)
     if g.n_edges:
         call("dig3d_sphere_init_e", _p(z, torch.int64, "z"), _p(g.src), _p(g.dst), _p(rbf0), g.n_edges,
              ctypes.byref(w), _p(e1), _p(v_in), _stream())
     return e1, v_in
 
 
-def sphere_update_e(e1, g, rbf0, sbf_p, t_p, col0, w, hidden, int_emb):
-    """One update_e block (parts A + B).  sbf_p/t_p: [T, 32] with this layer's 8 columns at col0."""
+def sphere_update_e(e1, g, rbf0, sbf_p, t_p, col0, w, hidden, int_emb, v_in=None):
+    """One update_e block (parts A + B).  sbf_p/t_p: [4, T, 8]; col0 // 8 selects the layer slice."""
     dev = e1.device
     e = g.n_edges
     x_ji = torch.empty(max(e, 1), hidden, dtype=torch.float32, device=dev)[:e]
     x_down = torch.empty(max(e, 1), int_emb, dtype=torch.float32, device=dev)[:e]
     e1_out = torch.empty(max(e, 1), hidden, dtype=torch.float32, device=dev)[:e]
-    v_in = torch.zeros(g.n_nodes, hidden, dtype=torch.float32, device=dev)
+    if v_in is None:
+        v_in = torch.zeros(g.n_nodes, hidden, dtype=torch.float32, device=dev)
     if e:
         st = _stream()
         call("dig3d_sphere_update_e_a", _p(e1), _p(rbf0), e, ctypes.byref(w), _p(x_ji), _p(x_down), st)
-        sp = ctypes.c_void_p(sbf_p.data_ptr() + 4 * col0)
-        tp = ctypes.c_void_p(t_p.data_ptr() + 4 * col0) if t_p is not None else None
-        call("dig3d_sphere_update_e_b", _p(e1), _p(x_ji), _p(x_down), _p(rbf0), sp, tp, 32, _p(g.src),
+        sp = ctypes.c_void_p(sbf_p[col0 // 8].data_ptr())
+        tp = ctypes.c_void_p(t_p[col0 // 8].data_ptr()) if t_p is not None else None
+        call("dig3d_sphere_update_e_b", _p(e1), _p(x_ji), _p(x_down), _p(rbf0), sp, tp, 8, _p(g.src),
              _p(g.dst), _p(g.row_ptr), _p(g.trip_ptr), e, ctypes.byref(w), _p(e1_out), _p(v_in), st)
     return e1_out, v_in
+
+
+def sphere_update_v_batched(v_in_all, holders, out_channels, v_out_all):
+    """All node MLPs of a forward in one launch.  v_in_all [NB, N, H], holders: NB update_v modules."""
+    nb, n, _ = v_in_all.shape
+    arr = (_lib.UpdateVWeights * nb)(*[pack_update_v(h) for h in holders])
+    if n:
+        call("dig3d_sphere_update_v_batched", _p(v_in_all, torch.float32, "v_in_all", 16), n, nb, int(out_channels),
+             arr, _p(v_out_all, align=4), _stream())
+    return v_out_all
 
 
 def sphere_update_v(v_in, w, out_channels, v_out):
@@ -406,7 +421,7 @@ def tc_pack_update_e(m, torsion, cache):
     return w
 
 
-def sphere_update_e_tc(e1, g, rbf0, sbf_p, t_p, col0, w, hidden, int_emb):
+def sphere_update_e_tc(e1, g, rbf0, sbf_p, t_p, col0, w, hidden, int_emb, v_in=None):
     """update_e (A + triplet gather + B) with the dense chain on tcgen05."""
     dev = e1.device
     e = g.n_edges
@@ -414,13 +429,14 @@ def sphere_update_e_tc(e1, g, rbf0, sbf_p, t_p, col0, w, hidden, int_emb):
     x_down = torch.empty(max(e, 1), int_emb, dtype=torch.float32, device=dev)[:e]
     m_ws = torch.empty(max(e, 1), int_emb, dtype=torch.float32, device=dev)[:e]
     e1_out = torch.empty(max(e, 1), hidden, dtype=torch.float32, device=dev)[:e]
-    v_in = torch.zeros(g.n_nodes, hidden, dtype=torch.float32, device=dev)
+    if v_in is None:
+        v_in = torch.zeros(g.n_nodes, hidden, dtype=torch.float32, device=dev)
     if e:
         st = _stream()
         call("dig3d_sphere_update_e_a_tc", _p(e1), _p(rbf0), e, ctypes.byref(w), _p(x_ji), _p(x_down), st)
-        sp = ctypes.c_void_p(sbf_p.data_ptr() + 4 * col0)
-        tp = ctypes.c_void_p(t_p.data_ptr() + 4 * col0) if t_p is not None else None
-        call("dig3d_sphere_triplet_gather", _p(x_down), sp, tp, 32, _p(g.src), _p(g.dst), _p(g.row_ptr),
+        sp = ctypes.c_void_p(sbf_p[col0 // 8].data_ptr())
+        tp = ctypes.c_void_p(t_p[col0 // 8].data_ptr()) if t_p is not None else None
+        call("dig3d_sphere_triplet_gather", _p(x_down), sp, tp, 8, _p(g.src), _p(g.dst), _p(g.row_ptr),
              _p(g.trip_ptr), e, w.w_sbf2, w.w_t2, _p(m_ws), st)
         call("dig3d_sphere_update_e_b_tc", _p(m_ws), _p(e1), _p(x_ji), _p(rbf0), _p(g.dst), e, ctypes.byref(w),
              _p(e1_out), _p(v_in), st)

@@ -230,37 +230,26 @@ class _DimeNetFamily(nn.Module):
             w_s, w_t = self._projection_rows(first, min(4, L - first))
             proj.append(ops.triplet_basis_project(g, bess, self._basis_id, w_s, w_t))
 
-        # The node MLP (update_v) of block l only feeds the readout, so it runs on a side stream and
-        # overlaps with the edge kernels of block l+1 (it fills SMs the 2-CTA/SM edge tiles leave idle).
-        main = torch.cuda.current_stream()
-        side = self._side_stream(pos.device)
-        v_all = torch.empty(L + 1, g.n_nodes, self.out_channels, dtype=torch.float32, device=pos.device)
-        v_all.record_stream(side)
-
-        def node_mlp(v_in, holder, out):
-            ready = torch.cuda.Event()
-            ready.record(main)
-            side.wait_event(ready)
-            v_in.record_stream(side)
-            with torch.cuda.stream(side):
-                ops.sphere_update_v(v_in, ops.pack_update_v(holder), self.out_channels, out)
-
+        # The node MLPs (update_v) only feed the readout: their inputs (the fused edge->node scatters) are
+        # collected in v_in_all and all L+1 MLPs run as ONE launch at the end (5 x 72 CTAs fill the GPU)
+        # instead of competing with the edge kernels of the next block for SMs.
+        dev = pos.device
+        v_in_all = torch.zeros(L + 1, g.n_nodes, self.hidden_channels, dtype=torch.float32, device=dev)
+        v_all = torch.empty(L + 1, g.n_nodes, self.out_channels, dtype=torch.float32, device=dev)
         dense_tc = os.environ.get("DIG3D_DENSE", "tc") != "simt"
         tc_cache = self.__dict__.setdefault("_tc_cache", {})
-        e1, v_in = ops.sphere_init_e(z, g, rbf0, ops.pack_init_e(self.init_e), self.hidden_channels)
-        node_mlp(v_in, self.init_v, v_all[0])
+        e1, _ = ops.sphere_init_e(z, g, rbf0, ops.pack_init_e(self.init_e), self.hidden_channels, v_in=v_in_all[0])
         for l in range(L):
             sbf_p, t_p = proj[l // 4]
             if dense_tc:      # tcgen05 3xTF32 dense chain (csrc/spherenet_tc.cu)
                 wt = ops.tc_pack_update_e(self.update_es[l], self._torsion, tc_cache)
-                e1, v_in, _, _ = ops.sphere_update_e_tc(e1, g, rbf0, sbf_p, t_p, 8 * (l % 4), wt,
-                                                        self.hidden_channels, self.int_emb_size)
+                e1, _, _, _ = ops.sphere_update_e_tc(e1, g, rbf0, sbf_p, t_p, 8 * (l % 4), wt,
+                                                     self.hidden_channels, self.int_emb_size, v_in=v_in_all[l + 1])
             else:             # exact-fp32 FFMA tile engine (csrc/spherenet.cu), kept as the validation twin
-                e1, v_in = ops.sphere_update_e(e1, g, rbf0, sbf_p, t_p, 8 * (l % 4),
-                                               ops.pack_update_e(self.update_es[l], self._torsion),
-                                               self.hidden_channels, self.int_emb_size)
-            node_mlp(v_in, self.update_vs[l], v_all[l + 1])
-        main.wait_stream(side)
+                e1, _ = ops.sphere_update_e(e1, g, rbf0, sbf_p, t_p, 8 * (l % 4),
+                                            ops.pack_update_e(self.update_es[l], self._torsion),
+                                            self.hidden_channels, self.int_emb_size, v_in=v_in_all[l + 1])
+        ops.sphere_update_v_batched(v_in_all, [self.init_v] + list(self.update_vs), self.out_channels, v_all)
         return ops.graph_readout(v_all, g.graph_ptr, g.n_graphs, g.n_nodes)
 
 

@@ -88,7 +88,7 @@ int dig3d_triplet_basis(const float* bess, const float* angle, const float* tors
                         int64_t n_triplets, int32_t basis_id, float* sbf, float* tbf, void* stream);
 
 /* Fused basis evaluation + first basis projection for ALL layers:
- *   sbf_p[T, L*B] = lin_sbf1_l(sbf),  t_p[T, L*B] = lin_t1_l(tbf) (nullable => DimeNet++)
+ *   sbf_p[L, T, B] = lin_sbf1_l(sbf),  t_p[L, T, B] = lin_t1_l(tbf) (nullable => DimeNet++), layer-major
  * w_sbf1: [L][B][ns*nr], w_t1: [L][B][ns*ns*nr] (PyTorch [out,in] per layer, layers concatenated).
  * Requires L*B == 32.                                     spherenet.py:163,167  dimenetpp.py:146 */
 int dig3d_triplet_basis_project(const float* bess, const float* angle, const float* torsion,
@@ -158,6 +158,11 @@ int dig3d_sphere_update_e_b(const float* e1_in, const float* x_ji, const float* 
 /* update_v.forward after the scatter (spherenet.py:212-215): v_out[N, out_channels]. */
 int dig3d_sphere_update_v(const float* v_in, int64_t n_nodes, int32_t out_channels,
                           const dig3d_update_v_weights* w, float* v_out, void* stream);
+
+/* All n_blocks (= num_layers + 1 <= 8) node MLPs in one launch: v_in_all [n_blocks, N, H], w[n_blocks],
+ * v_out_all [n_blocks, N, out_channels]. */
+int dig3d_sphere_update_v_batched(const float* v_in_all, int64_t n_nodes, int32_t n_blocks, int32_t out_channels,
+                                  const dig3d_update_v_weights* w, float* v_out_all, void* stream);
 
 /* update_u over all blocks (spherenet.py:223-225,313-318): u[g, c] = sum_l sum_{n in g} v[l][n][c],
  * v: [n_blocks, N, C] contiguous. */

@@ -83,7 +83,9 @@ def test_basis_bit_exact(name):
         assert torch.equal(tbf, it["tbf"])
     # fused projection (never materialises sbf/tbf) vs explicit fp32 matmul on the same values
     w_s, w_t = model._projection_rows(0, 4)
-    sbf_p, t_p = ops.triplet_basis_project(gr, bess, bid, w_s, w_t)
+    sbf_p, t_p = ops.triplet_basis_project(gr, bess, bid, w_s, w_t)        # layer-major [4, T, 8]
+    sbf_p = sbf_p.permute(1, 0, 2).reshape(-1, 32)
+    t_p = t_p.permute(1, 0, 2).reshape(-1, 32) if t_p is not None else None
     assert rel_err(sbf_p.cpu().numpy(), (it["sbf"].double() @ w_s.double().t()).cpu().numpy()) < 2e-6
     if tors:
         assert rel_err(t_p.cpu().numpy(), (it["tbf"].double() @ w_t.double().t()).cpu().numpy()) < 2e-6

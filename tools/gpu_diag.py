@@ -88,6 +88,8 @@ def main():
         L = 4
         w_s, w_t = model._projection_rows(0, L)
         sbf_p, t_p = ops.triplet_basis_project(gr, bess, bid, w_s, w_t)
+        sbf_p = sbf_p.permute(1, 0, 2).reshape(-1, 32)
+        t_p = t_p.permute(1, 0, 2).reshape(-1, 32) if t_p is not None else None
         cmp("sbf_p vs sbf@W (fp32 matmul)", sbf_p, it["sbf"] @ w_s.t())
         if tors:
             cmp("t_p vs tbf@W (fp32 matmul)", t_p, it["tbf"] @ w_t.t())
