@@ -13,9 +13,11 @@
 //     the row stays in the registers of the epilogue thread that owns it, so one A buffer (2 x 64 KB) suffices.
 //   * The tensor core ACCUMULATES WITH TRUNCATION (measured: mean signed relative error -4.7e-7 after 24
 //     accumulations, tools/tc_bias.cu), a systematic shrink that adds up coherently over the chain and over the
-//     nodes of a molecule (3.7e-5 on the energy with one accumulator).  So each K-quarter of the main
-//     hi*hi term gets its OWN accumulator (TMEM columns q*128), opened by that quarter's two small correction
-//     terms, and the epilogue adds the four partials with round-to-nearest.
+//     nodes of a molecule (3.7e-5 on the energy with one accumulator).  So the tensor core only ever
+//     accumulates ONE K-chunk (32 = four k-steps, opened by that chunk's two small correction terms): the
+//     chunks ping-pong between two TMEM accumulators, and the epilogue warps add each finished chunk into
+//     fp32 registers with round-to-nearest WHILE the tensor core works on the next chunk (streaming
+//     accumulation: the TMEM read-out overlaps the MMAs, only the activation phase is exposed).
 //   * B operand: weights are pre-split and pre-arranged (dig3d_tc_pack) as [K/32][hi|lo][8][N][4] so that a
 //     K-chunk is ONE contiguous 32 KB block, streamed by cp.async.bulk (TMA engine) through a 2-stage
 //     mbarrier ring.
@@ -38,15 +40,19 @@ constexpr int TC_THREADS = 64 + TC_EPI_THREADS;   // warp 0 producer, warp 1 MMA
 constexpr int TC_STAGES = 2;
 constexpr int TC_STAGE_FLOATS = 2 * 8 * 128 * 4;   // hi + lo planes of a K=32 chunk with N = 128
 
+// k-unit stride of the A planes, in 16-byte units: one unit of padding (LBO = 129 * 16 B) makes both the
+// "lane = row" epilogue stores and the "lane = k-unit" coalesced tile loads bank-conflict free.
+constexpr int TC_AKU = TC_M + 1;
+
 struct TcSmem {
-  float a_hi[32 * TC_M * 4];
-  float a_lo[32 * TC_M * 4];
+  float a_hi[32 * TC_AKU * 4];
+  float a_lo[32 * TC_AKU * 4];
   float w[TC_STAGES][TC_STAGE_FLOATS];
   float bias[8][128];
   float wr[128 * 8];      // lin_rbf (kernel B) or lin_rbf2 (kernel A) rows, padded to 8
   float wr1[8 * 8];       // lin_rbf1 rows (kernel A), padded to 8
   int dst[TC_M];
-  uint64_t full[TC_STAGES], empty[TC_STAGES], a_ready, d_ready;
+  uint64_t full[TC_STAGES], empty[TC_STAGES], a_ready, d_ready[2], d_free[2];
   uint32_t tmem_base;
 };
 
@@ -84,7 +90,7 @@ __device__ __forceinline__ void tc_producer(TcSmem& s, const TcGemm (&g)[NG]) {
   }
 }
 
-// ---- MMA issuer
+// ---- MMA issuer: one K-chunk per accumulator, accumulators ping-pong (it & 1)
 template <int NG>
 __device__ __forceinline__ void tc_mma(TcSmem& s, const TcGemm (&g)[NG], uint32_t tmem_d) {
   int it = 0;
@@ -96,32 +102,32 @@ __device__ __forceinline__ void tc_mma(TcSmem& s, const TcGemm (&g)[NG], uint32_
     tc_fence_after();
     if (q < 4) TC_TRACE(8 + 4 * q);            // A ready
     for (int c = 0; c < chunks; ++c, ++it) {
-      const int st = it % TC_STAGES;
+      const int st = it % TC_STAGES, ab = it & 1;
       mbar_wait(&s.full[st], (it / TC_STAGES) & 1);
+      mbar_wait(&s.d_free[ab], ((it >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
       tc_fence_after();
       if (q < 4 && c == 0) TC_TRACE(9 + 4 * q);   // first weight chunk landed
       const uint32_t w_hi = smem_u32(s.w[st]), w_lo = w_hi + 8u * n * 16u;
+      const uint32_t d = tmem_d + 128u * ab;
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
-        const uint32_t a_off = (uint32_t)((c * 4 + ks) * 2 * TC_M * 16);
+        const uint32_t a_off = (uint32_t)((c * 4 + ks) * 2 * TC_AKU * 16);
         const uint32_t b_off = (uint32_t)(ks * 2 * n * 16);
-        const uint64_t dah = smem_desc(a_hi + a_off, TC_M * 16, 128), dal = smem_desc(a_lo + a_off, TC_M * 16, 128);
+        const uint64_t dah = smem_desc(a_hi + a_off, TC_AKU * 16, 128), dal = smem_desc(a_lo + a_off, TC_AKU * 16, 128);
         const uint64_t dbh = smem_desc(w_hi + b_off, n * 16, 128), dbl = smem_desc(w_lo + b_off, n * 16, 128);
-        // this K-quarter's corrections (magnitude 2^-11 of the main term) open its accumulator ...
-        mma_tf32(tmem_d + 128u * c, dal, dbh, idesc, ks != 0);
-        mma_tf32(tmem_d + 128u * c, dah, dbl, idesc, 1);
+        // the chunk's corrections (magnitude 2^-11 of the main term) open the accumulator ...
+        mma_tf32(d, dal, dbh, idesc, ks != 0);
+        mma_tf32(d, dah, dbl, idesc, 1);
       }
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
-        const uint32_t a_off = (uint32_t)((c * 4 + ks) * 2 * TC_M * 16);
+        const uint32_t a_off = (uint32_t)((c * 4 + ks) * 2 * TC_AKU * 16);
         const uint32_t b_off = (uint32_t)(ks * 2 * n * 16);
-        const uint64_t dah = smem_desc(a_hi + a_off, TC_M * 16, 128);
-        const uint64_t dbh = smem_desc(w_hi + b_off, n * 16, 128);
-        mma_tf32(tmem_d + 128u * c, dah, dbh, idesc, 1);   // ... then its four hi*hi steps are added on top
-      }
+        mma_tf32(d, smem_desc(a_hi + a_off, TC_AKU * 16, 128), smem_desc(w_hi + b_off, n * 16, 128), idesc, 1);
+      }                                           // ... then its four hi*hi steps are added on top
       mma_commit(&s.empty[st]);
+      mma_commit(&s.d_ready[ab]);
     }
-    mma_commit(&s.d_ready);
     if (q < 4) TC_TRACE(10 + 4 * q);           // all MMAs of the GEMM issued
   }
 }
@@ -141,36 +147,60 @@ __device__ __forceinline__ void store_a(TcSmem& s, int row, int col, const float
   for (int i = 0; i < 16; i += 4) {
     float4 h, l;
     split_tf32(v[i], h.x, l.x); split_tf32(v[i + 1], h.y, l.y); split_tf32(v[i + 2], h.z, l.z); split_tf32(v[i + 3], h.w, l.w);
-    const int o = (((col + i) >> 2) * TC_M + row) * 4;
+    const int o = (((col + i) >> 2) * TC_AKU + row) * 4;
     *reinterpret_cast<float4*>(s.a_hi + o) = h;
     *reinterpret_cast<float4*>(s.a_lo + o) = l;
   }
 }
-// acc[i] = RN sum of the K-quarter accumulators (NQ = K/32 of them) for 16 columns starting at `col`
-template <int NQ>
-__device__ __forceinline__ void load_acc(uint32_t tl, int col, float (&acc)[16]) {
-  uint32_t r0[16], r1[16];
-  tmem_ld16(tl + col, r0);
-  tmem_ld16(tl + 128 + col, r1);
-  if (NQ == 4) {
-    uint32_t r2[16], r3[16];
-    tmem_ld16(tl + 256 + col, r2);
-    tmem_ld16(tl + 384 + col, r3);
-    tmem_ld_wait();
+// Streaming accumulation of one GEMM: every finished K-chunk is added (round-to-nearest) into this thread's
+// fp32 registers, NP 16-column pieces starting at column col0; `it` is the global chunk counter shared
+// (by construction) with the MMA issuer.
+template <int NP>
+__device__ __forceinline__ void epi_accumulate(TcSmem& s, uint32_t tl, int col0, int chunks, int& it,
+                                               float (&acc)[NP * 16]) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i)
-      acc[i] = __fadd_rn(__fadd_rn(__uint_as_float(r0[i]), __uint_as_float(r1[i])),
-                         __fadd_rn(__uint_as_float(r2[i]), __uint_as_float(r3[i])));
-  } else {
-    tmem_ld_wait();
+  for (int i = 0; i < NP * 16; ++i) acc[i] = 0.f;
+  for (int c = 0; c < chunks; ++c, ++it) {
+    const int ab = it & 1;
+    mbar_wait(&s.d_ready[ab], (it >> 1) & 1);
+    tc_fence_after();
+    uint32_t r[NP][16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = __fadd_rn(__uint_as_float(r0[i]), __uint_as_float(r1[i]));
+    for (int p = 0; p < NP; ++p) tmem_ld16(tl + 128u * ab + col0 + 16 * p, r[p]);
+    tmem_ld_wait();
+    tc_fence_before();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&s.d_free[ab]);   // one arrival per warp (512 serialised arrivals are slow)
+#pragma unroll
+    for (int p = 0; p < NP; ++p)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[p * 16 + i] = __fadd_rn(acc[p * 16 + i], __uint_as_float(r[p][i]));
+  }
+}
+// Cooperative (all epilogue threads) load of a row-major [128 x K4*4] fp32 tile from global memory into the A
+// planes: a warp reads one 512-byte (K4 = 32) row segment per instruction (coalesced) and scatters its
+// float4s over the k-units (conflict free thanks to the padded k-unit stride).
+template <int K4>
+__device__ __forceinline__ void load_a_tile(TcSmem& s, const float* __restrict__ g, int rows) {
+  const int et = threadIdx.x - 64;
+#pragma unroll
+  for (int k = 0; k < TC_M * K4 / TC_EPI_THREADS; ++k) {
+    const int f = et + k * TC_EPI_THREADS;
+    const int row = f / K4, c4 = f % K4;
+    const float4 x = row < rows ? __ldg(reinterpret_cast<const float4*>(g + (size_t)row * (K4 * 4)) + c4)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 h, l;
+    split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
+    const int o = (c4 * TC_AKU + row) * 4;
+    *reinterpret_cast<float4*>(s.a_hi + o) = h;
+    *reinterpret_cast<float4*>(s.a_lo + o) = l;
   }
 }
 __device__ __forceinline__ void epi_done(TcSmem& s) {
   fence_async_smem();
   tc_fence_before();
-  mbar_arrive(&s.a_ready);
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(&s.a_ready);
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory"); }
 
@@ -278,10 +308,11 @@ sphere_update_e_a_tc_kernel(const float* __restrict__ e1, const float* __restric
   const int e0 = blockIdx.x * TC_M, rows = min(TC_M, n_edges - e0);
   if (tid == 0) {
     for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
-    mbar_init(&s.a_ready, TC_EPI_THREADS); mbar_init(&s.d_ready, 1);
+    mbar_init(&s.a_ready, TC_EPI_WARPS);
+    for (int i = 0; i < 2; ++i) { mbar_init(&s.d_ready[i], 1); mbar_init(&s.d_free[i], TC_EPI_WARPS); }
     mbar_fence_init();
   }
-  if (warp == 0) tmem_alloc(&s.tmem_base, 512);
+  if (warp == 0) tmem_alloc(&s.tmem_base, 256);
   for (int i = tid; i < 2 * 128; i += TC_THREADS) s.bias[i / 128][i % 128] = __ldg(P.g[i / 128].bias + i % 128);
   for (int i = tid; i < 128 * 8; i += TC_THREADS) s.wr[i] = __ldg(P.w_rbf2 + i);      // [128][8]
   for (int i = tid; i < 64; i += TC_THREADS) s.wr1[i] = (i % 8 < 6) ? __ldg(P.w_rbf1 + (i / 8) * 6 + i % 8) : 0.f;
@@ -301,17 +332,7 @@ sphere_update_e_a_tc_kernel(const float* __restrict__ e1, const float* __restric
     const size_t ge = (size_t)(e0 + c.row);
     const uint32_t tl = c.tm + ((uint32_t)c.lane_base << 16);
     // A0 = e1 tile
-#pragma unroll
-    for (int cc = 0; cc < 2; ++cc) {
-      const int col = c.part * 32 + cc * 16;
-      float v[16];
-#pragma unroll
-      for (int i = 0; i < 16; i += 4) {
-        const float4 x = valid ? __ldg(reinterpret_cast<const float4*>(e1 + ge * 128 + col + i)) : make_float4(0, 0, 0, 0);
-        v[i] = x.x; v[i + 1] = x.y; v[i + 2] = x.z; v[i + 3] = x.w;
-      }
-      store_a(s, c.row, col, v);
-    }
+    load_a_tile<32>(s, e1 + (size_t)e0 * 128, rows);
     // rbf gate coefficients of this row: r8 = lin_rbf1(rbf0[row])            spherenet.py:157
     float r8[8];
     {
@@ -328,64 +349,56 @@ sphere_update_e_a_tc_kernel(const float* __restrict__ e1, const float* __restric
     }
     if (tid == 64) TC_TRACE(2);
     epi_done(s);
+    int it = 0;
+    const int col0 = c.part * 32;
+    float acc[32];
     // G0: x_ji = act(lin_ji(e1))                                                spherenet.py:154
-    mbar_wait(&s.d_ready, 0);
-    tc_fence_after();
+    epi_accumulate<2>(s, tl, col0, 4, it, acc);
     if (tid == 64) TC_TRACE(3);
+    epi_done(s);   // A (= e1) is reused unchanged by lin_kj: let its MMAs run under this activation + store
+    if (valid) {
 #pragma unroll
-    for (int cc = 0; cc < 2; ++cc) {
-      const int col = c.part * 32 + cc * 16;
-      float r[16];
-      load_acc<4>(tl, col, r);
-      if (valid) {
-#pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          float4 o;
-          o.x = swish_sel(r[i] + s.bias[0][col + i], fast);
-          o.y = swish_sel(r[i + 1] + s.bias[0][col + i + 1], fast);
-          o.z = swish_sel(r[i + 2] + s.bias[0][col + i + 2], fast);
-          o.w = swish_sel(r[i + 3] + s.bias[0][col + i + 3], fast);
-          *reinterpret_cast<float4*>(x_ji + ge * 128 + col + i) = o;
-        }
+      for (int i = 0; i < 32; i += 4) {
+        float4 o;
+        o.x = swish_sel(acc[i] + s.bias[0][col0 + i], fast);
+        o.y = swish_sel(acc[i + 1] + s.bias[0][col0 + i + 1], fast);
+        o.z = swish_sel(acc[i + 2] + s.bias[0][col0 + i + 2], fast);
+        o.w = swish_sel(acc[i + 3] + s.bias[0][col0 + i + 3], fast);
+        *reinterpret_cast<float4*>(x_ji + ge * 128 + col0 + i) = o;
       }
     }
     if (tid == 64) TC_TRACE(4);
-    epi_done(s);
     // G1: x_kj = act(lin_kj(e1)) * lin_rbf2(r8)                                 spherenet.py:155-159
-    mbar_wait(&s.d_ready, 1);
-    tc_fence_after();
+    epi_accumulate<2>(s, tl, col0, 4, it, acc);
     if (tid == 64) TC_TRACE(5);
 #pragma unroll
     for (int cc = 0; cc < 2; ++cc) {
-      const int col = c.part * 32 + cc * 16;
-      float r[16];
-      load_acc<4>(tl, col, r);
       float v[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        float gate = 0.f;
-#pragma unroll
-        for (int m = 0; m < 8; ++m) gate = fmaf(s.wr[(col + i) * 8 + m], r8[m], gate);
-        v[i] = swish_sel(r[i] + s.bias[1][col + i], fast) * gate;
+        const int col = col0 + cc * 16 + i;
+        const float4 w0 = *reinterpret_cast<const float4*>(s.wr + col * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(s.wr + col * 8 + 4);
+        const float gate = fmaf(w1.w, r8[7], fmaf(w1.z, r8[6], fmaf(w1.y, r8[5], fmaf(w1.x, r8[4],
+                           fmaf(w0.w, r8[3], fmaf(w0.z, r8[2], fmaf(w0.y, r8[1], w0.x * r8[0])))))));
+        v[i] = swish_sel(acc[cc * 16 + i] + s.bias[1][col], fast) * gate;
       }
-      store_a(s, c.row, col, v);
+      store_a(s, c.row, col0 + cc * 16, v);
     }
     if (tid == 64) TC_TRACE(6);
     epi_done(s);
     // G2: x_down = act(lin_down(x_kj)), N = 64                                  spherenet.py:161
-    mbar_wait(&s.d_ready, 0);
-    tc_fence_after();
-    if (tid == 64) TC_TRACE(7);
     {
       const int col = c.part * 16;
-      float r[16];
-      load_acc<4>(tl, col, r);
+      float a16[16];
+      epi_accumulate<1>(s, tl, col, 4, it, a16);
+      if (tid == 64) TC_TRACE(7);
       if (valid) {
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
           float4 o;
-          o.x = swish_sel(r[i], fast); o.y = swish_sel(r[i + 1], fast);
-          o.z = swish_sel(r[i + 2], fast); o.w = swish_sel(r[i + 3], fast);
+          o.x = swish_sel(a16[i], fast); o.y = swish_sel(a16[i + 1], fast);
+          o.z = swish_sel(a16[i + 2], fast); o.w = swish_sel(a16[i + 3], fast);
           *reinterpret_cast<float4*>(x_down + ge * 64 + col + i) = o;
         }
       }
@@ -393,7 +406,7 @@ sphere_update_e_a_tc_kernel(const float* __restrict__ e1, const float* __restric
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 0) tmem_dealloc(s.tmem_base, 512);
+  if (warp == 0) tmem_dealloc(s.tmem_base, 256);
 }
 
 // ---------------------------------------------------------------------------------- update_e part B (tensor)
@@ -413,10 +426,11 @@ sphere_update_e_b_tc_kernel(const float* __restrict__ m, const float* __restrict
   const int e0 = blockIdx.x * TC_M, rows = min(TC_M, n_edges - e0);
   if (tid == 0) {
     for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
-    mbar_init(&s.a_ready, TC_EPI_THREADS); mbar_init(&s.d_ready, 1);
+    mbar_init(&s.a_ready, TC_EPI_WARPS);
+    for (int i = 0; i < 2; ++i) { mbar_init(&s.d_ready[i], 1); mbar_init(&s.d_free[i], TC_EPI_WARPS); }
     mbar_fence_init();
   }
-  if (warp == 0) tmem_alloc(&s.tmem_base, 512);
+  if (warp == 0) tmem_alloc(&s.tmem_base, 256);
   for (int i = tid; i < 8 * 128; i += TC_THREADS) {
     const float* b = P.g[i / 128].bias;
     s.bias[i / 128][i % 128] = b ? __ldg(b + i % 128) : 0.f;
@@ -436,17 +450,8 @@ sphere_update_e_b_tc_kernel(const float* __restrict__ m, const float* __restrict
     const bool valid = c.row < rows;
     const size_t ge = (size_t)(e0 + c.row);
     const uint32_t tl = c.tm + ((uint32_t)c.lane_base << 16);
-    // A0 = m tile (K = 64): this thread's 16 columns
-    {
-      const int col = c.part * 16;
-      float v[16];
-#pragma unroll
-      for (int i = 0; i < 16; i += 4) {
-        const float4 x = valid ? __ldg(reinterpret_cast<const float4*>(m + ge * 64 + col + i)) : make_float4(0, 0, 0, 0);
-        v[i] = x.x; v[i + 1] = x.y; v[i + 2] = x.z; v[i + 3] = x.w;
-      }
-      store_a(s, c.row, col, v);
-    }
+    // A0 = m tile (K = 64)
+    load_a_tile<16>(s, m + (size_t)e0 * 64, rows);
     epi_done(s);
     // The eight epilogues of the chain (spherenet.py:172-179):
     //   q=0: h = x_ji + act(lin_up(m))                       -> A, stash
@@ -455,20 +460,20 @@ sphere_update_e_b_tc_kernel(const float* __restrict__ m, const float* __restrict
     //   q=3: h = act(lin(h)) + e1_in                         -> A, stash
     //   q=7: h = stash + act(lin2(t))                        -> e1_out, e2 tile
     float stash[32];     // fp32 residual of this thread's (row, 32 columns), lives in registers
+    int it = 0;
+    const int col0 = c.part * 32;
 #pragma unroll 1
     for (int q = 0; q < 8; ++q) {
-      mbar_wait(&s.d_ready, q & 1);
-      tc_fence_after();
+      float acc[32];
+      epi_accumulate<2>(s, tl, col0, q == 0 ? 2 : 4, it, acc);
       const bool add_stash = (q == 2 || q == 5 || q == 7);
       const bool to_stash = (q == 0 || q == 3 || q == 5);
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
-        const int col = c.part * 32 + cc * 16;
-        float r[16];
-        if (q == 0) load_acc<2>(tl, col, r); else load_acc<4>(tl, col, r);
+        const int col = col0 + cc * 16;
         float v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = swish_sel(r[i] + s.bias[q][col + i], fast);
+        for (int i = 0; i < 16; ++i) v[i] = swish_sel(acc[cc * 16 + i] + s.bias[q][col + i], fast);
         if (add_stash) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] += stash[cc * 16 + i];
@@ -530,7 +535,7 @@ sphere_update_e_b_tc_kernel(const float* __restrict__ m, const float* __restrict
     }
   }
   __syncthreads();
-  if (warp == 0) tmem_dealloc(s.tmem_base, 512);
+  if (warp == 0) tmem_dealloc(s.tmem_base, 256);
 }
 
 static int tc_smem_attr(const void* fn, size_t bytes) {
