@@ -15,6 +15,8 @@
 
 namespace dig3d {
 
+constexpr int GEO_MAXDEG = 64;  // in-degree supported per node (cap <= 64)
+
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -162,13 +164,52 @@ __global__ void edge_fill_kernel(const float* __restrict__ pos, const int32_t* _
   if (i == n_nodes - 1) trip_ptr[n_edges] = t;
 }
 
+// ------------------------------------------------------------------ CSR from a caller-supplied edge_index
+// xyz_to_dat(pos, edge_index, ...) (utils/geometric_computing.py:12) takes any edge list; the kernels need
+// it sorted by (target, source) -- what radius_graph produces.  flag[0] |= 1 if it is not.
+__global__ void edges_prepare_kernel(const int64_t* __restrict__ edge_index, int64_t n_edges, int n_nodes,
+                                     int32_t* __restrict__ src, int32_t* __restrict__ dst,
+                                     int32_t* __restrict__ flag) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  const int64_t j = edge_index[e], i = edge_index[n_edges + e];
+  src[e] = (int32_t)j; dst[e] = (int32_t)i;
+  bool bad = j < 0 || i < 0 || j >= n_nodes || i >= n_nodes;
+  if (e > 0) {
+    const int64_t pj = edge_index[e - 1], pi = edge_index[n_edges + e - 1];
+    bad |= (pi > i) || (pi == i && pj >= j);
+  }
+  if (bad) atomicOr(flag, 1);
+}
+
+__global__ void csr_from_sorted_kernel(const int32_t* __restrict__ dst, int n_edges, int n_nodes,
+                                       int32_t* __restrict__ row_ptr) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n > n_nodes) return;
+  int lo = 0, hi = n_edges;                   // first edge with dst >= n
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (dst[mid] < n) lo = mid + 1; else hi = mid; }
+  row_ptr[n] = lo;
+}
+
+__global__ void edge_triplet_count_kernel(const float* __restrict__ pos, const int32_t* __restrict__ src,
+                                          const int32_t* __restrict__ dst, const int32_t* __restrict__ row_ptr,
+                                          int n_edges, int max_deg, int32_t* __restrict__ cnt,
+                                          float* __restrict__ dist, int32_t* __restrict__ flag) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  const int j = src[e], i = dst[e];
+  const int b = row_ptr[j], d = row_ptr[j + 1] - b;
+  if (d > max_deg) atomicOr(flag, 2);   // the geometry kernel parks one plane per in-neighbour in shared memory
+  cnt[e] = d - (find_sorted(src + b, d, i) >= 0 ? 1 : 0);
+  dist[e] = norm3_aten(sub3(load3(pos, i), load3(pos, j)));
+}
+
 // ------------------------------------------------------------------ triplet geometry
 // One warp per edge e = (j -> i).  Lane s owns in-edge s of j (k = src[row_ptr[j]+s]); up to
 // WMAX in-edges per pass.  plane_s = cross(pos_ji, pos_k - pos_j) is both the angle's cross
 // product and the torsion's plane1/plane2, so each lane computes its plane once, parks it in
 // shared memory and every lane then scans all candidates k_n.
 constexpr int GEO_WARPS = 8;
-constexpr int GEO_MAXDEG = 64;  // in-degree supported per node (cap <= 64)
 
 __global__ void __launch_bounds__(GEO_WARPS * 32)
 triplet_geometry_kernel(const float* __restrict__ pos, const int32_t* __restrict__ src,
@@ -358,6 +399,29 @@ int dig3d_triplet_geometry(const float* pos, const int32_t* src, const int32_t* 
   triplet_geometry_kernel<<<ceil_div(n_edges, GEO_WARPS), GEO_WARPS * 32, 0, (cudaStream_t)stream>>>(
       pos, src, dst, row_ptr, trip_ptr, (int)n_edges, use_torsion, angle, torsion, idx_kj, idx_ji, idx_kj64,
       idx_ji64);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_edges_to_csr(const float* pos, const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, int32_t* src,
+                       int32_t* dst, int32_t* row_ptr, int32_t* cnt_ws, int32_t* trip_ptr, float* dist,
+                       int32_t* flags /*[4]: [0] unsorted/out-of-range, [2] E, [3] T*/, void* stream) {
+  DIG3D_REQUIRE(pos && edge_index && src && dst && row_ptr && cnt_ws && trip_ptr && dist && flags,
+                "edges_to_csr: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(flags, 0, 4 * sizeof(int32_t), st);
+  if (n_edges) {
+    edges_prepare_kernel<<<ceil_div(n_edges, 256), 256, 0, st>>>(edge_index, n_edges, (int)n_nodes, src, dst, flags);
+    DIG3D_LAUNCH_CHECK();
+  }
+  csr_from_sorted_kernel<<<ceil_div(n_nodes + 1, 256), 256, 0, st>>>(dst, (int)n_edges, (int)n_nodes, row_ptr);
+  DIG3D_LAUNCH_CHECK();
+  if (n_edges) {
+    edge_triplet_count_kernel<<<ceil_div(n_edges, 256), 256, 0, st>>>(pos, src, dst, row_ptr, (int)n_edges,
+                                                                    GEO_MAXDEG, cnt_ws, dist, flags);
+    DIG3D_LAUNCH_CHECK();
+  }
+  scan_counts_kernel<<<1, 1024, 0, st>>>(cnt_ws, cnt_ws, (int)n_edges, trip_ptr, cnt_ws + n_edges + 1, flags + 2);
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
 }

@@ -1,0 +1,60 @@
+"""Graph-sharded data parallelism for the 3D-graph path.
+
+Every op of the path is confined to one molecule, so a global batch is split into contiguous
+molecule ranges, one per rank (one process per GPU), with NO data-path collective in the forward
+pass.  The only exchanges are bookkeeping: the max-over-ranks step time (bench.py) and -- once the
+backward kernels exist -- one all-reduce of the flat fp32 gradient buffer per step.
+torch.distributed is the plumbing (NCCL on the GPUs, gloo in the CPU tests).
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_items, rank, world):
+    """Contiguous [lo, hi) of rank `rank`; sizes differ by at most one, earlier ranks get the extras."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside [0, {world})")
+    base, extra = divmod(n_items, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_molecules(molecules, rank=None, world=None):
+    """This rank's contiguous slice of a global list of molecules."""
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    lo, hi = shard_bounds(len(molecules), rank, world)
+    return molecules[lo:hi]
+
+
+def max_over_ranks(value, device="cpu"):
+    """max of a python float over all ranks (bench timing rule: the slowest rank defines the step)."""
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value, device="cpu"):
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def gather_per_molecule(values, device=None):
+    """Concatenate per-molecule results (e.g. energies [n_local, C]) of all ranks in rank order."""
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return values
+    world = dist.get_world_size()
+    n_local = torch.tensor([values.size(0)], dtype=torch.long, device=values.device)
+    sizes = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(sizes, n_local)
+    m = int(max(int(s) for s in sizes))
+    pad = torch.zeros(m, *values.shape[1:], dtype=values.dtype, device=values.device)
+    pad[:values.size(0)] = values
+    out = [torch.zeros_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad)
+    return torch.cat([o[:int(s)] for o, s in zip(out, sizes)], dim=0)

@@ -1,0 +1,55 @@
+"""`xyz_to_dat` / `radius_graph` with the reference's call signatures, on the sm_100a kernels.
+
+reference: dig/threedgraph/utils/geometric_computing.py:12-80 (xyz_to_dat);
+           torch_cluster.radius_graph as called at spherenet.py:304.
+The model classes do not go through these wrappers (they keep int32 CSR internally and never
+materialise idx_kj / idx_ji); they exist for users of the reference's utility API and for tests.
+"""
+import torch
+
+from ... import ops
+from ...ops import _p, _stream, call
+
+
+def radius_graph(x, r, batch=None, loop=False, max_num_neighbors=32, flow='source_to_target', num_workers=1):
+    """edge_index [2, E] int64 = (source j, target i), sorted by (i, j); torch_cluster CUDA semantics."""
+    if loop or flow != 'source_to_target':
+        raise NotImplementedError("radius_graph: only loop=False, flow='source_to_target' (the reference's use)")
+    g = ops.build_graph(x, batch, r, max_num_neighbors=max_num_neighbors)
+    return g.edge_index
+
+
+def xyz_to_dat(pos, edge_index, num_nodes, use_torsion=False):
+    """(dist, angle[, torsion], i, j, idx_kj, idx_ji) exactly as the reference returns them.
+
+    `edge_index` must be sorted by (target, source) -- what `radius_graph` returns; the reference also
+    accepts arbitrary order (SparseTensor sorts internally), which is not implemented here."""
+    if edge_index.dim() != 2 or edge_index.size(0) != 2:
+        raise ValueError("edge_index must be [2, E]")
+    dev = pos.device
+    e = edge_index.size(1)
+    n = int(num_nodes)
+    ei = edge_index.contiguous()
+    g = ops.Graph3D()
+    g.n_nodes, g.n_edges = n, e
+    g.src = torch.empty(max(e, 1), dtype=torch.int32, device=dev)[:e]
+    g.dst = torch.empty(max(e, 1), dtype=torch.int32, device=dev)[:e]
+    g.row_ptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    g.trip_ptr = torch.empty(e + 1, dtype=torch.int32, device=dev)
+    g.dist = torch.empty(max(e, 1), dtype=torch.float32, device=dev)[:e]
+    ws = torch.empty(2 * e + 2, dtype=torch.int32, device=dev)
+    flags = torch.empty(4, dtype=torch.int32, device=dev)
+    call("dig3d_edges_to_csr", _p(pos.detach(), torch.float32, "pos"), _p(ei, torch.int64, "edge_index"), e, n,
+         _p(g.src), _p(g.dst), _p(g.row_ptr), _p(ws), _p(g.trip_ptr), _p(g.dist), _p(flags), _stream())
+    fl = flags.tolist()
+    if fl[0] & 1:
+        raise NotImplementedError("xyz_to_dat: edge_index must be sorted by (target, source) with valid node ids "
+                                  "(as produced by radius_graph)")
+    if fl[0] & 2:
+        raise NotImplementedError("xyz_to_dat: in-degree above 64 is not supported by the geometry kernel")
+    g.n_triplets = int(fl[3])
+    ops.triplet_geometry(g, pos, use_torsion=use_torsion, want_idx=False, want_idx64=True)
+    j, i = ei[0], ei[1]
+    if use_torsion:
+        return g.dist, g.angle, g.torsion, i, j, g.idx_kj64, g.idx_ji64
+    return g.dist, g.angle, i, j, g.idx_kj64, g.idx_ji64

@@ -61,6 +61,14 @@ int dig3d_edge_fill(const float* pos, const int32_t* nbr, const int32_t* deg, co
                     int64_t* edge_index, int32_t* src, int32_t* dst, float* dist, float* vec,
                     int32_t* trip_ptr, void* stream);
 
+/* CSR / triplet offsets / distances for a CALLER-SUPPLIED edge_index [2,E] int64 sorted by (target, source)
+ * (the entry of xyz_to_dat(pos, edge_index, num_nodes, ...), utils/geometric_computing.py:12).
+ * cnt_ws: [2E+2] int32 workspace; flags[0] != 0 afterwards => edge_index unsorted or out of range;
+ * flags[3] = number of triplets. */
+int dig3d_edges_to_csr(const float* pos, const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, int32_t* src,
+                       int32_t* dst, int32_t* row_ptr, int32_t* cnt_ws, int32_t* trip_ptr, float* dist,
+                       int32_t* flags, void* stream);
+
 /* ------------------------------------------------------------------ geometry
  * xyz_to_dat(pos, edge_index, N, use_torsion)     utils/geometric_computing.py:43-75
  * angle[T], torsion[T] (nullable), idx_kj/idx_ji int32 (nullable) and int64 (nullable).

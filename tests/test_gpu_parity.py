@@ -217,3 +217,74 @@ def test_comenet_energy_parity():
     # vs the CPU fixture: bounded by the reference's own fp32/fp64 floor (2.6e-1 here)
     floor = rel_err(g["energy_f32"], g["energy_f64"])
     assert rel_err(u.cpu().numpy(), g["energy_f32"]) < max(TOL, floor)
+
+
+def test_xyz_to_dat_api_matches_reference_outputs():
+    """The utility API with the reference's signature (utils/geometric_computing.py:12) vs the fixture
+    written by the real reference and vs the notebook known-answer."""
+    from dig_b200.threedgraph.utils import xyz_to_dat, radius_graph
+    dev = torch.device("cuda:0")
+    g, z, pos, batch = case_inputs("spherenet_qm9", dev)
+    ei = radius_graph(pos, 5.0, batch)
+    assert np.array_equal(ei.cpu().numpy(), g["edge_index"])
+    dist, angle, torsion, i, j, idx_kj, idx_ji = xyz_to_dat(pos, ei, z.size(0), use_torsion=True)
+    assert idx_kj.dtype == torch.int64 and np.array_equal(idx_kj.cpu().numpy(), g["idx_kj"])
+    assert np.array_equal(idx_ji.cpu().numpy(), g["idx_ji"])
+    assert rel_err(dist.cpu().numpy(), g["dist"]) < 5e-7 and rel_err(angle.cpu().numpy(), g["angle"]) < 5e-7
+    # notebook example (examples/threedgraph/xyz_to_dat.ipynb): integer coordinates, exact answers
+    nb = load_golden("xyz_to_dat_notebook")
+    out = xyz_to_dat(torch.from_numpy(nb["pos"]).to(dev), torch.from_numpy(nb["edge_index"]).to(dev), 4, use_torsion=True)
+    assert out[5].tolist() == [2, 4, 1, 3] and out[6].tolist() == [0, 2, 3, 5]
+    assert np.array_equal(out[2].cpu().numpy(), nb["torsion"])
+    with pytest.raises(NotImplementedError):
+        xyz_to_dat(pos, ei.flip(1), z.size(0))
+
+
+def test_run_val_on_the_fused_path():
+    """run.val (reference run.py:137-180) over a DataLoader of synthetic molecules == MAE of the oracle's energies."""
+    from dig_b200.data import synthetic_molecules, collate
+    from dig_b200.threedgraph.method import SchNet, run
+    from dig_b200.threedgraph.evaluation import ThreeDEvaluator
+    from oracle import restated
+    dev = torch.device("cuda:0")
+    mols = synthetic_molecules(10, "schnet-plumbing", seed=3)
+    for m in mols:
+        m.y = m.y.reshape(())
+    model = SchNet(num_layers=2, hidden_channels=32, num_filters=32, cutoff=10.0)
+    sd = formula_state_dict(model.state_dict(), seed=1)
+    model.load_state_dict(sd)
+    model = model.to(dev)
+
+    class DS(list):
+        pass
+    from dig_b200.data import DataLoader
+    mae = run().val(model, DataLoader(DS(mols), 4, shuffle=False), False, 100, ThreeDEvaluator(), dev)
+    b = collate(mols).to(dev)
+    ref = restated.schnet_forward({k: v.to(dev) for k, v in sd.items()}, b.z, b.pos, b.batch, cutoff=10.0, num_layers=2)
+    want = float((ref.flatten() - b.y).abs().mean())
+    assert abs(mae - want) < 1e-5 * max(1.0, abs(want))
+    with pytest.raises(NotImplementedError):
+        run().train(model, torch.optim.Adam(model.parameters()), DataLoader(DS(mols), 4), False, 100,
+                    torch.nn.L1Loss(), dev)
+
+
+@pytest.mark.parametrize("cfg", ["cfg3-dimenetpp-md17-b256", "cfg4-comenet-oc20-b64"])
+def test_baseline_configs_full_size(cfg):
+    """BASELINE.json configs[2] / configs[3] at full size against the oracle on the same GPU."""
+    from dig_b200.data import synthetic_batch
+    from dig_b200.threedgraph.method import DimeNetPP, ComENet
+    from oracle import restated
+    dev = torch.device("cuda:0")
+    if cfg.startswith("cfg3"):
+        model, b, fn, kw = DimeNetPP(cutoff=5.0), synthetic_batch(256, "md17-aspirin", seed=3), restated.dimenetpp_forward, dict(cutoff=5.0)
+    else:
+        model, b, fn, kw = ComENet(cutoff=6.0), synthetic_batch(64, "oc20-is2re", seed=4), restated.comenet_forward, dict(cutoff=6.0)
+    sd = formula_state_dict(model.state_dict(), seed=9)
+    model.load_state_dict(sd)
+    model = model.to(dev)
+    b = b.to(dev)
+    with torch.no_grad():
+        u = model(b)
+        ref = fn({k: v.to(dev) for k, v in sd.items()}, b.z, b.pos, b.batch, **kw)
+    assert u.shape == ref.shape and torch.isfinite(u).all()
+    assert rel_err(u.cpu().numpy(), ref.cpu().numpy()) < TOL
