@@ -27,40 +27,42 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-template <int NOUT>
+template <int NOUT, int KCH>
 __device__ __forceinline__ void stage_weights(const float* __restrict__ Wg, int ldwg, int k0, float* Ws) {
-  // NOUT rows x KC floats; 8 x 16B segments per row
-  constexpr int SEGS = NOUT * (KC / 4);
+  // NOUT rows x KCH floats; KCH/4 16-byte segments per row
+  constexpr int SEGS = NOUT * (KCH / 4), PER = KCH / 4, LD = KCH + 4;
 #pragma unroll
   for (int it = 0; it < SEGS / DT; ++it) {
     const int id = threadIdx.x + it * DT;
-    const int o = id >> 3, part = id & 7;
-    cp_async16(Ws + o * LDW + part * 4, Wg + (size_t)o * ldwg + k0 + part * 4);
+    const int o = id / PER, part = id % PER;
+    cp_async16(Ws + o * LD + part * 4, Wg + (size_t)o * ldwg + k0 + part * 4);
   }
 }
 
-// Ws must hold 2 * NOUT * LDW floats.  All threads must call; ends with __syncthreads().
-template <int TM, int NOUT, int K>
+// Ws must hold 2 * NOUT * (KCH + 4) floats.  All threads must call; ends with __syncthreads().
+// KCH = K chunk staged per step (32 by default; 16 halves the staging footprint, used where it buys a
+// second resident CTA per SM).
+template <int TM, int NOUT, int K, int KCH = KC>
 __device__ __forceinline__ void gemm_tile(const float* As, int lda, const float* __restrict__ Wg, int ldwg,
                                           float* Ws, float (&acc)[TM / 16][NOUT / 16]) {
-  constexpr int RP = TM / 16, NQ = NOUT / 16, NCH = K / KC;
-  static_assert(K % KC == 0 && (NOUT * (KC / 4)) % DT == 0, "tile shape");
+  constexpr int RP = TM / 16, NQ = NOUT / 16, NCH = K / KCH, LDW = KCH + 4;
+  static_assert(K % KCH == 0 && (NOUT * (KCH / 4)) % DT == 0, "tile shape");
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-  stage_weights<NOUT>(Wg, ldwg, 0, Ws);
+  stage_weights<NOUT, KCH>(Wg, ldwg, 0, Ws);
   cp_async_commit();
   for (int ch = 0; ch < NCH; ++ch) {
     float* cur = Ws + (ch & 1) * (NOUT * LDW);
     if (ch + 1 < NCH) {
-      stage_weights<NOUT>(Wg, ldwg, (ch + 1) * KC, Ws + ((ch + 1) & 1) * (NOUT * LDW));
+      stage_weights<NOUT, KCH>(Wg, ldwg, (ch + 1) * KCH, Ws + ((ch + 1) & 1) * (NOUT * LDW));
       cp_async_commit();
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
     }
     __syncthreads();
-    const float* a_base = As + (ty * RP) * lda + ch * KC;
+    const float* a_base = As + (ty * RP) * lda + ch * KCH;
 #pragma unroll
-    for (int kk = 0; kk < KC; kk += 4) {
+    for (int kk = 0; kk < KCH; kk += 4) {
       float4 a[RP], b[NQ];
 #pragma unroll
       for (int p = 0; p < RP; ++p) a[p] = *reinterpret_cast<const float4*>(a_base + p * lda + kk);

@@ -299,10 +299,11 @@ sphere_update_e_b_kernel(const float* __restrict__ e1_in, const float* __restric
 }
 
 // ------------------------------------------------------------------ update_v (node MLP)
+constexpr int VKC = 16;    // K chunk of the node MLP: 107 KB per CTA -> two CTAs per SM
 struct NodeSmem {
   float buf0[TMV * LDV];
   float buf1[TMV * LDV];
-  float ws[2 * OE * LDW];
+  float ws[2 * OE * (VKC + 4)];
 };
 
 struct UpdateVBatch {
@@ -312,7 +313,7 @@ struct UpdateVBatch {
 __device__ __forceinline__ void sphere_update_v_body(const float* __restrict__ v_in, int n_nodes, int out_channels,
                                                      const dig3d_update_v_weights& W, float* __restrict__ v_out);
 
-__global__ void __launch_bounds__(DT, 1)
+__global__ void __launch_bounds__(DT, 2)
 sphere_update_v_kernel(const float* __restrict__ v_in, int n_nodes, int out_channels,
                        dig3d_update_v_weights W, float* __restrict__ v_out) {
   sphere_update_v_body(v_in, n_nodes, out_channels, W, v_out);
@@ -321,7 +322,7 @@ sphere_update_v_kernel(const float* __restrict__ v_in, int n_nodes, int out_chan
 // All (num_layers + 1) node MLPs of a forward pass in ONE launch (grid.y = block): they only feed the
 // readout, so they are deferred to the end where 5 x 72 CTAs fill the GPU instead of competing with
 // the edge kernels of the next block.
-__global__ void __launch_bounds__(DT, 1)
+__global__ void __launch_bounds__(DT, 2)
 sphere_update_v_batched_kernel(const float* __restrict__ v_in_all, int n_nodes, int out_channels,
                                UpdateVBatch B, float* __restrict__ v_out_all) {
   const int b = blockIdx.y;
@@ -342,7 +343,7 @@ __device__ __forceinline__ void sphere_update_v_body(const float* __restrict__ v
   float acc[2][16];
   // v = lin_up(v)  (no activation)                                      spherenet.py:212
   zero_acc(acc);
-  gemm_tile<TMV, OE, H>(s.buf0, LDV, W.w_up, H, s.ws, acc);
+  gemm_tile<TMV, OE, H, VKC>(s.buf0, LDV, W.w_up, H, s.ws, acc);
 #pragma unroll
   for (int p = 0; p < 2; ++p)
 #pragma unroll
@@ -355,7 +356,7 @@ __device__ __forceinline__ void sphere_update_v_body(const float* __restrict__ v
   float* nxt = s.buf0;
   for (int l = 0; l < W.n_lins; ++l) {  // v = act(lin(v))                spherenet.py:213-214
     zero_acc(acc);
-    gemm_tile<TMV, OE, OE>(cur, LDV, W.w_lins[l], OE, s.ws, acc);
+    gemm_tile<TMV, OE, OE, VKC>(cur, LDV, W.w_lins[l], OE, s.ws, acc);
 #pragma unroll
     for (int p = 0; p < 2; ++p)
 #pragma unroll

@@ -207,13 +207,16 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"
 // ---------------------------------------------------------------------------------- triplet gather (SIMT)
 // m[e] = sum_{t in trip(e)} x_down[kj(t)] * lin_sbf2(sbf_p[t]) * lin_t2(t_p[t])      spherenet.py:163-171
 template <bool TORSION>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 sphere_triplet_gather_kernel(const float* __restrict__ x_down, const float* __restrict__ sbf_p,
-                             const float* __restrict__ t_p, int ld_p, const int32_t* __restrict__ src,
+                             const float* __restrict__ t_p, const int32_t* __restrict__ src,
                              const int32_t* __restrict__ dst, const int32_t* __restrict__ row_ptr,
                              const int32_t* __restrict__ trip_ptr, int n_edges, const float* __restrict__ w_sbf2,
                              const float* __restrict__ w_t2, float* __restrict__ m) {
-  const int lane = threadIdx.x & 31;
+  // per warp: the projected basis rows of 8 consecutive triplets (8 x 8 floats each for sbf and t), loaded
+  // with two coalesced 256-byte reads instead of 32 broadcast loads, then re-read as warp broadcasts
+  __shared__ __align__(16) float stage[8][2][64];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (e >= n_edges) return;
   float ws2[2][8], wt2[2][8];
@@ -235,33 +238,41 @@ sphere_triplet_gather_kernel(const float* __restrict__ x_down, const float* __re
   }
   const int t0 = trip_ptr[e], nt = d - (p_i < d ? 1 : 0);
   float a0 = 0.f, a1 = 0.f;
-  // independent iterations, four triplets in flight per warp
-  for (int r0 = 0; r0 < nt; r0 += 4) {
-    float4 s0[4], s1[4], q0[4], q1[4];
-    float x0[4], x1[4];
+  for (int r0 = 0; r0 < nt; r0 += 8) {
+    const int n8 = min(8, nt - r0), lim = n8 * 8;
+    const float* sp = sbf_p + (size_t)(t0 + r0) * 8;
+    const float sa = lane < lim ? __ldg(sp + lane) : 0.f, sb = lane + 32 < lim ? __ldg(sp + lane + 32) : 0.f;
+    float ta = 0.f, tb = 0.f;
+    if (TORSION) {
+      const float* tp = t_p + (size_t)(t0 + r0) * 8;
+      ta = lane < lim ? __ldg(tp + lane) : 0.f; tb = lane + 32 < lim ? __ldg(tp + lane + 32) : 0.f;
+    }
+    float x0[8], x1[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       const int r = min(r0 + u, nt - 1);
       const int kj = base + r + (r >= p_i ? 1 : 0);
-      const float4* sp = reinterpret_cast<const float4*>(sbf_p + (size_t)(t0 + r) * ld_p);
-      s0[u] = __ldg(sp); s1[u] = __ldg(sp + 1);
-      if (TORSION) {
-        const float4* tp = reinterpret_cast<const float4*>(t_p + (size_t)(t0 + r) * ld_p);
-        q0[u] = __ldg(tp); q1[u] = __ldg(tp + 1);
-      }
       x0[u] = __ldg(x_down + (size_t)kj * 64 + lane);
       x1[u] = __ldg(x_down + (size_t)kj * 64 + lane + 32);
     }
+    __syncwarp();
+    stage[w][0][lane] = sa; stage[w][0][lane + 32] = sb;
+    if (TORSION) { stage[w][1][lane] = ta; stage[w][1][lane + 32] = tb; }
+    __syncwarp();
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (r0 + u < nt) {
-        const float sv[8] = {s0[u].x, s0[u].y, s0[u].z, s0[u].w, s1[u].x, s1[u].y, s1[u].z, s1[u].w};
+    for (int u = 0; u < 8; ++u) {
+      if (u < n8) {
+        const float4 s0 = *reinterpret_cast<const float4*>(&stage[w][0][u * 8]);
+        const float4 s1 = *reinterpret_cast<const float4*>(&stage[w][0][u * 8 + 4]);
+        const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
         float g0 = 0.f, g1 = 0.f;
 #pragma unroll
         for (int q = 0; q < 8; ++q) { g0 = fmaf(ws2[0][q], sv[q], g0); g1 = fmaf(ws2[1][q], sv[q], g1); }
         float m0 = __fmul_rn(x0[u], g0), m1 = __fmul_rn(x1[u], g1);
         if (TORSION) {
-          const float tv[8] = {q0[u].x, q0[u].y, q0[u].z, q0[u].w, q1[u].x, q1[u].y, q1[u].z, q1[u].w};
+          const float4 q0 = *reinterpret_cast<const float4*>(&stage[w][1][u * 8]);
+          const float4 q1 = *reinterpret_cast<const float4*>(&stage[w][1][u * 8 + 4]);
+          const float tv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
           float h0 = 0.f, h1 = 0.f;
 #pragma unroll
           for (int q = 0; q < 8; ++q) { h0 = fmaf(wt2[0][q], tv[q], h0); h1 = fmaf(wt2[1][q], tv[q], h1); }
@@ -615,15 +626,15 @@ int dig3d_sphere_triplet_gather(const float* x_down, const float* sbf_p, const f
                                 float* m, void* stream) {
   DIG3D_REQUIRE(x_down && sbf_p && src && dst && row_ptr && trip_ptr && w_sbf2 && m, "sphere_triplet_gather: null pointer");
   DIG3D_REQUIRE((t_p != nullptr) == (w_t2 != nullptr), "sphere_triplet_gather: t_p and w_t2 must agree");
-  DIG3D_REQUIRE(ld_p % 4 == 0, "sphere_triplet_gather: ld_p must be a multiple of 4");
+  DIG3D_REQUIRE(ld_p == 8, "sphere_triplet_gather: expects the layer-major [T, 8] slices (ld_p == 8), got %d", ld_p);
   if (n_edges == 0) return DIG3D_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int gblocks = ceil_div(n_edges * 32, 256);
   if (t_p)
-    sphere_triplet_gather_kernel<true><<<gblocks, 256, 0, st>>>(x_down, sbf_p, t_p, ld_p, src, dst, row_ptr, trip_ptr,
+    sphere_triplet_gather_kernel<true><<<gblocks, 256, 0, st>>>(x_down, sbf_p, t_p, src, dst, row_ptr, trip_ptr,
                                                                (int)n_edges, w_sbf2, w_t2, m);
   else
-    sphere_triplet_gather_kernel<false><<<gblocks, 256, 0, st>>>(x_down, sbf_p, t_p, ld_p, src, dst, row_ptr, trip_ptr,
+    sphere_triplet_gather_kernel<false><<<gblocks, 256, 0, st>>>(x_down, sbf_p, t_p, src, dst, row_ptr, trip_ptr,
                                                                 (int)n_edges, w_sbf2, w_t2, m);
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
