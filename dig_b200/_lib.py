@@ -78,6 +78,7 @@ SIGNATURES = {
     "dig3d_tc_packed_floats": [c_int32, c_int32],
     "dig3d_tc_pack": [P, P, P, P, c_int32, P],
     "dig3d_tc_timeouts": [],
+    "dig3d_sphere_init_e_tc": [P, P, P, P, c_int64, POINTER(InitEWeights), P, P, P, P],
     "dig3d_sphere_update_e_a_tc": [P, P, c_int64, POINTER(TcUpdateE), P, P, P],
     "dig3d_sphere_triplet_gather": [P, P, P, c_int32, P, P, P, P, c_int64, P, P, P, P],
     "dig3d_sphere_update_e_b_tc": [P, P, P, P, P, c_int64, POINTER(TcUpdateE), P, P, P],

@@ -52,6 +52,7 @@ struct TcSmem {
   float wr[128 * 8];      // lin_rbf (kernel B) or lin_rbf2 (kernel A) rows, padded to 8
   float wr1[8 * 8];       // lin_rbf1 rows (kernel A), padded to 8
   int dst[TC_M];
+  int aux[2][TC_M];       // init_e: atomic numbers of the target / source node of each row
   uint64_t full[TC_STAGES], empty[TC_STAGES], a_ready, d_ready[2], d_free[2];
   uint32_t tmem_base;
 };
@@ -155,11 +156,13 @@ __device__ __forceinline__ void store_a(TcSmem& s, int row, int col, const float
 // Streaming accumulation of one GEMM: every finished K-chunk is added (round-to-nearest) into this thread's
 // fp32 registers, NP 16-column pieces starting at column col0; `it` is the global chunk counter shared
 // (by construction) with the MMA issuer.
-template <int NP>
+template <int NP, bool ZERO = true>
 __device__ __forceinline__ void epi_accumulate(TcSmem& s, uint32_t tl, int col0, int chunks, int& it,
                                                float (&acc)[NP * 16]) {
+  if (ZERO) {
 #pragma unroll
-  for (int i = 0; i < NP * 16; ++i) acc[i] = 0.f;
+    for (int i = 0; i < NP * 16; ++i) acc[i] = 0.f;
+  }
   for (int c = 0; c < chunks; ++c, ++it) {
     const int ab = it & 1;
     mbar_wait(&s.d_ready[ab], (it >> 1) & 1);
@@ -549,6 +552,133 @@ sphere_update_e_b_tc_kernel(const float* __restrict__ m, const float* __restrict
   if (warp == 0) tmem_dealloc(s.tmem_base, 256);
 }
 
+// ---------------------------------------------------------------------------------- init_e (tensor)
+// e1 = act(lin(cat[x_i, x_j, act(lin_rbf_0(rbf))])), e2 = lin_rbf_1(rbf) * e1        spherenet.py:79-91
+// The K = 384 contraction runs as three K = 128 panels whose A operand is rebuilt between panels (embedding rows
+// of the target nodes, of the source nodes, then the radial term); the per-chunk partial products keep
+// accumulating in the epilogue registers across the panels.
+struct TcInitParams {
+  TcGemm g[3];                 // the three K-panels of init_e.lin (bias applied at the end)
+  const float *emb, *w_rbf0, *b_rbf0, *b_lin, *w_rbf1;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+sphere_init_e_tc_kernel(const int64_t* __restrict__ z, const int32_t* __restrict__ src,
+                        const int32_t* __restrict__ dst, const float* __restrict__ rbf0, int n_edges, TcInitParams P,
+                        float* __restrict__ e1, float* __restrict__ v_in) {
+  extern __shared__ __align__(1024) unsigned char tc_raw[];
+  TcSmem& s = *reinterpret_cast<TcSmem*>(tc_raw);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int e0 = blockIdx.x * TC_M, rows = min(TC_M, n_edges - e0);
+  float* w0 = &s.bias[2][0];   // lin_rbf_0.weight [128][6] parked in the unused bias rows
+  if (tid == 0) {
+    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    mbar_init(&s.a_ready, TC_EPI_WARPS);
+    for (int i = 0; i < 2; ++i) { mbar_init(&s.d_ready[i], 1); mbar_init(&s.d_free[i], TC_EPI_WARPS); }
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&s.tmem_base, 256);
+  for (int i = tid; i < 128; i += TC_THREADS) { s.bias[0][i] = __ldg(P.b_lin + i); s.bias[1][i] = __ldg(P.b_rbf0 + i); }
+  for (int i = tid; i < 128 * 6; i += TC_THREADS) w0[i] = __ldg(P.w_rbf0 + i);
+  for (int i = tid; i < 128 * 8; i += TC_THREADS) s.wr[i] = (i % 8 < 6) ? __ldg(P.w_rbf1 + (i / 8) * 6 + i % 8) : 0.f;
+  for (int i = tid; i < TC_M; i += TC_THREADS) {
+    const int d = (i < rows) ? dst[e0 + i] : -1, sj = (i < rows) ? src[e0 + i] : -1;
+    s.dst[i] = d;
+    s.aux[0][i] = d >= 0 ? (int)z[d] : 0;
+    s.aux[1][i] = sj >= 0 ? (int)z[sj] : 0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) {
+    if (tid == 0) tc_producer(s, P.g);
+  } else if (warp == 1) {
+    if (tid == 32) tc_mma(s, P.g, s.tmem_base);
+  } else {
+    const EpiCtx c = epi_ctx(s);
+    const int fast = g_fast_swish, et = tid - 64;
+    const bool valid = c.row < rows;
+    const size_t ge = (size_t)(e0 + c.row);
+    const uint32_t tl = c.tm + ((uint32_t)c.lane_base << 16);
+    const int col0 = c.part * 32;
+    float rb[6];
+#pragma unroll
+    for (int n = 0; n < 6; ++n) rb[n] = valid ? __ldg(rbf0 + ge * 6 + n) : 0.f;
+    auto fill_embedding = [&](const int* zrow) {   // A = emb[z[node of row]]: one coalesced 512 B row per warp step
+#pragma unroll
+      for (int k = 0; k < TC_M * 32 / TC_EPI_THREADS; ++k) {
+        const int f = et + k * TC_EPI_THREADS, row = f >> 5, c4 = f & 31;
+        const float4 x = row < rows ? __ldg(reinterpret_cast<const float4*>(P.emb + (size_t)zrow[row] * 128) + c4)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 h, l;
+        split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
+        const int o = (c4 * TC_AKU + row) * 4;
+        *reinterpret_cast<float4*>(s.a_hi + o) = h;
+        *reinterpret_cast<float4*>(s.a_lo + o) = l;
+      }
+    };
+    int it = 0;
+    float acc[32];
+    fill_embedding(s.aux[0]);                       // panel 0: x_i
+    epi_done(s);
+    epi_accumulate<2, true>(s, tl, col0, 4, it, acc);
+    fill_embedding(s.aux[1]);                       // panel 1: x_j
+    epi_done(s);
+    epi_accumulate<2, false>(s, tl, col0, 4, it, acc);
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {                // panel 2: act(lin_rbf_0(rbf))        spherenet.py:87
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int col = col0 + cc * 16 + i;
+        float a = 0.f;
+#pragma unroll
+        for (int n = 0; n < 6; ++n) a = fmaf(w0[col * 6 + n], rb[n], a);
+        v[i] = valid ? swish_sel(a + s.bias[1][col], fast) : 0.f;
+      }
+      store_a(s, c.row, col0 + cc * 16, v);
+    }
+    epi_done(s);
+    epi_accumulate<2, false>(s, tl, col0, 4, it, acc);
+    // e1 = act(. + b), e2 = lin_rbf_1(rbf) * e1 (tile staged over the A planes), edge -> node sums
+    float* e2t = s.a_hi;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      float o[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int col = col0 + i + u;
+        o[u] = swish_sel(acc[i + u] + s.bias[0][col], fast);
+        float gsum = 0.f;
+#pragma unroll
+        for (int n = 0; n < 6; ++n) gsum = fmaf(s.wr[col * 8 + n], rb[n], gsum);
+        e2t[c.row * 132 + col] = gsum * o[u];
+      }
+      if (valid) *reinterpret_cast<float4*>(e1 + ge * 128 + col0 + i) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    tc_fence_before();
+    epi_bar();
+    const int col = tid - 64;
+    if (col < 128 && rows > 0) {
+      float run = 0.f;
+      int cur = s.dst[0];
+      bool first = true;
+      for (int r = 0; r < rows; ++r) {
+        const int d = s.dst[r];
+        if (d != cur) {
+          if (first) atomicAdd(v_in + (size_t)cur * 128 + col, run);
+          else v_in[(size_t)cur * 128 + col] = run;
+          first = false; run = 0.f; cur = d;
+        }
+        run += e2t[r * 132 + col];
+      }
+      atomicAdd(v_in + (size_t)cur * 128 + col, run);
+    }
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(s.tmem_base, 256);
+}
+
 static int tc_smem_attr(const void* fn, size_t bytes) {
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   if (e != cudaSuccess) {
@@ -601,6 +731,24 @@ int dig3d_tc_timeouts(void) {
   unsigned int v = 0;
   cudaMemcpyFromSymbol(&v, tc05::g_mbar_timeout, sizeof(v));
   return (int)v;
+}
+
+int dig3d_sphere_init_e_tc(const int64_t* z, const int32_t* src, const int32_t* dst, const float* rbf0,
+                           int64_t n_edges, const dig3d_init_e_weights* w, const float* packed_lin, float* e1,
+                           float* v_in, void* stream) {
+  DIG3D_REQUIRE(z && src && dst && rbf0 && w && packed_lin && e1 && v_in, "sphere_init_e_tc: null pointer");
+  DIG3D_REQUIRE(w->emb && w->w_rbf0 && w->b_rbf0 && w->b_lin && w->w_rbf1, "sphere_init_e_tc: null weight");
+  if (n_edges == 0) return DIG3D_OK;
+  TcInitParams P;
+  const size_t panel = (size_t)4 * 2 * 8 * 128 * 4;   // four K=32 chunks of [hi|lo][8][128][4] floats
+  for (int p = 0; p < 3; ++p) P.g[p] = {packed_lin + p * panel, nullptr, 128, 128};
+  P.emb = w->emb; P.w_rbf0 = w->w_rbf0; P.b_rbf0 = w->b_rbf0; P.b_lin = w->b_lin; P.w_rbf1 = w->w_rbf1;
+  int rc = tc_smem_attr((const void*)sphere_init_e_tc_kernel, sizeof(TcSmem));
+  if (rc) return rc;
+  sphere_init_e_tc_kernel<<<ceil_div(n_edges, TC_M), TC_THREADS, sizeof(TcSmem), (cudaStream_t)stream>>>(
+      z, src, dst, rbf0, (int)n_edges, P, e1, v_in);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
 }
 
 int dig3d_sphere_update_e_a_tc(const float* e1, const float* rbf0, int64_t n_edges, const dig3d_tc_update_e* w,

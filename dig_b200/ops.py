@@ -421,6 +421,32 @@ def tc_pack_update_e(m, torsion, cache):
     return w
 
 
+def tc_pack_matrix(weight, cache, key):
+    """Packed copy of one [N, K] weight (cached until the parameter changes)."""
+    k = (weight.data_ptr(), weight._version)
+    hit = cache.get(key)
+    if hit is None or hit[0] != k:
+        buf = torch.empty(2 * weight.numel(), dtype=torch.float32, device=weight.device)
+        wp = (ctypes.c_void_p * 1)(_p(weight.detach(), torch.float32, "w", 16).value)
+        op = (ctypes.c_void_p * 1)(buf.data_ptr())
+        ns = (ctypes.c_int32 * 1)(weight.size(0))
+        ks = (ctypes.c_int32 * 1)(weight.size(1))
+        call("dig3d_tc_pack", wp, ns, ks, op, 1, _stream())
+        hit = (k, buf)
+        cache[key] = hit
+    return hit[1]
+
+
+def sphere_init_e_tc(z, g, rbf0, w, packed_lin, hidden, v_in=None):
+    e1 = torch.empty(max(g.n_edges, 1), hidden, dtype=torch.float32, device=rbf0.device)[:g.n_edges]
+    if v_in is None:
+        v_in = torch.zeros(g.n_nodes, hidden, dtype=torch.float32, device=rbf0.device)
+    if g.n_edges:
+        call("dig3d_sphere_init_e_tc", _p(z, torch.int64, "z"), _p(g.src), _p(g.dst), _p(rbf0), g.n_edges,
+             ctypes.byref(w), _p(packed_lin), _p(e1), _p(v_in), _stream())
+    return e1, v_in
+
+
 def sphere_update_e_tc(e1, g, rbf0, sbf_p, t_p, col0, w, hidden, int_emb, v_in=None):
     """update_e (A + triplet gather + B) with the dense chain on tcgen05."""
     dev = e1.device

@@ -238,7 +238,13 @@ class _DimeNetFamily(nn.Module):
         v_all = torch.empty(L + 1, g.n_nodes, self.out_channels, dtype=torch.float32, device=dev)
         dense_tc = os.environ.get("DIG3D_DENSE", "tc") != "simt"
         tc_cache = self.__dict__.setdefault("_tc_cache", {})
-        e1, _ = ops.sphere_init_e(z, g, rbf0, ops.pack_init_e(self.init_e), self.hidden_channels, v_in=v_in_all[0])
+        if dense_tc:
+            packed = ops.tc_pack_matrix(self.init_e.lin.weight, tc_cache, "init_e.lin")
+            e1, _ = ops.sphere_init_e_tc(z, g, rbf0, ops.pack_init_e(self.init_e), packed, self.hidden_channels,
+                                         v_in=v_in_all[0])
+        else:
+            e1, _ = ops.sphere_init_e(z, g, rbf0, ops.pack_init_e(self.init_e), self.hidden_channels,
+                                      v_in=v_in_all[0])
         for l in range(L):
             sbf_p, t_p = proj[l // 4]
             if dense_tc:      # tcgen05 3xTF32 dense chain (csrc/spherenet_tc.cu)

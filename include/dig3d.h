@@ -196,6 +196,10 @@ typedef struct {
   const float *w_sbf2, *w_t2;                 /* [64,8] (w_t2 null => DimeNet++) */
 } dig3d_tc_update_e;
 
+/* init.forward on tcgen05; packed_lin = dig3d_tc_pack of init_e.lin.weight [128, 384] (one matrix, K = 384). */
+int dig3d_sphere_init_e_tc(const int64_t* z, const int32_t* src, const int32_t* dst, const float* rbf0,
+                           int64_t n_edges, const dig3d_init_e_weights* w, const float* packed_lin, float* e1,
+                           float* v_in, void* stream);
 int dig3d_sphere_update_e_a_tc(const float* e1, const float* rbf0, int64_t n_edges, const dig3d_tc_update_e* w,
                                float* x_ji, float* x_down, void* stream);
 /* m[e] = sum over the triplets of edge e of x_down[kj] * lin_sbf2(sbf_p) * lin_t2(t_p)   (spherenet.py:163-171);
