@@ -127,7 +127,8 @@ struct PrjSmem {
   float wt[TORSION ? BS::NY * BS::NR * PRJ_LD : 1];   // [c][lane]: w_t1[lane][c]
   float ws[BS::NB * PRJ_LD];                          // [c][lane]: w_sbf1[lane][c]
   float bess[PRJ_WARPS][BS::NB];
-  float y[PRJ_WARPS][32][NYT + BS::NS + 1];
+  static constexpr int YLD = ((NYT + BS::NS + 3) / 4) * 4;   // harmonics row, padded for float4 broadcasts
+  alignas(16) float y[PRJ_WARPS][32][YLD];
   int32_t trip[PRJ_WARPS][32];
 };
 
@@ -160,22 +161,25 @@ triplet_basis_project_kernel(const float* __restrict__ bess, const float* __rest
     __syncwarp();
     // per-edge radial contraction
     float R[NYT], Rs[NS];
-    if (TORSION) {
 #pragma unroll
-      for (int ab = 0; ab < NY; ++ab) {
-        float acc = 0.f;
+    for (int b = 0; b < NS; ++b) {     // radial order b outermost: its NR Bessel values are read once
+      float rb[NR];
 #pragma unroll
-        for (int r = 0; r < NR; ++r)
-          acc = fmaf(sm.bess[w][(ab % NS) * NR + r], sm.wt[(ab * NR + r) * PRJ_LD + lane], acc);
-        R[ab] = acc;
-      }
-    }
-#pragma unroll
-    for (int l = 0; l < NS; ++l) {
+      for (int r = 0; r < NR; ++r) rb[r] = sm.bess[w][b * NR + r];
       float acc = 0.f;
 #pragma unroll
-      for (int r = 0; r < NR; ++r) acc = fmaf(sm.bess[w][l * NR + r], sm.ws[(l * NR + r) * PRJ_LD + lane], acc);
-      Rs[l] = acc;
+      for (int r = 0; r < NR; ++r) acc = fmaf(rb[r], sm.ws[(b * NR + r) * PRJ_LD + lane], acc);
+      Rs[b] = acc;
+      if (TORSION) {
+#pragma unroll
+        for (int a = 0; a < NS; ++a) {
+          const int ab = a * NS + b;
+          float acc_t = 0.f;
+#pragma unroll
+          for (int r = 0; r < NR; ++r) acc_t = fmaf(rb[r], sm.wt[(ab * NR + r) * PRJ_LD + lane], acc_t);
+          R[ab] = acc_t;
+        }
+      }
     }
     // enumerate the out-edges e = (j -> i), i != k, of j: candidates are the nodes of j's graph
     const int jbase = row_ptr[j], dj = row_ptr[j + 1] - jbase;
@@ -218,16 +222,23 @@ triplet_basis_project_kernel(const float* __restrict__ bess, const float* __rest
       const int cnt = __popc(m);
       for (int s = 0; s < cnt; ++s) {
         const int tt = sm.trip[w][s];
+        // harmonics of triplet s: float4 broadcasts (row stride padded to a multiple of 4 floats)
+        float yv[PrjSmem<BS, TORSION>::YLD];
+#pragma unroll
+        for (int i = 0; i < PrjSmem<BS, TORSION>::YLD; i += 4) {
+          const float4 q = *reinterpret_cast<const float4*>(&sm.y[w][s][i]);
+          yv[i] = q.x; yv[i + 1] = q.y; yv[i + 2] = q.z; yv[i + 3] = q.w;
+        }
         float acc_s = 0.f;
 #pragma unroll
-        for (int l = 0; l < NS; ++l) acc_s = fmaf(sm.y[w][s][NYT + l], Rs[l], acc_s);
+        for (int l = 0; l < NS; ++l) acc_s = fmaf(yv[NYT + l], Rs[l], acc_s);
         // layer-major output [4][T][8]: each layer later streams its own contiguous 32 B per triplet
         const size_t o = ((size_t)(lane >> 3) * n_triplets + tt) * 8 + (lane & 7);
         sbf_p[o] = acc_s;
         if (TORSION) {
           float acc_t = 0.f;
 #pragma unroll
-          for (int ab = 0; ab < NY; ++ab) acc_t = fmaf(sm.y[w][s][ab], R[ab], acc_t);
+          for (int ab = 0; ab < NY; ++ab) acc_t = fmaf(yv[ab], R[ab], acc_t);
           t_p[o] = acc_t;
         }
       }
