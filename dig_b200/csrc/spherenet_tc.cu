@@ -65,14 +65,16 @@ struct TcGemm {
 
 // x * sigmoid(x).  Default: MUFU ex2/rcp approximations (measured on the B200: no effect on the energy error,
 // 3.9e-6 vs 4.4e-6, and a much shorter epilogue); libdevice expf + IEEE division selectable for experiments.
-__device__ int g_fast_swish = 1;
+static int h_fast_swish = 1;   // host-side switch, selects the kernel instantiation
 // optional timeline probe: CTA 0 of the tensor kernels records clock64() at protocol points (tools/gpu_tc_timeline.py)
 __device__ long long g_tc_trace[64];
 __device__ int g_tc_trace_on = 0;
 #define TC_TRACE(slot) do { if (g_tc_trace_on && blockIdx.x == 0) g_tc_trace[(slot)] = clock64(); } while (0)
-__device__ __forceinline__ float swish_sel(float x, int fast) {
-  return fast ? __fdividef(x, 1.0f + __expf(-x)) : __fdiv_rn(x, 1.0f + expf(-x));
+template <bool FAST>
+__device__ __forceinline__ float swish_t(float x) {
+  return FAST ? __fdividef(x, 1.0f + __expf(-x)) : __fdiv_rn(x, 1.0f + expf(-x));
 }
+#define swish_sel(x, fast) swish_t<FAST>(x)
 
 // ---- producer: stream every K-chunk of every GEMM of the chain through the ring
 template <int NG>
@@ -313,6 +315,7 @@ struct TcAParams {
   const float *w_rbf1, *w_rbf2;
 };
 
+template <bool FAST>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 sphere_update_e_a_tc_kernel(const float* __restrict__ e1, const float* __restrict__ rbf0, int n_edges, TcAParams P,
                             float* __restrict__ x_ji, float* __restrict__ x_down) {
@@ -341,7 +344,6 @@ sphere_update_e_a_tc_kernel(const float* __restrict__ e1, const float* __restric
     if (tid == 32) tc_mma(s, P.g, s.tmem_base);
   } else {
     const EpiCtx c = epi_ctx(s);
-    const int fast = g_fast_swish;
     const bool valid = c.row < rows;
     const size_t ge = (size_t)(e0 + c.row);
     const uint32_t tl = c.tm + ((uint32_t)c.lane_base << 16);
@@ -429,6 +431,7 @@ struct TcBParams {
   const float* w_rbf;          // [128, 6]
 };
 
+template <bool FAST>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 sphere_update_e_b_tc_kernel(const float* __restrict__ m, const float* __restrict__ x_ji,
                             const float* __restrict__ e1_in, const float* __restrict__ rbf0,
@@ -460,7 +463,6 @@ sphere_update_e_b_tc_kernel(const float* __restrict__ m, const float* __restrict
     if (tid == 32) tc_mma(s, P.g, s.tmem_base);
   } else {
     const EpiCtx c = epi_ctx(s);
-    const int fast = g_fast_swish;
     const bool valid = c.row < rows;
     const size_t ge = (size_t)(e0 + c.row);
     const uint32_t tl = c.tm + ((uint32_t)c.lane_base << 16);
@@ -562,6 +564,7 @@ struct TcInitParams {
   const float *emb, *w_rbf0, *b_rbf0, *b_lin, *w_rbf1;
 };
 
+template <bool FAST>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 sphere_init_e_tc_kernel(const int64_t* __restrict__ z, const int32_t* __restrict__ src,
                         const int32_t* __restrict__ dst, const float* __restrict__ rbf0, int n_edges, TcInitParams P,
@@ -596,7 +599,7 @@ sphere_init_e_tc_kernel(const int64_t* __restrict__ z, const int32_t* __restrict
     if (tid == 32) tc_mma(s, P.g, s.tmem_base);
   } else {
     const EpiCtx c = epi_ctx(s);
-    const int fast = g_fast_swish, et = tid - 64;
+    const int et = tid - 64;
     const bool valid = c.row < rows;
     const size_t ge = (size_t)(e0 + c.row);
     const uint32_t tl = c.tm + ((uint32_t)c.lane_base << 16);
@@ -714,9 +717,7 @@ int dig3d_tc_pack(const float* const* weights, const int32_t* n, const int32_t* 
 }
 
 int dig3d_tc_set_fast_swish(int32_t on) {
-  int v = on ? 1 : 0;
-  cudaError_t e = cudaMemcpyToSymbol(g_fast_swish, &v, sizeof(v));
-  if (e != cudaSuccess) { set_error("tc_set_fast_swish: %s", cudaGetErrorString(e)); return DIG3D_ECUDA; }
+  h_fast_swish = on ? 1 : 0;
   return DIG3D_OK;
 }
 
@@ -743,10 +744,11 @@ int dig3d_sphere_init_e_tc(const int64_t* z, const int32_t* src, const int32_t* 
   const size_t panel = (size_t)4 * 2 * 8 * 128 * 4;   // four K=32 chunks of [hi|lo][8][128][4] floats
   for (int p = 0; p < 3; ++p) P.g[p] = {packed_lin + p * panel, nullptr, 128, 128};
   P.emb = w->emb; P.w_rbf0 = w->w_rbf0; P.b_rbf0 = w->b_rbf0; P.b_lin = w->b_lin; P.w_rbf1 = w->w_rbf1;
-  int rc = tc_smem_attr((const void*)sphere_init_e_tc_kernel, sizeof(TcSmem));
+  auto kfn = h_fast_swish ? sphere_init_e_tc_kernel<true> : sphere_init_e_tc_kernel<false>;
+  int rc = tc_smem_attr((const void*)kfn, sizeof(TcSmem));
   if (rc) return rc;
-  sphere_init_e_tc_kernel<<<ceil_div(n_edges, TC_M), TC_THREADS, sizeof(TcSmem), (cudaStream_t)stream>>>(
-      z, src, dst, rbf0, (int)n_edges, P, e1, v_in);
+  kfn<<<ceil_div(n_edges, TC_M), TC_THREADS, sizeof(TcSmem), (cudaStream_t)stream>>>(z, src, dst, rbf0, (int)n_edges, P,
+                                                                                    e1, v_in);
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
 }
@@ -760,10 +762,11 @@ int dig3d_sphere_update_e_a_tc(const float* e1, const float* rbf0, int64_t n_edg
   P.g[1] = {w->p_kj, w->b_kj, 128, 128};
   P.g[2] = {w->p_down, nullptr, 128, 64};
   P.w_rbf1 = w->w_rbf1; P.w_rbf2 = w->w_rbf2;
-  int rc = tc_smem_attr((const void*)sphere_update_e_a_tc_kernel, sizeof(TcSmem));
+  auto kfn = h_fast_swish ? sphere_update_e_a_tc_kernel<true> : sphere_update_e_a_tc_kernel<false>;
+  int rc = tc_smem_attr((const void*)kfn, sizeof(TcSmem));
   if (rc) return rc;
-  sphere_update_e_a_tc_kernel<<<ceil_div(n_edges, TC_M), TC_THREADS, sizeof(TcSmem), (cudaStream_t)stream>>>(
-      e1, rbf0, (int)n_edges, P, x_ji, x_down);
+  kfn<<<ceil_div(n_edges, TC_M), TC_THREADS, sizeof(TcSmem), (cudaStream_t)stream>>>(e1, rbf0, (int)n_edges, P, x_ji,
+                                                                                    x_down);
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
 }
@@ -800,10 +803,11 @@ int dig3d_sphere_update_e_b_tc(const float* m, const float* e1_in, const float* 
   P.g[3] = {w->p_lin, w->b_lin, 128, 128};
   for (int i = 2; i < 6; ++i) P.g[2 + i] = {w->p_res[i], w->b_res[i], 128, 128};
   P.w_rbf = w->w_rbf;
-  int rc = tc_smem_attr((const void*)sphere_update_e_b_tc_kernel, sizeof(TcSmem));
+  auto kfn = h_fast_swish ? sphere_update_e_b_tc_kernel<true> : sphere_update_e_b_tc_kernel<false>;
+  int rc = tc_smem_attr((const void*)kfn, sizeof(TcSmem));
   if (rc) return rc;
-  sphere_update_e_b_tc_kernel<<<ceil_div(n_edges, TC_M), TC_THREADS, sizeof(TcSmem), st>>>(
-      m, x_ji, e1_in, rbf0, dst, (int)n_edges, P, e1_out, v_in);
+  kfn<<<ceil_div(n_edges, TC_M), TC_THREADS, sizeof(TcSmem), st>>>(m, x_ji, e1_in, rbf0, dst, (int)n_edges, P, e1_out,
+                                                                   v_in);
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
 }
