@@ -288,3 +288,77 @@ def test_baseline_configs_full_size(cfg):
         ref = fn({k: v.to(dev) for k, v in sd.items()}, b.z, b.pos, b.batch, **kw)
     assert u.shape == ref.shape and torch.isfinite(u).all()
     assert rel_err(u.cpu().numpy(), ref.cpu().numpy()) < TOL
+
+
+@pytest.mark.parametrize("cls_name", ["SphereNet", "DimeNetPP"])
+def test_tensor_core_chain_matches_fp32_twin(cls_name):
+    """update_e on tcgen05 (3xTF32, streaming accumulation) vs the exact-fp32 FFMA twin, one block, and no
+    mbarrier wait ever hit its spin bound."""
+    from dig_b200 import ops
+    from dig_b200.data import synthetic_batch
+    from dig_b200.threedgraph import method
+    dev = torch.device("cuda:0")
+    tors = cls_name == "SphereNet"
+    model = getattr(method, cls_name)()
+    model.load_state_dict(formula_state_dict(model.state_dict(), seed=2))
+    model = model.to(dev)
+    b = synthetic_batch(24, "qm9", seed=2, variable=True).to(dev)      # ragged: last tile partially filled
+    g = ops.build_graph(b.pos, b.batch, 5.0, num_graphs=24)
+    ops.triplet_geometry(g, b.pos, use_torsion=tors, want_idx=False)
+    rbf0, bess = ops.edge_basis(g.dist, 5.0, 5, model.emb.dist_emb.freq, 0, not tors, 6, 42)
+    w_s, w_t = model._projection_rows(0, 4)
+    sbf_p, t_p = ops.triplet_basis_project(g, bess, 0, w_s, w_t)
+    e1_s, v_s = ops.sphere_init_e(b.z, g, rbf0, ops.pack_init_e(model.init_e), 128)
+    packed = ops.tc_pack_matrix(model.init_e.lin.weight, {}, "k")
+    e1_t, v_t = ops.sphere_init_e_tc(b.z, g, rbf0, ops.pack_init_e(model.init_e), packed, 128)
+    assert rel_err(e1_t.cpu().numpy(), e1_s.cpu().numpy()) < TOL and rel_err(v_t.cpu().numpy(), v_s.cpu().numpy()) < TOL
+    ue = model.update_es[1]
+    e_ref, v_ref = ops.sphere_update_e(e1_s, g, rbf0, sbf_p, t_p, 8, ops.pack_update_e(ue, tors), 128, 64)
+    e_tc, v_tc, _, _ = ops.sphere_update_e_tc(e1_s, g, rbf0, sbf_p, t_p, 8, ops.tc_pack_update_e(ue, tors, {}), 128, 64)
+    assert rel_err(e_tc.cpu().numpy(), e_ref.cpu().numpy()) < TOL
+    assert rel_err(v_tc.cpu().numpy(), v_ref.cpu().numpy()) < TOL
+    assert ops.tc_timeouts() == 0
+
+
+def test_packed_weights_follow_parameter_updates():
+    """The tcgen05 weight cache is keyed on tensor._version: an in-place optimiser-style update must be seen."""
+    from dig_b200.data import synthetic_batch
+    from dig_b200.threedgraph.method import DimeNetPP
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    model = DimeNetPP().to(dev)
+    b = synthetic_batch(4, "qm9", seed=1).to(dev)
+    with torch.no_grad():
+        u0 = model(b)
+        model.update_es[0].lin_kj.weight.mul_(0.5)
+        u1 = model(b)
+        model.update_es[0].lin_kj.weight.mul_(2.0)
+        u2 = model(b)
+    assert not torch.allclose(u0, u1) and torch.equal(u0, u2)
+
+
+@pytest.mark.parametrize("cls_name,kw", [
+    ("SphereNet", dict(num_layers=2, out_channels=3, num_output_layers=2, cutoff=4.0)),
+    ("DimeNetPP", dict(num_layers=6, out_channels=2, num_output_layers=1, cutoff=5.0)),
+    ("SphereNet", dict(num_layers=5, num_spherical=3, cutoff=5.0)),
+])
+def test_non_default_hyperparameters(cls_name, kw):
+    """Constructor options that change the kernel schedule (layer count != 4 -> padded / multiple projection
+    groups; several output channels; fewer output layers) against the oracle on the same GPU."""
+    from dig_b200.data import synthetic_batch
+    from dig_b200.threedgraph import method
+    from oracle import restated
+    dev = torch.device("cuda:0")
+    model = getattr(method, cls_name)(**kw)
+    sd = formula_state_dict(model.state_dict(), seed=11)
+    model.load_state_dict(sd)
+    model = model.to(dev)
+    b = synthetic_batch(5, "qm9", seed=8, variable=True).to(dev)
+    with torch.no_grad():
+        u = model(b)
+    ref = restated.dimenet_family_forward({k: v.to(dev) for k, v in sd.items()}, b.z, b.pos, b.batch,
+                                          torsion=(cls_name == "SphereNet"), cutoff=kw["cutoff"],
+                                          num_layers=kw["num_layers"], num_spherical=kw.get("num_spherical", 7),
+                                          num_output_layers=kw.get("num_output_layers", 3))
+    assert u.shape == ref.shape == (5, kw.get("out_channels", 1))
+    assert rel_err(u.cpu().numpy(), ref.cpu().numpy()) < TOL
