@@ -422,7 +422,8 @@ def tc_pack_update_e(m, torsion, cache):
 
 
 def tc_pack_matrix(weight, cache, key):
-    """Packed copy of one [N, K] weight (cached until the parameter changes)."""
+    """Packed copy of one [N, K] weight (cached until the parameter changes).  The buffer is OWNED by `cache`:
+    keep the dict alive until the kernels that read it have run (the model keeps it for its lifetime)."""
     k = (weight.data_ptr(), weight._version)
     hit = cache.get(key)
     if hit is None or hit[0] != k:

@@ -309,12 +309,13 @@ def test_tensor_core_chain_matches_fp32_twin(cls_name):
     w_s, w_t = model._projection_rows(0, 4)
     sbf_p, t_p = ops.triplet_basis_project(g, bess, 0, w_s, w_t)
     e1_s, v_s = ops.sphere_init_e(b.z, g, rbf0, ops.pack_init_e(model.init_e), 128)
-    packed = ops.tc_pack_matrix(model.init_e.lin.weight, {}, "k")
+    cache = {}     # owns the packed weight buffers: must outlive the kernels that read them
+    packed = ops.tc_pack_matrix(model.init_e.lin.weight, cache, "k")
     e1_t, v_t = ops.sphere_init_e_tc(b.z, g, rbf0, ops.pack_init_e(model.init_e), packed, 128)
     assert rel_err(e1_t.cpu().numpy(), e1_s.cpu().numpy()) < TOL and rel_err(v_t.cpu().numpy(), v_s.cpu().numpy()) < TOL
     ue = model.update_es[1]
     e_ref, v_ref = ops.sphere_update_e(e1_s, g, rbf0, sbf_p, t_p, 8, ops.pack_update_e(ue, tors), 128, 64)
-    e_tc, v_tc, _, _ = ops.sphere_update_e_tc(e1_s, g, rbf0, sbf_p, t_p, 8, ops.tc_pack_update_e(ue, tors, {}), 128, 64)
+    e_tc, v_tc, _, _ = ops.sphere_update_e_tc(e1_s, g, rbf0, sbf_p, t_p, 8, ops.tc_pack_update_e(ue, tors, cache), 128, 64)
     assert rel_err(e_tc.cpu().numpy(), e_ref.cpu().numpy()) < TOL
     assert rel_err(v_tc.cpu().numpy(), v_ref.cpu().numpy()) < TOL
     assert ops.tc_timeouts() == 0

@@ -14,7 +14,8 @@ g = ops.build_graph(b.pos, b.batch, 5.0, num_graphs=128)
 ops.triplet_geometry(g, b.pos, use_torsion=True, want_idx=False)
 rbf0, bess = ops.edge_basis(g.dist, 5.0, 5, model.emb.dist_emb.freq, 0, False, 6, 42)
 e1, _ = ops.sphere_init_e(b.z, g, rbf0, ops.pack_init_e(model.init_e), 128)
-wt = ops.tc_pack_update_e(model.update_es[0], True, {})
+_cache = {}
+wt = ops.tc_pack_update_e(model.update_es[0], True, _cache)
 x_ji = torch.empty(g.n_edges, 128, device=dev); x_down = torch.empty(g.n_edges, 64, device=dev)
 lib = _lib.load()
 for _ in range(3):
