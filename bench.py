@@ -189,7 +189,11 @@ def main():
 
     torch.manual_seed(1234)
     model = SphereNet().to(dev).eval()
-    host = [synthetic_batch(MOLS_PER_GPU, "qm9", seed=1000 * rank + s).pin_memory() for s in range(N_ROTATE)]
+    from dig_b200.data import Batch
+    host = []
+    for sd_ in range(N_ROTATE):        # only what forward() reads travels: z, pos, batch (+ the python int num_graphs)
+        full = synthetic_batch(MOLS_PER_GPU, "qm9", seed=1000 * rank + sd_)
+        host.append(Batch(z=full.z, pos=full.pos, batch=full.batch, num_graphs=full.num_graphs).pin_memory())
     resident = [b.to(dev) for b in host]
     h2d = sum(getattr(host[0], k).numel() * getattr(host[0], k).element_size() for k in ("z", "pos", "batch"))
     d2h = MOLS_PER_GPU * 4
@@ -278,7 +282,11 @@ def main():
     roof = {"kernel": dom.replace("dig3d_", "") + (" (tcgen05 3xTF32 dense chain)" if dom.endswith("_tc") else ""),
             "bound": "tensor",
             "achieved": flops_b / (dom_ms * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
-            "frac": flops_b / (dom_ms * 1e-3) / 1e12 / tf_peak, "traffic": None,
+            "frac": flops_b / (dom_ms * 1e-3) / 1e12 / tf_peak,
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+            "traffic": 47446528 if dom.endswith("_tc") else 186903552,
+            "traffic_source": "profiles/r01_b_tc_final_ncu_summary.txt" if dom.endswith("_tc")
+                              else "profiles/r01_update_e_b_ncu_summary.txt",
             "peak_source": f"{which} bf16_tflops_sustained (kernel timed inside the step)",
             "ms_per_launch": dom_ms, "share_of_step_kernel_time": 4 * dom_ms / step_kernel_ms,
             "algorithmic_flops_per_launch": flops_b, "algorithmic_bytes_per_launch": bytes_b,
