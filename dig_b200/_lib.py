@@ -91,6 +91,17 @@ SIGNATURES = {
     "dig3d_comenet_embed": [P, P, c_int64, P, P],
     "dig3d_comenet_block": [P, P, P, P, P, P, P, c_int64, c_int64, c_int64, POINTER(ComenetBlockWeights),
                             POINTER(ComenetHeadWeights), c_int32, P, P, P, P, P, P, P, P],
+    "dig3d_linear": [P, c_int64, c_int32, c_int32, P, P, P, P],
+    "dig3d_wgrad": [P, P, c_int64, c_int32, c_int32, P, P, P],
+    "dig3d_act": [P, c_int64, c_int32, P, P],
+    "dig3d_act_bwd": [P, P, c_int64, c_int32, P, P],
+    "dig3d_ewise": [P, P, c_int64, c_int32, P, P],
+    "dig3d_rowscale": [P, P, c_int64, c_int32, P, P],
+    "dig3d_gather_rows": [P, P, c_int32, c_int64, c_int32, P, P],
+    "dig3d_scatter_add_rows": [P, P, c_int32, c_int64, c_int32, P, P],
+    "dig3d_rbf_freq_grad": [P, c_int64, c_double, c_int32, P, c_int32, P, P, P],
+    "dig3d_transpose": [P, c_int32, c_int32, P, P],
+    "dig3d_schnet_edge_features": [P, c_int64, P, c_int32, c_double, c_double, P, P, P],
 }
 _RESTYPES = {"dig3d_last_error": c_char_p}
 

@@ -1,0 +1,255 @@
+"""Autograd Functions over the hand-written training primitives (csrc/train_ops.cu).
+
+The reference trains with `loss.backward()` over ATen ops (run.py:117-123).  Here torch.autograd only keeps the
+tape: every forward AND backward computation below is a kernel of libdig3d.so (ops.linear / ops.wgrad / ...).
+Nothing here has a CPU path; double backward (needed for force training, run.py:110-115) is not implemented and
+raises.
+"""
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import ops
+
+SWISH, SSP = 0, 1
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = _c(x)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return ops.linear(x, _c(weight.detach()), None if bias is None else bias.detach())
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = _c(dy)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.linear(dy, ops.transpose(_c(weight.detach())), None)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw, db = ops.wgrad(dy, x, tuple(weight.shape), ctx.has_bias)
+        return dx, dw, db
+
+
+class _Act(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mode):
+        x = _c(x)
+        ctx.save_for_backward(x)
+        ctx.mode = mode
+        return ops.act(x, mode)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return ops.act_bwd(x, _c(dy), ctx.mode), None
+
+
+class _Mul(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _c(a), _c(b)
+        ctx.save_for_backward(a, b)
+        return ops.ewise(a, b, 0)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        a, b = ctx.saved_tensors
+        dy = _c(dy)
+        da = ops.ewise(dy, b, 0) if ctx.needs_input_grad[0] else None
+        db = ops.ewise(dy, a, 0) if ctx.needs_input_grad[1] else None
+        return da, db
+
+
+class _Add(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        return ops.ewise(_c(a), _c(b), 1)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        return dy, dy
+
+
+class _RowScale(torch.autograd.Function):
+    """y[r, :] = a[r, :] * s[r]; s is geometry (no gradient without force training)."""
+
+    @staticmethod
+    def forward(ctx, a, s):
+        ctx.save_for_backward(s)
+        return ops.rowscale(_c(a), s)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        (s,) = ctx.saved_tensors
+        return ops.rowscale(_c(dy), s), None
+
+
+class _GatherRows(torch.autograd.Function):
+    """y = x[idx].  Backward: segment sum when idx is sorted and its CSR pointers are given, atomics otherwise."""
+
+    @staticmethod
+    def forward(ctx, x, idx, ptr):
+        ctx.save_for_backward(idx, ptr if ptr is not None else idx)
+        ctx.has_ptr = ptr is not None
+        ctx.n_rows = x.size(0)
+        return ops.gather_rows(_c(x), idx)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        idx, ptr = ctx.saved_tensors
+        dy = _c(dy)
+        if ctx.has_ptr:
+            return ops.segment_sum(dy.view(dy.size(0), -1), ptr).view((ctx.n_rows,) + tuple(dy.shape[1:])), None, None
+        return ops.scatter_add_rows(dy, idx, ctx.n_rows), None, None
+
+
+class _SegmentSum(torch.autograd.Function):
+    """out[s] = sum of the rows r with idx[r] == s, idx sorted with CSR pointers ptr."""
+
+    @staticmethod
+    def forward(ctx, x, ptr, idx):
+        ctx.save_for_backward(idx)
+        return ops.segment_sum(_c(x), ptr)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        return ops.gather_rows(_c(dy), idx), None, None
+
+
+class _ScatterAddRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, idx, n_rows):
+        ctx.save_for_backward(idx)
+        return ops.scatter_add_rows(_c(y), idx, n_rows)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        (idx,) = ctx.saved_tensors
+        return ops.gather_rows(_c(dout), idx), None, None
+
+
+def linear(x, weight, bias=None):
+    return _Linear.apply(x, weight, bias)
+
+
+def lin(module, x):
+    """Apply an nn.Linear-like module (attributes weight, bias)."""
+    return _Linear.apply(x, module.weight, getattr(module, "bias", None))
+
+
+def swish(x):
+    return _Act.apply(x, SWISH)
+
+
+def ssp(x):
+    return _Act.apply(x, SSP)
+
+
+def mul(a, b):
+    return _Mul.apply(a, b)
+
+
+def add(a, b):
+    return _Add.apply(a, b)
+
+
+def rowscale(a, s):
+    return _RowScale.apply(a, s)
+
+
+def gather_rows(x, idx, ptr=None):
+    return _GatherRows.apply(x, idx, ptr)
+
+
+def segment_sum(x, ptr, idx):
+    return _SegmentSum.apply(x, ptr, idx)
+
+
+def scatter_add_rows(y, idx, n_rows):
+    return _ScatterAddRows.apply(y, idx, n_rows)
+
+
+class _EdgeBasis(torch.autograd.Function):
+    """rbf0 = envelope(d/c) * sin(freq * d/c) (differentiable in freq) and the fixed Bessel basis of the edges."""
+
+    @staticmethod
+    def forward(ctx, freq, dist, cutoff, exponent, basis_id, env_on_bessel, nr, n_bessel):
+        rbf0, bess = ops.edge_basis(dist, cutoff, exponent, freq, basis_id, envelope_on_bessel=env_on_bessel,
+                                    num_radial=nr, n_bessel=n_bessel)
+        ctx.save_for_backward(freq, dist)
+        ctx.cfg = (cutoff, exponent)
+        ctx.mark_non_differentiable(bess)
+        return rbf0, bess
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, drbf0, _dbess):
+        freq, dist = ctx.saved_tensors
+        return (ops.rbf_freq_grad(dist, ctx.cfg[0], ctx.cfg[1], freq, _c(drbf0)),) + (None,) * 7
+
+
+class _BasisProject(torch.autograd.Function):
+    """lin_sbf1(sbf) / lin_t1(tbf) of up to four layers with the fused basis-projection kernel (basis.cu); the
+    [T, ns*nr] / [T, ns*ns*nr] bases are only materialised in backward, for the weight gradients."""
+
+    @staticmethod
+    def forward(ctx, g, bess, basis_id, ns, nr, n_layers, torsion, *weights):
+        def rows(ws):
+            w = torch.cat([w_.detach() for w_ in ws], 0)
+            if w.size(0) < 32:
+                w = torch.cat([w, w.new_zeros(32 - w.size(0), w.size(1))], 0)
+            return w.contiguous()
+        w_s = rows(weights[:n_layers])
+        w_t = rows(weights[n_layers:]) if torsion else None
+        sbf_p, t_p = ops.triplet_basis_project(g, bess, basis_id, w_s, w_t)
+        ctx.g, ctx.cfg = g, (basis_id, ns, nr, n_layers, torsion)
+        ctx.save_for_backward(bess)
+        ctx.set_materialize_grads(False)
+        outs = [sbf_p[l] for l in range(n_layers)]
+        if torsion:
+            outs += [t_p[l] for l in range(n_layers)]
+        return tuple(outs)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, *grads):
+        (bess,) = ctx.saved_tensors
+        basis_id, ns, nr, n_layers, torsion = ctx.cfg
+        g = ctx.g
+        sbf, tbf = ops.triplet_basis(bess, g.angle, g.torsion, g.idx_kj, basis_id, ns, nr, want_tbf=torsion)
+        out = []
+        for l in range(n_layers):
+            out.append(None if grads[l] is None else ops.wgrad(_c(grads[l]), sbf, (8, ns * nr), False)[0])
+        if torsion:
+            for l in range(n_layers):
+                d = grads[n_layers + l]
+                out.append(None if d is None else ops.wgrad(_c(d), tbf, (8, ns * ns * nr), False)[0])
+        return (None,) * 7 + tuple(out)
+
+
+def edge_basis(freq, dist, cutoff, exponent, basis_id, env_on_bessel, nr, n_bessel):
+    return _EdgeBasis.apply(freq, dist, cutoff, exponent, basis_id, env_on_bessel, nr, n_bessel)
+
+
+def basis_project(g, bess, basis_id, ns, nr, sbf1_weights, t1_weights):
+    """-> (list of sbf_p[l] [T, 8], list of t_p[l] [T, 8] or None) for len(sbf1_weights) <= 4 layers."""
+    n = len(sbf1_weights)
+    torsion = t1_weights is not None
+    outs = _BasisProject.apply(g, bess, basis_id, ns, nr, n, torsion, *sbf1_weights, *(t1_weights or []))
+    return list(outs[:n]), (list(outs[n:]) if torsion else None)

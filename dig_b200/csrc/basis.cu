@@ -79,6 +79,25 @@ __global__ void edge_basis_kernel(const float* __restrict__ dist, int n_edges, f
   }
 }
 
+
+// d(loss)/d(freq[n]) = sum_e drbf0[e][n] * env(x_e) * cos(freq[n] * x_e) * x_e     (training path; rbf0 = env * sin(freq x),
+// reference spherenet/features.py:180-182 -- freq is the only trainable tensor of the basis layers)
+__global__ void rbf_freq_grad_kernel(const float* __restrict__ dist, int64_t n_edges, float inv_cutoff, int p, float ea,
+                                     float eb, float ec, const float* __restrict__ freq, int nr,
+                                     const float* __restrict__ drbf0, float* __restrict__ dfreq) {
+  float part[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (int64_t)gridDim.x * blockDim.x) {
+    const float x = __fmul_rn(dist[e], inv_cutoff);
+    const float ex = envelope(x, p, ea, eb, ec) * x;
+    for (int n = 0; n < nr; ++n) part[n] = fmaf(drbf0[e * nr + n], ex * cosf(__ldg(freq + n) * x), part[n]);
+  }
+  for (int n = 0; n < nr; ++n) {
+    float v = part[n];
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(dfreq + n, v);
+  }
+}
+
 template <class BS>
 __global__ void triplet_basis_kernel(const float* __restrict__ bess, const float* __restrict__ angle,
                                      const float* __restrict__ torsion, const int32_t* __restrict__ idx_kj,
@@ -278,6 +297,20 @@ int dig3d_edge_basis(const float* dist, int64_t n_edges, double cutoff, int32_t 
     case 2: launch_edge_basis<G23>(dist, n_edges, cutoff, envelope_exponent, freq, envelope_on_bessel, rbf0, bess, st); break;
     default: set_error("edge_basis: unknown basis_id %d", basis_id); return DIG3D_EUNSUPPORTED;
   }
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_rbf_freq_grad(const float* dist, int64_t n_edges, double cutoff, int32_t envelope_exponent,
+                        const float* freq, int32_t num_radial, const float* drbf0, float* dfreq, void* stream) {
+  DIG3D_REQUIRE(dist && freq && drbf0 && dfreq && num_radial > 0 && num_radial <= 8, "rbf_freq_grad: bad arguments");
+  if (n_edges == 0) return DIG3D_OK;
+  const int p = envelope_exponent + 1;
+  const float a = (float)(-(p + 1) * (p + 2) / 2.0), b = (float)(p * (p + 2)), c = (float)(-p * (p + 1) / 2.0);
+  int grid = ceil_div(n_edges, 256);
+  if (grid > 592) grid = 592;
+  rbf_freq_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dist, n_edges, 1.0f / (float)cutoff, p, a, b, c, freq,
+                                                               num_radial, drbf0, dfreq);
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
 }

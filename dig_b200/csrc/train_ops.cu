@@ -1,0 +1,325 @@
+// Differentiable primitives for the TRAINING path (sm_100a, exact fp32).
+//
+// The fused inference kernels do not keep activations.  Training (reference run.py:103-135: forward,
+// loss.backward(), optimizer.step()) runs the same math as a composition of the primitives below, each with a
+// hand-written forward and backward kernel; torch.autograd only records the tape (dig_b200/autograd.py).
+//
+//   linear        y = x W^T + b                 nn.Linear at every call site of the models
+//   wgrad         dW += dY^T X, db += colsum dY
+//   act           swish / shifted softplus (+ derivative kernels)     spherenet.py:14, schnet.py:97-103
+//   mul / add / scale
+//   gather_rows   y = x[idx]                    x[i], x[j], x_kj[idx_kj] ...        (bwd: scatter_add_rows)
+//   scatter_add_rows                            atomics; used for unsorted indices (sources, idx_kj)
+//   (segment_sum over a sorted index lives in graph.cu)
+//
+// These are correctness-first kernels (first training path): tiled FFMA GEMMs for the big shapes, simple
+// one-thread-per-output kernels for the skinny ones (K or N in {1, 6, 8, 42, 50, ...}).
+#include "dense.cuh"
+
+namespace dig3d {
+
+// ------------------------------------------------------------------ linear, tiled (K % 32 == 0, NOUT in {64,128,256})
+template <int NOUT, int K>
+struct LinSmem {
+  float a[64 * (K + 4)];
+  float ws[2 * NOUT * LDW];
+};
+
+template <int NOUT, int K>
+__global__ void __launch_bounds__(DT, 1)
+linear_tiled_kernel(const float* __restrict__ x, int rows_total, const float* __restrict__ w,
+                    const float* __restrict__ bias, float* __restrict__ y) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  LinSmem<NOUT, K>& s = *reinterpret_cast<LinSmem<NOUT, K>*>(smem_raw);
+  const int r0 = blockIdx.x * 64, rows = min(64, rows_total - r0);
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  tile_load<K>(s.a, K + 4, x + (size_t)r0 * K, K, rows);
+  for (int id = threadIdx.x; id < (64 - rows) * K; id += DT) s.a[(rows + id / K) * (K + 4) + id % K] = 0.f;
+  __syncthreads();
+  float acc[4][NOUT / 16];
+  zero_acc(acc);
+  gemm_tile<64, NOUT, K>(s.a, K + 4, w, K, s.ws, acc);
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int r = ty * 4 + p;
+    if (r < rows) {
+#pragma unroll
+      for (int q = 0; q < NOUT / 16; ++q) {
+        const int c = tx + 16 * q;
+        y[(size_t)(r0 + r) * NOUT + c] = acc[p][q] + (bias ? __ldg(bias + c) : 0.f);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ linear, naive (any shape)
+__global__ void linear_naive_kernel(const float* __restrict__ x, int64_t rows, int k, int nout,
+                                    const float* __restrict__ w, const float* __restrict__ bias,
+                                    float* __restrict__ y) {
+  const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= rows * nout) return;
+  const int64_t r = id / nout;
+  const int c = (int)(id % nout);
+  const float* xr = x + r * k;
+  const float* wr = w + (size_t)c * k;
+  float acc = 0.f;
+  for (int i = 0; i < k; ++i) acc = fmaf(__ldg(xr + i), __ldg(wr + i), acc);
+  y[id] = acc + (bias ? __ldg(bias + c) : 0.f);
+}
+
+// ------------------------------------------------------------------ weight gradient: dW[n][k] += sum_r dY[r][n] X[r][k]
+// grid = (ceil(K/32), ceil(NOUT/32), row splits); each CTA owns a 32 x 32 block of dW and a slice of the rows.
+__global__ void __launch_bounds__(256)
+wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x, int64_t rows, int nout, int k,
+             float* __restrict__ dw, float* __restrict__ db) {
+  __shared__ float sdy[32][33];
+  __shared__ float sx[32][33];
+  const int kb = blockIdx.x * 32, nb = blockIdx.y * 32;
+  const int tn = threadIdx.x >> 5, tk = threadIdx.x & 31;   // thread owns dW[nb + tn + 8*i][kb + tk], i < 4
+  const int64_t per = (rows + gridDim.z - 1) / gridDim.z;
+  const int64_t r_lo = (int64_t)blockIdx.z * per, r_hi = min(rows, r_lo + per);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float bacc = 0.f;   // column sums of dY for db (threads with tk == 0... computed by lanes below)
+  for (int64_t r0 = r_lo; r0 < r_hi; r0 += 32) {
+    // stage 32 rows of dY[:, nb:nb+32] and X[:, kb:kb+32]
+    for (int id = threadIdx.x; id < 32 * 32; id += 256) {
+      const int rr = id >> 5, cc = id & 31;
+      const int64_t r = r0 + rr;
+      sdy[rr][cc] = (r < r_hi && nb + cc < nout) ? __ldg(dy + r * nout + nb + cc) : 0.f;
+      sx[rr][cc] = (r < r_hi && kb + cc < k) ? __ldg(x + r * k + kb + cc) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int rr = 0; rr < 32; ++rr) {
+      const float xv = sx[rr][tk];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = fmaf(sdy[rr][tn + 8 * i], xv, acc[i]);
+    }
+    if (db && blockIdx.x == 0 && threadIdx.x < 32) {
+      float sum = 0.f;
+#pragma unroll 8
+      for (int rr = 0; rr < 32; ++rr) sum += sdy[rr][threadIdx.x];
+      bacc += sum;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = nb + tn + 8 * i, kk = kb + tk;
+    if (n < nout && kk < k) atomicAdd(dw + (size_t)n * k + kk, acc[i]);
+  }
+  if (db && blockIdx.x == 0 && threadIdx.x < 32 && nb + threadIdx.x < nout) atomicAdd(db + nb + threadIdx.x, bacc);
+}
+
+// ------------------------------------------------------------------ elementwise
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+
+// mode 0: swish (x * sigmoid(x)); mode 1: shifted softplus (softplus(x) - ln 2)
+__global__ void act_fwd_kernel(const float* __restrict__ x, int64_t n, int mode, float* __restrict__ y) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = x[i];
+  y[i] = mode == 0 ? __fmul_rn(v, sigmoid_f(v))
+                   : __fsub_rn(v > 20.0f ? v : log1pf(expf(v)), 0.693147182464599609375f);
+}
+// dx = dy * act'(x):  swish' = s (1 + x (1 - s)),  ssp' = sigmoid(x)
+__global__ void act_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, int64_t n, int mode,
+                               float* __restrict__ dx) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = x[i], s = sigmoid_f(v);
+  const float d = mode == 0 ? s * (1.0f + v * (1.0f - s)) : s;
+  dx[i] = dy[i] * d;
+}
+// y = a * b (b broadcast over rows when b_rows == 1 is NOT needed here: same shape), y = a + b, y = alpha * a
+__global__ void mul_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n, float* __restrict__ y) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = __fmul_rn(a[i], b[i]);
+}
+__global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n, float* __restrict__ y) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = __fadd_rn(a[i], b[i]);
+}
+// y[r, c] = a[r, c] * s[r]   (row scale, e.g. the cosine cutoff of SchNet);  ds[r] = sum_c dy*a handled by rowdot
+__global__ void rowscale_kernel(const float* __restrict__ a, const float* __restrict__ s, int64_t rows, int width,
+                                float* __restrict__ y) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows * width) y[i] = __fmul_rn(a[i], s[i / width]);
+}
+
+// ------------------------------------------------------------------ row gather / scatter-add
+template <typename IDX>
+__global__ void gather_rows_kernel(const float* __restrict__ x, const IDX* __restrict__ idx, int64_t rows, int width,
+                                   float* __restrict__ y) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * width) return;
+  const int64_t r = i / width;
+  y[i] = __ldg(x + (size_t)idx[r] * width + (i % width));
+}
+template <typename IDX>
+__global__ void scatter_add_rows_kernel(const float* __restrict__ y, const IDX* __restrict__ idx, int64_t rows,
+                                        int width, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * width) return;
+  const int64_t r = i / width;
+  atomicAdd(out + (size_t)idx[r] * width + (i % width), y[i]);
+}
+
+
+// out[c][r] = in[r][c]  (weights are tiny: <= 256 x 512)
+__global__ void transpose_kernel(const float* __restrict__ in, int rows, int cols, float* __restrict__ out) {
+  __shared__ float t[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    t[i][threadIdx.x] = (r < rows && c < cols) ? in[(size_t)r * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) out[(size_t)c * rows + r] = t[threadIdx.x][i];
+  }
+}
+
+// SchNet edge features for the training path (schnet.py:24-33, 119-127): gaussian smearing [E, G] and the cosine
+// cutoff C[E]; same op order as the fused cfconv kernel (schnet.cu).
+__global__ void schnet_edge_features_kernel(const float* __restrict__ dist, int64_t n_edges,
+                                            const float* __restrict__ offset, int n_gauss, float coeff, float inv_cutoff,
+                                            float* __restrict__ gauss, float* __restrict__ cut) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_edges * (n_gauss + 1)) return;
+  const int64_t e = i / (n_gauss + 1);
+  const int g = (int)(i % (n_gauss + 1));
+  const float d = dist[e];
+  if (g == n_gauss) {
+    cut[e] = __fmul_rn(0.5f, __fadd_rn(cosf(__fmul_rn(__fmul_rn(d, 3.14159274101257324f), inv_cutoff)), 1.0f));
+  } else {
+    const float t = __fsub_rn(d, __ldg(offset + g));
+    gauss[e * n_gauss + g] = expf(__fmul_rn(coeff, __fmul_rn(t, t)));
+  }
+}
+
+template <int NOUT, int K>
+static int launch_linear_tiled(const float* x, int64_t rows, const float* w, const float* b, float* y, cudaStream_t st) {
+  auto kfn = linear_tiled_kernel<NOUT, K>;
+  const size_t sm = sizeof(LinSmem<NOUT, K>);
+  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  if (e != cudaSuccess) { set_error("linear: cudaFuncSetAttribute(%zu): %s", sm, cudaGetErrorString(e)); return DIG3D_ECUDA; }
+  kfn<<<ceil_div(rows, 64), DT, sm, st>>>(x, (int)rows, w, b, y);
+  return DIG3D_OK;
+}
+
+}  // namespace dig3d
+
+using namespace dig3d;
+
+extern "C" {
+
+int dig3d_linear(const float* x, int64_t rows, int32_t k, int32_t nout, const float* w, const float* bias, float* y,
+                 void* stream) {
+  DIG3D_REQUIRE(x && w && y && k > 0 && nout > 0, "linear: bad arguments");
+  if (rows == 0) return DIG3D_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = -100;
+#define DIG3D_LT(NO, KK) if (nout == NO && k == KK) rc = launch_linear_tiled<NO, KK>(x, rows, w, bias, y, st);
+  DIG3D_LT(128, 128) DIG3D_LT(64, 128) DIG3D_LT(128, 64) DIG3D_LT(256, 128) DIG3D_LT(256, 256) DIG3D_LT(128, 256)
+  DIG3D_LT(128, 384) DIG3D_LT(32, 32) DIG3D_LT(64, 64) DIG3D_LT(128, 32) DIG3D_LT(32, 128) DIG3D_LT(256, 64)
+  DIG3D_LT(64, 256) DIG3D_LT(256, 512) DIG3D_LT(384, 128)
+#undef DIG3D_LT
+  if (rc == -100) {
+    const int64_t total = rows * nout;
+    linear_naive_kernel<<<ceil_div(total, 256), 256, 0, st>>>(x, rows, k, nout, w, bias, y);
+    rc = DIG3D_OK;
+  }
+  if (rc) return rc;
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_wgrad(const float* dy, const float* x, int64_t rows, int32_t nout, int32_t k, float* dw, float* db,
+                void* stream) {
+  DIG3D_REQUIRE(dy && x && dw && nout > 0 && k > 0, "wgrad: bad arguments");
+  if (rows == 0) return DIG3D_OK;
+  int splits = (int)((rows + 2047) / 2048);
+  if (splits > 64) splits = 64;
+  dim3 grid(ceil_div(k, 32), ceil_div(nout, 32), splits);
+  wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, x, rows, nout, k, dw, db);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_act(const float* x, int64_t n, int32_t mode, float* y, void* stream) {
+  DIG3D_REQUIRE(x && y && (mode == 0 || mode == 1), "act: bad arguments");
+  if (n == 0) return DIG3D_OK;
+  act_fwd_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, mode, y);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_act_bwd(const float* x, const float* dy, int64_t n, int32_t mode, float* dx, void* stream) {
+  DIG3D_REQUIRE(x && dy && dx && (mode == 0 || mode == 1), "act_bwd: bad arguments");
+  if (n == 0) return DIG3D_OK;
+  act_bwd_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(x, dy, n, mode, dx);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_ewise(const float* a, const float* b, int64_t n, int32_t op, float* y, void* stream) {
+  DIG3D_REQUIRE(a && b && y && (op == 0 || op == 1), "ewise: bad arguments");
+  if (n == 0) return DIG3D_OK;
+  if (op == 0) mul_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, n, y);
+  else add_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, n, y);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_rowscale(const float* a, const float* s, int64_t rows, int32_t width, float* y, void* stream) {
+  DIG3D_REQUIRE(a && s && y && width > 0, "rowscale: bad arguments");
+  if (rows == 0) return DIG3D_OK;
+  rowscale_kernel<<<ceil_div(rows * width, 256), 256, 0, (cudaStream_t)stream>>>(a, s, rows, width, y);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_gather_rows(const float* x, const void* idx, int32_t idx_is_64, int64_t rows, int32_t width, float* y,
+                      void* stream) {
+  DIG3D_REQUIRE(x && idx && y && width > 0, "gather_rows: bad arguments");
+  if (rows == 0) return DIG3D_OK;
+  const int grid = ceil_div(rows * width, 256);
+  if (idx_is_64) gather_rows_kernel<int64_t><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (const int64_t*)idx, rows, width, y);
+  else gather_rows_kernel<int32_t><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (const int32_t*)idx, rows, width, y);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_scatter_add_rows(const float* y, const void* idx, int32_t idx_is_64, int64_t rows, int32_t width, float* out,
+                           void* stream) {
+  DIG3D_REQUIRE(y && idx && out && width > 0, "scatter_add_rows: bad arguments");
+  if (rows == 0) return DIG3D_OK;
+  const int grid = ceil_div(rows * width, 256);
+  if (idx_is_64) scatter_add_rows_kernel<int64_t><<<grid, 256, 0, (cudaStream_t)stream>>>(y, (const int64_t*)idx, rows, width, out);
+  else scatter_add_rows_kernel<int32_t><<<grid, 256, 0, (cudaStream_t)stream>>>(y, (const int32_t*)idx, rows, width, out);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_transpose(const float* in, int32_t rows, int32_t cols, float* out, void* stream) {
+  DIG3D_REQUIRE(in && out && rows > 0 && cols > 0, "transpose: bad arguments");
+  dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32)), block(32, 8);
+  transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(in, rows, cols, out);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_schnet_edge_features(const float* dist, int64_t n_edges, const float* offset, int32_t n_gauss, double coeff,
+                               double cutoff, float* gauss, float* cut, void* stream) {
+  DIG3D_REQUIRE(dist && offset && gauss && cut && n_gauss > 0, "schnet_edge_features: bad arguments");
+  if (n_edges == 0) return DIG3D_OK;
+  const int64_t total = n_edges * (n_gauss + 1);
+  schnet_edge_features_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      dist, n_edges, offset, n_gauss, (float)coeff, (float)(1.0 / cutoff), gauss, cut);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+}  // extern "C"

@@ -476,3 +476,108 @@ def tc_set_fast_swish(on):
 
 def tc_timeouts():
     return _lib.load().dig3d_tc_timeouts()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Training primitives (csrc/train_ops.cu); dig_b200/autograd.py wraps them in autograd Functions.
+F32 = torch.float32
+
+
+def _idx(t, name="index"):
+    if t.dtype not in (torch.int32, torch.int64):
+        raise TypeError(f"{name}: expected an int32 or int64 index tensor, got {t.dtype}")
+    return _p(t, None, name), int(t.dtype == torch.int64)
+
+
+def linear(x, weight, bias=None):
+    """y = x weight^T + bias for x [..., K] (nn.Linear)."""
+    k = x.size(-1)
+    nout = weight.size(0)
+    if weight.dim() != 2 or weight.size(1) != k:
+        raise ValueError(f"linear: weight {tuple(weight.shape)} does not match input width {k}")
+    rows = x.numel() // k if k else 0
+    y = torch.empty(x.shape[:-1] + (nout,), device=x.device, dtype=F32)
+    call("dig3d_linear", _p(x, F32, "x"), rows, k, nout, _p(weight, F32, "weight"), _p(bias, F32, "bias"),
+         _p(y), _stream())
+    return y
+
+
+def wgrad(dy, x, weight_shape, want_bias):
+    """(dW, db) of y = x W^T + b given dy."""
+    nout, k = weight_shape
+    rows = x.numel() // k
+    dw = torch.zeros(nout, k, device=x.device, dtype=F32)
+    db = torch.zeros(nout, device=x.device, dtype=F32) if want_bias else None
+    call("dig3d_wgrad", _p(dy, F32, "dy"), _p(x, F32, "x"), rows, nout, k, _p(dw), _p(db), _stream())
+    return dw, db
+
+
+def act(x, mode):
+    y = torch.empty_like(x)
+    call("dig3d_act", _p(x, F32, "x"), x.numel(), mode, _p(y), _stream())
+    return y
+
+
+def act_bwd(x, dy, mode):
+    dx = torch.empty_like(x)
+    call("dig3d_act_bwd", _p(x, F32, "x"), _p(dy, F32, "dy"), x.numel(), mode, _p(dx), _stream())
+    return dx
+
+
+def ewise(a, b, op):
+    if a.shape != b.shape:
+        raise ValueError(f"ewise: shapes differ {tuple(a.shape)} vs {tuple(b.shape)}")
+    y = torch.empty_like(a)
+    call("dig3d_ewise", _p(a, F32, "a"), _p(b, F32, "b"), a.numel(), op, _p(y), _stream())
+    return y
+
+
+def rowscale(a, s):
+    rows, width = a.size(0), a.numel() // max(a.size(0), 1)
+    if s.numel() != rows:
+        raise ValueError("rowscale: one scale per row expected")
+    y = torch.empty_like(a)
+    call("dig3d_rowscale", _p(a, F32, "a"), _p(s, F32, "s"), rows, width, _p(y), _stream())
+    return y
+
+
+def gather_rows(x, idx):
+    width = x.numel() // max(x.size(0), 1) if x.dim() > 1 else 1
+    rows = idx.numel()
+    y = torch.empty((rows,) + tuple(x.shape[1:]), device=x.device, dtype=F32)
+    ip, i64 = _idx(idx)
+    call("dig3d_gather_rows", _p(x, F32, "x"), ip, i64, rows, width, _p(y), _stream())
+    return y
+
+
+def scatter_add_rows(y, idx, n_rows):
+    width = y.numel() // max(y.size(0), 1) if y.dim() > 1 else 1
+    out = torch.zeros((n_rows,) + tuple(y.shape[1:]), device=y.device, dtype=F32)
+    ip, i64 = _idx(idx)
+    call("dig3d_scatter_add_rows", _p(y, F32, "y"), ip, i64, idx.numel(), width, _p(out), _stream())
+    return out
+
+
+def transpose(w):
+    rows, cols = w.shape
+    out = torch.empty(cols, rows, device=w.device, dtype=F32)
+    call("dig3d_transpose", _p(w, F32, "w"), rows, cols, _p(out), _stream())
+    return out
+
+
+def schnet_edge_features(dist, offset, coeff, cutoff):
+    """(gaussian smearing [E, G], cosine cutoff [E]) of schnet.py:92-94 / :31, materialised for the training path."""
+    e, ng = dist.numel(), offset.numel()
+    gauss = torch.empty(e, ng, device=dist.device, dtype=F32)
+    cut = torch.empty(e, device=dist.device, dtype=F32)
+    call("dig3d_schnet_edge_features", _p(dist, F32, "dist"), e, _p(offset, F32, "offset"), ng, float(coeff),
+         float(cutoff), _p(gauss), _p(cut), _stream())
+    return gauss, cut
+
+
+def rbf_freq_grad(dist, cutoff, envelope_exponent, freq, drbf0):
+    """d(loss)/d(dist_emb.freq) from d(loss)/d(rbf0)."""
+    dfreq = torch.zeros_like(freq, dtype=F32)
+    call("dig3d_rbf_freq_grad", _p(dist, F32, "dist"), dist.numel(), float(cutoff), int(envelope_exponent),
+         _p(freq.detach(), F32, "freq"), freq.numel(), _p(drbf0, F32, "drbf0"), _p(dfreq), _stream())
+    return dfreq

@@ -34,6 +34,12 @@ def require_cuda(t, what):
             "There is no CPU fallback; move the model and the batch to a B200 device.")
 
 
+def wants_grad(module):
+    """True when autograd is recording and the module has trainable parameters: forward() then takes the
+    differentiable training path (dig_b200/autograd.py) instead of the fused inference kernels."""
+    return torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters())
+
+
 class ResidualLayer(nn.Module):
     """Parameter holder for reference ResidualLayer (spherenet.py:34-50); evaluated inside the
     fused update_e kernel."""

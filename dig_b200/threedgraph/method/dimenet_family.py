@@ -18,9 +18,10 @@ from math import sqrt
 import torch
 from torch import nn
 
+from ... import autograd as ag
 from ... import ops
 from ...basis import envelope_coefficients  # noqa: F401  (documented dependency)
-from ._common import ResidualLayer, glorot_orthogonal, require_cuda, swish
+from ._common import ResidualLayer, glorot_orthogonal, require_cuda, swish, wants_grad
 
 _SUPPORTED = dict(hidden_channels=128, int_emb_size=64, out_emb_channels=256, num_radial=6,
                   num_before_skip=1, num_after_skip=2)
@@ -220,6 +221,8 @@ class _DimeNetFamily(nn.Module):
                 "round (forward inference only)")
         ns, nr = self.num_spherical, self.num_radial
         g = ops.build_graph(pos, batch, self.cutoff, num_graphs=getattr(batch_data, "num_graphs", None))
+        if wants_grad(self):
+            return self._forward_train(z, pos, g)
         ops.triplet_geometry(g, pos, use_torsion=self._torsion, want_idx=False)
         rbf0, bess = ops.edge_basis(g.dist, self.cutoff, self.envelope_exponent, self.emb.dist_emb.freq,
                                     self._basis_id, envelope_on_bessel=not self._torsion, num_radial=nr,
@@ -257,6 +260,64 @@ class _DimeNetFamily(nn.Module):
                                             self.hidden_channels, self.int_emb_size, v_in=v_in_all[l + 1])
         ops.sphere_update_v_batched(v_in_all, [self.init_v] + list(self.update_vs), self.out_channels, v_all)
         return ops.graph_readout(v_all, g.graph_ptr, g.n_graphs, g.n_nodes)
+
+
+    # ------------------------------------------------------------------ training path
+    def _update_v_train(self, m, e2, g):
+        """update_v.forward, reference spherenet.py:209-216."""
+        v = ag.segment_sum(e2, g.row_ptr, g.dst)
+        v = ag.lin(m.lin_up, v)
+        for lin in m.lins:
+            v = ag.swish(ag.lin(lin, v))
+        return ag.lin(m.lin, v)
+
+    def _forward_train(self, z, pos, g):
+        """Differentiable forward (reference spherenet.py:296-320 / dimenetpp.py:273-293, op for op) over the
+        primitives of dig_b200.autograd; taken whenever autograd is recording (run.train).  Geometry and the
+        spherical basis carry no parameters except dist_emb.freq, so they run on the same kernels as inference."""
+        ns, nr = self.num_spherical, self.num_radial
+        ops.triplet_geometry(g, pos, use_torsion=self._torsion, want_idx=True)
+        rbf0, bess = ag.edge_basis(self.emb.dist_emb.freq, g.dist, self.cutoff, self.envelope_exponent,
+                                   self._basis_id, not self._torsion, nr, ns * nr)
+        L = self.num_layers
+        sbf_ps, t_ps = [], []
+        for first in range(0, L, 4):
+            es = self.update_es[first:first + 4]
+            s_l, t_l = ag.basis_project(g, bess, self._basis_id, ns, nr, [m.lin_sbf1.weight for m in es],
+                                        [m.lin_t1.weight for m in es] if self._torsion else None)
+            sbf_ps += s_l
+            t_ps += t_l if t_l is not None else [None] * len(s_l)
+        swish_, lin = ag.swish, ag.lin
+        # init_e (spherenet.py:79-91)
+        ie = self.init_e
+        x = ag.gather_rows(ie.emb.weight, z)
+        r0 = swish_(lin(ie.lin_rbf_0, rbf0))
+        cat = torch.cat([ag.gather_rows(x, g.dst, g.row_ptr), ag.gather_rows(x, g.src), r0], dim=-1)   # copy only
+        e1 = swish_(lin(ie.lin, cat))
+        e2 = ag.mul(lin(ie.lin_rbf_1, rbf0), e1)
+        v = self._update_v_train(self.init_v, e2, g)
+        u = ag.segment_sum(v, g.graph_ptr, g.batch)
+        for l, (ue, uv) in enumerate(zip(self.update_es, self.update_vs)):      # spherenet.py:150-182
+            x_ji = swish_(lin(ue.lin_ji, e1))
+            x_kj = swish_(lin(ue.lin_kj, e1))
+            x_kj = ag.mul(x_kj, lin(ue.lin_rbf2, lin(ue.lin_rbf1, rbf0)))
+            x_kj = swish_(lin(ue.lin_down, x_kj))
+            t = ag.mul(ag.gather_rows(x_kj, g.idx_kj), lin(ue.lin_sbf2, sbf_ps[l]))
+            if self._torsion:
+                t = ag.mul(t, lin(ue.lin_t2, t_ps[l]))
+            x_kj = ag.segment_sum(t, g.trip_ptr, g.idx_ji)
+            x_kj = swish_(lin(ue.lin_up, x_kj))
+            h = ag.add(x_ji, x_kj)
+            for layer in ue.layers_before_skip:
+                h = ag.add(h, swish_(lin(layer.lin2, swish_(lin(layer.lin1, h)))))
+            h = ag.add(swish_(lin(ue.lin, h)), e1)
+            for layer in ue.layers_after_skip:
+                h = ag.add(h, swish_(lin(layer.lin2, swish_(lin(layer.lin1, h)))))
+            e1 = h
+            e2 = ag.mul(lin(ue.lin_rbf, rbf0), e1)
+            v = self._update_v_train(uv, e2, g)
+            u = ag.add(u, ag.segment_sum(v, g.graph_ptr, g.batch))
+        return u
 
 
 class SphereNet(_DimeNetFamily):

@@ -4,9 +4,10 @@ Same `run().run(...)`, `train(...)`, `val(...)` signatures, printed dictionaries
 contents and return values.  torch_geometric's DataLoader (reference run.py:6,53-55) is replaced by
 dig_b200.data.DataLoader (same constructor use, concatenating collate).
 
-Round-1 status: the sm_100a kernels are forward-only, so `val` (inference, the reference's eval
-loop) runs on the fused path, while `train` raises for the dig_b200 models until the backward
-kernels exist (any differentiable torch model still trains through this driver unchanged).
+`val` (inference, the reference's eval loop) runs the fused forward kernels; `train` runs the differentiable
+training path (dig_b200/autograd.py: hand-written forward + backward kernels, torch.autograd keeps the tape)
+for the models that have one, and raises for a model whose forward returns a non-differentiable output.
+Force training (energy_and_force=True) needs a double backward and raises in the models.
 """
 import os
 
@@ -95,8 +96,8 @@ class run():
             out = model(batch_data)
             if not out.requires_grad:
                 raise NotImplementedError(
-                    "run.train: this model's forward is not differentiable -- the dig_b200 sm_100a kernels are "
-                    "forward-only in this round (backward kernels: DESIGN.md 'next'); use run.val for inference")
+                    "run.train: this model's forward returned a non-differentiable output -- no training path "
+                    "(backward kernels) exists for it yet (DESIGN.md); use run.val for inference")
             if energy_and_force:
                 force = -grad(outputs=out, inputs=batch_data.pos, grad_outputs=torch.ones_like(out),
                               create_graph=True, retain_graph=True)[0]

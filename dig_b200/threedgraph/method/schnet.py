@@ -7,8 +7,9 @@ Appendix A), including its quirks: `mlp[0].bias` is zeroed twice and `mlp[2].bia
 import torch
 from torch import nn
 
+from ... import autograd as ag
 from ... import ops
-from ._common import require_cuda
+from ._common import require_cuda, wants_grad
 
 
 class ShiftedSoftplus(nn.Module):
@@ -118,6 +119,8 @@ class SchNet(nn.Module):
             raise NotImplementedError("energy_and_force=True needs the backward kernels (not in this round)")
         g = ops.build_graph(pos, batch, self.cutoff, num_graphs=getattr(batch_data, "num_graphs", None),
                             want_edge_index=False)
+        if wants_grad(self):
+            return self._forward_train(z, g)
         # v = init_v(z): an embedding row gather (torch indexing = plumbing, no arithmetic)
         v = self.init_v.weight.detach()[z].contiguous()
         keep = []
@@ -128,3 +131,22 @@ class SchNet(nn.Module):
                                  self.hidden_channels, self.num_filters, w)
         node_out = ops.schnet_readout(v, self.update_u.lin1, self.update_u.lin2, self.out_channels)
         return ops.segment_sum(node_out, g.graph_ptr)
+
+
+    def _forward_train(self, z, g):
+        """Differentiable forward (reference schnet.py:149-168 op for op) over dig_b200.autograd's primitives;
+        used whenever autograd is recording, i.e. by run.train."""
+        gauss, cut = ops.schnet_edge_features(g.dist, self.dist_emb.offset, self.dist_emb.coeff, self.cutoff)
+        v = ag.gather_rows(self.init_v.weight, z)
+        for ue, uv in zip(self.update_es, self.update_vs):
+            # update_e (schnet.py:29-35): W = mlp(dist_emb) * C ; e = lin(v)[j] * W
+            w = ag.lin(ue.mlp[2], ag.ssp(ag.lin(ue.mlp[0], gauss)))
+            w = ag.rowscale(w, cut)
+            e = ag.mul(ag.gather_rows(ag.lin(ue.lin, v), g.src), w)
+            # update_v (schnet.py:54-60): scatter over the target node, lin1, ssp, lin2, residual
+            out = ag.segment_sum(e, g.row_ptr, g.dst)
+            out = ag.lin(uv.lin2, ag.ssp(ag.lin(uv.lin1, out)))
+            v = ag.add(v, out)
+        # update_u (schnet.py:77-82)
+        node_out = ag.lin(self.update_u.lin2, ag.ssp(ag.lin(self.update_u.lin1, v)))
+        return ag.segment_sum(node_out, g.graph_ptr, g.batch)

@@ -282,6 +282,38 @@ int dig3d_comenet_block(const float* x_in, const float* feature1, const float* f
                         const dig3d_comenet_head_weights* head, int32_t out_channels, float* xs, float* agg1,
                         float* agg2, float* h, float* stats, float* x_out, float* node_out, void* stream);
 
+/* ------------------------------------------------------------------ training primitives (csrc/train_ops.cu)
+ * Forward/backward building blocks of the training path (reference run.py:103-135 = forward + loss.backward();
+ * the reference gets its backward from torch.autograd over ATen ops -- here each primitive has a hand-written
+ * kernel and torch.autograd only records the tape, see dig_b200/autograd.py).  All fp32, row-major.
+ *   linear:  y[rows,nout] = x[rows,k] w[nout,k]^T (+ bias)           nn.Linear (torch F.linear)
+ *   wgrad:   dw[nout,k] += dy^T x ; db[nout] += colsum(dy) (db nullable); dw/db must be initialised by caller
+ *   act:     mode 0 swish (spherenet.py:14), mode 1 shifted softplus (schnet.py:97-103); act_bwd: dx = dy*act'(x)
+ *   ewise:   op 0 y = a*b, op 1 y = a+b ; rowscale: y[r,:] = a[r,:] * s[r]
+ *   gather_rows: y[r,:] = x[idx[r],:] ; scatter_add_rows: out[idx[r],:] += y[r,:] (atomics; out initialised) */
+int dig3d_linear(const float* x, int64_t rows, int32_t k, int32_t nout, const float* w, const float* bias, float* y,
+                 void* stream);
+int dig3d_wgrad(const float* dy, const float* x, int64_t rows, int32_t nout, int32_t k, float* dw, float* db,
+                void* stream);
+int dig3d_act(const float* x, int64_t n, int32_t mode, float* y, void* stream);
+int dig3d_act_bwd(const float* x, const float* dy, int64_t n, int32_t mode, float* dx, void* stream);
+int dig3d_ewise(const float* a, const float* b, int64_t n, int32_t op, float* y, void* stream);
+int dig3d_rowscale(const float* a, const float* s, int64_t rows, int32_t width, float* y, void* stream);
+int dig3d_gather_rows(const float* x, const void* idx, int32_t idx_is_64, int64_t rows, int32_t width, float* y,
+                      void* stream);
+int dig3d_scatter_add_rows(const float* y, const void* idx, int32_t idx_is_64, int64_t rows, int32_t width,
+                           float* out, void* stream);
+/* dfreq[num_radial] += d(loss)/d(dist_emb.freq) given drbf0[E, num_radial] (rbf0 = envelope * sin(freq * d/cutoff),
+ * spherenet/features.py:180-182); dfreq initialised by the caller. */
+int dig3d_rbf_freq_grad(const float* dist, int64_t n_edges, double cutoff, int32_t envelope_exponent,
+                        const float* freq, int32_t num_radial, const float* drbf0, float* dfreq, void* stream);
+/* out[cols, rows] = in[rows, cols]^T (weights for the input-gradient GEMM dx = dy W) */
+int dig3d_transpose(const float* in, int32_t rows, int32_t cols, float* out, void* stream);
+/* SchNet training path: gaussian smearing gauss[E, n_gauss] (schnet.py:92-94) and cosine cutoff cut[E]
+ * (schnet.py:31) materialised (the fused inference kernel keeps them on chip). */
+int dig3d_schnet_edge_features(const float* dist, int64_t n_edges, const float* offset, int32_t n_gauss, double coeff,
+                               double cutoff, float* gauss, float* cut, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
