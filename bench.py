@@ -252,6 +252,37 @@ def main():
     value = total_mols / (ms * 1e-3)
     e2e = total_mols / (wall_e2e * 1e-3)          # wall clock: includes host work and the per-step sync
 
+    # ---- training step (BASELINE configs[4]): forward + backward kernels, NCCL gradient all-reduce, Adam.
+    #      Secondary number (the headline metric above is inference throughput); same batches, weak scaling.
+    from dig_b200 import parallel
+    torch.manual_seed(4321)
+    tmodel = SphereNet().to(dev)
+    topt = torch.optim.Adam(tmodel.parameters(), lr=5e-4)
+    gen = torch.Generator().manual_seed(99 + rank)
+    targets = [torch.randn(MOLS_PER_GPU, 1, generator=gen).to(dev) for _ in range(N_ROTATE)]
+    l1 = torch.nn.L1Loss()
+    train_bytes = [0]
+
+    def step_train(s):
+        topt.zero_grad()
+        out = tmodel(resident[s % N_ROTATE])
+        loss = l1(out, targets[s % N_ROTATE])
+        loss.backward()
+        train_bytes[0] = parallel.allreduce_gradients(tmodel.parameters())
+        topt.step()
+
+    train_steps = max(3, min(args.steps, 30))
+    for s in range(3):
+        step_train(s)
+    lt0 = _lib.launch_count
+    ms_train, _ = timed(step_train, train_steps)
+    train_launches = _lib.launch_count - lt0
+    train = {"value": MOLS_PER_GPU * world * train_steps / (ms_train * 1e-3), "unit": "molecules/s",
+             "ms_per_step": ms_train / train_steps, "steps": train_steps, "gpu_launches": train_launches,
+             "allreduce_bytes_per_step": train_bytes[0],
+             "step": "SphereNet forward + backward (dig_b200/autograd.py kernels) + gradient all-reduce + torch Adam, "
+                     "L1 loss on synthetic targets"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -338,6 +369,27 @@ def main():
                    "what": "reference op sequence (oracle/restated.py) on the same B200 through ATen/cuBLAS fp32, "
                            "torch-native scatter; same batch size and weights"}
 
+        # the same for a training step: torch.autograd over the reference op sequence + Adam
+        sd_t = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in tmodel.state_dict().items()}
+        ropt = torch.optim.Adam([v for v in sd_t.values() if v.requires_grad], lr=5e-4)
+
+        def ref_train(s_):
+            rb_ = resident[s_ % N_ROTATE]
+            ropt.zero_grad()
+            o = restated.spherenet_forward(sd_t, rb_.z, rb_.pos, rb_.batch, num_graphs=MOLS_PER_GPU)
+            l1(o, targets[s_ % N_ROTATE]).backward()
+            ropt.step()
+        ref_train(0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for s_ in range(3):
+            ref_train(s_)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        train["gpu_comparator"] = {"value": 3 * MOLS_PER_GPU / dt, "unit": "molecules/s", "ms_per_step": 1e3 * dt / 3,
+                                   "what": "torch.autograd over the reference op sequence + Adam on the same B200"}
+        del sd_t, ropt
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         rate, dt, iters, threads = cpu_oracle_rate(32)
@@ -352,14 +404,14 @@ def main():
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "molecules_per_gpu": MOLS_PER_GPU, "global_batch": MOLS_PER_GPU * world,
                        "parallelism": f"graph-sharded x{world} (no data-path collective in inference)",
-                       "edges": E, "triplets": T, "nodes": N, "step": "forward (inference); backward not built yet",
+                       "edges": E, "triplets": T, "nodes": N, "step": "forward (inference) = the headline metric; the training step (fwd+bwd+all-reduce+Adam) is under 'train'",
                        "l2": f"{N_ROTATE} distinct batches rotated; per-step intermediates "
                              f"{(2 * T * 32 * 4 + E * (42 + 4 * 128 + 64 + 6) * 4) / 1e6:.0f} MB > 126 MB L2"},
             "e2e": {"value": e2e, "unit": "molecules/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": wall_e2e / args.steps, "timing": "host wall clock incl. per-step stream sync"},
             "gpu_launches": launches, "wall_ms_per_step": wall_ms / args.steps,
             "clocks": sampler.summary(), "roofline": roof, "scatter_roofline": scatter, "cpu_baseline": cpu,
-            "gpu_comparator": gpu_cmp}
+            "gpu_comparator": gpu_cmp, "train": train}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -232,15 +232,39 @@ class _BasisProject(torch.autograd.Function):
         (bess,) = ctx.saved_tensors
         basis_id, ns, nr, n_layers, torsion = ctx.cfg
         g = ctx.g
-        sbf, tbf = ops.triplet_basis(bess, g.angle, g.torsion, g.idx_kj, basis_id, ns, nr, want_tbf=torsion)
-        out = []
-        for l in range(n_layers):
-            out.append(None if grads[l] is None else ops.wgrad(_c(grads[l]), sbf, (8, ns * nr), False)[0])
+        d_s = [None if d is None else _c(d) for d in grads[:n_layers]]
+        d_t = [None if d is None else _c(d) for d in grads[n_layers:]] if torsion else None
+        dws, dwt = ops.triplet_basis_project_bwd(g, bess, basis_id, d_s, d_t, ns * nr, ns * ns * nr)
+        out = [None if grads[l] is None else dws[8 * l:8 * l + 8] for l in range(n_layers)]
         if torsion:
-            for l in range(n_layers):
-                d = grads[n_layers + l]
-                out.append(None if d is None else ops.wgrad(_c(d), tbf, (8, ns * ns * nr), False)[0])
+            out += [None if grads[n_layers + l] is None else dwt[8 * l:8 * l + 8] for l in range(n_layers)]
         return (None,) * 7 + tuple(out)
+
+
+class _TripletGather(torch.autograd.Function):
+    """m[e] = sum_{t in trip(e)} x_down[kj(t)] * lin_sbf2(sbf_p[t]) * lin_t2(t_p[t])   (spherenet.py:163-171), one fused
+    kernel forward and one backward (csrc/train_sphere.cu)."""
+
+    @staticmethod
+    def forward(ctx, x_down, sbf_p, t_p, w_sbf2, w_t2, g):
+        x_down, sbf_p = _c(x_down), _c(sbf_p)
+        t_p = None if t_p is None else _c(t_p)
+        ws = _c(w_sbf2.detach())
+        wt = None if w_t2 is None else _c(w_t2.detach())
+        ctx.g = g
+        ctx.save_for_backward(x_down, sbf_p, t_p, ws, wt)
+        return ops.sphere_triplet_gather(x_down, sbf_p, t_p, g, ws, wt)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dm):
+        x_down, sbf_p, t_p, ws, wt = ctx.saved_tensors
+        dx, d_s, d_t, dws, dwt = ops.sphere_triplet_gather_bwd(_c(dm), x_down, sbf_p, t_p, ctx.g, ws, wt)
+        return dx, d_s, d_t, dws, dwt, None
+
+
+def triplet_gather(x_down, sbf_p, t_p, w_sbf2, w_t2, g):
+    return _TripletGather.apply(x_down, sbf_p, t_p, w_sbf2, w_t2, g)
 
 
 def edge_basis(freq, dist, cutoff, exponent, basis_id, env_on_bessel, nr, n_bessel):

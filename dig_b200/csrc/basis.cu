@@ -266,6 +266,139 @@ triplet_basis_project_kernel(const float* __restrict__ bess, const float* __rest
   }
 }
 
+// ------------------------------------------------------------------ backward of the fused projection (training path)
+// d(loss)/d(lin_sbf1.weight), d(loss)/d(lin_t1.weight) of up to four layers from d sbf_p[l][T, 8] / d t_p[l][T, 8]:
+//   dW_t1[q][(a*ns+b)*nr + r] = sum_kj ( sum_{t uses kj} d t_p[q][t] * Y_ab(t) ) * bess[kj][b*nr + r]      (q = layer*8 + row)
+// Same traversal as the forward kernel (one warp per (k->j) edge, lane = q, the harmonics of its triplets parked in
+// shared memory); the inner sum G[ab] stays in registers, the outer product with the edge's Bessel values goes into a
+// per-CTA shared-memory accumulator (shared atomics, lane-distinct banks) that is flushed once per CTA.  The [T, 294]
+// basis is never materialised.
+struct PrjGradPtrs { const float* ds[4]; const float* dt[4]; };
+
+template <class BS, bool TORSION>
+struct PrjBwdSmem {
+  static constexpr int NYT = TORSION ? BS::NY : 1;
+  float dwt[TORSION ? BS::NY * BS::NR * PRJ_LD : 1];
+  float dws[BS::NB * PRJ_LD];
+  float bess[PRJ_WARPS][BS::NB];
+  static constexpr int YLD = ((NYT + BS::NS + 3) / 4) * 4;
+  alignas(16) float y[PRJ_WARPS][32][YLD];
+  int32_t trip[PRJ_WARPS][32];
+};
+
+template <class BS, bool TORSION>
+__global__ void __launch_bounds__(PRJ_WARPS * 32)
+triplet_basis_project_bwd_kernel(const float* __restrict__ bess, const float* __restrict__ angle,
+                                 const float* __restrict__ torsion, const int32_t* __restrict__ src,
+                                 const int32_t* __restrict__ dst, const int32_t* __restrict__ row_ptr,
+                                 const int32_t* __restrict__ trip_ptr, const int32_t* __restrict__ graph_ptr,
+                                 const int64_t* __restrict__ batch, int n_edges, PrjGradPtrs gp,
+                                 float* __restrict__ dw_sbf1 /*[32, NB]*/, float* __restrict__ dw_t1 /*[32, NY*NR]*/) {
+  constexpr int NS = BS::NS, NR = BS::NR, NB = BS::NB, NY = BS::NY;
+  constexpr int NYT = TORSION ? NY : 1;
+  using SM = PrjBwdSmem<BS, TORSION>;
+  extern __shared__ __align__(16) unsigned char prj_smem_raw[];
+  SM& sm = *reinterpret_cast<SM*>(prj_smem_raw);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (TORSION)
+    for (int id = threadIdx.x; id < NY * NR * PRJ_LD; id += PRJ_WARPS * 32) sm.dwt[id] = 0.f;
+  for (int id = threadIdx.x; id < NB * PRJ_LD; id += PRJ_WARPS * 32) sm.dws[id] = 0.f;
+  __syncthreads();
+  const float* my_ds = gp.ds[lane >> 3];
+  const float* my_dt = TORSION ? gp.dt[lane >> 3] : nullptr;
+  const int mrow = lane & 7;
+  for (int kj = blockIdx.x * PRJ_WARPS + w; kj < n_edges; kj += gridDim.x * PRJ_WARPS) {
+    const int k = src[kj], j = dst[kj];
+    __syncwarp();
+    for (int c = lane; c < NB; c += 32) sm.bess[w][c] = __ldg(bess + (size_t)kj * NB + c);
+    float G[NYT], Gs[NS];
+#pragma unroll
+    for (int i = 0; i < NYT; ++i) G[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) Gs[i] = 0.f;
+    const int jbase = row_ptr[j], dj = row_ptr[j + 1] - jbase;
+    const int rank_k = kj - jbase;
+    const int g = (int)batch[j];
+    const int lo = graph_ptr[g], hi = graph_ptr[g + 1];
+    for (int c0 = lo; c0 < hi; c0 += 32) {
+      const int i = c0 + lane;
+      int t = -1;
+      if (i < hi && i != k && i != j) {
+        const int ib = row_ptr[i], di = row_ptr[i + 1] - ib;
+        int a = 0, b = di;
+        while (a < b) { int mid = (a + b) >> 1; if (src[ib + mid] < j) a = mid + 1; else b = mid; }
+        if (a < di && src[ib + a] == j) {
+          const int e = ib + a;
+          int a2 = 0, b2 = dj;
+          while (a2 < b2) { int mid = (a2 + b2) >> 1; if (src[jbase + mid] < i) a2 = mid + 1; else b2 = mid; }
+          const bool i_in = (a2 < dj && src[jbase + a2] == i);
+          t = trip_ptr[e] + rank_k - ((i_in && a2 < rank_k) ? 1 : 0);
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, t >= 0);
+      if (t >= 0) {
+        const int slot = __popc(m & ((1u << lane) - 1));
+        sm.trip[w][slot] = t;
+        const float th = angle[t];
+        float y0[NS];
+        BS::yl0(th, y0);
+#pragma unroll
+        for (int l = 0; l < NS; ++l) sm.y[w][slot][NYT + l] = y0[l];
+        if (TORSION) {
+          float y[NY];
+          BS::ylm(th, torsion[t], y);
+#pragma unroll
+          for (int ab = 0; ab < NY; ++ab) sm.y[w][slot][ab] = y[ab];
+        }
+      }
+      __syncwarp();
+      const int cnt = __popc(m);
+      for (int s = 0; s < cnt; ++s) {
+        const int tt = sm.trip[w][s];
+        float yv[SM::YLD];
+#pragma unroll
+        for (int i = 0; i < SM::YLD; i += 4) {
+          const float4 q = *reinterpret_cast<const float4*>(&sm.y[w][s][i]);
+          yv[i] = q.x; yv[i + 1] = q.y; yv[i + 2] = q.z; yv[i + 3] = q.w;
+        }
+        const float d_s = my_ds ? __ldg(my_ds + (size_t)tt * 8 + mrow) : 0.f;
+#pragma unroll
+        for (int l = 0; l < NS; ++l) Gs[l] = fmaf(d_s, yv[NYT + l], Gs[l]);
+        if (TORSION) {
+          const float d_t = my_dt ? __ldg(my_dt + (size_t)tt * 8 + mrow) : 0.f;
+#pragma unroll
+          for (int ab = 0; ab < NY; ++ab) G[ab] = fmaf(d_t, yv[ab], G[ab]);
+        }
+      }
+      __syncwarp();
+    }
+    // outer product with the edge's Bessel values into the CTA accumulators
+#pragma unroll
+    for (int b = 0; b < NS; ++b) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const float rb = sm.bess[w][b * NR + r];
+        atomicAdd(&sm.dws[(b * NR + r) * PRJ_LD + lane], Gs[b] * rb);
+        if (TORSION) {
+#pragma unroll
+          for (int a = 0; a < NS; ++a)
+            atomicAdd(&sm.dwt[((a * NS + b) * NR + r) * PRJ_LD + lane], G[a * NS + b] * rb);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int id = threadIdx.x; id < 32 * NB; id += PRJ_WARPS * 32) {
+    const int q = id / NB, c = id % NB;
+    atomicAdd(dw_sbf1 + id, sm.dws[c * PRJ_LD + q]);
+  }
+  if (TORSION)
+    for (int id = threadIdx.x; id < 32 * NY * NR; id += PRJ_WARPS * 32) {
+      const int q = id / (NY * NR), c = id % (NY * NR);
+      atomicAdd(dw_t1 + id, sm.dwt[c * PRJ_LD + q]);
+    }
+}
+
 template <class BS>
 static int launch_edge_basis(const float* dist, int64_t n_edges, double cutoff, int exponent,
                              const float* freq, int env_on_bessel, float* rbf0, float* bess,
@@ -370,6 +503,48 @@ int dig3d_triplet_basis_project(const float* bess, const float* angle, const flo
   }
 #undef DIG3D_PRJ_ONE
 #undef DIG3D_PRJ
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_triplet_basis_project_bwd(const float* bess, const float* angle, const float* torsion, const int32_t* src,
+                                    const int32_t* dst, const int32_t* row_ptr, const int32_t* trip_ptr,
+                                    const int32_t* graph_ptr, const int64_t* batch, int64_t n_edges, int64_t n_triplets,
+                                    int32_t basis_id, const float* const* d_sbf_p, const float* const* d_t_p,
+                                    float* dw_sbf1, float* dw_t1, void* stream) {
+  DIG3D_REQUIRE(bess && angle && src && dst && row_ptr && trip_ptr && graph_ptr && batch && d_sbf_p && dw_sbf1,
+                "triplet_basis_project_bwd: null pointer");
+  const bool tors = (dw_t1 != nullptr);
+  DIG3D_REQUIRE(!tors || (torsion && d_t_p), "triplet_basis_project_bwd: torsion path needs torsion and d_t_p");
+  if (n_edges == 0 || n_triplets == 0) return DIG3D_OK;
+  PrjGradPtrs gp;
+  for (int l = 0; l < 4; ++l) { gp.ds[l] = d_sbf_p[l]; gp.dt[l] = tors ? d_t_p[l] : nullptr; }
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t want = (n_edges + PRJ_WARPS - 1) / PRJ_WARPS;
+  const int grid = (int)(want < 2 * n_sm ? want : 2 * n_sm);
+#define DIG3D_PRJB_ONE(BS, TORS)                                                                            \
+  {                                                                                                         \
+    auto kfn = triplet_basis_project_bwd_kernel<BS, TORS>;                                                  \
+    const size_t smem = sizeof(PrjBwdSmem<BS, TORS>);                                                       \
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { \
+      set_error("triplet_basis_project_bwd: cannot reserve %zu bytes of shared memory", smem);              \
+      return DIG3D_ECUDA;                                                                                   \
+    }                                                                                                       \
+    kfn<<<grid, PRJ_WARPS * 32, smem, st>>>(bess, angle, torsion, src, dst, row_ptr, trip_ptr, graph_ptr,   \
+                                            batch, (int)n_edges, gp, dw_sbf1, dw_t1);                       \
+  }
+#define DIG3D_PRJB(BS) \
+  if (tors) DIG3D_PRJB_ONE(BS, true) else DIG3D_PRJB_ONE(BS, false)
+  switch (basis_id) {
+    case 0: DIG3D_PRJB(B76); break;
+    case 1: DIG3D_PRJB(B36); break;
+    default: set_error("triplet_basis_project_bwd: unsupported basis_id %d", basis_id); return DIG3D_EUNSUPPORTED;
+  }
+#undef DIG3D_PRJB_ONE
+#undef DIG3D_PRJB
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
 }

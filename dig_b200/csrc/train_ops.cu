@@ -68,47 +68,94 @@ __global__ void linear_naive_kernel(const float* __restrict__ x, int64_t rows, i
 }
 
 // ------------------------------------------------------------------ weight gradient: dW[n][k] += sum_r dY[r][n] X[r][k]
-// grid = (ceil(K/32), ceil(NOUT/32), row splits); each CTA owns a 32 x 32 block of dW and a slice of the rows.
+// grid = (ceil(K/BK), ceil(NOUT/BN), row splits).  A CTA owns a BN x BK block of dW and a slice of the rows; the 256
+// threads form a 16 (n) x 16 (k) grid of (BN/16) x (BK/16) register micro-tiles.  Rows are staged 32 at a time through
+// shared memory with the next chunk prefetched into registers while the current one is consumed; partial blocks of the
+// row splits are combined with atomicAdd (dW / db zero-initialised by the caller).
+template <int BN, int BK>
 __global__ void __launch_bounds__(256)
 wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x, int64_t rows, int nout, int k,
              float* __restrict__ dw, float* __restrict__ db) {
-  __shared__ float sdy[32][33];
-  __shared__ float sx[32][33];
-  const int kb = blockIdx.x * 32, nb = blockIdx.y * 32;
-  const int tn = threadIdx.x >> 5, tk = threadIdx.x & 31;   // thread owns dW[nb + tn + 8*i][kb + tk], i < 4
-  const int64_t per = (rows + gridDim.z - 1) / gridDim.z;
+  constexpr int RC = 32, MN = BN / 16, MK = BK / 16, LDN = BN + 4, LDK = BK + 4;
+  constexpr int EN = RC * BN / 256, EK = RC * BK / 256;
+  __shared__ __align__(16) float sdy[RC * LDN];
+  __shared__ __align__(16) float sx[RC * LDK];
+  const int kb = blockIdx.x * BK, nb = blockIdx.y * BN;
+  const int tk = threadIdx.x & 15, tn = threadIdx.x >> 4;
+  int64_t per = (rows + gridDim.z - 1) / gridDim.z;
+  per = (per + RC - 1) / RC * RC;
   const int64_t r_lo = (int64_t)blockIdx.z * per, r_hi = min(rows, r_lo + per);
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  float bacc = 0.f;   // column sums of dY for db (threads with tk == 0... computed by lanes below)
-  for (int64_t r0 = r_lo; r0 < r_hi; r0 += 32) {
-    // stage 32 rows of dY[:, nb:nb+32] and X[:, kb:kb+32]
-    for (int id = threadIdx.x; id < 32 * 32; id += 256) {
-      const int rr = id >> 5, cc = id & 31;
+  if (r_lo >= r_hi) return;
+  float pn[EN], pk[EK];
+  auto fetch = [&](int64_t r0) {
+#pragma unroll
+    for (int i = 0; i < EN; ++i) {
+      const int id = threadIdx.x + i * 256, rr = id / BN, cc = id % BN;
       const int64_t r = r0 + rr;
-      sdy[rr][cc] = (r < r_hi && nb + cc < nout) ? __ldg(dy + r * nout + nb + cc) : 0.f;
-      sx[rr][cc] = (r < r_hi && kb + cc < k) ? __ldg(x + r * k + kb + cc) : 0.f;
+      pn[i] = (r < r_hi && nb + cc < nout) ? __ldg(dy + r * nout + nb + cc) : 0.f;
     }
-    __syncthreads();
-#pragma unroll 8
-    for (int rr = 0; rr < 32; ++rr) {
-      const float xv = sx[rr][tk];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc[i] = fmaf(sdy[rr][tn + 8 * i], xv, acc[i]);
+    for (int i = 0; i < EK; ++i) {
+      const int id = threadIdx.x + i * 256, rr = id / BK, cc = id % BK;
+      const int64_t r = r0 + rr;
+      pk[i] = (r < r_hi && kb + cc < k) ? __ldg(x + r * k + kb + cc) : 0.f;
     }
-    if (db && blockIdx.x == 0 && threadIdx.x < 32) {
-      float sum = 0.f;
+  };
+  float acc[MN][MK], bacc[MN];
+#pragma unroll
+  for (int i = 0; i < MN; ++i) {
+    bacc[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < MK; ++j) acc[i][j] = 0.f;
+  }
+  const bool do_bias = db != nullptr && blockIdx.x == 0 && tk == 0;
+  fetch(r_lo);
+  for (int64_t r0 = r_lo; r0 < r_hi; r0 += RC) {
+#pragma unroll
+    for (int i = 0; i < EN; ++i) { const int id = threadIdx.x + i * 256; sdy[(id / BN) * LDN + id % BN] = pn[i]; }
+#pragma unroll
+    for (int i = 0; i < EK; ++i) { const int id = threadIdx.x + i * 256; sx[(id / BK) * LDK + id % BK] = pk[i]; }
+    __syncthreads();
+    if (r0 + RC < r_hi) fetch(r0 + RC);
 #pragma unroll 8
-      for (int rr = 0; rr < 32; ++rr) sum += sdy[rr][threadIdx.x];
-      bacc += sum;
+    for (int rr = 0; rr < RC; ++rr) {
+      float dv[MN], xv[MK];
+#pragma unroll
+      for (int i = 0; i < MN; ++i) dv[i] = sdy[rr * LDN + tn * MN + i];
+#pragma unroll
+      for (int j = 0; j < MK; ++j) xv[j] = sx[rr * LDK + tk * MK + j];
+#pragma unroll
+      for (int i = 0; i < MN; ++i) {
+#pragma unroll
+        for (int j = 0; j < MK; ++j) acc[i][j] = fmaf(dv[i], xv[j], acc[i][j]);
+        if (do_bias) bacc[i] += dv[i];
+      }
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int n = nb + tn + 8 * i, kk = kb + tk;
-    if (n < nout && kk < k) atomicAdd(dw + (size_t)n * k + kk, acc[i]);
+  for (int i = 0; i < MN; ++i) {
+    const int n = nb + tn * MN + i;
+    if (n >= nout) continue;
+#pragma unroll
+    for (int j = 0; j < MK; ++j) {
+      const int kk = kb + tk * MK + j;
+      if (kk < k) atomicAdd(dw + (size_t)n * k + kk, acc[i][j]);
+    }
+    if (do_bias) atomicAdd(db + n, bacc[i]);
   }
-  if (db && blockIdx.x == 0 && threadIdx.x < 32 && nb + threadIdx.x < nout) atomicAdd(db + nb + threadIdx.x, bacc);
+}
+
+template <int BN, int BK>
+static void launch_wgrad(const float* dy, const float* x, int64_t rows, int nout, int k, float* dw, float* db,
+                         cudaStream_t st) {
+  const int blocks = ceil_div(k, BK) * ceil_div(nout, BN);
+  int64_t splits = 592 / blocks;                       // ~4 CTAs per SM in total
+  const int64_t max_splits = (rows + 63) / 64;         // at least two 32-row chunks per CTA
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  dim3 grid(ceil_div(k, BK), ceil_div(nout, BN), (unsigned)splits);
+  wgrad_kernel<BN, BK><<<grid, 256, 0, st>>>(dy, x, rows, nout, k, dw, db);
 }
 
 // ------------------------------------------------------------------ elementwise
@@ -240,10 +287,11 @@ int dig3d_wgrad(const float* dy, const float* x, int64_t rows, int32_t nout, int
                 void* stream) {
   DIG3D_REQUIRE(dy && x && dw && nout > 0 && k > 0, "wgrad: bad arguments");
   if (rows == 0) return DIG3D_OK;
-  int splits = (int)((rows + 2047) / 2048);
-  if (splits > 64) splits = 64;
-  dim3 grid(ceil_div(k, 32), ceil_div(nout, 32), splits);
-  wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, x, rows, nout, k, dw, db);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nout > 16 && k > 16) launch_wgrad<64, 64>(dy, x, rows, nout, k, dw, db, st);
+  else if (nout > 16) launch_wgrad<64, 16>(dy, x, rows, nout, k, dw, db, st);
+  else if (k > 16) launch_wgrad<16, 64>(dy, x, rows, nout, k, dw, db, st);
+  else launch_wgrad<16, 16>(dy, x, rows, nout, k, dw, db, st);
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
 }

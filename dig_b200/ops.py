@@ -581,3 +581,47 @@ def rbf_freq_grad(dist, cutoff, envelope_exponent, freq, drbf0):
     call("dig3d_rbf_freq_grad", _p(dist, F32, "dist"), dist.numel(), float(cutoff), int(envelope_exponent),
          _p(freq.detach(), F32, "freq"), freq.numel(), _p(drbf0, F32, "drbf0"), _p(dfreq), _stream())
     return dfreq
+
+
+def sphere_triplet_gather(x_down, sbf_p, t_p, g, w_sbf2, w_t2):
+    """m[E, 64] = sum over the triplets of each edge of x_down[kj] * lin_sbf2(sbf_p) * lin_t2(t_p)  (spherenet.py:163-171)."""
+    e = g.n_edges
+    m = torch.empty(e, x_down.size(1), device=x_down.device, dtype=F32)
+    call("dig3d_sphere_triplet_gather", _p(x_down, F32, "x_down"), _p(sbf_p, F32, "sbf_p"), _p(t_p, F32, "t_p"), 8,
+         _p(g.src), _p(g.dst), _p(g.row_ptr), _p(g.trip_ptr), e, _p(w_sbf2, F32, "w_sbf2"), _p(w_t2, F32, "w_t2"),
+         _p(m), _stream())
+    return m
+
+
+def sphere_triplet_gather_bwd(dm, x_down, sbf_p, t_p, g, w_sbf2, w_t2):
+    """-> (dx_down, d_sbf_p, d_t_p | None, dw_sbf2, dw_t2 | None)."""
+    dev = dm.device
+    tors = t_p is not None
+    dx = torch.zeros_like(x_down)
+    d_s = torch.empty_like(sbf_p)
+    d_t = torch.empty_like(t_p) if tors else None
+    dws = torch.zeros_like(w_sbf2)
+    dwt = torch.zeros_like(w_t2) if tors else None
+    call("dig3d_sphere_triplet_gather_bwd", _p(dm, F32, "dm"), _p(x_down, F32), _p(sbf_p, F32), _p(t_p, F32),
+         _p(g.src), _p(g.dst), _p(g.row_ptr), _p(g.trip_ptr), g.n_edges, _p(w_sbf2, F32), _p(w_t2, F32), _p(dx),
+         _p(d_s), _p(d_t), _p(dws), _p(dwt), _stream())
+    return dx, d_s, d_t, dws, dwt
+
+
+def triplet_basis_project_bwd(g, bess, basis_id, d_sbf_p, d_t_p, n_sbf, n_tbf):
+    """d_sbf_p / d_t_p: lists (<= 4) of [T, 8] gradients or None -> dw_sbf1 [32, n_sbf], dw_t1 [32, n_tbf] | None."""
+    dev = bess.device
+    tors = d_t_p is not None
+    dws = torch.zeros(32, n_sbf, device=dev, dtype=F32)
+    dwt = torch.zeros(32, n_tbf, device=dev, dtype=F32) if tors else None
+    arr = ctypes.c_void_p * 4
+
+    def ptrs(lst):
+        vals = [(_p(t, F32, "grad").value if t is not None else None) for t in lst] + [None] * (4 - len(lst))
+        return arr(*vals)
+    ps = ptrs(d_sbf_p)
+    pt = ptrs(d_t_p) if tors else None
+    call("dig3d_triplet_basis_project_bwd", _p(bess, F32), _p(g.angle), _p(g.torsion) if tors else None, _p(g.src),
+         _p(g.dst), _p(g.row_ptr), _p(g.trip_ptr), _p(g.graph_ptr), _p(g.batch, torch.int64), g.n_edges, g.n_triplets,
+         int(basis_id), ps, pt, _p(dws), _p(dwt), _stream())
+    return dws, dwt

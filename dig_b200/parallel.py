@@ -58,3 +58,37 @@ def gather_per_molecule(values, device=None):
     out = [torch.zeros_like(pad) for _ in range(world)]
     dist.all_gather(out, pad)
     return torch.cat([o[:int(s)] for o, s in zip(out, sizes)], dim=0)
+
+
+def world_size():
+    return dist.get_world_size() if dist.is_initialized() else 1
+
+
+def allreduce_gradients(parameters):
+    """Data-parallel gradient exchange (BASELINE configs[4]: 'NCCL grad all-reduce'): every rank ran backward on its
+    own molecule shard; the gradients are averaged with ONE all-reduce of a flat fp32 buffer per step (the model has
+    ~1.9 M parameters = 7.6 MB, far below the size where bucketing/overlap would pay on NVLink 5).
+
+    NCCL averages in the collective (ReduceOp.AVG); gloo (CPU tests only) has no AVG, so SUM + scale there.
+    Parameters without a gradient on some rank would desynchronise the flat layout, so they are zero-filled."""
+    params = [p for p in parameters if p.requires_grad]
+    world = world_size()
+    if world == 1 or not params:
+        return 0
+    grads = []
+    for p in params:
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+        grads.append(p.grad)
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    if dist.get_backend() == "nccl":
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+    else:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat /= world
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+    return flat.numel() * flat.element_size()

@@ -276,7 +276,7 @@ class _DimeNetFamily(nn.Module):
         primitives of dig_b200.autograd; taken whenever autograd is recording (run.train).  Geometry and the
         spherical basis carry no parameters except dist_emb.freq, so they run on the same kernels as inference."""
         ns, nr = self.num_spherical, self.num_radial
-        ops.triplet_geometry(g, pos, use_torsion=self._torsion, want_idx=True)
+        ops.triplet_geometry(g, pos, use_torsion=self._torsion, want_idx=False)
         rbf0, bess = ag.edge_basis(self.emb.dist_emb.freq, g.dist, self.cutoff, self.envelope_exponent,
                                    self._basis_id, not self._torsion, nr, ns * nr)
         L = self.num_layers
@@ -302,10 +302,8 @@ class _DimeNetFamily(nn.Module):
             x_kj = swish_(lin(ue.lin_kj, e1))
             x_kj = ag.mul(x_kj, lin(ue.lin_rbf2, lin(ue.lin_rbf1, rbf0)))
             x_kj = swish_(lin(ue.lin_down, x_kj))
-            t = ag.mul(ag.gather_rows(x_kj, g.idx_kj), lin(ue.lin_sbf2, sbf_ps[l]))
-            if self._torsion:
-                t = ag.mul(t, lin(ue.lin_t2, t_ps[l]))
-            x_kj = ag.segment_sum(t, g.trip_ptr, g.idx_ji)
+            x_kj = ag.triplet_gather(x_kj, sbf_ps[l], t_ps[l], ue.lin_sbf2.weight,
+                                     ue.lin_t2.weight if self._torsion else None, g)
             x_kj = swish_(lin(ue.lin_up, x_kj))
             h = ag.add(x_ji, x_kj)
             for layer in ue.layers_before_skip:

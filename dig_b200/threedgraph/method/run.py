@@ -16,6 +16,7 @@ from torch.autograd import grad
 from torch.optim import Adam
 from torch.optim.lr_scheduler import StepLR
 
+from ... import parallel
 from ...data import DataLoader
 
 try:                       # progress bars are optional plumbing (reference run.py:10)
@@ -40,6 +41,8 @@ class run():
         print(f'#Params: {num_params}')
         optimizer = Adam(model.parameters(), lr=lr, weight_decay=weight_decay)
         scheduler = StepLR(optimizer, step_size=lr_decay_step_size, gamma=lr_decay_factor)
+        if parallel.world_size() > 1:       # data parallel: each rank trains on its contiguous shard of the molecules
+            train_dataset = parallel.shard_molecules(train_dataset)
         train_loader = DataLoader(train_dataset, batch_size, shuffle=True)
         valid_loader = DataLoader(valid_dataset, vt_batch_size, shuffle=False)
         test_loader = DataLoader(test_dataset, vt_batch_size, shuffle=False)
@@ -107,6 +110,9 @@ class run():
             else:
                 loss = loss_func(out, batch_data.y.unsqueeze(1))
             loss.backward()
+            # data-parallel launch (one process per GPU, torch.distributed initialised): average the gradients of
+            # the per-rank molecule shards; a no-op in the reference's single-process use
+            parallel.allreduce_gradients(model.parameters())
             optimizer.step()
             loss_accum += loss.detach().cpu().item()
         return loss_accum / (step + 1)

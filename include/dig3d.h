@@ -307,6 +307,22 @@ int dig3d_scatter_add_rows(const float* y, const void* idx, int32_t idx_is_64, i
  * spherenet/features.py:180-182); dfreq initialised by the caller. */
 int dig3d_rbf_freq_grad(const float* dist, int64_t n_edges, double cutoff, int32_t envelope_exponent,
                         const float* freq, int32_t num_radial, const float* drbf0, float* dfreq, void* stream);
+/* Backward of dig3d_triplet_basis_project w.r.t. the projection weights: dw_sbf1[32, ns*nr] / dw_t1[32, ns*ns*nr]
+ * (rows = layer*8 + basis row, same row order as the forward's w_sbf1 / w_t1; zero-initialised by the caller) from
+ * the per-layer gradients d_sbf_p[l] / d_t_p[l] ([T, 8] each, HOST arrays of 4 device pointers, entries may be NULL).
+ * The [T, ns*ns*nr] basis is recomputed on chip, never materialised.  dw_t1 NULL = no torsion (DimeNet++). */
+int dig3d_triplet_basis_project_bwd(const float* bess, const float* angle, const float* torsion, const int32_t* src,
+                                    const int32_t* dst, const int32_t* row_ptr, const int32_t* trip_ptr,
+                                    const int32_t* graph_ptr, const int64_t* batch, int64_t n_edges, int64_t n_triplets,
+                                    int32_t basis_id, const float* const* d_sbf_p, const float* const* d_t_p,
+                                    float* dw_sbf1, float* dw_t1, void* stream);
+/* Backward of dig3d_sphere_triplet_gather (spherenet.py:163-171): from dm[E, 64] computes dx_down[E, 64] (atomics, zeroed
+ * by the caller), d_sbf_p / d_t_p [T, 8] (every row written) and dw_sbf2 / dw_t2 [64, 8] (zeroed by the caller). */
+int dig3d_sphere_triplet_gather_bwd(const float* dm, const float* x_down, const float* sbf_p, const float* t_p,
+                                    const int32_t* src, const int32_t* dst, const int32_t* row_ptr,
+                                    const int32_t* trip_ptr, int64_t n_edges, const float* w_sbf2, const float* w_t2,
+                                    float* dx_down, float* d_sbf_p, float* d_t_p, float* dw_sbf2, float* dw_t2,
+                                    void* stream);
 /* out[cols, rows] = in[rows, cols]^T (weights for the input-gradient GEMM dx = dy W) */
 int dig3d_transpose(const float* in, int32_t rows, int32_t cols, float* out, void* stream);
 /* SchNet training path: gaussian smearing gauss[E, n_gauss] (schnet.py:92-94) and cosine cutoff cut[E]

@@ -49,3 +49,39 @@ def test_two_rank_gloo_sharding_and_reductions():
     port = 29000 + (os.getpid() % 500)
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     assert all(ret[r] for r in range(world)) and len(ret) == world
+
+
+def _grad_worker(rank, world, port, ret):
+    """Each rank backpropagates its shard; after allreduce_gradients every rank holds the full-batch gradient.
+    (A plain torch layer stands in for the model: the CUDA kernels cannot run here, the exchange logic can.)"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        model = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Tanh(), torch.nn.Linear(7, 1))
+        frozen = torch.nn.Parameter(torch.ones(3), requires_grad=False)
+        unused = torch.nn.Parameter(torch.ones(2))                  # never reaches the loss: grad None -> zeros
+        x = torch.randn(8, 5)
+        y = torch.randn(8, 1)
+        lo, hi = parallel.shard_bounds(8, rank, world)
+        loss = torch.nn.functional.mse_loss(model(x[lo:hi]), y[lo:hi])        # equal shards: mean of means = mean
+        loss.backward()
+        nbytes = parallel.allreduce_gradients(list(model.parameters()) + [frozen, unused])
+        ref = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Tanh(), torch.nn.Linear(7, 1))
+        ref.load_state_dict(model.state_dict())
+        torch.nn.functional.mse_loss(ref(x), y).backward()
+        ok = all(torch.allclose(p.grad, q.grad, atol=1e-6) for p, q in zip(model.parameters(), ref.parameters()))
+        ok = ok and frozen.grad is None and torch.equal(unused.grad, torch.zeros(2))
+        ok = ok and nbytes == 4 * (sum(p.numel() for p in model.parameters()) + 2)
+        ret[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gradient_allreduce():
+    world = 2
+    ret = mp.Manager().dict()
+    port = 29500 + (os.getpid() % 400)
+    mp.spawn(_grad_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert all(ret[r] for r in range(world)) and len(ret) == world
