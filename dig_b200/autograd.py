@@ -277,3 +277,24 @@ def basis_project(g, bess, basis_id, ns, nr, sbf1_weights, t1_weights):
     torsion = t1_weights is not None
     outs = _BasisProject.apply(g, bess, basis_id, ns, nr, n, torsion, *sbf1_weights, *(t1_weights or []))
     return list(outs[:n]), (list(outs[n:]) if torsion else None)
+
+
+class _GraphNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, weight, bias, mean_scale, graph_ptr, eps):
+        h = _c(h)
+        y, shift, std = ops.graphnorm(h, graph_ptr, weight.detach(), bias.detach(), mean_scale.detach(), eps)
+        ctx.save_for_backward(h, weight, mean_scale, shift, std, graph_ptr)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        h, weight, mean_scale, shift, std, graph_ptr = ctx.saved_tensors
+        dx, dw, db, dms = ops.graphnorm_bwd(h, _c(dy), graph_ptr, weight.detach(), mean_scale.detach(), shift, std)
+        return dx, dw, db, dms, None, None
+
+
+def graphnorm(h, module, graph_ptr):
+    """torch_geometric.nn.GraphNorm holder `module` (weight, bias, mean_scale, eps)."""
+    return _GraphNorm.apply(h, module.weight, module.bias, module.mean_scale, graph_ptr, module.eps)

@@ -246,6 +246,69 @@ __global__ void schnet_edge_features_kernel(const float* __restrict__ dist, int6
   }
 }
 
+// ------------------------------------------------------------------ GraphNorm (torch_geometric.nn.GraphNorm, comenet.py:160,213)
+// One CTA per graph, one thread per channel.  Forward: shift = mean * mean_scale, o = h - shift, std = sqrt(mean(o^2) + eps),
+// y = weight * o / std + bias (same operation order as the fused inference kernels in comenet.cu).
+__global__ void graphnorm_fwd_kernel(const float* __restrict__ h, const int32_t* __restrict__ graph_ptr, int width,
+                                     const float* __restrict__ weight, const float* __restrict__ bias,
+                                     const float* __restrict__ mean_scale, float eps, float* __restrict__ y,
+                                     float* __restrict__ shift, float* __restrict__ stdv) {
+  const int g = blockIdx.x;
+  const int n0 = graph_ptr[g], n1 = graph_ptr[g + 1];
+  const float cnt = (float)max(n1 - n0, 1);
+  for (int c = threadIdx.x; c < width; c += blockDim.x) {
+    float sum = 0.f;
+    for (int n = n0; n < n1; ++n) sum += h[(size_t)n * width + c];
+    const float sh = __fmul_rn(__fdiv_rn(sum, cnt), __ldg(mean_scale + c));
+    float sq = 0.f;
+    for (int n = n0; n < n1; ++n) { const float o = __fsub_rn(h[(size_t)n * width + c], sh); sq += __fmul_rn(o, o); }
+    const float sd = __fsqrt_rn(__fadd_rn(__fdiv_rn(sq, cnt), eps));
+    shift[(size_t)g * width + c] = sh;
+    stdv[(size_t)g * width + c] = sd;
+    const float w = __ldg(weight + c), b = __ldg(bias + c);
+    for (int n = n0; n < n1; ++n) {
+      const float o = __fsub_rn(h[(size_t)n * width + c], sh);
+      y[(size_t)n * width + c] = __fadd_rn(__fdiv_rn(__fmul_rn(w, o), sd), b);
+    }
+  }
+}
+
+// Backward.  With n nodes in the graph, r = 1/std, o_i = h_i - shift, A = sum dy_i o_i, B = sum dy_i, S = sum h_i:
+//   d weight += A r          d bias += B
+//   dv = -0.5 w A r^3        do_i = dy_i w r + 2 dv o_i / n        D = sum_i do_i = w r B + 2 dv (S - n shift) / n
+//   dx_i = do_i - mean_scale D / n            d mean_scale += -(S / n) D
+__global__ void graphnorm_bwd_kernel(const float* __restrict__ h, const float* __restrict__ dy,
+                                     const int32_t* __restrict__ graph_ptr, int width, const float* __restrict__ weight,
+                                     const float* __restrict__ mean_scale, const float* __restrict__ shift,
+                                     const float* __restrict__ stdv, float* __restrict__ dx, float* __restrict__ dweight,
+                                     float* __restrict__ dbias, float* __restrict__ dmean_scale) {
+  const int g = blockIdx.x;
+  const int n0 = graph_ptr[g], n1 = graph_ptr[g + 1];
+  if (n1 <= n0) return;
+  const float cnt = (float)(n1 - n0);
+  for (int c = threadIdx.x; c < width; c += blockDim.x) {
+    const float sh = shift[(size_t)g * width + c], r = 1.0f / stdv[(size_t)g * width + c];
+    const float w = __ldg(weight + c), ms = __ldg(mean_scale + c);
+    float A = 0.f, B = 0.f, S = 0.f;
+    for (int n = n0; n < n1; ++n) {
+      const float hv = h[(size_t)n * width + c], d = dy[(size_t)n * width + c];
+      A = fmaf(d, hv - sh, A);
+      B += d;
+      S += hv;
+    }
+    const float dv = -0.5f * w * A * r * r * r;
+    const float D = w * r * B + 2.0f * dv * (S - cnt * sh) / cnt;
+    const float back = ms * D / cnt;
+    for (int n = n0; n < n1; ++n) {
+      const float o = h[(size_t)n * width + c] - sh;
+      dx[(size_t)n * width + c] = dy[(size_t)n * width + c] * w * r + 2.0f * dv * o / cnt - back;
+    }
+    atomicAdd(dweight + c, A * r);
+    atomicAdd(dbias + c, B);
+    atomicAdd(dmean_scale + c, -(S / cnt) * D);
+  }
+}
+
 template <int NOUT, int K>
 static int launch_linear_tiled(const float* x, int64_t rows, const float* w, const float* b, float* y, cudaStream_t st) {
   auto kfn = linear_tiled_kernel<NOUT, K>;
@@ -271,7 +334,7 @@ int dig3d_linear(const float* x, int64_t rows, int32_t k, int32_t nout, const fl
 #define DIG3D_LT(NO, KK) if (nout == NO && k == KK) rc = launch_linear_tiled<NO, KK>(x, rows, w, bias, y, st);
   DIG3D_LT(128, 128) DIG3D_LT(64, 128) DIG3D_LT(128, 64) DIG3D_LT(256, 128) DIG3D_LT(256, 256) DIG3D_LT(128, 256)
   DIG3D_LT(128, 384) DIG3D_LT(32, 32) DIG3D_LT(64, 64) DIG3D_LT(128, 32) DIG3D_LT(32, 128) DIG3D_LT(256, 64)
-  DIG3D_LT(64, 256) DIG3D_LT(256, 512) DIG3D_LT(384, 128)
+  DIG3D_LT(64, 256) DIG3D_LT(256, 512) DIG3D_LT(384, 128) DIG3D_LT(512, 256)
 #undef DIG3D_LT
   if (rc == -100) {
     const int64_t total = rows * nout;
@@ -366,6 +429,29 @@ int dig3d_schnet_edge_features(const float* dist, int64_t n_edges, const float* 
   const int64_t total = n_edges * (n_gauss + 1);
   schnet_edge_features_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
       dist, n_edges, offset, n_gauss, (float)coeff, (float)(1.0 / cutoff), gauss, cut);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_graphnorm(const float* h, const int32_t* graph_ptr, int64_t n_graphs, int32_t width, const float* weight,
+                    const float* bias, const float* mean_scale, double eps, float* y, float* shift, float* stdv,
+                    void* stream) {
+  DIG3D_REQUIRE(h && graph_ptr && weight && bias && mean_scale && y && shift && stdv && width > 0, "graphnorm: bad arguments");
+  if (n_graphs == 0) return DIG3D_OK;
+  graphnorm_fwd_kernel<<<(int)n_graphs, width < 256 ? width : 256, 0, (cudaStream_t)stream>>>(
+      h, graph_ptr, width, weight, bias, mean_scale, (float)eps, y, shift, stdv);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_graphnorm_bwd(const float* h, const float* dy, const int32_t* graph_ptr, int64_t n_graphs, int32_t width,
+                        const float* weight, const float* mean_scale, const float* shift, const float* stdv, float* dx,
+                        float* dweight, float* dbias, float* dmean_scale, void* stream) {
+  DIG3D_REQUIRE(h && dy && graph_ptr && weight && mean_scale && shift && stdv && dx && dweight && dbias && dmean_scale &&
+                    width > 0, "graphnorm_bwd: bad arguments");
+  if (n_graphs == 0) return DIG3D_OK;
+  graphnorm_bwd_kernel<<<(int)n_graphs, width < 256 ? width : 256, 0, (cudaStream_t)stream>>>(
+      h, dy, graph_ptr, width, weight, mean_scale, shift, stdv, dx, dweight, dbias, dmean_scale);
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
 }

@@ -625,3 +625,25 @@ def triplet_basis_project_bwd(g, bess, basis_id, d_sbf_p, d_t_p, n_sbf, n_tbf):
          _p(g.dst), _p(g.row_ptr), _p(g.trip_ptr), _p(g.graph_ptr), _p(g.batch, torch.int64), g.n_edges, g.n_triplets,
          int(basis_id), ps, pt, _p(dws), _p(dwt), _stream())
     return dws, dwt
+
+
+def graphnorm(h, graph_ptr, weight, bias, mean_scale, eps=1e-5):
+    """-> (y, shift [G, W], std [G, W])"""
+    g, wd = graph_ptr.numel() - 1, h.size(1)
+    y = torch.empty_like(h)
+    shift = torch.empty(g, wd, device=h.device, dtype=F32)
+    std = torch.empty(g, wd, device=h.device, dtype=F32)
+    call("dig3d_graphnorm", _p(h, F32, "h"), _p(graph_ptr, torch.int32), g, wd, _p(weight, F32), _p(bias, F32),
+         _p(mean_scale, F32), float(eps), _p(y), _p(shift), _p(std), _stream())
+    return y, shift, std
+
+
+def graphnorm_bwd(h, dy, graph_ptr, weight, mean_scale, shift, std):
+    g, wd = graph_ptr.numel() - 1, h.size(1)
+    dx = torch.empty_like(h)
+    dw = torch.zeros(wd, device=h.device, dtype=F32)
+    db = torch.zeros(wd, device=h.device, dtype=F32)
+    dms = torch.zeros(wd, device=h.device, dtype=F32)
+    call("dig3d_graphnorm_bwd", _p(h, F32, "h"), _p(dy, F32, "dy"), _p(graph_ptr, torch.int32), g, wd, _p(weight, F32),
+         _p(mean_scale, F32), _p(shift), _p(std), _p(dx), _p(dw), _p(db), _p(dms), _stream())
+    return dx, dw, db, dms

@@ -10,8 +10,9 @@ from math import sqrt
 import torch
 from torch import nn
 
+from ... import autograd as ag
 from ... import ops
-from ._common import glorot, require_cuda
+from ._common import glorot, require_cuda, wants_grad
 
 
 class Linear(nn.Module):
@@ -168,6 +169,8 @@ class ComENet(nn.Module):
         g = ops.build_graph(pos, batch, self.cutoff, num_graphs=getattr(data, "num_graphs", None),
                             want_edge_index=False)
         f1, f2, _ = ops.comenet_geometry(g, pos, self.cutoff)
+        if wants_grad(self):
+            return self._forward_train(z, g, f1, f2)
         x = ops.comenet_embed(z, self.emb.emb.weight)
         no_head = ops.pack_comenet_head([], None)
         head = ops.pack_comenet_head(self.lins, self.lin_out)
@@ -176,6 +179,30 @@ class ComENet(nn.Module):
             x = ops.comenet_block(x, f1, f2, g, ops.pack_comenet_block(block), head if last else no_head,
                                   self.out_channels, last)
         return ops.segment_sum(x, g.graph_ptr)          # energy = scatter(x, batch)   comenet.py:398
+
+    def _forward_train(self, z, g, f1, f2):
+        """Differentiable forward (reference comenet.py:386-399 and SimpleInteractionBlock.forward :195-215, op for op)
+        over dig_b200.autograd's primitives; the geometry features f1 / f2 carry no parameters."""
+        swish_, lin = ag.swish, ag.lin
+        x = swish_(ag.gather_rows(self.emb.emb.weight, z))                     # comenet.py:125-127
+        for blk in self.interaction_blocks:
+            x = swish_(lin(blk.lin, x))
+            hs = []
+            for conv, lf, l, feat in ((blk.conv1, blk.lin_feature1, blk.lin1, f1),
+                                      (blk.conv2, blk.lin_feature2, blk.lin2, f2)):
+                w = lin(lf.lin2, lin(lf.lin1, feat))                            # TwoLayerLinear, no bias / act
+                agg = ag.segment_sum(ag.mul(w, ag.gather_rows(x, g.src)), g.row_ptr, g.dst)     # GraphConv, aggr='add'
+                h = ag.add(lin(conv.lin_rel, agg), lin(conv.lin_root, x))
+                hs.append(swish_(lin(l, h)))
+            h = ag.add(lin(blk.lin_cat, torch.cat(hs, 1)), x)
+            for l in blk.lins:
+                h = ag.add(swish_(lin(l, h)), h)
+            h = ag.graphnorm(h, blk.norm, g.graph_ptr)
+            x = lin(blk.final, h)
+        for l in self.lins:
+            x = swish_(lin(l, x))
+        x = lin(self.lin_out, x)
+        return ag.segment_sum(x, g.graph_ptr, g.batch)
 
     def forward(self, batch_data):
         return self._forward(batch_data)

@@ -323,6 +323,16 @@ int dig3d_sphere_triplet_gather_bwd(const float* dm, const float* x_down, const 
                                     const int32_t* trip_ptr, int64_t n_edges, const float* w_sbf2, const float* w_t2,
                                     float* dx_down, float* d_sbf_p, float* d_t_p, float* dw_sbf2, float* dw_t2,
                                     void* stream);
+/* GraphNorm (torch_geometric.nn.GraphNorm as used at comenet.py:160,213) for the training path:
+ * y = weight * (h - mean*mean_scale) / sqrt(mean((h - mean*mean_scale)^2) + eps) + bias per graph and channel;
+ * shift / stdv [n_graphs, width] are kept for the backward.  bwd: dx every row written; dweight / dbias /
+ * dmean_scale [width] accumulated with atomics (zeroed by the caller). */
+int dig3d_graphnorm(const float* h, const int32_t* graph_ptr, int64_t n_graphs, int32_t width, const float* weight,
+                    const float* bias, const float* mean_scale, double eps, float* y, float* shift, float* stdv,
+                    void* stream);
+int dig3d_graphnorm_bwd(const float* h, const float* dy, const int32_t* graph_ptr, int64_t n_graphs, int32_t width,
+                        const float* weight, const float* mean_scale, const float* shift, const float* stdv, float* dx,
+                        float* dweight, float* dbias, float* dmean_scale, void* stream);
 /* out[cols, rows] = in[rows, cols]^T (weights for the input-gradient GEMM dx = dy W) */
 int dig3d_transpose(const float* in, int32_t rows, int32_t cols, float* out, void* stream);
 /* SchNet training path: gaussian smearing gauss[E, n_gauss] (schnet.py:92-94) and cosine cutoff cut[E]
