@@ -82,18 +82,21 @@ class _Add(torch.autograd.Function):
 
 
 class _RowScale(torch.autograd.Function):
-    """y[r, :] = a[r, :] * s[r]; s is geometry (no gradient without force training)."""
+    """y[r, :] = a[r, :] * s[r]; s is geometry: its gradient is only needed on the force path."""
 
     @staticmethod
     def forward(ctx, a, s):
-        ctx.save_for_backward(s)
-        return ops.rowscale(_c(a), s)
+        a = _c(a)
+        ctx.save_for_backward(s, a if s.requires_grad else None)
+        return ops.rowscale(a, s)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
-        (s,) = ctx.saved_tensors
-        return ops.rowscale(_c(dy), s), None
+        s, a = ctx.saved_tensors
+        dy = _c(dy)
+        ds = ops.rowdot(dy, a) if (ctx.needs_input_grad[1] and a is not None) else None
+        return ops.rowscale(dy, s), ds
 
 
 class _GatherRows(torch.autograd.Function):
@@ -186,14 +189,15 @@ def scatter_add_rows(y, idx, n_rows):
 
 
 class _EdgeBasis(torch.autograd.Function):
-    """rbf0 = envelope(d/c) * sin(freq * d/c) (differentiable in freq) and the fixed Bessel basis of the edges."""
+    """rbf0 = envelope(d/c) * sin(freq * d/c) (differentiable in freq, and in dist on the force path) and the fixed
+    Bessel basis of the edges (its dist-derivative is handled by _BasisProject)."""
 
     @staticmethod
     def forward(ctx, freq, dist, cutoff, exponent, basis_id, env_on_bessel, nr, n_bessel):
-        rbf0, bess = ops.edge_basis(dist, cutoff, exponent, freq, basis_id, envelope_on_bessel=env_on_bessel,
+        rbf0, bess = ops.edge_basis(dist.detach(), cutoff, exponent, freq, basis_id, envelope_on_bessel=env_on_bessel,
                                     num_radial=nr, n_bessel=n_bessel)
         ctx.save_for_backward(freq, dist)
-        ctx.cfg = (cutoff, exponent)
+        ctx.cfg = (cutoff, exponent, basis_id, env_on_bessel, n_bessel)
         ctx.mark_non_differentiable(bess)
         return rbf0, bess
 
@@ -201,15 +205,22 @@ class _EdgeBasis(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, drbf0, _dbess):
         freq, dist = ctx.saved_tensors
-        return (ops.rbf_freq_grad(dist, ctx.cfg[0], ctx.cfg[1], freq, _c(drbf0)),) + (None,) * 7
+        cutoff, exponent, basis_id, env_on_bessel, n_bessel = ctx.cfg
+        drbf0 = _c(drbf0)
+        dfreq = ops.rbf_freq_grad(dist.detach(), cutoff, exponent, freq, drbf0) if ctx.needs_input_grad[0] else None
+        ddist = None
+        if ctx.needs_input_grad[1]:
+            ddist, _ = ops.edge_basis_bwd(dist.detach(), cutoff, exponent, freq, basis_id, env_on_bessel, drbf0, n_bessel)
+        return (dfreq, ddist) + (None,) * 6
 
 
 class _BasisProject(torch.autograd.Function):
-    """lin_sbf1(sbf) / lin_t1(tbf) of up to four layers with the fused basis-projection kernel (basis.cu); the
-    [T, ns*nr] / [T, ns*ns*nr] bases are only materialised in backward, for the weight gradients."""
+    """lin_sbf1(sbf) / lin_t1(tbf) of up to four layers with the fused basis-projection kernel (basis.cu).  Backward:
+    weight gradients with the harmonics recomputed on chip (the [T, ns*ns*nr] basis is never materialised) and, on the
+    force path, d/d(dist_kj) and d/d(angle) of the sbf branch (the torsion branch has no geometry backward yet)."""
 
     @staticmethod
-    def forward(ctx, g, bess, basis_id, ns, nr, n_layers, torsion, *weights):
+    def forward(ctx, g, bess, dist, angle, geo_cfg, basis_id, ns, nr, n_layers, torsion, *weights):
         def rows(ws):
             w = torch.cat([w_.detach() for w_ in ws], 0)
             if w.size(0) < 32:
@@ -218,8 +229,8 @@ class _BasisProject(torch.autograd.Function):
         w_s = rows(weights[:n_layers])
         w_t = rows(weights[n_layers:]) if torsion else None
         sbf_p, t_p = ops.triplet_basis_project(g, bess, basis_id, w_s, w_t)
-        ctx.g, ctx.cfg = g, (basis_id, ns, nr, n_layers, torsion)
-        ctx.save_for_backward(bess)
+        ctx.g, ctx.cfg, ctx.geo_cfg = g, (basis_id, ns, nr, n_layers, torsion), geo_cfg
+        ctx.save_for_backward(bess, w_s)
         ctx.set_materialize_grads(False)
         outs = [sbf_p[l] for l in range(n_layers)]
         if torsion:
@@ -229,16 +240,27 @@ class _BasisProject(torch.autograd.Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, *grads):
-        (bess,) = ctx.saved_tensors
+        bess, w_s = ctx.saved_tensors
         basis_id, ns, nr, n_layers, torsion = ctx.cfg
         g = ctx.g
         d_s = [None if d is None else _c(d) for d in grads[:n_layers]]
         d_t = [None if d is None else _c(d) for d in grads[n_layers:]] if torsion else None
-        dws, dwt = ops.triplet_basis_project_bwd(g, bess, basis_id, d_s, d_t, ns * nr, ns * ns * nr)
-        out = [None if grads[l] is None else dws[8 * l:8 * l + 8] for l in range(n_layers)]
-        if torsion:
-            out += [None if grads[n_layers + l] is None else dwt[8 * l:8 * l + 8] for l in range(n_layers)]
-        return (None,) * 7 + tuple(out)
+        out = [None] * len(grads)
+        if any(ctx.needs_input_grad[10:]):
+            dws, dwt = ops.triplet_basis_project_bwd(g, bess, basis_id, d_s, d_t, ns * nr, ns * ns * nr)
+            out = [None if grads[l] is None else dws[8 * l:8 * l + 8] for l in range(n_layers)]
+            if torsion:
+                out += [None if grads[n_layers + l] is None else dwt[8 * l:8 * l + 8] for l in range(n_layers)]
+        ddist = dangle = None
+        if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+            if torsion:
+                raise NotImplementedError("forces through the torsion basis (SphereNet, energy_and_force=True) are not "
+                                          "implemented: no backward kernel for torsion_emb / the torsion angle")
+            cutoff, exponent, env_on_bessel, dist = ctx.geo_cfg
+            _, bess_dx = ops.edge_basis_bwd(dist.detach(), cutoff, exponent, None, basis_id, env_on_bessel, None, ns * nr,
+                                            want_ddist=False, want_bess_dx=True)
+            ddist, dangle = ops.triplet_basis_project_bwd_geom(g, bess, bess_dx, basis_id, d_s, w_s, cutoff)
+        return (None, None, ddist, dangle) + (None,) * 6 + tuple(out)
 
 
 class _TripletGather(torch.autograd.Function):
@@ -271,11 +293,14 @@ def edge_basis(freq, dist, cutoff, exponent, basis_id, env_on_bessel, nr, n_bess
     return _EdgeBasis.apply(freq, dist, cutoff, exponent, basis_id, env_on_bessel, nr, n_bessel)
 
 
-def basis_project(g, bess, basis_id, ns, nr, sbf1_weights, t1_weights):
-    """-> (list of sbf_p[l] [T, 8], list of t_p[l] [T, 8] or None) for len(sbf1_weights) <= 4 layers."""
+def basis_project(g, bess, dist, angle, geo_cfg, basis_id, ns, nr, sbf1_weights, t1_weights):
+    """-> (list of sbf_p[l] [T, 8], list of t_p[l] [T, 8] or None) for len(sbf1_weights) <= 4 layers.
+    dist / angle: the (possibly position-dependent) geometry tensors, only used to route gradients;
+    geo_cfg = (cutoff, envelope_exponent, envelope_on_bessel, dist)."""
     n = len(sbf1_weights)
     torsion = t1_weights is not None
-    outs = _BasisProject.apply(g, bess, basis_id, ns, nr, n, torsion, *sbf1_weights, *(t1_weights or []))
+    outs = _BasisProject.apply(g, bess, dist, angle, geo_cfg, basis_id, ns, nr, n, torsion, *sbf1_weights,
+                               *(t1_weights or []))
     return list(outs[:n]), (list(outs[n:]) if torsion else None)
 
 
@@ -298,3 +323,56 @@ class _GraphNorm(torch.autograd.Function):
 def graphnorm(h, module, graph_ptr):
     """torch_geometric.nn.GraphNorm holder `module` (weight, bias, mean_scale, eps)."""
     return _GraphNorm.apply(h, module.weight, module.bias, module.mean_scale, graph_ptr, module.eps)
+
+
+class _Geometry(torch.autograd.Function):
+    """dist[E] (and angle[T]) as differentiable functions of pos: values are the ones the graph kernels computed
+    (bit-exact with inference), backward scatters d/d(pos) (csrc/train_geom.cu)."""
+
+    @staticmethod
+    def forward(ctx, pos, g, want_angle):
+        ctx.g = g
+        ctx.save_for_backward(pos)
+        dist = g.dist.detach().view(-1)
+        if want_angle:
+            return dist, g.angle.detach().view(-1)
+        return dist
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, ddist, dangle=None):
+        (pos,) = ctx.saved_tensors
+        g = ctx.g
+        dpos = torch.zeros_like(pos)
+        p = _c(pos.detach())
+        if ddist is not None:
+            ops.edge_dist_bwd(p, g, _c(ddist), dpos)
+        if dangle is not None:
+            ops.triplet_angle_bwd(p, g, _c(dangle), dpos)
+        return dpos, None, None
+
+
+class _SchnetEdgeFeatures(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, dist, offset, coeff, cutoff):
+        ctx.save_for_backward(dist, offset)
+        ctx.cfg = (coeff, cutoff)
+        return ops.schnet_edge_features(dist.detach(), offset, coeff, cutoff)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dgauss, dcut):
+        dist, offset = ctx.saved_tensors
+        if not ctx.needs_input_grad[0]:
+            return None, None, None, None
+        dg = None if dgauss is None else _c(dgauss)
+        dc = None if dcut is None else _c(dcut)
+        return ops.schnet_edge_features_bwd(dist.detach(), offset, ctx.cfg[0], ctx.cfg[1], dg, dc), None, None, None
+
+
+def geometry(pos, g, want_angle):
+    return _Geometry.apply(pos, g, want_angle)
+
+
+def schnet_edge_features(dist, offset, coeff, cutoff):
+    return _SchnetEdgeFeatures.apply(dist, offset, coeff, cutoff)

@@ -239,15 +239,19 @@ def basis_sources(flavor, num_spherical, num_radial):
         yall = harmonics_gemnet(num_spherical, zero_m_only=False)
     else:
         raise ValueError(flavor)
-    out = {"bessel": [], "yl0": [], "ylm": []}
+    out = {"bessel": [], "yl0": [], "ylm": [], "bessel_dx": [], "yl0_dtheta": []}
     for l in range(num_spherical):
         for n in range(num_radial):
             out["bessel"].append(_src(bess[l][n], [x]))
+            # d/dx of the same closed form (force path: dE/dpos needs d(basis)/d(dist)); not a reference string --
+            # the reference differentiates the lambdified graph with autograd
+            out["bessel_dx"].append(_src(sym.diff(bess[l][n], x), [x]))
     for l in range(num_spherical):
         if l == 0:
             out["yl0"].append(repr(float(sym.lambdify([theta], y0[0][0])(0))))
         else:
             out["yl0"].append(_src(y0[l][0], [theta]))
+        out["yl0_dtheta"].append("0.0" if l == 0 else _src(sym.diff(y0[l][0], theta), [theta]))
     for l in range(num_spherical):
         if l == 0:
             out["ylm"].append(repr(float(sym.lambdify([theta, phi], yall[0][0])(0, 0))))

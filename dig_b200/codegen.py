@@ -161,6 +161,9 @@ def emit_header(tag, flavor, num_spherical, num_radial, sources):
         emit_function("yl0", ["theta"], sources["yl0"], "real spherical harmonics Y_l^0(theta)"),
         emit_function("ylm", ["theta", "phi"], sources["ylm"],
                       "real spherical harmonics, reference flat order"),
+        emit_function("bessel_dx", ["x"], sources["bessel_dx"],
+                      "d/dx of bessel() (symbolic derivative of the same closed forms; force path)"),
+        emit_function("yl0_dtheta", ["theta"], sources["yl0_dtheta"], "d/dtheta of yl0() (force path)"),
         "}  // namespace\n",
     ]
     return "\n".join(parts)

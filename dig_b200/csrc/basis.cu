@@ -22,6 +22,8 @@ struct B76 {
   __device__ static void bessel(float x, float (&o)[NB]) { basis_dimenet_7_6::bessel(x, o); }
   __device__ static void yl0(float t, float (&o)[NS]) { basis_dimenet_7_6::yl0(t, o); }
   __device__ static void ylm(float t, float p, float (&o)[NY]) { basis_dimenet_7_6::ylm(t, p, o); }
+  __device__ static void bessel_dx(float x, float (&o)[NB]) { basis_dimenet_7_6::bessel_dx(x, o); }
+  __device__ static void yl0_dtheta(float t, float (&o)[NS]) { basis_dimenet_7_6::yl0_dtheta(t, o); }
 };
 struct B36 {
   static constexpr int NS = basis_dimenet_3_6::NS, NR = basis_dimenet_3_6::NR;
@@ -29,6 +31,8 @@ struct B36 {
   __device__ static void bessel(float x, float (&o)[NB]) { basis_dimenet_3_6::bessel(x, o); }
   __device__ static void yl0(float t, float (&o)[NS]) { basis_dimenet_3_6::yl0(t, o); }
   __device__ static void ylm(float t, float p, float (&o)[NY]) { basis_dimenet_3_6::ylm(t, p, o); }
+  __device__ static void bessel_dx(float x, float (&o)[NB]) { basis_dimenet_3_6::bessel_dx(x, o); }
+  __device__ static void yl0_dtheta(float t, float (&o)[NS]) { basis_dimenet_3_6::yl0_dtheta(t, o); }
 };
 struct G23 {
   static constexpr int NS = basis_gemnet_2_3::NS, NR = basis_gemnet_2_3::NR;
@@ -36,6 +40,8 @@ struct G23 {
   __device__ static void bessel(float x, float (&o)[NB]) { basis_gemnet_2_3::bessel(x, o); }
   __device__ static void yl0(float t, float (&o)[NS]) { basis_gemnet_2_3::yl0(t, o); }
   __device__ static void ylm(float t, float p, float (&o)[NY]) { basis_gemnet_2_3::ylm(t, p, o); }
+  __device__ static void bessel_dx(float x, float (&o)[NB]) { basis_gemnet_2_3::bessel_dx(x, o); }
+  __device__ static void yl0_dtheta(float t, float (&o)[NS]) { basis_gemnet_2_3::yl0_dtheta(t, o); }
 };
 
 // Envelope.forward (features.py:159-164), ATen-CUDA op order:
@@ -399,6 +405,155 @@ triplet_basis_project_bwd_kernel(const float* __restrict__ bess, const float* __
     }
 }
 
+// ------------------------------------------------------------------ force path: d(basis)/d(dist), d(basis)/d(angle)
+// env'(x) = -1/x^2 + a (p-1) x^(p-2) + b p x^(p-1) + c (p+1) x^p
+__device__ __forceinline__ float envelope_dx(float x, int p, float a, float b, float c) {
+  const float xp2 = powf(x, (float)(p - 2));
+  const float xp1 = xp2 * x, xp0 = xp1 * x;
+  return -1.0f / (x * x) + a * (float)(p - 1) * xp2 + b * (float)p * xp1 + c * (float)(p + 1) * xp0;
+}
+
+// Per edge: ddist[e] = sum_n drbf0[e][n] * d(env(x) sin(freq_n x))/dx / cutoff   (x = dist / cutoff), and the
+// x-derivative of the edge's (enveloped) Bessel basis, kept for triplet_basis_project_bwd_geom.
+template <class BS>
+__global__ void edge_basis_bwd_kernel(const float* __restrict__ dist, int n_edges, float inv_cutoff, int p, float ea,
+                                      float eb, float ec, const float* __restrict__ freq, int env_on_bessel,
+                                      const float* __restrict__ drbf0, float* __restrict__ ddist,
+                                      float* __restrict__ bess_dx) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  const float x = __fmul_rn(dist[e], inv_cutoff);
+  const float env = envelope(x, p, ea, eb, ec), envd = envelope_dx(x, p, ea, eb, ec);
+  if (ddist) {
+    float acc = 0.f;
+    if (drbf0) {
+#pragma unroll
+      for (int n = 0; n < BS::NR; ++n) {
+        const float f = __ldg(freq + n);
+        acc = fmaf(drbf0[(size_t)e * BS::NR + n], envd * sinf(f * x) + env * f * cosf(f * x), acc);
+      }
+    }
+    ddist[e] = acc * inv_cutoff;
+  }
+  if (bess_dx) {
+    float b[BS::NB], bd[BS::NB];
+    BS::bessel(x, b);
+    BS::bessel_dx(x, bd);
+#pragma unroll
+    for (int c = 0; c < BS::NB; ++c)
+      bess_dx[(size_t)e * BS::NB + c] = env_on_bessel ? fmaf(envd, b[c], env * bd[c]) : bd[c];
+  }
+}
+
+// Backward of the fused projection w.r.t. the geometry (DimeNet++ / SphereNet without the torsion branch):
+//   dangle[t]  = sum_q d sbf_p[q][t] * sum_l Y_l0'(angle_t) * Rs[q][l],      Rs[q][l]  = sum_r bess[kj][l,r]  w_sbf1[q][l,r]
+//   ddist[kj] += sum_{t uses kj} sum_q d sbf_p[q][t] * sum_l Y_l0(angle_t) * Rsd[q][l] / cutoff,   Rsd from bess_dx
+// One warp per (k->j) edge, lane = q = layer*8 + row; every triplet is visited exactly once (by its kj edge).
+template <class BS>
+struct PrjGeomSmem {
+  float ws[BS::NB * PRJ_LD];
+  float bess[PRJ_WARPS][BS::NB];
+  float bessd[PRJ_WARPS][BS::NB];
+  static constexpr int YLD = ((2 * BS::NS + 3) / 4) * 4;
+  alignas(16) float y[PRJ_WARPS][32][YLD];
+  int32_t trip[PRJ_WARPS][32];
+};
+
+template <class BS>
+__global__ void __launch_bounds__(PRJ_WARPS * 32)
+triplet_basis_project_bwd_geom_kernel(const float* __restrict__ bess, const float* __restrict__ bess_dx,
+                                      const float* __restrict__ angle, const int32_t* __restrict__ src,
+                                      const int32_t* __restrict__ dst, const int32_t* __restrict__ row_ptr,
+                                      const int32_t* __restrict__ trip_ptr, const int32_t* __restrict__ graph_ptr,
+                                      const int64_t* __restrict__ batch, int n_edges, PrjGradPtrs gp,
+                                      const float* __restrict__ w_sbf1, float inv_cutoff, float* __restrict__ ddist,
+                                      float* __restrict__ dangle) {
+  constexpr int NS = BS::NS, NR = BS::NR, NB = BS::NB;
+  using SM = PrjGeomSmem<BS>;
+  extern __shared__ __align__(16) unsigned char prj_smem_raw[];
+  SM& sm = *reinterpret_cast<SM*>(prj_smem_raw);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int id = threadIdx.x; id < 32 * NB; id += PRJ_WARPS * 32) sm.ws[(id % NB) * PRJ_LD + id / NB] = __ldg(w_sbf1 + id);
+  __syncthreads();
+  const float* my_ds = gp.ds[lane >> 3];
+  const int mrow = lane & 7;
+  for (int kj = blockIdx.x * PRJ_WARPS + w; kj < n_edges; kj += gridDim.x * PRJ_WARPS) {
+    const int k = src[kj], j = dst[kj];
+    __syncwarp();
+    for (int c = lane; c < NB; c += 32) {
+      sm.bess[w][c] = __ldg(bess + (size_t)kj * NB + c);
+      sm.bessd[w][c] = __ldg(bess_dx + (size_t)kj * NB + c);
+    }
+    __syncwarp();
+    float Rs[NS], Rsd[NS];
+#pragma unroll
+    for (int b = 0; b < NS; ++b) {
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const float wv = sm.ws[(b * NR + r) * PRJ_LD + lane];
+        a0 = fmaf(sm.bess[w][b * NR + r], wv, a0);
+        a1 = fmaf(sm.bessd[w][b * NR + r], wv, a1);
+      }
+      Rs[b] = a0;
+      Rsd[b] = a1;
+    }
+    float acc_x = 0.f;
+    const int jbase = row_ptr[j], dj = row_ptr[j + 1] - jbase;
+    const int rank_k = kj - jbase;
+    const int g = (int)batch[j];
+    const int lo = graph_ptr[g], hi = graph_ptr[g + 1];
+    for (int c0 = lo; c0 < hi; c0 += 32) {
+      const int i = c0 + lane;
+      int t = -1;
+      if (i < hi && i != k && i != j) {
+        const int ib = row_ptr[i], di = row_ptr[i + 1] - ib;
+        int a = 0, b = di;
+        while (a < b) { int mid = (a + b) >> 1; if (src[ib + mid] < j) a = mid + 1; else b = mid; }
+        if (a < di && src[ib + a] == j) {
+          const int e = ib + a;
+          int a2 = 0, b2 = dj;
+          while (a2 < b2) { int mid = (a2 + b2) >> 1; if (src[jbase + mid] < i) a2 = mid + 1; else b2 = mid; }
+          const bool i_in = (a2 < dj && src[jbase + a2] == i);
+          t = trip_ptr[e] + rank_k - ((i_in && a2 < rank_k) ? 1 : 0);
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, t >= 0);
+      if (t >= 0) {
+        const int slot = __popc(m & ((1u << lane) - 1));
+        sm.trip[w][slot] = t;
+        const float th = angle[t];
+        float y0[NS], yd[NS];
+        BS::yl0(th, y0);
+        BS::yl0_dtheta(th, yd);
+#pragma unroll
+        for (int l = 0; l < NS; ++l) { sm.y[w][slot][l] = y0[l]; sm.y[w][slot][NS + l] = yd[l]; }
+      }
+      __syncwarp();
+      const int cnt = __popc(m);
+      for (int s = 0; s < cnt; ++s) {
+        const int tt = sm.trip[w][s];
+        const float d_q = my_ds ? __ldg(my_ds + (size_t)tt * 8 + mrow) : 0.f;
+        float sy = 0.f, sd = 0.f;
+#pragma unroll
+        for (int l = 0; l < NS; ++l) {
+          sy = fmaf(sm.y[w][s][l], Rsd[l], sy);
+          sd = fmaf(sm.y[w][s][NS + l], Rs[l], sd);
+        }
+        acc_x = fmaf(d_q, sy, acc_x);
+        float va = d_q * sd;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) va += __shfl_xor_sync(0xffffffffu, va, o);
+        if (lane == 0) dangle[tt] = va;
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc_x += __shfl_xor_sync(0xffffffffu, acc_x, o);
+    if (lane == 0) ddist[kj] = acc_x * inv_cutoff;
+  }
+}
+
 template <class BS>
 static int launch_edge_basis(const float* dist, int64_t n_edges, double cutoff, int exponent,
                              const float* freq, int env_on_bessel, float* rbf0, float* bess,
@@ -545,6 +700,64 @@ int dig3d_triplet_basis_project_bwd(const float* bess, const float* angle, const
   }
 #undef DIG3D_PRJB_ONE
 #undef DIG3D_PRJB
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_edge_basis_bwd(const float* dist, int64_t n_edges, double cutoff, int32_t envelope_exponent, const float* freq,
+                         int32_t basis_id, int32_t envelope_on_bessel, const float* drbf0, float* ddist, float* bess_dx,
+                         void* stream) {
+  DIG3D_REQUIRE(dist && (ddist || bess_dx), "edge_basis_bwd: null pointer");
+  DIG3D_REQUIRE(!drbf0 || (freq && ddist), "edge_basis_bwd: drbf0 needs freq and ddist");
+  if (n_edges == 0) return DIG3D_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int p = envelope_exponent + 1;
+  const float a = (float)(-(p + 1) * (p + 2) / 2.0), b = (float)(p * (p + 2)), c = (float)(-p * (p + 1) / 2.0);
+  const float inv = 1.0f / (float)cutoff;
+  const int grid = ceil_div(n_edges, 128);
+  switch (basis_id) {
+    case 0: edge_basis_bwd_kernel<B76><<<grid, 128, 0, st>>>(dist, (int)n_edges, inv, p, a, b, c, freq, envelope_on_bessel, drbf0, ddist, bess_dx); break;
+    case 1: edge_basis_bwd_kernel<B36><<<grid, 128, 0, st>>>(dist, (int)n_edges, inv, p, a, b, c, freq, envelope_on_bessel, drbf0, ddist, bess_dx); break;
+    default: set_error("edge_basis_bwd: unsupported basis_id %d", basis_id); return DIG3D_EUNSUPPORTED;
+  }
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_triplet_basis_project_bwd_geom(const float* bess, const float* bess_dx, const float* angle, const int32_t* src,
+                                         const int32_t* dst, const int32_t* row_ptr, const int32_t* trip_ptr,
+                                         const int32_t* graph_ptr, const int64_t* batch, int64_t n_edges,
+                                         int64_t n_triplets, int32_t basis_id, const float* const* d_sbf_p,
+                                         const float* w_sbf1, double cutoff, float* ddist, float* dangle, void* stream) {
+  DIG3D_REQUIRE(bess && bess_dx && angle && src && dst && row_ptr && trip_ptr && graph_ptr && batch && d_sbf_p &&
+                    w_sbf1 && ddist && dangle, "triplet_basis_project_bwd_geom: null pointer");
+  if (n_edges == 0) return DIG3D_OK;
+  PrjGradPtrs gp;
+  for (int l = 0; l < 4; ++l) { gp.ds[l] = d_sbf_p[l]; gp.dt[l] = nullptr; }
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t want = (n_edges + PRJ_WARPS - 1) / PRJ_WARPS;
+  const int grid = (int)(want < 2 * n_sm ? want : 2 * n_sm);
+  const float inv = 1.0f / (float)cutoff;
+#define DIG3D_PRJG(BS)                                                                                      \
+  {                                                                                                         \
+    auto kfn = triplet_basis_project_bwd_geom_kernel<BS>;                                                   \
+    const size_t smem = sizeof(PrjGeomSmem<BS>);                                                            \
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { \
+      set_error("triplet_basis_project_bwd_geom: cannot reserve %zu bytes of shared memory", smem);         \
+      return DIG3D_ECUDA;                                                                                   \
+    }                                                                                                       \
+    kfn<<<grid, PRJ_WARPS * 32, smem, st>>>(bess, bess_dx, angle, src, dst, row_ptr, trip_ptr, graph_ptr,   \
+                                            batch, (int)n_edges, gp, w_sbf1, inv, ddist, dangle);           \
+  }
+  switch (basis_id) {
+    case 0: DIG3D_PRJG(B76); break;
+    case 1: DIG3D_PRJG(B36); break;
+    default: set_error("triplet_basis_project_bwd_geom: unsupported basis_id %d", basis_id); return DIG3D_EUNSUPPORTED;
+  }
+#undef DIG3D_PRJG
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
 }

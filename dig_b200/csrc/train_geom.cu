@@ -1,0 +1,175 @@
+// Position gradients (forces = -dE/dpos, reference run.py:126,165: torch.autograd.grad(out, pos)) for the geometry
+// the models read: edge lengths (all models) and triplet angles (DimeNet++ / SphereNet), plus the SchNet edge features.
+//
+//   edge_dist_bwd        dist[e] = |pos_i - pos_j|                         schnet.py:158, geometric_computing.py:23
+//   triplet_angle_bwd    angle[t] = atan2(|ji x jk|, ji . jk)              geometric_computing.py:43-48
+//   schnet_edge_features_bwd / rowdot                                        schnet.py:24-33,92-94
+//
+// The torsion angle's backward (SphereNet forces) is not implemented.
+#include "common.cuh"
+
+namespace dig3d {
+
+__device__ __forceinline__ f3 scale3(const f3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ f3 add3(const f3 a, const f3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ f3 cross3(const f3 a, const f3 b) {
+  return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+__device__ __forceinline__ void atomic_add3(float* __restrict__ p, int n, const f3 v) {
+  atomicAdd(p + 3 * n, v.x);
+  atomicAdd(p + 3 * n + 1, v.y);
+  atomicAdd(p + 3 * n + 2, v.z);
+}
+__device__ __forceinline__ f3 warp_sum3(f3 v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+    v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+    v.z += __shfl_xor_sync(0xffffffffu, v.z, o);
+  }
+  return v;
+}
+
+// dpos[i] += ddist * (pos_i - pos_j) / dist ; dpos[j] -= the same.  Edges are sorted by target, so a warp's 32 edges
+// mostly share the target: atomics on 3 floats per endpoint (E is small next to T).
+__global__ void edge_dist_bwd_kernel(const float* __restrict__ pos, const int32_t* __restrict__ src,
+                                     const int32_t* __restrict__ dst, const float* __restrict__ dist,
+                                     const float* __restrict__ ddist, int n_edges, float* __restrict__ dpos) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  const float d = dist[e];
+  if (d == 0.f) return;                              // norm backward at 0: zero subgradient (torch)
+  const int j = src[e], i = dst[e];
+  const f3 u = scale3(sub3(load3(pos, i), load3(pos, j)), ddist[e] / d);
+  atomic_add3(dpos, i, u);
+  atomic_add3(dpos, j, scale3(u, -1.f));
+}
+
+// One warp per (j -> i) edge, lanes over the in-neighbours k of j (same enumeration as triplet_geometry_kernel).
+// With u = pos_i - pos_j, v = pos_k - pos_j, a = u.v, w = u x v, b = |w|:  theta = atan2(b, a),
+//   dtheta/da = -b / (a^2 + b^2),  dtheta/db = a / (a^2 + b^2),  db/du = v x w_hat,  db/dv = w_hat x u.
+// The contributions to i and j are reduced over the warp (one atomic triple per edge), k gets its own atomics.
+__global__ void __launch_bounds__(256)
+triplet_angle_bwd_kernel(const float* __restrict__ pos, const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+                         const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ trip_ptr,
+                         const float* __restrict__ dangle, int n_edges, float* __restrict__ dpos) {
+  const int lane = threadIdx.x & 31;
+  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (e >= n_edges) return;
+  const int j = src[e], i = dst[e];
+  const int base = row_ptr[j], d = row_ptr[j + 1] - base;
+  int p_i = d;
+  for (int s0 = 0; s0 < d; s0 += 32) {
+    const int sl = s0 + lane;
+    const unsigned hit = __ballot_sync(0xffffffffu, sl < d && src[base + sl] == i);
+    if (hit) p_i = s0 + __ffs(hit) - 1;
+  }
+  const f3 pj = load3(pos, j);
+  const f3 u = sub3(load3(pos, i), pj);
+  const int t0 = trip_ptr[e];
+  f3 gi = {0.f, 0.f, 0.f};
+  for (int s = lane; s < d; s += 32) {
+    if (s == p_i) continue;
+    const int k = src[base + s];
+    const float g = dangle[t0 + s - (s > p_i ? 1 : 0)];
+    const f3 v = sub3(load3(pos, k), pj);
+    const float a = u.x * v.x + u.y * v.y + u.z * v.z;
+    const f3 w = cross3(u, v);
+    const float b = sqrtf(w.x * w.x + w.y * w.y + w.z * w.z);
+    const float den = a * a + b * b;
+    if (den == 0.f) continue;
+    const float ga = -b / den * g, gb = a / den * g;
+    f3 gu = scale3(v, ga), gv = scale3(u, ga);
+    if (b > 0.f) {
+      const f3 wh = scale3(w, 1.0f / b);
+      gu = add3(gu, scale3(cross3(v, wh), gb));
+      gv = add3(gv, scale3(cross3(wh, u), gb));
+    }
+    gi = add3(gi, gu);
+    atomic_add3(dpos, k, gv);
+    atomic_add3(dpos, j, scale3(add3(gu, gv), -1.f));
+  }
+  gi = warp_sum3(gi);
+  if (lane == 0) atomic_add3(dpos, i, gi);
+}
+
+// ddist[e] = sum_g dgauss[e,g] * gauss[e,g] * 2 coeff (d - mu_g)  +  dcut[e] * (-0.5 sin(d pi / c) pi / c)
+__global__ void schnet_edge_features_bwd_kernel(const float* __restrict__ dist, int64_t n_edges,
+                                                const float* __restrict__ offset, int n_gauss, float coeff,
+                                                float inv_cutoff, const float* __restrict__ dgauss,
+                                                const float* __restrict__ dcut, float* __restrict__ ddist) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  const float d = dist[e];
+  float acc = 0.f;
+  if (dgauss)
+    for (int g = 0; g < n_gauss; ++g) {
+      const float t = d - __ldg(offset + g);
+      acc = fmaf(dgauss[e * n_gauss + g], expf(coeff * t * t) * 2.0f * coeff * t, acc);
+    }
+  if (dcut) {
+    const float w = 3.14159274101257324f * inv_cutoff;
+    acc = fmaf(dcut[e], -0.5f * sinf(d * w) * w, acc);
+  }
+  ddist[e] = acc;
+}
+
+// out[r] = sum_c a[r, c] * b[r, c]   (one warp per row)
+__global__ void rowdot_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t rows, int width,
+                              float* __restrict__ out) {
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float acc = 0.f;
+  for (int c = lane; c < width; c += 32) acc = fmaf(a[r * width + c], b[r * width + c], acc);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[r] = acc;
+}
+
+}  // namespace dig3d
+
+using namespace dig3d;
+
+extern "C" {
+
+int dig3d_edge_dist_bwd(const float* pos, const int32_t* src, const int32_t* dst, const float* dist, const float* ddist,
+                        int64_t n_edges, float* dpos, void* stream) {
+  DIG3D_REQUIRE(pos && src && dst && dist && ddist && dpos, "edge_dist_bwd: null pointer");
+  if (n_edges == 0) return DIG3D_OK;
+  edge_dist_bwd_kernel<<<ceil_div(n_edges, 256), 256, 0, (cudaStream_t)stream>>>(pos, src, dst, dist, ddist,
+                                                                                (int)n_edges, dpos);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_triplet_angle_bwd(const float* pos, const int32_t* src, const int32_t* dst, const int32_t* row_ptr,
+                            const int32_t* trip_ptr, const float* dangle, int64_t n_edges, float* dpos, void* stream) {
+  DIG3D_REQUIRE(pos && src && dst && row_ptr && trip_ptr && dangle && dpos, "triplet_angle_bwd: null pointer");
+  if (n_edges == 0) return DIG3D_OK;
+  triplet_angle_bwd_kernel<<<ceil_div(n_edges * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      pos, src, dst, row_ptr, trip_ptr, dangle, (int)n_edges, dpos);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_schnet_edge_features_bwd(const float* dist, int64_t n_edges, const float* offset, int32_t n_gauss,
+                                   double coeff, double cutoff, const float* dgauss, const float* dcut, float* ddist,
+                                   void* stream) {
+  DIG3D_REQUIRE(dist && offset && ddist && n_gauss > 0 && (dgauss || dcut), "schnet_edge_features_bwd: bad arguments");
+  if (n_edges == 0) return DIG3D_OK;
+  schnet_edge_features_bwd_kernel<<<ceil_div(n_edges, 256), 256, 0, (cudaStream_t)stream>>>(
+      dist, n_edges, offset, n_gauss, (float)coeff, (float)(1.0 / cutoff), dgauss, dcut, ddist);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_rowdot(const float* a, const float* b, int64_t rows, int32_t width, float* out, void* stream) {
+  DIG3D_REQUIRE(a && b && out && width > 0, "rowdot: bad arguments");
+  if (rows == 0) return DIG3D_OK;
+  rowdot_kernel<<<ceil_div(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(a, b, rows, width, out);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+}  // extern "C"

@@ -647,3 +647,52 @@ def graphnorm_bwd(h, dy, graph_ptr, weight, mean_scale, shift, std):
     call("dig3d_graphnorm_bwd", _p(h, F32, "h"), _p(dy, F32, "dy"), _p(graph_ptr, torch.int32), g, wd, _p(weight, F32),
          _p(mean_scale, F32), _p(shift), _p(std), _p(dx), _p(dw), _p(db), _p(dms), _stream())
     return dx, dw, db, dms
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Position gradients (forces)
+def edge_dist_bwd(pos, g, ddist, dpos):
+    call("dig3d_edge_dist_bwd", _p(pos, F32, "pos"), _p(g.src), _p(g.dst), _p(g.dist), _p(ddist, F32, "ddist"), g.n_edges,
+         _p(dpos), _stream())
+
+
+def triplet_angle_bwd(pos, g, dangle, dpos):
+    call("dig3d_triplet_angle_bwd", _p(pos, F32, "pos"), _p(g.src), _p(g.dst), _p(g.row_ptr), _p(g.trip_ptr),
+         _p(dangle, F32, "dangle"), g.n_edges, _p(dpos), _stream())
+
+
+def edge_basis_bwd(dist, cutoff, envelope_exponent, freq, basis_id, envelope_on_bessel, drbf0, n_bessel,
+                   want_ddist=True, want_bess_dx=False):
+    e = dist.numel()
+    ddist = torch.zeros(e, device=dist.device, dtype=F32) if want_ddist else None
+    bdx = torch.empty(e, n_bessel, device=dist.device, dtype=F32) if want_bess_dx else None
+    call("dig3d_edge_basis_bwd", _p(dist, F32, "dist"), e, float(cutoff), int(envelope_exponent),
+         _p(freq.detach(), F32, "freq") if freq is not None else None, int(basis_id), int(bool(envelope_on_bessel)),
+         _p(drbf0, F32, "drbf0"), _p(ddist), _p(bdx), _stream())
+    return ddist, bdx
+
+
+def triplet_basis_project_bwd_geom(g, bess, bess_dx, basis_id, d_sbf_p, w_sbf1_rows, cutoff):
+    dev = bess.device
+    ddist = torch.zeros(g.n_edges, device=dev, dtype=F32)
+    dangle = torch.zeros(g.n_triplets, device=dev, dtype=F32)
+    arr = ctypes.c_void_p * 4
+    vals = [(_p(t, F32, "grad").value if t is not None else None) for t in d_sbf_p] + [None] * (4 - len(d_sbf_p))
+    call("dig3d_triplet_basis_project_bwd_geom", _p(bess, F32), _p(bess_dx, F32), _p(g.angle), _p(g.src), _p(g.dst),
+         _p(g.row_ptr), _p(g.trip_ptr), _p(g.graph_ptr), _p(g.batch, torch.int64), g.n_edges, g.n_triplets,
+         int(basis_id), arr(*vals), _p(w_sbf1_rows, F32), float(cutoff), _p(ddist), _p(dangle), _stream())
+    return ddist, dangle
+
+
+def schnet_edge_features_bwd(dist, offset, coeff, cutoff, dgauss, dcut):
+    ddist = torch.empty_like(dist)
+    call("dig3d_schnet_edge_features_bwd", _p(dist, F32, "dist"), dist.numel(), _p(offset, F32), offset.numel(),
+         float(coeff), float(cutoff), _p(dgauss, F32), _p(dcut, F32), _p(ddist), _stream())
+    return ddist
+
+
+def rowdot(a, b):
+    rows = a.size(0)
+    out = torch.empty(rows, device=a.device, dtype=F32)
+    call("dig3d_rowdot", _p(a, F32, "a"), _p(b, F32, "b"), rows, a.numel() // max(rows, 1), _p(out), _stream())
+    return out

@@ -37,7 +37,8 @@ def require_cuda(t, what):
 def wants_grad(module):
     """True when autograd is recording and the module has trainable parameters: forward() then takes the
     differentiable training path (dig_b200/autograd.py) instead of the fused inference kernels."""
-    return torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters())
+    return torch.is_grad_enabled() and (bool(getattr(module, "energy_and_force", False)) or
+                                        any(p.requires_grad for p in module.parameters()))
 
 
 class ResidualLayer(nn.Module):

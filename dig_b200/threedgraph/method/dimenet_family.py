@@ -215,10 +215,11 @@ class _DimeNetFamily(nn.Module):
         z, pos, batch = batch_data.z, batch_data.pos, batch_data.batch
         require_cuda(pos, type(self).__name__ + ".forward")
         if self.energy_and_force:
-            # Forces need d(energy)/d(pos), i.e. the backward kernels: not built yet.
-            raise NotImplementedError(
-                "energy_and_force=True needs the backward kernels, which are not implemented in this "
-                "round (forward inference only)")
+            if self._torsion:
+                raise NotImplementedError(
+                    "SphereNet energy_and_force=True: the torsion basis / torsion angle have no position-gradient "
+                    "kernels yet (DimeNetPP and SchNet do)")
+            pos.requires_grad_()                      # reference dimenetpp.py:275-276
         ns, nr = self.num_spherical, self.num_radial
         g = ops.build_graph(pos, batch, self.cutoff, num_graphs=getattr(batch_data, "num_graphs", None))
         if wants_grad(self):
@@ -277,13 +278,19 @@ class _DimeNetFamily(nn.Module):
         spherical basis carry no parameters except dist_emb.freq, so they run on the same kernels as inference."""
         ns, nr = self.num_spherical, self.num_radial
         ops.triplet_geometry(g, pos, use_torsion=self._torsion, want_idx=False)
-        rbf0, bess = ag.edge_basis(self.emb.dist_emb.freq, g.dist, self.cutoff, self.envelope_exponent,
+        if pos.requires_grad:      # forces: dist / angle carry the position gradient (csrc/train_geom.cu)
+            dist, angle = ag.geometry(pos, g, True)
+        else:
+            dist, angle = g.dist, g.angle
+        geo_cfg = (self.cutoff, self.envelope_exponent, not self._torsion, dist)
+        rbf0, bess = ag.edge_basis(self.emb.dist_emb.freq, dist, self.cutoff, self.envelope_exponent,
                                    self._basis_id, not self._torsion, nr, ns * nr)
         L = self.num_layers
         sbf_ps, t_ps = [], []
         for first in range(0, L, 4):
             es = self.update_es[first:first + 4]
-            s_l, t_l = ag.basis_project(g, bess, self._basis_id, ns, nr, [m.lin_sbf1.weight for m in es],
+            s_l, t_l = ag.basis_project(g, bess, dist, angle, geo_cfg, self._basis_id, ns, nr,
+                                        [m.lin_sbf1.weight for m in es],
                                         [m.lin_t1.weight for m in es] if self._torsion else None)
             sbf_ps += s_l
             t_ps += t_l if t_l is not None else [None] * len(s_l)

@@ -104,6 +104,11 @@ class run():
             if energy_and_force:
                 force = -grad(outputs=out, inputs=batch_data.pos, grad_outputs=torch.ones_like(out),
                               create_graph=True, retain_graph=True)[0]
+                if not force.requires_grad:
+                    raise NotImplementedError(
+                        "run.train(energy_and_force=True): the force loss needs d(force)/d(parameters), i.e. a double "
+                        "backward through the model; the dig_b200 backward kernels are first order only (forces are "
+                        "available for inference / run.val) -- training on forces would silently ignore the force term")
                 e_loss = loss_func(out, batch_data.y.unsqueeze(1))
                 f_loss = loss_func(force, batch_data.force)
                 loss = e_loss + p * f_loss

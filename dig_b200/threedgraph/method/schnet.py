@@ -80,7 +80,8 @@ class emb(nn.Module):
 class SchNet(nn.Module):
     r"""Drop-in for dig.threedgraph.method.SchNet (same constructor arguments and defaults).
     This round's kernels are compiled for hidden_channels == num_filters in {32, 64, 128} and
-    num_gaussians <= 64; energy_and_force=True raises at forward (no backward kernels yet)."""
+    num_gaussians <= 64.  energy_and_force=True: forward stays differentiable w.r.t. pos (first order: forces in
+    run.val / user code); force *training* needs a double backward and raises."""
 
     def __init__(self, energy_and_force=False, cutoff=10.0, num_layers=6, hidden_channels=128, out_channels=1,
                  num_filters=128, num_gaussians=50):
@@ -116,11 +117,11 @@ class SchNet(nn.Module):
         z, pos, batch = batch_data.z, batch_data.pos, batch_data.batch
         require_cuda(pos, "SchNet.forward")
         if self.energy_and_force:
-            raise NotImplementedError("energy_and_force=True needs the backward kernels (not in this round)")
+            pos.requires_grad_()                      # reference schnet.py:153-154
         g = ops.build_graph(pos, batch, self.cutoff, num_graphs=getattr(batch_data, "num_graphs", None),
                             want_edge_index=False)
         if wants_grad(self):
-            return self._forward_train(z, g)
+            return self._forward_train(z, pos, g)
         # v = init_v(z): an embedding row gather (torch indexing = plumbing, no arithmetic)
         v = self.init_v.weight.detach()[z].contiguous()
         keep = []
@@ -133,10 +134,12 @@ class SchNet(nn.Module):
         return ops.segment_sum(node_out, g.graph_ptr)
 
 
-    def _forward_train(self, z, g):
+    def _forward_train(self, z, pos, g):
         """Differentiable forward (reference schnet.py:149-168 op for op) over dig_b200.autograd's primitives;
         used whenever autograd is recording, i.e. by run.train."""
-        gauss, cut = ops.schnet_edge_features(g.dist, self.dist_emb.offset, self.dist_emb.coeff, self.cutoff)
+        # forces (run.py:126,165: autograd.grad(out, pos)): dist carries the position gradient
+        dist = ag.geometry(pos, g, False) if pos.requires_grad else g.dist
+        gauss, cut = ag.schnet_edge_features(dist, self.dist_emb.offset, self.dist_emb.coeff, self.cutoff)
         v = ag.gather_rows(self.init_v.weight, z)
         for ue, uv in zip(self.update_es, self.update_vs):
             # update_e (schnet.py:29-35): W = mlp(dist_emb) * C ; e = lin(v)[j] * W

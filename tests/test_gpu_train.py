@@ -266,3 +266,70 @@ def test_comenet_train_step_moves_every_parameter():
     loss = run().train(model, opt, DataLoader(mols, 2, shuffle=False), False, 100, torch.nn.L1Loss(), dev)
     assert np.isfinite(loss)
     assert all(bool((v.detach() != before[k]).any()) for k, v in model.named_parameters())
+
+
+# ------------------------------------------------------------------------------------------------ forces
+FTOL = 1e-5      # north_star: forces within 1e-5 (relative to the largest force component)
+
+
+@pytest.mark.parametrize("name", ["schnet_cfg1", "dimenetpp_md17"])
+def test_forces_match_reference(name):
+    """forces = -dE/dpos through the geometry / basis backward kernels vs (a) the real reference's fp32 and fp64
+    forces (golden fixture) and (b) torch.autograd over the oracle restatement on the same GPU."""
+    from dig_b200.threedgraph import method
+    from helpers import CASES
+    from oracle import restated
+    dev = torch.device("cuda:0")
+    model_name, ctor, _, wseed = CASES[name]
+    gold, z, pos, batch = case_inputs(name, dev)
+    model = getattr(method, model_name)(energy_and_force=True, **ctor)
+    sd = formula_state_dict(model.state_dict(), seed=wseed)
+    model.load_state_dict(sd)
+    model = model.to(dev)
+    b = _batch(z, pos.clone(), batch)
+    out = model(b)
+    assert b.pos.requires_grad
+    force = -torch.autograd.grad(out, b.pos, grad_outputs=torch.ones_like(out), create_graph=True, retain_graph=True)[0]
+    force = force.detach()
+    assert rel_err(out.detach().cpu().numpy(), gold["energy_f32"]) < 1e-5
+    assert rel_err(force.cpu().numpy(), gold["force_f64"]) < FTOL
+    assert rel_err(force.cpu().numpy(), gold["force_f32"]) < FTOL
+    pos2 = pos.clone().requires_grad_(True)
+    sd_dev = {k: v.to(dev) for k, v in sd.items()}
+    kw = {k: v for k, v in ctor.items() if k in ("cutoff", "num_layers")}
+    fwd = restated.schnet_forward if model_name == "SchNet" else restated.dimenetpp_forward
+    ref = fwd(sd_dev, z, pos2, batch, **kw)
+    f_ref = -torch.autograd.grad(ref.sum(), pos2)[0]
+    assert rel_err(force.cpu().numpy(), f_ref.cpu().numpy()) < FTOL
+
+
+def test_force_path_parameter_gradients_still_match():
+    """energy_and_force=True changes the graph (dist / angle become functions of pos); parameter gradients must not move."""
+    from dig_b200.threedgraph.method import DimeNetPP
+    from oracle import restated
+    dev = torch.device("cuda:0")
+    _, z, pos, batch = case_inputs("dimenetpp_md17", dev)
+    model = DimeNetPP(energy_and_force=True, cutoff=5.0)
+    sd = formula_state_dict(model.state_dict(), seed=3)
+    model.load_state_dict(sd)
+    model = model.to(dev)
+    sd = {k: v.to(dev) for k, v in sd.items()}
+    target = torch.linspace(-1, 1, 4, device=dev).view(4, 1)
+    _grad_compare(model, sd, lambda s, *a: restated.dimenetpp_forward(s, *a, cutoff=5.0), z, pos.clone(), batch, target)
+
+
+def test_run_val_energy_and_force_and_force_training_raises():
+    from dig_b200.data import DataLoader, synthetic_molecules
+    from dig_b200.threedgraph.evaluation import ThreeDEvaluator
+    from dig_b200.threedgraph.method import SchNet, SphereNet, run
+    dev = torch.device("cuda:0")
+    mols = synthetic_molecules(8, "md17-aspirin", seed=3)
+    model = SchNet(energy_and_force=True, num_layers=2, hidden_channels=32, num_filters=32, cutoff=5.0).to(dev)
+    mae = run().val(model, DataLoader(mols, 4, shuffle=False), True, 100, ThreeDEvaluator(), dev)
+    assert np.isfinite(mae)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    with pytest.raises(NotImplementedError, match="double"):
+        run().train(model, opt, DataLoader(mols, 4, shuffle=False), True, 100, torch.nn.L1Loss(), dev)
+    with pytest.raises(NotImplementedError):
+        SphereNet(energy_and_force=True).to(dev)(_batch(mols[0].z.to(dev), mols[0].pos.to(dev),
+                                                        torch.zeros(21, dtype=torch.long, device=dev)))
