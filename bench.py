@@ -157,6 +157,73 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def other_configs(dev):
+    """BASELINE.json configs[0], [2], [3] (parity-test cases, not the headline): short CUDA-event timings of the
+    inference forward, the energy+force forward where the config asks for forces, and one training step, so that every
+    configured mode has a measured number.  Errors are reported in the JSON, not swallowed."""
+    import torch
+    from dig_b200.data import synthetic_batch
+    from dig_b200.threedgraph.method import ComENet, DimeNetPP, SchNet
+
+    def time_ms(fn, n=10, warm=3):
+        for _ in range(warm):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    cases = [("cfg1 SchNet 2-layer h=32, 16 x 12 atoms, cutoff 10",
+              lambda f: SchNet(energy_and_force=f, num_layers=2, hidden_channels=32, num_filters=32, cutoff=10.0),
+              dict(nmol=16, shape="schnet-plumbing", seed=0), True),
+             ("cfg3 DimeNet++ 4-block h=128, MD17-aspirin-shape batch=256, energy+force",
+              lambda f: DimeNetPP(energy_and_force=f, cutoff=5.0), dict(nmol=256, shape="md17-aspirin", seed=3), True),
+             ("cfg4 ComENet 4-layer h=256, OC20-IS2RE-shape batch=64, cutoff 6.0",
+              lambda f: ComENet(cutoff=6.0), dict(nmol=64, shape="oc20-is2re", seed=4), False)]
+    out = []
+    for name, make, data_kw, forces in cases:
+        rec = {"config": name}
+        try:
+            torch.manual_seed(7)
+            b = synthetic_batch(**data_kw).to(dev)
+            nmol = data_kw["nmol"]
+            model = make(False).to(dev)
+
+            def infer():
+                with torch.no_grad():
+                    return model(b)
+            ms = time_ms(infer)
+            rec["inference"] = {"ms_per_step": ms, "molecules_per_s": nmol / (ms * 1e-3)}
+            y = torch.randn(nmol, 1, device=dev)
+            opt = torch.optim.Adam(model.parameters(), lr=5e-4)
+
+            def train():
+                opt.zero_grad()
+                torch.nn.functional.l1_loss(model(b), y).backward()
+                opt.step()
+            ms = time_ms(train, n=5)
+            rec["train_step"] = {"ms_per_step": ms, "molecules_per_s": nmol / (ms * 1e-3)}
+            if forces:
+                fmodel = make(True).to(dev)
+                fmodel.load_state_dict(model.state_dict())
+
+                def ef():
+                    b.pos.grad = None
+                    o = fmodel(b)
+                    return torch.autograd.grad(o, b.pos, grad_outputs=torch.ones_like(o))[0]
+                ms = time_ms(ef, n=5)
+                rec["energy_and_force"] = {"ms_per_step": ms, "molecules_per_s": nmol / (ms * 1e-3)}
+                b.pos.requires_grad_(False)
+        except Exception as exc:                      # reported, never hidden
+            rec["error"] = f"{type(exc).__name__}: {exc}"
+        out.append(rec)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -390,6 +457,8 @@ def main():
                                    "what": "torch.autograd over the reference op sequence + Adam on the same B200"}
         del sd_t, ropt
 
+    others = other_configs(dev) if world == 1 else None
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         rate, dt, iters, threads = cpu_oracle_rate(32)
@@ -411,7 +480,7 @@ def main():
                     "ms_per_step": wall_e2e / args.steps, "timing": "host wall clock incl. per-step stream sync"},
             "gpu_launches": launches, "wall_ms_per_step": wall_ms / args.steps,
             "clocks": sampler.summary(), "roofline": roof, "scatter_roofline": scatter, "cpu_baseline": cpu,
-            "gpu_comparator": gpu_cmp, "train": train}
+            "gpu_comparator": gpu_cmp, "train": train, "other_configs": others}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

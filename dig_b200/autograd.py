@@ -220,7 +220,7 @@ class _BasisProject(torch.autograd.Function):
     force path, d/d(dist_kj) and d/d(angle) of the sbf branch (the torsion branch has no geometry backward yet)."""
 
     @staticmethod
-    def forward(ctx, g, bess, dist, angle, geo_cfg, basis_id, ns, nr, n_layers, torsion, *weights):
+    def forward(ctx, g, bess, dist, angle, tors_angle, geo_cfg, basis_id, ns, nr, n_layers, torsion, *weights):
         def rows(ws):
             w = torch.cat([w_.detach() for w_ in ws], 0)
             if w.size(0) < 32:
@@ -230,7 +230,7 @@ class _BasisProject(torch.autograd.Function):
         w_t = rows(weights[n_layers:]) if torsion else None
         sbf_p, t_p = ops.triplet_basis_project(g, bess, basis_id, w_s, w_t)
         ctx.g, ctx.cfg, ctx.geo_cfg = g, (basis_id, ns, nr, n_layers, torsion), geo_cfg
-        ctx.save_for_backward(bess, w_s)
+        ctx.save_for_backward(bess, w_s, w_t)
         ctx.set_materialize_grads(False)
         outs = [sbf_p[l] for l in range(n_layers)]
         if torsion:
@@ -240,27 +240,25 @@ class _BasisProject(torch.autograd.Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, *grads):
-        bess, w_s = ctx.saved_tensors
+        bess, w_s, w_t = ctx.saved_tensors
         basis_id, ns, nr, n_layers, torsion = ctx.cfg
         g = ctx.g
         d_s = [None if d is None else _c(d) for d in grads[:n_layers]]
         d_t = [None if d is None else _c(d) for d in grads[n_layers:]] if torsion else None
         out = [None] * len(grads)
-        if any(ctx.needs_input_grad[10:]):
+        if any(ctx.needs_input_grad[11:]):
             dws, dwt = ops.triplet_basis_project_bwd(g, bess, basis_id, d_s, d_t, ns * nr, ns * ns * nr)
             out = [None if grads[l] is None else dws[8 * l:8 * l + 8] for l in range(n_layers)]
             if torsion:
                 out += [None if grads[n_layers + l] is None else dwt[8 * l:8 * l + 8] for l in range(n_layers)]
-        ddist = dangle = None
-        if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
-            if torsion:
-                raise NotImplementedError("forces through the torsion basis (SphereNet, energy_and_force=True) are not "
-                                          "implemented: no backward kernel for torsion_emb / the torsion angle")
+        ddist = dangle = dtors = None
+        if ctx.needs_input_grad[2] or ctx.needs_input_grad[3] or ctx.needs_input_grad[4]:
             cutoff, exponent, env_on_bessel, dist = ctx.geo_cfg
             _, bess_dx = ops.edge_basis_bwd(dist.detach(), cutoff, exponent, None, basis_id, env_on_bessel, None, ns * nr,
                                             want_ddist=False, want_bess_dx=True)
-            ddist, dangle = ops.triplet_basis_project_bwd_geom(g, bess, bess_dx, basis_id, d_s, w_s, cutoff)
-        return (None, None, ddist, dangle) + (None,) * 6 + tuple(out)
+            ddist, dangle, dtors = ops.triplet_basis_project_bwd_geom(g, bess, bess_dx, basis_id, d_s, d_t, w_s, w_t,
+                                                                      cutoff)
+        return (None, None, ddist, dangle, dtors) + (None,) * 6 + tuple(out)
 
 
 class _TripletGather(torch.autograd.Function):
@@ -293,13 +291,14 @@ def edge_basis(freq, dist, cutoff, exponent, basis_id, env_on_bessel, nr, n_bess
     return _EdgeBasis.apply(freq, dist, cutoff, exponent, basis_id, env_on_bessel, nr, n_bessel)
 
 
-def basis_project(g, bess, dist, angle, geo_cfg, basis_id, ns, nr, sbf1_weights, t1_weights):
+def basis_project(g, bess, dist, angle, tors_angle, geo_cfg, basis_id, ns, nr, sbf1_weights, t1_weights):
     """-> (list of sbf_p[l] [T, 8], list of t_p[l] [T, 8] or None) for len(sbf1_weights) <= 4 layers.
-    dist / angle: the (possibly position-dependent) geometry tensors, only used to route gradients;
+    dist / angle / tors_angle (None for DimeNet++): the (possibly position-dependent) geometry tensors, only used to
+    route gradients;
     geo_cfg = (cutoff, envelope_exponent, envelope_on_bessel, dist)."""
     n = len(sbf1_weights)
     torsion = t1_weights is not None
-    outs = _BasisProject.apply(g, bess, dist, angle, geo_cfg, basis_id, ns, nr, n, torsion, *sbf1_weights,
+    outs = _BasisProject.apply(g, bess, dist, angle, tors_angle, geo_cfg, basis_id, ns, nr, n, torsion, *sbf1_weights,
                                *(t1_weights or []))
     return list(outs[:n]), (list(outs[n:]) if torsion else None)
 
@@ -326,21 +325,24 @@ def graphnorm(h, module, graph_ptr):
 
 
 class _Geometry(torch.autograd.Function):
-    """dist[E] (and angle[T]) as differentiable functions of pos: values are the ones the graph kernels computed
-    (bit-exact with inference), backward scatters d/d(pos) (csrc/train_geom.cu)."""
+    """dist[E] (and angle[T], torsion[T]) as differentiable functions of pos: values are the ones the graph kernels
+    computed (bit-exact with inference), backward scatters d/d(pos) (csrc/train_geom.cu)."""
 
     @staticmethod
-    def forward(ctx, pos, g, want_angle):
+    def forward(ctx, pos, g, n_out):
         ctx.g = g
         ctx.save_for_backward(pos)
-        dist = g.dist.detach().view(-1)
-        if want_angle:
-            return dist, g.angle.detach().view(-1)
-        return dist
+        ctx.set_materialize_grads(False)
+        outs = [g.dist.detach().view(-1)]
+        if n_out >= 2:
+            outs.append(g.angle.detach().view(-1))
+        if n_out >= 3:
+            outs.append(g.torsion.detach().view(-1))
+        return outs[0] if n_out == 1 else tuple(outs)
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, ddist, dangle=None):
+    def backward(ctx, ddist, dangle=None, dtorsion=None):
         (pos,) = ctx.saved_tensors
         g = ctx.g
         dpos = torch.zeros_like(pos)
@@ -349,6 +351,8 @@ class _Geometry(torch.autograd.Function):
             ops.edge_dist_bwd(p, g, _c(ddist), dpos)
         if dangle is not None:
             ops.triplet_angle_bwd(p, g, _c(dangle), dpos)
+        if dtorsion is not None:
+            ops.triplet_torsion_bwd(p, g, _c(dtorsion), dpos)
         return dpos, None, None
 
 
@@ -370,8 +374,9 @@ class _SchnetEdgeFeatures(torch.autograd.Function):
         return ops.schnet_edge_features_bwd(dist.detach(), offset, ctx.cfg[0], ctx.cfg[1], dg, dc), None, None, None
 
 
-def geometry(pos, g, want_angle):
-    return _Geometry.apply(pos, g, want_angle)
+def geometry(pos, g, n_out):
+    """n_out = 1: dist; 2: (dist, angle); 3: (dist, angle, torsion)."""
+    return _Geometry.apply(pos, g, n_out)
 
 
 def schnet_edge_features(dist, offset, coeff, cutoff):

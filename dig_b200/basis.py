@@ -239,7 +239,7 @@ def basis_sources(flavor, num_spherical, num_radial):
         yall = harmonics_gemnet(num_spherical, zero_m_only=False)
     else:
         raise ValueError(flavor)
-    out = {"bessel": [], "yl0": [], "ylm": [], "bessel_dx": [], "yl0_dtheta": []}
+    out = {"bessel": [], "yl0": [], "ylm": [], "bessel_dx": [], "yl0_dtheta": [], "ylm_dtheta": [], "ylm_dphi": []}
     for l in range(num_spherical):
         for n in range(num_radial):
             out["bessel"].append(_src(bess[l][n], [x]))
@@ -255,9 +255,15 @@ def basis_sources(flavor, num_spherical, num_radial):
     for l in range(num_spherical):
         if l == 0:
             out["ylm"].append(repr(float(sym.lambdify([theta, phi], yall[0][0])(0, 0))))
+            out["ylm_dtheta"].append("0.0")
+            out["ylm_dphi"].append("0.0")
         else:
             for k in range(2 * l + 1):
                 out["ylm"].append(_src(yall[l][k], [theta, phi]))
+                # force path (not reference strings): partial derivatives of the same closed forms
+                dth, dph = sym.diff(yall[l][k], theta), sym.diff(yall[l][k], phi)
+                out["ylm_dtheta"].append("0.0" if dth == 0 else _src(dth, [theta, phi]))
+                out["ylm_dphi"].append("0.0" if dph == 0 else _src(dph, [theta, phi]))
     return out
 
 

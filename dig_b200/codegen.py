@@ -164,6 +164,8 @@ def emit_header(tag, flavor, num_spherical, num_radial, sources):
         emit_function("bessel_dx", ["x"], sources["bessel_dx"],
                       "d/dx of bessel() (symbolic derivative of the same closed forms; force path)"),
         emit_function("yl0_dtheta", ["theta"], sources["yl0_dtheta"], "d/dtheta of yl0() (force path)"),
+        emit_function("ylm_dtheta", ["theta", "phi"], sources["ylm_dtheta"], "d/dtheta of ylm() (force path)"),
+        emit_function("ylm_dphi", ["theta", "phi"], sources["ylm_dphi"], "d/dphi of ylm() (force path)"),
         "}  // namespace\n",
     ]
     return "\n".join(parts)

@@ -24,6 +24,8 @@ struct B76 {
   __device__ static void ylm(float t, float p, float (&o)[NY]) { basis_dimenet_7_6::ylm(t, p, o); }
   __device__ static void bessel_dx(float x, float (&o)[NB]) { basis_dimenet_7_6::bessel_dx(x, o); }
   __device__ static void yl0_dtheta(float t, float (&o)[NS]) { basis_dimenet_7_6::yl0_dtheta(t, o); }
+  __device__ static void ylm_dtheta(float t, float p, float (&o)[NY]) { basis_dimenet_7_6::ylm_dtheta(t, p, o); }
+  __device__ static void ylm_dphi(float t, float p, float (&o)[NY]) { basis_dimenet_7_6::ylm_dphi(t, p, o); }
 };
 struct B36 {
   static constexpr int NS = basis_dimenet_3_6::NS, NR = basis_dimenet_3_6::NR;
@@ -33,6 +35,8 @@ struct B36 {
   __device__ static void ylm(float t, float p, float (&o)[NY]) { basis_dimenet_3_6::ylm(t, p, o); }
   __device__ static void bessel_dx(float x, float (&o)[NB]) { basis_dimenet_3_6::bessel_dx(x, o); }
   __device__ static void yl0_dtheta(float t, float (&o)[NS]) { basis_dimenet_3_6::yl0_dtheta(t, o); }
+  __device__ static void ylm_dtheta(float t, float p, float (&o)[NY]) { basis_dimenet_3_6::ylm_dtheta(t, p, o); }
+  __device__ static void ylm_dphi(float t, float p, float (&o)[NY]) { basis_dimenet_3_6::ylm_dphi(t, p, o); }
 };
 struct G23 {
   static constexpr int NS = basis_gemnet_2_3::NS, NR = basis_gemnet_2_3::NR;
@@ -42,6 +46,8 @@ struct G23 {
   __device__ static void ylm(float t, float p, float (&o)[NY]) { basis_gemnet_2_3::ylm(t, p, o); }
   __device__ static void bessel_dx(float x, float (&o)[NB]) { basis_gemnet_2_3::bessel_dx(x, o); }
   __device__ static void yl0_dtheta(float t, float (&o)[NS]) { basis_gemnet_2_3::yl0_dtheta(t, o); }
+  __device__ static void ylm_dtheta(float t, float p, float (&o)[NY]) { basis_gemnet_2_3::ylm_dtheta(t, p, o); }
+  __device__ static void ylm_dphi(float t, float p, float (&o)[NY]) { basis_gemnet_2_3::ylm_dphi(t, p, o); }
 };
 
 // Envelope.forward (features.py:159-164), ATen-CUDA op order:
@@ -279,7 +285,7 @@ triplet_basis_project_kernel(const float* __restrict__ bess, const float* __rest
 // shared memory); the inner sum G[ab] stays in registers, the outer product with the edge's Bessel values goes into a
 // per-CTA shared-memory accumulator (shared atomics, lane-distinct banks) that is flushed once per CTA.  The [T, 294]
 // basis is never materialised.
-struct PrjGradPtrs { const float* ds[4]; const float* dt[4]; };
+struct PrjGradPtrs { const float* ds[4]; const float* dt[4]; };   // passed by value as a kernel argument
 
 template <class BS, bool TORSION>
 struct PrjBwdSmem {
@@ -445,39 +451,80 @@ __global__ void edge_basis_bwd_kernel(const float* __restrict__ dist, int n_edge
   }
 }
 
-// Backward of the fused projection w.r.t. the geometry (DimeNet++ / SphereNet without the torsion branch):
-//   dangle[t]  = sum_q d sbf_p[q][t] * sum_l Y_l0'(angle_t) * Rs[q][l],      Rs[q][l]  = sum_r bess[kj][l,r]  w_sbf1[q][l,r]
-//   ddist[kj] += sum_{t uses kj} sum_q d sbf_p[q][t] * sum_l Y_l0(angle_t) * Rsd[q][l] / cutoff,   Rsd from bess_dx
-// One warp per (k->j) edge, lane = q = layer*8 + row; every triplet is visited exactly once (by its kj edge).
-template <class BS>
+// Backward of the fused projection w.r.t. the geometry (forces):
+//   sbf_p[q][t] = sum_l  Y_l0(angle_t)            Rs[q][l],   Rs[q][l]  = sum_r bess[kj][l,r]  w_sbf1[q][l,r]
+//   t_p[q][t]   = sum_ab Y_ab(angle_t, torsion_t) R[q][ab],   R[q][ab]  = sum_r bess[kj][b,r]  w_t1[q][ab,r]
+// => dangle[t]   = sum_l Y_l0' Hs[l] + sum_ab dY_ab/dtheta H[ab],   Hs[l] = sum_q d sbf_p[q][t] Rs[q][l],  H[ab] = sum_q d t_p[q][t] R[q][ab]
+//    dtorsion[t] = sum_ab dY_ab/dphi H[ab]
+//    ddist[kj]   = (1/cutoff) sum_{t uses kj} ( sum_l Y_l0 Hsd[l] + sum_ab Y_ab Hd[ab] ),  Hsd / Hd from d(bess)/dx.
+// One warp per (k->j) edge: first lane = q builds the four per-edge matrices in shared memory, then lane = TRIPLET
+// (the candidate enumeration of the forward kernel already yields one triplet per lane) contracts them with its 32
+// upstream gradients; the harmonics and their derivatives are evaluated in registers, nothing per-triplet is staged.
+constexpr int PRJG_WARPS = 4;
+
+template <class BS, bool TORSION>
 struct PrjGeomSmem {
+  static constexpr int NYT = TORSION ? BS::NY : 1;
+  float wt[TORSION ? BS::NY * BS::NR * PRJ_LD : 1];
   float ws[BS::NB * PRJ_LD];
-  float bess[PRJ_WARPS][BS::NB];
-  float bessd[PRJ_WARPS][BS::NB];
-  static constexpr int YLD = ((2 * BS::NS + 3) / 4) * 4;
-  alignas(16) float y[PRJ_WARPS][32][YLD];
-  int32_t trip[PRJ_WARPS][32];
+  float bess[PRJG_WARPS][BS::NB];
+  float bessd[PRJG_WARPS][BS::NB];
+  alignas(16) float R[PRJG_WARPS][NYT][32];
+  alignas(16) float Rd[PRJG_WARPS][NYT][32];
+  alignas(16) float Rs[PRJG_WARPS][BS::NS][32];
+  alignas(16) float Rsd[PRJG_WARPS][BS::NS][32];
 };
 
-template <class BS>
-__global__ void __launch_bounds__(PRJ_WARPS * 32)
+__device__ __forceinline__ void dot32(const float (&d)[32], const float* __restrict__ row, const float* __restrict__ rowd,
+                                      float& h, float& hd) {
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+  for (int q = 0; q < 32; q += 4) {
+    const float4 r = *reinterpret_cast<const float4*>(row + q);
+    const float4 rd = *reinterpret_cast<const float4*>(rowd + q);
+    a0 = fmaf(d[q], r.x, a0); a0 = fmaf(d[q + 1], r.y, a0); a0 = fmaf(d[q + 2], r.z, a0); a0 = fmaf(d[q + 3], r.w, a0);
+    a1 = fmaf(d[q], rd.x, a1); a1 = fmaf(d[q + 1], rd.y, a1); a1 = fmaf(d[q + 2], rd.z, a1); a1 = fmaf(d[q + 3], rd.w, a1);
+  }
+  h = a0;
+  hd = a1;
+}
+
+__device__ __forceinline__ void load_grad32(const float* const (&ptr)[4], int t, float (&d)[32]) {
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    if (ptr[l]) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(ptr[l] + (size_t)t * 8));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(ptr[l] + (size_t)t * 8 + 4));
+      d[l * 8] = a.x; d[l * 8 + 1] = a.y; d[l * 8 + 2] = a.z; d[l * 8 + 3] = a.w;
+      d[l * 8 + 4] = b.x; d[l * 8 + 5] = b.y; d[l * 8 + 6] = b.z; d[l * 8 + 7] = b.w;
+    } else {
+#pragma unroll
+      for (int m = 0; m < 8; ++m) d[l * 8 + m] = 0.f;
+    }
+  }
+}
+
+template <class BS, bool TORSION>
+__global__ void __launch_bounds__(PRJG_WARPS * 32)
 triplet_basis_project_bwd_geom_kernel(const float* __restrict__ bess, const float* __restrict__ bess_dx,
-                                      const float* __restrict__ angle, const int32_t* __restrict__ src,
-                                      const int32_t* __restrict__ dst, const int32_t* __restrict__ row_ptr,
-                                      const int32_t* __restrict__ trip_ptr, const int32_t* __restrict__ graph_ptr,
-                                      const int64_t* __restrict__ batch, int n_edges, PrjGradPtrs gp,
-                                      const float* __restrict__ w_sbf1, float inv_cutoff, float* __restrict__ ddist,
-                                      float* __restrict__ dangle) {
-  constexpr int NS = BS::NS, NR = BS::NR, NB = BS::NB;
-  using SM = PrjGeomSmem<BS>;
+                                      const float* __restrict__ angle, const float* __restrict__ torsion,
+                                      const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+                                      const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ trip_ptr,
+                                      const int32_t* __restrict__ graph_ptr, const int64_t* __restrict__ batch,
+                                      int n_edges, PrjGradPtrs gp, const float* __restrict__ w_sbf1,
+                                      const float* __restrict__ w_t1, float inv_cutoff, float* __restrict__ ddist,
+                                      float* __restrict__ dangle, float* __restrict__ dtorsion) {
+  constexpr int NS = BS::NS, NR = BS::NR, NB = BS::NB, NY = BS::NY;
+  using SM = PrjGeomSmem<BS, TORSION>;
   extern __shared__ __align__(16) unsigned char prj_smem_raw[];
   SM& sm = *reinterpret_cast<SM*>(prj_smem_raw);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int id = threadIdx.x; id < 32 * NB; id += PRJ_WARPS * 32) sm.ws[(id % NB) * PRJ_LD + id / NB] = __ldg(w_sbf1 + id);
+  if (TORSION)
+    for (int id = threadIdx.x; id < 32 * NY * NR; id += PRJG_WARPS * 32)
+      sm.wt[(id % (NY * NR)) * PRJ_LD + id / (NY * NR)] = __ldg(w_t1 + id);
+  for (int id = threadIdx.x; id < 32 * NB; id += PRJG_WARPS * 32) sm.ws[(id % NB) * PRJ_LD + id / NB] = __ldg(w_sbf1 + id);
   __syncthreads();
-  const float* my_ds = gp.ds[lane >> 3];
-  const int mrow = lane & 7;
-  for (int kj = blockIdx.x * PRJ_WARPS + w; kj < n_edges; kj += gridDim.x * PRJ_WARPS) {
+  for (int kj = blockIdx.x * PRJG_WARPS + w; kj < n_edges; kj += gridDim.x * PRJG_WARPS) {
     const int k = src[kj], j = dst[kj];
     __syncwarp();
     for (int c = lane; c < NB; c += 32) {
@@ -485,19 +532,38 @@ triplet_basis_project_bwd_geom_kernel(const float* __restrict__ bess, const floa
       sm.bessd[w][c] = __ldg(bess_dx + (size_t)kj * NB + c);
     }
     __syncwarp();
-    float Rs[NS], Rsd[NS];
+    // lane = q: per-edge radial contractions (values and x-derivatives)
 #pragma unroll
     for (int b = 0; b < NS; ++b) {
+      float rb[NR], rbd[NR];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) { rb[r] = sm.bess[w][b * NR + r]; rbd[r] = sm.bessd[w][b * NR + r]; }
       float a0 = 0.f, a1 = 0.f;
 #pragma unroll
       for (int r = 0; r < NR; ++r) {
         const float wv = sm.ws[(b * NR + r) * PRJ_LD + lane];
-        a0 = fmaf(sm.bess[w][b * NR + r], wv, a0);
-        a1 = fmaf(sm.bessd[w][b * NR + r], wv, a1);
+        a0 = fmaf(rb[r], wv, a0);
+        a1 = fmaf(rbd[r], wv, a1);
       }
-      Rs[b] = a0;
-      Rsd[b] = a1;
+      sm.Rs[w][b][lane] = a0;
+      sm.Rsd[w][b][lane] = a1;
+      if (TORSION) {
+#pragma unroll
+        for (int a = 0; a < NS; ++a) {
+          const int ab = a * NS + b;
+          float c0 = 0.f, c1 = 0.f;
+#pragma unroll
+          for (int r = 0; r < NR; ++r) {
+            const float wv = sm.wt[(ab * NR + r) * PRJ_LD + lane];
+            c0 = fmaf(rb[r], wv, c0);
+            c1 = fmaf(rbd[r], wv, c1);
+          }
+          sm.R[w][ab][lane] = c0;
+          sm.Rd[w][ab][lane] = c1;
+        }
+      }
     }
+    __syncwarp();
     float acc_x = 0.f;
     const int jbase = row_ptr[j], dj = row_ptr[j + 1] - jbase;
     const int rank_k = kj - jbase;
@@ -518,36 +584,53 @@ triplet_basis_project_bwd_geom_kernel(const float* __restrict__ bess, const floa
           t = trip_ptr[e] + rank_k - ((i_in && a2 < rank_k) ? 1 : 0);
         }
       }
-      const unsigned m = __ballot_sync(0xffffffffu, t >= 0);
-      if (t >= 0) {
-        const int slot = __popc(m & ((1u << lane) - 1));
-        sm.trip[w][slot] = t;
-        const float th = angle[t];
-        float y0[NS], yd[NS];
+      if (t < 0) continue;                                  // lanes are independent from here on
+      const float th = angle[t];
+      float d[32];
+      float dth = 0.f, dph = 0.f, dx = 0.f;
+      {
+        load_grad32(gp.ds, t, d);
+        float y0[NS], y0d[NS];
         BS::yl0(th, y0);
-        BS::yl0_dtheta(th, yd);
-#pragma unroll
-        for (int l = 0; l < NS; ++l) { sm.y[w][slot][l] = y0[l]; sm.y[w][slot][NS + l] = yd[l]; }
-      }
-      __syncwarp();
-      const int cnt = __popc(m);
-      for (int s = 0; s < cnt; ++s) {
-        const int tt = sm.trip[w][s];
-        const float d_q = my_ds ? __ldg(my_ds + (size_t)tt * 8 + mrow) : 0.f;
-        float sy = 0.f, sd = 0.f;
+        BS::yl0_dtheta(th, y0d);
 #pragma unroll
         for (int l = 0; l < NS; ++l) {
-          sy = fmaf(sm.y[w][s][l], Rsd[l], sy);
-          sd = fmaf(sm.y[w][s][NS + l], Rs[l], sd);
+          float h, hd;
+          dot32(d, sm.Rs[w][l], sm.Rsd[w][l], h, hd);
+          dth = fmaf(y0d[l], h, dth);
+          dx = fmaf(y0[l], hd, dx);
         }
-        acc_x = fmaf(d_q, sy, acc_x);
-        float va = d_q * sd;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) va += __shfl_xor_sync(0xffffffffu, va, o);
-        if (lane == 0) dangle[tt] = va;
       }
-      __syncwarp();
+      if (TORSION) {
+        const float ph = torsion[t];
+        load_grad32(gp.dt, t, d);
+        float H[NY], Hd[NY];
+#pragma unroll
+        for (int ab = 0; ab < NY; ++ab) dot32(d, sm.R[w][ab], sm.Rd[w][ab], H[ab], Hd[ab]);
+        {
+          float y[NY];
+          BS::ylm(th, ph, y);
+#pragma unroll
+          for (int ab = 0; ab < NY; ++ab) dx = fmaf(y[ab], Hd[ab], dx);
+        }
+        {
+          float y[NY];
+          BS::ylm_dtheta(th, ph, y);
+#pragma unroll
+          for (int ab = 0; ab < NY; ++ab) dth = fmaf(y[ab], H[ab], dth);
+        }
+        {
+          float y[NY];
+          BS::ylm_dphi(th, ph, y);
+#pragma unroll
+          for (int ab = 0; ab < NY; ++ab) dph = fmaf(y[ab], H[ab], dph);
+        }
+        dtorsion[t] = dph;
+      }
+      dangle[t] = dth;
+      acc_x += dx;
     }
+    __syncwarp();
 #pragma unroll
     for (int o = 16; o; o >>= 1) acc_x += __shfl_xor_sync(0xffffffffu, acc_x, o);
     if (lane == 0) ddist[kj] = acc_x * inv_cutoff;
@@ -724,39 +807,47 @@ int dig3d_edge_basis_bwd(const float* dist, int64_t n_edges, double cutoff, int3
   return DIG3D_OK;
 }
 
-int dig3d_triplet_basis_project_bwd_geom(const float* bess, const float* bess_dx, const float* angle, const int32_t* src,
-                                         const int32_t* dst, const int32_t* row_ptr, const int32_t* trip_ptr,
-                                         const int32_t* graph_ptr, const int64_t* batch, int64_t n_edges,
-                                         int64_t n_triplets, int32_t basis_id, const float* const* d_sbf_p,
-                                         const float* w_sbf1, double cutoff, float* ddist, float* dangle, void* stream) {
+int dig3d_triplet_basis_project_bwd_geom(const float* bess, const float* bess_dx, const float* angle,
+                                         const float* torsion, const int32_t* src, const int32_t* dst,
+                                         const int32_t* row_ptr, const int32_t* trip_ptr, const int32_t* graph_ptr,
+                                         const int64_t* batch, int64_t n_edges, int64_t n_triplets, int32_t basis_id,
+                                         const float* const* d_sbf_p, const float* const* d_t_p, const float* w_sbf1,
+                                         const float* w_t1, double cutoff, float* ddist, float* dangle, float* dtorsion,
+                                         void* stream) {
   DIG3D_REQUIRE(bess && bess_dx && angle && src && dst && row_ptr && trip_ptr && graph_ptr && batch && d_sbf_p &&
                     w_sbf1 && ddist && dangle, "triplet_basis_project_bwd_geom: null pointer");
+  const bool tors = (dtorsion != nullptr);
+  DIG3D_REQUIRE(!tors || (torsion && d_t_p && w_t1), "triplet_basis_project_bwd_geom: torsion path needs torsion, d_t_p, w_t1");
   if (n_edges == 0) return DIG3D_OK;
   PrjGradPtrs gp;
-  for (int l = 0; l < 4; ++l) { gp.ds[l] = d_sbf_p[l]; gp.dt[l] = nullptr; }
+  for (int l = 0; l < 4; ++l) { gp.ds[l] = d_sbf_p[l]; gp.dt[l] = tors ? d_t_p[l] : nullptr; }
   cudaStream_t st = (cudaStream_t)stream;
   int dev = 0, n_sm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  const int64_t want = (n_edges + PRJ_WARPS - 1) / PRJ_WARPS;
-  const int grid = (int)(want < 2 * n_sm ? want : 2 * n_sm);
+  const int64_t want = (n_edges + PRJG_WARPS - 1) / PRJG_WARPS;
+  const int grid = (int)(want < 4 * n_sm ? want : 4 * n_sm);
   const float inv = 1.0f / (float)cutoff;
-#define DIG3D_PRJG(BS)                                                                                      \
+#define DIG3D_PRJG_ONE(BS, TORS)                                                                            \
   {                                                                                                         \
-    auto kfn = triplet_basis_project_bwd_geom_kernel<BS>;                                                   \
-    const size_t smem = sizeof(PrjGeomSmem<BS>);                                                            \
+    auto kfn = triplet_basis_project_bwd_geom_kernel<BS, TORS>;                                             \
+    const size_t smem = sizeof(PrjGeomSmem<BS, TORS>);                                                      \
     if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { \
       set_error("triplet_basis_project_bwd_geom: cannot reserve %zu bytes of shared memory", smem);         \
       return DIG3D_ECUDA;                                                                                   \
     }                                                                                                       \
-    kfn<<<grid, PRJ_WARPS * 32, smem, st>>>(bess, bess_dx, angle, src, dst, row_ptr, trip_ptr, graph_ptr,   \
-                                            batch, (int)n_edges, gp, w_sbf1, inv, ddist, dangle);           \
+    kfn<<<grid, PRJG_WARPS * 32, smem, st>>>(bess, bess_dx, angle, torsion, src, dst, row_ptr, trip_ptr,    \
+                                             graph_ptr, batch, (int)n_edges, gp, w_sbf1, w_t1, inv, ddist,  \
+                                             dangle, dtorsion);                                             \
   }
+#define DIG3D_PRJG(BS) \
+  if (tors) DIG3D_PRJG_ONE(BS, true) else DIG3D_PRJG_ONE(BS, false)
   switch (basis_id) {
     case 0: DIG3D_PRJG(B76); break;
     case 1: DIG3D_PRJG(B36); break;
     default: set_error("triplet_basis_project_bwd_geom: unsupported basis_id %d", basis_id); return DIG3D_EUNSUPPORTED;
   }
+#undef DIG3D_PRJG_ONE
 #undef DIG3D_PRJG
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;

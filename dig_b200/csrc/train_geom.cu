@@ -5,7 +5,7 @@
 //   triplet_angle_bwd    angle[t] = atan2(|ji x jk|, ji . jk)              geometric_computing.py:43-48
 //   schnet_edge_features_bwd / rowdot                                        schnet.py:24-33,92-94
 //
-// The torsion angle's backward (SphereNet forces) is not implemented.
+//   triplet_torsion_bwd  torsion[t] = min_c dihedral(k, j->i, c)              geometric_computing.py:53-75
 #include "common.cuh"
 
 namespace dig3d {
@@ -93,6 +93,83 @@ triplet_angle_bwd_kernel(const float* __restrict__ pos, const int32_t* __restric
   if (lane == 0) atomic_add3(dpos, i, gi);
 }
 
+
+// torsion[t] = min over the in-neighbours c != i of j of atan2(((p1 x p2) . u) / |u|, p1 . p2) (<= 0 -> + 2 pi), with
+// u = pos_i - pos_j, p1 = u x (pos_k - pos_j), p2 = u x (pos_c - pos_j)            geometric_computing.py:53-75.
+// The gradient flows through the minimising candidate only (torch.min / scatter_min backward).  The planes are
+// recomputed with the forward's ATen rounding so that the same candidate wins.
+constexpr int TGEO_WARPS = 8;
+constexpr int TGEO_MAXDEG = 64;
+
+__global__ void __launch_bounds__(TGEO_WARPS * 32)
+triplet_torsion_bwd_kernel(const float* __restrict__ pos, const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+                           const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ trip_ptr,
+                           const float* __restrict__ dtorsion, int n_edges, float* __restrict__ dpos) {
+  __shared__ float planes[TGEO_WARPS][TGEO_MAXDEG][3];
+  __shared__ int32_t ks[TGEO_WARPS][TGEO_MAXDEG];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int e = blockIdx.x * TGEO_WARPS + w;
+  if (e >= n_edges) return;
+  const int j = src[e], i = dst[e];
+  const int base = row_ptr[j], d = min(row_ptr[j + 1] - base, TGEO_MAXDEG);
+  const f3 pj = load3(pos, j);
+  const f3 u = sub3(load3(pos, i), pj);
+  const float n = norm3_aten(u);
+  for (int s = lane; s < d; s += 32) {
+    const int k = src[base + s];
+    ks[w][s] = k;
+    const f3 pl = cross_aten(u, sub3(load3(pos, k), pj));
+    planes[w][s][0] = pl.x; planes[w][s][1] = pl.y; planes[w][s][2] = pl.z;
+  }
+  __syncwarp();
+  int p_i = d;
+  for (int s = 0; s < d; ++s) if (ks[w][s] == i) p_i = s;
+  const int t0 = trip_ptr[e];
+  f3 gi = {0.f, 0.f, 0.f}, gj = {0.f, 0.f, 0.f};
+  for (int s = lane; s < d; s += 32) {
+    if (s == p_i) continue;
+    const float g = dtorsion[t0 + s - (s > p_i ? 1 : 0)];
+    const f3 p1 = {planes[w][s][0], planes[w][s][1], planes[w][s][2]};
+    float best = __int_as_float(0x7f800000), bta = 1.f, btb = 0.f;
+    int bc = -1;
+    for (int c = 0; c < d; ++c) {
+      if (c == p_i) continue;
+      const f3 p2 = {planes[w][c][0], planes[w][c][1], planes[w][c][2]};
+      const float ta = sum3_aten(mul3(p1, p2));
+      const float tb = __fdiv_rn(sum3_aten(mul3(cross_aten(p1, p2), u)), n);
+      float tor = atan2f(tb, ta);
+      if (tor <= 0.0f) tor = __fadd_rn(tor, 6.2831855f);
+      if (tor < best) { best = tor; bc = c; bta = ta; btb = tb; }
+    }
+    const float den = bta * bta + btb * btb;
+    if (bc < 0 || den == 0.f || g == 0.f) continue;
+    const float g_ta = -btb / den * g, g_tb = bta / den * g;
+    const f3 p2 = {planes[w][bc][0], planes[w][bc][1], planes[w][bc][2]};
+    const f3 q = cross3(p1, p2);
+    const float sq = q.x * u.x + q.y * u.y + q.z * u.z;
+    const float g_s = g_tb / n, g_n = -g_tb * sq / (n * n);
+    f3 g_p1 = scale3(p2, g_ta), g_p2 = scale3(p1, g_ta);
+    const f3 g_q = scale3(u, g_s);
+    f3 g_u = add3(scale3(q, g_s), scale3(u, g_n / n));
+    g_p1 = add3(g_p1, cross3(p2, g_q));
+    g_p2 = add3(g_p2, cross3(g_q, p1));
+    const int k = ks[w][s], c = ks[w][bc];
+    const f3 vk = sub3(load3(pos, k), pj), vc = sub3(load3(pos, c), pj);
+    g_u = add3(g_u, add3(cross3(vk, g_p1), cross3(vc, g_p2)));
+    const f3 g_vk = cross3(g_p1, u), g_vc = cross3(g_p2, u);
+    atomic_add3(dpos, k, g_vk);
+    atomic_add3(dpos, c, g_vc);
+    gi = add3(gi, g_u);
+    gj = add3(gj, add3(g_u, add3(g_vk, g_vc)));
+  }
+  gi = warp_sum3(gi);
+  gj = warp_sum3(gj);
+  if (lane == 0) {
+    atomic_add3(dpos, i, gi);
+    atomic_add3(dpos, j, scale3(gj, -1.f));
+  }
+}
+
 // ddist[e] = sum_g dgauss[e,g] * gauss[e,g] * 2 coeff (d - mu_g)  +  dcut[e] * (-0.5 sin(d pi / c) pi / c)
 __global__ void schnet_edge_features_bwd_kernel(const float* __restrict__ dist, int64_t n_edges,
                                                 const float* __restrict__ offset, int n_gauss, float coeff,
@@ -149,6 +226,16 @@ int dig3d_triplet_angle_bwd(const float* pos, const int32_t* src, const int32_t*
   if (n_edges == 0) return DIG3D_OK;
   triplet_angle_bwd_kernel<<<ceil_div(n_edges * 32, 256), 256, 0, (cudaStream_t)stream>>>(
       pos, src, dst, row_ptr, trip_ptr, dangle, (int)n_edges, dpos);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_triplet_torsion_bwd(const float* pos, const int32_t* src, const int32_t* dst, const int32_t* row_ptr,
+                              const int32_t* trip_ptr, const float* dtorsion, int64_t n_edges, float* dpos, void* stream) {
+  DIG3D_REQUIRE(pos && src && dst && row_ptr && trip_ptr && dtorsion && dpos, "triplet_torsion_bwd: null pointer");
+  if (n_edges == 0) return DIG3D_OK;
+  triplet_torsion_bwd_kernel<<<ceil_div(n_edges, TGEO_WARPS), TGEO_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      pos, src, dst, row_ptr, trip_ptr, dtorsion, (int)n_edges, dpos);
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
 }

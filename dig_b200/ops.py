@@ -672,16 +672,29 @@ def edge_basis_bwd(dist, cutoff, envelope_exponent, freq, basis_id, envelope_on_
     return ddist, bdx
 
 
-def triplet_basis_project_bwd_geom(g, bess, bess_dx, basis_id, d_sbf_p, w_sbf1_rows, cutoff):
+def triplet_torsion_bwd(pos, g, dtorsion, dpos):
+    call("dig3d_triplet_torsion_bwd", _p(pos, F32, "pos"), _p(g.src), _p(g.dst), _p(g.row_ptr), _p(g.trip_ptr),
+         _p(dtorsion, F32, "dtorsion"), g.n_edges, _p(dpos), _stream())
+
+
+def triplet_basis_project_bwd_geom(g, bess, bess_dx, basis_id, d_sbf_p, d_t_p, w_sbf1_rows, w_t1_rows, cutoff):
+    """-> (ddist_kj [E], dangle [T], dtorsion [T] | None); d_t_p / w_t1_rows None = no torsion branch."""
     dev = bess.device
+    tors = d_t_p is not None
     ddist = torch.zeros(g.n_edges, device=dev, dtype=F32)
     dangle = torch.zeros(g.n_triplets, device=dev, dtype=F32)
+    dtors = torch.zeros(g.n_triplets, device=dev, dtype=F32) if tors else None
     arr = ctypes.c_void_p * 4
-    vals = [(_p(t, F32, "grad").value if t is not None else None) for t in d_sbf_p] + [None] * (4 - len(d_sbf_p))
-    call("dig3d_triplet_basis_project_bwd_geom", _p(bess, F32), _p(bess_dx, F32), _p(g.angle), _p(g.src), _p(g.dst),
-         _p(g.row_ptr), _p(g.trip_ptr), _p(g.graph_ptr), _p(g.batch, torch.int64), g.n_edges, g.n_triplets,
-         int(basis_id), arr(*vals), _p(w_sbf1_rows, F32), float(cutoff), _p(ddist), _p(dangle), _stream())
-    return ddist, dangle
+
+    def ptrs(lst):
+        return arr(*([(_p(t, F32, "grad", align=16).value if t is not None else None) for t in lst]
+                     + [None] * (4 - len(lst))))
+    call("dig3d_triplet_basis_project_bwd_geom", _p(bess, F32), _p(bess_dx, F32), _p(g.angle),
+         _p(g.torsion) if tors else None, _p(g.src), _p(g.dst), _p(g.row_ptr), _p(g.trip_ptr), _p(g.graph_ptr),
+         _p(g.batch, torch.int64), g.n_edges, g.n_triplets, int(basis_id), ptrs(d_sbf_p), ptrs(d_t_p) if tors else None,
+         _p(w_sbf1_rows, F32), _p(w_t1_rows, F32) if tors else None, float(cutoff), _p(ddist), _p(dangle), _p(dtors),
+         _stream())
+    return ddist, dangle, dtors
 
 
 def schnet_edge_features_bwd(dist, offset, coeff, cutoff, dgauss, dcut):

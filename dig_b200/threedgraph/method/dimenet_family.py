@@ -215,10 +215,6 @@ class _DimeNetFamily(nn.Module):
         z, pos, batch = batch_data.z, batch_data.pos, batch_data.batch
         require_cuda(pos, type(self).__name__ + ".forward")
         if self.energy_and_force:
-            if self._torsion:
-                raise NotImplementedError(
-                    "SphereNet energy_and_force=True: the torsion basis / torsion angle have no position-gradient "
-                    "kernels yet (DimeNetPP and SchNet do)")
             pos.requires_grad_()                      # reference dimenetpp.py:275-276
         ns, nr = self.num_spherical, self.num_radial
         g = ops.build_graph(pos, batch, self.cutoff, num_graphs=getattr(batch_data, "num_graphs", None))
@@ -278,8 +274,12 @@ class _DimeNetFamily(nn.Module):
         spherical basis carry no parameters except dist_emb.freq, so they run on the same kernels as inference."""
         ns, nr = self.num_spherical, self.num_radial
         ops.triplet_geometry(g, pos, use_torsion=self._torsion, want_idx=False)
-        if pos.requires_grad:      # forces: dist / angle carry the position gradient (csrc/train_geom.cu)
-            dist, angle = ag.geometry(pos, g, True)
+        tors_angle = None
+        if pos.requires_grad:      # forces: dist / angle / torsion carry the position gradient (csrc/train_geom.cu)
+            if self._torsion:
+                dist, angle, tors_angle = ag.geometry(pos, g, 3)
+            else:
+                dist, angle = ag.geometry(pos, g, 2)
         else:
             dist, angle = g.dist, g.angle
         geo_cfg = (self.cutoff, self.envelope_exponent, not self._torsion, dist)
@@ -289,7 +289,7 @@ class _DimeNetFamily(nn.Module):
         sbf_ps, t_ps = [], []
         for first in range(0, L, 4):
             es = self.update_es[first:first + 4]
-            s_l, t_l = ag.basis_project(g, bess, dist, angle, geo_cfg, self._basis_id, ns, nr,
+            s_l, t_l = ag.basis_project(g, bess, dist, angle, tors_angle, geo_cfg, self._basis_id, ns, nr,
                                         [m.lin_sbf1.weight for m in es],
                                         [m.lin_t1.weight for m in es] if self._torsion else None)
             sbf_ps += s_l
@@ -330,7 +330,7 @@ class SphereNet(_DimeNetFamily):
 
     Same constructor arguments and defaults.  Restrictions of this round (raise at construction):
     `use_extra_node_feature=True`, `use_node_features=False`, non-swish `act`, and channel sizes other
-    than the class defaults; `energy_and_force=True` raises at forward (no backward kernels yet)."""
+    than the class defaults.  `energy_and_force=True`: forward is differentiable w.r.t. pos (first order)."""
     _torsion = True
 
     def __init__(self, energy_and_force=False, cutoff=5.0, num_layers=4, hidden_channels=128, out_channels=1,

@@ -138,7 +138,7 @@ class SchNet(nn.Module):
         """Differentiable forward (reference schnet.py:149-168 op for op) over dig_b200.autograd's primitives;
         used whenever autograd is recording, i.e. by run.train."""
         # forces (run.py:126,165: autograd.grad(out, pos)): dist carries the position gradient
-        dist = ag.geometry(pos, g, False) if pos.requires_grad else g.dist
+        dist = ag.geometry(pos, g, 1) if pos.requires_grad else g.dist
         gauss, cut = ag.schnet_edge_features(dist, self.dist_emb.offset, self.dist_emb.coeff, self.cutoff)
         v = ag.gather_rows(self.init_v.weight, z)
         for ue, uv in zip(self.update_es, self.update_vs):

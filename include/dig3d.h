@@ -338,9 +338,10 @@ int dig3d_graphnorm_bwd(const float* h, const float* dy, const int32_t* graph_pt
  * triplet_angle_bwd: dpos += d angle[t] for angle = atan2(|ji x jk|, ji.jk) (geometric_computing.py:43-48).
  * edge_basis_bwd: ddist[E] = drbf0 . d rbf0/d dist (written, 0 when drbf0 is NULL) and bess_dx[E, ns*nr] = d/dx of the
  *   (enveloped, when envelope_on_bessel) Bessel basis of dig3d_edge_basis; either output may be NULL.
- * triplet_basis_project_bwd_geom: dangle[T] (every row written) and ddist_kj[E] (every row written) of
- *   dig3d_triplet_basis_project's sbf branch given d_sbf_p (host array of 4 device pointers, NULL entries allowed);
- *   the torsion branch (SphereNet forces) is not implemented.
+ * triplet_torsion_bwd: dpos += d torsion[t] through the minimising candidate (geometric_computing.py:53-75).
+ * triplet_basis_project_bwd_geom: dangle[T], ddist_kj[E] (and dtorsion[T] when the torsion arguments are given; every
+ *   row written) of dig3d_triplet_basis_project given d_sbf_p / d_t_p (host arrays of 4 device pointers, NULL entries
+ *   allowed) and the forward's w_sbf1 / w_t1 rows.
  * schnet_edge_features_bwd: ddist[E] from dgauss[E,G] / dcut[E] (either may be NULL).  rowdot: out[r] = a[r,:].b[r,:]. */
 int dig3d_edge_dist_bwd(const float* pos, const int32_t* src, const int32_t* dst, const float* dist, const float* ddist,
                         int64_t n_edges, float* dpos, void* stream);
@@ -349,11 +350,15 @@ int dig3d_triplet_angle_bwd(const float* pos, const int32_t* src, const int32_t*
 int dig3d_edge_basis_bwd(const float* dist, int64_t n_edges, double cutoff, int32_t envelope_exponent, const float* freq,
                          int32_t basis_id, int32_t envelope_on_bessel, const float* drbf0, float* ddist, float* bess_dx,
                          void* stream);
-int dig3d_triplet_basis_project_bwd_geom(const float* bess, const float* bess_dx, const float* angle, const int32_t* src,
-                                         const int32_t* dst, const int32_t* row_ptr, const int32_t* trip_ptr,
-                                         const int32_t* graph_ptr, const int64_t* batch, int64_t n_edges,
-                                         int64_t n_triplets, int32_t basis_id, const float* const* d_sbf_p,
-                                         const float* w_sbf1, double cutoff, float* ddist, float* dangle, void* stream);
+int dig3d_triplet_basis_project_bwd_geom(const float* bess, const float* bess_dx, const float* angle,
+                                         const float* torsion, const int32_t* src, const int32_t* dst,
+                                         const int32_t* row_ptr, const int32_t* trip_ptr, const int32_t* graph_ptr,
+                                         const int64_t* batch, int64_t n_edges, int64_t n_triplets, int32_t basis_id,
+                                         const float* const* d_sbf_p, const float* const* d_t_p, const float* w_sbf1,
+                                         const float* w_t1, double cutoff, float* ddist, float* dangle, float* dtorsion,
+                                         void* stream);
+int dig3d_triplet_torsion_bwd(const float* pos, const int32_t* src, const int32_t* dst, const int32_t* row_ptr,
+                              const int32_t* trip_ptr, const float* dtorsion, int64_t n_edges, float* dpos, void* stream);
 int dig3d_schnet_edge_features_bwd(const float* dist, int64_t n_edges, const float* offset, int32_t n_gauss,
                                    double coeff, double cutoff, const float* dgauss, const float* dcut, float* ddist,
                                    void* stream);
