@@ -138,10 +138,12 @@ class ComENet(nn.Module):
     def __init__(self, cutoff=8.0, num_layers=4, hidden_channels=256, middle_channels=64, out_channels=1,
                  num_radial=3, num_spherical=2, num_output_layers=3):
         super().__init__()
-        if (hidden_channels, middle_channels, num_radial, num_spherical) != (256, 64, 3, 2) or num_output_layers > 8:
+        if (num_radial, num_spherical) != (3, 2):
             raise NotImplementedError(
-                "ComENet kernels of this round are compiled for hidden_channels=256, middle_channels=64, "
-                f"num_radial=3, num_spherical=2; got {(hidden_channels, middle_channels, num_radial, num_spherical)}")
+                "the ComENet geometry/basis kernel is generated for num_radial=3, num_spherical=2 "
+                f"(dig_b200/codegen.py:CONFIGS); got {(num_radial, num_spherical)}")
+        # fused block kernels: hidden 256 / middle 64 / <= 8 output layers; other widths run the generic CUDA primitives
+        self._generic = (hidden_channels, middle_channels) != (256, 64) or num_output_layers > 8
         if num_layers < 1:
             raise ValueError("num_layers must be >= 1")
         self.out_channels = out_channels
@@ -169,7 +171,7 @@ class ComENet(nn.Module):
         g = ops.build_graph(pos, batch, self.cutoff, num_graphs=getattr(data, "num_graphs", None),
                             want_edge_index=False)
         f1, f2, _ = ops.comenet_geometry(g, pos, self.cutoff)
-        if wants_grad(self):
+        if wants_grad(self) or self._generic:
             return self._forward_train(z, g, f1, f2)
         x = ops.comenet_embed(z, self.emb.emb.weight)
         no_head = ops.pack_comenet_head([], None)

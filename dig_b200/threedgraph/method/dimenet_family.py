@@ -151,10 +151,16 @@ class _DimeNetFamily(nn.Module):
                      out_emb_channels=out_emb_channels, num_radial=num_radial,
                      num_before_skip=num_before_skip, num_after_skip=num_after_skip)
         bad = {k: v for k, v in given.items() if _SUPPORTED[k] != v}
-        if bad or not (be_dist == be_angle == 8 and (be_torsion == 8 or not self._torsion)):
+        # The triplet kernels (fused basis projection, triplet gather) are compiled for int_emb_size 64 and
+        # basis_emb_size_angle/torsion 8; everything else (hidden / out_emb widths, basis_emb_size_dist, number of
+        # residual layers) is free on the GENERIC path: the same CUDA primitives the training path is made of
+        # (dig3d_linear & co., any shape), slower than the fused kernels that exist for the class defaults.
+        if int_emb_size != 64 or be_angle != 8 or (self._torsion and be_torsion != 8) or num_radial != 6:
             raise NotImplementedError(
-                f"{type(self).__name__}: the sm_100a kernels of this round are compiled for "
-                f"{_SUPPORTED} and basis_emb_size 8; got {bad or (be_dist, be_angle, be_torsion)}")
+                f"{type(self).__name__}: the triplet kernels are compiled for int_emb_size=64, "
+                f"basis_emb_size_angle/torsion=8, num_radial=6; got int_emb_size={int_emb_size}, "
+                f"basis_emb sizes {(be_dist, be_angle, be_torsion)}, num_radial={num_radial}")
+        self._generic = bool(bad) or be_dist != 8
         if ("dimenet", num_spherical, num_radial) not in ops.BASIS_IDS:
             raise NotImplementedError(
                 f"no generated basis for num_spherical={num_spherical}, num_radial={num_radial}; "
@@ -218,7 +224,7 @@ class _DimeNetFamily(nn.Module):
             pos.requires_grad_()                      # reference dimenetpp.py:275-276
         ns, nr = self.num_spherical, self.num_radial
         g = ops.build_graph(pos, batch, self.cutoff, num_graphs=getattr(batch_data, "num_graphs", None))
-        if wants_grad(self):
+        if wants_grad(self) or self._generic:
             return self._forward_train(z, pos, g)
         ops.triplet_geometry(g, pos, use_torsion=self._torsion, want_idx=False)
         rbf0, bess = ops.edge_basis(g.dist, self.cutoff, self.envelope_exponent, self.emb.dist_emb.freq,
@@ -329,7 +335,7 @@ class SphereNet(_DimeNetFamily):
     r"""Drop-in for dig.threedgraph.method.SphereNet (reference spherenet.py:228-320).
 
     Same constructor arguments and defaults.  Restrictions of this round (raise at construction):
-    `use_extra_node_feature=True`, `use_node_features=False`, non-swish `act`, and channel sizes other
+    `use_extra_node_feature=True`, `use_node_features=False`, non-swish `act`, and triplet-branch sizes other
     than the class defaults.  `energy_and_force=True`: forward is differentiable w.r.t. pos (first order)."""
     _torsion = True
 

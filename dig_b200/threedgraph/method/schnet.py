@@ -79,17 +79,16 @@ class emb(nn.Module):
 
 class SchNet(nn.Module):
     r"""Drop-in for dig.threedgraph.method.SchNet (same constructor arguments and defaults).
-    This round's kernels are compiled for hidden_channels == num_filters in {32, 64, 128} and
-    num_gaussians <= 64.  energy_and_force=True: forward stays differentiable w.r.t. pos (first order: forces in
+    Fused kernels: hidden_channels == num_filters in {32, 64, 128} and num_gaussians <= 64; other sizes
+    run the (slower) generic CUDA primitives.  energy_and_force=True: forward stays differentiable w.r.t. pos (first order: forces in
     run.val / user code); force *training* needs a double backward and raises."""
 
     def __init__(self, energy_and_force=False, cutoff=10.0, num_layers=6, hidden_channels=128, out_channels=1,
                  num_filters=128, num_gaussians=50):
         super().__init__()
-        if hidden_channels != num_filters or hidden_channels not in (32, 64, 128) or num_gaussians > 64:
-            raise NotImplementedError(
-                "SchNet kernels of this round need hidden_channels == num_filters in {32, 64, 128} and "
-                f"num_gaussians <= 64; got {hidden_channels}/{num_filters}/{num_gaussians}")
+        # fused cfconv kernels exist for hidden_channels == num_filters in {32, 64, 128} and num_gaussians <= 64; other
+        # sizes run the generic path (the CUDA primitives of the training path, any shape)
+        self._generic = hidden_channels != num_filters or hidden_channels not in (32, 64, 128) or num_gaussians > 64
         self.energy_and_force = energy_and_force
         self.cutoff = cutoff
         self.num_layers = num_layers
@@ -120,7 +119,7 @@ class SchNet(nn.Module):
             pos.requires_grad_()                      # reference schnet.py:153-154
         g = ops.build_graph(pos, batch, self.cutoff, num_graphs=getattr(batch_data, "num_graphs", None),
                             want_edge_index=False)
-        if wants_grad(self):
+        if wants_grad(self) or self._generic:
             return self._forward_train(z, pos, g)
         # v = init_v(z): an embedding row gather (torch indexing = plumbing, no arithmetic)
         v = self.init_v.weight.detach()[z].contiguous()

@@ -263,9 +263,6 @@ def test_run_val_on_the_fused_path():
     ref = restated.schnet_forward({k: v.to(dev) for k, v in sd.items()}, b.z, b.pos, b.batch, cutoff=10.0, num_layers=2)
     want = float((ref.flatten() - b.y).abs().mean())
     assert abs(mae - want) < 1e-5 * max(1.0, abs(want))
-    with pytest.raises(NotImplementedError):
-        run().train(model, torch.optim.Adam(model.parameters()), DataLoader(DS(mols), 4), False, 100,
-                    torch.nn.L1Loss(), dev)
 
 
 @pytest.mark.parametrize("cfg", ["cfg3-dimenetpp-md17-b256", "cfg4-comenet-oc20-b64"])
@@ -362,4 +359,43 @@ def test_non_default_hyperparameters(cls_name, kw):
                                           num_layers=kw["num_layers"], num_spherical=kw.get("num_spherical", 7),
                                           num_output_layers=kw.get("num_output_layers", 3))
     assert u.shape == ref.shape == (5, kw.get("out_channels", 1))
+    assert rel_err(u.cpu().numpy(), ref.cpu().numpy()) < TOL
+
+
+@pytest.mark.parametrize("cls_name,kw", [
+    ("SphereNet", dict(hidden_channels=64, out_emb_channels=128, basis_emb_size_dist=4, num_before_skip=2,
+                       num_after_skip=1, num_output_layers=2, out_channels=2, num_layers=3, cutoff=5.0)),
+    ("DimeNetPP", dict(hidden_channels=96, out_emb_channels=192, num_layers=2, cutoff=5.0)),
+    ("SchNet", dict(hidden_channels=48, num_filters=80, num_gaussians=70, num_layers=3, cutoff=6.0)),
+    ("ComENet", dict(hidden_channels=128, middle_channels=32, num_layers=2, num_output_layers=2, cutoff=5.0)),
+])
+def test_generic_channel_sizes(cls_name, kw):
+    """Widths the fused kernels are not compiled for run on the generic CUDA primitives (same kernels as the training
+    path): parity against the oracle on the same GPU."""
+    from dig_b200.data import synthetic_batch
+    from dig_b200.threedgraph import method
+    from oracle import restated
+    dev = torch.device("cuda:0")
+    model = getattr(method, cls_name)(**kw)
+    assert model._generic
+    sd = formula_state_dict(model.state_dict(), seed=13)
+    model.load_state_dict(sd)
+    model = model.to(dev)
+    b = synthetic_batch(5, "qm9", seed=8, variable=True).to(dev)
+    with torch.no_grad():
+        u = model(b)
+    sd_dev = {k: v.to(dev) for k, v in sd.items()}
+    if cls_name in ("SphereNet", "DimeNetPP"):
+        ref = restated.dimenet_family_forward(sd_dev, b.z, b.pos, b.batch, torsion=(cls_name == "SphereNet"),
+                                              cutoff=kw["cutoff"], num_layers=kw["num_layers"],
+                                              num_before_skip=kw.get("num_before_skip", 1),
+                                              num_after_skip=kw.get("num_after_skip", 2),
+                                              num_output_layers=kw.get("num_output_layers", 3))
+    elif cls_name == "SchNet":
+        ref = restated.schnet_forward(sd_dev, b.z, b.pos, b.batch, cutoff=kw["cutoff"], num_layers=kw["num_layers"],
+                                      num_gaussians=kw["num_gaussians"])
+    else:
+        ref = restated.comenet_forward(sd_dev, b.z, b.pos, b.batch, cutoff=kw["cutoff"], num_layers=kw["num_layers"],
+                                       num_output_layers=kw["num_output_layers"])
+    assert u.shape == ref.shape
     assert rel_err(u.cpu().numpy(), ref.cpu().numpy()) < TOL
