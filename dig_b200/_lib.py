@@ -91,7 +91,7 @@ SIGNATURES = {
     "dig3d_comenet_embed": [P, P, c_int64, P, P],
     "dig3d_comenet_block": [P, P, P, P, P, P, P, c_int64, c_int64, c_int64, POINTER(ComenetBlockWeights),
                             POINTER(ComenetHeadWeights), c_int32, P, P, P, P, P, P, P, P],
-    "dig3d_linear": [P, c_int64, c_int32, c_int32, P, P, P, P],
+    "dig3d_linear": [P, c_int64, c_int32, c_int32, P, P, P, P, P],
     "dig3d_wgrad": [P, P, c_int64, c_int32, c_int32, P, P, P],
     "dig3d_act": [P, c_int64, c_int32, P, P],
     "dig3d_act_bwd": [P, P, c_int64, c_int32, P, P],
@@ -112,6 +112,9 @@ SIGNATURES = {
     "dig3d_triplet_torsion_bwd": [P, P, P, P, P, P, c_int64, P, P],
     "dig3d_schnet_edge_features_bwd": [P, c_int64, P, c_int32, c_double, c_double, P, P, P, P],
     "dig3d_rowdot": [P, P, c_int64, c_int32, P, P],
+    "dig3d_tc_pack_t": [P, P, P, P, P, c_int32, P],
+    "dig3d_linear_tc_supported": [c_int32, c_int32],
+    "dig3d_linear_tc": [P, c_int64, c_int32, c_int32, P, P, P, P, P],
     "dig3d_transpose": [P, c_int32, c_int32, P, P],
     "dig3d_schnet_edge_features": [P, c_int64, P, c_int32, c_double, c_double, P, P, P],
 }

@@ -5,6 +5,8 @@ tape: every forward AND backward computation below is a kernel of libdig3d.so (o
 Nothing here has a CPU path; double backward (needed for force training, run.py:110-115) is not implemented and
 raises.
 """
+import os
+
 import torch
 from torch.autograd.function import once_differentiable
 
@@ -17,13 +19,36 @@ def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _use_tc(weight, rows, k, nout):
+    """The exact-fp32 FFMA GEMMs are the default of the training path.  DIG3D_TRAIN_DENSE=tc moves the shapes tcgen05 is
+    compiled for (3xTF32, fp32-accurate) to the tensor cores; measured on the B200 the unfused per-linear kernel gains
+    little (32 vs 44 us for 34.5 k x 128 x 128) and pays a weight re-pack per parameter update, so it is opt-in."""
+    return (os.environ.get("DIG3D_TRAIN_DENSE", "simt") == "tc" and rows >= ops.TC_LINEAR_MIN_ROWS
+            and weight.is_contiguous() and ops.linear_tc_supported(k, nout))
+
+
+def _linear_fwd(x, weight, bias, want_act=False):
+    k, nout = weight.size(1), weight.size(0)
+    b = None if bias is None else bias.detach()
+    if _use_tc(weight, x.numel() // k, k, nout):
+        return ops.linear_tc(x, weight, b, want_act=want_act)
+    return ops.linear(x, _c(weight.detach()), b, want_act=want_act)
+
+
+def _linear_bwd_input(dy, weight):
+    k, nout = weight.size(1), weight.size(0)
+    if _use_tc(weight, dy.numel() // nout, nout, k):
+        return ops.linear_tc(dy, weight, None, transposed=True)
+    return ops.linear(dy, ops.transpose(_c(weight.detach())), None)
+
+
 class _Linear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias):
         x = _c(x)
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
-        return ops.linear(x, _c(weight.detach()), None if bias is None else bias.detach())
+        return _linear_fwd(x, weight, bias)
 
     @staticmethod
     @once_differentiable
@@ -32,9 +57,33 @@ class _Linear(torch.autograd.Function):
         dy = _c(dy)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = ops.linear(dy, ops.transpose(_c(weight.detach())), None)
+            dx = _linear_bwd_input(dy, weight)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             dw, db = ops.wgrad(dy, x, tuple(weight.shape), ctx.has_bias)
+        return dx, dw, db
+
+
+class _LinearSwish(torch.autograd.Function):
+    """swish(x W^T + b) with the activation fused into the GEMM epilogue; the pre-activation is kept for the backward."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = _c(x)
+        pre, y = _linear_fwd(x, weight, bias, want_act=True)
+        ctx.save_for_backward(x, weight, pre)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, weight, pre = ctx.saved_tensors
+        dpre = ops.act_bwd(pre, _c(dy), SWISH)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = _linear_bwd_input(dpre, weight)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw, db = ops.wgrad(dpre, x, tuple(weight.shape), ctx.has_bias)
         return dx, dw, db
 
 
@@ -154,6 +203,11 @@ def linear(x, weight, bias=None):
 def lin(module, x):
     """Apply an nn.Linear-like module (attributes weight, bias)."""
     return _Linear.apply(x, module.weight, getattr(module, "bias", None))
+
+
+def lin_swish(module, x):
+    """swish(module(x)) with the activation fused into the linear's epilogue."""
+    return _LinearSwish.apply(x, module.weight, getattr(module, "bias", None))
 
 
 def swish(x):

@@ -293,7 +293,7 @@ sphere_triplet_gather_kernel(const float* __restrict__ x_down, const float* __re
 
 // ---------------------------------------------------------------------------------- weight packing
 // W [N, K] (nn.Linear layout) -> [K/32][hi|lo][8][N][4], hi/lo = TF32 split.  One launch packs up to 16 matrices.
-struct PackJob { const float* w; float* out; int N, K; };
+struct PackJob { const float* w; float* out; int N, K, trans; };   // trans: the source is stored [K, N] (W^T)
 struct PackJobs { PackJob job[16]; int n; };
 __global__ void tc_pack_kernel(PackJobs jobs) {
   const PackJob jb = jobs.job[blockIdx.y];
@@ -301,7 +301,7 @@ __global__ void tc_pack_kernel(PackJobs jobs) {
   for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < total; id += gridDim.x * blockDim.x) {
     const int n = id / jb.K, k = id % jb.K;
     float h, l;
-    split_tf32(__ldg(jb.w + id), h, l);
+    split_tf32(__ldg(jb.w + (jb.trans ? (size_t)k * jb.N + n : (size_t)id)), h, l);
     const int c = k >> 5, ku = (k & 31) >> 2, kk = k & 3;
     const size_t blk = (size_t)c * (2 * 8 * jb.N * 4);
     jb.out[blk + ((size_t)ku * jb.N + n) * 4 + kk] = h;
@@ -682,6 +682,92 @@ sphere_init_e_tc_kernel(const int64_t* __restrict__ z, const int32_t* __restrict
   if (warp == 0) tmem_dealloc(s.tmem_base, 256);
 }
 
+
+// ---------------------------------------------------------------------------------- generic linear (training path)
+// y[rows, N] = x[rows, K] W^T + bias on tcgen05 (3xTF32, streaming accumulation), K = NPANEL panels of K4*4 columns,
+// N in {64, 128}; optionally also act_out = swish(y) (the training forward keeps the pre-activation for the backward).
+template <int NPANEL>
+struct TcLinParams { TcGemm g[NPANEL]; };
+
+template <int K4>
+__device__ __forceinline__ void load_a_tile_ld(TcSmem& s, const float* __restrict__ g, size_t ld, int rows) {
+  const int et = threadIdx.x - 64;
+#pragma unroll
+  for (int k = 0; k < TC_M * K4 / TC_EPI_THREADS; ++k) {
+    const int f = et + k * TC_EPI_THREADS;
+    const int row = f / K4, c4 = f % K4;
+    const float4 x = row < rows ? __ldg(reinterpret_cast<const float4*>(g + (size_t)row * ld) + c4)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 h, l;
+    split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
+    const int o = (c4 * TC_AKU + row) * 4;
+    *reinterpret_cast<float4*>(s.a_hi + o) = h;
+    *reinterpret_cast<float4*>(s.a_lo + o) = l;
+  }
+}
+
+template <int NPANEL, int N, int K4>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+linear_tc_kernel(const float* __restrict__ x, int n_rows, TcLinParams<NPANEL> P, const float* __restrict__ bias,
+                 float* __restrict__ y, float* __restrict__ act_out) {
+  extern __shared__ __align__(1024) unsigned char tc_raw[];
+  TcSmem& s = *reinterpret_cast<TcSmem*>(tc_raw);
+  constexpr int K = NPANEL * K4 * 4;
+  constexpr int PW = N / 4;                          // columns per epilogue column-part (32 or 16)
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int r0 = blockIdx.x * TC_M, rows = min(TC_M, n_rows - r0);
+  if (tid == 0) {
+    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    mbar_init(&s.a_ready, TC_EPI_WARPS);
+    for (int i = 0; i < 2; ++i) { mbar_init(&s.d_ready[i], 1); mbar_init(&s.d_free[i], TC_EPI_WARPS); }
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&s.tmem_base, 256);
+  for (int i = tid; i < N; i += TC_THREADS) s.bias[0][i] = bias ? __ldg(bias + i) : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) {
+    if (tid == 0) tc_producer(s, P.g);
+  } else if (warp == 1) {
+    if (tid == 32) tc_mma(s, P.g, s.tmem_base);
+  } else {
+    const EpiCtx c = epi_ctx(s);
+    const bool valid = c.row < rows;
+    const uint32_t tl = c.tm + ((uint32_t)c.lane_base << 16);
+    const int col0 = c.part * PW;
+    int it = 0;
+    float acc[PW];
+#pragma unroll
+    for (int p = 0; p < NPANEL; ++p) {
+      load_a_tile_ld<K4>(s, x + (size_t)r0 * K + p * (K4 * 4), K, rows);
+      epi_done(s);
+      if (p == 0) epi_accumulate<PW / 16, true>(s, tl, col0, K4 / 8, it, acc);
+      else epi_accumulate<PW / 16, false>(s, tl, col0, K4 / 8, it, acc);
+    }
+    if (valid) {
+      float* yr = y + (size_t)(r0 + c.row) * N + col0;
+      float* ar = act_out ? act_out + (size_t)(r0 + c.row) * N + col0 : nullptr;
+#pragma unroll
+      for (int i = 0; i < PW; i += 4) {
+        float4 o;
+        o.x = acc[i] + s.bias[0][col0 + i];
+        o.y = acc[i + 1] + s.bias[0][col0 + i + 1];
+        o.z = acc[i + 2] + s.bias[0][col0 + i + 2];
+        o.w = acc[i + 3] + s.bias[0][col0 + i + 3];
+        *reinterpret_cast<float4*>(yr + i) = o;
+        if (ar) {
+          float4 a;
+          a.x = swish_t<false>(o.x); a.y = swish_t<false>(o.y); a.z = swish_t<false>(o.z); a.w = swish_t<false>(o.w);
+          *reinterpret_cast<float4*>(ar + i) = a;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(s.tmem_base, 256);
+}
+
 static int tc_smem_attr(const void* fn, size_t bytes) {
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   if (e != cudaSuccess) {
@@ -690,6 +776,20 @@ static int tc_smem_attr(const void* fn, size_t bytes) {
   }
   return DIG3D_OK;
 }
+
+template <int NPANEL, int N, int K4>
+static int launch_linear_tc(const float* x, int64_t rows, const float* packed, const float* bias, float* y, float* act_out,
+                            cudaStream_t st) {
+  TcLinParams<NPANEL> P;
+  const size_t panel = (size_t)(K4 / 8) * 2 * 8 * N * 4;      // K4/8 chunks of [hi|lo][8][N][4] floats
+  for (int p = 0; p < NPANEL; ++p) P.g[p] = {packed + p * panel, nullptr, K4 * 4, N};
+  auto kfn = linear_tc_kernel<NPANEL, N, K4>;
+  int rc = tc_smem_attr((const void*)kfn, sizeof(TcSmem));
+  if (rc) return rc;
+  kfn<<<ceil_div(rows, TC_M), TC_THREADS, sizeof(TcSmem), st>>>(x, (int)rows, P, bias, y, act_out);
+  return DIG3D_OK;
+}
+
 
 }  // namespace dig3d
 
@@ -707,11 +807,49 @@ int dig3d_tc_pack(const float* const* weights, const int32_t* n, const int32_t* 
   int max_total = 0;
   for (int i = 0; i < count; ++i) {
     DIG3D_REQUIRE(weights[i] && outs[i] && k[i] % 32 == 0 && n[i] % 8 == 0, "tc_pack: matrix %d has N=%d K=%d", i, n[i], k[i]);
-    jobs.job[i] = {weights[i], outs[i], n[i], k[i]};
+    jobs.job[i] = {weights[i], outs[i], n[i], k[i], 0};
     max_total = max_total > n[i] * k[i] ? max_total : n[i] * k[i];
   }
   dim3 grid(ceil_div(max_total, 256), count);
   tc_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(jobs);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_tc_pack_t(const float* const* weights, const int32_t* n, const int32_t* k, const int32_t* trans,
+                    float* const* outs, int32_t count, void* stream) {
+  DIG3D_REQUIRE(weights && n && k && trans && outs && count >= 1 && count <= 16, "tc_pack_t: bad arguments");
+  PackJobs jobs;
+  jobs.n = count;
+  int max_total = 0;
+  for (int i = 0; i < count; ++i) {
+    DIG3D_REQUIRE(weights[i] && outs[i] && k[i] % 32 == 0 && n[i] % 8 == 0, "tc_pack_t: matrix %d has N=%d K=%d", i, n[i], k[i]);
+    jobs.job[i] = {weights[i], outs[i], n[i], k[i], trans[i] ? 1 : 0};
+    max_total = max_total > n[i] * k[i] ? max_total : n[i] * k[i];
+  }
+  dim3 grid(ceil_div(max_total, 256), count);
+  tc_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(jobs);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_linear_tc_supported(int32_t k, int32_t nout) {
+  return ((nout == 128 && (k == 64 || k == 128 || k == 256 || k == 384)) || (nout == 64 && k == 128)) ? 1 : 0;
+}
+
+int dig3d_linear_tc(const float* x, int64_t rows, int32_t k, int32_t nout, const float* packed, const float* bias,
+                    float* y, float* act_out, void* stream) {
+  DIG3D_REQUIRE(x && packed && y, "linear_tc: null pointer");
+  DIG3D_REQUIRE(dig3d_linear_tc_supported(k, nout), "linear_tc: shape %d -> %d is not compiled", k, nout);
+  if (rows == 0) return DIG3D_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if (nout == 64) rc = launch_linear_tc<1, 64, 32>(x, rows, packed, bias, y, act_out, st);
+  else if (k == 64) rc = launch_linear_tc<1, 128, 16>(x, rows, packed, bias, y, act_out, st);
+  else if (k == 128) rc = launch_linear_tc<1, 128, 32>(x, rows, packed, bias, y, act_out, st);
+  else if (k == 256) rc = launch_linear_tc<2, 128, 32>(x, rows, packed, bias, y, act_out, st);
+  else rc = launch_linear_tc<3, 128, 32>(x, rows, packed, bias, y, act_out, st);
+  if (rc) return rc;
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
 }

@@ -28,7 +28,7 @@ struct LinSmem {
 template <int NOUT, int K>
 __global__ void __launch_bounds__(DT, 1)
 linear_tiled_kernel(const float* __restrict__ x, int rows_total, const float* __restrict__ w,
-                    const float* __restrict__ bias, float* __restrict__ y) {
+                    const float* __restrict__ bias, float* __restrict__ y, float* __restrict__ act_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LinSmem<NOUT, K>& s = *reinterpret_cast<LinSmem<NOUT, K>*>(smem_raw);
   const int r0 = blockIdx.x * 64, rows = min(64, rows_total - r0);
@@ -46,7 +46,9 @@ linear_tiled_kernel(const float* __restrict__ x, int rows_total, const float* __
 #pragma unroll
       for (int q = 0; q < NOUT / 16; ++q) {
         const int c = tx + 16 * q;
-        y[(size_t)(r0 + r) * NOUT + c] = acc[p][q] + (bias ? __ldg(bias + c) : 0.f);
+        const float v = acc[p][q] + (bias ? __ldg(bias + c) : 0.f);
+        y[(size_t)(r0 + r) * NOUT + c] = v;
+        if (act_out) act_out[(size_t)(r0 + r) * NOUT + c] = swish(v);
       }
     }
   }
@@ -55,7 +57,7 @@ linear_tiled_kernel(const float* __restrict__ x, int rows_total, const float* __
 // ------------------------------------------------------------------ linear, naive (any shape)
 __global__ void linear_naive_kernel(const float* __restrict__ x, int64_t rows, int k, int nout,
                                     const float* __restrict__ w, const float* __restrict__ bias,
-                                    float* __restrict__ y) {
+                                    float* __restrict__ y, float* __restrict__ act_out) {
   const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= rows * nout) return;
   const int64_t r = id / nout;
@@ -64,7 +66,9 @@ __global__ void linear_naive_kernel(const float* __restrict__ x, int64_t rows, i
   const float* wr = w + (size_t)c * k;
   float acc = 0.f;
   for (int i = 0; i < k; ++i) acc = fmaf(__ldg(xr + i), __ldg(wr + i), acc);
-  y[id] = acc + (bias ? __ldg(bias + c) : 0.f);
+  const float v = acc + (bias ? __ldg(bias + c) : 0.f);
+  y[id] = v;
+  if (act_out) act_out[id] = swish(v);
 }
 
 // ------------------------------------------------------------------ weight gradient: dW[n][k] += sum_r dY[r][n] X[r][k]
@@ -310,12 +314,13 @@ __global__ void graphnorm_bwd_kernel(const float* __restrict__ h, const float* _
 }
 
 template <int NOUT, int K>
-static int launch_linear_tiled(const float* x, int64_t rows, const float* w, const float* b, float* y, cudaStream_t st) {
+static int launch_linear_tiled(const float* x, int64_t rows, const float* w, const float* b, float* y, float* act_out,
+                               cudaStream_t st) {
   auto kfn = linear_tiled_kernel<NOUT, K>;
   const size_t sm = sizeof(LinSmem<NOUT, K>);
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (e != cudaSuccess) { set_error("linear: cudaFuncSetAttribute(%zu): %s", sm, cudaGetErrorString(e)); return DIG3D_ECUDA; }
-  kfn<<<ceil_div(rows, 64), DT, sm, st>>>(x, (int)rows, w, b, y);
+  kfn<<<ceil_div(rows, 64), DT, sm, st>>>(x, (int)rows, w, b, y, act_out);
   return DIG3D_OK;
 }
 
@@ -326,19 +331,19 @@ using namespace dig3d;
 extern "C" {
 
 int dig3d_linear(const float* x, int64_t rows, int32_t k, int32_t nout, const float* w, const float* bias, float* y,
-                 void* stream) {
+                 float* act_out, void* stream) {
   DIG3D_REQUIRE(x && w && y && k > 0 && nout > 0, "linear: bad arguments");
   if (rows == 0) return DIG3D_OK;
   cudaStream_t st = (cudaStream_t)stream;
   int rc = -100;
-#define DIG3D_LT(NO, KK) if (nout == NO && k == KK) rc = launch_linear_tiled<NO, KK>(x, rows, w, bias, y, st);
+#define DIG3D_LT(NO, KK) if (nout == NO && k == KK) rc = launch_linear_tiled<NO, KK>(x, rows, w, bias, y, act_out, st);
   DIG3D_LT(128, 128) DIG3D_LT(64, 128) DIG3D_LT(128, 64) DIG3D_LT(256, 128) DIG3D_LT(256, 256) DIG3D_LT(128, 256)
   DIG3D_LT(128, 384) DIG3D_LT(32, 32) DIG3D_LT(64, 64) DIG3D_LT(128, 32) DIG3D_LT(32, 128) DIG3D_LT(256, 64)
   DIG3D_LT(64, 256) DIG3D_LT(256, 512) DIG3D_LT(384, 128) DIG3D_LT(512, 256)
 #undef DIG3D_LT
   if (rc == -100) {
     const int64_t total = rows * nout;
-    linear_naive_kernel<<<ceil_div(total, 256), 256, 0, st>>>(x, rows, k, nout, w, bias, y);
+    linear_naive_kernel<<<ceil_div(total, 256), 256, 0, st>>>(x, rows, k, nout, w, bias, y, act_out);
     rc = DIG3D_OK;
   }
   if (rc) return rc;

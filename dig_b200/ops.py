@@ -489,25 +489,27 @@ def _idx(t, name="index"):
     return _p(t, None, name), int(t.dtype == torch.int64)
 
 
-def linear(x, weight, bias=None):
-    """y = x weight^T + bias for x [..., K] (nn.Linear)."""
+def linear(x, weight, bias=None, want_act=False):
+    """y = x weight^T + bias for x [..., K] (nn.Linear); want_act: also swish(y) from the same kernel."""
     k = x.size(-1)
     nout = weight.size(0)
     if weight.dim() != 2 or weight.size(1) != k:
         raise ValueError(f"linear: weight {tuple(weight.shape)} does not match input width {k}")
     rows = x.numel() // k if k else 0
     y = torch.empty(x.shape[:-1] + (nout,), device=x.device, dtype=F32)
+    act_out = torch.empty_like(y) if want_act else None
     call("dig3d_linear", _p(x, F32, "x"), rows, k, nout, _p(weight, F32, "weight"), _p(bias, F32, "bias"),
-         _p(y), _stream())
-    return y
+         _p(y), _p(act_out), _stream())
+    return (y, act_out) if want_act else y
 
 
 def wgrad(dy, x, weight_shape, want_bias):
     """(dW, db) of y = x W^T + b given dy."""
     nout, k = weight_shape
     rows = x.numel() // k
-    dw = torch.zeros(nout, k, device=x.device, dtype=F32)
-    db = torch.zeros(nout, device=x.device, dtype=F32) if want_bias else None
+    buf = torch.zeros(nout * k + (nout if want_bias else 0), device=x.device, dtype=F32)     # one fill for both
+    dw = buf[:nout * k].view(nout, k)
+    db = buf[nout * k:] if want_bias else None
     call("dig3d_wgrad", _p(dy, F32, "dy"), _p(x, F32, "x"), rows, nout, k, _p(dw), _p(db), _stream())
     return dw, db
 
@@ -709,3 +711,44 @@ def rowdot(a, b):
     out = torch.empty(rows, device=a.device, dtype=F32)
     call("dig3d_rowdot", _p(a, F32, "a"), _p(b, F32, "b"), rows, a.numel() // max(rows, 1), _p(out), _stream())
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# tcgen05 linears of the training path
+TC_LINEAR_MIN_ROWS = 512
+
+
+def linear_tc_supported(k, nout):
+    return (nout == 128 and k in (64, 128, 256, 384)) or (nout == 64 and k == 128)
+
+
+def _packed_weight(weight, transposed):
+    """TF32 hi/lo-split UMMA-layout copy of W (or W^T).  The copy lives ON the tensor object (attribute
+    `_dig3d_packed`), so it dies with the parameter -- a cache keyed by address could hand a new tensor that reuses
+    the storage the packed weights of a dead one -- and is re-packed when the tensor changes (tensor._version).
+    Pass the parameter itself (not a .detach() view, which is a new object every time)."""
+    store = weight.__dict__.setdefault("_dig3d_packed", {})
+    hit = store.get(bool(transposed))
+    if hit is not None and hit[0] == (weight._version, weight.data_ptr(), tuple(weight.shape)):
+        return hit[1]
+    n, k = (weight.size(1), weight.size(0)) if transposed else (weight.size(0), weight.size(1))
+    buf = torch.empty(2 * n * k, dtype=F32, device=weight.device)
+    one = ctypes.c_void_p * 1
+    call("dig3d_tc_pack_t", one(_p(weight.detach(), F32, "w", 16).value), (ctypes.c_int32 * 1)(n), (ctypes.c_int32 * 1)(k),
+         (ctypes.c_int32 * 1)(int(bool(transposed))), one(buf.data_ptr()), 1, _stream())
+    store[bool(transposed)] = ((weight._version, weight.data_ptr(), tuple(weight.shape)), buf)
+    return buf
+
+
+def linear_tc(x, weight, bias=None, transposed=False, want_act=False):
+    """y = x W^T + b (transposed=False) or y = x W (transposed=True: the input-gradient GEMM) on tcgen05 3xTF32.
+    want_act: also return swish(y)."""
+    k = x.size(-1)
+    nout = weight.size(1) if transposed else weight.size(0)
+    rows = x.numel() // k
+    packed = _packed_weight(weight, transposed)
+    y = torch.empty(x.shape[:-1] + (nout,), device=x.device, dtype=F32)
+    act_out = torch.empty_like(y) if want_act else None
+    call("dig3d_linear_tc", _p(x, F32, "x", 16), rows, k, nout, _p(packed), _p(bias, F32, "bias"), _p(y), _p(act_out),
+         _stream())
+    return (y, act_out) if want_act else y

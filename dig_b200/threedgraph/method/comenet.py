@@ -188,21 +188,21 @@ class ComENet(nn.Module):
         swish_, lin = ag.swish, ag.lin
         x = swish_(ag.gather_rows(self.emb.emb.weight, z))                     # comenet.py:125-127
         for blk in self.interaction_blocks:
-            x = swish_(lin(blk.lin, x))
+            x = ag.lin_swish(blk.lin, x)
             hs = []
             for conv, lf, l, feat in ((blk.conv1, blk.lin_feature1, blk.lin1, f1),
                                       (blk.conv2, blk.lin_feature2, blk.lin2, f2)):
                 w = lin(lf.lin2, lin(lf.lin1, feat))                            # TwoLayerLinear, no bias / act
                 agg = ag.segment_sum(ag.mul(w, ag.gather_rows(x, g.src)), g.row_ptr, g.dst)     # GraphConv, aggr='add'
                 h = ag.add(lin(conv.lin_rel, agg), lin(conv.lin_root, x))
-                hs.append(swish_(lin(l, h)))
+                hs.append(ag.lin_swish(l, h))
             h = ag.add(lin(blk.lin_cat, torch.cat(hs, 1)), x)
             for l in blk.lins:
-                h = ag.add(swish_(lin(l, h)), h)
+                h = ag.add(ag.lin_swish(l, h), h)
             h = ag.graphnorm(h, blk.norm, g.graph_ptr)
             x = lin(blk.final, h)
         for l in self.lins:
-            x = swish_(lin(l, x))
+            x = ag.lin_swish(l, x)
         x = lin(self.lin_out, x)
         return ag.segment_sum(x, g.graph_ptr, g.batch)
 

@@ -271,7 +271,7 @@ class _DimeNetFamily(nn.Module):
         v = ag.segment_sum(e2, g.row_ptr, g.dst)
         v = ag.lin(m.lin_up, v)
         for lin in m.lins:
-            v = ag.swish(ag.lin(lin, v))
+            v = ag.lin_swish(lin, v)
         return ag.lin(m.lin, v)
 
     def _forward_train(self, z, pos, g):
@@ -304,26 +304,26 @@ class _DimeNetFamily(nn.Module):
         # init_e (spherenet.py:79-91)
         ie = self.init_e
         x = ag.gather_rows(ie.emb.weight, z)
-        r0 = swish_(lin(ie.lin_rbf_0, rbf0))
+        r0 = ag.lin_swish(ie.lin_rbf_0, rbf0)
         cat = torch.cat([ag.gather_rows(x, g.dst, g.row_ptr), ag.gather_rows(x, g.src), r0], dim=-1)   # copy only
-        e1 = swish_(lin(ie.lin, cat))
+        e1 = ag.lin_swish(ie.lin, cat)
         e2 = ag.mul(lin(ie.lin_rbf_1, rbf0), e1)
         v = self._update_v_train(self.init_v, e2, g)
         u = ag.segment_sum(v, g.graph_ptr, g.batch)
         for l, (ue, uv) in enumerate(zip(self.update_es, self.update_vs)):      # spherenet.py:150-182
-            x_ji = swish_(lin(ue.lin_ji, e1))
-            x_kj = swish_(lin(ue.lin_kj, e1))
+            x_ji = ag.lin_swish(ue.lin_ji, e1)
+            x_kj = ag.lin_swish(ue.lin_kj, e1)
             x_kj = ag.mul(x_kj, lin(ue.lin_rbf2, lin(ue.lin_rbf1, rbf0)))
-            x_kj = swish_(lin(ue.lin_down, x_kj))
+            x_kj = ag.lin_swish(ue.lin_down, x_kj)
             x_kj = ag.triplet_gather(x_kj, sbf_ps[l], t_ps[l], ue.lin_sbf2.weight,
                                      ue.lin_t2.weight if self._torsion else None, g)
-            x_kj = swish_(lin(ue.lin_up, x_kj))
+            x_kj = ag.lin_swish(ue.lin_up, x_kj)
             h = ag.add(x_ji, x_kj)
             for layer in ue.layers_before_skip:
-                h = ag.add(h, swish_(lin(layer.lin2, swish_(lin(layer.lin1, h)))))
-            h = ag.add(swish_(lin(ue.lin, h)), e1)
+                h = ag.add(h, ag.lin_swish(layer.lin2, ag.lin_swish(layer.lin1, h)))
+            h = ag.add(ag.lin_swish(ue.lin, h), e1)
             for layer in ue.layers_after_skip:
-                h = ag.add(h, swish_(lin(layer.lin2, swish_(lin(layer.lin1, h)))))
+                h = ag.add(h, ag.lin_swish(layer.lin2, ag.lin_swish(layer.lin1, h)))
             e1 = h
             e2 = ag.mul(lin(ue.lin_rbf, rbf0), e1)
             v = self._update_v_train(uv, e2, g)

@@ -292,7 +292,7 @@ int dig3d_comenet_block(const float* x_in, const float* feature1, const float* f
  *   ewise:   op 0 y = a*b, op 1 y = a+b ; rowscale: y[r,:] = a[r,:] * s[r]
  *   gather_rows: y[r,:] = x[idx[r],:] ; scatter_add_rows: out[idx[r],:] += y[r,:] (atomics; out initialised) */
 int dig3d_linear(const float* x, int64_t rows, int32_t k, int32_t nout, const float* w, const float* bias, float* y,
-                 void* stream);
+                 float* act_out /* nullable: also receives swish(y) */, void* stream);
 int dig3d_wgrad(const float* dy, const float* x, int64_t rows, int32_t nout, int32_t k, float* dw, float* db,
                 void* stream);
 int dig3d_act(const float* x, int64_t n, int32_t mode, float* y, void* stream);
@@ -363,6 +363,15 @@ int dig3d_schnet_edge_features_bwd(const float* dist, int64_t n_edges, const flo
                                    double coeff, double cutoff, const float* dgauss, const float* dcut, float* ddist,
                                    void* stream);
 int dig3d_rowdot(const float* a, const float* b, int64_t rows, int32_t width, float* out, void* stream);
+/* Generic linear on tcgen05 (3xTF32 split, fp32-accurate; same machinery as the fused update_e chain): y = x W^T + bias
+ * for the shapes dig3d_linear_tc_supported() reports (K in {64,128,256,384} -> 128, 128 -> 64); act_out (nullable)
+ * additionally receives swish(y).  `packed` = dig3d_tc_pack / dig3d_tc_pack_t output for W; tc_pack_t packs W^T when
+ * trans[i] != 0 (the source is then read as [K, N]), which gives the input-gradient GEMM dx = dy W. */
+int dig3d_tc_pack_t(const float* const* weights, const int32_t* n, const int32_t* k, const int32_t* trans,
+                    float* const* outs, int32_t count, void* stream);
+int dig3d_linear_tc_supported(int32_t k, int32_t nout);
+int dig3d_linear_tc(const float* x, int64_t rows, int32_t k, int32_t nout, const float* packed, const float* bias,
+                    float* y, float* act_out, void* stream);
 /* out[cols, rows] = in[rows, cols]^T (weights for the input-gradient GEMM dx = dy W) */
 int dig3d_transpose(const float* in, int32_t rows, int32_t cols, float* out, void* stream);
 /* SchNet training path: gaussian smearing gauss[E, n_gauss] (schnet.py:92-94) and cosine cutoff cut[E]

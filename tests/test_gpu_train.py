@@ -356,3 +356,57 @@ def test_spherenet_forces_match_oracle_autograd(name):
     f_ref = -torch.autograd.grad(ref.sum(), pos2)[0]
     assert rel_err(out.detach().cpu().numpy(), ref.detach().cpu().numpy()) < 1e-5
     assert rel_err(force.cpu().numpy(), f_ref.cpu().numpy()) < FTOL
+
+
+@pytest.mark.parametrize("k,nout", [(128, 128), (64, 128), (128, 64), (256, 128), (384, 128)])
+def test_linear_tc_matches_fp64(k, nout):
+    """tcgen05 3xTF32 linear of the training path (forward, fused swish, and the W^T orientation used for dX)."""
+    from dig_b200 import ops
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(k + nout)
+    rows = 1000
+    x = torch.randn(rows, k, generator=gen).to(dev)
+    w = (torch.randn(nout, k, generator=gen) / k ** 0.5).to(dev)
+    b = torch.randn(nout, generator=gen).to(dev)
+    y, a = ops.linear_tc(x, w, b, want_act=True)
+    ref = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    assert rel_err(y.cpu().numpy(), ref.cpu().numpy()) < 2e-6
+    assert rel_err(a.cpu().numpy(), (ref * torch.sigmoid(ref)).cpu().numpy()) < 2e-6
+    if ops.linear_tc_supported(nout, k):
+        dy = torch.randn(rows, nout, generator=gen).to(dev)
+        dx = ops.linear_tc(dy, w, None, transposed=True)
+        assert rel_err(dx.cpu().numpy(), (dy.double() @ w.double()).cpu().numpy()) < 2e-6
+    w2 = w.clone()
+    w2.mul_(2.0)                                       # new storage: packed separately
+    y2 = ops.linear_tc(x, w2, b)
+    assert rel_err(y2.cpu().numpy(), torch.nn.functional.linear(x.double(), w2.double(), b.double()).cpu().numpy()) < 2e-6
+    w.mul_(0.5)                                        # in-place update bumps _version: the cache must re-pack
+    y3 = ops.linear_tc(x, w, b)
+    assert rel_err(y3.cpu().numpy(), torch.nn.functional.linear(x.double(), w.double(), b.double()).cpu().numpy()) < 2e-6
+    assert ops.tc_timeouts() == 0
+
+
+def test_training_path_on_tensor_cores_opt_in(monkeypatch):
+    """DIG3D_TRAIN_DENSE=tc: the 128-wide linears (forward and input-gradient GEMMs) on tcgen05 3xTF32; two different
+    models back to back (freed parameters' addresses get reused: the packed-weight copies must not be)."""
+    from dig_b200.threedgraph import method
+    from helpers import CASES
+    from oracle import restated
+    from dig_b200 import ops
+    monkeypatch.setenv("DIG3D_TRAIN_DENSE", "tc")
+    dev = torch.device("cuda:0")
+    for name in ("spherenet_qm9", "dimenetpp_md17", "spherenet_qm9"):
+        model_name, ctor, _, wseed = CASES[name]
+        _, z, pos, batch = case_inputs(name, dev)
+        model = getattr(method, model_name)(**ctor)
+        sd = formula_state_dict(model.state_dict(), seed=wseed)
+        model.load_state_dict(sd)
+        model = model.to(dev)
+        sd = {k: v.to(dev) for k, v in sd.items()}
+        nb = int(batch.max().item()) + 1
+        target = torch.linspace(-1, 1, nb, device=dev).view(nb, 1)
+        fwd = restated.spherenet_forward if model_name == "SphereNet" else restated.dimenetpp_forward
+        _grad_compare(model, sd, lambda s_, *a: fwd(s_, *a, cutoff=5.0), z, pos, batch, target)
+        assert any("_dig3d_packed" in p.__dict__ for p in model.parameters())      # the tensor path really ran
+        del model
+    assert ops.tc_timeouts() == 0
