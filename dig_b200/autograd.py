@@ -164,7 +164,10 @@ class _GatherRows(torch.autograd.Function):
         idx, ptr = ctx.saved_tensors
         dy = _c(dy)
         if ctx.has_ptr:
-            return ops.segment_sum(dy.view(dy.size(0), -1), ptr).view((ctx.n_rows,) + tuple(dy.shape[1:])), None, None
+            width = 1
+            for d in dy.shape[1:]:
+                width *= int(d)
+            return ops.segment_sum(dy.view(dy.size(0), width), ptr).view((ctx.n_rows,) + tuple(dy.shape[1:])), None, None
         return ops.scatter_add_rows(dy, idx, ctx.n_rows), None, None
 
 

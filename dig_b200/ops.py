@@ -170,6 +170,8 @@ def segment_sum(x, ptr):
     if x.dim() != 2:
         raise ValueError("segment_sum expects [rows, width]")
     s = ptr.numel() - 1
+    if x.size(0) == 0:
+        return torch.zeros(s, x.size(1), dtype=torch.float32, device=x.device)
     out = torch.empty(s, x.size(1), dtype=torch.float32, device=x.device)
     if s:
         call("dig3d_segment_sum", _p(x, torch.float32, "x", align=16 if x.size(1) % 4 == 0 else 4), _p(ptr, torch.int32, "ptr"), s, x.size(1),
@@ -491,6 +493,9 @@ def _idx(t, name="index"):
 
 def linear(x, weight, bias=None, want_act=False):
     """y = x weight^T + bias for x [..., K] (nn.Linear); want_act: also swish(y) from the same kernel."""
+    if x.numel() == 0:                       # empty edge / triplet sets (isolated atoms): nothing to launch
+        y = torch.zeros(x.shape[:-1] + (weight.size(0),), device=x.device, dtype=torch.float32)
+        return (y, y.clone()) if want_act else y
     k = x.size(-1)
     nout = weight.size(0)
     if weight.dim() != 2 or weight.size(1) != k:
@@ -505,6 +510,10 @@ def linear(x, weight, bias=None, want_act=False):
 
 def wgrad(dy, x, weight_shape, want_bias):
     """(dW, db) of y = x W^T + b given dy."""
+    if x.numel() == 0:
+        dev = x.device
+        return (torch.zeros(*weight_shape, device=dev, dtype=torch.float32),
+                torch.zeros(weight_shape[0], device=dev, dtype=torch.float32) if want_bias else None)
     nout, k = weight_shape
     rows = x.numel() // k
     buf = torch.zeros(nout * k + (nout if want_bias else 0), device=x.device, dtype=F32)     # one fill for both
@@ -515,12 +524,16 @@ def wgrad(dy, x, weight_shape, want_bias):
 
 
 def act(x, mode):
+    if x.numel() == 0:
+        return torch.empty_like(x)
     y = torch.empty_like(x)
     call("dig3d_act", _p(x, F32, "x"), x.numel(), mode, _p(y), _stream())
     return y
 
 
 def act_bwd(x, dy, mode):
+    if x.numel() == 0:
+        return torch.empty_like(x)
     dx = torch.empty_like(x)
     call("dig3d_act_bwd", _p(x, F32, "x"), _p(dy, F32, "dy"), x.numel(), mode, _p(dx), _stream())
     return dx
@@ -530,11 +543,15 @@ def ewise(a, b, op):
     if a.shape != b.shape:
         raise ValueError(f"ewise: shapes differ {tuple(a.shape)} vs {tuple(b.shape)}")
     y = torch.empty_like(a)
+    if a.numel() == 0:
+        return y
     call("dig3d_ewise", _p(a, F32, "a"), _p(b, F32, "b"), a.numel(), op, _p(y), _stream())
     return y
 
 
 def rowscale(a, s):
+    if a.numel() == 0:
+        return torch.empty_like(a)
     rows, width = a.size(0), a.numel() // max(a.size(0), 1)
     if s.numel() != rows:
         raise ValueError("rowscale: one scale per row expected")
@@ -544,6 +561,8 @@ def rowscale(a, s):
 
 
 def gather_rows(x, idx):
+    if idx.numel() == 0:
+        return torch.empty((0,) + tuple(x.shape[1:]), device=x.device, dtype=torch.float32)
     width = x.numel() // max(x.size(0), 1) if x.dim() > 1 else 1
     rows = idx.numel()
     y = torch.empty((rows,) + tuple(x.shape[1:]), device=x.device, dtype=F32)
@@ -553,6 +572,8 @@ def gather_rows(x, idx):
 
 
 def scatter_add_rows(y, idx, n_rows):
+    if idx.numel() == 0:
+        return torch.zeros((n_rows,) + tuple(y.shape[1:]), device=y.device, dtype=torch.float32)
     width = y.numel() // max(y.size(0), 1) if y.dim() > 1 else 1
     out = torch.zeros((n_rows,) + tuple(y.shape[1:]), device=y.device, dtype=F32)
     ip, i64 = _idx(idx)
@@ -572,6 +593,8 @@ def schnet_edge_features(dist, offset, coeff, cutoff):
     e, ng = dist.numel(), offset.numel()
     gauss = torch.empty(e, ng, device=dist.device, dtype=F32)
     cut = torch.empty(e, device=dist.device, dtype=F32)
+    if e == 0:
+        return gauss, cut
     call("dig3d_schnet_edge_features", _p(dist, F32, "dist"), e, _p(offset, F32, "offset"), ng, float(coeff),
          float(cutoff), _p(gauss), _p(cut), _stream())
     return gauss, cut
@@ -580,6 +603,8 @@ def schnet_edge_features(dist, offset, coeff, cutoff):
 def rbf_freq_grad(dist, cutoff, envelope_exponent, freq, drbf0):
     """d(loss)/d(dist_emb.freq) from d(loss)/d(rbf0)."""
     dfreq = torch.zeros_like(freq, dtype=F32)
+    if dist.numel() == 0:
+        return dfreq
     call("dig3d_rbf_freq_grad", _p(dist, F32, "dist"), dist.numel(), float(cutoff), int(envelope_exponent),
          _p(freq.detach(), F32, "freq"), freq.numel(), _p(drbf0, F32, "drbf0"), _p(dfreq), _stream())
     return dfreq
@@ -588,6 +613,8 @@ def rbf_freq_grad(dist, cutoff, envelope_exponent, freq, drbf0):
 def sphere_triplet_gather(x_down, sbf_p, t_p, g, w_sbf2, w_t2):
     """m[E, 64] = sum over the triplets of each edge of x_down[kj] * lin_sbf2(sbf_p) * lin_t2(t_p)  (spherenet.py:163-171)."""
     e = g.n_edges
+    if e == 0 or g.n_triplets == 0:
+        return torch.zeros(e, x_down.size(1), device=x_down.device, dtype=F32)
     m = torch.empty(e, x_down.size(1), device=x_down.device, dtype=F32)
     call("dig3d_sphere_triplet_gather", _p(x_down, F32, "x_down"), _p(sbf_p, F32, "sbf_p"), _p(t_p, F32, "t_p"), 8,
          _p(g.src), _p(g.dst), _p(g.row_ptr), _p(g.trip_ptr), e, _p(w_sbf2, F32, "w_sbf2"), _p(w_t2, F32, "w_t2"),
@@ -604,6 +631,8 @@ def sphere_triplet_gather_bwd(dm, x_down, sbf_p, t_p, g, w_sbf2, w_t2):
     d_t = torch.empty_like(t_p) if tors else None
     dws = torch.zeros_like(w_sbf2)
     dwt = torch.zeros_like(w_t2) if tors else None
+    if g.n_edges == 0 or g.n_triplets == 0:
+        return dx, d_s, d_t, dws, dwt
     call("dig3d_sphere_triplet_gather_bwd", _p(dm, F32, "dm"), _p(x_down, F32), _p(sbf_p, F32), _p(t_p, F32),
          _p(g.src), _p(g.dst), _p(g.row_ptr), _p(g.trip_ptr), g.n_edges, _p(w_sbf2, F32), _p(w_t2, F32), _p(dx),
          _p(d_s), _p(d_t), _p(dws), _p(dwt), _stream())
@@ -621,6 +650,8 @@ def triplet_basis_project_bwd(g, bess, basis_id, d_sbf_p, d_t_p, n_sbf, n_tbf):
     def ptrs(lst):
         vals = [(_p(t, F32, "grad").value if t is not None else None) for t in lst] + [None] * (4 - len(lst))
         return arr(*vals)
+    if g.n_edges == 0 or g.n_triplets == 0:
+        return dws, dwt
     ps = ptrs(d_sbf_p)
     pt = ptrs(d_t_p) if tors else None
     call("dig3d_triplet_basis_project_bwd", _p(bess, F32), _p(g.angle), _p(g.torsion) if tors else None, _p(g.src),
@@ -654,11 +685,15 @@ def graphnorm_bwd(h, dy, graph_ptr, weight, mean_scale, shift, std):
 # ---------------------------------------------------------------------------------------------------------------
 # Position gradients (forces)
 def edge_dist_bwd(pos, g, ddist, dpos):
+    if g.n_edges == 0:
+        return
     call("dig3d_edge_dist_bwd", _p(pos, F32, "pos"), _p(g.src), _p(g.dst), _p(g.dist), _p(ddist, F32, "ddist"), g.n_edges,
          _p(dpos), _stream())
 
 
 def triplet_angle_bwd(pos, g, dangle, dpos):
+    if g.n_edges == 0 or g.n_triplets == 0:
+        return
     call("dig3d_triplet_angle_bwd", _p(pos, F32, "pos"), _p(g.src), _p(g.dst), _p(g.row_ptr), _p(g.trip_ptr),
          _p(dangle, F32, "dangle"), g.n_edges, _p(dpos), _stream())
 
@@ -668,6 +703,8 @@ def edge_basis_bwd(dist, cutoff, envelope_exponent, freq, basis_id, envelope_on_
     e = dist.numel()
     ddist = torch.zeros(e, device=dist.device, dtype=F32) if want_ddist else None
     bdx = torch.empty(e, n_bessel, device=dist.device, dtype=F32) if want_bess_dx else None
+    if e == 0:
+        return ddist, bdx
     call("dig3d_edge_basis_bwd", _p(dist, F32, "dist"), e, float(cutoff), int(envelope_exponent),
          _p(freq.detach(), F32, "freq") if freq is not None else None, int(basis_id), int(bool(envelope_on_bessel)),
          _p(drbf0, F32, "drbf0"), _p(ddist), _p(bdx), _stream())
@@ -675,6 +712,8 @@ def edge_basis_bwd(dist, cutoff, envelope_exponent, freq, basis_id, envelope_on_
 
 
 def triplet_torsion_bwd(pos, g, dtorsion, dpos):
+    if g.n_edges == 0 or g.n_triplets == 0:
+        return
     call("dig3d_triplet_torsion_bwd", _p(pos, F32, "pos"), _p(g.src), _p(g.dst), _p(g.row_ptr), _p(g.trip_ptr),
          _p(dtorsion, F32, "dtorsion"), g.n_edges, _p(dpos), _stream())
 
@@ -691,6 +730,8 @@ def triplet_basis_project_bwd_geom(g, bess, bess_dx, basis_id, d_sbf_p, d_t_p, w
     def ptrs(lst):
         return arr(*([(_p(t, F32, "grad", align=16).value if t is not None else None) for t in lst]
                      + [None] * (4 - len(lst))))
+    if g.n_edges == 0 or g.n_triplets == 0:
+        return ddist, dangle, dtors
     call("dig3d_triplet_basis_project_bwd_geom", _p(bess, F32), _p(bess_dx, F32), _p(g.angle),
          _p(g.torsion) if tors else None, _p(g.src), _p(g.dst), _p(g.row_ptr), _p(g.trip_ptr), _p(g.graph_ptr),
          _p(g.batch, torch.int64), g.n_edges, g.n_triplets, int(basis_id), ptrs(d_sbf_p), ptrs(d_t_p) if tors else None,
@@ -701,12 +742,16 @@ def triplet_basis_project_bwd_geom(g, bess, bess_dx, basis_id, d_sbf_p, d_t_p, w
 
 def schnet_edge_features_bwd(dist, offset, coeff, cutoff, dgauss, dcut):
     ddist = torch.empty_like(dist)
+    if dist.numel() == 0:
+        return ddist
     call("dig3d_schnet_edge_features_bwd", _p(dist, F32, "dist"), dist.numel(), _p(offset, F32), offset.numel(),
          float(coeff), float(cutoff), _p(dgauss, F32), _p(dcut, F32), _p(ddist), _stream())
     return ddist
 
 
 def rowdot(a, b):
+    if a.numel() == 0:
+        return torch.zeros(a.size(0), device=a.device, dtype=torch.float32)
     rows = a.size(0)
     out = torch.empty(rows, device=a.device, dtype=F32)
     call("dig3d_rowdot", _p(a, F32, "a"), _p(b, F32, "b"), rows, a.numel() // max(rows, 1), _p(out), _stream())

@@ -77,3 +77,47 @@ def test_evaluator_known_answer():
     ev = ThreeDEvaluator()
     assert ev.eval({"y_true": np.array([1.0, -0.5]), "y_pred": np.array([0.6, 0.0])})["mae"] == pytest.approx(0.45)
     assert ev.eval({"y_true": torch.tensor([1.0, -0.5]), "y_pred": torch.tensor([0.6, 0.0])})["mae"] == pytest.approx(0.45)
+
+
+def test_generic_size_flags_and_constructor_contract():
+    """Host logic (no GPU): which constructor arguments select the fused kernels, the generic CUDA primitives, or raise."""
+    from dig_b200.threedgraph.method import ComENet, DimeNetPP, SchNet, SphereNet
+    assert not SphereNet()._generic and not DimeNetPP()._generic and not ComENet()._generic
+    assert not SchNet()._generic and not SchNet(hidden_channels=32, num_filters=32)._generic
+    assert SphereNet(hidden_channels=64, out_emb_channels=128)._generic
+    assert SphereNet(basis_emb_size_dist=4)._generic and DimeNetPP(num_before_skip=2)._generic
+    assert SchNet(hidden_channels=48, num_filters=80)._generic and SchNet(num_gaussians=70)._generic
+    assert ComENet(hidden_channels=128, middle_channels=32)._generic
+    for bad in (dict(int_emb_size=32), dict(basis_emb_size_angle=4), dict(num_radial=5), dict(num_spherical=5)):
+        with pytest.raises(NotImplementedError):
+            SphereNet(**bad)
+    with pytest.raises(NotImplementedError):
+        ComENet(num_radial=4)
+    # parameter counts pinned by the reference (SURVEY.md 8c): defaults and the notebook's ns=3 SphereNet
+    count = lambda m: sum(p.numel() for p in m.parameters())
+    assert count(SphereNet()) == 1898566 and count(SphereNet(num_spherical=3)) == 1890118
+    assert count(DimeNetPP()) == 1887110 and count(ComENet(hidden_channels=256, middle_channels=64)) == 3778817
+    assert count(SchNet(num_layers=2, hidden_channels=32, num_filters=32)) == 15393
+
+
+def test_linear_tc_shape_rule_matches_library():
+    from dig_b200 import _lib, ops
+    lib = _lib.load()
+    for k in (6, 8, 32, 64, 128, 256, 384, 512):
+        for n in (1, 8, 64, 128, 256):
+            assert bool(lib.dig3d_linear_tc_supported(k, n)) == bool(ops.linear_tc_supported(k, n)), (k, n)
+
+
+def test_wants_grad_switch():
+    import torch
+    from dig_b200.threedgraph.method import SchNet
+    from dig_b200.threedgraph.method._common import wants_grad
+    m = SchNet(num_layers=1, hidden_channels=32, num_filters=32)
+    assert wants_grad(m)
+    with torch.no_grad():
+        assert not wants_grad(m)
+    for p in m.parameters():
+        p.requires_grad_(False)
+    assert not wants_grad(m)
+    m.energy_and_force = True              # forces need the differentiable path even with frozen parameters
+    assert wants_grad(m)

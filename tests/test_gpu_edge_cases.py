@@ -73,3 +73,53 @@ def test_errors_are_loud():
     with pytest.raises(Dig3dError):
         ops.build_graph(torch.rand(4, 3, device=dev), torch.zeros(4, dtype=torch.long, device=dev), 5.0,
                         max_num_neighbors=200)
+
+
+@pytest.mark.parametrize("cls_name", ["SphereNet", "DimeNetPP", "SchNet"])      # the reference ComENet indexes out of range for atoms without neighbours (comenet.py:305-327)
+def test_training_path_with_isolated_atoms_and_no_triplets(cls_name):
+    """Training forward+backward (and forces where the model has them) on a batch with a no-edge graph, a single atom, a
+    diatomic (edges but no triplets) and a bonded quadruple; then on a batch with no edges at all."""
+    from dig_b200.data import Batch
+    from dig_b200.threedgraph import method
+    from oracle import restated
+    from helpers import formula_state_dict, rel_err
+    dev = torch.device("cuda:0")
+    pos = torch.tensor([[0, 0, 0], [30, 0, 0], [5, 5, 5], [0, 0, 0], [1.1, 0, 0],
+                        [0, 0, 0], [1, 0.1, 0], [0.2, 1.2, 0], [0.9, 1.0, 0.8]], dtype=torch.float32, device=dev)
+    batch = torch.tensor([0, 0, 1, 2, 2, 3, 3, 3, 3], device=dev)
+    z = torch.tensor([1, 6, 7, 8, 1, 6, 1, 1, 8], device=dev)
+    kw = dict(cutoff=5.0)
+    if cls_name in ("SphereNet", "DimeNetPP", "SchNet"):
+        kw["energy_and_force"] = True
+    if cls_name == "SchNet":
+        kw.update(num_layers=2, hidden_channels=32, num_filters=32)
+    model = getattr(method, cls_name)(**kw)
+    sd = formula_state_dict(model.state_dict(), seed=21)
+    model.load_state_dict(sd)
+    model = model.to(dev)
+    b = Batch(z=z, pos=pos.clone(), batch=batch)
+    out = model(b)
+    assert out.shape == (4, 1) and torch.isfinite(out).all()
+    target = torch.tensor([[0.1], [-0.2], [0.3], [0.4]], device=dev)
+    torch.nn.functional.l1_loss(out, target).backward()
+    sd_ref = {k: v.to(dev).clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    pos2 = pos.clone().requires_grad_(True)
+    fwd = {"SphereNet": restated.spherenet_forward, "DimeNetPP": restated.dimenetpp_forward,
+           "SchNet": lambda s, *a, **k: restated.schnet_forward(s, *a, num_layers=2, **k)}[cls_name]
+    ref = fwd(sd_ref, z, pos2, batch, cutoff=5.0, num_graphs=4)
+    torch.nn.functional.l1_loss(ref, target).backward()
+    assert rel_err(out.detach().cpu().numpy(), ref.detach().cpu().numpy()) < 1e-5
+    for name, p in model.named_parameters():
+        r = sd_ref[name].grad
+        scale = max(float(r.abs().max()), 1e-6)
+        assert p.grad is not None and float((p.grad - r).abs().max()) / scale < 2e-4, name
+    if "energy_and_force" in kw:
+        scale = max(float(pos2.grad.abs().max()), 1e-6)
+        assert float((b.pos.grad - pos2.grad).abs().max()) / scale < 1e-4
+    # no edges at all: still differentiable, finite
+    b2 = Batch(z=z[:3], pos=torch.tensor([[0., 0, 0], [40, 0, 0], [80, 0, 0]], device=dev),
+               batch=torch.tensor([0, 0, 1], device=dev))
+    model.zero_grad()
+    out2 = model(b2)
+    out2.sum().backward()
+    assert out2.shape == (2, 1) and torch.isfinite(out2).all()
