@@ -52,3 +52,34 @@ def test_codegen_typing_rules():
 
 def test_envelope_coefficients():
     assert basis.envelope_coefficients(5) == (6, -28.0, 48, -21.0)
+
+
+@pytest.mark.parametrize("flavor,ns,nr", [("dimenet", 7, 6), ("dimenet", 3, 6)])
+def test_derivative_sources_match_finite_differences(flavor, ns, nr):
+    """The force path's generated derivatives (bessel_dx, yl0_dtheta, ylm_dtheta, ylm_dphi) are the symbolic
+    derivatives of the reference's closed forms: check every one against a central difference of the VALUE source,
+    evaluated in float64 (the value sources themselves are pinned to the reference above)."""
+    import math
+    src = basis.basis_sources(flavor, ns, nr)
+    env = {"sin": math.sin, "cos": math.cos, "sqrt": math.sqrt, "pi": math.pi}
+
+    def ev(s, **kw):
+        return float(eval(s, dict(env, **kw)))
+
+    h = 1e-6
+    for x in (0.31, 0.77):
+        for v, d in zip(src["bessel"], src["bessel_dx"]):
+            fd = (ev(v, x=x + h) - ev(v, x=x - h)) / (2 * h)
+            an = ev(d, x=x)
+            assert abs(an - fd) <= 1e-5 * max(1.0, abs(fd)) + 1e-6 * max(abs(ev(v, x=x)) / h * 1e-9, 1.0), (v[:40], x)
+    for th in (0.4, 1.9):
+        for v, d in zip(src["yl0"], src["yl0_dtheta"]):
+            fd = (ev(v, theta=th + h) - ev(v, theta=th - h)) / (2 * h)
+            assert abs(ev(d, theta=th) - fd) <= 1e-6 * max(1.0, abs(fd))
+        for ph in (0.3, 4.1):
+            for v, dt, dp in zip(src["ylm"], src["ylm_dtheta"], src["ylm_dphi"]):
+                fdt = (ev(v, theta=th + h, phi=ph) - ev(v, theta=th - h, phi=ph)) / (2 * h)
+                fdp = (ev(v, theta=th, phi=ph + h) - ev(v, theta=th, phi=ph - h)) / (2 * h)
+                assert abs(ev(dt, theta=th, phi=ph) - fdt) <= 1e-6 * max(1.0, abs(fdt))
+                assert abs(ev(dp, theta=th, phi=ph) - fdp) <= 1e-6 * max(1.0, abs(fdp))
+    assert len(src["bessel_dx"]) == ns * nr and len(src["ylm_dphi"]) == ns * ns
