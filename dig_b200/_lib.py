@@ -115,6 +115,9 @@ SIGNATURES = {
     "dig3d_tc_pack_t": [P, P, P, P, P, c_int32, P],
     "dig3d_linear_tc_supported": [c_int32, c_int32],
     "dig3d_linear_tc": [P, c_int64, c_int32, c_int32, P, P, P, P, P],
+    "dig3d_act_bwd2": [P, P, P, c_int64, c_int32, P, P],
+    "dig3d_edge_dist_bwd2": [P, P, P, P, P, P, c_int64, P, P, P],
+    "dig3d_schnet_edge_features_bwd2": [P, c_int64, P, c_int32, c_double, c_double, P, P, P, P, P, P, P],
     "dig3d_transpose": [P, c_int32, c_int32, P, P],
     "dig3d_schnet_edge_features": [P, c_int64, P, c_int32, c_double, c_double, P, P, P],
 }

@@ -191,6 +191,55 @@ __global__ void schnet_edge_features_bwd_kernel(const float* __restrict__ dist, 
   ddist[e] = acc;
 }
 
+
+// ---- second order (force TRAINING: loss.backward() through forces taken with create_graph=True, run.py:110-123) ----
+// Backward of edge_dist_bwd, i.e. of  dpos = sum_e ddist_e (+u_e at i, -u_e at j),  u_e = (pos_i - pos_j) / d_e,
+// given G = d(loss)/d(dpos) [N,3]:   with w_e = G_i - G_j
+//   d(ddist)_e = u_e . w_e ;   d(pos_i) += ddist_e (w_e - (u_e . w_e) u_e) / d_e ,  d(pos_j) -= the same.
+__global__ void edge_dist_bwd2_kernel(const float* __restrict__ pos, const int32_t* __restrict__ src,
+                                      const int32_t* __restrict__ dst, const float* __restrict__ dist,
+                                      const float* __restrict__ ddist, const float* __restrict__ G, int n_edges,
+                                      float* __restrict__ d_ddist, float* __restrict__ d_pos) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  const float d = dist[e];
+  if (d == 0.f) { d_ddist[e] = 0.f; return; }
+  const int j = src[e], i = dst[e];
+  const f3 u = scale3(sub3(load3(pos, i), load3(pos, j)), 1.0f / d);
+  const f3 w = sub3(load3(G, i), load3(G, j));
+  const float uw = u.x * w.x + u.y * w.y + u.z * w.z;
+  d_ddist[e] = uw;
+  const f3 h = scale3(add3(w, scale3(u, -uw)), ddist[e] / d);
+  atomic_add3(d_pos, i, h);
+  atomic_add3(d_pos, j, scale3(h, -1.f));
+}
+
+// Backward of schnet_edge_features_bwd (ddist = sum_g dgauss gauss' + dcut cut') given g = d(loss)/d(ddist) [E]:
+//   d(dgauss)[e,k] = g_e gauss_k'(d_e),  d(dcut)[e] = g_e cut'(d_e),  d(dist)[e] = g_e (sum_k dgauss gauss_k'' + dcut cut'')
+//   gauss = exp(c t^2), t = d - mu:  gauss' = 2 c t gauss,  gauss'' = (2c + 4 c^2 t^2) gauss;   cut = 0.5 (cos(d w) + 1), w = pi / cutoff
+__global__ void schnet_edge_features_bwd2_kernel(const float* __restrict__ dist, int64_t n_edges,
+                                                 const float* __restrict__ offset, int n_gauss, float coeff,
+                                                 float inv_cutoff, const float* __restrict__ dgauss,
+                                                 const float* __restrict__ dcut, const float* __restrict__ g,
+                                                 float* __restrict__ d_dgauss, float* __restrict__ d_dcut,
+                                                 float* __restrict__ d_dist) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  const float d = dist[e], ge = g[e];
+  float acc = 0.f;
+  for (int k = 0; k < n_gauss; ++k) {
+    const float t = d - __ldg(offset + k);
+    const float ga = expf(coeff * t * t);
+    const float g1 = 2.0f * coeff * t * ga;
+    if (d_dgauss) d_dgauss[e * n_gauss + k] = ge * g1;
+    if (dgauss) acc = fmaf(dgauss[e * n_gauss + k], (2.0f * coeff + 4.0f * coeff * coeff * t * t) * ga, acc);
+  }
+  const float w = 3.14159274101257324f * inv_cutoff;
+  if (d_dcut) d_dcut[e] = ge * (-0.5f * w * sinf(d * w));
+  if (dcut) acc = fmaf(dcut[e], -0.5f * w * w * cosf(d * w), acc);
+  d_dist[e] = ge * acc;
+}
+
 // out[r] = sum_c a[r, c] * b[r, c]   (one warp per row)
 __global__ void rowdot_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t rows, int width,
                               float* __restrict__ out) {
@@ -255,6 +304,27 @@ int dig3d_rowdot(const float* a, const float* b, int64_t rows, int32_t width, fl
   DIG3D_REQUIRE(a && b && out && width > 0, "rowdot: bad arguments");
   if (rows == 0) return DIG3D_OK;
   rowdot_kernel<<<ceil_div(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(a, b, rows, width, out);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_edge_dist_bwd2(const float* pos, const int32_t* src, const int32_t* dst, const float* dist, const float* ddist,
+                         const float* g_dpos, int64_t n_edges, float* d_ddist, float* d_pos, void* stream) {
+  DIG3D_REQUIRE(pos && src && dst && dist && ddist && g_dpos && d_ddist && d_pos, "edge_dist_bwd2: null pointer");
+  if (n_edges == 0) return DIG3D_OK;
+  edge_dist_bwd2_kernel<<<ceil_div(n_edges, 256), 256, 0, (cudaStream_t)stream>>>(pos, src, dst, dist, ddist, g_dpos,
+                                                                                 (int)n_edges, d_ddist, d_pos);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_schnet_edge_features_bwd2(const float* dist, int64_t n_edges, const float* offset, int32_t n_gauss,
+                                    double coeff, double cutoff, const float* dgauss, const float* dcut, const float* g,
+                                    float* d_dgauss, float* d_dcut, float* d_dist, void* stream) {
+  DIG3D_REQUIRE(dist && offset && g && d_dist && n_gauss > 0, "schnet_edge_features_bwd2: bad arguments");
+  if (n_edges == 0) return DIG3D_OK;
+  schnet_edge_features_bwd2_kernel<<<ceil_div(n_edges, 256), 256, 0, (cudaStream_t)stream>>>(
+      dist, n_edges, offset, n_gauss, (float)coeff, (float)(1.0 / cutoff), dgauss, dcut, g, d_dgauss, d_dcut, d_dist);
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
 }

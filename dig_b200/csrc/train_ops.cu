@@ -182,6 +182,16 @@ __global__ void act_bwd_kernel(const float* __restrict__ x, const float* __restr
   const float d = mode == 0 ? s * (1.0f + v * (1.0f - s)) : s;
   dx[i] = dy[i] * d;
 }
+// second order: d/dx of (dy * act'(x)) contracted with g:  out = g * dy * act''(x)
+//   swish'' = s (1 - s) (2 + x (1 - 2 s)),  ssp'' = s (1 - s)
+__global__ void act_bwd2_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ g,
+                                int64_t n, int mode, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = x[i], s = sigmoid_f(v);
+  const float d2 = mode == 0 ? s * (1.0f - s) * (2.0f + v * (1.0f - 2.0f * s)) : s * (1.0f - s);
+  out[i] = g[i] * dy[i] * d2;
+}
 // y = a * b (b broadcast over rows when b_rows == 1 is NOT needed here: same shape), y = a + b, y = alpha * a
 __global__ void mul_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n, float* __restrict__ y) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -376,6 +386,14 @@ int dig3d_act_bwd(const float* x, const float* dy, int64_t n, int32_t mode, floa
   DIG3D_REQUIRE(x && dy && dx && (mode == 0 || mode == 1), "act_bwd: bad arguments");
   if (n == 0) return DIG3D_OK;
   act_bwd_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(x, dy, n, mode, dx);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_act_bwd2(const float* x, const float* dy, const float* g, int64_t n, int32_t mode, float* out, void* stream) {
+  DIG3D_REQUIRE(x && dy && g && out && (mode == 0 || mode == 1), "act_bwd2: bad arguments");
+  if (n == 0) return DIG3D_OK;
+  act_bwd2_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(x, dy, g, n, mode, out);
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
 }

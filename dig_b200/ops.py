@@ -797,3 +797,34 @@ def linear_tc(x, weight, bias=None, transposed=False, want_act=False):
     call("dig3d_linear_tc", _p(x, F32, "x", 16), rows, k, nout, _p(packed), _p(bias, F32, "bias"), _p(y), _p(act_out),
          _stream())
     return (y, act_out) if want_act else y
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# second order (force training, SchNet)
+def act_bwd2(x, dy, g, mode):
+    out = torch.empty_like(x)
+    if x.numel():
+        call("dig3d_act_bwd2", _p(x, F32, "x"), _p(dy, F32, "dy"), _p(g, F32, "g"), x.numel(), mode, _p(out), _stream())
+    return out
+
+
+def edge_dist_bwd2(pos, g, ddist, g_dpos):
+    """-> (d_ddist [E], d_pos [N,3]) of edge_dist_bwd given g_dpos = d(loss)/d(dpos)."""
+    d_ddist = torch.zeros(g.n_edges, device=pos.device, dtype=F32)
+    d_pos = torch.zeros_like(pos)
+    if g.n_edges:
+        call("dig3d_edge_dist_bwd2", _p(pos, F32, "pos"), _p(g.src), _p(g.dst), _p(g.dist), _p(ddist, F32, "ddist"),
+             _p(g_dpos, F32, "g_dpos"), g.n_edges, _p(d_ddist), _p(d_pos), _stream())
+    return d_ddist, d_pos
+
+
+def schnet_edge_features_bwd2(dist, offset, coeff, cutoff, dgauss, dcut, g):
+    """-> (d_dgauss [E,G], d_dcut [E], d_dist [E]) of schnet_edge_features_bwd given g = d(loss)/d(ddist)."""
+    e, ng = dist.numel(), offset.numel()
+    d_dg = torch.empty(e, ng, device=dist.device, dtype=F32)
+    d_dc = torch.empty(e, device=dist.device, dtype=F32)
+    d_d = torch.empty(e, device=dist.device, dtype=F32)
+    if e:
+        call("dig3d_schnet_edge_features_bwd2", _p(dist, F32, "dist"), e, _p(offset, F32), ng, float(coeff), float(cutoff),
+             _p(dgauss, F32), _p(dcut, F32), _p(g, F32, "g"), _p(d_dg), _p(d_dc), _p(d_d), _stream())
+    return d_dg, d_dc, d_d

@@ -8,6 +8,7 @@ import torch
 from torch import nn
 
 from ... import autograd as ag
+from ... import autograd_dd
 from ... import ops
 from ._common import require_cuda, wants_grad
 
@@ -136,19 +137,21 @@ class SchNet(nn.Module):
     def _forward_train(self, z, pos, g):
         """Differentiable forward (reference schnet.py:149-168 op for op) over dig_b200.autograd's primitives;
         used whenever autograd is recording, i.e. by run.train."""
-        # forces (run.py:126,165: autograd.grad(out, pos)): dist carries the position gradient
-        dist = ag.geometry(pos, g, 1) if pos.requires_grad else g.dist
-        gauss, cut = ag.schnet_edge_features(dist, self.dist_emb.offset, self.dist_emb.coeff, self.cutoff)
-        v = ag.gather_rows(self.init_v.weight, z)
+        # forces (run.py:126,165: autograd.grad(out, pos)): dist carries the position gradient.  Training ON forces
+        # differentiates that backward once more: use the twice-differentiable Functions (autograd_dd) then.
+        P = autograd_dd if (pos.requires_grad and any(p.requires_grad for p in self.parameters())) else ag
+        dist = P.geometry(pos, g, 1) if pos.requires_grad else g.dist
+        gauss, cut = P.schnet_edge_features(dist, self.dist_emb.offset, self.dist_emb.coeff, self.cutoff)
+        v = P.gather_rows(self.init_v.weight, z)
         for ue, uv in zip(self.update_es, self.update_vs):
             # update_e (schnet.py:29-35): W = mlp(dist_emb) * C ; e = lin(v)[j] * W
-            w = ag.lin(ue.mlp[2], ag.ssp(ag.lin(ue.mlp[0], gauss)))
-            w = ag.rowscale(w, cut)
-            e = ag.mul(ag.gather_rows(ag.lin(ue.lin, v), g.src), w)
+            w = P.lin(ue.mlp[2], P.ssp(P.lin(ue.mlp[0], gauss)))
+            w = P.rowscale(w, cut)
+            e = P.mul(P.gather_rows(P.lin(ue.lin, v), g.src), w)
             # update_v (schnet.py:54-60): scatter over the target node, lin1, ssp, lin2, residual
-            out = ag.segment_sum(e, g.row_ptr, g.dst)
-            out = ag.lin(uv.lin2, ag.ssp(ag.lin(uv.lin1, out)))
-            v = ag.add(v, out)
+            out = P.segment_sum(e, g.row_ptr, g.dst)
+            out = P.lin(uv.lin2, P.ssp(P.lin(uv.lin1, out)))
+            v = P.add(v, out)
         # update_u (schnet.py:77-82)
-        node_out = ag.lin(self.update_u.lin2, ag.ssp(ag.lin(self.update_u.lin1, v)))
-        return ag.segment_sum(node_out, g.graph_ptr, g.batch)
+        node_out = P.lin(self.update_u.lin2, P.ssp(P.lin(self.update_u.lin1, v)))
+        return P.segment_sum(node_out, g.graph_ptr, g.batch)

@@ -372,6 +372,16 @@ int dig3d_tc_pack_t(const float* const* weights, const int32_t* n, const int32_t
 int dig3d_linear_tc_supported(int32_t k, int32_t nout);
 int dig3d_linear_tc(const float* x, int64_t rows, int32_t k, int32_t nout, const float* packed, const float* bias,
                     float* y, float* act_out, void* stream);
+/* ---- second order, for training ON forces (run.py:110-123: loss.backward() through forces taken with create_graph=True);
+ * built for the ops SchNet uses.  act_bwd2: out = g * dy * act''(x).  edge_dist_bwd2 / schnet_edge_features_bwd2: the
+ * backward of the corresponding *_bwd entry points w.r.t. all their inputs (d_pos accumulated with atomics into a
+ * caller-initialised buffer; d_dgauss / d_dcut / dgauss / dcut nullable). */
+int dig3d_act_bwd2(const float* x, const float* dy, const float* g, int64_t n, int32_t mode, float* out, void* stream);
+int dig3d_edge_dist_bwd2(const float* pos, const int32_t* src, const int32_t* dst, const float* dist, const float* ddist,
+                         const float* g_dpos, int64_t n_edges, float* d_ddist, float* d_pos, void* stream);
+int dig3d_schnet_edge_features_bwd2(const float* dist, int64_t n_edges, const float* offset, int32_t n_gauss,
+                                    double coeff, double cutoff, const float* dgauss, const float* dcut, const float* g,
+                                    float* d_dgauss, float* d_dcut, float* d_dist, void* stream);
 /* out[cols, rows] = in[rows, cols]^T (weights for the input-gradient GEMM dx = dy W) */
 int dig3d_transpose(const float* in, int32_t rows, int32_t cols, float* out, void* stream);
 /* SchNet training path: gaussian smearing gauss[E, n_gauss] (schnet.py:92-94) and cosine cutoff cut[E]

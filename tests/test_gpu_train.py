@@ -318,18 +318,70 @@ def test_force_path_parameter_gradients_still_match():
     _grad_compare(model, sd, lambda s, *a: restated.dimenetpp_forward(s, *a, cutoff=5.0), z, pos.clone(), batch, target)
 
 
-def test_run_val_energy_and_force_and_force_training_raises():
+def test_run_val_energy_and_force_and_force_training():
+    """run.val with forces (SchNet); run.train ON forces works for SchNet (twice-differentiable Functions) and raises
+    loudly for the models without a second-order path instead of silently dropping the force term."""
     from dig_b200.data import DataLoader, synthetic_molecules
     from dig_b200.threedgraph.evaluation import ThreeDEvaluator
-    from dig_b200.threedgraph.method import SchNet, run
+    from dig_b200.threedgraph.method import DimeNetPP, SchNet, run
     dev = torch.device("cuda:0")
     mols = synthetic_molecules(8, "md17-aspirin", seed=3)
+    torch.manual_seed(0)
     model = SchNet(energy_and_force=True, num_layers=2, hidden_channels=32, num_filters=32, cutoff=5.0).to(dev)
     mae = run().val(model, DataLoader(mols, 4, shuffle=False), True, 100, ThreeDEvaluator(), dev)
     assert np.isfinite(mae)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    opt = torch.optim.Adam(model.parameters(), lr=2e-3)
+    losses = [run().train(model, opt, DataLoader(mols, 4, shuffle=False), True, 100, torch.nn.L1Loss(), dev)
+              for _ in range(6)]
+    assert np.isfinite(losses).all() and losses[-1] < losses[0], losses
+    dpp = DimeNetPP(energy_and_force=True).to(dev)
     with pytest.raises(NotImplementedError, match="double"):
-        run().train(model, opt, DataLoader(mols, 4, shuffle=False), True, 100, torch.nn.L1Loss(), dev)
+        run().train(dpp, torch.optim.Adam(dpp.parameters(), lr=1e-3), DataLoader(mols, 4, shuffle=False), True, 100,
+                    torch.nn.L1Loss(), dev)
+
+
+def test_schnet_force_training_gradients_match_oracle():
+    """d/d(parameters) of  L1(E, y) + p * L1(F, f)  with F = -dE/dpos taken with create_graph=True (run.py:110-123):
+    the second backward through the twice-differentiable Functions (dig_b200/autograd_dd.py) vs torch.autograd over the
+    oracle restatement."""
+    from dig_b200.threedgraph.method import SchNet
+    from oracle import restated
+    dev = torch.device("cuda:0")
+    _, z, pos, batch = case_inputs("schnet_cfg1", dev)
+    model = SchNet(energy_and_force=True, num_layers=2, hidden_channels=32, num_filters=32, cutoff=10.0)
+    sd = formula_state_dict(model.state_dict(), seed=1)
+    model.load_state_dict(sd)
+    model = model.to(dev)
+    gen = torch.Generator().manual_seed(12)
+    y = torch.randn(16, 1, generator=gen).to(dev)
+    f_t = torch.randn(pos.size(0), 3, generator=gen).to(dev)
+    p_w = 100.0
+
+    def total_loss(energy, position):
+        force = -torch.autograd.grad(energy, position, grad_outputs=torch.ones_like(energy), create_graph=True,
+                                     retain_graph=True)[0]
+        return torch.nn.functional.l1_loss(energy, y) + p_w * torch.nn.functional.l1_loss(force, f_t), force
+
+    b = _batch(z, pos.clone(), batch)
+    out = model(b)
+    loss, force = total_loss(out, b.pos)
+    assert force.requires_grad
+    loss.backward()
+    sd_ref = {k: v.to(dev).clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    pos2 = pos.clone().requires_grad_(True)
+    ref = restated.schnet_forward(sd_ref, z, pos2, batch, cutoff=10.0, num_layers=2)
+    ref_loss, ref_force = total_loss(ref, pos2)
+    ref_loss.backward()
+    assert rel_err(force.detach().cpu().numpy(), ref_force.detach().cpu().numpy()) < FTOL
+    assert abs(loss.item() - ref_loss.item()) < 1e-5 * abs(ref_loss.item())
+    bad = {}
+    for name, prm in model.named_parameters():
+        r = sd_ref[name].grad
+        assert prm.grad is not None and r is not None, name
+        err = rel_err(prm.grad.cpu().numpy(), r.cpu().numpy())
+        if err > 2e-4:
+            bad[name] = err
+    assert not bad, bad
 
 
 @pytest.mark.parametrize("name", ["spherenet_qm9", "spherenet_ns3"])
