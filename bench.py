@@ -162,8 +162,8 @@ def other_configs(dev):
     inference forward, the energy+force forward where the config asks for forces, and one training step, so that every
     configured mode has a measured number.  Errors are reported in the JSON, not swallowed."""
     import torch
-    from dig_b200.data import synthetic_batch
-    from dig_b200.threedgraph.method import ComENet, DimeNetPP, SchNet
+    from dig_b200.data import synthetic_batch, synthetic_proteins
+    from dig_b200.threedgraph.method import ComENet, DimeNetPP, ProNet, SchNet
 
     def time_ms(fn, n=10, warm=3):
         for _ in range(warm):
@@ -183,13 +183,19 @@ def other_configs(dev):
              ("cfg3 DimeNet++ 4-block h=128, MD17-aspirin-shape batch=256, energy+force",
               lambda f: DimeNetPP(energy_and_force=f, cutoff=5.0), dict(nmol=256, shape="md17-aspirin", seed=3), True),
              ("cfg4 ComENet 4-layer h=256, OC20-IS2RE-shape batch=64, cutoff 6.0",
-              lambda f: ComENet(cutoff=6.0), dict(nmol=64, shape="oc20-is2re", seed=4), False)]
+              lambda f: ComENet(cutoff=6.0), dict(nmol=64, shape="oc20-is2re", seed=4), False),
+             ("next row (SURVEY 8f-1): ProNet aminoacid level, 32 synthetic proteins x ~100 residues, cutoff 10 "
+              "(generic primitives, no fused block kernels yet)",
+              lambda f: ProNet(level="aminoacid"), dict(protein=True, nmol=32), False)]
     out = []
     for name, make, data_kw, forces in cases:
         rec = {"config": name}
         try:
             torch.manual_seed(7)
-            b = synthetic_batch(**data_kw).to(dev)
+            if data_kw.get("protein"):
+                b = synthetic_proteins(data_kw["nmol"], length=100, seed=5).to(dev)
+            else:
+                b = synthetic_batch(**data_kw).to(dev)
             nmol = data_kw["nmol"]
             model = make(False).to(dev)
 

@@ -12,7 +12,7 @@ from torch.autograd.function import once_differentiable
 
 from . import ops
 
-SWISH, SSP = 0, 1
+SWISH, SSP, RELU = 0, 1, 2
 
 
 def _c(t):
@@ -219,6 +219,10 @@ def swish(x):
 
 def ssp(x):
     return _Act.apply(x, SSP)
+
+
+def relu(x):
+    return _Act.apply(x, RELU)
 
 
 def mul(a, b):

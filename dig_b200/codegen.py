@@ -176,6 +176,7 @@ CONFIGS = {
     "dimenet_7_6": ("dimenet", 7, 6),      # SphereNet / DimeNet++ defaults
     "dimenet_3_6": ("dimenet", 3, 6),      # SphereNet notebook example (ns=3)
     "gemnet_2_3": ("gemnet", 2, 3),        # ComENet defaults
+    "gemnet_2_6": ("gemnet", 2, 6),        # ProNet defaults (pronet/features.py is comenet/features.py with nr = 6)
 }
 
 

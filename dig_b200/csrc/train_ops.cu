@@ -165,13 +165,14 @@ static void launch_wgrad(const float* dy, const float* x, int64_t rows, int nout
 // ------------------------------------------------------------------ elementwise
 __device__ __forceinline__ float sigmoid_f(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
 
-// mode 0: swish (x * sigmoid(x)); mode 1: shifted softplus (softplus(x) - ln 2)
+// mode 0: swish (x * sigmoid(x)); mode 1: shifted softplus (softplus(x) - ln 2); mode 2: relu (pronet.py:340,464)
 __global__ void act_fwd_kernel(const float* __restrict__ x, int64_t n, int mode, float* __restrict__ y) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float v = x[i];
   y[i] = mode == 0 ? __fmul_rn(v, sigmoid_f(v))
-                   : __fsub_rn(v > 20.0f ? v : log1pf(expf(v)), 0.693147182464599609375f);
+         : mode == 1 ? __fsub_rn(v > 20.0f ? v : log1pf(expf(v)), 0.693147182464599609375f)
+                     : fmaxf(v, 0.0f);
 }
 // dx = dy * act'(x):  swish' = s (1 + x (1 - s)),  ssp' = sigmoid(x)
 __global__ void act_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, int64_t n, int mode,
@@ -179,7 +180,7 @@ __global__ void act_bwd_kernel(const float* __restrict__ x, const float* __restr
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float v = x[i], s = sigmoid_f(v);
-  const float d = mode == 0 ? s * (1.0f + v * (1.0f - s)) : s;
+  const float d = mode == 0 ? s * (1.0f + v * (1.0f - s)) : mode == 1 ? s : (v > 0.0f ? 1.0f : 0.0f);
   dx[i] = dy[i] * d;
 }
 // second order: d/dx of (dy * act'(x)) contracted with g:  out = g * dy * act''(x)
@@ -189,7 +190,7 @@ __global__ void act_bwd2_kernel(const float* __restrict__ x, const float* __rest
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float v = x[i], s = sigmoid_f(v);
-  const float d2 = mode == 0 ? s * (1.0f - s) * (2.0f + v * (1.0f - 2.0f * s)) : s * (1.0f - s);
+  const float d2 = mode == 0 ? s * (1.0f - s) * (2.0f + v * (1.0f - 2.0f * s)) : mode == 1 ? s * (1.0f - s) : 0.0f;
   out[i] = g[i] * dy[i] * d2;
 }
 // y = a * b (b broadcast over rows when b_rows == 1 is NOT needed here: same shape), y = a + b, y = alpha * a
@@ -375,7 +376,7 @@ int dig3d_wgrad(const float* dy, const float* x, int64_t rows, int32_t nout, int
 }
 
 int dig3d_act(const float* x, int64_t n, int32_t mode, float* y, void* stream) {
-  DIG3D_REQUIRE(x && y && (mode == 0 || mode == 1), "act: bad arguments");
+  DIG3D_REQUIRE(x && y && mode >= 0 && mode <= 2, "act: bad arguments");
   if (n == 0) return DIG3D_OK;
   act_fwd_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, mode, y);
   DIG3D_LAUNCH_CHECK();
@@ -383,7 +384,7 @@ int dig3d_act(const float* x, int64_t n, int32_t mode, float* y, void* stream) {
 }
 
 int dig3d_act_bwd(const float* x, const float* dy, int64_t n, int32_t mode, float* dx, void* stream) {
-  DIG3D_REQUIRE(x && dy && dx && (mode == 0 || mode == 1), "act_bwd: bad arguments");
+  DIG3D_REQUIRE(x && dy && dx && mode >= 0 && mode <= 2, "act_bwd: bad arguments");
   if (n == 0) return DIG3D_OK;
   act_bwd_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(x, dy, n, mode, dx);
   DIG3D_LAUNCH_CHECK();
@@ -391,7 +392,7 @@ int dig3d_act_bwd(const float* x, const float* dy, int64_t n, int32_t mode, floa
 }
 
 int dig3d_act_bwd2(const float* x, const float* dy, const float* g, int64_t n, int32_t mode, float* out, void* stream) {
-  DIG3D_REQUIRE(x && dy && g && out && (mode == 0 || mode == 1), "act_bwd2: bad arguments");
+  DIG3D_REQUIRE(x && dy && g && out && mode >= 0 && mode <= 2, "act_bwd2: bad arguments");
   if (n == 0) return DIG3D_OK;
   act_bwd2_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(x, dy, g, n, mode, out);
   DIG3D_LAUNCH_CHECK();

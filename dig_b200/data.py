@@ -139,3 +139,40 @@ def synthetic_molecules(nmol, shape="qm9", seed=0, natoms=None, variable=False, 
 
 def synthetic_batch(nmol, shape="qm9", seed=0, **kw):
     return collate(synthetic_molecules(nmol, shape, seed, **kw))
+
+
+def synthetic_proteins(nprot, length=60, seed=0, variable=True):
+    """Seeded protein-shaped batch for ProNet (reference pronet.py:365-372 reads `.x .coords_ca .coords_n .coords_c
+    .bb_embs .side_chain_embs .batch`): a C-alpha random walk with 3.8 A steps, N / C atoms ~1.45 / 1.52 A from it,
+    amino-acid types in [0, 26), backbone / side-chain torsion embeddings as sin / cos pairs."""
+    gen = torch.Generator().manual_seed(seed)
+    parts = {k: [] for k in ("x", "coords_ca", "coords_n", "coords_c", "bb_embs", "side_chain_embs")}
+    sizes = []
+    for _ in range(nprot):
+        n = length
+        if variable:
+            n = int(torch.randint(max(4, length // 2), length + length // 2 + 1, (1,), generator=gen))
+        step = torch.randn(n, 3, generator=gen)
+        step = 3.8 * step / step.norm(dim=1, keepdim=True)
+        ca = torch.cumsum(step, 0)
+        # keep the walk compact (fold it back towards the origin) so that the 10 A radius graph is not a chain
+        ca = ca * (6.0 * n ** (1.0 / 3.0) / ca.norm(dim=1).max().clamp_min(1.0))
+
+        def offset(r):
+            v = torch.randn(n, 3, generator=gen)
+            return r * v / v.norm(dim=1, keepdim=True)
+        parts["coords_ca"].append(ca)
+        parts["coords_n"].append(ca + offset(1.45))
+        parts["coords_c"].append(ca + offset(1.52))
+        parts["x"].append(torch.randint(0, 26, (n, 1), generator=gen))
+        ang = (torch.rand(n, 3, generator=gen) * 2 - 1) * math.pi
+        parts["bb_embs"].append(torch.cat([torch.sin(ang), torch.cos(ang)], 1))
+        ang = (torch.rand(n, 4, generator=gen) * 2 - 1) * math.pi
+        parts["side_chain_embs"].append(torch.cat([torch.sin(ang), torch.cos(ang)], 1))
+        sizes.append(n)
+    out = Batch(**{k: torch.cat(v, 0) for k, v in parts.items()})
+    sz = torch.tensor(sizes, dtype=torch.long)
+    out.batch = torch.repeat_interleave(torch.arange(nprot), sz)
+    out.num_graphs = nprot
+    out.y = torch.randn(nprot, generator=gen)
+    return out

@@ -828,3 +828,23 @@ def schnet_edge_features_bwd2(dist, offset, coeff, cutoff, dgauss, dcut, g):
         call("dig3d_schnet_edge_features_bwd2", _p(dist, F32, "dist"), e, _p(offset, F32), ng, float(coeff), float(cutoff),
              _p(dgauss, F32), _p(dcut, F32), _p(g, F32, "g"), _p(d_dg), _p(d_dc), _p(d_d), _stream())
     return d_dg, d_dc, d_d
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# ProNet
+def pronet_edge_features(g, pos_ca, pos_n, pos_c, level, cutoff, num_pos_emb, want_angles=False):
+    """-> (feature0 [E,24], feature1 [E,12|36], pos_emb [E,P], dist [E], angles [E,5] | None); level 0 = aminoacid,
+    1 = backbone / allatom."""
+    e = g.n_edges
+    dev = pos_ca.device
+    n_ang = 1 if level == 0 else 3
+    f0 = torch.empty(e, 24, device=dev, dtype=F32)
+    f1 = torch.empty(e, 12 * n_ang, device=dev, dtype=F32)
+    pe = torch.empty(e, num_pos_emb, device=dev, dtype=F32)
+    dist = torch.empty(e, device=dev, dtype=F32)
+    ang = torch.empty(e, 5, device=dev, dtype=F32) if want_angles else None
+    if e:
+        call("dig3d_pronet_edge_features", _p(pos_ca, F32, "coords_ca"), _p(pos_n, F32, "coords_n"),
+             _p(pos_c, F32, "coords_c"), _p(g.src), _p(g.dst), e, g.n_nodes, int(level), float(cutoff), int(num_pos_emb),
+             _p(dist), _p(f0), _p(f1), _p(pe), _p(ang), _stream())
+    return f0, f1, pe, dist, ang

@@ -288,7 +288,8 @@ int dig3d_comenet_block(const float* x_in, const float* feature1, const float* f
  * kernel and torch.autograd only records the tape, see dig_b200/autograd.py).  All fp32, row-major.
  *   linear:  y[rows,nout] = x[rows,k] w[nout,k]^T (+ bias)           nn.Linear (torch F.linear)
  *   wgrad:   dw[nout,k] += dy^T x ; db[nout] += colsum(dy) (db nullable); dw/db must be initialised by caller
- *   act:     mode 0 swish (spherenet.py:14), mode 1 shifted softplus (schnet.py:97-103); act_bwd: dx = dy*act'(x)
+ *   act:     mode 0 swish (spherenet.py:14), mode 1 shifted softplus (schnet.py:97-103), mode 2 relu (pronet.py:340);
+ *            act_bwd: dx = dy*act'(x)
  *   ewise:   op 0 y = a*b, op 1 y = a+b ; rowscale: y[r,:] = a[r,:] * s[r]
  *   gather_rows: y[r,:] = x[idx[r],:] ; scatter_add_rows: out[idx[r],:] += y[r,:] (atomics; out initialised) */
 int dig3d_linear(const float* x, int64_t rows, int32_t k, int32_t nout, const float* w, const float* bias, float* y,
@@ -382,6 +383,14 @@ int dig3d_edge_dist_bwd2(const float* pos, const int32_t* src, const int32_t* ds
 int dig3d_schnet_edge_features_bwd2(const float* dist, int64_t n_edges, const float* offset, int32_t n_gauss,
                                     double coeff, double cutoff, const float* dgauss, const float* dcut, const float* g,
                                     float* d_dgauss, float* d_dcut, float* d_dist, void* stream);
+/* ProNet (pronet.py:352-449, pronet/features.py:253-344): per-edge geometry from the C-alpha chain (sequence-neighbour
+ * references), level 0 = aminoacid (feature1[E,12] from tau), level 1 = backbone / allatom (feature1[E,36] from the three
+ * Euler angles of the N-CA-C frames; needs pos_n / pos_c); feature0[E,24] = d_theta_phi_emb, pos_emb[E,num_pos_emb];
+ * dist[E] and angles[E,5] = (theta, phi, a1, a2, a3) are optional outputs (nullable). */
+int dig3d_pronet_edge_features(const float* pos_ca, const float* pos_n, const float* pos_c, const int32_t* src,
+                               const int32_t* dst, int64_t n_edges, int64_t n_nodes, int32_t level, double cutoff,
+                               int32_t num_pos_emb, float* dist, float* feature0, float* feature1, float* pos_emb,
+                               float* angles, void* stream);
 /* out[cols, rows] = in[rows, cols]^T (weights for the input-gradient GEMM dx = dy W) */
 int dig3d_transpose(const float* in, int32_t rows, int32_t cols, float* out, void* stream);
 /* SchNet training path: gaussian smearing gauss[E, n_gauss] (schnet.py:92-94) and cosine cutoff cut[E]

@@ -372,3 +372,116 @@ def comenet_forward(sd, z, pos, batch, *, cutoff=8.0, num_layers=4, num_radial=3
         return energy, dict(edge_index=edge_index, dist=dist, theta=theta, phi=phi, tau=tau,
                             feature1=f1, feature2=f2)
     return energy
+
+
+# ----------------------------------------------------------------------------- ProNet
+def pronet_geometry(pos, pos_n, pos_c, edge_index, level):
+    """dist, theta, phi and tau (aminoacid) or the three Euler angles (backbone / allatom); pronet.py:383-449."""
+    j, i = edge_index
+    n = pos.size(0)
+    dist = (pos[i] - pos[j]).norm(dim=1)
+    refi0, refi1 = (i - 1) % n, (i + 1) % n
+    a = ((pos[j] - pos[i]) * (pos[refi0] - pos[i])).sum(dim=-1)
+    b = torch.cross(pos[j] - pos[i], pos[refi0] - pos[i], dim=-1).norm(dim=-1)
+    theta = torch.atan2(b, a)
+    plane1 = torch.cross(pos[refi0] - pos[i], pos[refi1] - pos[i], dim=-1)
+    plane2 = torch.cross(pos[refi0] - pos[i], pos[j] - pos[i], dim=-1)
+    a = (plane1 * plane2).sum(dim=-1)
+    b = (torch.cross(plane1, plane2, dim=-1) * (pos[refi0] - pos[i])).sum(dim=-1) / ((pos[refi0] - pos[i]).norm(dim=-1))
+    phi = torch.atan2(b, a)
+    if level == "aminoacid":
+        refi = (i - 1) % n
+        refj0 = (j - 1) % n
+        refj = (j - 1) % n
+        refj1 = (j + 1) % n
+        mask = refi0 == j
+        refi[mask] = refi1[mask]
+        mask = refj0 == i
+        refj[mask] = refj1[mask]
+        plane1 = torch.cross(pos[j] - pos[i], pos[refi] - pos[i], dim=-1)
+        plane2 = torch.cross(pos[j] - pos[i], pos[refj] - pos[j], dim=-1)
+        a = (plane1 * plane2).sum(dim=-1)
+        b = (torch.cross(plane1, plane2, dim=-1) * (pos[j] - pos[i])).sum(dim=-1) / dist
+        return dist, theta, phi, [torch.atan2(b, a)]
+    or1_x = pos_n[i] - pos[i]
+    or1_z = torch.cross(or1_x, torch.cross(or1_x, pos_c[i] - pos[i], dim=-1), dim=-1)
+    or1_len = or1_z.norm(dim=1) + 1e-7
+    or2_x = pos_n[j] - pos[j]
+    or2_z = torch.cross(or2_x, torch.cross(or2_x, pos_c[j] - pos[j], dim=-1), dim=-1)
+    or2_len = or2_z.norm(dim=1) + 1e-7
+    nn_ = torch.cross(or1_z, or2_z, dim=-1)
+    angle1 = torch.atan2((torch.cross(or1_x, nn_, dim=-1) * or1_z).sum(dim=-1) / or1_len, (or1_x * nn_).sum(dim=-1))
+    angle2 = torch.atan2(torch.cross(or1_z, or2_z, dim=-1).norm(dim=-1), (or1_z * or2_z).sum(dim=-1))
+    angle3 = torch.atan2((torch.cross(nn_, or2_x, dim=-1) * or2_z).sum(dim=-1) / or2_len, (nn_ * or2_x).sum(dim=-1))
+    return dist, theta, phi, [angle1, angle2, angle3]
+
+
+def pronet_pos_emb(edge_index, num_pos_emb=16):                              # pronet.py:352-362
+    import numpy as np
+    d = edge_index[0] - edge_index[1]
+    frequency = torch.exp(torch.arange(0, num_pos_emb, 2, dtype=torch.float32, device=edge_index.device)
+                          * -(np.log(10000.0) / num_pos_emb))
+    angles = d.unsqueeze(-1) * frequency
+    return torch.cat((torch.cos(angles), torch.sin(angles)), -1)
+
+
+def pronet_features(dist, theta, phi, angles, cutoff, ns=2, nr=6):
+    """feature0 = d_theta_phi_emb(dist, theta, phi) [E, nr*ns^2]; feature1 = cat of d_angle_emb(dist, a) [E, nr*ns] per
+    angle (pronet/features.py:253-344: the ComENet closed forms with num_radial = 6)."""
+    bs = basis(f"pronet_{ns}_{nr}", ns, nr)
+    rbf = bs.rbf(dist, cutoff)
+    ylm = torch.stack([torch.zeros_like(theta) + bs.ylm_const] + [fn(theta, phi) for fn in bs.ylm], dim=1)
+    degree = torch.arange(ns, device=dist.device) * 2 + 1
+    r = rbf.view(-1, ns, nr).repeat_interleave(degree, dim=1).view(-1, ns ** 2 * nr)
+    f0 = r * ylm.repeat_interleave(nr, dim=1)
+    f1 = []
+    for ang in angles:
+        y0 = torch.stack([torch.zeros_like(ang) + bs.y0_const] + [fn(ang) for fn in bs.yl0], dim=1)
+        f1.append((rbf.view(-1, ns, nr) * y0.view(-1, ns, 1)).view(-1, ns * nr))
+    return f0, torch.cat(f1, 1)
+
+
+def pronet_forward(sd, data, *, level="aminoacid", cutoff=10.0, num_blocks=4, int_emb_layers=3, out_layers=2,
+                   num_pos_emb=16, max_num_neighbors=32, num_radial=6, num_spherical=2, return_intermediates=False):
+    """ProNet.forward (pronet.py:364-469), dropout 0, no noise."""
+    z = torch.squeeze(data.x.long())
+    pos, batch = data.coords_ca, data.batch
+    if level == "aminoacid":
+        x = F.embedding(z, sd["embedding.weight"])
+    else:
+        feats = [F.one_hot(z, num_classes=26).float(), data.bb_embs]
+        if level == "allatom":
+            feats.append(data.side_chain_embs)
+        x = _lin(sd, "embedding", torch.cat(feats, dim=1))
+    edge_index = radius_graph(pos, cutoff, batch, max_num_neighbors=max_num_neighbors)
+    pe = pronet_pos_emb(edge_index, num_pos_emb)
+    j, i = edge_index
+    dist, theta, phi, angles = pronet_geometry(pos, data.coords_n, data.coords_c, edge_index, level)
+    f0, f1 = pronet_features(dist, theta, phi, angles, cutoff, num_spherical, num_radial)
+    n = z.size(0)
+    for b in range(num_blocks):                                              # InteractionBlock.forward, pronet.py:222-253
+        p = f"interaction_blocks.{b}"
+        x1 = swish(_lin(sd, p + ".lin_1", x))
+        x2 = swish(_lin(sd, p + ".lin_2", x))
+        hs = []
+        for c, feat in ((0, f0), (1, f1), (2, pe)):
+            w = _lin(sd, f"{p}.lin_feature{c}.lin2", _lin(sd, f"{p}.lin_feature{c}.lin1", feat))
+            agg = torch.zeros_like(x1).index_add_(0, i, w * x1[j])
+            h = _lin(sd, f"{p}.conv{c}.lin_l", agg) + _lin(sd, f"{p}.conv{c}.lin_r", x1)
+            hs.append(swish(_lin(sd, f"{p}.lin{c}", h)))
+        h = torch.cat(hs, 1)
+        for l in range(int_emb_layers):
+            h = swish(_lin(sd, f"{p}.lins_cat.{l}", h))
+        h = h + x2
+        for l in range(int_emb_layers - 1):
+            h = swish(_lin(sd, f"{p}.lins.{l}", h))
+        x = _lin(sd, p + ".final", h)
+    num_graphs = int(batch.max()) + 1
+    y = shim.scatter(x, batch, dim=0, dim_size=num_graphs)
+    for l in range(out_layers - 1):
+        y = torch.relu(_lin(sd, f"lins_out.{l}", y))
+    y = _lin(sd, "lin_out", y)
+    if return_intermediates:
+        return y, dict(edge_index=edge_index, dist=dist, theta=theta, phi=phi, angles=angles, feature0=f0, feature1=f1,
+                       pos_emb=pe)
+    return y

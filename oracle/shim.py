@@ -269,6 +269,17 @@ class MessagePassing(torch.nn.Module):
         super().__init__()
         self.aggr = aggr
 
+    def propagate(self, edge_index, size=None, **kwargs):
+        """torch_geometric 2.1 MessagePassing.propagate for a dense edge_index, flow source_to_target, as ProNet's
+        EdgeGraphConv uses it (pronet.py:136): x_j = x[0][edge_index[0]], message(x_j, edge_weight), `aggr` over the
+        target edge_index[1]."""
+        x = kwargs["x"]
+        x_src = x[0] if isinstance(x, (tuple, list)) else x
+        x_dst = x[1] if isinstance(x, (tuple, list)) else x
+        msg = self.message(x_src[edge_index[0]], kwargs.get("edge_weight"))
+        reduce = {"add": "sum"}.get(self.aggr, self.aggr)
+        return scatter(msg, edge_index[1], dim=0, dim_size=x_dst.size(0), reduce=reduce)
+
 
 class GraphConv(MessagePassing):
     """torch_geometric.nn.GraphConv(in, out, aggr='add', bias=True) with an overridable

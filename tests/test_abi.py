@@ -121,3 +121,25 @@ def test_wants_grad_switch():
     assert not wants_grad(m)
     m.energy_and_force = True              # forces need the differentiable path even with frozen parameters
     assert wants_grad(m)
+
+
+def test_pronet_state_dict_contract():
+    """ProNet ("next" row): parameter names / shapes equal the real reference's (golden state_shapes.json,
+    written by oracle/gen_golden_pronet.py) for the three levels; parameter count of the default model."""
+    import json
+    from dig_b200.threedgraph.method import ProNet
+    with open(os.path.join(ROOT, "tests", "golden", "state_shapes.json")) as fh:
+        shapes = json.load(fh)
+    seen = 0
+    for key, want in shapes.items():
+        if not key.startswith("ProNet"):
+            continue
+        ctor = json.loads(key[len("ProNet"):])
+        got = {k: list(v.shape) for k, v in ProNet(**ctor).state_dict().items()}
+        assert got == want, key
+        seen += 1
+    assert seen == 3
+    assert ProNet().num_params == 1383937
+    for bad in (dict(dropout=0.1), dict(euler_noise=True), dict(num_radial=3), dict(level="residue")):
+        with pytest.raises((NotImplementedError, ValueError)):
+            ProNet(**bad)

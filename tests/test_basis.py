@@ -14,7 +14,8 @@ with open(os.path.join(GOLDEN, "basis_formulas.json")) as _fh:
 
 @pytest.mark.parametrize("tag,flavor,ns,nr", [("spherenet_7_6", "dimenet", 7, 6),
                                              ("spherenet_3_6", "dimenet", 3, 6),
-                                             ("comenet_2_3", "gemnet", 2, 3)])
+                                             ("comenet_2_3", "gemnet", 2, 3),
+                                             ("pronet_2_6", "gemnet", 2, 6)])
 def test_generator_reproduces_reference_formulas(tag, flavor, ns, nr):
     """dig_b200/basis.py must emit exactly the strings the reference's sympy code lambdifies."""
     mine = basis.basis_sources(flavor, ns, nr)
