@@ -1,0 +1,70 @@
+"""CPU tests of the dataset readers against the pins of the reference's own tests
+(test/threedgraph/dataset/test_QM93D.py:11-34, test_MD17.py:8-18) on small npz files written with the reference's keys."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from dig_b200.data import DataLoader
+from dig_b200.threedgraph.dataset import MD17, QM93D
+from dig_b200.threedgraph.dataset.datasets import QM9_TARGETS
+
+
+def _write_qm9(root, sizes, seed=0):
+    rng = np.random.default_rng(seed)
+    os.makedirs(os.path.join(root, "qm9", "raw"))
+    n = np.asarray(sizes)
+    data = {"N": n, "R": rng.normal(size=(int(n.sum()), 3)), "Z": rng.integers(1, 10, size=int(n.sum()))}
+    for t in QM9_TARGETS:
+        data[t] = rng.normal(size=len(sizes))
+    np.savez(os.path.join(root, "qm9", "raw", "qm9_eV.npz"), **data)
+    return data
+
+
+def test_qm93d_reader_matches_reference_contract(tmp_path):
+    raw = _write_qm9(str(tmp_path), [5, 4, 7, 3, 9, 6])
+    ds = QM93D(root=str(tmp_path))
+    ds.data.y = ds.data['U0']                                  # the reference's usage (PygQM93D.py:44-45)
+    assert len(ds) == 6 and repr(ds) == 'QM93D(6)'
+    m = ds[0]
+    assert len(vars(m)) == 15                                  # test_QM93D.py:16: pos, z, y + 12 targets
+    assert m.y.size() == (1,) and m.z.size() == (5,) and m.pos.size() == (5, 3) and m.Cv.size() == (1,)
+    assert m.z.dtype == torch.int64 and m.pos.dtype == torch.float32
+    assert float(m.y) == pytest.approx(float(raw['U0'][0]), rel=1e-6)
+    assert torch.equal(ds[2].pos, torch.tensor(raw['R'][9:16], dtype=torch.float32))
+    split = ds.get_idx_split(len(ds.data.y), train_size=3, valid_size=2, seed=42)
+    sub = ds[split['train']]
+    assert len(sub) == 3 and torch.equal(sub[1].z, ds[int(split['train'][1])].z)
+    assert len(sub[torch.tensor([2, 0])]) == 2 and torch.equal(sub[torch.tensor([2, 0])][0].z, sub[2].z)
+    batch = next(iter(DataLoader(sub, batch_size=3, shuffle=False)))
+    want_atoms = sum(int(raw['N'][int(i)]) for i in split['train'])
+    assert batch.z.shape == (want_atoms,) and batch.pos.shape == (want_atoms, 3) and batch.y.shape == (3,)
+    assert batch.batch.shape == (want_atoms,) and batch.num_graphs == 3 and batch.mu.shape == (3,)
+    with pytest.raises(FileNotFoundError, match="no network"):
+        QM93D(root=str(tmp_path / "nowhere"))
+
+
+def test_split_indices_equal_the_reference_test_pins():
+    """test_QM93D.py:30-33 and test_MD17.py:15-18 pin the first index of each split for seed 42 on the real dataset sizes;
+    the split only depends on (size, seed), so it can be checked without the data."""
+    ds = object.__new__(QM93D)
+    s = ds.get_idx_split(130831, train_size=1000, valid_size=10000, seed=42)
+    assert int(s['train'][0]) == 112526 and int(s['valid'][0]) == 120798 and int(s['test'][0]) == 107901
+    assert len(s['train']) == 1000 and len(s['valid']) == 10000 and len(s['test']) == 130831 - 11000
+
+
+def test_md17_reader(tmp_path):
+    rng = np.random.default_rng(1)
+    os.makedirs(os.path.join(tmp_path, "aspirin", "raw"))
+    frames, atoms = 12, 21
+    raw = {"E": rng.normal(size=(frames, 1)), "F": rng.normal(size=(frames, atoms, 3)),
+           "R": rng.normal(size=(frames, atoms, 3)), "z": rng.integers(1, 9, size=atoms)}
+    np.savez(os.path.join(tmp_path, "aspirin", "raw", "aspirin_dft.npz"), **raw)
+    ds = MD17(root=str(tmp_path), name='aspirin')
+    assert len(ds) == frames and repr(ds) == 'MD17(12)'
+    m = ds[3]
+    assert len(vars(m)) == 4 and m.z.size() == (21,) and m.pos.size() == (21, 3) and m.force.size() == (21, 3)
+    assert m.y.size() == (1,) and torch.equal(m.force, torch.tensor(raw['F'][3], dtype=torch.float32))
+    batch = next(iter(DataLoader(ds[torch.arange(4)], batch_size=4)))
+    assert batch.force.shape == (84, 3) and batch.y.shape == (4,) and batch.num_graphs == 4
