@@ -19,17 +19,10 @@ def radius_graph(x, r, batch=None, loop=False, max_num_neighbors=32, flow='sourc
     return g.edge_index
 
 
-def xyz_to_dat(pos, edge_index, num_nodes, use_torsion=False):
-    """(dist, angle[, torsion], i, j, idx_kj, idx_ji) exactly as the reference returns them.
-
-    `edge_index` must be sorted by (target, source) -- what `radius_graph` returns; the reference also
-    accepts arbitrary order (SparseTensor sorts internally), which is not implemented here."""
-    if edge_index.dim() != 2 or edge_index.size(0) != 2:
-        raise ValueError("edge_index must be [2, E]")
+def _xyz_to_dat_sorted(pos, ei, n, use_torsion):
+    """Kernel path for an edge_index sorted by (target, source); returns None when it is not sorted."""
     dev = pos.device
-    e = edge_index.size(1)
-    n = int(num_nodes)
-    ei = edge_index.contiguous()
+    e = ei.size(1)
     g = ops.Graph3D()
     g.n_nodes, g.n_edges = n, e
     g.src = torch.empty(max(e, 1), dtype=torch.int32, device=dev)[:e]
@@ -43,13 +36,53 @@ def xyz_to_dat(pos, edge_index, num_nodes, use_torsion=False):
          _p(g.src), _p(g.dst), _p(g.row_ptr), _p(ws), _p(g.trip_ptr), _p(g.dist), _p(flags), _stream())
     fl = flags.tolist()
     if fl[0] & 1:
-        raise NotImplementedError("xyz_to_dat: edge_index must be sorted by (target, source) with valid node ids "
-                                  "(as produced by radius_graph)")
+        return None
     if fl[0] & 2:
         raise NotImplementedError("xyz_to_dat: in-degree above 64 is not supported by the geometry kernel")
     g.n_triplets = int(fl[3])
     ops.triplet_geometry(g, pos, use_torsion=use_torsion, want_idx=False, want_idx64=True)
+    return g
+
+
+def xyz_to_dat(pos, edge_index, num_nodes, use_torsion=False):
+    """(dist, angle[, torsion], i, j, idx_kj, idx_ji) exactly as the reference returns them
+    (utils/geometric_computing.py:12-80).
+
+    An `edge_index` sorted by (target, source) -- what `radius_graph` returns -- goes straight to the kernels.  Any other
+    order is handled like the reference's SparseTensor does: the edges are sorted (stable, by target then source), the
+    kernels run on the sorted list, and the results are mapped back: `dist` in the caller's edge order, triplets grouped
+    by the caller's edge order with k ascending inside a group, `idx_kj` / `idx_ji` holding the caller's edge ids (the
+    re-ordering is index plumbing with torch; all geometry is computed by the kernels)."""
+    if edge_index.dim() != 2 or edge_index.size(0) != 2:
+        raise ValueError("edge_index must be [2, E]")
+    e = edge_index.size(1)
+    n = int(num_nodes)
+    ei = edge_index.contiguous()
     j, i = ei[0], ei[1]
+    if e and (int(ei.min()) < 0 or int(ei.max()) >= n):
+        raise ValueError("xyz_to_dat: edge_index holds node ids outside [0, num_nodes)")
+    g = _xyz_to_dat_sorted(pos, ei, n, use_torsion)
+    if g is not None:
+        if use_torsion:
+            return g.dist, g.angle, g.torsion, i, j, g.idx_kj64, g.idx_ji64
+        return g.dist, g.angle, i, j, g.idx_kj64, g.idx_ji64
+    # arbitrary edge order
+    perm = torch.sort(i * n + j, stable=True).indices                  # sorted position -> caller's edge id
+    g = _xyz_to_dat_sorted(pos, ei[:, perm].contiguous(), n, use_torsion)
+    if g is None:
+        raise RuntimeError("xyz_to_dat: internal error, sorted edge list rejected")
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(e, device=perm.device)                    # caller's edge id -> sorted position
+    tp = g.trip_ptr.long()
+    cnt = (tp[1:] - tp[:-1])[inv]                                      # triplets per edge, caller's order
+    start = tp[:-1][inv]
+    t = int(cnt.sum())
+    first = torch.cumsum(cnt, 0) - cnt
+    take = torch.repeat_interleave(start - first, cnt) + torch.arange(t, device=perm.device)
+    dist = g.dist[inv]
+    angle = g.angle[take]
+    idx_kj = perm[g.idx_kj64[take]]
+    idx_ji = torch.repeat_interleave(torch.arange(e, device=perm.device), cnt)
     if use_torsion:
-        return g.dist, g.angle, g.torsion, i, j, g.idx_kj64, g.idx_ji64
-    return g.dist, g.angle, i, j, g.idx_kj64, g.idx_ji64
+        return dist, angle, g.torsion[take], i, j, idx_kj, idx_ji
+    return dist, angle, i, j, idx_kj, idx_ji

@@ -222,6 +222,7 @@ def test_comenet_energy_parity():
 def test_xyz_to_dat_api_matches_reference_outputs():
     """The utility API with the reference's signature (utils/geometric_computing.py:12) vs the fixture
     written by the real reference and vs the notebook known-answer."""
+    from oracle import restated
     from dig_b200.threedgraph.utils import xyz_to_dat, radius_graph
     dev = torch.device("cuda:0")
     g, z, pos, batch = case_inputs("spherenet_qm9", dev)
@@ -236,8 +237,25 @@ def test_xyz_to_dat_api_matches_reference_outputs():
     out = xyz_to_dat(torch.from_numpy(nb["pos"]).to(dev), torch.from_numpy(nb["edge_index"]).to(dev), 4, use_torsion=True)
     assert out[5].tolist() == [2, 4, 1, 3] and out[6].tolist() == [0, 2, 3, 5]
     assert np.array_equal(out[2].cpu().numpy(), nb["torsion"])
-    with pytest.raises(NotImplementedError):
-        xyz_to_dat(pos, ei.flip(1), z.size(0))
+    # arbitrary edge order (the reference's SparseTensor sorts internally): fixture written by the real reference
+    un = load_golden("xyz_to_dat_unsorted")
+    pos_u, ei_u = torch.from_numpy(un["pos"]).to(dev), torch.from_numpy(un["edge_index"]).to(dev)
+    got = xyz_to_dat(pos_u, ei_u, pos_u.size(0), use_torsion=True)
+    assert np.array_equal(got[5].cpu().numpy(), un["idx_kj"]) and np.array_equal(got[6].cpu().numpy(), un["idx_ji"])
+    assert rel_err(got[0].cpu().numpy(), un["dist"]) < 5e-7 and rel_err(got[1].cpu().numpy(), un["angle"]) < 5e-7
+    # torsion: the CPU fixture differs in the self-candidate coin flips; check it against the kernels'
+    # own (bit-exact-tested) sorted result instead: the same (k->j, j->i) pair must carry the same value
+    order = torch.sort(ei_u[1] * pos_u.size(0) + ei_u[0], stable=True).indices
+    srt = xyz_to_dat(pos_u, ei_u[:, order].contiguous(), pos_u.size(0), use_torsion=True)
+    e_n = ei_u.size(1)
+    key_s = order[srt[6]] * e_n + order[srt[5]]
+    key_u = got[6] * e_n + got[5]
+    ps, pu = torch.argsort(key_s), torch.argsort(key_u)
+    assert torch.equal(key_s[ps], key_u[pu]) and torch.equal(srt[2][ps], got[2][pu]) and torch.equal(srt[1][ps], got[1][pu])
+    close = np.abs(got[2].cpu().numpy() - un["torsion"]) < 1e-3
+    assert close.mean() > 0.9
+    with pytest.raises(ValueError):
+        xyz_to_dat(pos, ei + z.size(0), z.size(0))
 
 
 def test_run_val_on_the_fused_path():

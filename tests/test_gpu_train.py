@@ -462,3 +462,27 @@ def test_training_path_on_tensor_cores_opt_in(monkeypatch):
         assert any("_dig3d_packed" in p.__dict__ for p in model.parameters())      # the tensor path really ran
         del model
     assert ops.tc_timeouts() == 0
+
+
+def test_run_run_end_to_end(tmp_path, capsys):
+    """run().run(...) as in the reference notebook (threedgraph.ipynb cell 11 / run.py:20-101): two epochs on synthetic
+    molecules, checkpoint written with the reference's keys, printed summary lines."""
+    from dig_b200.data import synthetic_molecules
+    from dig_b200.threedgraph.evaluation import ThreeDEvaluator
+    from dig_b200.threedgraph.method import SchNet, run
+    dev = torch.device("cuda:0")
+    mols = synthetic_molecules(24, natoms=8, seed=2)
+    for m in mols:
+        m.y = torch.tensor([float(m.z.sum()) * 0.05])
+    torch.manual_seed(0)
+    model = SchNet(num_layers=2, hidden_channels=32, num_filters=32, cutoff=5.0)
+    run().run(dev, mols[:16], mols[16:20], mols[20:], model, loss_func=torch.nn.L1Loss(), evaluation=ThreeDEvaluator(),
+              epochs=2, batch_size=8, vt_batch_size=4, lr=1e-3, lr_decay_factor=0.5, lr_decay_step_size=1,
+              save_dir=str(tmp_path / "ckpt"), log_dir='')
+    out = capsys.readouterr().out
+    assert "#Params: 15393" in out and "=====Epoch 2" in out and "Best validation MAE so far" in out
+    ckpt = torch.load(str(tmp_path / "ckpt" / "valid_checkpoint.pt"), weights_only=False)
+    assert set(ckpt) == {'epoch', 'model_state_dict', 'optimizer_state_dict', 'scheduler_state_dict', 'best_valid_mae',
+                         'num_params'}
+    fresh = SchNet(num_layers=2, hidden_channels=32, num_filters=32, cutoff=5.0)
+    fresh.load_state_dict(ckpt['model_state_dict'])
