@@ -250,6 +250,11 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # keep stdout to the one JSON line: some environments export NCCL_DEBUG=VERSION, which makes NCCL print its
+        # version banner on stdout at communicator creation
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     import __graft_entry__
     if rank == 0:
