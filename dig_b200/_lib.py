@@ -91,8 +91,8 @@ SIGNATURES = {
     "dig3d_comenet_embed": [P, P, c_int64, P, P],
     "dig3d_comenet_block": [P, P, P, P, P, P, P, c_int64, c_int64, c_int64, POINTER(ComenetBlockWeights),
                             POINTER(ComenetHeadWeights), c_int32, P, P, P, P, P, P, P, P],
-    "dig3d_linear": [P, c_int64, c_int32, c_int32, P, P, P, P, P],
-    "dig3d_wgrad": [P, P, c_int64, c_int32, c_int32, P, P, P],
+    "dig3d_linear": [P, c_int64, c_int32, c_int32, P, P, P, P, c_int32, P],
+    "dig3d_wgrad": [P, P, c_int64, c_int32, c_int32, P, P, c_int32, P],
     "dig3d_act": [P, c_int64, c_int32, P, P],
     "dig3d_act_bwd": [P, P, c_int64, c_int32, P, P],
     "dig3d_ewise": [P, P, c_int64, c_int32, P, P],

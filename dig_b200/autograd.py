@@ -87,6 +87,39 @@ class _LinearSwish(torch.autograd.Function):
         return dx, dw, db
 
 
+class _GroupedLinear(torch.autograd.Function):
+    """G independent linears of the same shape in one launch: y[g] = (swish?)(x[g] W[g]^T + b[g]).  Used for the node MLPs of
+    all interaction blocks at once (2304 rows each: latency-bound one at a time)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act):
+        x, w = _c(x), _c(weight.detach())
+        b = None if bias is None else _c(bias.detach())
+        ctx.has_bias, ctx.act = bias is not None, act
+        if act:
+            pre, y = ops.linear(x, w, b, want_act=True)
+            ctx.save_for_backward(x, w, pre)
+            return y
+        ctx.save_for_backward(x, w)
+        return ops.linear(x, w, b)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        if ctx.act:
+            x, w, pre = ctx.saved_tensors
+            dpre = ops.act_bwd(pre, _c(dy), SWISH)
+        else:
+            x, w = ctx.saved_tensors
+            dpre = _c(dy)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.linear(dpre, w.transpose(1, 2).contiguous(), None)       # the transposed copy is plumbing
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw, db = ops.wgrad(dpre, x, tuple(w.shape), ctx.has_bias)
+        return dx, dw, db, None
+
+
 class _Act(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, mode):
@@ -211,6 +244,15 @@ def lin(module, x):
 def lin_swish(module, x):
     """swish(module(x)) with the activation fused into the linear's epilogue."""
     return _LinearSwish.apply(x, module.weight, getattr(module, "bias", None))
+
+
+def grouped_lin(modules, x, act=False):
+    """[m(x[g]) for g, m in enumerate(modules)] as ONE launch; x [G, rows, K] -> [G, rows, N].  The per-module parameters are
+    stacked with torch.stack (a copy; its backward hands every module its slice of the stacked gradient)."""
+    w = torch.stack([m.weight for m in modules])
+    biases = [getattr(m, "bias", None) for m in modules]
+    b = torch.stack(biases) if biases[0] is not None else None
+    return _GroupedLinear.apply(x, w, b, act)
 
 
 def swish(x):

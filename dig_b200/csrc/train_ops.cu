@@ -31,6 +31,14 @@ linear_tiled_kernel(const float* __restrict__ x, int rows_total, const float* __
                     const float* __restrict__ bias, float* __restrict__ y, float* __restrict__ act_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LinSmem<NOUT, K>& s = *reinterpret_cast<LinSmem<NOUT, K>*>(smem_raw);
+  {   // grouped call: blockIdx.y selects one of `groups` independent (x, w, bias, y) problems of the same shape
+    const size_t gi = blockIdx.y;
+    x += gi * (size_t)rows_total * K;
+    w += gi * (size_t)NOUT * K;
+    if (bias) bias += gi * NOUT;
+    y += gi * (size_t)rows_total * NOUT;
+    if (act_out) act_out += gi * (size_t)rows_total * NOUT;
+  }
   const int r0 = blockIdx.x * 64, rows = min(64, rows_total - r0);
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
   tile_load<K>(s.a, K + 4, x + (size_t)r0 * K, K, rows);
@@ -58,8 +66,16 @@ linear_tiled_kernel(const float* __restrict__ x, int rows_total, const float* __
 __global__ void linear_naive_kernel(const float* __restrict__ x, int64_t rows, int k, int nout,
                                     const float* __restrict__ w, const float* __restrict__ bias,
                                     float* __restrict__ y, float* __restrict__ act_out) {
-  const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= rows * nout) return;
+  {
+    const size_t gi = blockIdx.y;
+    x += gi * (size_t)rows * k;
+    w += gi * (size_t)nout * k;
+    if (bias) bias += gi * nout;
+    y += gi * (size_t)rows * nout;
+    if (act_out) act_out += gi * (size_t)rows * nout;
+  }
   const int64_t r = id / nout;
   const int c = (int)(id % nout);
   const float* xr = x + r * k;
@@ -79,16 +95,24 @@ __global__ void linear_naive_kernel(const float* __restrict__ x, int64_t rows, i
 template <int BN, int BK>
 __global__ void __launch_bounds__(256)
 wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x, int64_t rows, int nout, int k,
-             float* __restrict__ dw, float* __restrict__ db) {
+             float* __restrict__ dw, float* __restrict__ db, int splits) {
   constexpr int RC = 32, MN = BN / 16, MK = BK / 16, LDN = BN + 4, LDK = BK + 4;
+  const int split = blockIdx.z % splits;
+  {   // grouped call: blockIdx.z = group * splits + split
+    const size_t gi = blockIdx.z / splits;
+    dy += gi * (size_t)rows * nout;
+    x += gi * (size_t)rows * k;
+    dw += gi * (size_t)nout * k;
+    if (db) db += gi * nout;
+  }
   constexpr int EN = RC * BN / 256, EK = RC * BK / 256;
   __shared__ __align__(16) float sdy[RC * LDN];
   __shared__ __align__(16) float sx[RC * LDK];
   const int kb = blockIdx.x * BK, nb = blockIdx.y * BN;
   const int tk = threadIdx.x & 15, tn = threadIdx.x >> 4;
-  int64_t per = (rows + gridDim.z - 1) / gridDim.z;
+  int64_t per = (rows + splits - 1) / splits;
   per = (per + RC - 1) / RC * RC;
-  const int64_t r_lo = (int64_t)blockIdx.z * per, r_hi = min(rows, r_lo + per);
+  const int64_t r_lo = (int64_t)split * per, r_hi = min(rows, r_lo + per);
   if (r_lo >= r_hi) return;
   float pn[EN], pk[EK];
   auto fetch = [&](int64_t r0) {
@@ -152,14 +176,14 @@ wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x, int64_t 
 
 template <int BN, int BK>
 static void launch_wgrad(const float* dy, const float* x, int64_t rows, int nout, int k, float* dw, float* db,
-                         cudaStream_t st) {
-  const int blocks = ceil_div(k, BK) * ceil_div(nout, BN);
+                         int groups, cudaStream_t st) {
+  const int blocks = ceil_div(k, BK) * ceil_div(nout, BN) * groups;
   int64_t splits = 592 / blocks;                       // ~4 CTAs per SM in total
   const int64_t max_splits = (rows + 63) / 64;         // at least two 32-row chunks per CTA
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
-  dim3 grid(ceil_div(k, BK), ceil_div(nout, BN), (unsigned)splits);
-  wgrad_kernel<BN, BK><<<grid, 256, 0, st>>>(dy, x, rows, nout, k, dw, db);
+  dim3 grid(ceil_div(k, BK), ceil_div(nout, BN), (unsigned)(splits * groups));
+  wgrad_kernel<BN, BK><<<grid, 256, 0, st>>>(dy, x, rows, nout, k, dw, db, (int)splits);
 }
 
 // ------------------------------------------------------------------ elementwise
@@ -326,12 +350,12 @@ __global__ void graphnorm_bwd_kernel(const float* __restrict__ h, const float* _
 
 template <int NOUT, int K>
 static int launch_linear_tiled(const float* x, int64_t rows, const float* w, const float* b, float* y, float* act_out,
-                               cudaStream_t st) {
+                               int groups, cudaStream_t st) {
   auto kfn = linear_tiled_kernel<NOUT, K>;
   const size_t sm = sizeof(LinSmem<NOUT, K>);
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (e != cudaSuccess) { set_error("linear: cudaFuncSetAttribute(%zu): %s", sm, cudaGetErrorString(e)); return DIG3D_ECUDA; }
-  kfn<<<ceil_div(rows, 64), DT, sm, st>>>(x, (int)rows, w, b, y, act_out);
+  kfn<<<dim3(ceil_div(rows, 64), groups), DT, sm, st>>>(x, (int)rows, w, b, y, act_out);
   return DIG3D_OK;
 }
 
@@ -342,19 +366,19 @@ using namespace dig3d;
 extern "C" {
 
 int dig3d_linear(const float* x, int64_t rows, int32_t k, int32_t nout, const float* w, const float* bias, float* y,
-                 float* act_out, void* stream) {
-  DIG3D_REQUIRE(x && w && y && k > 0 && nout > 0, "linear: bad arguments");
+                 float* act_out, int32_t groups, void* stream) {
+  DIG3D_REQUIRE(x && w && y && k > 0 && nout > 0 && groups >= 1 && groups <= 65535, "linear: bad arguments");
   if (rows == 0) return DIG3D_OK;
   cudaStream_t st = (cudaStream_t)stream;
   int rc = -100;
-#define DIG3D_LT(NO, KK) if (nout == NO && k == KK) rc = launch_linear_tiled<NO, KK>(x, rows, w, bias, y, act_out, st);
+#define DIG3D_LT(NO, KK) if (nout == NO && k == KK) rc = launch_linear_tiled<NO, KK>(x, rows, w, bias, y, act_out, groups, st);
   DIG3D_LT(128, 128) DIG3D_LT(64, 128) DIG3D_LT(128, 64) DIG3D_LT(256, 128) DIG3D_LT(256, 256) DIG3D_LT(128, 256)
   DIG3D_LT(128, 384) DIG3D_LT(32, 32) DIG3D_LT(64, 64) DIG3D_LT(128, 32) DIG3D_LT(32, 128) DIG3D_LT(256, 64)
   DIG3D_LT(64, 256) DIG3D_LT(256, 512) DIG3D_LT(384, 128) DIG3D_LT(512, 256)
 #undef DIG3D_LT
   if (rc == -100) {
     const int64_t total = rows * nout;
-    linear_naive_kernel<<<ceil_div(total, 256), 256, 0, st>>>(x, rows, k, nout, w, bias, y, act_out);
+    linear_naive_kernel<<<dim3(ceil_div(total, 256), groups), 256, 0, st>>>(x, rows, k, nout, w, bias, y, act_out);
     rc = DIG3D_OK;
   }
   if (rc) return rc;
@@ -363,14 +387,14 @@ int dig3d_linear(const float* x, int64_t rows, int32_t k, int32_t nout, const fl
 }
 
 int dig3d_wgrad(const float* dy, const float* x, int64_t rows, int32_t nout, int32_t k, float* dw, float* db,
-                void* stream) {
-  DIG3D_REQUIRE(dy && x && dw && nout > 0 && k > 0, "wgrad: bad arguments");
+                int32_t groups, void* stream) {
+  DIG3D_REQUIRE(dy && x && dw && nout > 0 && k > 0 && groups >= 1 && groups <= 64, "wgrad: bad arguments");
   if (rows == 0) return DIG3D_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (nout > 16 && k > 16) launch_wgrad<64, 64>(dy, x, rows, nout, k, dw, db, st);
-  else if (nout > 16) launch_wgrad<64, 16>(dy, x, rows, nout, k, dw, db, st);
-  else if (k > 16) launch_wgrad<16, 64>(dy, x, rows, nout, k, dw, db, st);
-  else launch_wgrad<16, 16>(dy, x, rows, nout, k, dw, db, st);
+  if (nout > 16 && k > 16) launch_wgrad<64, 64>(dy, x, rows, nout, k, dw, db, groups, st);
+  else if (nout > 16) launch_wgrad<64, 16>(dy, x, rows, nout, k, dw, db, groups, st);
+  else if (k > 16) launch_wgrad<16, 64>(dy, x, rows, nout, k, dw, db, groups, st);
+  else launch_wgrad<16, 16>(dy, x, rows, nout, k, dw, db, groups, st);
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
 }

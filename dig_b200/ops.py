@@ -492,34 +492,40 @@ def _idx(t, name="index"):
 
 
 def linear(x, weight, bias=None, want_act=False):
-    """y = x weight^T + bias for x [..., K] (nn.Linear); want_act: also swish(y) from the same kernel."""
-    if x.numel() == 0:                       # empty edge / triplet sets (isolated atoms): nothing to launch
-        y = torch.zeros(x.shape[:-1] + (weight.size(0),), device=x.device, dtype=torch.float32)
-        return (y, y.clone()) if want_act else y
+    """y = x weight^T + bias for x [..., K] (nn.Linear); want_act: also swish(y) from the same kernel.
+    Grouped form: weight [G, N, K] (3-D) with x [G, rows, K] and bias [G, N]: G independent linears in one launch."""
+    groups = weight.size(0) if weight.dim() == 3 else 1
     k = x.size(-1)
-    nout = weight.size(0)
-    if weight.dim() != 2 or weight.size(1) != k:
+    nout = weight.size(-2)
+    if weight.dim() not in (2, 3) or weight.size(-1) != k:
         raise ValueError(f"linear: weight {tuple(weight.shape)} does not match input width {k}")
-    rows = x.numel() // k if k else 0
+    if groups > 1 or weight.dim() == 3:
+        if x.dim() != 3 or x.size(0) != groups or (bias is not None and tuple(bias.shape) != (groups, nout)):
+            raise ValueError(f"grouped linear: x {tuple(x.shape)}, weight {tuple(weight.shape)} do not agree")
+    if x.numel() == 0:                       # empty edge / triplet sets (isolated atoms): nothing to launch
+        y = torch.zeros(x.shape[:-1] + (nout,), device=x.device, dtype=torch.float32)
+        return (y, y.clone()) if want_act else y
+    rows = x.numel() // k // groups
     y = torch.empty(x.shape[:-1] + (nout,), device=x.device, dtype=F32)
     act_out = torch.empty_like(y) if want_act else None
     call("dig3d_linear", _p(x, F32, "x"), rows, k, nout, _p(weight, F32, "weight"), _p(bias, F32, "bias"),
-         _p(y), _p(act_out), _stream())
+         _p(y), _p(act_out), groups, _stream())
     return (y, act_out) if want_act else y
 
 
 def wgrad(dy, x, weight_shape, want_bias):
-    """(dW, db) of y = x W^T + b given dy."""
+    """(dW, db) of y = x W^T + b given dy; weight_shape (N, K) or, grouped, (G, N, K) with dy [G,rows,N], x [G,rows,K]."""
+    groups = weight_shape[0] if len(weight_shape) == 3 else 1
+    nout, k = weight_shape[-2], weight_shape[-1]
+    lead = (groups,) if len(weight_shape) == 3 else ()
+    dev = x.device
+    buf = torch.zeros(groups * nout * k + (groups * nout if want_bias else 0), device=dev, dtype=F32)   # one fill
+    dw = buf[:groups * nout * k].view(lead + (nout, k))
+    db = buf[groups * nout * k:].view(lead + (nout,)) if want_bias else None
     if x.numel() == 0:
-        dev = x.device
-        return (torch.zeros(*weight_shape, device=dev, dtype=torch.float32),
-                torch.zeros(weight_shape[0], device=dev, dtype=torch.float32) if want_bias else None)
-    nout, k = weight_shape
-    rows = x.numel() // k
-    buf = torch.zeros(nout * k + (nout if want_bias else 0), device=x.device, dtype=F32)     # one fill for both
-    dw = buf[:nout * k].view(nout, k)
-    db = buf[nout * k:] if want_bias else None
-    call("dig3d_wgrad", _p(dy, F32, "dy"), _p(x, F32, "x"), rows, nout, k, _p(dw), _p(db), _stream())
+        return dw, db
+    rows = x.numel() // k // groups
+    call("dig3d_wgrad", _p(dy, F32, "dy"), _p(x, F32, "x"), rows, nout, k, _p(dw), _p(db), groups, _stream())
     return dw, db
 
 

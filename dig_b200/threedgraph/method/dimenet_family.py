@@ -266,13 +266,15 @@ class _DimeNetFamily(nn.Module):
 
 
     # ------------------------------------------------------------------ training path
-    def _update_v_train(self, m, e2, g):
-        """update_v.forward, reference spherenet.py:209-216."""
-        v = ag.segment_sum(e2, g.row_ptr, g.dst)
-        v = ag.lin(m.lin_up, v)
-        for lin in m.lins:
-            v = ag.lin_swish(lin, v)
-        return ag.lin(m.lin, v)
+    def _update_v_train(self, mods, e2_list, g):
+        """update_v.forward (reference spherenet.py:209-216) of ALL blocks at once: the node MLPs only feed the readout, so
+        they are deferred to the end of the forward and run as grouped launches (one per layer instead of one per layer
+        and block).  Returns v [G, N, out_channels]."""
+        v = torch.stack([ag.segment_sum(e2, g.row_ptr, g.dst) for e2 in e2_list])        # [G, N, H] (stack = copy)
+        v = ag.grouped_lin([m.lin_up for m in mods], v)
+        for j in range(len(mods[0].lins)):
+            v = ag.grouped_lin([m.lins[j] for m in mods], v, act=True)
+        return ag.grouped_lin([m.lin for m in mods], v)
 
     def _forward_train(self, z, pos, g):
         """Differentiable forward (reference spherenet.py:296-320 / dimenetpp.py:273-293, op for op) over the
@@ -308,8 +310,7 @@ class _DimeNetFamily(nn.Module):
         cat = torch.cat([ag.gather_rows(x, g.dst, g.row_ptr), ag.gather_rows(x, g.src), r0], dim=-1)   # copy only
         e1 = ag.lin_swish(ie.lin, cat)
         e2 = ag.mul(lin(ie.lin_rbf_1, rbf0), e1)
-        v = self._update_v_train(self.init_v, e2, g)
-        u = ag.segment_sum(v, g.graph_ptr, g.batch)
+        e2_list = [e2]
         for l, (ue, uv) in enumerate(zip(self.update_es, self.update_vs)):      # spherenet.py:150-182
             x_ji = ag.lin_swish(ue.lin_ji, e1)
             x_kj = ag.lin_swish(ue.lin_kj, e1)
@@ -325,9 +326,11 @@ class _DimeNetFamily(nn.Module):
             for layer in ue.layers_after_skip:
                 h = ag.add(h, ag.lin_swish(layer.lin2, ag.lin_swish(layer.lin1, h)))
             e1 = h
-            e2 = ag.mul(lin(ue.lin_rbf, rbf0), e1)
-            v = self._update_v_train(uv, e2, g)
-            u = ag.add(u, ag.segment_sum(v, g.graph_ptr, g.batch))
+            e2_list.append(ag.mul(lin(ue.lin_rbf, rbf0), e1))
+        v = self._update_v_train([self.init_v] + list(self.update_vs), e2_list, g)
+        u = ag.segment_sum(v[0], g.graph_ptr, g.batch)                           # u = sum_l scatter(v_l, batch)
+        for l in range(1, v.size(0)):
+            u = ag.add(u, ag.segment_sum(v[l], g.graph_ptr, g.batch))
         return u
 
 

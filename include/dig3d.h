@@ -292,10 +292,13 @@ int dig3d_comenet_block(const float* x_in, const float* feature1, const float* f
  *            act_bwd: dx = dy*act'(x)
  *   ewise:   op 0 y = a*b, op 1 y = a+b ; rowscale: y[r,:] = a[r,:] * s[r]
  *   gather_rows: y[r,:] = x[idx[r],:] ; scatter_add_rows: out[idx[r],:] += y[r,:] (atomics; out initialised) */
+/* groups >= 1: that many independent problems of the same shape stacked along a leading dimension (x [G,rows,k],
+ * w [G,nout,k], bias [G,nout], y [G,rows,nout], dw [G,nout,k], db [G,nout]) in ONE launch -- the five node MLPs of a
+ * SphereNet / DimeNet++ forward are small (2304 rows) and latency-bound one at a time. */
 int dig3d_linear(const float* x, int64_t rows, int32_t k, int32_t nout, const float* w, const float* bias, float* y,
-                 float* act_out /* nullable: also receives swish(y) */, void* stream);
+                 float* act_out /* nullable: also receives swish(y) */, int32_t groups, void* stream);
 int dig3d_wgrad(const float* dy, const float* x, int64_t rows, int32_t nout, int32_t k, float* dw, float* db,
-                void* stream);
+                int32_t groups, void* stream);
 int dig3d_act(const float* x, int64_t n, int32_t mode, float* y, void* stream);
 int dig3d_act_bwd(const float* x, const float* dy, int64_t n, int32_t mode, float* dx, void* stream);
 int dig3d_ewise(const float* a, const float* b, int64_t n, int32_t op, float* y, void* stream);
