@@ -200,13 +200,6 @@ class _DimeNetFamily(nn.Module):
             m.reset_parameters()
 
     # ------------------------------------------------------------------ forward
-    def _side_stream(self, device):
-        streams = self.__dict__.setdefault("_streams", {})
-        key = (device.type, device.index)
-        if key not in streams:
-            streams[key] = torch.cuda.Stream(device=device)
-        return streams[key]
-
     def _projection_rows(self, first, count):
         """Rows [32, C] of lin_sbf1 (and lin_t1) for layers first..first+count-1, zero padded."""
         def rows(name):
