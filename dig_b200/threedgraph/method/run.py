@@ -35,58 +35,71 @@ class run():
     def run(self, device, train_dataset, valid_dataset, test_dataset, model, loss_func, evaluation, epochs=500,
             batch_size=32, vt_batch_size=32, lr=0.0005, lr_decay_factor=0.5, lr_decay_step_size=50, weight_decay=0,
             energy_and_force=False, p=100, save_dir='', log_dir=''):
-        r"""reference run.py:20-101."""
+        r"""Same contract as reference run.py:20-101 (arguments, printed lines, checkpoint contents); organised as
+        loaders / per-epoch step / bookkeeping helpers."""
         model = model.to(device)
-        num_params = sum(p.numel() for p in model.parameters())
+        num_params = sum(q.numel() for q in model.parameters())
         print(f'#Params: {num_params}')
         optimizer = Adam(model.parameters(), lr=lr, weight_decay=weight_decay)
         scheduler = StepLR(optimizer, step_size=lr_decay_step_size, gamma=lr_decay_factor)
-        if parallel.world_size() > 1:       # data parallel: each rank trains on its contiguous shard of the molecules
-            train_dataset = parallel.shard_molecules(train_dataset)
-        train_loader = DataLoader(train_dataset, batch_size, shuffle=True)
-        valid_loader = DataLoader(valid_dataset, vt_batch_size, shuffle=False)
-        test_loader = DataLoader(test_dataset, vt_batch_size, shuffle=False)
-        best_valid = float('inf')
-        best_test = float('inf')
-        if save_dir != '' and not os.path.exists(save_dir):
-            os.makedirs(save_dir)
-        writer = None
-        if log_dir != '':
-            if not os.path.exists(log_dir):
-                os.makedirs(log_dir)
-            from torch.utils.tensorboard import SummaryWriter
-            writer = SummaryWriter(log_dir=log_dir)
-
+        loaders = self._loaders(train_dataset, valid_dataset, test_dataset, batch_size, vt_batch_size)
+        for d in (save_dir, log_dir):
+            if d != '':
+                os.makedirs(d, exist_ok=True)
+        writer = self._open_writer(log_dir)
+        best = {'valid': float('inf'), 'test': float('inf')}
         for epoch in range(1, epochs + 1):
-            print("\n=====Epoch {}".format(epoch), flush=True)
-            print('\nTraining...', flush=True)
-            train_mae = self.train(model, optimizer, train_loader, energy_and_force, p, loss_func, device)
-            print('\n\nEvaluating...', flush=True)
-            valid_mae = self.val(model, valid_loader, energy_and_force, p, evaluation, device)
-            print('\n\nTesting...', flush=True)
-            test_mae = self.val(model, test_loader, energy_and_force, p, evaluation, device)
-            print()
-            print({'Train': train_mae, 'Validation': valid_mae, 'Test': test_mae})
+            maes = self._epoch(epoch, model, optimizer, loaders, energy_and_force, p, loss_func, evaluation, device)
             if writer is not None:
-                writer.add_scalar('train_mae', train_mae, epoch)
-                writer.add_scalar('valid_mae', valid_mae, epoch)
-                writer.add_scalar('test_mae', test_mae, epoch)
-            if valid_mae < best_valid:
-                best_valid = valid_mae
-                best_test = test_mae
+                for key in ('train', 'valid', 'test'):
+                    writer.add_scalar(key + '_mae', maes[key], epoch)
+            if maes['valid'] < best['valid']:
+                best = {'valid': maes['valid'], 'test': maes['test']}
                 if save_dir != '':
-                    print('Saving checkpoint...')
-                    checkpoint = {'epoch': epoch, 'model_state_dict': model.state_dict(),
-                                  'optimizer_state_dict': optimizer.state_dict(),
-                                  'scheduler_state_dict': scheduler.state_dict(), 'best_valid_mae': best_valid,
-                                  'num_params': num_params}
-                    torch.save(checkpoint, os.path.join(save_dir, 'valid_checkpoint.pt'))
+                    self._checkpoint(save_dir, epoch, model, optimizer, scheduler, best['valid'], num_params)
             scheduler.step()
-
-        print(f'Best validation MAE so far: {best_valid}')
-        print(f'Test MAE when got best validation result: {best_test}')
+        print(f"Best validation MAE so far: {best['valid']}")
+        print(f"Test MAE when got best validation result: {best['test']}")
         if writer is not None:
             writer.close()
+
+    @staticmethod
+    def _loaders(train_dataset, valid_dataset, test_dataset, batch_size, vt_batch_size):
+        """Shuffled training loader, ordered validation / test loaders (reference run.py:53-55).  Under a data-parallel
+        launch (one process per GPU) every rank trains on its contiguous shard of the molecules."""
+        if parallel.world_size() > 1:
+            train_dataset = parallel.shard_molecules(train_dataset)
+        return {'train': DataLoader(train_dataset, batch_size, shuffle=True),
+                'valid': DataLoader(valid_dataset, vt_batch_size, shuffle=False),
+                'test': DataLoader(test_dataset, vt_batch_size, shuffle=False)}
+
+    @staticmethod
+    def _open_writer(log_dir):
+        if log_dir == '':
+            return None
+        from torch.utils.tensorboard import SummaryWriter
+        return SummaryWriter(log_dir=log_dir)
+
+    def _epoch(self, epoch, model, optimizer, loaders, energy_and_force, p, loss_func, evaluation, device):
+        """One training pass + validation + test, with the reference's progress lines (run.py:73-80)."""
+        print("\n=====Epoch {}".format(epoch), flush=True)
+        print('\nTraining...', flush=True)
+        maes = {'train': self.train(model, optimizer, loaders['train'], energy_and_force, p, loss_func, device)}
+        for key, banner in (('valid', '\n\nEvaluating...'), ('test', '\n\nTesting...')):
+            print(banner, flush=True)
+            maes[key] = self.val(model, loaders[key], energy_and_force, p, evaluation, device)
+        print()
+        print({'Train': maes['train'], 'Validation': maes['valid'], 'Test': maes['test']})
+        return maes
+
+    @staticmethod
+    def _checkpoint(save_dir, epoch, model, optimizer, scheduler, best_valid, num_params):
+        """valid_checkpoint.pt with the reference's keys (run.py:91-93)."""
+        print('Saving checkpoint...')
+        state = {'epoch': epoch, 'best_valid_mae': best_valid, 'num_params': num_params}
+        for key, obj in (('model', model), ('optimizer', optimizer), ('scheduler', scheduler)):
+            state[key + '_state_dict'] = obj.state_dict()
+        torch.save(state, os.path.join(save_dir, 'valid_checkpoint.pt'))
 
     def train(self, model, optimizer, train_loader, energy_and_force, p, loss_func, device):
         r"""reference run.py:103-135; returns the mean training loss."""

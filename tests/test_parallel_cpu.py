@@ -85,3 +85,33 @@ def test_two_rank_gloo_gradient_allreduce():
     port = 29500 + (os.getpid() % 400)
     mp.spawn(_grad_worker, args=(world, port, ret), nprocs=world, join=True)
     assert all(ret[r] for r in range(world)) and len(ret) == world
+
+
+def test_run_driver_contract_on_cpu(tmp_path, capsys):
+    """run().run(...) (reference run.py:20-101) with a plain torch model on CPU: the host-side driver logic (loaders,
+    epoch loop, printed lines, checkpoint keys, best-validation bookkeeping) does not need the CUDA kernels."""
+    from dig_b200.threedgraph.evaluation import ThreeDEvaluator
+    from dig_b200.threedgraph.method import run
+
+    class Tiny(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.emb = torch.nn.Embedding(10, 4)
+            self.lin = torch.nn.Linear(4, 1)
+
+        def forward(self, b):
+            h = self.lin(self.emb(b.z))
+            return torch.zeros(b.num_graphs, 1).index_add_(0, b.batch, h)
+
+    mols = synthetic_molecules(12, "qm9", seed=1, natoms=5)
+    torch.manual_seed(0)
+    run().run(torch.device("cpu"), mols[:8], mols[8:10], mols[10:], Tiny(), loss_func=torch.nn.L1Loss(),
+              evaluation=ThreeDEvaluator(), epochs=3, batch_size=4, vt_batch_size=2, lr=1e-2, lr_decay_step_size=1,
+              save_dir=str(tmp_path / "ck"), log_dir='')
+    out = capsys.readouterr().out
+    assert "#Params: 45" in out and out.count("=====Epoch") == 3 and "Training..." in out and "Evaluating..." in out
+    assert "Testing..." in out and "'Train':" in out and "Best validation MAE so far:" in out
+    assert "Test MAE when got best validation result:" in out
+    ck = torch.load(str(tmp_path / "ck" / "valid_checkpoint.pt"), weights_only=False)
+    assert set(ck) == {'epoch', 'model_state_dict', 'optimizer_state_dict', 'scheduler_state_dict', 'best_valid_mae',
+                       'num_params'} and ck['num_params'] == 45
