@@ -86,9 +86,10 @@ def allreduce_gradients(parameters):
     else:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
         flat /= world
-    off = 0
+    views, off = [], 0
     for g in grads:
         n = g.numel()
-        g.copy_(flat[off:off + n].view_as(g))
+        views.append(flat[off:off + n].view_as(g))
         off += n
+    torch._foreach_copy_(grads, views)              # one multi-tensor copy instead of ~160 small ones
     return flat.numel() * flat.element_size()
