@@ -114,3 +114,30 @@ def test_restated_matches_live_reference(name):
     mine = restated.dimenet_family_forward(sd, z, pos, batch, torsion=(model_name == "SphereNet"),
                                            cutoff=kw["cutoff"])
     assert torch.equal(ref, mine)
+
+
+@pytest.mark.parametrize("name,ctor,wseed", [
+    ("pronet_aminoacid", dict(level="aminoacid"), 6),
+    ("pronet_backbone", dict(level="backbone", num_blocks=2), 7),
+    ("pronet_allatom", dict(level="allatom", num_blocks=2, out_channels=3, out_layers=3), 8)])
+def test_pronet_oracle_equals_reference_fixture(name, ctor, wseed):
+    """oracle/restated.pronet_forward vs the outputs of the unmodified reference ProNet (fixtures written by
+    oracle/gen_golden_pronet.py): energies, edge list and every geometric feature, bit for bit on CPU fp32."""
+    import json
+    import os
+    from helpers import GOLDEN
+    from dig_b200.data import Batch
+    g = load_golden(name)
+    with open(os.path.join(GOLDEN, "state_shapes.json")) as fh:
+        shapes = json.load(fh)["ProNet" + json.dumps(ctor, sort_keys=True)]
+    sd = formula_state_dict({k: torch.empty(*v) for k, v in shapes.items()}, seed=wseed)
+    b = Batch(**{k: torch.from_numpy(g[k]) for k in ("x", "coords_ca", "coords_n", "coords_c", "bb_embs", "side_chain_embs",
+                                                    "batch")})
+    kw = {k: v for k, v in ctor.items() if k != "out_channels"}
+    with torch.no_grad():
+        y, inter = restated.pronet_forward(sd, b, return_intermediates=True, **kw)
+    assert np.array_equal(inter["edge_index"].numpy(), g["edge_index"])
+    for key in ("dist", "theta", "phi", "feature0", "feature1", "pos_emb"):
+        assert np.array_equal(inter[key].numpy(), g[key]), key
+    assert np.array_equal(y.numpy(), g["energy_f32"])
+    assert sum(int(np.prod(v)) for v in shapes.values()) == int(g["num_params"])
