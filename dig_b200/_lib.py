@@ -119,6 +119,7 @@ SIGNATURES = {
     "dig3d_edge_dist_bwd2": [P, P, P, P, P, P, c_int64, P, P, P],
     "dig3d_schnet_edge_features_bwd2": [P, c_int64, P, c_int32, c_double, c_double, P, P, P, P, P, P, P],
     "dig3d_pronet_edge_features": [P, P, P, P, P, c_int64, c_int64, c_int32, c_double, c_int32, P, P, P, P, P, P],
+    "dig3d_linear_set_config": [c_int32],
     "dig3d_transpose": [P, c_int32, c_int32, P, P],
     "dig3d_schnet_edge_features": [P, c_int64, P, c_int32, c_double, c_double, P, P, P],
 }

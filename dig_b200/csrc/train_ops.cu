@@ -19,18 +19,19 @@
 namespace dig3d {
 
 // ------------------------------------------------------------------ linear, tiled (K % 32 == 0, NOUT in {64,128,256})
-template <int NOUT, int K>
+template <int NOUT, int K, int TM = 64>
 struct LinSmem {
-  float a[64 * (K + 4)];
+  float a[TM * (K + 4)];
   float ws[2 * NOUT * LDW];
 };
 
-template <int NOUT, int K>
-__global__ void __launch_bounds__(DT, 1)
+// TM rows per CTA; MINB = CTAs per SM the register allocation is capped for (2 -> <= 128 registers per thread)
+template <int NOUT, int K, int TM = 64, int MINB = 1>
+__global__ void __launch_bounds__(DT, MINB)
 linear_tiled_kernel(const float* __restrict__ x, int rows_total, const float* __restrict__ w,
                     const float* __restrict__ bias, float* __restrict__ y, float* __restrict__ act_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  LinSmem<NOUT, K>& s = *reinterpret_cast<LinSmem<NOUT, K>*>(smem_raw);
+  LinSmem<NOUT, K, TM>& s = *reinterpret_cast<LinSmem<NOUT, K, TM>*>(smem_raw);
   {   // grouped call: blockIdx.y selects one of `groups` independent (x, w, bias, y) problems of the same shape
     const size_t gi = blockIdx.y;
     x += gi * (size_t)rows_total * K;
@@ -39,17 +40,18 @@ linear_tiled_kernel(const float* __restrict__ x, int rows_total, const float* __
     y += gi * (size_t)rows_total * NOUT;
     if (act_out) act_out += gi * (size_t)rows_total * NOUT;
   }
-  const int r0 = blockIdx.x * 64, rows = min(64, rows_total - r0);
+  constexpr int RP = TM / 16;
+  const int r0 = blockIdx.x * TM, rows = min(TM, rows_total - r0);
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
   tile_load<K>(s.a, K + 4, x + (size_t)r0 * K, K, rows);
-  for (int id = threadIdx.x; id < (64 - rows) * K; id += DT) s.a[(rows + id / K) * (K + 4) + id % K] = 0.f;
+  for (int id = threadIdx.x; id < (TM - rows) * K; id += DT) s.a[(rows + id / K) * (K + 4) + id % K] = 0.f;
   __syncthreads();
-  float acc[4][NOUT / 16];
+  float acc[RP][NOUT / 16];
   zero_acc(acc);
-  gemm_tile<64, NOUT, K>(s.a, K + 4, w, K, s.ws, acc);
+  gemm_tile<TM, NOUT, K>(s.a, K + 4, w, K, s.ws, acc);
 #pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    const int r = ty * 4 + p;
+  for (int p = 0; p < RP; ++p) {
+    const int r = ty * RP + p;
     if (r < rows) {
 #pragma unroll
       for (int q = 0; q < NOUT / 16; ++q) {
@@ -348,16 +350,20 @@ __global__ void graphnorm_bwd_kernel(const float* __restrict__ h, const float* _
   }
 }
 
-template <int NOUT, int K>
+template <int NOUT, int K, int TM = 64, int MINB = 1>
 static int launch_linear_tiled(const float* x, int64_t rows, const float* w, const float* b, float* y, float* act_out,
                                int groups, cudaStream_t st) {
-  auto kfn = linear_tiled_kernel<NOUT, K>;
-  const size_t sm = sizeof(LinSmem<NOUT, K>);
+  auto kfn = linear_tiled_kernel<NOUT, K, TM, MINB>;
+  const size_t sm = sizeof(LinSmem<NOUT, K, TM>);
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (e != cudaSuccess) { set_error("linear: cudaFuncSetAttribute(%zu): %s", sm, cudaGetErrorString(e)); return DIG3D_ECUDA; }
-  kfn<<<dim3(ceil_div(rows, 64), groups), DT, sm, st>>>(x, (int)rows, w, b, y, act_out);
+  kfn<<<dim3(ceil_div(rows, TM), groups), DT, sm, st>>>(x, (int)rows, w, b, y, act_out);
   return DIG3D_OK;
 }
+
+// tuning switch for the dominant shape (128 -> 128 on ~34 k edge rows): 0 = 64-row tiles, 1 CTA/SM by registers;
+// 1 = 64-row tiles capped at 128 registers (2 CTAs/SM); 2 = 128-row tiles
+static int h_lin_cfg = 1;
 
 }  // namespace dig3d
 
@@ -371,7 +377,12 @@ int dig3d_linear(const float* x, int64_t rows, int32_t k, int32_t nout, const fl
   if (rows == 0) return DIG3D_OK;
   cudaStream_t st = (cudaStream_t)stream;
   int rc = -100;
-#define DIG3D_LT(NO, KK) if (nout == NO && k == KK) rc = launch_linear_tiled<NO, KK>(x, rows, w, bias, y, act_out, groups, st);
+  if (nout == 128 && k == 128 && h_lin_cfg == 1) {
+    rc = launch_linear_tiled<128, 128, 64, 2>(x, rows, w, bias, y, act_out, groups, st);
+  } else if (nout == 128 && k == 128 && h_lin_cfg == 2) {
+    rc = launch_linear_tiled<128, 128, 128, 1>(x, rows, w, bias, y, act_out, groups, st);
+  }
+#define DIG3D_LT(NO, KK) if (rc == -100 && nout == NO && k == KK) rc = launch_linear_tiled<NO, KK>(x, rows, w, bias, y, act_out, groups, st);
   DIG3D_LT(128, 128) DIG3D_LT(64, 128) DIG3D_LT(128, 64) DIG3D_LT(256, 128) DIG3D_LT(256, 256) DIG3D_LT(128, 256)
   DIG3D_LT(128, 384) DIG3D_LT(32, 32) DIG3D_LT(64, 64) DIG3D_LT(128, 32) DIG3D_LT(32, 128) DIG3D_LT(256, 64)
   DIG3D_LT(64, 256) DIG3D_LT(256, 512) DIG3D_LT(384, 128) DIG3D_LT(512, 256)
@@ -383,6 +394,12 @@ int dig3d_linear(const float* x, int64_t rows, int32_t k, int32_t nout, const fl
   }
   if (rc) return rc;
   DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_linear_set_config(int32_t cfg) {
+  DIG3D_REQUIRE(cfg >= 0 && cfg <= 2, "linear_set_config: cfg must be 0, 1 or 2");
+  h_lin_cfg = cfg;
   return DIG3D_OK;
 }
 

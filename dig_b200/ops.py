@@ -854,3 +854,8 @@ def pronet_edge_features(g, pos_ca, pos_n, pos_c, level, cutoff, num_pos_emb, wa
              _p(pos_c, F32, "coords_c"), _p(g.src), _p(g.dst), e, g.n_nodes, int(level), float(cutoff), int(num_pos_emb),
              _p(dist), _p(f0), _p(f1), _p(pe), _p(ang), _stream())
     return f0, f1, pe, dist, ang
+
+
+def linear_set_config(cfg):
+    """Tile configuration of the 128 -> 128 training linear (0 / 1 / 2, see include/dig3d.h); experiments only."""
+    call("dig3d_linear_set_config", int(cfg))

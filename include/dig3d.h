@@ -299,6 +299,9 @@ int dig3d_linear(const float* x, int64_t rows, int32_t k, int32_t nout, const fl
                  float* act_out /* nullable: also receives swish(y) */, int32_t groups, void* stream);
 int dig3d_wgrad(const float* dy, const float* x, int64_t rows, int32_t nout, int32_t k, float* dw, float* db,
                 int32_t groups, void* stream);
+/* tile configuration of the 128 -> 128 linear (tuning / experiments): 0 = 64-row tiles, 1 = 64-row tiles with two CTAs
+ * per SM (default), 2 = 128-row tiles */
+int dig3d_linear_set_config(int32_t cfg);
 int dig3d_act(const float* x, int64_t n, int32_t mode, float* y, void* stream);
 int dig3d_act_bwd(const float* x, const float* dy, int64_t n, int32_t mode, float* dx, void* stream);
 int dig3d_ewise(const float* a, const float* b, int64_t n, int32_t op, float* y, void* stream);
