@@ -7,7 +7,9 @@
  *
  * Conventions (all entry points):
  *   - plain pointers + sizes, no torch types; all pointers are DEVICE pointers unless named *_host;
- *   - caller owns every buffer (no allocation, no synchronisation, no global state inside);
+ *   - caller owns every buffer (no allocation, no synchronisation inside; the only process-wide state are the
+ *     experiment switches dig3d_tc_set_fast_swish / dig3d_tc_trace / dig3d_linear_set_config and a thread-local
+ *     error string);
  *   - `stream` is a cudaStream_t passed as void*;
  *   - returns 0 on success, a negative DIG3D_E* code otherwise; dig3d_last_error() returns a
  *     thread-local message for the last failing call;
