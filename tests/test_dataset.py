@@ -68,3 +68,25 @@ def test_md17_reader(tmp_path):
     assert m.y.size() == (1,) and torch.equal(m.force, torch.tensor(raw['F'][3], dtype=torch.float32))
     batch = next(iter(DataLoader(ds[torch.arange(4)], batch_size=4)))
     assert batch.force.shape == (84, 3) and batch.y.shape == (4,) and batch.num_graphs == 4
+
+
+def test_collate_and_synthetic_generators_are_deterministic():
+    """Host-side batch plumbing (dig_b200/data.py): seeded generators reproduce, collate builds the sorted batch vector /
+    ptr, per-graph targets stack, Batch.to / pin-free round trip keeps python attributes."""
+    from dig_b200.data import Batch, collate, synthetic_batch, synthetic_molecules, synthetic_proteins
+    a, b = synthetic_batch(5, "qm9", seed=3, variable=True), synthetic_batch(5, "qm9", seed=3, variable=True)
+    assert torch.equal(a.pos, b.pos) and torch.equal(a.z, b.z) and torch.equal(a.batch, b.batch)
+    assert not torch.equal(a.pos, synthetic_batch(5, "qm9", seed=4, variable=True).pos)
+    mols = synthetic_molecules(4, "md17-aspirin", seed=1)
+    c = collate(mols)
+    assert c.num_graphs == 4 and c.ptr.tolist() == [0, 21, 42, 63, 84] and c.y.shape == (4,) and c.force.shape == (84, 3)
+    assert torch.equal(c.batch, torch.arange(4).repeat_interleave(21))
+    assert c.z[:21].tolist() == [6] * 9 + [8] * 4 + [1] * 8               # aspirin pattern (SURVEY 8d)
+    d = (c.pos[:21].unsqueeze(0) - c.pos[:21].unsqueeze(1)).norm(dim=-1) + torch.eye(21) * 10
+    assert float(d.min()) >= 0.95 - 1e-6                                  # rejection-sampled minimum distance
+    moved = c.to("cpu")
+    assert isinstance(moved, Batch) and moved.num_graphs == 4 and set(moved.keys()) >= {"z", "pos", "batch", "y", "force"}
+    p, q = synthetic_proteins(3, length=20, seed=2), synthetic_proteins(3, length=20, seed=2)
+    assert torch.equal(p.coords_ca, q.coords_ca) and p.x.shape[1] == 1 and p.bb_embs.shape[1] == 6
+    assert p.side_chain_embs.shape[1] == 8 and int(p.x.max()) < 26 and p.batch.numel() == p.x.size(0)
+    assert torch.allclose((p.coords_n - p.coords_ca).norm(dim=1), torch.full((p.x.size(0),), 1.45), atol=1e-4)
