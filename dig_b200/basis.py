@@ -267,6 +267,30 @@ def basis_sources(flavor, num_spherical, num_radial):
     return out
 
 
+@functools.lru_cache(maxsize=None)
+def basis_sources_second_order(flavor, num_spherical, num_radial):
+    """Second derivatives of the closed forms of `basis_sources` (bessel_dxx [ns*nr] in x; yl0_dtheta2 [ns] in theta):
+    what a second-order path through angle_emb needs (training ON forces for DimeNet++: d/dpos of the force goes through
+    d2(basis)/d(dist)2, d2/d(angle)2 and the mixed product of first derivatives, which `basis_sources` already has).
+    Not emitted into the generated headers yet -- no kernel consumes them in this round."""
+    sym = _sym()
+    x, theta = sym.symbols("x"), sym.symbols("theta")
+    if flavor == "dimenet":
+        bess = bessel_expressions(_jn_dimenet, num_spherical, num_radial)
+        y0 = harmonics_dimenet(num_spherical, zero_m_only=True)
+    elif flavor == "gemnet":
+        bess = bessel_expressions(_jn_gemnet, num_spherical, num_radial)
+        y0 = harmonics_gemnet(num_spherical, zero_m_only=True)
+    else:
+        raise ValueError(flavor)
+    out = {"bessel_dxx": [], "yl0_dtheta2": []}
+    for l in range(num_spherical):
+        for n in range(num_radial):
+            out["bessel_dxx"].append(_src(sym.diff(bess[l][n], x, 2), [x]))
+        out["yl0_dtheta2"].append("0.0" if l == 0 else _src(sym.diff(y0[l][0], theta, 2), [theta]))
+    return out
+
+
 def envelope_coefficients(exponent):
     """Smooth cutoff env(x) = 1/x + a x^(p-1) + b x^p + c x^(p+1), p = exponent + 1
     (reference Envelope, features.py:151-164)."""

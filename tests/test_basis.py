@@ -84,3 +84,26 @@ def test_derivative_sources_match_finite_differences(flavor, ns, nr):
                 assert abs(ev(dt, theta=th, phi=ph) - fdt) <= 1e-6 * max(1.0, abs(fdt))
                 assert abs(ev(dp, theta=th, phi=ph) - fdp) <= 1e-6 * max(1.0, abs(fdp))
     assert len(src["bessel_dx"]) == ns * nr and len(src["ylm_dphi"]) == ns * ns
+
+
+def test_second_order_sources_match_finite_differences():
+    """basis_sources_second_order (groundwork for force training through the angular basis): second derivatives vs a
+    central difference of the FIRST-derivative sources, in float64."""
+    import math
+    first = basis.basis_sources("dimenet", 3, 6)
+    second = basis.basis_sources_second_order("dimenet", 3, 6)
+    env = {"sin": math.sin, "cos": math.cos, "sqrt": math.sqrt, "pi": math.pi}
+
+    def ev(s, **kw):
+        return float(eval(s, dict(env, **kw)))
+
+    h = 1e-6
+    for x in (0.37, 0.81):
+        for d1, d2 in zip(first["bessel_dx"], second["bessel_dxx"]):
+            fd = (ev(d1, x=x + h) - ev(d1, x=x - h)) / (2 * h)
+            assert abs(ev(d2, x=x) - fd) <= 2e-5 * max(1.0, abs(fd))
+    for th in (0.5, 2.2):
+        for d1, d2 in zip(first["yl0_dtheta"], second["yl0_dtheta2"]):
+            fd = (ev(d1, theta=th + h) - ev(d1, theta=th - h)) / (2 * h)
+            assert abs(ev(d2, theta=th) - fd) <= 1e-6 * max(1.0, abs(fd))
+    assert len(second["bessel_dxx"]) == 18 and len(second["yl0_dtheta2"]) == 3
