@@ -143,3 +143,28 @@ def test_pronet_state_dict_contract():
     for bad in (dict(dropout=0.1), dict(euler_noise=True), dict(num_radial=3), dict(level="residue")):
         with pytest.raises((NotImplementedError, ValueError)):
             ProNet(**bad)
+
+
+def test_product_never_touches_the_oracle_or_the_reference():
+    """The oracle is test infrastructure: nothing under dig_b200/ (the product) may import oracle/ or read /root/reference;
+    bench.py may only do so in its baseline legs (cpu_baseline / gpu_comparator / --impl reference)."""
+    import glob
+    import re
+    pat = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b)|/root/reference", re.M)
+    offenders = []
+    for path in glob.glob(os.path.join(ROOT, "dig_b200", "**", "*.py"), recursive=True):
+        with open(path) as fh:
+            src = fh.read()
+        # provenance comments / docstrings may NAME reference files; only imports and filesystem paths are forbidden
+        if pat.search(src):
+            offenders.append(os.path.relpath(path, ROOT))
+    assert not offenders, offenders
+    for path in glob.glob(os.path.join(ROOT, "dig_b200", "csrc", "**", "*.cu*"), recursive=True):
+        with open(path) as fh:
+            assert "/root/reference" not in fh.read(), path
+    with open(os.path.join(ROOT, "bench.py")) as fh:
+        bench = fh.read()
+    for m in re.finditer(r"^\s*from oracle import", bench, re.M):
+        ctx = bench[max(0, m.start() - 1500):m.start()]
+        assert any(k in ctx for k in ("cpu_oracle_rate", "run_reference_arm", "gpu_cmp", "GPU comparator")), \
+            "bench.py imports the oracle outside its baseline legs"
