@@ -83,6 +83,14 @@ SIGNATURES = {
     "dig3d_sphere_triplet_gather": [P, P, P, c_int32, P, P, P, P, c_int64, P, P, P, P],
     "dig3d_sphere_update_e_b_tc": [P, P, P, P, P, c_int64, POINTER(TcUpdateE), P, P, P],
     "dig3d_tc_set_fast_swish": [c_int32],
+    "dig3d_h16_packed_bytes": [c_int32, c_int32],
+    "dig3d_h16_pack": [P, P, P, P, c_int32, P],
+    "dig3d_sphere_init_e_h16": [P, P, P, P, c_int64, POINTER(InitEWeights), P, P, P, P],
+    "dig3d_sphere_update_e_a_h16": [P, P, c_int64, POINTER(TcUpdateE), P, P, P],
+    "dig3d_sphere_update_e_b_h16": [P, P, P, P, P, c_int64, POINTER(TcUpdateE), P, P, P],
+    "dig3d_h16_overflow": [c_int32],
+    "dig3d_h16_timeouts": [],
+    "dig3d_h16_set_fast_swish": [c_int32],
     "dig3d_tc_trace": [c_int32, P],
     "dig3d_schnet_block": [P, c_int64, P, P, P, c_int64, P, c_int32, c_double, c_double, c_int32, c_int32,
                            POINTER(SchnetBlockWeights), P, P, P, P],
@@ -123,7 +131,7 @@ SIGNATURES = {
     "dig3d_transpose": [P, c_int32, c_int32, P, P],
     "dig3d_schnet_edge_features": [P, c_int64, P, c_int32, c_double, c_double, P, P, P],
 }
-_RESTYPES = {"dig3d_last_error": c_char_p}
+_RESTYPES = {"dig3d_last_error": c_char_p, "dig3d_h16_packed_bytes": c_int64}
 
 _lib = None
 

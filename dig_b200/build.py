@@ -1,33 +1,53 @@
 """Builds dig_b200/libdig3d.so in-tree with nvcc for sm_100a.
 
-    python -m dig_b200.build [--force]
+    python -m dig_b200.build [--force] [-v]
 
-The generated basis headers (csrc/generated/*.cuh) are committed; they are regenerated from
-dig_b200/basis.py + codegen.py only if missing.
+One object per translation unit under dig_b200/csrc/_obj/ (git-ignored), compiled in parallel and only when the
+source or a header it can include is newer; then one link.  The generated basis headers (csrc/generated/*.cuh)
+are committed; they are regenerated from dig_b200/basis.py + codegen.py only if missing.
 """
 import glob
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "_obj")
 OUT = os.path.join(HERE, "libdig3d.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC"]
+              "-Xcompiler", "-fPIC"]
 
 
 def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
+def _headers(src):
+    """Headers a translation unit may include (coarse: the generated basis tables only where they are named)."""
+    deps = glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(HERE, "..", "include", "dig3d.h")]
+    with open(src) as fh:
+        if "generated/" in fh.read():
+            deps += glob.glob(os.path.join(CSRC, "generated", "*.cuh"))
+    return deps
+
+
+def _obj(src):
+    return os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
 def up_to_date():
-    if not os.path.exists(OUT):
-        return False
-    t = os.path.getmtime(OUT)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "generated", "*.cuh"))
-    deps.append(os.path.join(HERE, "..", "include", "dig3d.h"))
-    return all(os.path.getmtime(d) <= t for d in deps)
+    return not _stale(OUT, sources() + glob.glob(os.path.join(CSRC, "*.cuh"))
+                      + glob.glob(os.path.join(CSRC, "generated", "*.cuh"))
+                      + [os.path.join(HERE, "..", "include", "dig3d.h")])
 
 
 def build(force=False, verbose=False):
@@ -36,12 +56,23 @@ def build(force=False, verbose=False):
     if not force and up_to_date():
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + sources()
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    os.makedirs(OBJ, exist_ok=True)
+    todo = [s for s in sources() if force or _stale(_obj(s), [s] + _headers(s))]
+
+    def compile_one(src):
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", _obj(src)]
+        return src, subprocess.run(cmd, capture_output=True, text=True)
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+        for src, res in pool.map(compile_one, todo):
+            if res.returncode != 0:
+                raise RuntimeError(f"nvcc failed on {src}:\n" + res.stdout + res.stderr)
+            if verbose:
+                print(res.stderr)
+    res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT]
+                         + [_obj(s) for s in sources()], capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+        raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     return OUT
 
 

@@ -1,0 +1,745 @@
+// SphereNet / DimeNet++ dense edge-MLP chain, second generation: TWO 128-edge tiles in flight per SM.
+//
+// The first-generation chain (spherenet_tc.cu, 3xTF32) is serialisation bound: per 128-edge tile every linear
+// costs ~5 k cycles of MMAs and ~6 k cycles of epilogue (TMEM -> bias / swish / residual -> split -> smem),
+// strictly alternating, and its fp32-sized operand planes (2 x 66 KB) leave room for one tile per SM only
+// (profiles/r01_b_tc_final_ncu_summary.txt: tensor pipe 19.8 % busy).  Here:
+//
+//   * operands are split into TWO FP16 planes after a power-of-two pre-scale, x*8 = hi + lo (+ 2^-22 x),
+//     w*64 = hi + lo: fp16 carries the same 11 significant bits as TF32, so the three-product form
+//     D = A_lo*W_hi + A_hi*W_lo + A_hi*W_hi keeps fp32-level accuracy (tools/emulate_split.py: energy error
+//     2.2e-7 vs 3.6e-7 for 3xTF32), while kind::f16 MMAs move K = 16 per instruction (twice TF32) and the
+//     planes are half the size: two tiles' A operands (132 KB) + a 4-stage weight ring (64 KB) fit in shared
+//     memory.  The pre-scales keep `lo` in fp16's normal range for |x| > 0.03 (below that the ABSOLUTE error
+//     floor is 4e-9); activations must stay below 8190 in magnitude - a larger value overflows to inf/NaN in
+//     the energies and raises the flag read by dig3d_h16_overflow() (the 3xTF32 chain has fp32 range).
+//   * the MMA issuer alternates between the two tiles layer by layer: while tile X's eight epilogue warps run
+//     the exposed activation phase of layer q, the tensor core runs layer q of tile Y, and vice versa.  The
+//     two TMEM accumulators (one K = 64 chunk each, see the truncation note in spherenet_tc.cu) are shared by
+//     the tiles; the fp32 residual / skip rows live in the other half of TMEM (2 x 128 columns) instead of
+//     registers, which is what lets one epilogue thread own 64 columns of a row.
+//   * warp roles (576 threads): warp 0 = bulk-copy producer, warp 1 = MMA issuer, warps 2..9 = epilogue of
+//     tile X, warps 10..17 = epilogue of tile Y (two warps per TMEM lane quarter, 64 columns each).
+//
+// Reference ops: update_e.forward spherenet.py:150-182 (dimenetpp.py:133-161), init.forward spherenet.py:79-91.
+#include <cuda_fp16.h>
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace dig3d {
+using namespace tc05;
+
+constexpr int H_M = 128;
+constexpr int H_AKU = H_M + 1;                     // k-unit stride of the A planes in 16-byte units (padded)
+constexpr int H_PLANE = 16 * H_AKU * 16;           // bytes of one fp16 plane of a [128 x 128] operand tile
+constexpr int H_STAGES = 4;
+constexpr int H_SLAB_K = 32;                       // ring granularity: K = 32 slab = [hi|lo][4 k-units][N][8 halves]
+constexpr int H_STAGE_BYTES = 2 * 4 * 128 * 16;    // 16 KB (N = 128)
+constexpr int H_TILE_WARPS = 8;
+constexpr int H_TILE_THREADS = H_TILE_WARPS * 32;
+constexpr int H_THREADS = 64 + 2 * H_TILE_THREADS;
+constexpr float H_SA = 8.0f, H_SW = 64.0f;
+constexpr float H_INV = 1.0f / (H_SA * H_SW);
+constexpr float H_RANGE = 8190.0f;                 // |activation| limit (65504 / H_SA)
+constexpr int H_LDS = 129;                         // row stride (floats) of the fp32 staging overlay of a tile's planes
+
+struct HSmem {
+  unsigned char a[2][2][H_PLANE];                  // [tile][hi | lo]
+  unsigned char w[H_STAGES][H_STAGE_BYTES];
+  float bias[8][128];
+  float wr[128 * 8];
+  float wr1[64];
+  int dst[2][H_M];
+  int aux[2][2][H_M];                              // init_e: atomic numbers of the target / source node of each row
+  uint64_t full[H_STAGES], empty[H_STAGES], a_ready[2], d_ready[2], d_free[2];
+  uint32_t tmem_base;
+};
+static_assert(sizeof(HSmem) <= 227 * 1024, "HSmem exceeds the shared memory of an SM");
+static_assert(2 * H_PLANE == H_M * H_LDS * 4, "the fp32 staging overlay must cover exactly one tile's planes");
+
+struct HGemm {
+  const unsigned char* w;   // packed slabs (dig3d_h16_pack)
+  const float* bias;        // [N] or null
+  int K, N;
+};
+
+static __device__ unsigned int g_h16_overflow = 0;
+static int h16_fast_swish = 1;
+
+template <bool FAST>
+__device__ __forceinline__ float hswish(float x) {
+  return FAST ? __fdividef(x, 1.0f + __expf(-x)) : __fdiv_rn(x, 1.0f + expf(-x));
+}
+
+// ---- producer: every K = 32 slab of every job (layer x tile) through the ring
+template <int NG>
+__device__ __forceinline__ void h_producer(HSmem& s, const HGemm (&g)[NG], int ntile) {
+  int it = 0;
+  for (int q = 0; q < NG; ++q) {
+    const int nslab = g[q].K / H_SLAB_K;
+    const uint32_t bytes = 2u * 4u * (uint32_t)g[q].N * 16u;
+    for (int t = 0; t < ntile; ++t)
+      for (int c = 0; c < nslab; ++c, ++it) {
+        const int st = it % H_STAGES;
+        mbar_wait(&s.empty[st], ((it / H_STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(&s.full[st], bytes);
+        bulk_g2s(s.w[st], g[q].w + (size_t)c * bytes, bytes, &s.full[st]);
+      }
+  }
+}
+
+// ---- MMA issuer: jobs alternate between the tiles; one K = 64 chunk (two slabs) per TMEM accumulator
+template <int NG>
+__device__ __forceinline__ void h_mma(HSmem& s, const HGemm (&g)[NG], int ntile, uint32_t tmem) {
+  int it = 0, ch = 0;
+  for (int q = 0; q < NG; ++q) {
+    const int nslab = g[q].K / H_SLAB_K, n = g[q].N;
+    const uint32_t idesc = idesc_f16(H_M, n);
+    for (int t = 0; t < ntile; ++t) {
+      mbar_wait(&s.a_ready[t], q & 1);
+      tc_fence_after();
+      const uint32_t a_hi = smem_u32(s.a[t][0]), a_lo = smem_u32(s.a[t][1]);
+      for (int c = 0; c < nslab; ++c, ++it) {
+        const int st = it % H_STAGES, ab = ch & 1;
+        if ((c & 1) == 0) mbar_wait(&s.d_free[ab], ((ch >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
+        mbar_wait(&s.full[st], (it / H_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t w_hi = smem_u32(s.w[st]), w_lo = w_hi + 4u * n * 16u;
+        const uint32_t d = tmem + 128u * ab;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {   // the slab's corrections (2^-11 of the main term) first ...
+          const uint32_t a_off = (uint32_t)((c * 4 + ks * 2) * H_AKU * 16), b_off = (uint32_t)(ks * 2 * n * 16);
+          mma_f16(d, smem_desc(a_lo + a_off, H_AKU * 16, 128), smem_desc(w_hi + b_off, n * 16, 128), idesc,
+                  ((c & 1) | ks) != 0);
+          mma_f16(d, smem_desc(a_hi + a_off, H_AKU * 16, 128), smem_desc(w_lo + b_off, n * 16, 128), idesc, 1);
+        }
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {   // ... then its two hi*hi steps
+          const uint32_t a_off = (uint32_t)((c * 4 + ks * 2) * H_AKU * 16), b_off = (uint32_t)(ks * 2 * n * 16);
+          mma_f16(d, smem_desc(a_hi + a_off, H_AKU * 16, 128), smem_desc(w_hi + b_off, n * 16, 128), idesc, 1);
+        }
+        mma_commit(&s.empty[st]);
+        if (c & 1) { mma_commit(&s.d_ready[ab]); ++ch; }
+      }
+    }
+  }
+}
+
+// ---- epilogue context: thread = one row of its tile, NC = 64 (N = 128) or 32 (N = 64) columns
+struct HCtx {
+  int t, et, row, half;     // tile in the pair, thread index within the tile's epilogue, row, column half
+  uint32_t tl;              // TMEM address of this warp's lane quarter, column 0
+  int ntile, ch;            // tiles in this CTA, accumulator-chunk counter (shared by construction with the issuer)
+  float amax;               // largest |activation| written as an operand (range check)
+};
+__device__ __forceinline__ HCtx h_ctx(const HSmem& s, int ntile) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = (warp - 2) / H_TILE_WARPS, we = (warp - 2) % H_TILE_WARPS;
+  const int quarter = warp & 3;   // a warp may only touch TMEM lanes [32*(warp%4), +32)
+  return {t, (int)threadIdx.x - 64 - t * H_TILE_THREADS, 32 * quarter + lane, we >> 2,
+          s.tmem_base + ((uint32_t)(32 * quarter) << 16), ntile, 0, 0.f};
+}
+__device__ __forceinline__ void h_tile_bar(int t) {
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + t), "n"(H_TILE_THREADS) : "memory");
+}
+__device__ __forceinline__ void h_epi_done(HSmem& s, int t) {
+  fence_async_smem();
+  tc_fence_before();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(&s.a_ready[t]);
+}
+// 8 consecutive K elements of a row (one k-unit): pre-scale, split into fp16 hi / lo, one 16-byte store per plane
+__device__ __forceinline__ void h_store_ku(HSmem& s, HCtx& c, int row, int ku, const float (&x)[8]) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float a = x[2 * i] * H_SA, b = x[2 * i + 1] * H_SA;
+    c.amax = fmaxf(c.amax, fmaxf(fabsf(x[2 * i]), fabsf(x[2 * i + 1])));
+    const __half2 hh = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(a - hf.x, b - hf.y);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  const int o = (ku * H_AKU + row) * 16;
+  *reinterpret_cast<uint4*>(s.a[c.t][0] + o) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(s.a[c.t][1] + o) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+__device__ __forceinline__ void h_store_a16(HSmem& s, HCtx& c, int col, const float (&v)[16]) {
+  float x[8];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = v[8 * u + i];
+    h_store_ku(s, c, c.row, (col >> 3) + u, x);
+  }
+}
+// Cooperative load of a row-major [rows x KU*8] fp32 tile (leading dimension ld floats) into the tile's planes:
+// a warp reads 32 consecutive k-units (1 KB when ld == KU*8) per step.
+template <int KU>
+__device__ __forceinline__ void h_load_tile(HSmem& s, HCtx& c, const float* __restrict__ g, size_t ld, int rows) {
+#pragma unroll
+  for (int k = 0; k < H_M * KU / H_TILE_THREADS; ++k) {
+    const int f = c.et + k * H_TILE_THREADS, row = f / KU, ku = f % KU;
+    float x[8];
+    if (row < rows) {
+      const float4 p0 = __ldg(reinterpret_cast<const float4*>(g + (size_t)row * ld + ku * 8));
+      const float4 p1 = __ldg(reinterpret_cast<const float4*>(g + (size_t)row * ld + ku * 8 + 4));
+      x[0] = p0.x; x[1] = p0.y; x[2] = p0.z; x[3] = p0.w; x[4] = p1.x; x[5] = p1.y; x[6] = p1.z; x[7] = p1.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = 0.f;
+    }
+    h_store_ku(s, c, row, ku, x);
+  }
+}
+// Skip the accumulator chunks of the OTHER tile's job of this layer (keeps c.ch in step with the issuer).
+__device__ __forceinline__ void h_skip_before(HCtx& c, int chunks) { if (c.t == 1) c.ch += chunks; }
+__device__ __forceinline__ void h_skip_after(HCtx& c, int chunks) { if (c.t == 0 && c.ntile == 2) c.ch += chunks; }
+// Streaming accumulation of this tile's job: each finished K = 64 chunk is added (round to nearest) into the
+// thread's fp32 registers; NP 16-column pieces starting at column col0.
+template <int NP, bool FIRST>
+__device__ __forceinline__ void h_drain(HSmem& s, HCtx& c, int col0, int chunks, float (&acc)[NP * 16]) {
+  h_skip_before(c, chunks);
+  for (int k = 0; k < chunks; ++k, ++c.ch) {
+    const int ab = c.ch & 1;
+    mbar_wait(&s.d_ready[ab], (c.ch >> 1) & 1);
+    tc_fence_after();
+    const uint32_t ta = c.tl + 128u * ab + col0;
+#pragma unroll
+    for (int p = 0; p < NP; p += 2) {
+      uint32_t r[2][16];
+      tmem_ld16(ta + 16 * p, r[0]);
+      if (p + 1 < NP) tmem_ld16(ta + 16 * p + 16, r[1]);
+      tmem_ld_wait();
+      if (FIRST && k == 0) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          acc[p * 16 + i] = __uint_as_float(r[0][i]);
+          if (p + 1 < NP) acc[p * 16 + 16 + i] = __uint_as_float(r[1][i]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          acc[p * 16 + i] = __fadd_rn(acc[p * 16 + i], __uint_as_float(r[0][i]));
+          if (p + 1 < NP) acc[p * 16 + 16 + i] = __fadd_rn(acc[p * 16 + 16 + i], __uint_as_float(r[1][i]));
+        }
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&s.d_free[ab]);   // one arrival per warp
+  }
+  h_skip_after(c, chunks);
+}
+__device__ __forceinline__ void h_setup(HSmem& s) {
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < H_STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s.a_ready[i], H_TILE_WARPS);
+      mbar_init(&s.d_ready[i], 1);
+      mbar_init(&s.d_free[i], H_TILE_WARPS);
+    }
+    mbar_fence_init();
+  }
+  if ((threadIdx.x >> 5) == 0) tmem_alloc(&s.tmem_base, 512);
+}
+__device__ __forceinline__ void h_finish(HSmem& s, const HCtx* c) {
+  if (c && c->amax > H_RANGE) atomicOr(&g_h16_overflow, 1u);
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) tmem_dealloc(s.tmem_base, 512);
+}
+// e2 tile (staged as [128][H_LDS] fp32 over the tile's own planes) -> segmented edge -> node sums; the tile's 256
+// threads take one column and one half of the rows each.  Rows are target-sorted: only the first and the last
+// segment of a half can be shared with another half / tile (atomics), interior segments are plain stores.
+__device__ __forceinline__ void h_segment_sums(const HSmem& s, const HCtx& c, int rows, float* __restrict__ v_in) {
+  const int col = c.et & 127, r0 = (c.et >> 7) * 64, r1 = min(rows, r0 + 64);
+  if (r0 >= r1) return;
+  const float* e2t = reinterpret_cast<const float*>(s.a[c.t][0]);
+  const int* dst = s.dst[c.t];
+  float run = 0.f;
+  int cur = dst[r0];
+  bool first = true;
+  for (int r = r0; r < r1; ++r) {
+    const int d = dst[r];
+    if (d != cur) {
+      if (first) atomicAdd(v_in + (size_t)cur * 128 + col, run);
+      else v_in[(size_t)cur * 128 + col] = run;
+      first = false; run = 0.f; cur = d;
+    }
+    run += e2t[r * H_LDS + col];
+  }
+  atomicAdd(v_in + (size_t)cur * 128 + col, run);
+}
+
+// ---------------------------------------------------------------------------------- weight packing
+// W [N, K] fp32 (nn.Linear layout) -> K/32 slabs of [hi|lo][4 k-units][N][8 halves], w*64 = hi + lo.
+struct HPackJob { const float* w; unsigned char* out; int N, K; };
+struct HPackJobs { HPackJob job[16]; };
+__global__ void h16_pack_kernel(HPackJobs jobs) {
+  const HPackJob jb = jobs.job[blockIdx.y];
+  const int total = jb.N * jb.K;
+  for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < total; id += gridDim.x * blockDim.x) {
+    const int n = id / jb.K, k = id % jb.K;
+    const float x = __ldg(jb.w + id) * H_SW;
+    const __half h = __float2half_rn(x);
+    const __half l = __float2half_rn(x - __half2float(h));
+    const int c = k >> 5, ku = (k & 31) >> 3, kk = k & 7;
+    const size_t slab = (size_t)c * (2 * 4 * jb.N * 16);
+    const size_t o = ((size_t)ku * jb.N + n) * 16 + kk * 2;
+    *reinterpret_cast<__half*>(jb.out + slab + o) = h;
+    *reinterpret_cast<__half*>(jb.out + slab + (size_t)4 * jb.N * 16 + o) = l;
+  }
+}
+
+// ---------------------------------------------------------------------------------- update_e part B
+struct HBParams {
+  HGemm g[8];                  // lin_up, res0.lin1, res0.lin2, lin, res1.lin1, res1.lin2, res2.lin1, res2.lin2
+  const float* w_rbf;          // [128, 6]
+};
+
+template <bool FAST>
+__global__ void __launch_bounds__(H_THREADS, 1)
+sphere_update_e_b_h16_kernel(const float* __restrict__ m, const float* __restrict__ x_ji,
+                             const float* __restrict__ e1_in, const float* __restrict__ rbf0,
+                             const int32_t* __restrict__ dst, int n_edges, HBParams P, float* __restrict__ e1_out,
+                             float* __restrict__ v_in) {
+  extern __shared__ __align__(1024) unsigned char h_raw[];
+  HSmem& s = *reinterpret_cast<HSmem*>(h_raw);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int n_tiles = (n_edges + H_M - 1) / H_M, tile0 = blockIdx.x * 2, ntile = min(2, n_tiles - tile0);
+  h_setup(s);
+  for (int i = tid; i < 8 * 128; i += H_THREADS) {
+    const float* b = P.g[i / 128].bias;
+    s.bias[i / 128][i % 128] = b ? __ldg(b + i % 128) : 0.f;
+  }
+  for (int i = tid; i < 128 * 8; i += H_THREADS) s.wr[i] = (i % 8 < 6) ? __ldg(P.w_rbf + (i / 8) * 6 + i % 8) : 0.f;
+  for (int i = tid; i < 2 * H_M; i += H_THREADS) {
+    const int e = (tile0 + i / H_M) * H_M + i % H_M;
+    s.dst[i / H_M][i % H_M] = (e < n_edges) ? dst[e] : -1;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  HCtx c;
+  bool epi = false;
+  if (warp == 0) {
+    if (tid == 0) h_producer(s, P.g, ntile);
+  } else if (warp == 1) {
+    if (tid == 32) h_mma(s, P.g, ntile, s.tmem_base);
+  } else if ((c = h_ctx(s, ntile)).t < ntile) {
+    epi = true;
+    const int e0 = (tile0 + c.t) * H_M, rows = min(H_M, n_edges - e0);
+    const bool valid = c.row < rows;
+    const size_t ge = (size_t)(e0 + c.row);
+    const int col0 = c.half * 64;
+    const uint32_t stash = c.tl + 256u + 128u * c.t + col0;
+    // A0 = m tile (K = 64)
+    h_load_tile<8>(s, c, m + (size_t)e0 * 64, 64, rows);
+    h_epi_done(s, c.t);
+    // The eight epilogues of the chain (spherenet.py:172-179):
+    //   q=0: h = x_ji + act(lin_up(m))                       -> A, stash
+    //   q=1,4,6: t = act(lin1(h))                            -> A
+    //   q=2,5: h = stash + act(lin2(t))                      -> A, stash      (q=2: stash not needed afterwards)
+    //   q=3: h = act(lin(h)) + e1_in                         -> A, stash
+    //   q=7: h = stash + act(lin2(t))                        -> e1_out, e2 tile
+#pragma unroll 1
+    for (int q = 0; q < 8; ++q) {
+      float acc[64];
+      h_drain<4, true>(s, c, col0, q == 0 ? 1 : 2, acc);
+      const bool add_stash = (q == 2 || q == 5 || q == 7);
+      const bool to_stash = (q == 0 || q == 3 || q == 5);
+      float rb[6];
+      if (q == 7) {
+#pragma unroll
+        for (int n = 0; n < 6; ++n) rb[n] = valid ? __ldg(rbf0 + ge * 6 + n) : 0.f;
+      }
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int col = col0 + 16 * p;
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const float4 b = *reinterpret_cast<const float4*>(&s.bias[q][col + i]);
+          v[i] = hswish<FAST>(fmaf(acc[16 * p + i], H_INV, b.x));
+          v[i + 1] = hswish<FAST>(fmaf(acc[16 * p + i + 1], H_INV, b.y));
+          v[i + 2] = hswish<FAST>(fmaf(acc[16 * p + i + 2], H_INV, b.z));
+          v[i + 3] = hswish<FAST>(fmaf(acc[16 * p + i + 3], H_INV, b.w));
+        }
+        if (add_stash) {
+          uint32_t r[16];
+          tmem_ld16(stash + 16 * p, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += __uint_as_float(r[i]);
+        }
+        if (q == 0 || q == 3) {
+          const float* gsrc = (q == 0 ? x_ji : e1_in) + ge * 128 + col;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 x = valid ? __ldg(reinterpret_cast<const float4*>(gsrc + i)) : make_float4(0, 0, 0, 0);
+            v[i] += x.x; v[i + 1] += x.y; v[i + 2] += x.z; v[i + 3] += x.w;
+          }
+        }
+        if (q < 7) {
+          if (to_stash) {
+            uint32_t r[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(v[i]);
+            tmem_st16(stash + 16 * p, r);
+          }
+          h_store_a16(s, c, col, v);
+        } else {
+          // e1_out and e2 = lin_rbf(rbf0) * e1 (tile staged over this tile's planes; all its MMAs are done)
+          float* e2t = reinterpret_cast<float*>(s.a[c.t][0]);
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            if (valid) *reinterpret_cast<float4*>(e1_out + ge * 128 + col + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float gsum = 0.f;
+#pragma unroll
+              for (int n = 0; n < 6; ++n) gsum = fmaf(s.wr[(col + i + u) * 8 + n], rb[n], gsum);
+              e2t[c.row * H_LDS + col + i + u] = gsum * v[i + u];
+            }
+          }
+        }
+      }
+      if (q < 7) {
+        if (to_stash) tmem_st_wait();
+        h_epi_done(s, c.t);
+      }
+    }
+    h_tile_bar(c.t);
+    h_segment_sums(s, c, rows, v_in);   // spherenet.py:211
+  }
+  h_finish(s, epi ? &c : nullptr);
+}
+
+// ---------------------------------------------------------------------------------- update_e part A
+struct HAParams {
+  HGemm g[3];                  // lin_ji, lin_kj, lin_down
+  const float *w_rbf1, *w_rbf2;
+};
+
+template <bool FAST>
+__global__ void __launch_bounds__(H_THREADS, 1)
+sphere_update_e_a_h16_kernel(const float* __restrict__ e1, const float* __restrict__ rbf0, int n_edges, HAParams P,
+                             float* __restrict__ x_ji, float* __restrict__ x_down) {
+  extern __shared__ __align__(1024) unsigned char h_raw[];
+  HSmem& s = *reinterpret_cast<HSmem*>(h_raw);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int n_tiles = (n_edges + H_M - 1) / H_M, tile0 = blockIdx.x * 2, ntile = min(2, n_tiles - tile0);
+  h_setup(s);
+  for (int i = tid; i < 2 * 128; i += H_THREADS) s.bias[i / 128][i % 128] = __ldg(P.g[i / 128].bias + i % 128);
+  for (int i = tid; i < 128 * 8; i += H_THREADS) s.wr[i] = __ldg(P.w_rbf2 + i);      // [128][8]
+  for (int i = tid; i < 64; i += H_THREADS) s.wr1[i] = (i % 8 < 6) ? __ldg(P.w_rbf1 + (i / 8) * 6 + i % 8) : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  HCtx c;
+  bool epi = false;
+  if (warp == 0) {
+    if (tid == 0) h_producer(s, P.g, ntile);
+  } else if (warp == 1) {
+    if (tid == 32) h_mma(s, P.g, ntile, s.tmem_base);
+  } else if ((c = h_ctx(s, ntile)).t < ntile) {
+    epi = true;
+    const int e0 = (tile0 + c.t) * H_M, rows = min(H_M, n_edges - e0);
+    const bool valid = c.row < rows;
+    const size_t ge = (size_t)(e0 + c.row);
+    const int col0 = c.half * 64;
+    h_load_tile<16>(s, c, e1 + (size_t)e0 * 128, 128, rows);
+    // rbf gate coefficients of this row: r8 = lin_rbf1(rbf0[row])                spherenet.py:157
+    float r8[8];
+    {
+      float rb[6];
+#pragma unroll
+      for (int n = 0; n < 6; ++n) rb[n] = valid ? __ldg(rbf0 + ge * 6 + n) : 0.f;
+#pragma unroll
+      for (int mm = 0; mm < 8; ++mm) {
+        float a = 0.f;
+#pragma unroll
+        for (int n = 0; n < 6; ++n) a = fmaf(s.wr1[mm * 8 + n], rb[n], a);
+        r8[mm] = a;
+      }
+    }
+    h_epi_done(s, c.t);
+    {
+      float acc[64];
+      // G0: x_ji = act(lin_ji(e1))                                                spherenet.py:154
+      h_drain<4, true>(s, c, col0, 2, acc);
+      h_epi_done(s, c.t);   // A (= e1) is reused unchanged by lin_kj: its MMAs may run under this activation
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < 64; i += 4) {
+          const float4 b = *reinterpret_cast<const float4*>(&s.bias[0][col0 + i]);
+          float4 o;
+          o.x = hswish<FAST>(fmaf(acc[i], H_INV, b.x));
+          o.y = hswish<FAST>(fmaf(acc[i + 1], H_INV, b.y));
+          o.z = hswish<FAST>(fmaf(acc[i + 2], H_INV, b.z));
+          o.w = hswish<FAST>(fmaf(acc[i + 3], H_INV, b.w));
+          *reinterpret_cast<float4*>(x_ji + ge * 128 + col0 + i) = o;
+        }
+      }
+      // G1: x_kj = act(lin_kj(e1)) * lin_rbf2(r8)                                 spherenet.py:155-159
+      h_drain<4, true>(s, c, col0, 2, acc);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int col = col0 + 16 * p + i;
+          const float4 w0 = *reinterpret_cast<const float4*>(s.wr + col * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(s.wr + col * 8 + 4);
+          const float gate = fmaf(w1.w, r8[7], fmaf(w1.z, r8[6], fmaf(w1.y, r8[5], fmaf(w1.x, r8[4],
+                             fmaf(w0.w, r8[3], fmaf(w0.z, r8[2], fmaf(w0.y, r8[1], w0.x * r8[0])))))));
+          v[i] = hswish<FAST>(fmaf(acc[16 * p + i], H_INV, s.bias[1][col])) * gate;
+        }
+        h_store_a16(s, c, col0 + 16 * p, v);
+      }
+      h_epi_done(s, c.t);
+    }
+    // G2: x_down = act(lin_down(x_kj)), N = 64                                    spherenet.py:161
+    {
+      const int col = c.half * 32;
+      float a32[32];
+      h_drain<2, true>(s, c, col, 2, a32);
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          float4 o;
+          o.x = hswish<FAST>(a32[i] * H_INV); o.y = hswish<FAST>(a32[i + 1] * H_INV);
+          o.z = hswish<FAST>(a32[i + 2] * H_INV); o.w = hswish<FAST>(a32[i + 3] * H_INV);
+          *reinterpret_cast<float4*>(x_down + ge * 64 + col + i) = o;
+        }
+      }
+    }
+  }
+  h_finish(s, epi ? &c : nullptr);
+}
+
+// ---------------------------------------------------------------------------------- init_e
+// e1 = act(lin(cat[x_i, x_j, act(lin_rbf_0(rbf))])), e2 = lin_rbf_1(rbf) * e1        spherenet.py:79-91
+// K = 384 as three K = 128 panels whose A operand is rebuilt between panels; the chunk sums keep accumulating in
+// the epilogue registers across the panels.
+struct HInitParams {
+  HGemm g[3];
+  const float *emb, *w_rbf0, *b_rbf0, *b_lin, *w_rbf1;
+};
+
+template <bool FAST>
+__global__ void __launch_bounds__(H_THREADS, 1)
+sphere_init_e_h16_kernel(const int64_t* __restrict__ z, const int32_t* __restrict__ src,
+                         const int32_t* __restrict__ dst, const float* __restrict__ rbf0, int n_edges, HInitParams P,
+                         float* __restrict__ e1, float* __restrict__ v_in) {
+  extern __shared__ __align__(1024) unsigned char h_raw[];
+  HSmem& s = *reinterpret_cast<HSmem*>(h_raw);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int n_tiles = (n_edges + H_M - 1) / H_M, tile0 = blockIdx.x * 2, ntile = min(2, n_tiles - tile0);
+  float* w0 = &s.bias[2][0];   // lin_rbf_0.weight [128][6] parked in the unused bias rows
+  h_setup(s);
+  for (int i = tid; i < 128; i += H_THREADS) { s.bias[0][i] = __ldg(P.b_lin + i); s.bias[1][i] = __ldg(P.b_rbf0 + i); }
+  for (int i = tid; i < 128 * 6; i += H_THREADS) w0[i] = __ldg(P.w_rbf0 + i);
+  for (int i = tid; i < 128 * 8; i += H_THREADS) s.wr[i] = (i % 8 < 6) ? __ldg(P.w_rbf1 + (i / 8) * 6 + i % 8) : 0.f;
+  for (int i = tid; i < 2 * H_M; i += H_THREADS) {
+    const int t = i / H_M, r = i % H_M, e = (tile0 + t) * H_M + r;
+    const int d = (e < n_edges) ? dst[e] : -1, sj = (e < n_edges) ? src[e] : -1;
+    s.dst[t][r] = d;
+    s.aux[t][0][r] = d >= 0 ? (int)z[d] : 0;
+    s.aux[t][1][r] = sj >= 0 ? (int)z[sj] : 0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  HCtx c;
+  bool epi = false;
+  if (warp == 0) {
+    if (tid == 0) h_producer(s, P.g, ntile);
+  } else if (warp == 1) {
+    if (tid == 32) h_mma(s, P.g, ntile, s.tmem_base);
+  } else if ((c = h_ctx(s, ntile)).t < ntile) {
+    epi = true;
+    const int e0 = (tile0 + c.t) * H_M, rows = min(H_M, n_edges - e0);
+    const bool valid = c.row < rows;
+    const size_t ge = (size_t)(e0 + c.row);
+    const int col0 = c.half * 64;
+    float rb[6];
+#pragma unroll
+    for (int n = 0; n < 6; ++n) rb[n] = valid ? __ldg(rbf0 + ge * 6 + n) : 0.f;
+    auto fill_embedding = [&](const int* zrow) {   // A = emb[z[node of row]]
+#pragma unroll
+      for (int k = 0; k < H_M * 16 / H_TILE_THREADS; ++k) {
+        const int f = c.et + k * H_TILE_THREADS, row = f >> 4, ku = f & 15;
+        float x[8];
+        if (row < rows) {
+          const float* er = P.emb + (size_t)zrow[row] * 128 + ku * 8;
+          const float4 p0 = __ldg(reinterpret_cast<const float4*>(er));
+          const float4 p1 = __ldg(reinterpret_cast<const float4*>(er + 4));
+          x[0] = p0.x; x[1] = p0.y; x[2] = p0.z; x[3] = p0.w; x[4] = p1.x; x[5] = p1.y; x[6] = p1.z; x[7] = p1.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x[i] = 0.f;
+        }
+        h_store_ku(s, c, row, ku, x);
+      }
+    };
+    float acc[64];
+    fill_embedding(s.aux[c.t][0]);                  // panel 0: x_i
+    h_epi_done(s, c.t);
+    h_drain<4, true>(s, c, col0, 2, acc);
+    fill_embedding(s.aux[c.t][1]);                  // panel 1: x_j
+    h_epi_done(s, c.t);
+    h_drain<4, false>(s, c, col0, 2, acc);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {                   // panel 2: act(lin_rbf_0(rbf))        spherenet.py:87
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int col = col0 + 16 * p + i;
+        float a = 0.f;
+#pragma unroll
+        for (int n = 0; n < 6; ++n) a = fmaf(w0[col * 6 + n], rb[n], a);
+        v[i] = valid ? hswish<FAST>(a + s.bias[1][col]) : 0.f;
+      }
+      h_store_a16(s, c, col0 + 16 * p, v);
+    }
+    h_epi_done(s, c.t);
+    h_drain<4, false>(s, c, col0, 2, acc);
+    // e1 = act(. + b), e2 = lin_rbf_1(rbf) * e1 (tile staged over the planes), edge -> node sums
+    float* e2t = reinterpret_cast<float*>(s.a[c.t][0]);
+#pragma unroll
+    for (int i = 0; i < 64; i += 4) {
+      float o[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int col = col0 + i + u;
+        o[u] = hswish<FAST>(fmaf(acc[i + u], H_INV, s.bias[0][col]));
+        float gsum = 0.f;
+#pragma unroll
+        for (int n = 0; n < 6; ++n) gsum = fmaf(s.wr[col * 8 + n], rb[n], gsum);
+        e2t[c.row * H_LDS + col] = gsum * o[u];
+      }
+      if (valid) *reinterpret_cast<float4*>(e1 + ge * 128 + col0 + i) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    h_tile_bar(c.t);
+    h_segment_sums(s, c, rows, v_in);
+  }
+  h_finish(s, epi ? &c : nullptr);
+}
+
+static int h_smem_attr(const void* fn) {
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HSmem));
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(%zu): %s", sizeof(HSmem), cudaGetErrorString(e));
+    return DIG3D_ECUDA;
+  }
+  return DIG3D_OK;
+}
+
+}  // namespace dig3d
+
+using namespace dig3d;
+
+extern "C" {
+
+int64_t dig3d_h16_packed_bytes(int32_t n, int32_t k) { return (int64_t)4 * n * k; }
+
+int dig3d_h16_pack(const float* const* weights, const int32_t* n, const int32_t* k, void* const* outs, int32_t count,
+                   void* stream) {
+  DIG3D_REQUIRE(weights && n && k && outs && count >= 1 && count <= 16, "h16_pack: bad arguments");
+  HPackJobs jobs;
+  int max_total = 0;
+  for (int i = 0; i < count; ++i) {
+    DIG3D_REQUIRE(weights[i] && outs[i] && k[i] % 64 == 0 && n[i] % 8 == 0 && n[i] <= 128,
+                  "h16_pack: matrix %d has N=%d K=%d (need K %% 64 == 0, N %% 8 == 0, N <= 128)", i, n[i], k[i]);
+    jobs.job[i] = {weights[i], (unsigned char*)outs[i], n[i], k[i]};
+    max_total = max_total > n[i] * k[i] ? max_total : n[i] * k[i];
+  }
+  dim3 grid(ceil_div(max_total, 256), count);
+  h16_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(jobs);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_h16_set_fast_swish(int32_t on) {
+  h16_fast_swish = on ? 1 : 0;
+  return DIG3D_OK;
+}
+
+int dig3d_h16_overflow(int32_t clear) {
+  unsigned int v = 0;
+  cudaMemcpyFromSymbol(&v, g_h16_overflow, sizeof(v));
+  if (clear && v) {
+    unsigned int zero = 0;
+    cudaMemcpyToSymbol(g_h16_overflow, &zero, sizeof(zero));
+  }
+  return (int)v;
+}
+
+int dig3d_h16_timeouts(void) {
+  unsigned int v = 0;
+  cudaMemcpyFromSymbol(&v, tc05::g_mbar_timeout, sizeof(v));
+  return (int)v;
+}
+
+int dig3d_sphere_init_e_h16(const int64_t* z, const int32_t* src, const int32_t* dst, const float* rbf0,
+                            int64_t n_edges, const dig3d_init_e_weights* w, const void* packed_lin, float* e1,
+                            float* v_in, void* stream) {
+  DIG3D_REQUIRE(z && src && dst && rbf0 && w && packed_lin && e1 && v_in, "sphere_init_e_h16: null pointer");
+  DIG3D_REQUIRE(w->emb && w->w_rbf0 && w->b_rbf0 && w->b_lin && w->w_rbf1, "sphere_init_e_h16: null weight");
+  if (n_edges == 0) return DIG3D_OK;
+  HInitParams P;
+  const size_t panel = (size_t)4 * 2 * 4 * 128 * 16;   // four K=32 slabs
+  for (int p = 0; p < 3; ++p) P.g[p] = {(const unsigned char*)packed_lin + p * panel, nullptr, 128, 128};
+  P.emb = w->emb; P.w_rbf0 = w->w_rbf0; P.b_rbf0 = w->b_rbf0; P.b_lin = w->b_lin; P.w_rbf1 = w->w_rbf1;
+  auto kfn = h16_fast_swish ? sphere_init_e_h16_kernel<true> : sphere_init_e_h16_kernel<false>;
+  int rc = h_smem_attr((const void*)kfn);
+  if (rc) return rc;
+  const int pairs = ceil_div(ceil_div(n_edges, H_M), 2);
+  kfn<<<pairs, H_THREADS, sizeof(HSmem), (cudaStream_t)stream>>>(z, src, dst, rbf0, (int)n_edges, P, e1, v_in);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_sphere_update_e_a_h16(const float* e1, const float* rbf0, int64_t n_edges, const dig3d_tc_update_e* w,
+                                float* x_ji, float* x_down, void* stream) {
+  DIG3D_REQUIRE(e1 && rbf0 && w && x_ji && x_down, "sphere_update_e_a_h16: null pointer");
+  if (n_edges == 0) return DIG3D_OK;
+  HAParams P;
+  P.g[0] = {(const unsigned char*)w->p_ji, w->b_ji, 128, 128};
+  P.g[1] = {(const unsigned char*)w->p_kj, w->b_kj, 128, 128};
+  P.g[2] = {(const unsigned char*)w->p_down, nullptr, 128, 64};
+  P.w_rbf1 = w->w_rbf1; P.w_rbf2 = w->w_rbf2;
+  auto kfn = h16_fast_swish ? sphere_update_e_a_h16_kernel<true> : sphere_update_e_a_h16_kernel<false>;
+  int rc = h_smem_attr((const void*)kfn);
+  if (rc) return rc;
+  const int pairs = ceil_div(ceil_div(n_edges, H_M), 2);
+  kfn<<<pairs, H_THREADS, sizeof(HSmem), (cudaStream_t)stream>>>(e1, rbf0, (int)n_edges, P, x_ji, x_down);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_sphere_update_e_b_h16(const float* m, const float* e1_in, const float* x_ji, const float* rbf0,
+                                const int32_t* dst, int64_t n_edges, const dig3d_tc_update_e* w, float* e1_out,
+                                float* v_in, void* stream) {
+  DIG3D_REQUIRE(m && e1_in && x_ji && rbf0 && dst && w && e1_out && v_in, "sphere_update_e_b_h16: null pointer");
+  if (n_edges == 0) return DIG3D_OK;
+  HBParams P;
+  P.g[0] = {(const unsigned char*)w->p_up, nullptr, 64, 128};
+  for (int i = 0; i < 2; ++i) P.g[1 + i] = {(const unsigned char*)w->p_res[i], w->b_res[i], 128, 128};
+  P.g[3] = {(const unsigned char*)w->p_lin, w->b_lin, 128, 128};
+  for (int i = 2; i < 6; ++i) P.g[2 + i] = {(const unsigned char*)w->p_res[i], w->b_res[i], 128, 128};
+  P.w_rbf = w->w_rbf;
+  auto kfn = h16_fast_swish ? sphere_update_e_b_h16_kernel<true> : sphere_update_e_b_h16_kernel<false>;
+  int rc = h_smem_attr((const void*)kfn);
+  if (rc) return rc;
+  const int pairs = ceil_div(ceil_div(n_edges, H_M), 2);
+  kfn<<<pairs, H_THREADS, sizeof(HSmem), (cudaStream_t)stream>>>(m, x_ji, e1_in, rbf0, dst, (int)n_edges, P, e1_out,
+                                                                 v_in);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+}  // extern "C"

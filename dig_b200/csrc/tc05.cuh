@@ -26,23 +26,42 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// Bounded spin: a protocol bug must not hang the GPU.  On timeout the global flag is raised and the
-// caller proceeds (results are garbage, the host reports the error).
-__device__ unsigned int g_mbar_timeout = 0;
+// Bounded spin: a protocol bug must not hang the GPU.  After ~2 s without progress the wait records the event
+// in g_mbar_timeout and TRAPS: the launch fails with a sticky CUDA error that the next host call reports
+// (a kernel that carried on after a missed barrier would hand back garbage silently).
+static __device__ unsigned int g_mbar_timeout = 0;   // one copy per translation unit
+__device__ __forceinline__ uint64_t global_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ bool mbar_try(uint32_t addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(addr), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+static __device__ __noinline__ void mbar_timeout_trap() {
+  atomicAdd(&g_mbar_timeout, 1u);
+  __threadfence_system();
+  __trap();
+}
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
-  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (ok) return true;
+  if (mbar_try(addr, parity)) return true;
+  const uint64_t t0 = global_ns();
+  for (;;) {
+#pragma unroll 1
+    for (int spin = 0; spin < 4096; ++spin)
+      if (mbar_try(addr, parity)) return true;
+    if (global_ns() - t0 > 2000000000ull) break;
   }
-  atomicAdd(&g_mbar_timeout, 1u);
+  mbar_timeout_trap();
   return false;
 }
 
@@ -103,6 +122,19 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// kind::f16 (fp16 operands, K = 16 per instruction), fp32 accumulate, A and B K-major.
+__host__ __device__ constexpr uint32_t idesc_f16(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // Make all previously issued MMAs arrive on an mbarrier when they complete (implies fence::before_thread_sync).

@@ -382,38 +382,62 @@ def comenet_block(x, f1, f2, g, w, head, out_channels, last):
 _TC_MATS = ("lin_ji", "lin_kj", "lin_down", "lin_up", "lin")
 
 
-def tc_pack_update_e(m, torsion, cache):
-    """Packed (TF32 hi/lo split, UMMA layout) copies of the dense weights of one update_e block.
-    `cache` (a dict owned by the model) keeps them until a parameter changes (tensor._version)."""
+# Generation counter of every packed-weight cache below.  Writes through `tensor.data` (EMA weight swaps,
+# `reset_parameters`) do not bump `tensor._version`, so the model classes call invalidate_packed() from
+# reset_parameters / load_state_dict / train(); user code that edits `.data` of an eval-mode model must call it too.
+_PACK_GENERATION = [0]
+
+
+def invalidate_packed():
+    _PACK_GENERATION[0] += 1
+
+
+def _pack_matrices(mats, kind):
+    """One device buffer holding the packed copies of `mats` ([N, K] fp32 weights) + their byte offsets.
+    kind 'tc': TF32 hi/lo planes (dig3d_tc_pack, 8*N*K bytes); kind 'h16': FP16 hi/lo slabs (dig3d_h16_pack, 4*N*K)."""
+    dev = mats[0].device
+    per = 8 if kind == "tc" else 4
+    sizes = [per * w.size(0) * w.size(1) for w in mats]
+    offs = [0]
+    for sz in sizes:
+        offs.append(offs[-1] + sz)
+    buf = torch.empty(offs[-1], dtype=torch.uint8, device=dev)
+    if buf.data_ptr() % 128:
+        raise RuntimeError("packed weight buffer is not 128-byte aligned")
+    for first in range(0, len(mats), 16):
+        chunk = mats[first:first + 16]
+        n = len(chunk)
+        wp = (ctypes.c_void_p * n)(*[_p(w.detach(), torch.float32, "w", 16).value for w in chunk])
+        op = (ctypes.c_void_p * n)(*[buf.data_ptr() + o for o in offs[first:first + n]])
+        ns = (ctypes.c_int32 * n)(*[w.size(0) for w in chunk])
+        ks = (ctypes.c_int32 * n)(*[w.size(1) for w in chunk])
+        call("dig3d_tc_pack" if kind == "tc" else "dig3d_h16_pack", wp, ns, ks, op, n, _stream())
+    return buf, offs
+
+
+def tc_pack_update_e(m, torsion, cache, kind="tc"):
+    """Packed (hi/lo split, UMMA layout) copies of the dense weights of one update_e block for the tensor-core
+    chain `kind` ('tc' = 3xTF32, 'h16' = 3xFP16).  `cache` (a dict owned by the model) keeps them until a
+    parameter changes (tensor._version) or the model invalidates it (`invalidate_packed()`: writes through
+    `.data` do not bump `_version`)."""
     mats = [m.lin_ji.weight, m.lin_kj.weight, m.lin_down.weight, m.lin_up.weight]
     res = list(m.layers_before_skip) + list(m.layers_after_skip)
     for layer in res:
         mats += [layer.lin1.weight, layer.lin2.weight]
     mats.append(m.lin.weight)
-    key = tuple((w.data_ptr(), w._version) for w in mats)
-    hit = cache.get(id(m))
+    key = (_PACK_GENERATION[0],) + tuple((w.data_ptr(), w._version) for w in mats)
+    hit = cache.get((id(m), kind))
     if hit is None or hit[0] != key:
-        dev = mats[0].device
-        sizes = [2 * w.size(0) * w.size(1) for w in mats]
-        buf = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
-        offs = [0]
-        for sz in sizes:
-            offs.append(offs[-1] + sz)
-        n = len(mats)
-        wp = (ctypes.c_void_p * n)(*[_p(w.detach(), torch.float32, "w", 16).value for w in mats])
-        op = (ctypes.c_void_p * n)(*[buf.data_ptr() + 4 * o for o in offs[:-1]])
-        ns = (ctypes.c_int32 * n)(*[w.size(0) for w in mats])
-        ks = (ctypes.c_int32 * n)(*[w.size(1) for w in mats])
-        call("dig3d_tc_pack", wp, ns, ks, op, n, _stream())
+        buf, offs = _pack_matrices(mats, kind)
         hit = (key, buf, offs)
-        cache[id(m)] = hit
+        cache[(id(m), kind)] = hit
     _, buf, offs = hit
     base = buf.data_ptr()
     w = _lib.TcUpdateE()
-    w.p_ji, w.p_kj, w.p_down, w.p_up = (base + 4 * offs[0], base + 4 * offs[1], base + 4 * offs[2], base + 4 * offs[3])
+    w.p_ji, w.p_kj, w.p_down, w.p_up = (base + offs[0], base + offs[1], base + offs[2], base + offs[3])
     for r in range(6):
-        w.p_res[r] = base + 4 * offs[4 + r]
-    w.p_lin = base + 4 * offs[10]
+        w.p_res[r] = base + offs[4 + r]
+    w.p_lin = base + offs[10]
     w.b_ji, w.b_kj, w.b_lin = _wp(m.lin_ji.bias, "b_ji"), _wp(m.lin_kj.bias, "b_kj"), _wp(m.lin.bias, "b_lin")
     for r, layer in enumerate(res):
         w.b_res[2 * r], w.b_res[2 * r + 1] = _wp(layer.lin1.bias, "res.b1"), _wp(layer.lin2.bias, "res.b2")
@@ -423,20 +447,15 @@ def tc_pack_update_e(m, torsion, cache):
     return w
 
 
-def tc_pack_matrix(weight, cache, key):
+def tc_pack_matrix(weight, cache, key, kind="tc"):
     """Packed copy of one [N, K] weight (cached until the parameter changes).  The buffer is OWNED by `cache`:
     keep the dict alive until the kernels that read it have run (the model keeps it for its lifetime)."""
-    k = (weight.data_ptr(), weight._version)
-    hit = cache.get(key)
+    k = (_PACK_GENERATION[0], weight.data_ptr(), weight._version)
+    hit = cache.get((key, kind))
     if hit is None or hit[0] != k:
-        buf = torch.empty(2 * weight.numel(), dtype=torch.float32, device=weight.device)
-        wp = (ctypes.c_void_p * 1)(_p(weight.detach(), torch.float32, "w", 16).value)
-        op = (ctypes.c_void_p * 1)(buf.data_ptr())
-        ns = (ctypes.c_int32 * 1)(weight.size(0))
-        ks = (ctypes.c_int32 * 1)(weight.size(1))
-        call("dig3d_tc_pack", wp, ns, ks, op, 1, _stream())
+        buf, _ = _pack_matrices([weight], kind)
         hit = (k, buf)
-        cache[key] = hit
+        cache[(key, kind)] = hit
     return hit[1]
 
 
@@ -472,12 +491,56 @@ def sphere_update_e_tc(e1, g, rbf0, sbf_p, t_p, col0, w, hidden, int_emb, v_in=N
     return e1_out, v_in, x_ji, x_down
 
 
+def sphere_init_e_h16(z, g, rbf0, w, packed_lin, hidden, v_in=None):
+    e1 = torch.empty(max(g.n_edges, 1), hidden, dtype=torch.float32, device=rbf0.device)[:g.n_edges]
+    if v_in is None:
+        v_in = torch.zeros(g.n_nodes, hidden, dtype=torch.float32, device=rbf0.device)
+    if g.n_edges:
+        call("dig3d_sphere_init_e_h16", _p(z, torch.int64, "z"), _p(g.src), _p(g.dst), _p(rbf0), g.n_edges,
+             ctypes.byref(w), _p(packed_lin), _p(e1), _p(v_in), _stream())
+    return e1, v_in
+
+
+def sphere_update_e_h16(e1, g, rbf0, sbf_p, t_p, col0, w, hidden, int_emb, v_in=None):
+    """update_e (A + triplet gather + B) with the dense chain on tcgen05, two tiles in flight per SM (3xFP16)."""
+    dev = e1.device
+    e = g.n_edges
+    x_ji = torch.empty(max(e, 1), hidden, dtype=torch.float32, device=dev)[:e]
+    x_down = torch.empty(max(e, 1), int_emb, dtype=torch.float32, device=dev)[:e]
+    m_ws = torch.empty(max(e, 1), int_emb, dtype=torch.float32, device=dev)[:e]
+    e1_out = torch.empty(max(e, 1), hidden, dtype=torch.float32, device=dev)[:e]
+    if v_in is None:
+        v_in = torch.zeros(g.n_nodes, hidden, dtype=torch.float32, device=dev)
+    if e:
+        st = _stream()
+        call("dig3d_sphere_update_e_a_h16", _p(e1), _p(rbf0), e, ctypes.byref(w), _p(x_ji), _p(x_down), st)
+        sp = ctypes.c_void_p(sbf_p[col0 // 8].data_ptr())
+        tp = ctypes.c_void_p(t_p[col0 // 8].data_ptr()) if t_p is not None else None
+        call("dig3d_sphere_triplet_gather", _p(x_down), sp, tp, 8, _p(g.src), _p(g.dst), _p(g.row_ptr),
+             _p(g.trip_ptr), e, w.w_sbf2, w.w_t2, _p(m_ws), st)
+        call("dig3d_sphere_update_e_b_h16", _p(m_ws), _p(e1), _p(x_ji), _p(rbf0), _p(g.dst), e, ctypes.byref(w),
+             _p(e1_out), _p(v_in), st)
+    return e1_out, v_in, x_ji, x_down
+
+
+def h16_overflow(clear=True):
+    """True if an operand of the 3xFP16 chain left the fp16 range (|activation| >= 8190) since the last clear."""
+    return bool(_lib.load().dig3d_h16_overflow(int(bool(clear))))
+
+
+def h16_set_fast_swish(on):
+    call("dig3d_h16_set_fast_swish", int(bool(on)))
+
+
 def tc_set_fast_swish(on):
     call("dig3d_tc_set_fast_swish", int(bool(on)))
 
 
 def tc_timeouts():
-    return _lib.load().dig3d_tc_timeouts()
+    """mbarrier waits that timed out in the tensor-core kernels (they trap, so a non-zero count is only ever seen
+    together with a failed launch)."""
+    lib = _lib.load()
+    return lib.dig3d_tc_timeouts() + lib.dig3d_h16_timeouts()
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -780,14 +843,15 @@ def _packed_weight(weight, transposed):
     Pass the parameter itself (not a .detach() view, which is a new object every time)."""
     store = weight.__dict__.setdefault("_dig3d_packed", {})
     hit = store.get(bool(transposed))
-    if hit is not None and hit[0] == (weight._version, weight.data_ptr(), tuple(weight.shape)):
+    tag = (_PACK_GENERATION[0], weight._version, weight.data_ptr(), tuple(weight.shape))
+    if hit is not None and hit[0] == tag:
         return hit[1]
     n, k = (weight.size(1), weight.size(0)) if transposed else (weight.size(0), weight.size(1))
     buf = torch.empty(2 * n * k, dtype=F32, device=weight.device)
     one = ctypes.c_void_p * 1
     call("dig3d_tc_pack_t", one(_p(weight.detach(), F32, "w", 16).value), (ctypes.c_int32 * 1)(n), (ctypes.c_int32 * 1)(k),
          (ctypes.c_int32 * 1)(int(bool(transposed))), one(buf.data_ptr()), 1, _stream())
-    store[bool(transposed)] = ((weight._version, weight.data_ptr(), tuple(weight.shape)), buf)
+    store[bool(transposed)] = (tag, buf)
     return buf
 
 

@@ -198,6 +198,24 @@ class _DimeNetFamily(nn.Module):
             m.reset_parameters()
         for m in self.update_vs:
             m.reset_parameters()
+        self.invalidate_packed()
+
+    # The tensor-core chains run on packed copies of the dense weights, cached per parameter version.  Writes
+    # through `.data` (reset_parameters above, EMA weight swaps) do not bump the version, so every entry point that
+    # can change weights behind autograd's back drops the cache; user code that edits `p.data` of an eval-mode
+    # model must call invalidate_packed() itself.
+    def invalidate_packed(self):
+        self.__dict__.setdefault("_tc_cache", {}).clear()
+        ops.invalidate_packed()
+
+    def load_state_dict(self, *args, **kw):
+        out = super().load_state_dict(*args, **kw)
+        self.invalidate_packed()
+        return out
+
+    def train(self, mode=True):
+        self.invalidate_packed()
+        return super().train(mode)
 
     # ------------------------------------------------------------------ forward
     def _projection_rows(self, first, count):
@@ -235,9 +253,18 @@ class _DimeNetFamily(nn.Module):
         dev = pos.device
         v_in_all = torch.zeros(L + 1, g.n_nodes, self.hidden_channels, dtype=torch.float32, device=dev)
         v_all = torch.empty(L + 1, g.n_nodes, self.out_channels, dtype=torch.float32, device=dev)
-        dense_tc = os.environ.get("DIG3D_DENSE", "tc") != "simt"
+        # dense edge-MLP chain: "h16" (default) = two tiles in flight per SM, 3xFP16 operands (csrc/spherenet_h16.cu);
+        # "tc" = first-generation 3xTF32 chain with fp32 operand range (csrc/spherenet_tc.cu); "simt" = exact-fp32 FFMA
+        # twin (csrc/spherenet.cu).  All three are sm_100a kernels of libdig3d.so.
+        dense = os.environ.get("DIG3D_DENSE", "h16")
+        if dense not in ("h16", "tc", "simt"):
+            raise ValueError(f"DIG3D_DENSE={dense!r}: expected h16, tc or simt")
         tc_cache = self.__dict__.setdefault("_tc_cache", {})
-        if dense_tc:
+        if dense == "h16":
+            packed = ops.tc_pack_matrix(self.init_e.lin.weight, tc_cache, "init_e.lin", kind="h16")
+            e1, _ = ops.sphere_init_e_h16(z, g, rbf0, ops.pack_init_e(self.init_e), packed, self.hidden_channels,
+                                          v_in=v_in_all[0])
+        elif dense == "tc":
             packed = ops.tc_pack_matrix(self.init_e.lin.weight, tc_cache, "init_e.lin")
             e1, _ = ops.sphere_init_e_tc(z, g, rbf0, ops.pack_init_e(self.init_e), packed, self.hidden_channels,
                                          v_in=v_in_all[0])
@@ -246,11 +273,15 @@ class _DimeNetFamily(nn.Module):
                                       v_in=v_in_all[0])
         for l in range(L):
             sbf_p, t_p = proj[l // 4]
-            if dense_tc:      # tcgen05 3xTF32 dense chain (csrc/spherenet_tc.cu)
+            if dense == "h16":
+                wt = ops.tc_pack_update_e(self.update_es[l], self._torsion, tc_cache, kind="h16")
+                e1, _, _, _ = ops.sphere_update_e_h16(e1, g, rbf0, sbf_p, t_p, 8 * (l % 4), wt,
+                                                      self.hidden_channels, self.int_emb_size, v_in=v_in_all[l + 1])
+            elif dense == "tc":
                 wt = ops.tc_pack_update_e(self.update_es[l], self._torsion, tc_cache)
                 e1, _, _, _ = ops.sphere_update_e_tc(e1, g, rbf0, sbf_p, t_p, 8 * (l % 4), wt,
                                                      self.hidden_channels, self.int_emb_size, v_in=v_in_all[l + 1])
-            else:             # exact-fp32 FFMA tile engine (csrc/spherenet.cu), kept as the validation twin
+            else:
                 e1, _ = ops.sphere_update_e(e1, g, rbf0, sbf_p, t_p, 8 * (l % 4),
                                             ops.pack_update_e(self.update_es[l], self._torsion),
                                             self.hidden_channels, self.int_emb_size, v_in=v_in_all[l + 1])

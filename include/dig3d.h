@@ -219,6 +219,28 @@ int dig3d_tc_trace(int32_t on, long long* out64);
 /* 1: MUFU-only swish in the tensor-path epilogues (faster, ~1e-6 less accurate); default 0. */
 int dig3d_tc_set_fast_swish(int32_t on);
 
+/* ---- second-generation dense chain: two 128-edge tiles in flight per SM, fp16 x3 split operands on tcgen05
+ * (csrc/spherenet_h16.cu).  Same arithmetic contract as the *_tc entry points above (update_e.forward
+ * spherenet.py:150-182, init.forward spherenet.py:79-91); `w` is a dig3d_tc_update_e whose p_* members point to
+ * dig3d_h16_pack output (4*N*K bytes per matrix: K/32 slabs of [hi|lo][4][N][8 halves], w*64 = hi + lo).
+ * Activations must stay below 8190 in magnitude: larger values poison the affected energies with inf/NaN and
+ * raise the flag returned by dig3d_h16_overflow (the *_tc chain has fp32 range and is the fallback). */
+int64_t dig3d_h16_packed_bytes(int32_t n, int32_t k);
+int dig3d_h16_pack(const float* const* weights, const int32_t* n, const int32_t* k, void* const* outs, int32_t count,
+                   void* stream);
+int dig3d_sphere_init_e_h16(const int64_t* z, const int32_t* src, const int32_t* dst, const float* rbf0,
+                            int64_t n_edges, const dig3d_init_e_weights* w, const void* packed_lin, float* e1,
+                            float* v_in, void* stream);
+int dig3d_sphere_update_e_a_h16(const float* e1, const float* rbf0, int64_t n_edges, const dig3d_tc_update_e* w,
+                                float* x_ji, float* x_down, void* stream);
+int dig3d_sphere_update_e_b_h16(const float* m, const float* e1_in, const float* x_ji, const float* rbf0,
+                                const int32_t* dst, int64_t n_edges, const dig3d_tc_update_e* w, float* e1_out,
+                                float* v_in, void* stream);
+/* 1 if an operand left the fp16 range since the flag was last cleared (synchronises the device). */
+int dig3d_h16_overflow(int32_t clear);
+int dig3d_h16_timeouts(void);
+int dig3d_h16_set_fast_swish(int32_t on);
+
 /* ------------------------------------------------------------------ SchNet
  * One interaction (update_e + update_v, schnet.py:29-35,53-59) for hidden_channels == num_filters in
  * {32, 64, 128}:  vlin = lin(v);  agg[i] = sum_{j->i} vlin[j] * mlp(gauss(d)) * C(d);

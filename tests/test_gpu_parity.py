@@ -336,6 +336,99 @@ def test_tensor_core_chain_matches_fp32_twin(cls_name):
     assert ops.tc_timeouts() == 0
 
 
+@pytest.mark.parametrize("cls_name", ["SphereNet", "DimeNetPP"])
+def test_two_tile_fp16_chain_matches_fp32_twin(cls_name):
+    """update_e / init_e on the second-generation chain (two tiles in flight, 3xFP16 operands) vs the exact-fp32
+    FFMA twin: one block, ragged last tile AND an odd tile count (the last CTA owns a single tile)."""
+    from dig_b200 import ops
+    from dig_b200.data import synthetic_batch
+    from dig_b200.threedgraph import method
+    dev = torch.device("cuda:0")
+    tors = cls_name == "SphereNet"
+    model = getattr(method, cls_name)()
+    model.load_state_dict(formula_state_dict(model.state_dict(), seed=2))
+    model = model.to(dev)
+    for nmol in (24, 11, 1):
+        b = synthetic_batch(nmol, "qm9", seed=2, variable=True).to(dev)
+        g = ops.build_graph(b.pos, b.batch, 5.0, num_graphs=nmol)
+        ops.triplet_geometry(g, b.pos, use_torsion=tors, want_idx=False)
+        rbf0, bess = ops.edge_basis(g.dist, 5.0, 5, model.emb.dist_emb.freq, 0, not tors, 6, 42)
+        w_s, w_t = model._projection_rows(0, 4)
+        sbf_p, t_p = ops.triplet_basis_project(g, bess, 0, w_s, w_t)
+        e1_s, v_s = ops.sphere_init_e(b.z, g, rbf0, ops.pack_init_e(model.init_e), 128)
+        cache = {}     # owns the packed weight buffers: must outlive the kernels that read them
+        packed = ops.tc_pack_matrix(model.init_e.lin.weight, cache, "k", kind="h16")
+        e1_t, v_t = ops.sphere_init_e_h16(b.z, g, rbf0, ops.pack_init_e(model.init_e), packed, 128)
+        assert rel_err(e1_t.cpu().numpy(), e1_s.cpu().numpy()) < TOL, nmol
+        assert rel_err(v_t.cpu().numpy(), v_s.cpu().numpy()) < TOL, nmol
+        ue = model.update_es[1]
+        e_ref, v_ref = ops.sphere_update_e(e1_s, g, rbf0, sbf_p, t_p, 8, ops.pack_update_e(ue, tors), 128, 64)
+        e_h, v_h, _, _ = ops.sphere_update_e_h16(e1_s, g, rbf0, sbf_p, t_p, 8,
+                                                 ops.tc_pack_update_e(ue, tors, cache, kind="h16"), 128, 64)
+        assert rel_err(e_h.cpu().numpy(), e_ref.cpu().numpy()) < TOL, nmol
+        assert rel_err(v_h.cpu().numpy(), v_ref.cpu().numpy()) < TOL, nmol
+    assert ops.tc_timeouts() == 0 and not ops.h16_overflow()
+
+
+def test_fp16_chain_flags_out_of_range_activations():
+    """Operands of the 3xFP16 chain must stay below 8190: a larger activation poisons the energies (inf / NaN) and
+    raises the overflow flag; the 3xTF32 chain (DIG3D_DENSE=tc) has fp32 range and still matches the oracle."""
+    import os
+    from oracle import restated
+    from dig_b200 import ops
+    from dig_b200.data import synthetic_batch
+    from dig_b200.threedgraph.method import DimeNetPP
+    dev = torch.device("cuda:0")
+    model = DimeNetPP()
+    sd = formula_state_dict(model.state_dict(), seed=3)
+    sd["init_e.lin.bias"] = sd["init_e.lin.bias"] + 3.0e4          # e1 = swish(. + 3e4) ~ 3e4 > 8190
+    model.load_state_dict(sd)
+    model = model.to(dev)
+    b = synthetic_batch(3, "qm9", seed=5).to(dev)
+    ops.h16_overflow(clear=True)
+    with torch.no_grad():
+        u = model(b)
+    assert ops.h16_overflow(clear=True) and not torch.isfinite(u).all()
+    os.environ["DIG3D_DENSE"] = "tc"
+    try:
+        with torch.no_grad():
+            u_tc = model(b)
+    finally:
+        del os.environ["DIG3D_DENSE"]
+    ref = restated.dimenetpp_forward({k: v.to(dev) for k, v in sd.items()}, b.z, b.pos, b.batch)
+    assert torch.isfinite(u_tc).all() and rel_err(u_tc.cpu().numpy(), ref.cpu().numpy()) < TOL
+
+
+def test_headline_config_matches_oracle_at_full_size():
+    """BASELINE configs[1] at the size bench.py times (SphereNet defaults, 128 QM9-shape molecules, bench seeds):
+    every energy vs the oracle on the same GPU to 1e-5 -- 269 tiles over 148 SMs (ragged last tile, odd tile
+    count), for each dense chain; no barrier timeout, no fp16 range overflow."""
+    import os
+    from oracle import restated
+    from dig_b200 import ops
+    from dig_b200.data import synthetic_batch
+    from dig_b200.threedgraph.method import SphereNet
+    dev = torch.device("cuda:0")
+    model = SphereNet()
+    sd = formula_state_dict(model.state_dict(), seed=2)
+    model.load_state_dict(sd)
+    model = model.to(dev)
+    b = synthetic_batch(128, "qm9", seed=2).to(dev)
+    with torch.no_grad():
+        ref = restated.spherenet_forward({k: v.to(dev) for k, v in sd.items()}, b.z, b.pos, b.batch)
+    ops.h16_overflow(clear=True)
+    for dense in ("h16", "tc"):
+        os.environ["DIG3D_DENSE"] = dense
+        try:
+            with torch.no_grad():
+                u = model(b)
+        finally:
+            del os.environ["DIG3D_DENSE"]
+        assert u.shape == ref.shape == (128, 1) and torch.isfinite(u).all()
+        assert rel_err(u.cpu().numpy(), ref.cpu().numpy()) < TOL, dense
+    assert ops.tc_timeouts() == 0 and not ops.h16_overflow()
+
+
 def test_packed_weights_follow_parameter_updates():
     """The tcgen05 weight cache is keyed on tensor._version: an in-place optimiser-style update must be seen."""
     from dig_b200.data import synthetic_batch
