@@ -25,45 +25,62 @@ constexpr int NF1 = 12, NF2 = 6; // num_radial * num_spherical^2, num_radial * n
 // a0_in/a1_in: nearest / second-nearest IN-edge of each node (scatter_min over the target index);
 // a0_out/a1_out: the same over the OUT-edges (scatter_min over the source index).  Ties keep the
 // first edge id; nodes without edges get 0 (argmin >= E -> 0, comenet.py:305).
+// Reference quirk reproduced (comenet.py:305-308,318-322): the +cutoff penalty of the second pass is written with
+// `add[argmin0] = cutoff` AFTER the empty segments were mapped to edge 0, so whenever ANY node of the batch has no
+// in-edge (resp. out-edge -- routine under the 32-neighbour cap), edge 0 is penalised too, which can change the
+// second-nearest reference atom of dst[0] (resp. src[0]).  PASS 0 finds the nearest edges and raises the two
+// batch-wide flags; PASS 1 (a second launch) finds the second-nearest ones.
+template <int PASS>
 __global__ void comenet_refs_kernel(const float* __restrict__ dist, const int32_t* __restrict__ src,
                                     const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ graph_ptr,
                                     const int64_t* __restrict__ batch, int n_nodes, float cutoff,
                                     int32_t* __restrict__ a0_in, int32_t* __restrict__ a1_in,
-                                    int32_t* __restrict__ a0_out, int32_t* __restrict__ a1_out) {
+                                    int32_t* __restrict__ a0_out, int32_t* __restrict__ a1_out,
+                                    int32_t* __restrict__ flags /* [2]: some node has no in-edge / no out-edge */) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= n_nodes) return;
   const float INF = __int_as_float(0x7f800000);
   {
     const int b = row_ptr[n], e = row_ptr[n + 1];
-    int best = -1; float bv = INF;
-    for (int k = b; k < e; ++k) { const float d = dist[k]; if (d < bv) { bv = d; best = k; } }
-    int sec = -1; float sv = INF;
-    for (int k = b; k < e; ++k) {
-      const float d = (k == best) ? __fadd_rn(dist[k], cutoff) : dist[k];
-      if (d < sv) { sv = d; sec = k; }
+    if (PASS == 0) {
+      int best = -1; float bv = INF;
+      for (int k = b; k < e; ++k) { const float d = dist[k]; if (d < bv) { bv = d; best = k; } }
+      a0_in[n] = best < 0 ? 0 : best;
+      if (best < 0) atomicOr(flags, 1);
+    } else {
+      const int best = a0_in[n];
+      const bool pen0 = flags[0] != 0;
+      int sec = -1; float sv = INF;
+      for (int k = b; k < e; ++k) {
+        const float d = (k == best || (pen0 && k == 0)) ? __fadd_rn(dist[k], cutoff) : dist[k];
+        if (d < sv) { sv = d; sec = k; }
+      }
+      a1_in[n] = sec < 0 ? 0 : sec;
     }
-    a0_in[n] = best < 0 ? 0 : best;
-    a1_in[n] = sec < 0 ? 0 : sec;
   }
   {
     const int g = (int)batch[n];
     const int lo = graph_ptr[g], hi = graph_ptr[g + 1];
-    int best = -1, sec = -1; float bv = INF, sv = INF;
-    for (int pass = 0; pass < 2; ++pass) {
-      for (int i = lo; i < hi; ++i) {
-        if (i == n) continue;
-        const int ib = row_ptr[i], di = row_ptr[i + 1] - ib;
-        int a = 0, b = di;
-        while (a < b) { int mid = (a + b) >> 1; if (src[ib + mid] < n) a = mid + 1; else b = mid; }
-        if (a < di && src[ib + a] == n) {
-          const int e = ib + a;
-          if (pass == 0) { const float d = dist[e]; if (d < bv) { bv = d; best = e; } }
-          else { const float d = (e == best) ? __fadd_rn(dist[e], cutoff) : dist[e]; if (d < sv) { sv = d; sec = e; } }
-        }
+    const int best0 = PASS == 0 ? -1 : a0_out[n];
+    const bool pen0 = PASS == 1 && flags[1] != 0;
+    int best = -1; float bv = INF;
+    for (int i = lo; i < hi; ++i) {
+      if (i == n) continue;
+      const int ib = row_ptr[i], di = row_ptr[i + 1] - ib;
+      int a = 0, b = di;
+      while (a < b) { int mid = (a + b) >> 1; if (src[ib + mid] < n) a = mid + 1; else b = mid; }
+      if (a < di && src[ib + a] == n) {
+        const int e = ib + a;
+        const float d = (PASS == 1 && (e == best0 || (pen0 && e == 0))) ? __fadd_rn(dist[e], cutoff) : dist[e];
+        if (d < bv) { bv = d; best = e; }
       }
     }
-    a0_out[n] = best < 0 ? 0 : best;
-    a1_out[n] = sec < 0 ? 0 : sec;
+    if (PASS == 0) {
+      a0_out[n] = best < 0 ? 0 : best;
+      if (best < 0) atomicOr(flags + 1, 1);
+    } else {
+      a1_out[n] = best < 0 ? 0 : best;
+    }
   }
 }
 
@@ -384,15 +401,19 @@ extern "C" {
 
 int dig3d_comenet_geometry(const float* pos, const float* dist, const int32_t* src, const int32_t* dst,
                            const int32_t* row_ptr, const int32_t* graph_ptr, const int64_t* batch,
-                           int64_t n_nodes, int64_t n_edges, double cutoff, int32_t* refs /*[4, N]*/,
+                           int64_t n_nodes, int64_t n_edges, double cutoff, int32_t* refs /*[4 * N + 2]*/,
                            float* feature1, float* feature2, float* angles, void* stream) {
   DIG3D_REQUIRE(pos && dist && src && dst && row_ptr && graph_ptr && batch && refs && feature1 && feature2,
                 "comenet_geometry: null pointer");
   if (n_nodes == 0) return DIG3D_OK;
   cudaStream_t st = (cudaStream_t)stream;
   int32_t* a0i = refs; int32_t* a1i = refs + n_nodes; int32_t* a0o = refs + 2 * n_nodes; int32_t* a1o = refs + 3 * n_nodes;
-  comenet_refs_kernel<<<ceil_div(n_nodes, 128), 128, 0, st>>>(dist, src, row_ptr, graph_ptr, batch, (int)n_nodes,
-                                                            (float)cutoff, a0i, a1i, a0o, a1o);
+  int32_t* flags = refs + 4 * n_nodes;
+  cudaMemsetAsync(flags, 0, 2 * sizeof(int32_t), st);
+  comenet_refs_kernel<0><<<ceil_div(n_nodes, 128), 128, 0, st>>>(dist, src, row_ptr, graph_ptr, batch, (int)n_nodes,
+                                                               (float)cutoff, a0i, a1i, a0o, a1o, flags);
+  comenet_refs_kernel<1><<<ceil_div(n_nodes, 128), 128, 0, st>>>(dist, src, row_ptr, graph_ptr, batch, (int)n_nodes,
+                                                               (float)cutoff, a0i, a1i, a0o, a1o, flags);
   DIG3D_LAUNCH_CHECK();
   if (n_edges) {
     comenet_edge_features_kernel<<<ceil_div(n_edges, 128), 128, 0, st>>>(

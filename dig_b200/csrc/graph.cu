@@ -33,7 +33,7 @@ __global__ void graph_ptr_kernel(const int64_t* __restrict__ batch, int n_nodes,
   // node n opens every graph in (batch[n-1], batch[n]]; n == n_nodes closes the tail.
   int64_t prev = (n == 0) ? -1 : batch[n - 1];
   int64_t cur = (n == n_nodes) ? (int64_t)n_graphs : batch[n];
-  for (int64_t g = prev + 1; g <= cur && g <= n_graphs; ++g) ptr[g] = n;
+  for (int64_t g = prev < -1 ? 0 : prev + 1; g <= cur && g <= n_graphs; ++g) ptr[g] = n;   // invalid ids: see validate_nodes
 }
 
 // ------------------------------------------------------------------ radius neighbours
@@ -41,11 +41,13 @@ __global__ void graph_ptr_kernel(const int64_t* __restrict__ batch, int n_nodes,
 // torch_cluster's radius_kernel: d2 accumulated as fma(diff, diff, d2), strict '<', at most
 // `cap` hits counted INCLUDING the query itself, which is then dropped.
 __global__ void radius_neighbors_kernel(const float* __restrict__ pos, const int64_t* __restrict__ batch,
-                                        const int32_t* __restrict__ ptr, int n_nodes, float r2, int cap,
+                                        const int32_t* __restrict__ ptr, int n_nodes, int n_graphs, float r2, int cap,
                                         int32_t* __restrict__ nbr, int32_t* __restrict__ deg) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= n_nodes) return;
-  int g = (int)batch[n];
+  const int64_t gb = batch[n];
+  if (gb < 0 || gb >= n_graphs) { deg[n] = 0; return; }   // reported by validate_nodes_kernel; never index ptr[] with it
+  int g = (int)gb;
   int lo = ptr[g], hi = ptr[g + 1];
   f3 q = load3(pos, n);
   int hits = 0, m = 0;
@@ -60,6 +62,20 @@ __global__ void radius_neighbors_kernel(const float* __restrict__ pos, const int
     }
   }
   deg[n] = m;
+}
+
+// Index validation (the reference's nn.Embedding / scatter raise a device-side assert for these): bit 0 = a batch
+// id outside [0, n_graphs), bit 1 = batch not sorted ascending, bit 2 = an atomic number outside [0, z_rows).
+__global__ void validate_nodes_kernel(const int64_t* __restrict__ batch, const int64_t* __restrict__ z, int n_nodes,
+                                      int n_graphs, int z_rows, int32_t* __restrict__ flags) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_nodes) return;
+  int bad = 0;
+  const int64_t b = batch[n];
+  if (b < 0 || b >= n_graphs) bad |= 1;
+  if (n > 0 && batch[n - 1] > b) bad |= 2;
+  if (z) { const int64_t zz = z[n]; if (zz < 0 || zz >= z_rows) bad |= 4; }
+  if (bad) atomicOr(flags, bad);
 }
 
 __device__ __forceinline__ int find_sorted(const int32_t* __restrict__ list, int len, int key) {
@@ -344,14 +360,24 @@ int dig3d_graph_ptr(const int64_t* batch, int64_t n_nodes, int64_t n_graphs, int
   return DIG3D_OK;
 }
 
+int dig3d_validate_nodes(const int64_t* batch, const int64_t* z, int64_t n_nodes, int64_t n_graphs, int32_t z_rows,
+                         int32_t* flags, void* stream) {
+  DIG3D_REQUIRE(batch && flags, "validate_nodes: null pointer");
+  if (n_nodes == 0) return DIG3D_OK;
+  validate_nodes_kernel<<<ceil_div(n_nodes, 256), 256, 0, (cudaStream_t)stream>>>(batch, z, (int)n_nodes,
+                                                                                (int)n_graphs, z_rows, flags);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
 int dig3d_radius_neighbors(const float* pos, const int64_t* batch, const int32_t* ptr, int64_t n_nodes,
-                           double cutoff, int32_t cap, int32_t* nbr, int32_t* deg, void* stream) {
+                           int64_t n_graphs, double cutoff, int32_t cap, int32_t* nbr, int32_t* deg, void* stream) {
   DIG3D_REQUIRE(pos && batch && ptr && nbr && deg, "radius_neighbors: null pointer");
   DIG3D_REQUIRE(cap >= 1 && cap <= GEO_MAXDEG, "radius_neighbors: cap=%d outside [1,%d]", cap, GEO_MAXDEG);
   if (n_nodes == 0) return DIG3D_OK;
   const float r2 = (float)(cutoff * cutoff);
   radius_neighbors_kernel<<<ceil_div(n_nodes, 128), 128, 0, (cudaStream_t)stream>>>(
-      pos, batch, ptr, (int)n_nodes, r2, cap, nbr, deg);
+      pos, batch, ptr, (int)n_nodes, (int)n_graphs, r2, cap, nbr, deg);
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
 }

@@ -51,7 +51,9 @@ struct HSmem {
   float wr1[64];
   int dst[2][H_M];
   int aux[2][2][H_M];                              // init_e: atomic numbers of the target / source node of each row
-  uint64_t full[H_STAGES], empty[H_STAGES], a_ready[2], d_ready[2], d_free[2];
+  // d_ready / d_free are indexed [tile][accumulator]: each barrier has ONE waiter that sees every phase in order
+  // (a parity wait may never lag or lead its barrier by two phases, which a barrier shared by the tiles allows)
+  uint64_t full[H_STAGES], empty[H_STAGES], a_ready[2], d_ready[2][2], d_free[2][2];
   uint32_t tmem_base;
 };
 static_assert(sizeof(HSmem) <= 227 * 1024, "HSmem exceeds the shared memory of an SM");
@@ -88,10 +90,14 @@ __device__ __forceinline__ void h_producer(HSmem& s, const HGemm (&g)[NG], int n
   }
 }
 
-// ---- MMA issuer: jobs alternate between the tiles; one K = 64 chunk (two slabs) per TMEM accumulator
+// ---- MMA issuer: jobs alternate between the tiles; one K = 64 chunk (two slabs) per TMEM accumulator.  The two
+// accumulators are shared by the tiles: before chunk `ch` overwrites accumulator ch & 1, the tile that used it last
+// (chunk ch - 2, possibly the other tile) must have drained it.
 template <int NG>
 __device__ __forceinline__ void h_mma(HSmem& s, const HGemm (&g)[NG], int ntile, uint32_t tmem) {
   int it = 0, ch = 0;
+  int uses00 = 0, uses01 = 0, uses10 = 0, uses11 = 0;   // uses[tile][accumulator] so far
+  int last0 = -1, last1 = -1;                            // tile that used accumulator 0 / 1 last
   for (int q = 0; q < NG; ++q) {
     const int nslab = g[q].K / H_SLAB_K, n = g[q].N;
     const uint32_t idesc = idesc_f16(H_M, n);
@@ -101,7 +107,13 @@ __device__ __forceinline__ void h_mma(HSmem& s, const HGemm (&g)[NG], int ntile,
       const uint32_t a_hi = smem_u32(s.a[t][0]), a_lo = smem_u32(s.a[t][1]);
       for (int c = 0; c < nslab; ++c, ++it) {
         const int st = it % H_STAGES, ab = ch & 1;
-        if ((c & 1) == 0) mbar_wait(&s.d_free[ab], ((ch >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
+        if ((c & 1) == 0) {
+          const int lt = ab ? last1 : last0;
+          if (lt >= 0) {
+            const int u = lt ? (ab ? uses11 : uses10) : (ab ? uses01 : uses00);
+            mbar_wait(&s.d_free[lt][ab], (u - 1) & 1);   // that tile's epilogue has drained this accumulator
+          }
+        }
         mbar_wait(&s.full[st], (it / H_STAGES) & 1);
         tc_fence_after();
         const uint32_t w_hi = smem_u32(s.w[st]), w_lo = w_hi + 4u * n * 16u;
@@ -119,7 +131,12 @@ __device__ __forceinline__ void h_mma(HSmem& s, const HGemm (&g)[NG], int ntile,
           mma_f16(d, smem_desc(a_hi + a_off, H_AKU * 16, 128), smem_desc(w_hi + b_off, n * 16, 128), idesc, 1);
         }
         mma_commit(&s.empty[st]);
-        if (c & 1) { mma_commit(&s.d_ready[ab]); ++ch; }
+        if (c & 1) {
+          mma_commit(&s.d_ready[t][ab]);
+          if (t) { if (ab) ++uses11; else ++uses10; } else { if (ab) ++uses01; else ++uses00; }
+          if (ab) last1 = t; else last0 = t;
+          ++ch;
+        }
       }
     }
   }
@@ -129,7 +146,8 @@ __device__ __forceinline__ void h_mma(HSmem& s, const HGemm (&g)[NG], int ntile,
 struct HCtx {
   int t, et, row, half;     // tile in the pair, thread index within the tile's epilogue, row, column half
   uint32_t tl;              // TMEM address of this warp's lane quarter, column 0
-  int ntile, ch;            // tiles in this CTA, accumulator-chunk counter (shared by construction with the issuer)
+  int ntile, ch;            // tiles in this CTA, global accumulator-chunk counter (same sequence as the issuer's)
+  int use0, use1;           // chunks of THIS tile drained from accumulator 0 / 1 so far (barrier phases)
   float amax;               // largest |activation| written as an operand (range check)
 };
 __device__ __forceinline__ HCtx h_ctx(const HSmem& s, int ntile) {
@@ -137,7 +155,7 @@ __device__ __forceinline__ HCtx h_ctx(const HSmem& s, int ntile) {
   const int t = (warp - 2) / H_TILE_WARPS, we = (warp - 2) % H_TILE_WARPS;
   const int quarter = warp & 3;   // a warp may only touch TMEM lanes [32*(warp%4), +32)
   return {t, (int)threadIdx.x - 64 - t * H_TILE_THREADS, 32 * quarter + lane, we >> 2,
-          s.tmem_base + ((uint32_t)(32 * quarter) << 16), ntile, 0, 0.f};
+          s.tmem_base + ((uint32_t)(32 * quarter) << 16), ntile, 0, 0, 0, 0.f};
 }
 __device__ __forceinline__ void h_tile_bar(int t) {
   asm volatile("bar.sync %0, %1;" ::"r"(1 + t), "n"(H_TILE_THREADS) : "memory");
@@ -193,17 +211,17 @@ __device__ __forceinline__ void h_load_tile(HSmem& s, HCtx& c, const float* __re
     h_store_ku(s, c, row, ku, x);
   }
 }
-// Skip the accumulator chunks of the OTHER tile's job of this layer (keeps c.ch in step with the issuer).
-__device__ __forceinline__ void h_skip_before(HCtx& c, int chunks) { if (c.t == 1) c.ch += chunks; }
-__device__ __forceinline__ void h_skip_after(HCtx& c, int chunks) { if (c.t == 0 && c.ntile == 2) c.ch += chunks; }
 // Streaming accumulation of this tile's job: each finished K = 64 chunk is added (round to nearest) into the
-// thread's fp32 registers; NP 16-column pieces starting at column col0.
+// thread's fp32 registers; NP 16-column pieces starting at column col0.  The global chunk counter advances over the
+// other tile's chunks of the same layer without touching a barrier (they use that tile's own barriers).
 template <int NP, bool FIRST>
 __device__ __forceinline__ void h_drain(HSmem& s, HCtx& c, int col0, int chunks, float (&acc)[NP * 16]) {
-  h_skip_before(c, chunks);
+  if (c.t == 1) c.ch += chunks;
   for (int k = 0; k < chunks; ++k, ++c.ch) {
     const int ab = c.ch & 1;
-    mbar_wait(&s.d_ready[ab], (c.ch >> 1) & 1);
+    const int use = ab ? c.use1 : c.use0;
+    mbar_wait(&s.d_ready[c.t][ab], use & 1);
+    if (ab) ++c.use1; else ++c.use0;
     tc_fence_after();
     const uint32_t ta = c.tl + 128u * ab + col0;
 #pragma unroll
@@ -228,17 +246,16 @@ __device__ __forceinline__ void h_drain(HSmem& s, HCtx& c, int col0, int chunks,
     }
     tc_fence_before();
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive(&s.d_free[ab]);   // one arrival per warp
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&s.d_free[c.t][ab]);   // one arrival per warp
   }
-  h_skip_after(c, chunks);
+  if (c.t == 0 && c.ntile == 2) c.ch += chunks;
 }
 __device__ __forceinline__ void h_setup(HSmem& s) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < H_STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s.a_ready[i], H_TILE_WARPS);
-      mbar_init(&s.d_ready[i], 1);
-      mbar_init(&s.d_free[i], H_TILE_WARPS);
+      for (int j = 0; j < 2; ++j) { mbar_init(&s.d_ready[i][j], 1); mbar_init(&s.d_free[i][j], H_TILE_WARPS); }
     }
     mbar_fence_init();
   }

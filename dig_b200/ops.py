@@ -49,11 +49,14 @@ class Graph3D:
 
 
 def build_graph(pos, batch, cutoff, num_graphs=None, max_num_neighbors=32, want_vec=False,
-                want_edge_index=True):
+                want_edge_index=True, z=None, z_rows=0):
     """radius_graph(pos, r=cutoff, batch) (reference spherenet.py:304 etc.) + triplet offsets.
 
     One host<->device synchronisation: the edge and triplet totals (two ints) are read back to size
-    the per-edge / per-triplet buffers (the reference path has >= 10 implicit syncs)."""
+    the per-edge / per-triplet buffers (the reference path has >= 10 implicit syncs).
+    The same read-back carries the index validation (batch ids inside [0, num_graphs) and sorted; with `z`,
+    atomic numbers inside the `z_rows`-row embedding table): the reference's nn.Embedding / scatter raise a
+    device-side assert for those, here they raise ValueError before any kernel indexes with them."""
     if pos.dim() != 2 or pos.size(1) != 3:
         raise ValueError(f"pos must be [N, 3], got {tuple(pos.shape)}")
     n = pos.size(0)
@@ -75,14 +78,22 @@ def build_graph(pos, batch, cutoff, num_graphs=None, max_num_neighbors=32, want_
     nbr = torch.empty(max(n, 1) * cap, dtype=torch.int32, device=dev)
     deg = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
     tcnt = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
-    call("dig3d_radius_neighbors", _p(pos, torch.float32, "pos"), _p(batch), _p(g.graph_ptr), n,
+    totals = torch.zeros(4, dtype=torch.int32, device=dev)
+    if z is not None and z.shape != (n,):
+        raise ValueError("z must be [N]")
+    call("dig3d_validate_nodes", _p(batch), _p(z, torch.int64, "z"), n, g.n_graphs, int(z_rows),
+         ctypes.c_void_p(totals.data_ptr() + 8), st)
+    call("dig3d_radius_neighbors", _p(pos, torch.float32, "pos"), _p(batch), _p(g.graph_ptr), n, g.n_graphs,
          float(cutoff), cap, _p(nbr), _p(deg), st)
     call("dig3d_triplet_count", _p(nbr), _p(deg), n, cap, _p(tcnt), st)
     g.row_ptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
     node_trip_ptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
-    totals = torch.empty(4, dtype=torch.int32, device=dev)
     call("dig3d_scan_counts", _p(deg), _p(tcnt), n, _p(g.row_ptr), _p(node_trip_ptr), _p(totals), st)
-    tot = totals[:2].tolist()                      # the one sync of the forward pass
+    tot = totals[:3].tolist()                      # the one sync of the forward pass
+    if tot[2]:
+        what = [msg for bit, msg in ((1, f"batch ids outside [0, {g.n_graphs})"), (2, "batch is not sorted ascending"),
+                                     (4, f"atomic numbers outside the {z_rows}-row embedding table")) if tot[2] & bit]
+        raise ValueError("invalid node indices: " + "; ".join(what))
     g.n_edges, g.n_triplets = int(tot[0]), int(tot[1])
     e = g.n_edges
     g.src = torch.empty(max(e, 1), dtype=torch.int32, device=dev)[:e]
@@ -314,7 +325,7 @@ def schnet_readout(v, lin1, lin2, out_channels):
 def comenet_geometry(g, pos, cutoff, want_angles=False):
     dev = pos.device
     e, n = g.n_edges, g.n_nodes
-    refs = torch.empty(4 * max(n, 1), dtype=torch.int32, device=dev)
+    refs = torch.empty(4 * max(n, 1) + 2, dtype=torch.int32, device=dev)   # + the two batch-wide "empty segment" flags
     f1 = torch.empty(max(e, 1), 12, dtype=torch.float32, device=dev)[:e]
     f2 = torch.empty(max(e, 1), 6, dtype=torch.float32, device=dev)[:e]
     angles = torch.empty(e, 3, dtype=torch.float32, device=dev) if want_angles else None

@@ -29,6 +29,29 @@ def shard_molecules(molecules, rank=None, world=None):
     return molecules[lo:hi]
 
 
+def shard_molecules_equal(molecules, rank=None, world=None):
+    """This rank's contiguous slice with the SAME length on every rank (the trailing len % world molecules are
+    dropped): data-parallel training needs identical step counts per epoch, or the ranks issue different numbers
+    of gradient all-reduces and the collectives pair up gradients of different steps (then hang)."""
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside [0, {world})")
+    per = len(molecules) // world
+    return molecules[rank * per:(rank + 1) * per]
+
+
+def rank():
+    return dist.get_rank() if dist.is_initialized() else 0
+
+
+def barrier():
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()
+
+
 def max_over_ranks(value, device="cpu"):
     """max of a python float over all ranks (bench timing rule: the slowest rank defines the step)."""
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)

@@ -169,7 +169,7 @@ class ComENet(nn.Module):
         batch, z, pos = data.batch, data.z.long(), data.pos
         require_cuda(pos, "ComENet.forward")
         g = ops.build_graph(pos, batch, self.cutoff, num_graphs=getattr(data, "num_graphs", None),
-                            want_edge_index=False)
+                            want_edge_index=False, z=z, z_rows=self.emb.emb.num_embeddings)
         f1, f2, _ = ops.comenet_geometry(g, pos, self.cutoff)
         if wants_grad(self) or self._generic:
             return self._forward_train(z, g, f1, f2)

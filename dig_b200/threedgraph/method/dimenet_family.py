@@ -234,7 +234,8 @@ class _DimeNetFamily(nn.Module):
         if self.energy_and_force:
             pos.requires_grad_()                      # reference dimenetpp.py:275-276
         ns, nr = self.num_spherical, self.num_radial
-        g = ops.build_graph(pos, batch, self.cutoff, num_graphs=getattr(batch_data, "num_graphs", None))
+        g = ops.build_graph(pos, batch, self.cutoff, num_graphs=getattr(batch_data, "num_graphs", None),
+                            z=z, z_rows=self.init_e.emb.num_embeddings)
         if wants_grad(self) or self._generic:
             return self._forward_train(z, pos, g)
         ops.triplet_geometry(g, pos, use_torsion=self._torsion, want_idx=False)

@@ -139,7 +139,8 @@ class ProNet(nn.Module):
         pos, batch = batch_data.coords_ca, batch_data.batch
         require_cuda(pos, "ProNet.forward")
         g = ops.build_graph(pos, batch, self.cutoff, num_graphs=getattr(batch_data, "num_graphs", None),
-                            max_num_neighbors=self.max_num_neighbors, want_edge_index=False)
+                            max_num_neighbors=self.max_num_neighbors, want_edge_index=False,
+                            z=z.reshape(-1), z_rows=num_aa_type)
         lvl = 0 if self.level == 'aminoacid' else 1
         f0, f1, pe, _, _ = ops.pronet_edge_features(
             g, pos, batch_data.coords_n if lvl else None, batch_data.coords_c if lvl else None, lvl, self.cutoff,

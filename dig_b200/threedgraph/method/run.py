@@ -46,7 +46,8 @@ class run():
         for d in (save_dir, log_dir):
             if d != '':
                 os.makedirs(d, exist_ok=True)
-        writer = self._open_writer(log_dir)
+        main = parallel.rank() == 0          # data-parallel launch: one writer of checkpoints / event files
+        writer = self._open_writer(log_dir) if main else None
         best = {'valid': float('inf'), 'test': float('inf')}
         for epoch in range(1, epochs + 1):
             maes = self._epoch(epoch, model, optimizer, loaders, energy_and_force, p, loss_func, evaluation, device)
@@ -55,8 +56,9 @@ class run():
                     writer.add_scalar(key + '_mae', maes[key], epoch)
             if maes['valid'] < best['valid']:
                 best = {'valid': maes['valid'], 'test': maes['test']}
-                if save_dir != '':
+                if save_dir != '' and main:
                     self._checkpoint(save_dir, epoch, model, optimizer, scheduler, best['valid'], num_params)
+            parallel.barrier()               # unconditional (a rank-dependent branch must never guard a collective)
             scheduler.step()
         print(f"Best validation MAE so far: {best['valid']}")
         print(f"Test MAE when got best validation result: {best['test']}")
@@ -66,9 +68,11 @@ class run():
     @staticmethod
     def _loaders(train_dataset, valid_dataset, test_dataset, batch_size, vt_batch_size):
         """Shuffled training loader, ordered validation / test loaders (reference run.py:53-55).  Under a data-parallel
-        launch (one process per GPU) every rank trains on its contiguous shard of the molecules."""
+        launch (one process per GPU) every rank trains on its contiguous shard of the molecules; the shards have the
+        SAME length (the trailing len % world molecules are dropped), so every rank runs the same number of steps
+        with the same batch sizes and issues the same number of gradient all-reduces per epoch."""
         if parallel.world_size() > 1:
-            train_dataset = parallel.shard_molecules(train_dataset)
+            train_dataset = parallel.shard_molecules_equal(train_dataset)
         return {'train': DataLoader(train_dataset, batch_size, shuffle=True),
                 'valid': DataLoader(valid_dataset, vt_batch_size, shuffle=False),
                 'test': DataLoader(test_dataset, vt_batch_size, shuffle=False)}

@@ -119,7 +119,7 @@ class SchNet(nn.Module):
         if self.energy_and_force:
             pos.requires_grad_()                      # reference schnet.py:153-154
         g = ops.build_graph(pos, batch, self.cutoff, num_graphs=getattr(batch_data, "num_graphs", None),
-                            want_edge_index=False)
+                            want_edge_index=False, z=z, z_rows=self.init_v.num_embeddings)
         if wants_grad(self) or self._generic:
             return self._forward_train(z, pos, g)
         # v = init_v(z): an embedding row gather (torch indexing = plumbing, no arithmetic)

@@ -44,7 +44,13 @@ int dig3d_graph_ptr(const int64_t* batch, int64_t n_nodes, int64_t n_graphs, int
 /* nbr[n*cap + s] = s-th in-neighbour (ascending) of node n, deg[n] = count (self excluded);
  * cap = max_num_neighbors + 1. */
 int dig3d_radius_neighbors(const float* pos, const int64_t* batch, const int32_t* ptr, int64_t n_nodes,
-                           double cutoff, int32_t cap, int32_t* nbr, int32_t* deg, void* stream);
+                           int64_t n_graphs, double cutoff, int32_t cap, int32_t* nbr, int32_t* deg, void* stream);
+
+/* Index validation (the reference's nn.Embedding / scatter raise a device-side assert for these; e.g.
+ * spherenet.py:86 `self.emb(x)`): ORs into *flags (caller-zeroed) bit 0 = a batch id outside [0, n_graphs),
+ * bit 1 = batch not sorted ascending, bit 2 = an atomic number outside [0, z_rows) (z nullable). */
+int dig3d_validate_nodes(const int64_t* batch, const int64_t* z, int64_t n_nodes, int64_t n_graphs, int32_t z_rows,
+                         int32_t* flags, void* stream);
 
 /* tcnt[i] = number of triplets (k->j->i, k != i) over the in-edges of node i. */
 int dig3d_triplet_count(const int32_t* nbr, const int32_t* deg, int64_t n_nodes, int32_t cap,
@@ -266,8 +272,9 @@ int dig3d_schnet_readout(const float* v, int64_t n_nodes, int32_t hidden, const 
 /* ------------------------------------------------------------------ ComENet (hidden 256, middle 64, nr=3, ns=2)
  * dig3d_comenet_geometry: reference atoms (4x scatter_min, comenet.py:304-327), theta/phi/tau
  * (comenet.py:365-385) and the basis features feature1[E,12] / feature2[E,6]
- * (comenet/features.py:289-295,340-348).  refs: [4, N] int32 workspace (nearest / second-nearest
- * in-edge, nearest / second-nearest out-edge of every node); angles: nullable [E,3] (theta,phi,tau). */
+ * (comenet/features.py:289-295,340-348).  refs: [4 * N + 2] int32 workspace (nearest / second-nearest
+ * in-edge, nearest / second-nearest out-edge of every node, then two batch-wide flags "some node has no in-edge /
+ * no out-edge": the reference penalises edge 0 in that case, comenet.py:305-308); angles: nullable [E,3]. */
 int dig3d_comenet_geometry(const float* pos, const float* dist, const int32_t* src, const int32_t* dst,
                            const int32_t* row_ptr, const int32_t* graph_ptr, const int64_t* batch,
                            int64_t n_nodes, int64_t n_edges, double cutoff, int32_t* refs, float* feature1,

@@ -123,3 +123,32 @@ def test_training_path_with_isolated_atoms_and_no_triplets(cls_name):
     out2 = model(b2)
     out2.sum().backward()
     assert out2.shape == (2, 1) and torch.isfinite(out2).all()
+
+
+def test_out_of_range_indices_raise_instead_of_reading_out_of_bounds():
+    """an atomic number outside the embedding table, a batch id >= num_graphs or an unsorted batch vector
+    raise ValueError at the forward's one sync point (the reference's nn.Embedding / scatter assert on the device)."""
+    from dig_b200 import ops
+    from dig_b200.data import synthetic_batch
+    from dig_b200.threedgraph.method import DimeNetPP, SchNet
+    dev = torch.device("cuda:0")
+    b = synthetic_batch(3, "qm9", seed=1).to(dev)
+    model = DimeNetPP().to(dev)
+    with torch.no_grad():
+        ok = model(b)
+        assert torch.isfinite(ok).all()
+        bad = synthetic_batch(3, "qm9", seed=1).to(dev)
+        bad.z[4] = 95
+        with pytest.raises(ValueError, match="atomic numbers"):
+            model(bad)
+        bad.z[4] = -1
+        with pytest.raises(ValueError, match="atomic numbers"):
+            SchNet(num_layers=2, hidden_channels=32, num_filters=32).to(dev)(bad)
+    with pytest.raises(ValueError, match="batch ids"):
+        ops.build_graph(b.pos, b.batch, 5.0, num_graphs=2)
+    unsorted = b.batch.clone()
+    unsorted[0] = 2
+    with pytest.raises(ValueError, match="not sorted"):
+        ops.build_graph(b.pos, unsorted, 5.0, num_graphs=3)
+    g = ops.build_graph(b.pos, b.batch, 5.0, num_graphs=3)       # the context is still healthy afterwards
+    assert g.n_edges > 0

@@ -206,6 +206,32 @@ def test_comenet_geometry_bit_exact():
     assert torch.equal(f1, f1_ref) and torch.equal(f2, f2_ref)
 
 
+def test_comenet_reference_atoms_when_a_node_has_no_out_edge():
+    """comenet.py:305-308,318-322: `add[argmin0] = cutoff` is written after the empty segments were mapped to edge 0,
+    so when any node of the BATCH has no out-edge (routine under the 32-neighbour cap) edge 0 is penalised in the
+    second scatter_min as well.  A dense 70-atom cluster behind a 5-atom molecule: theta / phi / tau of every edge
+    (including molecule 0's, which owns edge 0) stay bit-equal to the reference's op sequence."""
+    from dig_b200 import ops
+    from oracle import restated
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(5)
+    # molecule 0: edge 0 is (1 -> 0) and it is node 1's SECOND-nearest out-edge (nearest: 1 -> 2), so the extra
+    # penalty on edge 0 moves node 1's second reference atom from node 0 to node 3
+    mol0 = torch.tensor([[0.0, 1.5, 0.0], [0.0, 0.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 2.2], [2.0, 2.0, 0.3]])
+    pos = torch.cat([mol0, 20.0 + torch.rand(70, 3, generator=gen) * 3.0]).to(dev)
+    batch = torch.cat([torch.zeros(5, dtype=torch.long), torch.ones(70, dtype=torch.long)]).to(dev)
+    ei = restated.radius_graph(pos, 6.0, batch)
+    out_deg = torch.bincount(ei[0], minlength=75)
+    assert int((out_deg == 0).sum()) > 0 and int(torch.bincount(ei[1], minlength=75).min()) > 0
+    dist, theta, phi, tau = restated.comenet_geometry(pos, ei, 75, 6.0)
+    f1_ref, f2_ref = restated.comenet_features(dist, theta, phi, tau, 6.0)
+    gr = ops.build_graph(pos, batch, 6.0)
+    f1, f2, ang = ops.comenet_geometry(gr, pos, 6.0, want_angles=True)
+    assert torch.equal(gr.edge_index, ei)
+    assert torch.equal(ang[:, 0], theta) and torch.equal(ang[:, 1], phi) and torch.equal(ang[:, 2], tau)
+    assert torch.equal(f1, f1_ref) and torch.equal(f2, f2_ref)
+
+
 def test_comenet_energy_parity():
     from oracle import restated
     g, z, pos, batch, model, sd = _comenet_setup()
@@ -214,9 +240,10 @@ def test_comenet_energy_parity():
     ref = restated.comenet_forward(sd, z, pos, batch, cutoff=6.0)
     assert u.shape == ref.shape == (2, 1)
     assert rel_err(u.cpu().numpy(), ref.cpu().numpy()) < TOL
-    # vs the CPU fixture: bounded by the reference's own fp32/fp64 floor (2.6e-1 here)
-    floor = rel_err(g["energy_f32"], g["energy_f64"])
-    assert rel_err(u.cpu().numpy(), g["energy_f32"]) < max(TOL, floor)
+    # The CPU fixture (g["energy_f32"]) is NOT compared here: the reference's own fp32-vs-fp64 gap on this case is
+    # 2.6e-1 (0/0 noise in phi / tau), so a CPU-vs-GPU energy check cannot fail.  The fixture pins the
+    # oracle bit for bit on the CPU instead (tests/test_oracle.py::test_restated_matches_golden_bitwise[comenet_oc20]),
+    # and the oracle's op sequence executed on this GPU is the checker above.
 
 
 def test_xyz_to_dat_api_matches_reference_outputs():

@@ -61,13 +61,15 @@ def test_radius_graph_ordering_and_cap():
     assert not torch.any(i == j)
 
 
-@pytest.mark.parametrize("name", ["spherenet_qm9", "dimenetpp_md17", "spherenet_ns3", "schnet_cfg1"])
+@pytest.mark.parametrize("name", ["spherenet_qm9", "dimenetpp_md17", "spherenet_ns3", "schnet_cfg1", "comenet_oc20"])
 def test_restated_matches_golden_bitwise(name):
     g, z, pos, batch = case_inputs(name)
     model_name, kw, _, wseed = CASES[name]
     sd = _formula_sd(model_name, kw, wseed)
     if model_name == "SchNet":
         u = restated.schnet_forward(sd, z, pos, batch, cutoff=kw["cutoff"], num_layers=kw["num_layers"])
+    elif model_name == "ComENet":
+        u = restated.comenet_forward(sd, z, pos, batch, cutoff=kw["cutoff"])
     else:
         u = restated.dimenet_family_forward(sd, z, pos, batch, torsion=(model_name == "SphereNet"),
                                             cutoff=kw["cutoff"], num_spherical=kw.get("num_spherical", 7))

@@ -43,6 +43,18 @@ def _worker(rank, world, port, ret):
         dist.destroy_process_group()
 
 
+def test_equal_shards_give_equal_step_counts():
+    """961 molecules on 2 ranks at batch_size 32 must give the same number of steps on both ranks."""
+    from dig_b200 import parallel
+    from dig_b200.data import DataLoader, synthetic_molecules
+    mols = synthetic_molecules(13, "qm9", seed=0)
+    for world in (2, 3, 4):
+        shards = [parallel.shard_molecules_equal(mols, r, world) for r in range(world)]
+        assert len({len(s) for s in shards}) == 1 and sum(len(s) for s in shards) == 13 - 13 % world
+        assert shards[0][0] is mols[0] and shards[-1][-1] is mols[world * (13 // world) - 1]
+        assert len({len(DataLoader(s, 2, shuffle=True)) for s in shards}) == 1
+
+
 def test_two_rank_gloo_sharding_and_reductions():
     world = 2
     ret = mp.Manager().dict()
