@@ -67,6 +67,10 @@ struct HGemm {
 
 static __device__ unsigned int g_h16_overflow = 0;
 static int h16_fast_swish = 1;
+// optional timeline probe: CTA 0 of update_e part B records clock64() at protocol points (tools/gpu_h16_timeline.py)
+static __device__ long long g_h16_trace[128];
+static __device__ int g_h16_trace_on = 0;
+#define H_TRACE(slot) do { if (TRACE && g_h16_trace_on && blockIdx.x == 0) g_h16_trace[(slot)] = clock64(); } while (0)
 
 template <bool FAST>
 __device__ __forceinline__ float hswish(float x) {
@@ -93,7 +97,7 @@ __device__ __forceinline__ void h_producer(HSmem& s, const HGemm (&g)[NG], int n
 // ---- MMA issuer: jobs alternate between the tiles; one K = 64 chunk (two slabs) per TMEM accumulator.  The two
 // accumulators are shared by the tiles: before chunk `ch` overwrites accumulator ch & 1, the tile that used it last
 // (chunk ch - 2, possibly the other tile) must have drained it.
-template <int NG>
+template <int NG, bool TRACE = false>
 __device__ __forceinline__ void h_mma(HSmem& s, const HGemm (&g)[NG], int ntile, uint32_t tmem) {
   int it = 0, ch = 0;
   int uses00 = 0, uses01 = 0, uses10 = 0, uses11 = 0;   // uses[tile][accumulator] so far
@@ -104,6 +108,7 @@ __device__ __forceinline__ void h_mma(HSmem& s, const HGemm (&g)[NG], int ntile,
     for (int t = 0; t < ntile; ++t) {
       mbar_wait(&s.a_ready[t], q & 1);
       tc_fence_after();
+      if (q < 8) H_TRACE((q * 2 + t) * 2);
       const uint32_t a_hi = smem_u32(s.a[t][0]), a_lo = smem_u32(s.a[t][1]);
       for (int c = 0; c < nslab; ++c, ++it) {
         const int st = it % H_STAGES, ab = ch & 1;
@@ -138,6 +143,7 @@ __device__ __forceinline__ void h_mma(HSmem& s, const HGemm (&g)[NG], int ntile,
           ++ch;
         }
       }
+      if (q < 8) H_TRACE((q * 2 + t) * 2 + 1);
     }
   }
 }
@@ -326,6 +332,7 @@ sphere_update_e_b_h16_kernel(const float* __restrict__ m, const float* __restric
   HSmem& s = *reinterpret_cast<HSmem*>(h_raw);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int n_tiles = (n_edges + H_M - 1) / H_M, tile0 = blockIdx.x * 2, ntile = min(2, n_tiles - tile0);
+  if (tid == 0 && g_h16_trace_on && blockIdx.x == 0) { g_h16_trace[100] = clock64(); g_h16_trace[101] = (long long)global_ns(); }
   h_setup(s);
   for (int i = tid; i < 8 * 128; i += H_THREADS) {
     const float* b = P.g[i / 128].bias;
@@ -344,9 +351,11 @@ sphere_update_e_b_h16_kernel(const float* __restrict__ m, const float* __restric
   if (warp == 0) {
     if (tid == 0) h_producer(s, P.g, ntile);
   } else if (warp == 1) {
-    if (tid == 32) h_mma(s, P.g, ntile, s.tmem_base);
+    if (tid == 32) h_mma<8, true>(s, P.g, ntile, s.tmem_base);
   } else if ((c = h_ctx(s, ntile)).t < ntile) {
     epi = true;
+    constexpr bool TRACE = true;
+    const bool probe = c.et == 0;
     const int e0 = (tile0 + c.t) * H_M, rows = min(H_M, n_edges - e0);
     const bool valid = c.row < rows;
     const size_t ge = (size_t)(e0 + c.row);
@@ -364,7 +373,9 @@ sphere_update_e_b_h16_kernel(const float* __restrict__ m, const float* __restric
 #pragma unroll 1
     for (int q = 0; q < 8; ++q) {
       float acc[64];
+      if (probe) H_TRACE(32 + c.t * 32 + q * 4);
       h_drain<4, true>(s, c, col0, q == 0 ? 1 : 2, acc);
+      if (probe) H_TRACE(32 + c.t * 32 + q * 4 + 1);
       const bool add_stash = (q == 2 || q == 5 || q == 7);
       const bool to_stash = (q == 0 || q == 3 || q == 5);
       float rb[6];
@@ -423,15 +434,19 @@ sphere_update_e_b_h16_kernel(const float* __restrict__ m, const float* __restric
           }
         }
       }
+      if (probe) H_TRACE(32 + c.t * 32 + q * 4 + 2);
       if (q < 7) {
         if (to_stash) tmem_st_wait();
         h_epi_done(s, c.t);
       }
+      if (probe) H_TRACE(32 + c.t * 32 + q * 4 + 3);
     }
     h_tile_bar(c.t);
     h_segment_sums(s, c, rows, v_in);   // spherenet.py:211
+    if (probe) H_TRACE(96 + c.t);
   }
   h_finish(s, epi ? &c : nullptr);
+  if (tid == 0 && g_h16_trace_on && blockIdx.x == 0) { g_h16_trace[102] = clock64(); g_h16_trace[103] = (long long)global_ns(); }
 }
 
 // ---------------------------------------------------------------------------------- update_e part A
@@ -693,6 +708,13 @@ int dig3d_h16_overflow(int32_t clear) {
     cudaMemcpyToSymbol(g_h16_overflow, &zero, sizeof(zero));
   }
   return (int)v;
+}
+
+int dig3d_h16_trace(int32_t on, long long* out128 /* host, 128 entries, nullable */) {
+  if (out128) cudaMemcpyFromSymbol(out128, g_h16_trace, sizeof(long long) * 128);
+  int v = on ? 1 : 0;
+  cudaMemcpyToSymbol(g_h16_trace_on, &v, sizeof(v));
+  return DIG3D_OK;
 }
 
 int dig3d_h16_timeouts(void) {

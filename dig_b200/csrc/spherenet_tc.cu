@@ -291,6 +291,127 @@ sphere_triplet_gather_kernel(const float* __restrict__ x_down, const float* __re
   m[(size_t)e * 64 + lane + 32] = a1;
 }
 
+// ---------------------------------------------------------------------------------- triplet gather, node-centred
+// Same result as sphere_triplet_gather_kernel, organised around the SOURCE node j of the edges: every out-edge
+// (j -> i) sums over the same in-edges (k -> j) of j, whose x_down rows are CONTIGUOUS in the target-sorted edge
+// list.  One CTA per node j stages those rows (<= 33 x 256 B) in shared memory with ONE bulk copy (cp.async.bulk,
+// mbarrier completion) and then serves all out-edges of j from it: the per-triplet 256-byte L2 gathers of the
+// edge-centred kernel (~125 MB / launch at the headline size, profiles/r01_gather_ncu_summary.txt) become
+// E x 256 B of coalesced staging.  The out-edges of j are discovered on the fly (one binary search per atom of
+// the molecule); their order does not matter, every m[e] is produced by exactly one warp (no atomics).
+constexpr int TGN_THREADS = 128;
+constexpr int TGN_MAXIN = 64;     // in-degree supported (cap + 1 <= 64, same bound as GEO_MAXDEG in graph.cu)
+constexpr int TGN_LIST = 256;     // out-edges handled per pass
+
+template <bool TORSION>
+__global__ void __launch_bounds__(TGN_THREADS)
+sphere_triplet_gather_node_kernel(const float* __restrict__ x_down, const float* __restrict__ sbf_p,
+                                  const float* __restrict__ t_p, const int32_t* __restrict__ src,
+                                  const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ trip_ptr,
+                                  const int32_t* __restrict__ graph_ptr, const int64_t* __restrict__ batch,
+                                  int n_nodes, const float* __restrict__ w_sbf2, const float* __restrict__ w_t2,
+                                  float* __restrict__ m) {
+  extern __shared__ __align__(128) float tgn_rows[];          // [cap][64]: x_down rows of j's in-edges
+  float (*rows)[64] = reinterpret_cast<float (*)[64]>(tgn_rows);
+  __shared__ __align__(16) float stage[TGN_THREADS / 32][2][64];
+  __shared__ int in_src[TGN_MAXIN];
+  __shared__ int out_e[TGN_LIST], out_p[TGN_LIST];
+  __shared__ int n_out;
+  __shared__ uint64_t bar;
+  const int j = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int base = row_ptr[j], d = row_ptr[j + 1] - base;
+  const int g = (int)batch[j], lo = graph_ptr[g], hi = graph_ptr[g + 1];
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+    n_out = 0;
+  }
+  __syncthreads();
+  if (tid == 0 && d > 0) {
+    mbar_arrive_expect_tx(&bar, (uint32_t)d * 256u);
+    bulk_g2s(&rows[0][0], x_down + (size_t)base * 64, (uint32_t)d * 256u, &bar);
+  }
+  for (int k = tid; k < d; k += TGN_THREADS) in_src[k] = src[base + k];
+  float ws2[2][8], wt2[2][8];
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      ws2[h][q] = __ldg(w_sbf2 + (lane + 32 * h) * 8 + q);
+      wt2[h][q] = TORSION ? __ldg(w_t2 + (lane + 32 * h) * 8 + q) : 0.f;
+    }
+  __syncthreads();
+  bool staged = false;
+  for (int c0 = lo; c0 < hi; c0 += TGN_LIST) {
+    // out-edges (j -> i) with i in [c0, c0 + TGN_LIST): edge id and the position of i among j's in-neighbours
+    for (int i = c0 + tid; i < min(hi, c0 + TGN_LIST); i += TGN_THREADS) {
+      if (i == j) continue;
+      const int ib = row_ptr[i], di = row_ptr[i + 1] - ib;
+      int a = 0, b = di;
+      while (a < b) { const int mid = (a + b) >> 1; if (src[ib + mid] < j) a = mid + 1; else b = mid; }
+      if (a < di && src[ib + a] == j) {
+        int pa = 0, pb = d;
+        while (pa < pb) { const int mid = (pa + pb) >> 1; if (in_src[mid] < i) pa = mid + 1; else pb = mid; }
+        const int slot = atomicAdd(&n_out, 1);
+        out_e[slot] = ib + a;
+        out_p[slot] = (pa < d && in_src[pa] == i) ? pa : d;
+      }
+    }
+    __syncthreads();
+    const int no = n_out;
+    if (!staged && no > 0 && d > 0) { mbar_wait(&bar, 0); staged = true; }
+    for (int idx = w; idx < no; idx += TGN_THREADS / 32) {
+      const int e = out_e[idx], p_i = out_p[idx];
+      const int t0 = trip_ptr[e], nt = d - (p_i < d ? 1 : 0);
+      float a0 = 0.f, a1 = 0.f;
+      for (int r0 = 0; r0 < nt; r0 += 8) {
+        const int n8 = min(8, nt - r0), lim = n8 * 8;
+        const float* sp = sbf_p + (size_t)(t0 + r0) * 8;
+        const float sa = lane < lim ? __ldg(sp + lane) : 0.f, sb = lane + 32 < lim ? __ldg(sp + lane + 32) : 0.f;
+        float ta = 0.f, tb = 0.f;
+        if (TORSION) {
+          const float* tp = t_p + (size_t)(t0 + r0) * 8;
+          ta = lane < lim ? __ldg(tp + lane) : 0.f; tb = lane + 32 < lim ? __ldg(tp + lane + 32) : 0.f;
+        }
+        __syncwarp();
+        stage[w][0][lane] = sa; stage[w][0][lane + 32] = sb;
+        if (TORSION) { stage[w][1][lane] = ta; stage[w][1][lane + 32] = tb; }
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (u < n8) {
+            const int r = r0 + u, row = r + (r >= p_i ? 1 : 0);
+            const float x0 = rows[row][lane], x1 = rows[row][lane + 32];
+            const float4 s0 = *reinterpret_cast<const float4*>(&stage[w][0][u * 8]);
+            const float4 s1 = *reinterpret_cast<const float4*>(&stage[w][0][u * 8 + 4]);
+            const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            float g0 = 0.f, g1 = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { g0 = fmaf(ws2[0][q], sv[q], g0); g1 = fmaf(ws2[1][q], sv[q], g1); }
+            float m0 = __fmul_rn(x0, g0), m1 = __fmul_rn(x1, g1);
+            if (TORSION) {
+              const float4 q0 = *reinterpret_cast<const float4*>(&stage[w][1][u * 8]);
+              const float4 q1 = *reinterpret_cast<const float4*>(&stage[w][1][u * 8 + 4]);
+              const float tv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+              float h0 = 0.f, h1 = 0.f;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) { h0 = fmaf(wt2[0][q], tv[q], h0); h1 = fmaf(wt2[1][q], tv[q], h1); }
+              m0 = __fmul_rn(m0, h0); m1 = __fmul_rn(m1, h1);
+            }
+            a0 += m0; a1 += m1;
+          }
+        }
+      }
+      m[(size_t)e * 64 + lane] = a0;
+      m[(size_t)e * 64 + lane + 32] = a1;
+    }
+    __syncthreads();
+    if (tid == 0) n_out = 0;
+    __syncthreads();
+  }
+}
+
 // ---------------------------------------------------------------------------------- weight packing
 // W [N, K] (nn.Linear layout) -> [K/32][hi|lo][8][N][4], hi/lo = TF32 split.  One launch packs up to 16 matrices.
 struct PackJob { const float* w; float* out; int N, K, trans; };   // trans: the source is stored [K, N] (W^T)
@@ -925,6 +1046,28 @@ int dig3d_sphere_triplet_gather(const float* x_down, const float* sbf_p, const f
   else
     sphere_triplet_gather_kernel<false><<<gblocks, 256, 0, st>>>(x_down, sbf_p, t_p, src, dst, row_ptr, trip_ptr,
                                                                 (int)n_edges, w_sbf2, w_t2, m);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_sphere_triplet_gather_node(const float* x_down, const float* sbf_p, const float* t_p, int32_t ld_p,
+                                     const int32_t* src, const int32_t* row_ptr, const int32_t* trip_ptr,
+                                     const int32_t* graph_ptr, const int64_t* batch, int64_t n_nodes, int32_t cap,
+                                     const float* w_sbf2, const float* w_t2, float* m, void* stream) {
+  DIG3D_REQUIRE(x_down && sbf_p && src && row_ptr && trip_ptr && graph_ptr && batch && w_sbf2 && m,
+                "sphere_triplet_gather_node: null pointer");
+  DIG3D_REQUIRE((t_p != nullptr) == (w_t2 != nullptr), "sphere_triplet_gather_node: t_p and w_t2 must agree");
+  DIG3D_REQUIRE(ld_p == 8, "sphere_triplet_gather_node: expects the layer-major [T, 8] slices (ld_p == 8), got %d", ld_p);
+  DIG3D_REQUIRE(cap >= 1 && cap <= TGN_MAXIN, "sphere_triplet_gather_node: cap=%d outside [1,%d]", cap, TGN_MAXIN);
+  DIG3D_REQUIRE(((uintptr_t)x_down & 15) == 0, "sphere_triplet_gather_node: x_down must be 16-byte aligned");
+  if (n_nodes == 0) return DIG3D_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (t_p)
+    sphere_triplet_gather_node_kernel<true><<<(int)n_nodes, TGN_THREADS, (size_t)cap * 256, st>>>(
+        x_down, sbf_p, t_p, src, row_ptr, trip_ptr, graph_ptr, batch, (int)n_nodes, w_sbf2, w_t2, m);
+  else
+    sphere_triplet_gather_node_kernel<false><<<(int)n_nodes, TGN_THREADS, (size_t)cap * 256, st>>>(
+        x_down, sbf_p, t_p, src, row_ptr, trip_ptr, graph_ptr, batch, (int)n_nodes, w_sbf2, w_t2, m);
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
 }

@@ -502,6 +502,19 @@ def sphere_update_e_tc(e1, g, rbf0, sbf_p, t_p, col0, w, hidden, int_emb, v_in=N
     return e1_out, v_in, x_ji, x_down
 
 
+GATHER_MODE = ["node"]       # "node" (source-node CTAs, shared-memory staged rows) | "edge" (one warp per edge)
+
+
+def triplet_gather(x_down, sp, tp, g, w_sbf2, w_t2, m_out, st):
+    """m[e] = sum_t x_down[kj] * lin_sbf2(sbf_p) * lin_t2(t_p)  (spherenet.py:163-171); sp / tp are layer slices."""
+    if GATHER_MODE[0] == "node":
+        call("dig3d_sphere_triplet_gather_node", _p(x_down), sp, tp, 8, _p(g.src), _p(g.row_ptr), _p(g.trip_ptr),
+             _p(g.graph_ptr), _p(g.batch, torch.int64), g.n_nodes, g.cap, w_sbf2, w_t2, _p(m_out), st)
+    else:
+        call("dig3d_sphere_triplet_gather", _p(x_down), sp, tp, 8, _p(g.src), _p(g.dst), _p(g.row_ptr),
+             _p(g.trip_ptr), g.n_edges, w_sbf2, w_t2, _p(m_out), st)
+
+
 def sphere_init_e_h16(z, g, rbf0, w, packed_lin, hidden, v_in=None):
     e1 = torch.empty(max(g.n_edges, 1), hidden, dtype=torch.float32, device=rbf0.device)[:g.n_edges]
     if v_in is None:
@@ -527,8 +540,7 @@ def sphere_update_e_h16(e1, g, rbf0, sbf_p, t_p, col0, w, hidden, int_emb, v_in=
         call("dig3d_sphere_update_e_a_h16", _p(e1), _p(rbf0), e, ctypes.byref(w), _p(x_ji), _p(x_down), st)
         sp = ctypes.c_void_p(sbf_p[col0 // 8].data_ptr())
         tp = ctypes.c_void_p(t_p[col0 // 8].data_ptr()) if t_p is not None else None
-        call("dig3d_sphere_triplet_gather", _p(x_down), sp, tp, 8, _p(g.src), _p(g.dst), _p(g.row_ptr),
-             _p(g.trip_ptr), e, w.w_sbf2, w.w_t2, _p(m_ws), st)
+        triplet_gather(x_down, sp, tp, g, w.w_sbf2, w.w_t2, m_ws, st)
         call("dig3d_sphere_update_e_b_h16", _p(m_ws), _p(e1), _p(x_ji), _p(rbf0), _p(g.dst), e, ctypes.byref(w),
              _p(e1_out), _p(v_in), st)
     return e1_out, v_in, x_ji, x_down

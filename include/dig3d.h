@@ -216,6 +216,14 @@ int dig3d_sphere_triplet_gather(const float* x_down, const float* sbf_p, const f
                                 const int32_t* src, const int32_t* dst, const int32_t* row_ptr,
                                 const int32_t* trip_ptr, int64_t n_edges, const float* w_sbf2, const float* w_t2,
                                 float* m, void* stream);
+/* The same sums organised around the SOURCE node: one CTA per node j stages the x_down rows of j's in-edges
+ * (contiguous in the target-sorted edge list, <= cap x 256 B) in shared memory with one cp.async.bulk and serves
+ * every out-edge (j -> i) of j from it.  Every edge that has a source is written (all of m[E, 64]); cap = the
+ * max_num_neighbors + 1 the graph was built with. */
+int dig3d_sphere_triplet_gather_node(const float* x_down, const float* sbf_p, const float* t_p, int32_t ld_p,
+                                     const int32_t* src, const int32_t* row_ptr, const int32_t* trip_ptr,
+                                     const int32_t* graph_ptr, const int64_t* batch, int64_t n_nodes, int32_t cap,
+                                     const float* w_sbf2, const float* w_t2, float* m, void* stream);
 /* lin_up + residual stack + lin (spherenet.py:172-180) on tcgen05; writes e1_out, ACCUMULATES e2 into v_in. */
 int dig3d_sphere_update_e_b_tc(const float* m, const float* e1_in, const float* x_ji, const float* rbf0,
                                const int32_t* dst, int64_t n_edges, const dig3d_tc_update_e* w, float* e1_out,
@@ -245,6 +253,8 @@ int dig3d_sphere_update_e_b_h16(const float* m, const float* e1_in, const float*
 /* 1 if an operand left the fp16 range since the flag was last cleared (synchronises the device). */
 int dig3d_h16_overflow(int32_t clear);
 int dig3d_h16_timeouts(void);
+/* debugging probe: enable / read the clock64() timeline CTA 0 of update_e part B records (host buffer, 128 x i64) */
+int dig3d_h16_trace(int32_t on, long long* out128);
 int dig3d_h16_set_fast_swish(int32_t on);
 
 /* ------------------------------------------------------------------ SchNet

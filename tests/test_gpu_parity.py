@@ -217,7 +217,8 @@ def test_comenet_reference_atoms_when_a_node_has_no_out_edge():
     gen = torch.Generator().manual_seed(5)
     # molecule 0: edge 0 is (1 -> 0) and it is node 1's SECOND-nearest out-edge (nearest: 1 -> 2), so the extra
     # penalty on edge 0 moves node 1's second reference atom from node 0 to node 3
-    mol0 = torch.tensor([[0.0, 1.5, 0.0], [0.0, 0.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 2.2], [2.0, 2.0, 0.3]])
+    # (generic coordinates: an exactly planar molecule would make tau a signed-zero coin flip)
+    mol0 = torch.tensor([[0.03, 1.5, 0.07], [0.0, 0.0, 0.0], [1.0, 0.02, -0.05], [0.04, -0.03, 2.2], [2.0, 2.0, 0.3]])
     pos = torch.cat([mol0, 20.0 + torch.rand(70, 3, generator=gen) * 3.0]).to(dev)
     batch = torch.cat([torch.zeros(5, dtype=torch.long), torch.ones(70, dtype=torch.long)]).to(dev)
     ei = restated.radius_graph(pos, 6.0, batch)
