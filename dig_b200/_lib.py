@@ -106,6 +106,7 @@ SIGNATURES = {
     "dig3d_wgrad": [P, P, c_int64, c_int32, c_int32, P, P, c_int32, P],
     "dig3d_act": [P, c_int64, c_int32, P, P],
     "dig3d_act_bwd": [P, P, c_int64, c_int32, P, P],
+    "dig3d_adam_step": [P, P, P, P, c_int64, c_double, c_double, c_double, c_double, c_double, c_int64, P],
     "dig3d_ewise": [P, P, c_int64, c_int32, P, P],
     "dig3d_rowscale": [P, P, c_int64, c_int32, P, P],
     "dig3d_gather_rows": [P, P, c_int32, c_int64, c_int32, P, P],

@@ -72,9 +72,29 @@ static __device__ long long g_h16_trace[128];
 static __device__ int g_h16_trace_on = 0;
 #define H_TRACE(slot) do { if (TRACE && g_h16_trace_on && blockIdx.x == 0) g_h16_trace[(slot)] = clock64(); } while (0)
 
+// x * sigmoid(x).  FAST (default): MUFU ex2 / rcp approximations in their flush-to-zero forms (the non-ftz forms
+// cost three extra instructions per element for denormal inputs that cannot occur here); measured on the B200: no
+// effect on the energy error (tools/gpu_h16_check.py).  FAST = false: libdevice expf + IEEE division.
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 template <bool FAST>
 __device__ __forceinline__ float hswish(float x) {
-  return FAST ? __fdividef(x, 1.0f + __expf(-x)) : __fdiv_rn(x, 1.0f + expf(-x));
+  return FAST ? x * rcp_ftz(1.0f + ex2_ftz(x * -1.4426950408889634f)) : __fdiv_rn(x, 1.0f + expf(-x));
+}
+// H_SA * swish(t8 / H_SA): the chain keeps its activations pre-scaled by the operand scale, so the split needs no
+// multiply and the scale costs nothing (it is folded into the accumulator scale and the bias).
+template <bool FAST>
+__device__ __forceinline__ float hswish8(float t8) {
+  return FAST ? t8 * rcp_ftz(1.0f + ex2_ftz(t8 * (-1.4426950408889634f / H_SA)))
+              : __fdiv_rn(t8, 1.0f + expf(-t8 * (1.0f / H_SA)));
 }
 
 // ---- producer: every K = 32 slab of every job (layer x tile) through the ring
@@ -154,14 +174,14 @@ struct HCtx {
   uint32_t tl;              // TMEM address of this warp's lane quarter, column 0
   int ntile, ch;            // tiles in this CTA, global accumulator-chunk counter (same sequence as the issuer's)
   int use0, use1;           // chunks of THIS tile drained from accumulator 0 / 1 so far (barrier phases)
-  float amax;               // largest |activation| written as an operand (range check)
+  bool bad;                 // a non-finite value reached an OUTPUT of the kernel (fp16 operand range exceeded upstream)
 };
 __device__ __forceinline__ HCtx h_ctx(const HSmem& s, int ntile) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = (warp - 2) / H_TILE_WARPS, we = (warp - 2) % H_TILE_WARPS;
   const int quarter = warp & 3;   // a warp may only touch TMEM lanes [32*(warp%4), +32)
   return {t, (int)threadIdx.x - 64 - t * H_TILE_THREADS, 32 * quarter + lane, we >> 2,
-          s.tmem_base + ((uint32_t)(32 * quarter) << 16), ntile, 0, 0, 0, 0.f};
+          s.tmem_base + ((uint32_t)(32 * quarter) << 16), ntile, 0, 0, 0, false};
 }
 __device__ __forceinline__ void h_tile_bar(int t) {
   asm volatile("bar.sync %0, %1;" ::"r"(1 + t), "n"(H_TILE_THREADS) : "memory");
@@ -172,16 +192,16 @@ __device__ __forceinline__ void h_epi_done(HSmem& s, int t) {
   __syncwarp();
   if ((threadIdx.x & 31) == 0) mbar_arrive(&s.a_ready[t]);
 }
-// 8 consecutive K elements of a row (one k-unit): pre-scale, split into fp16 hi / lo, one 16-byte store per plane
-__device__ __forceinline__ void h_store_ku(HSmem& s, HCtx& c, int row, int ku, const float (&x)[8]) {
+// 8 consecutive K elements of a row (one k-unit), ALREADY multiplied by H_SA: split into fp16 hi / lo, one 16-byte
+// store per plane.  A value beyond the fp16 range becomes inf here and NaN in the products; the kernels flag
+// non-finite OUTPUTS (HCtx::bad) instead of paying a range test per operand element.
+__device__ __forceinline__ void h_store_ku(HSmem& s, const HCtx& c, int row, int ku, const float (&x)[8]) {
   uint32_t h[4], l[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float a = x[2 * i] * H_SA, b = x[2 * i + 1] * H_SA;
-    c.amax = fmaxf(c.amax, fmaxf(fabsf(x[2 * i]), fabsf(x[2 * i + 1])));
-    const __half2 hh = __floats2half2_rn(a, b);
+    const __half2 hh = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
     const float2 hf = __half22float2(hh);
-    const __half2 ll = __floats2half2_rn(a - hf.x, b - hf.y);
+    const __half2 ll = __floats2half2_rn(x[2 * i] - hf.x, x[2 * i + 1] - hf.y);
     h[i] = *reinterpret_cast<const uint32_t*>(&hh);
     l[i] = *reinterpret_cast<const uint32_t*>(&ll);
   }
@@ -189,15 +209,16 @@ __device__ __forceinline__ void h_store_ku(HSmem& s, HCtx& c, int row, int ku, c
   *reinterpret_cast<uint4*>(s.a[c.t][0] + o) = make_uint4(h[0], h[1], h[2], h[3]);
   *reinterpret_cast<uint4*>(s.a[c.t][1] + o) = make_uint4(l[0], l[1], l[2], l[3]);
 }
-__device__ __forceinline__ void h_store_a16(HSmem& s, HCtx& c, int col, const float (&v)[16]) {
+__device__ __forceinline__ void h_store_a16(HSmem& s, const HCtx& c, int col, const float (&v8)[16]) {
   float x[8];
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = v[8 * u + i];
+    for (int i = 0; i < 8; ++i) x[i] = v8[8 * u + i];
     h_store_ku(s, c, c.row, (col >> 3) + u, x);
   }
 }
+__device__ __forceinline__ bool h_finite(float x) { return fabsf(x) <= 3.402823466e38f; }
 // Cooperative load of a row-major [rows x KU*8] fp32 tile (leading dimension ld floats) into the tile's planes:
 // a warp reads 32 consecutive k-units (1 KB when ld == KU*8) per step.
 template <int KU>
@@ -209,7 +230,8 @@ __device__ __forceinline__ void h_load_tile(HSmem& s, HCtx& c, const float* __re
     if (row < rows) {
       const float4 p0 = __ldg(reinterpret_cast<const float4*>(g + (size_t)row * ld + ku * 8));
       const float4 p1 = __ldg(reinterpret_cast<const float4*>(g + (size_t)row * ld + ku * 8 + 4));
-      x[0] = p0.x; x[1] = p0.y; x[2] = p0.z; x[3] = p0.w; x[4] = p1.x; x[5] = p1.y; x[6] = p1.z; x[7] = p1.w;
+      x[0] = p0.x * H_SA; x[1] = p0.y * H_SA; x[2] = p0.z * H_SA; x[3] = p0.w * H_SA;
+      x[4] = p1.x * H_SA; x[5] = p1.y * H_SA; x[6] = p1.z * H_SA; x[7] = p1.w * H_SA;
     } else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) x[i] = 0.f;
@@ -230,19 +252,17 @@ __device__ __forceinline__ void h_drain(HSmem& s, HCtx& c, int col0, int chunks,
     if (ab) ++c.use1; else ++c.use0;
     tc_fence_after();
     const uint32_t ta = c.tl + 128u * ab + col0;
+    if (FIRST && k == 0) {            // straight into the accumulator registers: all loads in flight, one wait
 #pragma unroll
-    for (int p = 0; p < NP; p += 2) {
-      uint32_t r[2][16];
-      tmem_ld16(ta + 16 * p, r[0]);
-      if (p + 1 < NP) tmem_ld16(ta + 16 * p + 16, r[1]);
+      for (int p = 0; p < NP; ++p) tmem_ld16f(ta + 16 * p, &acc[p * 16]);
       tmem_ld_wait();
-      if (FIRST && k == 0) {
+    } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          acc[p * 16 + i] = __uint_as_float(r[0][i]);
-          if (p + 1 < NP) acc[p * 16 + 16 + i] = __uint_as_float(r[1][i]);
-        }
-      } else {
+      for (int p = 0; p < NP; p += 2) {
+        uint32_t r[2][16];
+        tmem_ld16(ta + 16 * p, r[0]);
+        if (p + 1 < NP) tmem_ld16(ta + 16 * p + 16, r[1]);
+        tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           acc[p * 16 + i] = __fadd_rn(acc[p * 16 + i], __uint_as_float(r[0][i]));
@@ -268,7 +288,7 @@ __device__ __forceinline__ void h_setup(HSmem& s) {
   if ((threadIdx.x >> 5) == 0) tmem_alloc(&s.tmem_base, 512);
 }
 __device__ __forceinline__ void h_finish(HSmem& s, const HCtx* c) {
-  if (c && c->amax > H_RANGE) atomicOr(&g_h16_overflow, 1u);
+  if (c && c->bad) atomicOr(&g_h16_overflow, 1u);
   tc_fence_before();
   __syncthreads();
   if ((threadIdx.x >> 5) == 0) tmem_dealloc(s.tmem_base, 512);
@@ -336,7 +356,7 @@ sphere_update_e_b_h16_kernel(const float* __restrict__ m, const float* __restric
   h_setup(s);
   for (int i = tid; i < 8 * 128; i += H_THREADS) {
     const float* b = P.g[i / 128].bias;
-    s.bias[i / 128][i % 128] = b ? __ldg(b + i % 128) : 0.f;
+    s.bias[i / 128][i % 128] = b ? H_SA * __ldg(b + i % 128) : 0.f;          // the chain runs pre-scaled by H_SA
   }
   for (int i = tid; i < 128 * 8; i += H_THREADS) s.wr[i] = (i % 8 < 6) ? __ldg(P.w_rbf + (i / 8) * 6 + i % 8) : 0.f;
   for (int i = tid; i < 2 * H_M; i += H_THREADS) {
@@ -361,14 +381,32 @@ sphere_update_e_b_h16_kernel(const float* __restrict__ m, const float* __restric
     const size_t ge = (size_t)(e0 + c.row);
     const int col0 = c.half * 64;
     const uint32_t stash = c.tl + 256u + 128u * c.t + col0;
+    // The fp32 skip rows (x_ji for q = 0, e1_in for q = 3) are fetched into the TMEM stash while this thread would
+    // otherwise wait for its tile's MMAs, so no global load sits on the critical path of an epilogue.
+    auto prefetch_skip = [&](const float* __restrict__ src) {
+      const float* gsrc = src + ge * 128 + col0;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        uint32_t r[16];
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const float4 x = valid ? __ldg(reinterpret_cast<const float4*>(gsrc + 16 * p + i)) : make_float4(0, 0, 0, 0);
+          r[i] = __float_as_uint(x.x * H_SA); r[i + 1] = __float_as_uint(x.y * H_SA);
+          r[i + 2] = __float_as_uint(x.z * H_SA); r[i + 3] = __float_as_uint(x.w * H_SA);
+        }
+        tmem_st16(stash + 16 * p, r);
+      }
+      tmem_st_wait();
+    };
     // A0 = m tile (K = 64)
     h_load_tile<8>(s, c, m + (size_t)e0 * 64, 64, rows);
     h_epi_done(s, c.t);
-    // The eight epilogues of the chain (spherenet.py:172-179):
-    //   q=0: h = x_ji + act(lin_up(m))                       -> A, stash
+    prefetch_skip(x_ji);
+    // The eight epilogues of the chain (spherenet.py:172-179); stash = the fp32 skip / residual row (x H_SA):
+    //   q=0: h = stash(x_ji) + act(lin_up(m))                -> A, stash
     //   q=1,4,6: t = act(lin1(h))                            -> A
-    //   q=2,5: h = stash + act(lin2(t))                      -> A, stash      (q=2: stash not needed afterwards)
-    //   q=3: h = act(lin(h)) + e1_in                         -> A, stash
+    //   q=2,5: h = stash + act(lin2(t))                      -> A, stash      (q=2: then stash <- e1_in)
+    //   q=3: h = act(lin(h)) + stash(e1_in)                  -> A, stash
     //   q=7: h = stash + act(lin2(t))                        -> e1_out, e2 tile
 #pragma unroll 1
     for (int q = 0; q < 8; ++q) {
@@ -376,7 +414,7 @@ sphere_update_e_b_h16_kernel(const float* __restrict__ m, const float* __restric
       if (probe) H_TRACE(32 + c.t * 32 + q * 4);
       h_drain<4, true>(s, c, col0, q == 0 ? 1 : 2, acc);
       if (probe) H_TRACE(32 + c.t * 32 + q * 4 + 1);
-      const bool add_stash = (q == 2 || q == 5 || q == 7);
+      const bool add_stash = (q == 0 || q == 2 || q == 3 || q == 5 || q == 7);
       const bool to_stash = (q == 0 || q == 3 || q == 5);
       float rb[6];
       if (q == 7) {
@@ -386,51 +424,48 @@ sphere_update_e_b_h16_kernel(const float* __restrict__ m, const float* __restric
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
         const int col = col0 + 16 * p;
-        float v[16];
+        uint32_t r[16];
+        if (add_stash) tmem_ld16(stash + 16 * p, r);           // in flight under the 16 activations below
+        float* v = &acc[16 * p];                               // in place: v8 = H_SA * act(.)
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
           const float4 b = *reinterpret_cast<const float4*>(&s.bias[q][col + i]);
-          v[i] = hswish<FAST>(fmaf(acc[16 * p + i], H_INV, b.x));
-          v[i + 1] = hswish<FAST>(fmaf(acc[16 * p + i + 1], H_INV, b.y));
-          v[i + 2] = hswish<FAST>(fmaf(acc[16 * p + i + 2], H_INV, b.z));
-          v[i + 3] = hswish<FAST>(fmaf(acc[16 * p + i + 3], H_INV, b.w));
+          v[i] = hswish8<FAST>(fmaf(v[i], H_SA * H_INV, b.x));
+          v[i + 1] = hswish8<FAST>(fmaf(v[i + 1], H_SA * H_INV, b.y));
+          v[i + 2] = hswish8<FAST>(fmaf(v[i + 2], H_SA * H_INV, b.z));
+          v[i + 3] = hswish8<FAST>(fmaf(v[i + 3], H_SA * H_INV, b.w));
         }
         if (add_stash) {
-          uint32_t r[16];
-          tmem_ld16(stash + 16 * p, r);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] += __uint_as_float(r[i]);
         }
-        if (q == 0 || q == 3) {
-          const float* gsrc = (q == 0 ? x_ji : e1_in) + ge * 128 + col;
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            const float4 x = valid ? __ldg(reinterpret_cast<const float4*>(gsrc + i)) : make_float4(0, 0, 0, 0);
-            v[i] += x.x; v[i + 1] += x.y; v[i + 2] += x.z; v[i + 3] += x.w;
-          }
-        }
         if (q < 7) {
           if (to_stash) {
-            uint32_t r[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(v[i]);
             tmem_st16(stash + 16 * p, r);
           }
-          h_store_a16(s, c, col, v);
+          float v16[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v16[i] = v[i];
+          h_store_a16(s, c, col, v16);
         } else {
           // e1_out and e2 = lin_rbf(rbf0) * e1 (tile staged over this tile's planes; all its MMAs are done)
           float* e2t = reinterpret_cast<float*>(s.a[c.t][0]);
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
-            if (valid) *reinterpret_cast<float4*>(e1_out + ge * 128 + col + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            float o[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
+              o[u] = v[i + u] * (1.0f / H_SA);
+              c.bad |= !h_finite(o[u]);
               float gsum = 0.f;
 #pragma unroll
               for (int n = 0; n < 6; ++n) gsum = fmaf(s.wr[(col + i + u) * 8 + n], rb[n], gsum);
-              e2t[c.row * H_LDS + col + i + u] = gsum * v[i + u];
+              e2t[c.row * H_LDS + col + i + u] = gsum * o[u];
             }
+            if (valid) *reinterpret_cast<float4*>(e1_out + ge * 128 + col + i) = make_float4(o[0], o[1], o[2], o[3]);
           }
         }
       }
@@ -438,6 +473,7 @@ sphere_update_e_b_h16_kernel(const float* __restrict__ m, const float* __restric
       if (q < 7) {
         if (to_stash) tmem_st_wait();
         h_epi_done(s, c.t);
+        if (q == 2) prefetch_skip(e1_in);     // the stash was consumed above; q = 3 adds e1_in from it
       }
       if (probe) H_TRACE(32 + c.t * 32 + q * 4 + 3);
     }
@@ -464,7 +500,8 @@ sphere_update_e_a_h16_kernel(const float* __restrict__ e1, const float* __restri
   const int tid = threadIdx.x, warp = tid >> 5;
   const int n_tiles = (n_edges + H_M - 1) / H_M, tile0 = blockIdx.x * 2, ntile = min(2, n_tiles - tile0);
   h_setup(s);
-  for (int i = tid; i < 2 * 128; i += H_THREADS) s.bias[i / 128][i % 128] = __ldg(P.g[i / 128].bias + i % 128);
+  for (int i = tid; i < 2 * 128; i += H_THREADS)     // lin_ji's output leaves unscaled, lin_kj's feeds an operand (x H_SA)
+    s.bias[i / 128][i % 128] = (i / 128 ? H_SA : 1.0f) * __ldg(P.g[i / 128].bias + i % 128);
   for (int i = tid; i < 128 * 8; i += H_THREADS) s.wr[i] = __ldg(P.w_rbf2 + i);      // [128][8]
   for (int i = tid; i < 64; i += H_THREADS) s.wr1[i] = (i % 8 < 6) ? __ldg(P.w_rbf1 + (i / 8) * 6 + i % 8) : 0.f;
   tc_fence_before();
@@ -527,7 +564,7 @@ sphere_update_e_a_h16_kernel(const float* __restrict__ e1, const float* __restri
           const float4 w1 = *reinterpret_cast<const float4*>(s.wr + col * 8 + 4);
           const float gate = fmaf(w1.w, r8[7], fmaf(w1.z, r8[6], fmaf(w1.y, r8[5], fmaf(w1.x, r8[4],
                              fmaf(w0.w, r8[3], fmaf(w0.z, r8[2], fmaf(w0.y, r8[1], w0.x * r8[0])))))));
-          v[i] = hswish<FAST>(fmaf(acc[16 * p + i], H_INV, s.bias[1][col])) * gate;
+          v[i] = hswish8<FAST>(fmaf(acc[16 * p + i], H_SA * H_INV, s.bias[1][col])) * gate;
         }
         h_store_a16(s, c, col0 + 16 * p, v);
       }
@@ -609,7 +646,8 @@ sphere_init_e_h16_kernel(const int64_t* __restrict__ z, const int32_t* __restric
           const float* er = P.emb + (size_t)zrow[row] * 128 + ku * 8;
           const float4 p0 = __ldg(reinterpret_cast<const float4*>(er));
           const float4 p1 = __ldg(reinterpret_cast<const float4*>(er + 4));
-          x[0] = p0.x; x[1] = p0.y; x[2] = p0.z; x[3] = p0.w; x[4] = p1.x; x[5] = p1.y; x[6] = p1.z; x[7] = p1.w;
+          x[0] = p0.x * H_SA; x[1] = p0.y * H_SA; x[2] = p0.z * H_SA; x[3] = p0.w * H_SA;
+          x[4] = p1.x * H_SA; x[5] = p1.y * H_SA; x[6] = p1.z * H_SA; x[7] = p1.w * H_SA;
         } else {
 #pragma unroll
           for (int i = 0; i < 8; ++i) x[i] = 0.f;
@@ -633,7 +671,7 @@ sphere_init_e_h16_kernel(const int64_t* __restrict__ z, const int32_t* __restric
         float a = 0.f;
 #pragma unroll
         for (int n = 0; n < 6; ++n) a = fmaf(w0[col * 6 + n], rb[n], a);
-        v[i] = valid ? hswish<FAST>(a + s.bias[1][col]) : 0.f;
+        v[i] = valid ? H_SA * hswish<FAST>(a + s.bias[1][col]) : 0.f;
       }
       h_store_a16(s, c, col0 + 16 * p, v);
     }
@@ -648,6 +686,7 @@ sphere_init_e_h16_kernel(const int64_t* __restrict__ z, const int32_t* __restric
       for (int u = 0; u < 4; ++u) {
         const int col = col0 + i + u;
         o[u] = hswish<FAST>(fmaf(acc[i + u], H_INV, s.bias[0][col]));
+        c.bad |= !h_finite(o[u]);
         float gsum = 0.f;
 #pragma unroll
         for (int n = 0; n < 6; ++n) gsum = fmaf(s.wr[col * 8 + n], rb[n], gsum);

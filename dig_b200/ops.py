@@ -599,6 +599,15 @@ def linear(x, weight, bias=None, want_act=False):
     return (y, act_out) if want_act else y
 
 
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step):
+    """One fused Adam update over flat fp32 buffers (parallel.FlatAdam)."""
+    n = param.numel()
+    if not (grad.numel() == exp_avg.numel() == exp_avg_sq.numel() == n):
+        raise ValueError("adam_step: buffer sizes differ")
+    call("dig3d_adam_step", _p(param, F32, "param", 16), _p(grad, F32, "grad", 16), _p(exp_avg, F32, "exp_avg", 16),
+         _p(exp_avg_sq, F32, "exp_avg_sq", 16), n, lr, beta1, beta2, eps, weight_decay, int(step), _stream())
+
+
 def wgrad(dy, x, weight_shape, want_bias):
     """(dW, db) of y = x W^T + b given dy; weight_shape (N, K) or, grouped, (G, N, K) with dy [G,rows,N], x [G,rows,K]."""
     groups = weight_shape[0] if len(weight_shape) == 3 else 1

@@ -116,3 +116,186 @@ def allreduce_gradients(parameters):
         off += n
     torch._foreach_copy_(grads, views)              # one multi-tensor copy instead of ~160 small ones
     return flat.numel() * flat.element_size()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Flat parameter / gradient storage, overlapped gradient all-reduce, fused Adam
+class FlatParameters:
+    """All trainable parameters of a model as views of ONE flat fp32 buffer, their gradients as views of a second
+    one (allocated once): the gradient exchange is an all-reduce of slices of `grad` with no gather / copy-back,
+    zero_grad is one fill, and the optimizer is one kernel over the flat buffers.
+
+    Slices start at multiples of 4 elements (16 B) so that every view is vector-load aligned."""
+
+    def __init__(self, model):
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        if not self.params:
+            raise ValueError("FlatParameters: the model has no trainable parameter")
+        dev, dt = self.params[0].device, self.params[0].dtype
+        if any(p.device != dev or p.dtype != dt for p in self.params) or dt != torch.float32:
+            raise ValueError("FlatParameters: parameters must be fp32 tensors on one device")
+        self.offsets, total = [], 0
+        for p in self.params:
+            self.offsets.append(total)
+            total += (p.numel() + 3) // 4 * 4
+        self.numel = total
+        self.data = torch.zeros(total, dtype=dt, device=dev)
+        self.grad = torch.zeros(total, dtype=dt, device=dev)
+        with torch.no_grad():
+            for p, off in zip(self.params, self.offsets):
+                view = self.data[off:off + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+                p.grad = self.grad[off:off + p.numel()].view_as(p)
+        invalidate = getattr(model, "invalidate_packed", None)
+        if callable(invalidate):
+            invalidate()
+
+    def zero_grad(self):
+        """One fill; re-attaches the views if something (optimizer.zero_grad(set_to_none=True)) dropped them."""
+        self.grad.zero_()
+        for p, off in zip(self.params, self.offsets):
+            g = p.grad
+            if g is None or g.data_ptr() != self.grad.data_ptr() + 4 * off:
+                p.grad = self.grad[off:off + p.numel()].view_as(p)
+
+    def adopt_stray_gradients(self):
+        """Autograd accumulates in place into an existing .grad, so gradients normally land in the flat buffer; a
+        gradient that was replaced instead (create_graph=True accumulates out of place) is copied back in."""
+        for p, off in zip(self.params, self.offsets):
+            g = p.grad
+            if g is not None and g.data_ptr() != self.grad.data_ptr() + 4 * off:
+                view = self.grad[off:off + p.numel()].view_as(p)
+                view.copy_(g.detach())
+                p.grad = view
+
+
+class GradientReducer:
+    """Data-parallel gradient averaging over the flat gradient buffer, launched DURING backward.
+
+    The buffer is cut into `n_buckets` contiguous ranges (parameter order); a post-accumulate hook on every
+    parameter counts arrivals, and the moment the last gradient of a bucket has been written the bucket's
+    all-reduce is enqueued asynchronously (NCCL runs it on its own stream, behind an event of the compute stream),
+    i.e. under the tail of the backward pass.  `finish()` reduces whatever did not fire (parameters without a
+    gradient this step) and makes the compute stream wait for the collectives.  With world_size 1 it does nothing."""
+
+    def __init__(self, flat, n_buckets=2):
+        self.flat = flat
+        self.world = world_size()
+        self.bytes_per_step = flat.numel * 4
+        self.buckets = []          # (start, stop, [param indices])
+        if self.world == 1:
+            return
+        target = (flat.numel + n_buckets - 1) // n_buckets
+        start, members = 0, []
+        for idx, (p, off) in enumerate(zip(flat.params, flat.offsets)):
+            members.append(idx)
+            stop = off + (p.numel() + 3) // 4 * 4
+            if stop - start >= target or idx == len(flat.params) - 1:
+                self.buckets.append((start, stop, members))
+                start, members = stop, []
+        self.bucket_of = {}
+        for b, (_, _, mem) in enumerate(self.buckets):
+            for idx in mem:
+                self.bucket_of[idx] = b
+        self.pending = [0] * len(self.buckets)
+        self.works = [None] * len(self.buckets)
+        self.armed = False
+        for idx, p in enumerate(flat.params):
+            p.register_post_accumulate_grad_hook(self._make_hook(idx))
+
+    def _make_hook(self, idx):
+        def hook(_param):
+            if not self.armed:
+                return
+            b = self.bucket_of[idx]
+            self.pending[b] -= 1
+            if self.pending[b] == 0:
+                self._launch(b)
+        return hook
+
+    def _launch(self, b):
+        start, stop, _ = self.buckets[b]
+        view = self.flat.grad[start:stop]
+        if dist.get_backend() == "nccl":
+            self.works[b] = dist.all_reduce(view, op=dist.ReduceOp.AVG, async_op=True)
+        else:
+            self.works[b] = (dist.all_reduce(view, op=dist.ReduceOp.SUM, async_op=True), view)
+
+    def arm(self):
+        """Call once per step before backward."""
+        if self.world == 1:
+            return
+        self.pending = [len(mem) for _, _, mem in self.buckets]
+        self.works = [None] * len(self.buckets)
+        self.armed = True
+
+    def finish(self):
+        """Call after backward: every bucket reduced, compute stream ordered behind the collectives."""
+        if self.world == 1:
+            return
+        self.armed = False
+        self.flat.adopt_stray_gradients()
+        for b in range(len(self.buckets)):
+            if self.works[b] is None:
+                self._launch(b)
+        for b, w in enumerate(self.works):
+            if isinstance(w, tuple):            # gloo: SUM, then scale
+                w[0].wait()
+                w[1].div_(self.world)
+            else:
+                w.wait()
+        self.works = [None] * len(self.buckets)
+
+
+class FlatAdam(torch.optim.Optimizer):
+    """torch.optim.Adam semantics (amsgrad off) as ONE kernel over FlatParameters (dig3d_adam_step).
+
+    An Optimizer subclass so that lr schedulers (run.py:51 StepLR) and state_dict / load_state_dict keep working:
+    the per-parameter state entries ('step', 'exp_avg', 'exp_avg_sq') are views of the flat moment buffers, i.e. the
+    checkpoint has the keys of the reference's Adam checkpoint (run.py:92)."""
+
+    def __init__(self, flat, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        if not isinstance(flat, FlatParameters):
+            raise TypeError("FlatAdam takes a FlatParameters object")
+        self.flat = flat
+        super().__init__(flat.params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.exp_avg = torch.zeros_like(flat.data)
+        self.exp_avg_sq = torch.zeros_like(flat.data)
+        self.steps = 0
+        for p, off in zip(flat.params, flat.offsets):
+            self.state[p] = {"step": torch.tensor(0.0),
+                             "exp_avg": self.exp_avg[off:off + p.numel()].view_as(p),
+                             "exp_avg_sq": self.exp_avg_sq[off:off + p.numel()].view_as(p)}
+
+    def zero_grad(self, set_to_none=True):
+        self.flat.zero_grad()
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        from . import ops
+        loss = closure() if closure is not None else None
+        self.flat.adopt_stray_gradients()
+        grp = self.param_groups[0]
+        self.steps += 1
+        ops.adam_step(self.flat.data, self.flat.grad, self.exp_avg, self.exp_avg_sq, float(grp["lr"]),
+                      float(grp["betas"][0]), float(grp["betas"][1]), float(grp["eps"]), float(grp["weight_decay"]),
+                      self.steps)
+        for st in self.state.values():
+            st["step"].fill_(float(self.steps))
+        ops.invalidate_packed()            # the weights changed behind tensor._version
+        return loss
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        # re-home the loaded moments in the flat buffers
+        steps = 0
+        for p, off in zip(self.flat.params, self.flat.offsets):
+            st = self.state[p]
+            for key, buf in (("exp_avg", self.exp_avg), ("exp_avg_sq", self.exp_avg_sq)):
+                view = buf[off:off + p.numel()].view_as(p)
+                if st[key].data_ptr() != view.data_ptr():
+                    view.copy_(st[key])
+                    st[key] = view
+            steps = max(steps, int(float(st["step"])))
+        self.steps = steps

@@ -345,6 +345,10 @@ int dig3d_wgrad(const float* dy, const float* x, int64_t rows, int32_t nout, int
 int dig3d_linear_set_config(int32_t cfg);
 int dig3d_act(const float* x, int64_t n, int32_t mode, float* y, void* stream);
 int dig3d_act_bwd(const float* x, const float* dy, int64_t n, int32_t mode, float* dx, void* stream);
+/* Fused Adam step over FLAT fp32 buffers (run.py:49 `Adam(model.parameters(), lr, weight_decay)`; torch.optim.Adam
+ * semantics, amsgrad off): step = 1-based count of this update. */
+int dig3d_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
+                    double beta1, double beta2, double eps, double weight_decay, int64_t step, void* stream);
 int dig3d_ewise(const float* a, const float* b, int64_t n, int32_t op, float* y, void* stream);
 int dig3d_rowscale(const float* a, const float* s, int64_t rows, int32_t width, float* y, void* stream);
 int dig3d_gather_rows(const float* x, const void* idx, int32_t idx_is_64, int64_t rows, int32_t width, float* y,

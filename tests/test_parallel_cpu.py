@@ -99,6 +99,55 @@ def test_two_rank_gloo_gradient_allreduce():
     assert all(ret[r] for r in range(world)) and len(ret) == world
 
 
+def _reducer_worker(rank, world, port, ret):
+    """Overlapped bucketed all-reduce over the flat gradient buffer: hooks fire during backward, a parameter that gets
+    no gradient this step is reduced by finish(); result = the full-batch gradient on every rank, for 2 steps."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+
+        class Net(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.a, self.b = torch.nn.Linear(5, 7), torch.nn.Linear(7, 1)
+                self.unused = torch.nn.Parameter(torch.ones(3))
+
+            def forward(self, x):
+                return self.b(torch.tanh(self.a(x)))
+        model, ref = Net(), Net()
+        ref.load_state_dict(model.state_dict())
+        flat = parallel.FlatParameters(model)
+        reducer = parallel.GradientReducer(flat, n_buckets=2)
+        ok = len(reducer.buckets) == 2 and reducer.buckets[-1][1] == flat.numel
+        ok = ok and all(p.data_ptr() == flat.data.data_ptr() + 4 * o for p, o in zip(flat.params, flat.offsets))
+        for step in range(2):
+            x, y = torch.randn(8, 5), torch.randn(8, 1)
+            lo, hi = parallel.shard_bounds(8, rank, world)
+            flat.zero_grad()
+            reducer.arm()
+            torch.nn.functional.mse_loss(model(x[lo:hi]), y[lo:hi]).backward()
+            reducer.finish()
+            ref.zero_grad()
+            torch.nn.functional.mse_loss(ref(x), y).backward()
+            for (n, p), q in zip(model.named_parameters(), ref.parameters()):
+                want = q.grad if q.grad is not None else torch.zeros_like(q)
+                ok = ok and torch.allclose(p.grad, want, atol=1e-6)
+                ok = ok and p.grad.data_ptr() >= flat.grad.data_ptr()          # still a view of the flat buffer
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_overlapped_flat_gradient_reducer():
+    world = 2
+    ret = mp.Manager().dict()
+    port = 28000 + (os.getpid() % 400)
+    mp.spawn(_reducer_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert all(ret[r] for r in range(world)) and len(ret) == world
+
+
 def test_run_driver_contract_on_cpu(tmp_path, capsys):
     """run().run(...) (reference run.py:20-101) with a plain torch model on CPU: the host-side driver logic (loaders,
     epoch loop, printed lines, checkpoint keys, best-validation bookkeeping) does not need the CUDA kernels."""
