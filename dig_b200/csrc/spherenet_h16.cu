@@ -37,10 +37,18 @@ constexpr int H_SLAB_K = 32;                       // ring granularity: K = 32 s
 constexpr int H_STAGE_BYTES = 2 * 4 * 128 * 16;    // 16 KB (N = 128)
 constexpr int H_TILE_WARPS = 8;
 constexpr int H_TILE_THREADS = H_TILE_WARPS * 32;
-constexpr int H_THREADS = 64 + 2 * H_TILE_THREADS;
+constexpr int H_CTRL_THREADS = 128;                // warpgroup 0: warp 0 = producer, warp 1 = MMA issuer, warps 2-3 idle
+constexpr int H_THREADS = H_CTRL_THREADS + 2 * H_TILE_THREADS;
+constexpr int H_CTRL_WARPS = H_CTRL_THREADS / 32;
+// Register re-allocation between the warpgroups (setmaxnreg): the kernels are compiled for 96 registers (five warps
+// per scheduler); the control warpgroup then drops to 56 and each epilogue warp grows to 112 (4 x 32 x 112 + 32 x 56
+// <= 16384 per scheduler), which is what lets an epilogue thread keep its 64 accumulator values plus the TMEM
+// staging registers without spilling (round-2 ncu: the 96-register build spilled the drained accumulators).
+__device__ __forceinline__ void h_regs_ctrl() { asm volatile("setmaxnreg.dec.sync.aligned.u32 56;"); }
+__device__ __forceinline__ void h_regs_epi() { asm volatile("setmaxnreg.inc.sync.aligned.u32 112;"); }
 constexpr float H_SA = 8.0f, H_SW = 64.0f;
 constexpr float H_INV = 1.0f / (H_SA * H_SW);
-constexpr float H_RANGE = 8190.0f;                 // |activation| limit (65504 / H_SA)
+// |activation| limit of the chain: 65504 / H_SA = 8188
 constexpr int H_LDS = 129;                         // row stride (floats) of the fp32 staging overlay of a tile's planes
 
 struct HSmem {
@@ -54,6 +62,7 @@ struct HSmem {
   // d_ready / d_free are indexed [tile][accumulator]: each barrier has ONE waiter that sees every phase in order
   // (a parity wait may never lag or lead its barrier by two phases, which a barrier shared by the tiles allows)
   uint64_t full[H_STAGES], empty[H_STAGES], a_ready[2], d_ready[2][2], d_free[2][2];
+  uint64_t l_done;                                 // shared-A mode: every MMA of the layer has completed
   uint32_t tmem_base;
 };
 static_assert(sizeof(HSmem) <= 227 * 1024, "HSmem exceeds the shared memory of an SM");
@@ -63,6 +72,7 @@ struct HGemm {
   const unsigned char* w;   // packed slabs (dig3d_h16_pack)
   const float* bias;        // [N] or null
   int K, N;
+  int tile_stride;          // bytes added to `w` for the second job of a layer (shared-A mode: the other N half)
 };
 
 static __device__ unsigned int g_h16_overflow = 0;
@@ -98,10 +108,9 @@ __device__ __forceinline__ float hswish8(float t8) {
 }
 
 // ---- producer: every K = 32 slab of every job (layer x tile) through the ring
-template <int NG>
-__device__ __forceinline__ void h_producer(HSmem& s, const HGemm (&g)[NG], int ntile) {
+__device__ __forceinline__ void h_producer_n(HSmem& s, const HGemm* g, int ng, int ntile) {
   int it = 0;
-  for (int q = 0; q < NG; ++q) {
+  for (int q = 0; q < ng; ++q) {
     const int nslab = g[q].K / H_SLAB_K;
     const uint32_t bytes = 2u * 4u * (uint32_t)g[q].N * 16u;
     for (int t = 0; t < ntile; ++t)
@@ -109,27 +118,33 @@ __device__ __forceinline__ void h_producer(HSmem& s, const HGemm (&g)[NG], int n
         const int st = it % H_STAGES;
         mbar_wait(&s.empty[st], ((it / H_STAGES) & 1) ^ 1);
         mbar_arrive_expect_tx(&s.full[st], bytes);
-        bulk_g2s(s.w[st], g[q].w + (size_t)c * bytes, bytes, &s.full[st]);
+        bulk_g2s(s.w[st], g[q].w + (size_t)t * g[q].tile_stride + (size_t)c * bytes, bytes, &s.full[st]);
       }
   }
 }
+template <int NG>
+__device__ __forceinline__ void h_producer(HSmem& s, const HGemm (&g)[NG], int ntile) { h_producer_n(s, g, NG, ntile); }
 
 // ---- MMA issuer: jobs alternate between the tiles; one K = 64 chunk (two slabs) per TMEM accumulator.  The two
 // accumulators are shared by the tiles: before chunk `ch` overwrites accumulator ch & 1, the tile that used it last
 // (chunk ch - 2, possibly the other tile) must have drained it.
-template <int NG, bool TRACE = false>
-__device__ __forceinline__ void h_mma(HSmem& s, const HGemm (&g)[NG], int ntile, uint32_t tmem) {
+template <bool TRACE, bool SHARED_A>
+__device__ __forceinline__ void h_mma_n(HSmem& s, const HGemm* g, int ng, int ntile, uint32_t tmem) {
   int it = 0, ch = 0;
   int uses00 = 0, uses01 = 0, uses10 = 0, uses11 = 0;   // uses[tile][accumulator] so far
   int last0 = -1, last1 = -1;                            // tile that used accumulator 0 / 1 last
-  for (int q = 0; q < NG; ++q) {
+  for (int q = 0; q < ng; ++q) {
     const int nslab = g[q].K / H_SLAB_K, n = g[q].N;
     const uint32_t idesc = idesc_f16(H_M, n);
     for (int t = 0; t < ntile; ++t) {
-      mbar_wait(&s.a_ready[t], q & 1);
-      tc_fence_after();
+      // SHARED_A: the two jobs of a layer are the two N halves of ONE operand tile (K up to 256: the hi plane spans
+      // s.a[0], the lo plane s.a[1]), published once per layer by all sixteen epilogue warps
+      if (!SHARED_A || t == 0) {
+        mbar_wait(&s.a_ready[SHARED_A ? 0 : t], q & 1);
+        tc_fence_after();
+      }
       if (q < 8) H_TRACE((q * 2 + t) * 2);
-      const uint32_t a_hi = smem_u32(s.a[t][0]), a_lo = smem_u32(s.a[t][1]);
+      const uint32_t a_hi = smem_u32(SHARED_A ? s.a[0][0] : s.a[t][0]), a_lo = smem_u32(SHARED_A ? s.a[1][0] : s.a[t][1]);
       for (int c = 0; c < nslab; ++c, ++it) {
         const int st = it % H_STAGES, ab = ch & 1;
         if ((c & 1) == 0) {
@@ -164,8 +179,13 @@ __device__ __forceinline__ void h_mma(HSmem& s, const HGemm (&g)[NG], int ntile,
         }
       }
       if (q < 8) H_TRACE((q * 2 + t) * 2 + 1);
+      if (SHARED_A && t == ntile - 1) mma_commit(&s.l_done);
     }
   }
+}
+template <int NG, bool TRACE = false>
+__device__ __forceinline__ void h_mma(HSmem& s, const HGemm (&g)[NG], int ntile, uint32_t tmem) {
+  h_mma_n<TRACE, false>(s, g, NG, ntile, tmem);
 }
 
 // ---- epilogue context: thread = one row of its tile, NC = 64 (N = 128) or 32 (N = 64) columns
@@ -175,13 +195,14 @@ struct HCtx {
   int ntile, ch;            // tiles in this CTA, global accumulator-chunk counter (same sequence as the issuer's)
   int use0, use1;           // chunks of THIS tile drained from accumulator 0 / 1 so far (barrier phases)
   bool bad;                 // a non-finite value reached an OUTPUT of the kernel (fp16 operand range exceeded upstream)
+  unsigned char *ahi, *alo; // operand planes this thread writes
 };
-__device__ __forceinline__ HCtx h_ctx(const HSmem& s, int ntile) {
+__device__ __forceinline__ HCtx h_ctx(HSmem& s, int ntile) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int t = (warp - 2) / H_TILE_WARPS, we = (warp - 2) % H_TILE_WARPS;
+  const int t = (warp - H_CTRL_WARPS) / H_TILE_WARPS, we = (warp - H_CTRL_WARPS) % H_TILE_WARPS;
   const int quarter = warp & 3;   // a warp may only touch TMEM lanes [32*(warp%4), +32)
-  return {t, (int)threadIdx.x - 64 - t * H_TILE_THREADS, 32 * quarter + lane, we >> 2,
-          s.tmem_base + ((uint32_t)(32 * quarter) << 16), ntile, 0, 0, 0, false};
+  return {t, (int)threadIdx.x - H_CTRL_THREADS - t * H_TILE_THREADS, 32 * quarter + lane, we >> 2,
+          s.tmem_base + ((uint32_t)(32 * quarter) << 16), ntile, 0, 0, 0, false, s.a[t][0], s.a[t][1]};
 }
 __device__ __forceinline__ void h_tile_bar(int t) {
   asm volatile("bar.sync %0, %1;" ::"r"(1 + t), "n"(H_TILE_THREADS) : "memory");
@@ -206,8 +227,8 @@ __device__ __forceinline__ void h_store_ku(HSmem& s, const HCtx& c, int row, int
     l[i] = *reinterpret_cast<const uint32_t*>(&ll);
   }
   const int o = (ku * H_AKU + row) * 16;
-  *reinterpret_cast<uint4*>(s.a[c.t][0] + o) = make_uint4(h[0], h[1], h[2], h[3]);
-  *reinterpret_cast<uint4*>(s.a[c.t][1] + o) = make_uint4(l[0], l[1], l[2], l[3]);
+  *reinterpret_cast<uint4*>(c.ahi + o) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(c.alo + o) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 __device__ __forceinline__ void h_store_a16(HSmem& s, const HCtx& c, int col, const float (&v8)[16]) {
   float x[8];
@@ -276,13 +297,14 @@ __device__ __forceinline__ void h_drain(HSmem& s, HCtx& c, int col0, int chunks,
   }
   if (c.t == 0 && c.ntile == 2) c.ch += chunks;
 }
-__device__ __forceinline__ void h_setup(HSmem& s) {
+__device__ __forceinline__ void h_setup(HSmem& s, int a_ready_warps = H_TILE_WARPS) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < H_STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&s.a_ready[i], H_TILE_WARPS);
+      mbar_init(&s.a_ready[i], a_ready_warps);
       for (int j = 0; j < 2; ++j) { mbar_init(&s.d_ready[i][j], 1); mbar_init(&s.d_free[i][j], H_TILE_WARPS); }
     }
+    mbar_init(&s.l_done, 1);
     mbar_fence_init();
   }
   if ((threadIdx.x >> 5) == 0) tmem_alloc(&s.tmem_base, 512);
@@ -368,11 +390,11 @@ sphere_update_e_b_h16_kernel(const float* __restrict__ m, const float* __restric
   tc_fence_after();
   HCtx c;
   bool epi = false;
-  if (warp == 0) {
+  if (warp < H_CTRL_WARPS) {
+    h_regs_ctrl();
     if (tid == 0) h_producer(s, P.g, ntile);
-  } else if (warp == 1) {
-    if (tid == 32) h_mma<8, true>(s, P.g, ntile, s.tmem_base);
-  } else if ((c = h_ctx(s, ntile)).t < ntile) {
+    else if (tid == 32) h_mma<8, true>(s, P.g, ntile, s.tmem_base);
+  } else if (h_regs_epi(), (c = h_ctx(s, ntile)).t < ntile) {
     epi = true;
     constexpr bool TRACE = true;
     const bool probe = c.et == 0;
@@ -509,11 +531,11 @@ sphere_update_e_a_h16_kernel(const float* __restrict__ e1, const float* __restri
   tc_fence_after();
   HCtx c;
   bool epi = false;
-  if (warp == 0) {
+  if (warp < H_CTRL_WARPS) {
+    h_regs_ctrl();
     if (tid == 0) h_producer(s, P.g, ntile);
-  } else if (warp == 1) {
-    if (tid == 32) h_mma(s, P.g, ntile, s.tmem_base);
-  } else if ((c = h_ctx(s, ntile)).t < ntile) {
+    else if (tid == 32) h_mma(s, P.g, ntile, s.tmem_base);
+  } else if (h_regs_epi(), (c = h_ctx(s, ntile)).t < ntile) {
     epi = true;
     const int e0 = (tile0 + c.t) * H_M, rows = min(H_M, n_edges - e0);
     const bool valid = c.row < rows;
@@ -624,11 +646,11 @@ sphere_init_e_h16_kernel(const int64_t* __restrict__ z, const int32_t* __restric
   tc_fence_after();
   HCtx c;
   bool epi = false;
-  if (warp == 0) {
+  if (warp < H_CTRL_WARPS) {
+    h_regs_ctrl();
     if (tid == 0) h_producer(s, P.g, ntile);
-  } else if (warp == 1) {
-    if (tid == 32) h_mma(s, P.g, ntile, s.tmem_base);
-  } else if ((c = h_ctx(s, ntile)).t < ntile) {
+    else if (tid == 32) h_mma(s, P.g, ntile, s.tmem_base);
+  } else if (h_regs_epi(), (c = h_ctx(s, ntile)).t < ntile) {
     epi = true;
     const int e0 = (tile0 + c.t) * H_M, rows = min(H_M, n_edges - e0);
     const bool valid = c.row < rows;
@@ -698,6 +720,132 @@ sphere_init_e_h16_kernel(const int64_t* __restrict__ z, const int32_t* __restric
     h_segment_sums(s, c, rows, v_in);
   }
   h_finish(s, epi ? &c : nullptr);
+}
+
+// ---------------------------------------------------------------------------------- update_v (node MLP)
+// v = lin_up(v_in) ; v = act(lins[l](v)) ... ; out = lin(v)                              spherenet.py:212-215
+// H = 128 -> O = 256 -> O ... -> out_channels on the same engine in SHARED-A mode: one 128-node tile per CTA whose
+// operand (K up to 256) spans both plane regions; the two jobs of a layer are the two 128-column halves of its
+// output, drained by the two epilogue groups.  Group X activates its half while the tensor core still runs group
+// Y's half; both write the next operand only after every MMA of the layer has completed (l_done).  The last linear
+// (out_channels <= 4) is a dot product over the activated row, reduced in a fixed order through shared memory.
+// All blocks (init_v + update_vs) run in one launch: blockIdx.y selects the block's weights.
+struct HVBlock {
+  const unsigned char* p[9];     // packed lin_up [256 x 128], lins[l] [256 x 256] (rows 0..127 then 128..255)
+  const float* b[9];             // biases [256]
+  const float* w_out;            // [out_channels, 256]
+};
+struct HVParams { HVBlock blk[8]; int n_lins, out_channels; };
+
+template <bool FAST>
+__global__ void __launch_bounds__(H_THREADS, 1)
+sphere_update_v_h16_kernel(const float* __restrict__ v_in_all, int n_nodes, HVParams P, float* __restrict__ v_out_all) {
+  extern __shared__ __align__(1024) unsigned char h_raw[];
+  HSmem& s = *reinterpret_cast<HSmem*>(h_raw);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const HVBlock& B = P.blk[blockIdx.y];
+  const int r0 = blockIdx.x * H_M, rows = min(H_M, n_nodes - r0);
+  const int ng = P.n_lins + 1, C = P.out_channels;
+  __shared__ HGemm g[9];
+  h_setup(s, 2 * H_TILE_WARPS);
+  if (tid < ng) g[tid] = {B.p[tid], nullptr, tid == 0 ? 128 : 256, 128, (tid == 0 ? 128 : 256) * 128 * 4};
+  // biases of the first four layers live in s.bias ([8][128] floats = 4 x 256), later ones are read from global
+  for (int i = tid; i < min(ng, 4) * 256; i += H_THREADS) (&s.bias[0][0])[i] = H_SA * __ldg(B.b[i / 256] + i % 256);
+  for (int i = tid; i < C * 256; i += H_THREADS) s.wr[i] = __ldg(B.w_out + i);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp < H_CTRL_WARPS) {
+    h_regs_ctrl();
+    if (tid == 0) h_producer_n(s, g, ng, 2);
+    else if (tid == 32) h_mma_n<false, true>(s, g, ng, 2, s.tmem_base);
+  } else {
+    h_regs_epi();
+    HCtx c = h_ctx(s, 2);
+    c.ahi = s.a[0][0];
+    c.alo = s.a[1][0];
+    const int et2 = tid - H_CTRL_THREADS;           // 0 .. 511 over both groups
+    const int col0 = c.half * 64;                   // within this group's 128-column half
+    const int gcol0 = 128 * c.t + col0;             // output column of acc[0]
+    const float* vin = v_in_all + ((size_t)blockIdx.y * n_nodes + r0) * 128;
+    // A0 = v_in tile (K = 128), all 512 threads
+#pragma unroll
+    for (int k = 0; k < H_M * 16 / (2 * H_TILE_THREADS); ++k) {
+      const int f = et2 + k * 2 * H_TILE_THREADS, row = f >> 4, ku = f & 15;
+      float x[8];
+      if (row < rows) {
+        const float4 p0 = __ldg(reinterpret_cast<const float4*>(vin + (size_t)row * 128 + ku * 8));
+        const float4 p1 = __ldg(reinterpret_cast<const float4*>(vin + (size_t)row * 128 + ku * 8 + 4));
+        x[0] = p0.x * H_SA; x[1] = p0.y * H_SA; x[2] = p0.z * H_SA; x[3] = p0.w * H_SA;
+        x[4] = p1.x * H_SA; x[5] = p1.y * H_SA; x[6] = p1.z * H_SA; x[7] = p1.w * H_SA;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = 0.f;
+      }
+      h_store_ku(s, c, row, ku, x);
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&s.a_ready[0]);
+    float acc[64];
+#pragma unroll 1
+    for (int q = 0; q < ng; ++q) {
+      h_drain<4, true>(s, c, col0, q == 0 ? 2 : 4, acc);
+      // v8 = H_SA * (acc / (H_SA H_SW) + b) ; layers >= 1 apply the activation
+#pragma unroll
+      for (int i = 0; i < 64; i += 4) {
+        float4 b;
+        if (q < 4) b = *reinterpret_cast<const float4*>(&(&s.bias[0][0])[q * 256 + gcol0 + i]);
+        else {
+          b = __ldg(reinterpret_cast<const float4*>(B.b[q] + gcol0 + i));
+          b.x *= H_SA; b.y *= H_SA; b.z *= H_SA; b.w *= H_SA;
+        }
+        acc[i] = fmaf(acc[i], H_SA * H_INV, b.x); acc[i + 1] = fmaf(acc[i + 1], H_SA * H_INV, b.y);
+        acc[i + 2] = fmaf(acc[i + 2], H_SA * H_INV, b.z); acc[i + 3] = fmaf(acc[i + 3], H_SA * H_INV, b.w);
+        if (q > 0) {
+          acc[i] = hswish8<FAST>(acc[i]); acc[i + 1] = hswish8<FAST>(acc[i + 1]);
+          acc[i + 2] = hswish8<FAST>(acc[i + 2]); acc[i + 3] = hswish8<FAST>(acc[i + 3]);
+        }
+      }
+      mbar_wait(&s.l_done, q & 1);          // every MMA that reads the current operand has completed
+      tc_fence_after();
+      if (q + 1 < ng) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          float v16[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v16[i] = acc[16 * p + i];
+          h_store_a16(s, c, gcol0 + 16 * p, v16);
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&s.a_ready[0]);
+      }
+    }
+    // out[row][o] = sum_c v[row][c] * w_out[o][c]: partial sums of this thread's 64 columns, fixed-order reduction
+    float* red = reinterpret_cast<float*>(s.a[0][0]);        // [128][4 slots][C], the operand planes are free now
+    const int slot = 2 * c.t + c.half;
+    for (int o = 0; o < C; ++o) {
+      float part = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) part = fmaf(acc[i], s.wr[o * 256 + gcol0 + i], part);
+      red[(c.row * 4 + slot) * C + o] = part * (1.0f / H_SA);
+      c.bad |= !h_finite(part);
+    }
+    asm volatile("bar.sync 3, %0;" ::"n"(2 * H_TILE_THREADS) : "memory");
+    if (slot == 0 && c.row < rows) {
+      float* out = v_out_all + ((size_t)blockIdx.y * n_nodes + r0 + c.row) * C;
+      for (int o = 0; o < C; ++o) {
+        const float* rr = red + (c.row * 4) * C + o;
+        out[o] = ((rr[0] + rr[C]) + rr[2 * C]) + rr[3 * C];
+      }
+    }
+    h_finish(s, &c);
+    return;
+  }
+  h_finish(s, nullptr);
 }
 
 static int h_smem_attr(const void* fn) {
@@ -816,6 +964,38 @@ int dig3d_sphere_update_e_b_h16(const float* m, const float* e1_in, const float*
   const int pairs = ceil_div(ceil_div(n_edges, H_M), 2);
   kfn<<<pairs, H_THREADS, sizeof(HSmem), (cudaStream_t)stream>>>(m, x_ji, e1_in, rbf0, dst, (int)n_edges, P, e1_out,
                                                                  v_in);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_sphere_update_v_h16_supported(int32_t hidden, int32_t out_emb, int32_t out_channels, int32_t n_lins) {
+  return (hidden == 128 && out_emb == 256 && out_channels >= 1 && out_channels <= 4 && n_lins >= 0 && n_lins <= 8) ? 1 : 0;
+}
+
+int dig3d_sphere_update_v_h16(const float* v_in_all, int64_t n_nodes, int32_t n_blocks, int32_t out_channels,
+                              int32_t n_lins, const void* const* packed /* [n_blocks][n_lins + 1] */,
+                              const dig3d_update_v_weights* w, float* v_out_all, void* stream) {
+  DIG3D_REQUIRE(v_in_all && packed && w && v_out_all, "sphere_update_v_h16: null pointer");
+  DIG3D_REQUIRE(n_blocks >= 1 && n_blocks <= 8, "sphere_update_v_h16: n_blocks=%d outside [1,8]", n_blocks);
+  DIG3D_REQUIRE(dig3d_sphere_update_v_h16_supported(128, 256, out_channels, n_lins),
+                "sphere_update_v_h16: out_channels=%d / n_lins=%d not compiled", out_channels, n_lins);
+  if (n_nodes == 0) return DIG3D_OK;
+  HVParams P;
+  P.n_lins = n_lins; P.out_channels = out_channels;
+  for (int b = 0; b < n_blocks; ++b) {
+    DIG3D_REQUIRE(w[b].n_lins == n_lins && w[b].w_out && w[b].b_up, "sphere_update_v_h16: block %d weights", b);
+    for (int l = 0; l <= n_lins; ++l) {
+      P.blk[b].p[l] = (const unsigned char*)packed[b * (n_lins + 1) + l];
+      P.blk[b].b[l] = l == 0 ? w[b].b_up : w[b].b_lins[l - 1];
+      DIG3D_REQUIRE(P.blk[b].p[l] && P.blk[b].b[l], "sphere_update_v_h16: block %d layer %d null", b, l);
+    }
+    P.blk[b].w_out = w[b].w_out;
+  }
+  auto kfn = h16_fast_swish ? sphere_update_v_h16_kernel<true> : sphere_update_v_h16_kernel<false>;
+  int rc = h_smem_attr((const void*)kfn);
+  if (rc) return rc;
+  dim3 grid(ceil_div(n_nodes, H_M), n_blocks);
+  kfn<<<grid, H_THREADS, sizeof(HSmem), (cudaStream_t)stream>>>(v_in_all, (int)n_nodes, P, v_out_all);
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
 }

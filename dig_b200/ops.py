@@ -546,6 +546,38 @@ def sphere_update_e_h16(e1, g, rbf0, sbf_p, t_p, col0, w, hidden, int_emb, v_in=
     return e1_out, v_in, x_ji, x_down
 
 
+def update_v_h16_supported(holder, out_channels):
+    return bool(_lib.load().dig3d_sphere_update_v_h16_supported(
+        holder.lin_up.weight.size(1), holder.lin_up.weight.size(0), int(out_channels), len(holder.lins)))
+
+
+def sphere_update_v_h16(v_in_all, holders, out_channels, v_out_all, cache):
+    """All node MLPs of a forward in one launch on the two-tile tensor-core engine (3xFP16 operands).
+    v_in_all [NB, N, 128], holders: NB update_v modules (128 -> 256 -> ... -> out_channels)."""
+    nb, n, _ = v_in_all.shape
+    n_lins = len(holders[0].lins)
+    ptrs = []
+    for h in holders:
+        mats = [h.lin_up.weight] + [lin.weight for lin in h.lins]
+        key = (_PACK_GENERATION[0],) + tuple((w.data_ptr(), w._version) for w in mats)
+        hit = cache.get((id(h), "h16v"))
+        if hit is None or hit[0] != key:
+            halves = []
+            for w in mats:                                   # output rows 0..127, then 128..255, back to back
+                halves += [w.detach()[:128], w.detach()[128:]]
+            buf, offs = _pack_matrices(halves, "h16")
+            hit = (key, buf, offs)
+            cache[(id(h), "h16v")] = hit
+        _, buf, offs = hit
+        ptrs += [buf.data_ptr() + offs[2 * l] for l in range(n_lins + 1)]
+    parr = (ctypes.c_void_p * len(ptrs))(*ptrs)
+    arr = (_lib.UpdateVWeights * nb)(*[pack_update_v(h) for h in holders])
+    if n:
+        call("dig3d_sphere_update_v_h16", _p(v_in_all, torch.float32, "v_in_all", 16), n, nb, int(out_channels), n_lins,
+             parr, arr, _p(v_out_all, align=4), _stream())
+    return v_out_all
+
+
 def h16_overflow(clear=True):
     """True if an operand of the 3xFP16 chain left the fp16 range (|activation| >= 8190) since the last clear."""
     return bool(_lib.load().dig3d_h16_overflow(int(bool(clear))))

@@ -286,7 +286,11 @@ class _DimeNetFamily(nn.Module):
                 e1, _ = ops.sphere_update_e(e1, g, rbf0, sbf_p, t_p, 8 * (l % 4),
                                             ops.pack_update_e(self.update_es[l], self._torsion),
                                             self.hidden_channels, self.int_emb_size, v_in=v_in_all[l + 1])
-        ops.sphere_update_v_batched(v_in_all, [self.init_v] + list(self.update_vs), self.out_channels, v_all)
+        holders = [self.init_v] + list(self.update_vs)
+        if dense == "h16" and ops.update_v_h16_supported(self.init_v, self.out_channels):
+            ops.sphere_update_v_h16(v_in_all, holders, self.out_channels, v_all, tc_cache)
+        else:                                  # exact-fp32 FFMA engine (other widths, DIG3D_DENSE=tc / simt)
+            ops.sphere_update_v_batched(v_in_all, holders, self.out_channels, v_all)
         return ops.graph_readout(v_all, g.graph_ptr, g.n_graphs, g.n_nodes)
 
 

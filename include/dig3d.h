@@ -250,6 +250,14 @@ int dig3d_sphere_update_e_a_h16(const float* e1, const float* rbf0, int64_t n_ed
 int dig3d_sphere_update_e_b_h16(const float* m, const float* e1_in, const float* x_ji, const float* rbf0,
                                 const int32_t* dst, int64_t n_edges, const dig3d_tc_update_e* w, float* e1_out,
                                 float* v_in, void* stream);
+/* update_v.forward after the scatter (spherenet.py:212-215) for ALL blocks of a forward on the same engine (one
+ * 128-node tile per CTA, the two 128-column halves of every 256-wide layer in flight); H = 128, O = 256,
+ * out_channels <= 4.  packed[b * (n_lins + 1) + l] = dig3d_h16_pack of block b's lin_up (l = 0) / lins[l - 1]
+ * as TWO [128, K] matrices back to back (output rows 0..127, then 128..255). */
+int dig3d_sphere_update_v_h16_supported(int32_t hidden, int32_t out_emb, int32_t out_channels, int32_t n_lins);
+int dig3d_sphere_update_v_h16(const float* v_in_all, int64_t n_nodes, int32_t n_blocks, int32_t out_channels,
+                              int32_t n_lins, const void* const* packed, const dig3d_update_v_weights* w,
+                              float* v_out_all, void* stream);
 /* 1 if an operand left the fp16 range since the flag was last cleared (synchronises the device). */
 int dig3d_h16_overflow(int32_t clear);
 int dig3d_h16_timeouts(void);

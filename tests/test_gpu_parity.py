@@ -457,6 +457,31 @@ def test_headline_config_matches_oracle_at_full_size():
     assert ops.tc_timeouts() == 0 and not ops.h16_overflow()
 
 
+@pytest.mark.parametrize("kw", [dict(), dict(out_channels=3, num_output_layers=2), dict(num_output_layers=5)])
+def test_update_v_on_the_tensor_engine_matches_fp32(kw):
+    """All node MLPs (update_v.forward, spherenet.py:212-215) in one launch on the shared-operand mode of the
+    two-tile engine vs the exact-fp32 FFMA kernel: ragged last tile, 1..5 hidden layers, several output channels."""
+    from dig_b200 import ops
+    from dig_b200.threedgraph.method import SphereNet
+    dev = torch.device("cuda:0")
+    model = SphereNet(**kw)
+    model.load_state_dict(formula_state_dict(model.state_dict(), seed=5))
+    model = model.to(dev)
+    holders = [model.init_v] + list(model.update_vs)
+    assert ops.update_v_h16_supported(model.init_v, model.out_channels)
+    torch.manual_seed(3)
+    for n in (300, 128, 5):
+        v_in = torch.randn(len(holders), n, 128, device=dev) * 2.0
+        want = torch.empty(len(holders), n, model.out_channels, device=dev)
+        got = torch.full_like(want, float("nan"))
+        ops.sphere_update_v_batched(v_in, holders, model.out_channels, want)
+        cache = {}
+        ops.sphere_update_v_h16(v_in, holders, model.out_channels, got, cache)
+        assert torch.isfinite(got).all()
+        assert rel_err(got.cpu().numpy(), want.cpu().numpy()) < TOL, (kw, n)
+    assert ops.tc_timeouts() == 0 and not ops.h16_overflow()
+
+
 def test_packed_weights_follow_parameter_updates():
     """The tcgen05 weight cache is keyed on tensor._version: an in-place optimiser-style update must be seen."""
     from dig_b200.data import synthetic_batch
