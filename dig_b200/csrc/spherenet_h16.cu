@@ -41,10 +41,10 @@ constexpr int H_CTRL_THREADS = 128;                // warpgroup 0: warp 0 = prod
 constexpr int H_THREADS = H_CTRL_THREADS + 2 * H_TILE_THREADS;
 constexpr int H_CTRL_WARPS = H_CTRL_THREADS / 32;
 // Register re-allocation between the warpgroups (setmaxnreg): the kernels are compiled for 96 registers (five warps
-// per scheduler); the control warpgroup then drops to 56 and each epilogue warp grows to 112 (4 x 32 x 112 + 32 x 56
+// per scheduler); the control warpgroup then drops to 32 and each epilogue warp grows to 112 (the CTA pool is conserved: 128 x 32 + 512 x 112 = 640 x 96; per scheduler 4 x 32 x 112 + 32 x 32
 // <= 16384 per scheduler), which is what lets an epilogue thread keep its 64 accumulator values plus the TMEM
 // staging registers without spilling (round-2 ncu: the 96-register build spilled the drained accumulators).
-__device__ __forceinline__ void h_regs_ctrl() { asm volatile("setmaxnreg.dec.sync.aligned.u32 56;"); }
+__device__ __forceinline__ void h_regs_ctrl() { asm volatile("setmaxnreg.dec.sync.aligned.u32 32;"); }
 __device__ __forceinline__ void h_regs_epi() { asm volatile("setmaxnreg.inc.sync.aligned.u32 112;"); }
 constexpr float H_SA = 8.0f, H_SW = 64.0f;
 constexpr float H_INV = 1.0f / (H_SA * H_SW);

@@ -55,18 +55,25 @@ class emb(nn.Module):
 
 
 class init(nn.Module):
-    """reference spherenet.py:53-91 / dimenetpp.py:55-78."""
+    """reference spherenet.py:53-91 / dimenetpp.py:55-78 (DimeNet++ has neither option)."""
 
-    def __init__(self, num_radial, hidden_channels):
+    def __init__(self, num_radial, hidden_channels, use_node_features=True, use_extra_node_feature=False):
         super().__init__()
-        self.emb = nn.Embedding(95, hidden_channels)
+        self.use_node_features = use_node_features
+        self.use_extra_node_feature = use_extra_node_feature
+        if use_node_features:
+            self.emb = nn.Embedding(95, hidden_channels)
+        else:            # one learned embedding vector shared by all nodes (spherenet.py:61-63)
+            self.node_embedding = nn.Parameter(torch.empty((hidden_channels,)))
+            nn.init.normal_(self.node_embedding)
         self.lin_rbf_0 = nn.Linear(num_radial, hidden_channels)
-        self.lin = nn.Linear(3 * hidden_channels, hidden_channels)
+        self.lin = nn.Linear((5 if use_extra_node_feature else 3) * hidden_channels, hidden_channels)
         self.lin_rbf_1 = nn.Linear(num_radial, hidden_channels, bias=False)
         self.reset_parameters()
 
     def reset_parameters(self):
-        self.emb.weight.data.uniform_(-sqrt(3), sqrt(3))
+        if self.use_node_features:
+            self.emb.weight.data.uniform_(-sqrt(3), sqrt(3))
         self.lin_rbf_0.reset_parameters()
         self.lin.reset_parameters()
         glorot_orthogonal(self.lin_rbf_1.weight, scale=2.0)
@@ -146,7 +153,8 @@ class _DimeNetFamily(nn.Module):
 
     def _build(self, energy_and_force, cutoff, num_layers, hidden_channels, out_channels, int_emb_size,
                be_dist, be_angle, be_torsion, out_emb_channels, num_spherical, num_radial,
-               envelope_exponent, num_before_skip, num_after_skip, num_output_layers, act, output_init):
+               envelope_exponent, num_before_skip, num_after_skip, num_output_layers, act, output_init,
+               use_node_features=True, use_extra_node_feature=False, extra_node_feature_dim=1):
         given = dict(hidden_channels=hidden_channels, int_emb_size=int_emb_size,
                      out_emb_channels=out_emb_channels, num_radial=num_radial,
                      num_before_skip=num_before_skip, num_after_skip=num_after_skip)
@@ -160,7 +168,12 @@ class _DimeNetFamily(nn.Module):
                 f"{type(self).__name__}: the triplet kernels are compiled for int_emb_size=64, "
                 f"basis_emb_size_angle/torsion=8, num_radial=6; got int_emb_size={int_emb_size}, "
                 f"basis_emb sizes {(be_dist, be_angle, be_torsion)}, num_radial={num_radial}")
-        self._generic = bool(bad) or be_dist != 8
+        # use_node_features=False / use_extra_node_feature change init_e only (spherenet.py:79-91); they run on the
+        # generic primitives as well (the fused init_e kernels are compiled for the 3H-wide default)
+        self._generic = bool(bad) or be_dist != 8 or not use_node_features or use_extra_node_feature
+        self.use_extra_node_feature = use_extra_node_feature
+        if use_extra_node_feature:
+            self.extra_emb = nn.Linear(extra_node_feature_dim, hidden_channels)
         if ("dimenet", num_spherical, num_radial) not in ops.BASIS_IDS:
             raise NotImplementedError(
                 f"no generated basis for num_spherical={num_spherical}, num_radial={num_radial}; "
@@ -177,7 +190,7 @@ class _DimeNetFamily(nn.Module):
         self.num_spherical, self.num_radial, self.envelope_exponent = num_spherical, num_radial, envelope_exponent
         self._basis_id = ops.BASIS_IDS[("dimenet", num_spherical, num_radial)]
 
-        self.init_e = init(num_radial, hidden_channels)
+        self.init_e = init(num_radial, hidden_channels, use_node_features, use_extra_node_feature)
         self.init_v = update_v(hidden_channels, out_emb_channels, out_channels, num_output_layers, output_init)
         self.init_u = update_u()
         self.emb = emb(num_spherical, num_radial, cutoff, envelope_exponent)
@@ -191,6 +204,8 @@ class _DimeNetFamily(nn.Module):
         self.reset_parameters()
 
     def reset_parameters(self):
+        if self.use_extra_node_feature:
+            self.extra_emb.reset_parameters()
         self.init_e.reset_parameters()
         self.init_v.reset_parameters()
         self.emb.reset_parameters()
@@ -234,10 +249,11 @@ class _DimeNetFamily(nn.Module):
         if self.energy_and_force:
             pos.requires_grad_()                      # reference dimenetpp.py:275-276
         ns, nr = self.num_spherical, self.num_radial
+        with_emb = self.init_e.use_node_features
         g = ops.build_graph(pos, batch, self.cutoff, num_graphs=getattr(batch_data, "num_graphs", None),
-                            z=z, z_rows=self.init_e.emb.num_embeddings)
+                            z=z if with_emb else None, z_rows=self.init_e.emb.num_embeddings if with_emb else 0)
         if wants_grad(self) or self._generic:
-            return self._forward_train(z, pos, g)
+            return self._forward_train(z, pos, g, getattr(batch_data, "node_feature", None))
         ops.triplet_geometry(g, pos, use_torsion=self._torsion, want_idx=False)
         rbf0, bess = ops.edge_basis(g.dist, self.cutoff, self.envelope_exponent, self.emb.dist_emb.freq,
                                     self._basis_id, envelope_on_bessel=not self._torsion, num_radial=nr,
@@ -305,7 +321,7 @@ class _DimeNetFamily(nn.Module):
             v = ag.grouped_lin([m.lins[j] for m in mods], v, act=True)
         return ag.grouped_lin([m.lin for m in mods], v)
 
-    def _forward_train(self, z, pos, g):
+    def _forward_train(self, z, pos, g, node_feature=None):
         """Differentiable forward (reference spherenet.py:296-320 / dimenetpp.py:273-293, op for op) over the
         primitives of dig_b200.autograd; taken whenever autograd is recording (run.train).  Geometry and the
         spherical basis carry no parameters except dist_emb.freq, so they run on the same kernels as inference."""
@@ -334,7 +350,12 @@ class _DimeNetFamily(nn.Module):
         swish_, lin = ag.swish, ag.lin
         # init_e (spherenet.py:79-91)
         ie = self.init_e
-        x = ag.gather_rows(ie.emb.weight, z)
+        if ie.use_node_features:
+            x = ag.gather_rows(ie.emb.weight, z)
+        else:                                                    # spherenet.py:83-84: the same row for every node
+            x = ag.gather_rows(ie.node_embedding.view(1, -1), torch.zeros_like(z))
+        if self.use_extra_node_feature and node_feature is not None:      # spherenet.py:85-86, :298-299
+            x = torch.cat([x, lin(self.extra_emb, node_feature.to(torch.float32).contiguous())], dim=1)   # copy only
         r0 = ag.lin_swish(ie.lin_rbf_0, rbf0)
         cat = torch.cat([ag.gather_rows(x, g.dst, g.row_ptr), ag.gather_rows(x, g.src), r0], dim=-1)   # copy only
         e1 = ag.lin_swish(ie.lin, cat)
@@ -366,9 +387,9 @@ class _DimeNetFamily(nn.Module):
 class SphereNet(_DimeNetFamily):
     r"""Drop-in for dig.threedgraph.method.SphereNet (reference spherenet.py:228-320).
 
-    Same constructor arguments and defaults.  Restrictions of this round (raise at construction):
-    `use_extra_node_feature=True`, `use_node_features=False`, non-swish `act`, and triplet-branch sizes other
-    than the class defaults.  `energy_and_force=True`: forward is differentiable w.r.t. pos (first order)."""
+    Same constructor arguments and defaults.  `use_extra_node_feature=True` / `use_node_features=False` run on the
+    generic primitives (the fused init_e kernels are compiled for the default 3H-wide input).  Restrictions (raise
+    at construction): non-swish `act`, and triplet-branch sizes other than the class defaults.  `energy_and_force=True`: forward is differentiable w.r.t. pos (first order)."""
     _torsion = True
 
     def __init__(self, energy_and_force=False, cutoff=5.0, num_layers=4, hidden_channels=128, out_channels=1,
@@ -377,13 +398,11 @@ class SphereNet(_DimeNetFamily):
                  num_after_skip=2, num_output_layers=3, act=swish, output_init='GlorotOrthogonal',
                  use_node_features=True, use_extra_node_feature=False, extra_node_feature_dim=1):
         super().__init__()
-        if use_extra_node_feature or not use_node_features:
-            raise NotImplementedError("use_extra_node_feature / use_node_features=False are not fused yet")
-        self.use_extra_node_feature = use_extra_node_feature
         self._build(energy_and_force, cutoff, num_layers, hidden_channels, out_channels, int_emb_size,
                     basis_emb_size_dist, basis_emb_size_angle, basis_emb_size_torsion, out_emb_channels,
                     num_spherical, num_radial, envelope_exponent, num_before_skip, num_after_skip,
-                    num_output_layers, act, output_init)
+                    num_output_layers, act, output_init, use_node_features, use_extra_node_feature,
+                    extra_node_feature_dim)
 
 
 class DimeNetPP(_DimeNetFamily):

@@ -180,7 +180,7 @@ def _update_v(sd, name, e2, i, num_nodes, n_lins):                        # sphe
 
 def dimenet_family_forward(sd, z, pos, batch, *, torsion, cutoff=5.0, num_layers=4, num_spherical=7,
                            num_radial=6, envelope_exponent=5, num_before_skip=1, num_after_skip=2,
-                           num_output_layers=3, num_graphs=None, return_intermediates=False):
+                           num_output_layers=3, num_graphs=None, return_intermediates=False, node_feature=None):
     """SphereNet.forward (spherenet.py:296-320, torsion=True) / DimeNetPP.forward
     (dimenetpp.py:273-293, torsion=False) as one function over a state_dict."""
     n = z.size(0)
@@ -202,7 +202,12 @@ def dimenet_family_forward(sd, z, pos, batch, *, torsion, cutoff=5.0, num_layers
         sbf = bs.angle_emb(dist, angle, idx_kj, cutoff, envelope_exponent)
         tbf = None
     # init_e                                                               spherenet.py:79-91
-    x = F.embedding(z, sd["init_e.emb.weight"])
+    if "init_e.emb.weight" in sd:
+        x = F.embedding(z, sd["init_e.emb.weight"])
+    else:                                                                  # use_node_features=False   spherenet.py:83-84
+        x = sd["init_e.node_embedding"][None, :].expand(z.shape[0], -1)
+    if node_feature is not None and "extra_emb.weight" in sd:              # use_extra_node_feature    spherenet.py:85-86,298-299
+        x = torch.cat((x, _lin(sd, "extra_emb", node_feature)), 1)
     r0 = swish(_lin(sd, "init_e.lin_rbf_0", rbf0))
     e1 = swish(_lin(sd, "init_e.lin", torch.cat([x[i], x[j], r0], dim=-1)))
     e2 = _lin(sd, "init_e.lin_rbf_1", rbf0) * e1

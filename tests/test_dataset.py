@@ -90,3 +90,26 @@ def test_collate_and_synthetic_generators_are_deterministic():
     assert torch.equal(p.coords_ca, q.coords_ca) and p.x.shape[1] == 1 and p.bb_embs.shape[1] == 6
     assert p.side_chain_embs.shape[1] == 8 and int(p.x.max()) < 26 and p.batch.numel() == p.x.size(0)
     assert torch.allclose((p.coords_n - p.coords_ca).norm(dim=1), torch.full((p.x.size(0),), 1.45), atol=1e-4)
+
+
+def test_size_sorted_collate_keeps_every_tensor_with_its_molecule():
+    """collate(sort_by_size=True): molecules ordered by atom count (largest first, stable); y / pos / z move with their
+    molecule, `perm` maps back, and the unsorted collate is unchanged (reference order)."""
+    from dig_b200.data import DataLoader, collate, synthetic_molecules
+    mols = synthetic_molecules(7, "qm9", seed=3, variable=True)
+    for i, m in enumerate(mols):
+        m.y = torch.tensor([float(i)])
+    plain, srt = collate(mols), collate(mols, sort_by_size=True)
+    sizes = [int(m.z.numel()) for m in mols]
+    assert plain.y.tolist() == [float(i) for i in range(7)] and not hasattr(plain, "perm")
+    order = srt.perm.tolist()
+    assert sorted(order) == list(range(7)) and [sizes[i] for i in order] == sorted(sizes, reverse=True)
+    assert srt.y.tolist() == [float(i) for i in order]
+    assert torch.equal(srt.batch, torch.repeat_interleave(torch.arange(7), torch.tensor([sizes[i] for i in order])))
+    lo = 0
+    for slot, i in enumerate(order):
+        assert torch.equal(srt.pos[lo:lo + sizes[i]], mols[i].pos) and torch.equal(srt.z[lo:lo + sizes[i]], mols[i].z)
+        lo += sizes[i]
+    assert torch.equal(srt.y[srt.perm.argsort()], plain.y)
+    b = next(iter(DataLoader(mols, batch_size=4, shuffle=False, sort_by_size=True, pin_memory=False)))
+    assert b.num_graphs == 4 and sorted(b.perm.tolist()) == [0, 1, 2, 3]

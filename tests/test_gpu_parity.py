@@ -482,6 +482,37 @@ def test_update_v_on_the_tensor_engine_matches_fp32(kw):
     assert ops.tc_timeouts() == 0 and not ops.h16_overflow()
 
 
+@pytest.mark.parametrize("kw", [dict(use_node_features=False), dict(use_extra_node_feature=True, extra_node_feature_dim=3)])
+def test_spherenet_node_feature_options(kw):
+    """SphereNet(use_node_features=False) / (use_extra_node_feature=True) (spherenet.py:54-91,259-267): same state_dict
+    keys as the reference, energies and every parameter gradient vs the oracle on the same GPU."""
+    from oracle import restated
+    from dig_b200.data import Batch, synthetic_batch
+    from dig_b200.threedgraph.method import SphereNet
+    dev = torch.device("cuda:0")
+    model = SphereNet(num_layers=2, **kw)
+    keys = set(model.state_dict())
+    assert ("init_e.node_embedding" in keys) == (kw.get("use_node_features") is False)
+    assert ("extra_emb.weight" in keys) == bool(kw.get("use_extra_node_feature"))
+    assert tuple(model.init_e.lin.weight.shape) == (128, 640 if kw.get("use_extra_node_feature") else 384)
+    sd = formula_state_dict(model.state_dict(), seed=11)
+    model.load_state_dict(sd)
+    model = model.to(dev)
+    b = synthetic_batch(5, "qm9", seed=6).to(dev)
+    nf = torch.randn(b.z.numel(), 3, device=dev) if "extra_node_feature_dim" in kw else None
+    bd = Batch(z=b.z, pos=b.pos, batch=b.batch, node_feature=nf)
+    out = model(bd)
+    sd_ref = {k: v.to(dev).clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    ref = restated.spherenet_forward(sd_ref, b.z, b.pos, b.batch, num_layers=2, node_feature=nf)
+    assert rel_err(out.detach().cpu().numpy(), ref.detach().cpu().numpy()) < TOL
+    out.sum().backward()
+    ref.sum().backward()
+    for name, p in model.named_parameters():
+        r = sd_ref[name].grad
+        assert p.grad is not None and r is not None, name
+        assert rel_err(p.grad.cpu().numpy(), r.cpu().numpy()) < 1e-4, name
+
+
 def test_packed_weights_follow_parameter_updates():
     """The tcgen05 weight cache is keyed on tensor._version: an in-place optimiser-style update must be seen."""
     from dig_b200.data import synthetic_batch

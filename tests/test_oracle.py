@@ -143,3 +143,23 @@ def test_pronet_oracle_equals_reference_fixture(name, ctor, wseed):
         assert np.array_equal(inter[key].numpy(), g[key]), key
     assert np.array_equal(y.numpy(), g["energy_f32"])
     assert sum(int(np.prod(v)) for v in shapes.values()) == int(g["num_params"])
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("kw", [dict(use_node_features=False), dict(use_extra_node_feature=True, extra_node_feature_dim=3)])
+def test_restated_node_feature_options_match_live_reference(kw):
+    """spherenet.py:54-91,259-267: the learned shared node embedding and the extra node features, restated vs the real
+    reference run now (no fixture: these options only change init_e)."""
+    from oracle.ref_loader import load_reference
+    from dig_b200.data import Batch, synthetic_batch
+    method = load_reference()
+    torch.manual_seed(0)
+    model = method.SphereNet(cutoff=5.0, num_layers=2, **kw)
+    sd = formula_state_dict(model.state_dict(), seed=11)
+    model.load_state_dict(sd)
+    b = synthetic_batch(3, "qm9", seed=6)
+    nf = torch.randn(b.z.numel(), 3) if "extra_node_feature_dim" in kw else None
+    with torch.no_grad():
+        want = model(Batch(z=b.z, pos=b.pos, batch=b.batch, node_feature=nf))
+        got = restated.spherenet_forward(sd, b.z, b.pos, b.batch, num_layers=2, node_feature=nf)
+    assert torch.equal(got, want)
