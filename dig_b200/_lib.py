@@ -59,6 +59,8 @@ SIGNATURES = {
     "dig3d_graph_ptr": [P, c_int64, c_int64, P, P],
     "dig3d_radius_neighbors": [P, P, P, c_int64, c_int64, c_double, c_int32, P, P, P],
     "dig3d_validate_nodes": [P, P, c_int64, c_int64, c_int32, P, P],
+    "dig3d_knn2": [P, P, P, c_int64, c_int64, P, P, P],
+    "dig3d_triplet_geometry_knn": [P, P, P, P, P, c_int64, P, P, P, P, P, P, P],
     "dig3d_triplet_count": [P, P, c_int64, c_int32, P, P],
     "dig3d_scan_counts": [P, P, c_int64, P, P, P, P],
     "dig3d_edge_fill": [P, P, P, P, P, c_int64, c_int32, c_int64, P, P, P, P, P, P, P],

@@ -78,6 +78,44 @@ __global__ void validate_nodes_kernel(const int64_t* __restrict__ batch, const i
   if (bad) atomicOr(flags, bad);
 }
 
+// Two nearest neighbours of every node inside its graph, torch_cluster.knn (CUDA) semantics as used by
+// knn_graph(pos, 1 / 2, batch) at ggraph3D/.../geometric_computing.py:14,16: candidates scanned in ascending index,
+// squared distance accumulated as fma(diff, diff, acc), the three best kept by strict-`>` insertion (self included,
+// ties keep the lower index in front), then self is dropped.  nn1 / nn2 = -1 where the graph is too small.
+__global__ void knn2_kernel(const float* __restrict__ pos, const int64_t* __restrict__ batch,
+                            const int32_t* __restrict__ ptr, int n_nodes, int n_graphs,
+                            int32_t* __restrict__ nn1, int32_t* __restrict__ nn2) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_nodes) return;
+  const int64_t gb = batch[n];
+  if (gb < 0 || gb >= n_graphs) { nn1[n] = nn2[n] = -1; return; }
+  const int lo = ptr[gb], hi = ptr[gb + 1];
+  const f3 q = load3(pos, n);
+  const float INF = __int_as_float(0x7f800000);
+  float bd[3] = {INF, INF, INF};
+  int bi[3] = {-1, -1, -1};
+  for (int c = lo; c < hi; ++c) {
+    const f3 p = load3(pos, c);
+    const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
+    const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+      if (bd[e] > d2) {
+#pragma unroll
+        for (int m = 2; m > e; --m) { bd[m] = bd[m - 1]; bi[m] = bi[m - 1]; }
+        bd[e] = d2; bi[e] = c;
+        break;
+      }
+    }
+  }
+  int out[2] = {-1, -1}, k = 0;
+#pragma unroll
+  for (int e = 0; e < 3; ++e)
+    if (bi[e] >= 0 && bi[e] != n && k < 2) out[k++] = bi[e];
+  nn1[n] = out[0];
+  nn2[n] = out[1];
+}
+
 __device__ __forceinline__ int find_sorted(const int32_t* __restrict__ list, int len, int key) {
   // position of key in ascending list, or -1
   int lo = 0, hi = len;
@@ -233,7 +271,8 @@ triplet_geometry_kernel(const float* __restrict__ pos, const int32_t* __restrict
                         const int32_t* __restrict__ trip_ptr, int n_edges, int use_torsion,
                         float* __restrict__ angle, float* __restrict__ torsion, int32_t* __restrict__ idx_kj,
                         int32_t* __restrict__ idx_ji, int64_t* __restrict__ idx_kj64,
-                        int64_t* __restrict__ idx_ji64) {
+                        int64_t* __restrict__ idx_ji64, const int32_t* __restrict__ nn1 = nullptr,
+                        const int32_t* __restrict__ nn2 = nullptr) {
   __shared__ float planes[GEO_WARPS][GEO_MAXDEG][3];
   __shared__ int32_t ks[GEO_WARPS][GEO_MAXDEG];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -271,7 +310,17 @@ triplet_geometry_kernel(const float* __restrict__ pos, const int32_t* __restrict
     if (idx_ji) idx_ji[t] = e;
     if (idx_kj64) idx_kj64[t] = base + s;
     if (idx_ji64) idx_ji64[t] = e;
-    if (use_torsion) {
+    if (use_torsion == 2) {
+      // G-SphereNet's variant (ggraph3D/.../geometric_computing.py:87-103): ONE reference atom, the nearest
+      // neighbour of j in its graph, or the second nearest when the nearest is i
+      const int k_n = (nn1[j] == i) ? nn2[j] : nn1[j];
+      const f3 p2 = cross_aten(pos_ji, sub3(load3(pos, k_n), pj));
+      const float ta = sum3_aten(mul3(p1, p2));
+      const float tb = __fdiv_rn(sum3_aten(mul3(cross_aten(p1, p2), pos_ji)), dist_ji);
+      float tor = atan2f(tb, ta);
+      if (tor <= 0.0f) tor = __fadd_rn(tor, 6.2831855f);
+      torsion[t] = tor;
+    } else if (use_torsion) {
       // min over k_n != i (k_n == k kept) of atan2(((p1 x p2).ji)/|ji|, p1.p2), <=0 -> +2pi
       //                                         geometric_computing.py:53-75
       float best = __int_as_float(0x7f800000);
@@ -425,6 +474,29 @@ int dig3d_triplet_geometry(const float* pos, const int32_t* src, const int32_t* 
   triplet_geometry_kernel<<<ceil_div(n_edges, GEO_WARPS), GEO_WARPS * 32, 0, (cudaStream_t)stream>>>(
       pos, src, dst, row_ptr, trip_ptr, (int)n_edges, use_torsion, angle, torsion, idx_kj, idx_ji, idx_kj64,
       idx_ji64);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_knn2(const float* pos, const int64_t* batch, const int32_t* graph_ptr, int64_t n_nodes, int64_t n_graphs,
+               int32_t* nn1, int32_t* nn2, void* stream) {
+  DIG3D_REQUIRE(pos && batch && graph_ptr && nn1 && nn2, "knn2: null pointer");
+  if (n_nodes == 0) return DIG3D_OK;
+  knn2_kernel<<<ceil_div(n_nodes, 128), 128, 0, (cudaStream_t)stream>>>(pos, batch, graph_ptr, (int)n_nodes,
+                                                                       (int)n_graphs, nn1, nn2);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_triplet_geometry_knn(const float* pos, const int32_t* src, const int32_t* dst, const int32_t* row_ptr,
+                               const int32_t* trip_ptr, int64_t n_edges, const int32_t* nn1, const int32_t* nn2,
+                               float* angle, float* torsion, int64_t* idx_kj64, int64_t* idx_ji64, void* stream) {
+  DIG3D_REQUIRE(pos && src && dst && row_ptr && trip_ptr && nn1 && nn2 && angle && torsion,
+                "triplet_geometry_knn: null pointer");
+  if (n_edges == 0) return DIG3D_OK;
+  triplet_geometry_kernel<<<ceil_div(n_edges, GEO_WARPS), GEO_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      pos, src, dst, row_ptr, trip_ptr, (int)n_edges, 2, angle, torsion, nullptr, nullptr, idx_kj64, idx_ji64, nn1,
+      nn2);
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
 }

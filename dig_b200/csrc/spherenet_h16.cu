@@ -32,7 +32,7 @@ using namespace tc05;
 constexpr int H_M = 128;
 constexpr int H_AKU = H_M + 1;                     // k-unit stride of the A planes in 16-byte units (padded)
 constexpr int H_PLANE = 16 * H_AKU * 16;           // bytes of one fp16 plane of a [128 x 128] operand tile
-constexpr int H_STAGES = 4;
+constexpr int H_STAGES = 5;                       // 80 KB of weight slabs in flight (the L2 -> smem latency is ~2 k cycles)
 constexpr int H_SLAB_K = 32;                       // ring granularity: K = 32 slab = [hi|lo][4 k-units][N][8 halves]
 constexpr int H_STAGE_BYTES = 2 * 4 * 128 * 16;    // 16 KB (N = 128)
 constexpr int H_TILE_WARPS = 8;
@@ -315,6 +315,27 @@ __device__ __forceinline__ void h_finish(HSmem& s, const HCtx* c) {
   __syncthreads();
   if ((threadIdx.x >> 5) == 0) tmem_dealloc(s.tmem_base, 512);
 }
+// Row-major [rows x W] fp32 tile (W = 128 or 64) -> global memory with full-line stores: every thread parks its W/2
+// values in a [128][W + 1] staging overlay of the tile's planes (lane = row: conflict free), then each warp writes
+// whole rows (a direct store from the row-per-thread layout touches 32 lines with 16 bytes each per instruction).
+template <int W>
+__device__ __forceinline__ void h_store_tile_coalesced(HSmem& s, const HCtx& c, int col0, const float (&v)[W / 2],
+                                                       float* __restrict__ out, int rows) {
+  constexpr int LD = W + 1, RPW = 128 / W;            // rows written per warp instruction (float4 per lane)
+  float* st = reinterpret_cast<float*>(s.a[c.t][0]);
+#pragma unroll
+  for (int i = 0; i < W / 2; ++i) st[c.row * LD + col0 + i] = v[i];
+  h_tile_bar(c.t);
+  const int w = c.et >> 5, lane = c.et & 31;
+  for (int r0 = w * RPW; r0 < rows; r0 += H_TILE_WARPS * RPW) {
+    const int r = r0 + (RPW == 2 ? (lane >> 4) : 0), c4 = 4 * (RPW == 2 ? (lane & 15) : lane);
+    if (r < rows) {
+      const float* src = st + r * LD + c4;
+      *reinterpret_cast<float4*>(out + (size_t)r * W + c4) = make_float4(src[0], src[1], src[2], src[3]);
+    }
+  }
+}
+
 // e2 tile (staged as [128][H_LDS] fp32 over the tile's own planes) -> segmented edge -> node sums; the tile's 256
 // threads take one column and one half of the rows each.  Rows are target-sorted: only the first and the last
 // segment of a half can be shared with another half / tile (atomics), interior segments are plain stores.
@@ -388,6 +409,7 @@ sphere_update_e_b_h16_kernel(const float* __restrict__ m, const float* __restric
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (tid == 0 && g_h16_trace_on && blockIdx.x == 0) g_h16_trace[104] = clock64();
   HCtx c;
   bool epi = false;
   if (warp < H_CTRL_WARPS) {
@@ -398,6 +420,7 @@ sphere_update_e_b_h16_kernel(const float* __restrict__ m, const float* __restric
     epi = true;
     constexpr bool TRACE = true;
     const bool probe = c.et == 0;
+    if (probe && c.t == 0) H_TRACE(105);
     const int e0 = (tile0 + c.t) * H_M, rows = min(H_M, n_edges - e0);
     const bool valid = c.row < rows;
     const size_t ge = (size_t)(e0 + c.row);
@@ -422,17 +445,21 @@ sphere_update_e_b_h16_kernel(const float* __restrict__ m, const float* __restric
     };
     // A0 = m tile (K = 64)
     h_load_tile<8>(s, c, m + (size_t)e0 * 64, 64, rows);
+    if (probe && c.t == 0) H_TRACE(106);
     h_epi_done(s, c.t);
+    if (probe && c.t == 0) H_TRACE(107);
     prefetch_skip(x_ji);
+    if (probe && c.t == 0) H_TRACE(108);
     // The eight epilogues of the chain (spherenet.py:172-179); stash = the fp32 skip / residual row (x H_SA):
     //   q=0: h = stash(x_ji) + act(lin_up(m))                -> A, stash
     //   q=1,4,6: t = act(lin1(h))                            -> A
     //   q=2,5: h = stash + act(lin2(t))                      -> A, stash      (q=2: then stash <- e1_in)
     //   q=3: h = act(lin(h)) + stash(e1_in)                  -> A, stash
     //   q=7: h = stash + act(lin2(t))                        -> e1_out, e2 tile
+    float acc_final[64];
 #pragma unroll 1
     for (int q = 0; q < 8; ++q) {
-      float acc[64];
+      float (&acc)[64] = acc_final;
       if (probe) H_TRACE(32 + c.t * 32 + q * 4);
       h_drain<4, true>(s, c, col0, q == 0 ? 1 : 2, acc);
       if (probe) H_TRACE(32 + c.t * 32 + q * 4 + 1);
@@ -473,21 +500,19 @@ sphere_update_e_b_h16_kernel(const float* __restrict__ m, const float* __restric
           for (int i = 0; i < 16; ++i) v16[i] = v[i];
           h_store_a16(s, c, col, v16);
         } else {
-          // e1_out and e2 = lin_rbf(rbf0) * e1 (tile staged over this tile's planes; all its MMAs are done)
+          // e1 (unscaled, kept in the accumulator registers for the coalesced store below) and
+          // e2 = lin_rbf(rbf0) * e1, staged as a [128][H_LDS] tile over this tile's planes (all its MMAs are done)
           float* e2t = reinterpret_cast<float*>(s.a[c.t][0]);
 #pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            float o[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              o[u] = v[i + u] * (1.0f / H_SA);
-              c.bad |= !h_finite(o[u]);
-              float gsum = 0.f;
-#pragma unroll
-              for (int n = 0; n < 6; ++n) gsum = fmaf(s.wr[(col + i + u) * 8 + n], rb[n], gsum);
-              e2t[c.row * H_LDS + col + i + u] = gsum * o[u];
-            }
-            if (valid) *reinterpret_cast<float4*>(e1_out + ge * 128 + col + i) = make_float4(o[0], o[1], o[2], o[3]);
+          for (int i = 0; i < 16; ++i) {
+            const float o = v[i] * (1.0f / H_SA);
+            c.bad |= !h_finite(o);
+            const float4 w0 = *reinterpret_cast<const float4*>(s.wr + (col + i) * 8);
+            const float2 w1 = *reinterpret_cast<const float2*>(s.wr + (col + i) * 8 + 4);
+            const float gsum = fmaf(w1.y, rb[5], fmaf(w1.x, rb[4], fmaf(w0.w, rb[3], fmaf(w0.z, rb[2],
+                               fmaf(w0.y, rb[1], w0.x * rb[0])))));
+            e2t[c.row * H_LDS + col + i] = gsum * o;
+            v[i] = o;
           }
         }
       }
@@ -501,6 +526,8 @@ sphere_update_e_b_h16_kernel(const float* __restrict__ m, const float* __restric
     }
     h_tile_bar(c.t);
     h_segment_sums(s, c, rows, v_in);   // spherenet.py:211
+    h_tile_bar(c.t);
+    h_store_tile_coalesced<128>(s, c, col0, acc_final, e1_out + (size_t)e0 * 128, rows);
     if (probe) H_TRACE(96 + c.t);
   }
   h_finish(s, epi ? &c : nullptr);
@@ -597,15 +624,9 @@ sphere_update_e_a_h16_kernel(const float* __restrict__ e1, const float* __restri
       const int col = c.half * 32;
       float a32[32];
       h_drain<2, true>(s, c, col, 2, a32);
-      if (valid) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          float4 o;
-          o.x = hswish<FAST>(a32[i] * H_INV); o.y = hswish<FAST>(a32[i + 1] * H_INV);
-          o.z = hswish<FAST>(a32[i + 2] * H_INV); o.w = hswish<FAST>(a32[i + 3] * H_INV);
-          *reinterpret_cast<float4*>(x_down + ge * 64 + col + i) = o;
-        }
-      }
+      for (int i = 0; i < 32; ++i) a32[i] = hswish<FAST>(a32[i] * H_INV);
+      h_store_tile_coalesced<64>(s, c, col, a32, x_down + (size_t)e0 * 64, rows);   // all MMAs of the tile are done
     }
   }
   h_finish(s, epi ? &c : nullptr);
@@ -699,25 +720,24 @@ sphere_init_e_h16_kernel(const int64_t* __restrict__ z, const int32_t* __restric
     }
     h_epi_done(s, c.t);
     h_drain<4, false>(s, c, col0, 2, acc);
-    // e1 = act(. + b), e2 = lin_rbf_1(rbf) * e1 (tile staged over the planes), edge -> node sums
+    // e1 = act(. + b), e2 = lin_rbf_1(rbf) * e1 (tile staged over the planes), edge -> node sums, coalesced e1 store
     float* e2t = reinterpret_cast<float*>(s.a[c.t][0]);
 #pragma unroll
-    for (int i = 0; i < 64; i += 4) {
-      float o[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int col = col0 + i + u;
-        o[u] = hswish<FAST>(fmaf(acc[i + u], H_INV, s.bias[0][col]));
-        c.bad |= !h_finite(o[u]);
-        float gsum = 0.f;
-#pragma unroll
-        for (int n = 0; n < 6; ++n) gsum = fmaf(s.wr[col * 8 + n], rb[n], gsum);
-        e2t[c.row * H_LDS + col] = gsum * o[u];
-      }
-      if (valid) *reinterpret_cast<float4*>(e1 + ge * 128 + col0 + i) = make_float4(o[0], o[1], o[2], o[3]);
+    for (int i = 0; i < 64; ++i) {
+      const int col = col0 + i;
+      const float o = hswish<FAST>(fmaf(acc[i], H_INV, s.bias[0][col]));
+      c.bad |= !h_finite(o);
+      const float4 w0 = *reinterpret_cast<const float4*>(s.wr + col * 8);
+      const float2 w1 = *reinterpret_cast<const float2*>(s.wr + col * 8 + 4);
+      const float gsum = fmaf(w1.y, rb[5], fmaf(w1.x, rb[4], fmaf(w0.w, rb[3], fmaf(w0.z, rb[2],
+                         fmaf(w0.y, rb[1], w0.x * rb[0])))));
+      e2t[c.row * H_LDS + col] = gsum * o;
+      acc[i] = o;
     }
     h_tile_bar(c.t);
     h_segment_sums(s, c, rows, v_in);
+    h_tile_bar(c.t);
+    h_store_tile_coalesced<128>(s, c, col0, acc, e1 + (size_t)e0 * 128, rows);
   }
   h_finish(s, epi ? &c : nullptr);
 }

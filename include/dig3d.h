@@ -38,6 +38,16 @@ int dig3d_abi_version(void);
  * + SparseTensor / repeat_interleave triplet enumeration   utils/geometric_computing.py:27-41
  */
 
+/* G-SphereNet's private geometry (reference dig/ggraph3D/method/G_SphereNet/model/geometric_computing.py:12-19,54-104):
+ * dig3d_knn2 = the two nearest neighbours of every node inside its graph (torch_cluster knn semantics; -1 where the
+ * graph is too small); dig3d_triplet_geometry_knn = angles as dig3d_triplet_geometry plus the single-reference torsion
+ * (reference atom = nearest neighbour of j, or the second nearest when the nearest is i), mapped to (0, 2 pi]. */
+int dig3d_knn2(const float* pos, const int64_t* batch, const int32_t* graph_ptr, int64_t n_nodes, int64_t n_graphs,
+               int32_t* nn1, int32_t* nn2, void* stream);
+int dig3d_triplet_geometry_knn(const float* pos, const int32_t* src, const int32_t* dst, const int32_t* row_ptr,
+                               const int32_t* trip_ptr, int64_t n_edges, const int32_t* nn1, const int32_t* nn2,
+                               float* angle, float* torsion, int64_t* idx_kj64, int64_t* idx_ji64, void* stream);
+
 /* ptr[g] = first node of graph g, ptr[n_graphs] = n_nodes (batch is sorted ascending). */
 int dig3d_graph_ptr(const int64_t* batch, int64_t n_nodes, int64_t n_graphs, int32_t* ptr, void* stream);
 

@@ -104,6 +104,31 @@ def xyz_to_dat(pos, edge_index, num_nodes, use_torsion=False):
 
 
 # ----------------------------------------------------------------------------- basis
+def xyztodat_knn(pos, edge_index, num_nodes, batch):
+    """G-SphereNet's private geometry (ggraph3D/method/G_SphereNet/model/geometric_computing.py:54-104): same distances,
+    triplets and angles as xyz_to_dat; the torsion of a triplet (k -> j -> i) uses ONE reference atom, the nearest
+    neighbour of j in its graph (the second nearest when the nearest is i), and is mapped to (0, 2 pi]."""
+    dist, angle, i, j, idx_kj, idx_ji = xyz_to_dat(pos, edge_index, num_nodes, use_torsion=False)
+    n = pos.size(0)
+    nbr = shim.knn_graph(pos, 2, batch)                                     # grouped by query, nearest first  :14-19
+    cnt = torch.bincount(nbr[1], minlength=n)
+    assert int(cnt.min()) == 2, "every graph needs at least three atoms (the reference errors otherwise)"
+    near = nbr[0].view(n, 2)
+    idx_i, idx_j, idx_k = i[idx_ji], j[idx_ji], j[idx_kj]
+    k_n = near[idx_j, 0].clone()                                            # :87-93
+    mask = k_n == idx_i
+    k_n[mask] = near[idx_j, 1][mask]
+    pos_j0, pos_ji, pos_jk = pos[idx_k] - pos[idx_j], pos[idx_i] - pos[idx_j], pos[k_n] - pos[idx_j]   # :96-98
+    dist_ji = pos_ji.pow(2).sum(dim=-1).sqrt()
+    plane1 = torch.linalg.cross(pos_ji, pos_j0, dim=-1)
+    plane2 = torch.linalg.cross(pos_ji, pos_jk, dim=-1)
+    a = (plane1 * plane2).sum(dim=-1)
+    b = (torch.linalg.cross(plane1, plane2, dim=-1) * pos_ji).sum(dim=-1) / dist_ji
+    torsion = torch.atan2(b, a)
+    torsion = torch.where(torsion <= 0, torsion + 2 * math.pi, torsion)    # :102-103
+    return dist, angle, torsion, i, j, idx_kj, idx_ji
+
+
 def envelope(x, exponent):                       # spherenet/features.py:151-164
     p = exponent + 1
     a, b, c = -(p + 1) * (p + 2) / 2, p * (p + 2), -p * (p + 1) / 2

@@ -148,6 +148,21 @@ class SparseTensor:
         val = val[src] if val is not None else None
         return SparseTensor(new_row, col, val, (idx.numel(), self._sizes[1]), is_sorted=True)
 
+    def to_dense(self):
+        """Dense [rows, cols] matrix of the values (duplicates add up, like torch_sparse)."""
+        val = self.storage.value()
+        if val is None:
+            val = torch.ones_like(self.storage.row(), dtype=torch.float)
+        out = torch.zeros(self._sizes, dtype=val.dtype, device=val.device)
+        return out.index_put_((self.storage.row(), self.storage.col()), val, accumulate=True)
+
+    @classmethod
+    def from_dense(cls, mat, has_value=True):
+        """torch_sparse.SparseTensor.from_dense: the non-zero entries in row-major order."""
+        idx = mat.nonzero()
+        row, col = idx[:, 0], idx[:, 1]
+        return cls(row, col, mat[row, col] if has_value else None, tuple(mat.shape), is_sorted=True)
+
     def sum(self, dim=None):
         assert dim == 1
         val = self.storage.value()
@@ -200,6 +215,29 @@ def radius_graph(x, r, batch=None, loop=False, max_num_neighbors=32,
         keep = query != neigh
         query, neigh = query[keep], neigh[keep]
     return torch.stack([neigh, query], dim=0)
+
+
+def knn_graph(x, k, batch=None, loop=False, flow="source_to_target", cosine=False, num_workers=1):
+    """torch_cluster.knn_graph with the CUDA kernel's semantics: every node queries the nodes of its own graph in
+    ascending index, keeps the (k + 1 when loop=False) smallest squared distances by strict-`>` insertion (ties: the
+    lower index stays in front), then the self pair is dropped.  Returns [2, n*k] = (source = neighbour, target =
+    query), grouped by query, nearest first.  Called at ggraph3D/.../geometric_computing.py:14,16."""
+    assert flow == "source_to_target" and not cosine
+    n = x.size(0)
+    if batch is None:
+        batch = torch.zeros(n, dtype=torch.long, device=x.device)
+    kk = k if loop else k + 1
+    xd = x.detach().to(torch.float32)
+    acc = torch.zeros(n, n, dtype=torch.float32, device=x.device)
+    for d in range(x.size(1)):
+        diff = xd[None, :, d] - xd[:, None, d]
+        acc = (diff.double() * diff.double() + acc.double()).float()          # fma emulation, as in radius_graph
+    acc = torch.where(batch[None, :] == batch[:, None], acc, torch.full_like(acc, float("inf")))
+    order = torch.sort(acc, dim=1, stable=True).indices[:, :kk]               # stable: the lower index wins ties
+    valid = torch.gather(acc, 1, order) < float("inf")
+    query = torch.arange(n, device=x.device)[:, None].expand_as(order)
+    keep = valid if loop else (valid & (order != query))
+    return torch.stack([order[keep], query[keep]], dim=0)
 
 
 # --------------------------------------------------------------------------
@@ -401,12 +439,12 @@ def install():
         return
     _module("torch_scatter", scatter=scatter, scatter_min=scatter_min, _dig_oracle_shim=True)
     _module("torch_sparse", SparseTensor=SparseTensor, matmul=_sparse_matmul)
-    _module("torch_cluster", radius_graph=radius_graph)
+    _module("torch_cluster", radius_graph=radius_graph, knn_graph=knn_graph)
     inits = _module("torch_geometric.nn.inits", glorot_orthogonal=glorot_orthogonal, glorot=glorot,
                     zeros=zeros, ones=ones, uniform=uniform, kaiming_uniform=kaiming_uniform)
     schnet = _module("torch_geometric.nn.models.schnet", GaussianSmearing=GaussianSmearing)
     models = _module("torch_geometric.nn.models", schnet=schnet)
-    nn = _module("torch_geometric.nn", radius_graph=radius_graph, GraphConv=GraphConv,
+    nn = _module("torch_geometric.nn", radius_graph=radius_graph, knn_graph=knn_graph, GraphConv=GraphConv,
                  GraphNorm=GraphNorm, MessagePassing=MessagePassing, inits=inits, models=models)
     data = _module("torch_geometric.data", Data=Data, DataLoader=DataLoader,
                    InMemoryDataset=InMemoryDataset, download_url=_download_url)

@@ -594,3 +594,34 @@ def test_generic_channel_sizes(cls_name, kw):
                                        num_output_layers=kw["num_output_layers"])
     assert u.shape == ref.shape
     assert rel_err(u.cpu().numpy(), ref.cpu().numpy()) < TOL
+
+
+def test_gspherenet_private_geometry_bit_exact():
+    """xyztodat / xyztoda of G-SphereNet's SphereNet copy (ggraph3D/.../geometric_computing.py:22-104,
+    kNN-referenced torsion) vs the oracle's op sequence on the same GPU -- indices equal, dist / angle / torsion bit
+    equal -- for the radius graph's sorted edge list and for a shuffled one."""
+    from oracle import restated
+    from dig_b200.data import synthetic_batch
+    from dig_b200.ggraph3D.method.G_SphereNet.model.geometric_computing import xyztoda, xyztodat
+    dev = torch.device("cuda:0")
+    b = synthetic_batch(7, "qm9", seed=9, variable=True).to(dev)
+    n = b.pos.size(0)
+    ei = restated.radius_graph(b.pos, 5.0, b.batch)
+    want = restated.xyztodat_knn(b.pos, ei, n, b.batch)
+    got = xyztodat(b.pos, ei, n, b.batch)
+    for name, w, g in zip("dist angle torsion i j idx_kj idx_ji".split(), want, got):
+        assert torch.equal(w, g), name
+    assert float(got[2].min()) > 0.0 and float(got[2].max()) <= 6.2831856
+    want2 = restated.xyz_to_dat(b.pos, ei, n, use_torsion=False)
+    for name, w, g in zip("dist angle i j idx_kj idx_ji".split(), want2, xyztoda(b.pos, ei, n)):
+        assert torch.equal(w, g), name
+    # a shuffled edge list goes through the same re-ordering as xyz_to_dat: per (k -> j -> i) triplet the values agree
+    perm = torch.randperm(ei.size(1), generator=torch.Generator().manual_seed(1)).to(dev)
+    shuf = xyztodat(b.pos, ei[:, perm].contiguous(), n, b.batch)
+    key = lambda r, edges: (edges[1][r[6]] * n + edges[0][r[6]]) * n + edges[0][r[5]]      # (i, j, k) of a triplet
+    o1, o2 = torch.argsort(key(got, ei)), torch.argsort(key(shuf, ei[:, perm]))
+    assert torch.equal(got[1][o1], shuf[1][o2]) and torch.equal(got[2][o1], shuf[2][o2])
+    with pytest.raises(ValueError, match="three atoms"):
+        two = synthetic_batch(1, "qm9", seed=1).to(dev)
+        e2 = torch.tensor([[1, 0], [0, 1]], device=dev)
+        xyztodat(two.pos[:2].contiguous(), e2, 2, torch.zeros(2, dtype=torch.long, device=dev))

@@ -6,6 +6,7 @@
 * oracle/restated.py == real reference, bit for bit, on every fixture case (CPU fp32)
 """
 import math
+import os
 
 import numpy as np
 import pytest
@@ -163,3 +164,24 @@ def test_restated_node_feature_options_match_live_reference(kw):
         want = model(Batch(z=b.z, pos=b.pos, batch=b.batch, node_feature=nf))
         got = restated.spherenet_forward(sd, b.z, b.pos, b.batch, num_layers=2, node_feature=nf)
     assert torch.equal(got, want)
+
+
+@pytest.mark.reference
+def test_restated_gspherenet_geometry_matches_live_reference():
+    """oracle.restated.xyztodat_knn vs the real ggraph3D/method/G_SphereNet/model/geometric_computing.py (loaded from its
+    file over the shim: the ggraph3D package itself needs rdkit), bit for bit."""
+    import importlib.util
+    from oracle import shim
+    from oracle.ref_loader import REFERENCE_ROOT
+    from dig_b200.data import synthetic_batch
+    shim.install()
+    path = os.path.join(REFERENCE_ROOT, "dig", "ggraph3D", "method", "G_SphereNet", "model", "geometric_computing.py")
+    spec = importlib.util.spec_from_file_location("gsn_geo", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    b = synthetic_batch(5, "qm9", seed=9, variable=True)
+    ei = restated.radius_graph(b.pos, 5.0, b.batch)
+    want = mod.xyztodat(b.pos, ei, b.pos.size(0), b.batch)       # (the restatement takes target-sorted edge lists)
+    got = restated.xyztodat_knn(b.pos, ei, b.pos.size(0), b.batch)
+    for w, g in zip(want, got):
+        assert torch.equal(w, g)

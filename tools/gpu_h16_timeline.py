@@ -29,6 +29,8 @@ buf = (ctypes.c_longlong * 128)()
 lib.dig3d_h16_trace(0, buf)
 t = list(buf); t0 = t[100]
 print(f"kernel (CTA 0): {t[102] - t0} cycles, {t[103] - t[101]} ns -> {1e3 * (t[102] - t0) / max(1, t[103] - t[101]):.0f} MHz")
+print(f"startup: setup+sync +{t[104] - t0}, epilogue registers +{t[105] - t0}, m tile staged +{t[106] - t0}, "
+      f"A published +{t[107] - t0}, skip row prefetched +{t[108] - t0}")
 print("MMA issuer: job (layer q, tile t): A-ready .. all issued")
 for q in range(8):
     for tt in range(2):
