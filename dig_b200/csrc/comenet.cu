@@ -84,14 +84,19 @@ __global__ void comenet_refs_kernel(const float* __restrict__ dist, const int32_
   }
 }
 
+// vecs = pos[j] - pos[i] (comenet.py:297), or -- FROM_VEC, the OCP variant with periodic images -- the precomputed
+// distance vectors of get_pbc_distances (comenet-ocp.py:352-365), passed in `pos` as [E, 3].
+template <bool FROM_VEC = false>
 __device__ __forceinline__ f3 edge_vec(const float* __restrict__ pos, const int32_t* __restrict__ src,
                                        const int32_t* __restrict__ dst, int e) {
-  return sub3(load3(pos, src[e]), load3(pos, dst[e]));   // vecs = pos[j] - pos[i]   comenet.py:297
+  if (FROM_VEC) return load3(pos, e);
+  return sub3(load3(pos, src[e]), load3(pos, dst[e]));
 }
 __device__ __forceinline__ f3 neg3(const f3 a) { return {-a.x, -a.y, -a.z}; }
 __device__ __forceinline__ float fold_pi(float t) { return t < 0.f ? __fadd_rn(t, 3.14159274101257324f) : t; }
 
 // theta / phi / tau and the two basis features of every edge
+template <bool FROM_VEC>
 __global__ void comenet_edge_features_kernel(const float* __restrict__ pos, const float* __restrict__ dist,
                                              const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
                                              const int32_t* __restrict__ a0_in, const int32_t* __restrict__ a1_in,
@@ -105,9 +110,9 @@ __global__ void comenet_edge_features_kernel(const float* __restrict__ pos, cons
   const int n0 = src[e0i], n0_j = dst[e0j];
   const int idx_iref = (n0 == j) ? e1i : e0i;                            // comenet.py:344-348
   const int idx_jref = (n0_j == i) ? e1j : e0j;                          // comenet.py:350-354
-  const f3 pos_ji = edge_vec(pos, src, dst, e);
-  const f3 pos_in0 = edge_vec(pos, src, dst, e0i), pos_in1 = edge_vec(pos, src, dst, e1i);
-  const f3 pos_iref = edge_vec(pos, src, dst, idx_iref), pos_jref = edge_vec(pos, src, dst, idx_jref);
+  const f3 pos_ji = edge_vec<FROM_VEC>(pos, src, dst, e);
+  const f3 pos_in0 = edge_vec<FROM_VEC>(pos, src, dst, e0i), pos_in1 = edge_vec<FROM_VEC>(pos, src, dst, e1i);
+  const f3 pos_iref = edge_vec<FROM_VEC>(pos, src, dst, idx_iref), pos_jref = edge_vec<FROM_VEC>(pos, src, dst, idx_jref);
   const f3 mji = neg3(pos_ji);
   // theta                                                                comenet.py:365-368
   const f3 pl1 = cross_aten(mji, pos_in0);
@@ -136,6 +141,66 @@ __global__ void comenet_edge_features_kernel(const float* __restrict__ pos, cons
   for (int h = 0; h < 4; ++h)
 #pragma unroll
     for (int r = 0; r < 3; ++r) f1[(size_t)e * NF1 + h * 3 + r] = __fmul_rn(rb[(h == 0 ? 0 : 1) * 3 + r], ylm[h]);
+}
+
+// ------------------------------------------------------------------ OCP variant: arbitrary edge lists, periodic images
+// distance_vec = pos[row] - pos[col] + cell_offsets . cell[graph of the edge]      (ocpmodels get_pbc_distances, called
+// at comenet-ocp.py:352-359; row = edge_index[0] = source j, col = edge_index[1] = target i)
+__global__ void pbc_edge_vectors_kernel(const float* __restrict__ pos, const int64_t* __restrict__ edge_index,
+                                        const float* __restrict__ cell, const float* __restrict__ cell_offsets,
+                                        const int32_t* __restrict__ edge_graph, int n_edges,
+                                        float* __restrict__ vec, float* __restrict__ dist) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  const int64_t j = edge_index[e], i = edge_index[(size_t)n_edges + e];
+  const float* c = cell + (size_t)edge_graph[e] * 9;
+  const float o0 = cell_offsets[3 * (size_t)e], o1 = cell_offsets[3 * (size_t)e + 1], o2 = cell_offsets[3 * (size_t)e + 2];
+  f3 v = sub3(load3(pos, (int)j), load3(pos, (int)i));
+  // offsets = cell_offsets[1x3] . cell[3x3] (bmm), accumulated over the cell rows in order
+  v.x = __fadd_rn(v.x, __fmaf_rn(o2, c[6], __fmaf_rn(o1, c[3], __fmul_rn(o0, c[0]))));
+  v.y = __fadd_rn(v.y, __fmaf_rn(o2, c[7], __fmaf_rn(o1, c[4], __fmul_rn(o0, c[1]))));
+  v.z = __fadd_rn(v.z, __fmaf_rn(o2, c[8], __fmaf_rn(o1, c[5], __fmul_rn(o0, c[2]))));
+  vec[3 * (size_t)e] = v.x; vec[3 * (size_t)e + 1] = v.y; vec[3 * (size_t)e + 2] = v.z;
+  dist[e] = norm3_aten(v);
+}
+
+// scatter_min + argmin over an UNSORTED index (comenet-ocp.py:374-399) as a 64-bit atomicMin of
+// (distance bits << 32 | edge id): distances are positive, so their bit patterns order like the values, and the
+// edge id breaks ties towards the first occurrence exactly like torch_scatter's CPU argmin.
+// pass 0: nearest edges; pass 1: second nearest (the nearest edge of the node, and edge 0 when some node of the batch
+// has no edge -- the reference's `add[argmin0] = cutoff` quirk -- are penalised by +cutoff).
+template <int PASS>
+__global__ void refs_atomic_edges_kernel(const float* __restrict__ dist, const int64_t* __restrict__ edge_index,
+                                         int n_edges, float cutoff, const int32_t* __restrict__ a0_in,
+                                         const int32_t* __restrict__ a0_out, const int32_t* __restrict__ flags,
+                                         unsigned long long* __restrict__ key_in,
+                                         unsigned long long* __restrict__ key_out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  const int j = (int)edge_index[e], i = (int)edge_index[(size_t)n_edges + e];
+  float di = dist[e], dj = di;
+  if (PASS == 1) {
+    if (e == a0_in[i] || (flags[0] && e == 0)) di = __fadd_rn(di, cutoff);
+    if (e == a0_out[j] || (flags[1] && e == 0)) dj = __fadd_rn(dj, cutoff);
+  }
+  atomicMin(key_in + i, ((unsigned long long)__float_as_uint(di) << 32) | (unsigned)e);
+  atomicMin(key_out + j, ((unsigned long long)__float_as_uint(dj) << 32) | (unsigned)e);
+}
+template <int PASS>
+__global__ void refs_atomic_nodes_kernel(const unsigned long long* __restrict__ key_in,
+                                         const unsigned long long* __restrict__ key_out, int n_nodes,
+                                         int32_t* __restrict__ a_in, int32_t* __restrict__ a_out,
+                                         int32_t* __restrict__ flags) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_nodes) return;
+  const unsigned long long ki = key_in[n], ko = key_out[n];
+  const bool ei = ki == ~0ull, eo = ko == ~0ull;
+  a_in[n] = ei ? 0 : (int)(ki & 0xffffffffull);           // argmin >= E -> 0      comenet-ocp.py:375
+  a_out[n] = eo ? 0 : (int)(ko & 0xffffffffull);
+  if (PASS == 0) {
+    if (ei) atomicOr(flags, 1);
+    if (eo) atomicOr(flags + 1, 1);
+  }
 }
 
 // ------------------------------------------------------------------ node linear: y = act?(x W^T + b)
@@ -416,10 +481,46 @@ int dig3d_comenet_geometry(const float* pos, const float* dist, const int32_t* s
                                                                (float)cutoff, a0i, a1i, a0o, a1o, flags);
   DIG3D_LAUNCH_CHECK();
   if (n_edges) {
-    comenet_edge_features_kernel<<<ceil_div(n_edges, 128), 128, 0, st>>>(
+    comenet_edge_features_kernel<false><<<ceil_div(n_edges, 128), 128, 0, st>>>(
         pos, dist, src, dst, a0i, a1i, a0o, a1o, (int)n_edges, 1.0f / (float)cutoff, feature1, feature2, angles);
     DIG3D_LAUNCH_CHECK();
   }
+  return DIG3D_OK;
+}
+
+int dig3d_pbc_edge_vectors(const float* pos, const int64_t* edge_index, const float* cell, const float* cell_offsets,
+                           const int32_t* edge_graph, int64_t n_edges, float* vec, float* dist, void* stream) {
+  DIG3D_REQUIRE(pos && edge_index && cell && cell_offsets && edge_graph && vec && dist, "pbc_edge_vectors: null pointer");
+  if (n_edges == 0) return DIG3D_OK;
+  pbc_edge_vectors_kernel<<<ceil_div(n_edges, 256), 256, 0, (cudaStream_t)stream>>>(
+      pos, edge_index, cell, cell_offsets, edge_graph, (int)n_edges, vec, dist);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_comenet_geometry_edges(const float* vec, const float* dist, const int64_t* edge_index, const int32_t* src,
+                                 const int32_t* dst, int64_t n_nodes, int64_t n_edges, double cutoff,
+                                 int32_t* refs /*[4 * N + 2]*/, unsigned long long* keys /*[2 * N]*/,
+                                 float* feature1, float* feature2, float* angles, void* stream) {
+  DIG3D_REQUIRE(vec && dist && edge_index && src && dst && refs && keys && feature1 && feature2,
+                "comenet_geometry_edges: null pointer");
+  if (n_nodes == 0 || n_edges == 0) return DIG3D_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int32_t* a0i = refs; int32_t* a1i = refs + n_nodes; int32_t* a0o = refs + 2 * n_nodes; int32_t* a1o = refs + 3 * n_nodes;
+  int32_t* flags = refs + 4 * n_nodes;
+  unsigned long long* ki = keys; unsigned long long* ko = keys + n_nodes;
+  const int ge = ceil_div(n_edges, 256), gn = ceil_div(n_nodes, 256);
+  cudaMemsetAsync(flags, 0, 2 * sizeof(int32_t), st);
+  cudaMemsetAsync(keys, 0xff, 2 * n_nodes * sizeof(unsigned long long), st);
+  refs_atomic_edges_kernel<0><<<ge, 256, 0, st>>>(dist, edge_index, (int)n_edges, (float)cutoff, a0i, a0o, flags, ki, ko);
+  refs_atomic_nodes_kernel<0><<<gn, 256, 0, st>>>(ki, ko, (int)n_nodes, a0i, a0o, flags);
+  cudaMemsetAsync(keys, 0xff, 2 * n_nodes * sizeof(unsigned long long), st);
+  refs_atomic_edges_kernel<1><<<ge, 256, 0, st>>>(dist, edge_index, (int)n_edges, (float)cutoff, a0i, a0o, flags, ki, ko);
+  refs_atomic_nodes_kernel<1><<<gn, 256, 0, st>>>(ki, ko, (int)n_nodes, a1i, a1o, flags);
+  DIG3D_LAUNCH_CHECK();
+  comenet_edge_features_kernel<true><<<ceil_div(n_edges, 128), 128, 0, st>>>(
+      vec, dist, src, dst, a0i, a1i, a0o, a1o, (int)n_edges, 1.0f / (float)cutoff, feature1, feature2, angles);
+  DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
 }
 

@@ -260,6 +260,34 @@ __device__ __forceinline__ void h_load_tile(HSmem& s, HCtx& c, const float* __re
     h_store_ku(s, c, row, ku, x);
   }
 }
+// The same load in two halves, so that the global-memory round trip of the FIRST operand tile overlaps the kernel's
+// set-up (barrier init, TMEM allocation, bias / index loads): fetch before the set-up barrier, commit after it.
+// et / t are passed explicitly because the epilogue context does not exist yet.
+template <int KU>
+struct HTileRegs { float4 v[H_M * KU / H_TILE_THREADS][2]; };
+template <int KU>
+__device__ __forceinline__ void h_tile_fetch(HTileRegs<KU>& r, int et, const float* __restrict__ g, size_t ld, int rows) {
+#pragma unroll
+  for (int k = 0; k < H_M * KU / H_TILE_THREADS; ++k) {
+    const int f = et + k * H_TILE_THREADS, row = f / KU, ku = f % KU;
+    if (row < rows) {
+      r.v[k][0] = __ldg(reinterpret_cast<const float4*>(g + (size_t)row * ld + ku * 8));
+      r.v[k][1] = __ldg(reinterpret_cast<const float4*>(g + (size_t)row * ld + ku * 8 + 4));
+    } else {
+      r.v[k][0] = r.v[k][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+template <int KU>
+__device__ __forceinline__ void h_tile_commit(HSmem& s, const HCtx& c, const HTileRegs<KU>& r) {
+#pragma unroll
+  for (int k = 0; k < H_M * KU / H_TILE_THREADS; ++k) {
+    const int f = c.et + k * H_TILE_THREADS, row = f / KU, ku = f % KU;
+    const float4 p0 = r.v[k][0], p1 = r.v[k][1];
+    const float x[8] = {p0.x * H_SA, p0.y * H_SA, p0.z * H_SA, p0.w * H_SA, p1.x * H_SA, p1.y * H_SA, p1.z * H_SA, p1.w * H_SA};
+    h_store_ku(s, c, row, ku, x);
+  }
+}
 // Streaming accumulation of this tile's job: each finished K = 64 chunk is added (round to nearest) into the
 // thread's fp32 registers; NP 16-column pieces starting at column col0.  The global chunk counter advances over the
 // other tile's chunks of the same layer without touching a barrier (they use that tile's own barriers).
@@ -396,6 +424,12 @@ sphere_update_e_b_h16_kernel(const float* __restrict__ m, const float* __restric
   const int tid = threadIdx.x, warp = tid >> 5;
   const int n_tiles = (n_edges + H_M - 1) / H_M, tile0 = blockIdx.x * 2, ntile = min(2, n_tiles - tile0);
   if (tid == 0 && g_h16_trace_on && blockIdx.x == 0) { g_h16_trace[100] = clock64(); g_h16_trace[101] = (long long)global_ns(); }
+  HTileRegs<8> m_regs;                              // the m tile (K = 64) of this thread's tile, in flight during set-up
+  if (warp >= H_CTRL_WARPS) {
+    const int t = (warp - H_CTRL_WARPS) / H_TILE_WARPS, et = tid - H_CTRL_THREADS - t * H_TILE_THREADS;
+    const int e0 = (tile0 + t) * H_M;
+    if (t < ntile) h_tile_fetch<8>(m_regs, et, m + (size_t)e0 * 64, 64, min(H_M, n_edges - e0));
+  }
   h_setup(s);
   for (int i = tid; i < 8 * 128; i += H_THREADS) {
     const float* b = P.g[i / 128].bias;
@@ -443,8 +477,8 @@ sphere_update_e_b_h16_kernel(const float* __restrict__ m, const float* __restric
       }
       tmem_st_wait();
     };
-    // A0 = m tile (K = 64)
-    h_load_tile<8>(s, c, m + (size_t)e0 * 64, 64, rows);
+    // A0 = m tile (K = 64), fetched before the set-up barrier
+    h_tile_commit<8>(s, c, m_regs);
     if (probe && c.t == 0) H_TRACE(106);
     h_epi_done(s, c.t);
     if (probe && c.t == 0) H_TRACE(107);

@@ -170,6 +170,52 @@ def synthetic_molecules(nmol, shape="qm9", seed=0, natoms=None, variable=False, 
     return mols
 
 
+def synthetic_pbc_batch(nsys, natoms=40, cell=(9.0, 9.0, 14.0), cutoff=6.0, max_neighbors=50, seed=0, shuffle_edges=True):
+    """Seeded OC20-IS2RE-like periodic batch for the ComENet-OCP variant (reference comenet-ocp.py:335-365 reads
+    `atomic_numbers, pos, batch, tags, cell, edge_index, cell_offsets, neighbors`): `nsys` slabs of `natoms` atoms in a
+    sheared cell that is periodic in x and y; the edge list holds, per target atom, its `max_neighbors` nearest periodic
+    images within `cutoff` (the role of OCP's preprocessed graphs), in a deliberately shuffled order."""
+    gen = torch.Generator().manual_seed(seed)
+    out = {k: [] for k in ("atomic_numbers", "pos", "tags", "cell", "edge_index", "cell_offsets", "neighbors")}
+    sizes, base = [], 0
+    for _ in range(nsys):
+        n = natoms
+        a, b, c = cell
+        box = torch.tensor([[a, 0.0, 0.0], [0.3 * b, b, 0.0], [0.0, 0.0, c]]) * (0.9 + 0.2 * torch.rand(1, generator=gen))
+        frac = torch.rand(n, 3, generator=gen) * torch.tensor([1.0, 1.0, 0.6])
+        pos = frac @ box
+        shifts = torch.tensor([[i, j, 0] for i in (-1, 0, 1) for j in (-1, 0, 1)], dtype=torch.float32)
+        # image (s, source) seen from target: pos[src] + shifts . box - pos[tgt]
+        d = (pos[None, :, None, :] + (shifts @ box)[None, None, :, :] - pos[:, None, None, :]).norm(dim=-1)   # [tgt, src, 9]
+        d = d.reshape(n, n * 9)
+        ok = (d < cutoff) & (d > 1e-6)
+        dd = torch.where(ok, d, torch.full_like(d, float("inf")))
+        order = torch.argsort(dd, dim=1)[:, :max_neighbors]
+        valid = torch.gather(dd, 1, order) < float("inf")
+        tgt = torch.arange(n)[:, None].expand_as(order)[valid]
+        flat = order[valid]
+        src, sh = flat // 9, flat % 9
+        if shuffle_edges:
+            p = torch.randperm(tgt.numel(), generator=gen)
+            tgt, src, sh = tgt[p], src[p], sh[p]
+        out["edge_index"].append(torch.stack([src, tgt]) + base)
+        out["cell_offsets"].append(shifts[sh])
+        out["neighbors"].append(torch.tensor([tgt.numel()]))
+        out["atomic_numbers"].append(torch.randint(1, 84, (n,), generator=gen))
+        out["tags"].append((frac[:, 2] * 5).long().clamp(max=2))
+        out["pos"].append(pos)
+        out["cell"].append(box[None])
+        sizes.append(n)
+        base += n
+    b = Batch(atomic_numbers=torch.cat(out["atomic_numbers"]), pos=torch.cat(out["pos"]), tags=torch.cat(out["tags"]),
+              cell=torch.cat(out["cell"]), edge_index=torch.cat(out["edge_index"], 1),
+              cell_offsets=torch.cat(out["cell_offsets"]), neighbors=torch.cat(out["neighbors"]))
+    b.batch = torch.repeat_interleave(torch.arange(nsys), torch.tensor(sizes))
+    b.natoms = torch.tensor(sizes)
+    b.num_graphs = nsys
+    return b
+
+
 def synthetic_batch(nmol, shape="qm9", seed=0, **kw):
     return collate(synthetic_molecules(nmol, shape, seed, **kw))
 

@@ -308,6 +308,20 @@ int dig3d_comenet_geometry(const float* pos, const float* dist, const int32_t* s
                            int64_t n_nodes, int64_t n_edges, double cutoff, int32_t* refs, float* feature1,
                            float* feature2, float* angles, void* stream);
 
+/* ComENet-OCP (reference dig/threedgraph/method/comenet/ocp/comenet-ocp.py:343-474): the graph arrives as an arbitrary
+ * edge list with periodic images.  dig3d_pbc_edge_vectors = ocpmodels' get_pbc_distances (distance_vec = pos[row] -
+ * pos[col] + cell_offsets . cell, called at :352-359; edge_graph[e] = graph of edge e).  dig3d_comenet_geometry_edges =
+ * the four scatter_min / argmin over the UNSORTED target / source index (:374-399, 64-bit atomicMin of (distance, edge
+ * id): ties resolve to the first edge like torch_scatter), then theta / phi / tau and the two basis features from the
+ * distance vectors.  src / dst = int32 copies of edge_index[0] / [1]; refs [4 * N + 2] int32 and keys [2 * N] u64 are
+ * workspaces. */
+int dig3d_pbc_edge_vectors(const float* pos, const int64_t* edge_index, const float* cell, const float* cell_offsets,
+                           const int32_t* edge_graph, int64_t n_edges, float* vec, float* dist, void* stream);
+int dig3d_comenet_geometry_edges(const float* vec, const float* dist, const int64_t* edge_index, const int32_t* src,
+                                 const int32_t* dst, int64_t n_nodes, int64_t n_edges, double cutoff, int32_t* refs,
+                                 unsigned long long* keys, float* feature1, float* feature2, float* angles,
+                                 void* stream);
+
 /* x = act(emb(z))   EmbeddingBlock.forward, comenet.py:125-127 */
 int dig3d_comenet_embed(const int64_t* z, const float* emb, int64_t n_nodes, float* x, void* stream);
 

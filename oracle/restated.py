@@ -301,10 +301,11 @@ def schnet_forward(sd, z, pos, batch, *, cutoff=10.0, num_layers=6, num_gaussian
 
 
 # ----------------------------------------------------------------------------- ComENet
-def comenet_geometry(pos, edge_index, num_nodes, cutoff):
+def comenet_geometry(pos, edge_index, num_nodes, cutoff, vecs=None):
     """comenet.py:295-385: nearest / second-nearest reference atoms and the angles theta, phi, tau."""
     j, i = edge_index
-    vecs = pos[j] - pos[i]                                                 # :297
+    if vecs is None:
+        vecs = pos[j] - pos[i]                                             # :297
     dist = vecs.norm(dim=-1)
     n_e = i.numel()
 
@@ -402,6 +403,45 @@ def comenet_forward(sd, z, pos, batch, *, cutoff=8.0, num_layers=4, num_radial=3
         return energy, dict(edge_index=edge_index, dist=dist, theta=theta, phi=phi, tau=tau,
                             feature1=f1, feature2=f2)
     return energy
+
+
+def comenet_ocp_forward(sd, data, *, cutoff=6.0, num_blocks=4, num_radial=3, num_spherical=2, num_output_layers=3):
+    """ComENet._forward of the OCP variant (comenet/ocp/comenet-ocp.py:335-470) with use_pbc=True, otf_graph=False,
+    hetero=False: get_pbc_distances (oracle/ocp_stub.py restates the third-party function), the same reference-atom /
+    angle code as comenet.py on the periodic distance vectors, blocks with middle = hidden width."""
+    from .ocp_stub import get_pbc_distances
+    z, batch = data.atomic_numbers.long(), data.batch
+    n = z.size(0)
+    num_graphs = int(batch.max()) + 1
+    out = get_pbc_distances(data.pos, data.edge_index, data.cell, data.cell_offsets, data.neighbors,
+                            return_distance_vec=True)                     # :352-365
+    edge_index, vecs = out["edge_index"], out["distance_vec"]
+    j, i = edge_index
+    dist, theta, phi, tau = comenet_geometry(None, edge_index, n, cutoff, vecs=vecs)
+    f1, f2 = comenet_features(dist, theta, phi, tau, cutoff, num_spherical, num_radial)
+    x = swish(F.embedding(z, sd["emb.emb.weight"]))
+    for b in range(num_blocks):                                            # :241-266
+        p = f"interaction_blocks.{b}"
+        x = swish(_lin(sd, p + ".lin", x))
+        hs = []
+        for c, feat in ((1, f1), (2, f2)):
+            w = _lin(sd, f"{p}.lin_feature{c}.lin2", _lin(sd, f"{p}.lin_feature{c}.lin1", feat))
+            agg = torch.zeros_like(x).index_add_(0, i, w * x[j])
+            h = _lin(sd, f"{p}.conv{c}.lin_rel", agg) + _lin(sd, f"{p}.conv{c}.lin_root", x)
+            hs.append(swish(_lin(sd, f"{p}.lin{c}", h)))
+        h = _lin(sd, p + ".lin_cat", torch.cat(hs, 1)) + x
+        for l in range(num_output_layers):
+            h = swish(_lin(sd, f"{p}.lins.{l}", h)) + h
+        mean = shim.scatter(h, batch, dim=0, dim_size=num_graphs, reduce="mean")
+        o = h - mean.index_select(0, batch) * sd[p + ".norm.mean_scale"]
+        var = shim.scatter(o.pow(2), batch, dim=0, dim_size=num_graphs, reduce="mean")
+        std = (var + 1e-5).sqrt().index_select(0, batch)
+        h = sd[p + ".norm.weight"] * o / std + sd[p + ".norm.bias"]
+        x = _lin(sd, p + ".final", h)
+    for l in range(num_output_layers):
+        x = swish(_lin(sd, f"lins.{l}", x))
+    x = _lin(sd, "lin_out", x)
+    return shim.scatter(x, batch, dim=0, dim_size=num_graphs)               # :469
 
 
 # ----------------------------------------------------------------------------- ProNet (SURVEY.md 8f rank 1)

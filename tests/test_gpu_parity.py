@@ -625,3 +625,46 @@ def test_gspherenet_private_geometry_bit_exact():
         two = synthetic_batch(1, "qm9", seed=1).to(dev)
         e2 = torch.tensor([[1, 0], [0, 1]], device=dev)
         xyztodat(two.pos[:2].contiguous(), e2, 2, torch.zeros(2, dtype=torch.long, device=dev))
+
+
+def test_comenet_ocp_matches_oracle():
+    """the OCP variant (comenet-ocp.py:335-470) on a shuffled periodic edge list: distance vectors and
+    distances bit-equal to get_pbc_distances on the same GPU, energies and every parameter gradient vs the oracle
+    (which is bit-identical to the unmodified reference on the CPU fixture, tests/test_oracle.py)."""
+    import json
+    import os
+    from oracle import restated
+    from oracle.ocp_stub import get_pbc_distances
+    from dig_b200.data import synthetic_pbc_batch
+    from dig_b200.threedgraph.method.comenet_ocp import ComENet
+    dev = torch.device("cuda:0")
+    with open(os.path.join(os.path.dirname(__file__), "golden", "comenet_ocp_checkpoint_shapes.json")) as fh:
+        pin = json.load(fh)
+    sd = formula_state_dict({k[len("module."):]: torch.empty(s) for k, s in pin["keys"].items()}, seed=21)
+    sd["lin_out.weight"] = sd["lin_out.weight"] + 0.05
+    model = ComENet(0, 0, hidden_channels=256, num_blocks=4, cutoff=6.0, num_radial=3, num_spherical=2)
+    model.load_state_dict({"module." + k: v for k, v in sd.items()})
+    model = model.to(dev)
+    b = synthetic_pbc_batch(3, natoms=30, seed=7).to(dev)
+    ref_geo = get_pbc_distances(b.pos, b.edge_index, b.cell, b.cell_offsets, b.neighbors, return_distance_vec=True)
+    src, dst, row_ptr, f1, f2 = model._geometry(b)
+    assert int(row_ptr[-1]) == ref_geo["edge_index"].size(1)
+    perm = torch.sort(ref_geo["edge_index"][1], stable=True).indices
+    dist, theta, phi, tau = restated.comenet_geometry(None, ref_geo["edge_index"], b.pos.size(0), 6.0,
+                                                      vecs=ref_geo["distance_vec"])
+    f1_ref, f2_ref = restated.comenet_features(dist, theta, phi, tau, 6.0)
+    assert torch.equal(src.long(), ref_geo["edge_index"][0][perm]) and torch.equal(dst.long(), ref_geo["edge_index"][1][perm])
+    assert torch.equal(f1, f1_ref[perm]) and torch.equal(f2, f2_ref[perm])
+    out = model(b)
+    sd_ref = {k: v.to(dev).clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    ref = restated.comenet_ocp_forward(sd_ref, b, cutoff=6.0)
+    assert out.shape == ref.shape == (3, 1)
+    assert rel_err(out.detach().cpu().numpy(), ref.detach().cpu().numpy()) < TOL
+    out.sum().backward()
+    ref.sum().backward()
+    for name, p in model.named_parameters():
+        r = sd_ref[name].grad
+        assert p.grad is not None and r is not None, name
+        assert rel_err(p.grad.cpu().numpy(), r.cpu().numpy()) < 1e-4, name
+    with pytest.raises(NotImplementedError, match="hetero"):
+        ComENet(0, 0, hidden_channels=256, num_blocks=1, num_radial=3, num_spherical=2, hetero=True).to(dev)(b)
