@@ -19,25 +19,43 @@ def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _dense_mode():
+    """DIG3D_TRAIN_DENSE: "h16" (default) = the training linears of the shapes the two-tile tcgen05 engine is compiled
+    for run on it (3xFP16 operands, fp32-level accuracy); "tc" = the first-generation per-linear 3xTF32 kernel;
+    "simt" = exact-fp32 FFMA GEMMs everywhere."""
+    mode = os.environ.get("DIG3D_TRAIN_DENSE", "h16")
+    if mode not in ("h16", "tc", "simt"):
+        raise ValueError(f"DIG3D_TRAIN_DENSE={mode!r}: expected h16, tc or simt")
+    return mode
+
+
 def _use_tc(weight, rows, k, nout):
-    """The exact-fp32 FFMA GEMMs are the default of the training path.  DIG3D_TRAIN_DENSE=tc moves the shapes tcgen05 is
-    compiled for (3xTF32, fp32-accurate) to the tensor cores; measured on the B200 the unfused per-linear kernel gains
-    little (32 vs 44 us for 34.5 k x 128 x 128) and pays a weight re-pack per parameter update, so it is opt-in."""
-    return (os.environ.get("DIG3D_TRAIN_DENSE", "simt") == "tc" and rows >= ops.TC_LINEAR_MIN_ROWS
+    return (_dense_mode() == "tc" and rows >= ops.TC_LINEAR_MIN_ROWS
             and weight.is_contiguous() and ops.linear_tc_supported(k, nout))
+
+
+def _use_h16(weight, rows, k, nout):
+    return (_dense_mode() == "h16" and rows >= ops.H16_LINEAR_MIN_ROWS and weight.is_contiguous()
+            and weight.dim() == 2 and ops.linear_h16_supported(k, nout))
 
 
 def _linear_fwd(x, weight, bias, want_act=False):
     k, nout = weight.size(1), weight.size(0)
     b = None if bias is None else bias.detach()
-    if _use_tc(weight, x.numel() // k, k, nout):
+    rows = x.numel() // k
+    if _use_h16(weight, rows, k, nout):
+        return ops.linear_h16(x, weight, b, want_act=want_act)
+    if _use_tc(weight, rows, k, nout):
         return ops.linear_tc(x, weight, b, want_act=want_act)
     return ops.linear(x, _c(weight.detach()), b, want_act=want_act)
 
 
 def _linear_bwd_input(dy, weight):
     k, nout = weight.size(1), weight.size(0)
-    if _use_tc(weight, dy.numel() // nout, nout, k):
+    rows = dy.numel() // nout
+    if _use_h16(weight, rows, nout, k):
+        return ops.linear_h16(dy, weight, None, transposed=True)
+    if _use_tc(weight, rows, nout, k):
         return ops.linear_tc(dy, weight, None, transposed=True)
     return ops.linear(dy, ops.transpose(_c(weight.detach())), None)
 

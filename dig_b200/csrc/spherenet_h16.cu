@@ -364,6 +364,25 @@ __device__ __forceinline__ void h_store_tile_coalesced(HSmem& s, const HCtx& c, 
   }
 }
 
+// Same with an output leading dimension (the tile is a column slice of a wider row-major matrix).
+template <int W>
+__device__ __forceinline__ void h_store_tile_strided(HSmem& s, const HCtx& c, int col0, const float (&v)[W / 2],
+                                                     float* __restrict__ out, int ld, int rows) {
+  constexpr int LD = W + 1, RPW = 128 / W;
+  float* st = reinterpret_cast<float*>(s.a[c.t][0]);
+#pragma unroll
+  for (int i = 0; i < W / 2; ++i) st[c.row * LD + col0 + i] = v[i];
+  h_tile_bar(c.t);
+  const int w = c.et >> 5, lane = c.et & 31;
+  for (int r0 = w * RPW; r0 < rows; r0 += H_TILE_WARPS * RPW) {
+    const int r = r0 + (RPW == 2 ? (lane >> 4) : 0), c4 = 4 * (RPW == 2 ? (lane & 15) : lane);
+    if (r < rows) {
+      const float* src = st + r * LD + c4;
+      *reinterpret_cast<float4*>(out + (size_t)r * ld + c4) = make_float4(src[0], src[1], src[2], src[3]);
+    }
+  }
+}
+
 // e2 tile (staged as [128][H_LDS] fp32 over the tile's own planes) -> segmented edge -> node sums; the tile's 256
 // threads take one column and one half of the rows each.  Rows are target-sorted: only the first and the last
 // segment of a half can be shared with another half / tile (atomics), interior segments are plain stores.
@@ -389,14 +408,14 @@ __device__ __forceinline__ void h_segment_sums(const HSmem& s, const HCtx& c, in
 
 // ---------------------------------------------------------------------------------- weight packing
 // W [N, K] fp32 (nn.Linear layout) -> K/32 slabs of [hi|lo][4 k-units][N][8 halves], w*64 = hi + lo.
-struct HPackJob { const float* w; unsigned char* out; int N, K; };
+struct HPackJob { const float* w; unsigned char* out; int N, K, trans; };   // trans > 0: the source is stored [K, trans] (a column slice of W^T's source)
 struct HPackJobs { HPackJob job[16]; };
 __global__ void h16_pack_kernel(HPackJobs jobs) {
   const HPackJob jb = jobs.job[blockIdx.y];
   const int total = jb.N * jb.K;
   for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < total; id += gridDim.x * blockDim.x) {
     const int n = id / jb.K, k = id % jb.K;
-    const float x = __ldg(jb.w + id) * H_SW;
+    const float x = __ldg(jb.w + (jb.trans ? (size_t)k * jb.trans + n : (size_t)id)) * H_SW;
     const __half h = __float2half_rn(x);
     const __half l = __float2half_rn(x - __half2float(h));
     const int c = k >> 5, ku = (k & 31) >> 3, kk = k & 7;
@@ -902,6 +921,72 @@ sphere_update_v_h16_kernel(const float* __restrict__ v_in_all, int n_nodes, HVPa
   h_finish(s, nullptr);
 }
 
+// ---------------------------------------------------------------------------------- generic linear (training path)
+// y[rows, ldy-strided N columns] = x[rows, K] W^T + bias (+ act_out = swish(y)) on the two-tile engine: K as NPANEL
+// panels of K4*8 columns whose operand tile is rebuilt between panels (the chunk sums keep accumulating in the
+// epilogue registers), N = 128 or 64 output columns per launch (a wider layer is launched once per 128-column slice).
+struct HLinParams { HGemm g[3]; };
+
+template <int NPANEL, int KU, int N>
+__global__ void __launch_bounds__(H_THREADS, 1)
+linear_h16_kernel(const float* __restrict__ x, int n_rows, int ldx, HLinParams P, const float* __restrict__ bias,
+                  float* __restrict__ y, float* __restrict__ act_out, int ldy) {
+  extern __shared__ __align__(1024) unsigned char h_raw[];
+  HSmem& s = *reinterpret_cast<HSmem*>(h_raw);
+  constexpr int NC = N / 2;                                // columns per epilogue thread
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int n_tiles = (n_rows + H_M - 1) / H_M, tile0 = blockIdx.x * 2, ntile = min(2, n_tiles - tile0);
+  h_setup(s);
+  for (int i = tid; i < N; i += H_THREADS) s.bias[0][i] = bias ? __ldg(bias + i) : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  HCtx c;
+  bool epi = false;
+  if (warp < H_CTRL_WARPS) {
+    h_regs_ctrl();
+    if (tid == 0) h_producer_n(s, P.g, NPANEL, ntile);
+    else if (tid == 32) h_mma_n<false, false>(s, P.g, NPANEL, ntile, s.tmem_base);
+  } else if (h_regs_epi(), (c = h_ctx(s, ntile)).t < ntile) {
+    epi = true;
+    const int r0 = (tile0 + c.t) * H_M, rows = min(H_M, n_rows - r0);
+    const int col0 = c.half * NC;
+    float acc[NC];
+#pragma unroll
+    for (int p = 0; p < NPANEL; ++p) {
+      h_load_tile<KU>(s, c, x + (size_t)r0 * ldx + p * (KU * 8), ldx, rows);
+      h_epi_done(s, c.t);
+      if (p == 0) h_drain<NC / 16, true>(s, c, col0, KU / 8, acc);
+      else h_drain<NC / 16, false>(s, c, col0, KU / 8, acc);
+    }
+#pragma unroll
+    for (int i = 0; i < NC; ++i) acc[i] = fmaf(acc[i], H_INV, s.bias[0][col0 + i]);
+    h_store_tile_strided<N>(s, c, col0, acc, y + (size_t)r0 * ldy, ldy, rows);
+    if (act_out) {
+#pragma unroll
+      for (int i = 0; i < NC; ++i) acc[i] = hswish<false>(acc[i]);
+      h_tile_bar(c.t);
+      h_store_tile_strided<N>(s, c, col0, acc, act_out + (size_t)r0 * ldy, ldy, rows);
+    }
+  }
+  h_finish(s, epi ? &c : nullptr);
+}
+
+static int h_smem_attr(const void* fn);
+template <int NPANEL, int KU, int N>
+static int launch_linear_h16(const float* x, int64_t rows, int ldx, const unsigned char* packed, const float* bias,
+                             float* y, float* act_out, int ldy, cudaStream_t st) {
+  HLinParams P;
+  const size_t panel = (size_t)(KU / 4) * 2 * 4 * N * 16;      // KU/4 slabs of [hi|lo][4][N][8 halves]
+  for (int p = 0; p < NPANEL; ++p) P.g[p] = {packed + p * panel, nullptr, KU * 8, N};
+  auto kfn = linear_h16_kernel<NPANEL, KU, N>;
+  int rc = h_smem_attr((const void*)kfn);
+  if (rc) return rc;
+  const int pairs = ceil_div(ceil_div(rows, H_M), 2);
+  kfn<<<pairs, H_THREADS, sizeof(HSmem), st>>>(x, (int)rows, ldx, P, bias, y, act_out, ldy);
+  return DIG3D_OK;
+}
+
 static int h_smem_attr(const void* fn) {
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HSmem));
   if (e != cudaSuccess) {
@@ -919,21 +1004,32 @@ extern "C" {
 
 int64_t dig3d_h16_packed_bytes(int32_t n, int32_t k) { return (int64_t)4 * n * k; }
 
-int dig3d_h16_pack(const float* const* weights, const int32_t* n, const int32_t* k, void* const* outs, int32_t count,
-                   void* stream) {
+static int h16_pack_impl(const float* const* weights, const int32_t* n, const int32_t* k, const int32_t* trans,
+                         void* const* outs, int32_t count, void* stream) {
   DIG3D_REQUIRE(weights && n && k && outs && count >= 1 && count <= 16, "h16_pack: bad arguments");
   HPackJobs jobs;
   int max_total = 0;
   for (int i = 0; i < count; ++i) {
     DIG3D_REQUIRE(weights[i] && outs[i] && k[i] % 64 == 0 && n[i] % 8 == 0 && n[i] <= 128,
                   "h16_pack: matrix %d has N=%d K=%d (need K %% 64 == 0, N %% 8 == 0, N <= 128)", i, n[i], k[i]);
-    jobs.job[i] = {weights[i], (unsigned char*)outs[i], n[i], k[i]};
+    jobs.job[i] = {weights[i], (unsigned char*)outs[i], n[i], k[i], trans ? trans[i] : 0};
     max_total = max_total > n[i] * k[i] ? max_total : n[i] * k[i];
   }
   dim3 grid(ceil_div(max_total, 256), count);
   h16_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(jobs);
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
+}
+
+int dig3d_h16_pack(const float* const* weights, const int32_t* n, const int32_t* k, void* const* outs, int32_t count,
+                   void* stream) {
+  return h16_pack_impl(weights, n, k, nullptr, outs, count, stream);
+}
+
+int dig3d_h16_pack_t(const float* const* weights, const int32_t* n, const int32_t* k, const int32_t* trans,
+                     void* const* outs, int32_t count, void* stream) {
+  DIG3D_REQUIRE(trans, "h16_pack_t: null pointer");
+  return h16_pack_impl(weights, n, k, trans, outs, count, stream);
 }
 
 int dig3d_h16_set_fast_swish(int32_t on) {
@@ -1018,6 +1114,41 @@ int dig3d_sphere_update_e_b_h16(const float* m, const float* e1_in, const float*
   const int pairs = ceil_div(ceil_div(n_edges, H_M), 2);
   kfn<<<pairs, H_THREADS, sizeof(HSmem), (cudaStream_t)stream>>>(m, x_ji, e1_in, rbf0, dst, (int)n_edges, P, e1_out,
                                                                  v_in);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_linear_h16_supported(int32_t k, int32_t nout) {
+  return ((k == 64 || k == 128 || k == 256 || k == 384) && nout >= 64 && nout % 64 == 0 && nout <= 512) ? 1 : 0;
+}
+
+/* y = x W^T + bias (+ act_out = swish(y)); packed = dig3d_h16_pack(_t) of W as consecutive [min(128, N - c), K] row
+ * slices (one per 128 output columns; a trailing 64-column slice is allowed). */
+int dig3d_linear_h16(const float* x, int64_t rows, int32_t k, int32_t nout, const void* packed, const float* bias,
+                     float* y, float* act_out, void* stream) {
+  DIG3D_REQUIRE(x && packed && y, "linear_h16: null pointer");
+  DIG3D_REQUIRE(dig3d_linear_h16_supported(k, nout), "linear_h16: shape %d -> %d is not compiled", k, nout);
+  DIG3D_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)act_out) & 15) == 0, "linear_h16: 16-byte alignment");
+  if (rows == 0) return DIG3D_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned char* pw = (const unsigned char*)packed;
+  for (int c0 = 0; c0 < nout; c0 += 128) {
+    const int n = nout - c0 >= 128 ? 128 : 64;
+    const float* b = bias ? bias + c0 : nullptr;
+    float* yo = y + c0;
+    float* ao = act_out ? act_out + c0 : nullptr;
+    int rc;
+#define DIG3D_LIN(NP, KU)                                                                                             \
+    (n == 128 ? launch_linear_h16<NP, KU, 128>(x, rows, k, pw, b, yo, ao, nout, st)                                    \
+              : launch_linear_h16<NP, KU, 64>(x, rows, k, pw, b, yo, ao, nout, st))
+    if (k == 64) rc = DIG3D_LIN(1, 8);
+    else if (k == 128) rc = DIG3D_LIN(1, 16);
+    else if (k == 256) rc = DIG3D_LIN(2, 16);
+    else rc = DIG3D_LIN(3, 16);
+#undef DIG3D_LIN
+    if (rc) return rc;
+    pw += (size_t)4 * n * k;
+  }
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
 }

@@ -934,6 +934,102 @@ def linear_tc(x, weight, bias=None, transposed=False, want_act=False):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# training-path linears on the two-tile tensor engine (3xFP16 operands, csrc/spherenet_h16.cu)
+H16_LINEAR_MIN_ROWS = 1024
+_H16_REGISTRY = {}          # id(weight) -> [weakref, {transposed: (tag, buffer)}]
+
+
+def linear_h16_supported(k, nout):
+    return bool(_lib.load().dig3d_linear_h16_supported(int(k), int(nout)))
+
+
+def _h16_tag(weight):
+    return (_PACK_GENERATION[0], weight._version, weight.data_ptr(), tuple(weight.shape))
+
+
+def _h16_slices(weight, transposed):
+    """(source pointer offset in elements, N, K, trans) of the <= 128-row output slices of W (or W^T)."""
+    n_out, k = (weight.size(1), weight.size(0)) if transposed else (weight.size(0), weight.size(1))
+    out = []
+    for c0 in range(0, n_out, 128):
+        n = 128 if n_out - c0 >= 128 else 64
+        # W [n_out, k] row-major: slice rows c0..c0+n (offset c0*k); W^T from W [k, n_out]: column slice (offset c0)
+        out.append((c0 if transposed else c0 * k, n, k, n_out if transposed else 0))     # trans = source row stride
+    return out
+
+
+def _h16_pack_jobs(jobs):
+    """jobs: (weight, transposed, buffer).  Packs every output slice, 16 slices per launch."""
+    flat = []
+    for w, tr, buf in jobs:
+        off = 0
+        for src_off, n, k, trans in _h16_slices(w, tr):
+            flat.append((w.data_ptr() + 4 * src_off, n, k, trans, buf.data_ptr() + off))
+            off += 4 * n * k
+    for first in range(0, len(flat), 16):
+        chunk = flat[first:first + 16]
+        m = len(chunk)
+        wp = (ctypes.c_void_p * m)(*[c[0] for c in chunk])
+        ns = (ctypes.c_int32 * m)(*[c[1] for c in chunk])
+        ks = (ctypes.c_int32 * m)(*[c[2] for c in chunk])
+        ts = (ctypes.c_int32 * m)(*[c[3] for c in chunk])
+        op = (ctypes.c_void_p * m)(*[c[4] for c in chunk])
+        call("dig3d_h16_pack_t", wp, ns, ks, ts, op, m, _stream())
+
+
+def _h16_packed(weight, transposed):
+    """Packed 3xFP16 copy of W (or W^T) for dig3d_linear_h16, owned by a registry entry that dies with the tensor;
+    repacked when the tensor changed (version / generation)."""
+    import weakref
+    ent = _H16_REGISTRY.get(id(weight))
+    if ent is None or ent[0]() is not weight:
+        ent = [weakref.ref(weight, lambda _r, key=id(weight): _H16_REGISTRY.pop(key, None)), {}]
+        _H16_REGISTRY[id(weight)] = ent
+    tag = _h16_tag(weight)
+    hit = ent[1].get(bool(transposed))
+    if hit is not None and hit[0] == tag:
+        return hit[1]
+    buf = hit[1] if hit is not None else torch.empty(4 * weight.numel(), dtype=torch.uint8, device=weight.device)
+    _h16_pack_jobs([(weight.detach(), transposed, buf)])
+    ent[1][bool(transposed)] = (tag, buf)
+    return buf
+
+
+def repack_h16_all():
+    """Re-pack every registered weight (both orientations in use) in a few batched launches: called by the optimizer
+    right after it changed the parameters, so the next step's linears find current copies."""
+    jobs, entries = [], []
+    for key, ent in list(_H16_REGISTRY.items()):
+        w = ent[0]()
+        if w is None:
+            _H16_REGISTRY.pop(key, None)
+            continue
+        for tr, (tag, buf) in ent[1].items():
+            new = _h16_tag(w)
+            if tag != new:
+                jobs.append((w.detach(), tr, buf))
+                entries.append((ent, tr, new, buf))
+    if jobs:
+        _h16_pack_jobs(jobs)
+        for ent, tr, new, buf in entries:
+            ent[1][tr] = (new, buf)
+
+
+def linear_h16(x, weight, bias=None, transposed=False, want_act=False):
+    """y = x W^T + b (transposed=False) or y = x W (transposed=True: the input-gradient GEMM) on the two-tile tcgen05
+    engine, 3xFP16 operands (fp32-level accuracy, |x| < 8190); want_act: also return swish(y)."""
+    k = x.size(-1)
+    nout = weight.size(1) if transposed else weight.size(0)
+    rows = x.numel() // k
+    packed = _h16_packed(weight, transposed)
+    y = torch.empty(x.shape[:-1] + (nout,), device=x.device, dtype=F32)
+    act_out = torch.empty_like(y) if want_act else None
+    call("dig3d_linear_h16", _p(x, F32, "x", 16), rows, k, nout, _p(packed), _p(bias, F32, "bias"), _p(y, align=16),
+         _p(act_out, align=16), _stream())
+    return (y, act_out) if want_act else y
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # second order (force training, SchNet)
 def act_bwd2(x, dy, g, mode):
     out = torch.empty_like(x)

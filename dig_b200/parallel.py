@@ -284,6 +284,7 @@ class FlatAdam(torch.optim.Optimizer):
         for st in self.state.values():
             st["step"].fill_(float(self.steps))
         ops.invalidate_packed()            # the weights changed behind tensor._version
+        ops.repack_h16_all()               # ... and the training linears get fresh packed copies in a few launches
         return loss
 
     def load_state_dict(self, state_dict):

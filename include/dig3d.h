@@ -268,6 +268,14 @@ int dig3d_sphere_update_v_h16_supported(int32_t hidden, int32_t out_emb, int32_t
 int dig3d_sphere_update_v_h16(const float* v_in_all, int64_t n_nodes, int32_t n_blocks, int32_t out_channels,
                               int32_t n_lins, const void* const* packed, const dig3d_update_v_weights* w,
                               float* v_out_all, void* stream);
+/* Training-path linears on the same engine: y[rows, nout] = x[rows, k] W^T + bias, optionally also swish(y);
+ * dig3d_h16_pack_t: trans[i] = 0 packs weights[i] as a row-major [n, k] matrix; trans[i] = ld > 0 packs the TRANSPOSE of
+ * a [k, n] block whose rows are ld floats apart (a column slice of W for the input-gradient GEMM dX = dY W). */
+int dig3d_h16_pack_t(const float* const* weights, const int32_t* n, const int32_t* k, const int32_t* trans,
+                     void* const* outs, int32_t count, void* stream);
+int dig3d_linear_h16_supported(int32_t k, int32_t nout);
+int dig3d_linear_h16(const float* x, int64_t rows, int32_t k, int32_t nout, const void* packed, const float* bias,
+                     float* y, float* act_out, void* stream);
 /* 1 if an operand left the fp16 range since the flag was last cleared (synchronises the device). */
 int dig3d_h16_overflow(int32_t clear);
 int dig3d_h16_timeouts(void);

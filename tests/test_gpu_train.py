@@ -637,3 +637,28 @@ def test_config5_global_batch_1024_shards_reproduce_the_single_batch():
         b = collate(mols[:256]).to(dev)
         ref = restated.spherenet_forward({k: v.to(dev) for k, v in sd.items()}, b.z, b.pos, b.batch)
     assert rel_err(full[:256].cpu().numpy(), ref.cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("k,nout", [(128, 128), (64, 128), (128, 64), (256, 256), (384, 128), (128, 256), (256, 64)])
+def test_linear_on_the_two_tile_engine_matches_fp64(k, nout):
+    """dig3d_linear_h16 (3xFP16 operands on tcgen05): y = x W^T + b, its fused swish output and the input-gradient GEMM
+    (packed W^T, column slices) vs fp64, ragged row count, odd tile count."""
+    from dig_b200 import ops
+    dev = torch.device("cuda:0")
+    torch.manual_seed(k * 7 + nout)
+    for rows in (1300, 129):
+        x = torch.randn(rows, k, device=dev)
+        w = torch.nn.Parameter(torch.randn(nout, k, device=dev) / k ** 0.5)
+        b = torch.randn(nout, device=dev)
+        y, a = ops.linear_h16(x, w, b, want_act=True)
+        ref = x.double() @ w.double().t() + b.double()
+        assert rel_err(y.cpu().numpy(), ref.cpu().numpy()) < 2e-6
+        assert rel_err(a.cpu().numpy(), (ref * torch.sigmoid(ref)).cpu().numpy()) < 2e-6
+        dy = torch.randn(rows, nout, device=dev)
+        dx = ops.linear_h16(dy, w, None, transposed=True)
+        assert rel_err(dx.cpu().numpy(), (dy.double() @ w.double()).cpu().numpy()) < 2e-6
+        with torch.no_grad():
+            w.mul_(0.5)                                  # a parameter update must be seen (version-keyed cache)
+        y2 = ops.linear_h16(x, w, b)
+        assert rel_err(y2.cpu().numpy(), (x.double() @ w.double().t() + b.double()).cpu().numpy()) < 2e-6
+    assert ops.tc_timeouts() == 0 and not ops.h16_overflow()
