@@ -70,6 +70,8 @@ SIGNATURES = {
     "dig3d_triplet_basis": [P, P, P, P, c_int64, c_int32, P, P, P],
     "dig3d_triplet_basis_project": [P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int32, c_int32,
                                     c_int32, P, P, P, P, P],
+    "dig3d_triplet_basis_project_node": [P, P, P, P, P, P, P, P, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32,
+                                         P, P, P, P, P],
     "dig3d_segment_sum": [P, P, c_int64, c_int64, P, P],
     "dig3d_sphere_init_e": [P, P, P, P, c_int64, POINTER(InitEWeights), P, P, P],
     "dig3d_sphere_update_e_a": [P, P, c_int64, POINTER(UpdateEWeights), P, P, P],

@@ -20,10 +20,12 @@ def _c(t):
 
 
 def _dense_mode():
-    """DIG3D_TRAIN_DENSE: "h16" (default) = the training linears of the shapes the two-tile tcgen05 engine is compiled
-    for run on it (3xFP16 operands, fp32-level accuracy); "tc" = the first-generation per-linear 3xTF32 kernel;
-    "simt" = exact-fp32 FFMA GEMMs everywhere."""
-    mode = os.environ.get("DIG3D_TRAIN_DENSE", "h16")
+    """DIG3D_TRAIN_DENSE: "simt" (default) = exact-fp32 FFMA GEMMs everywhere; "h16" = the training linears of the
+    shapes the two-tile tcgen05 engine is compiled for run on it (3xFP16 operands: 23 vs 44 us per 34 k x 128 x 128
+    linear on the B200, but ~50 unfused linears in a row put the SphereNet energy 1.1e-5 from the oracle -- just
+    outside the 1e-5 bar -- and the training step is host-bound at ~400 launches, so it is opt-in until the chain is
+    fused); "tc" = the first-generation per-linear 3xTF32 kernel."""
+    mode = os.environ.get("DIG3D_TRAIN_DENSE", "simt")
     if mode not in ("h16", "tc", "simt"):
         raise ValueError(f"DIG3D_TRAIN_DENSE={mode!r}: expected h16, tc or simt")
     return mode

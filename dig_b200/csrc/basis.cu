@@ -278,6 +278,161 @@ triplet_basis_project_kernel(const float* __restrict__ bess, const float* __rest
   }
 }
 
+// ------------------------------------------------------------------ fused projection, node-centred (round 2)
+// Same outputs as triplet_basis_project_kernel, organised around the MIDDLE node j of the triplets (k -> j -> i): all
+// in-edges (k -> j) of j meet the same out-edges (j -> i), so a CTA owns one node at a time and
+//   * discovers the out-edges of j ONCE (the edge-centred kernel repeats the binary searches for every in-edge),
+//   * evaluates the harmonics of up to PN_TRIP triplets with ALL 256 threads (one triplet per thread; with one warp
+//     per (k -> j) edge only ~14 of 32 lanes had a triplet at QM9 sizes, and the ~1200 instructions of the 49 + 7
+//     closed forms are half of this kernel's work),
+//   * then contracts with lane = output column q exactly like the edge-centred kernel (same FMA order: the results
+//     are bit-identical).
+constexpr int PN_THREADS = 256;
+constexpr int PN_TRIP = 256;     // triplets whose harmonics are staged per pass
+constexpr int PN_MAXIN = 64;     // in-degree bound (cap + 1 <= 64)
+constexpr int PN_OUT = 256;      // out-edges handled per sweep over the molecule
+
+template <class BS, bool TORSION>
+struct PrjNodeSmem {
+  static constexpr int NYT = TORSION ? BS::NY : 1;
+  float wt[TORSION ? BS::NY * BS::NR * PRJ_LD : 1];
+  float ws[BS::NB * PRJ_LD];
+  float bess[PN_THREADS / 32][BS::NB];
+  static constexpr int YLD = ((NYT + BS::NS + 3) / 4) * 4;
+  alignas(16) float y[PN_TRIP][YLD];
+  int32_t trip[PN_TRIP];
+  int32_t in_src[PN_MAXIN];
+  int32_t out_e[PN_OUT], out_pos[PN_OUT];
+  int32_t n_out;
+};
+
+template <class BS, bool TORSION>
+__global__ void __launch_bounds__(PN_THREADS)
+triplet_basis_project_node_kernel(const float* __restrict__ bess, const float* __restrict__ angle,
+                                  const float* __restrict__ torsion, const int32_t* __restrict__ src,
+                                  const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ trip_ptr,
+                                  const int32_t* __restrict__ graph_ptr, const int64_t* __restrict__ batch,
+                                  int n_nodes, int n_triplets, const float* __restrict__ w_sbf1,
+                                  const float* __restrict__ w_t1, float* __restrict__ sbf_p, float* __restrict__ t_p) {
+  constexpr int NS = BS::NS, NR = BS::NR, NB = BS::NB, NY = BS::NY;
+  constexpr int NYT = TORSION ? NY : 1;
+  using SM = PrjNodeSmem<BS, TORSION>;
+  extern __shared__ __align__(16) unsigned char prj_smem_raw[];
+  SM& sm = *reinterpret_cast<SM*>(prj_smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (TORSION)
+    for (int id = tid; id < 32 * NY * NR; id += PN_THREADS)
+      sm.wt[(id % (NY * NR)) * PRJ_LD + id / (NY * NR)] = __ldg(w_t1 + id);
+  for (int id = tid; id < 32 * NB; id += PN_THREADS) sm.ws[(id % NB) * PRJ_LD + id / NB] = __ldg(w_sbf1 + id);
+  for (int j = blockIdx.x; j < n_nodes; j += gridDim.x) {
+    const int base = row_ptr[j], d = row_ptr[j + 1] - base;
+    if (d == 0) continue;                      // no in-edge, no triplet through j          (uniform over the CTA)
+    const int g = (int)batch[j], lo = graph_ptr[g], hi = graph_ptr[g + 1];
+    __syncthreads();                           // previous node fully consumed; weight tables staged
+    for (int s = tid; s < d; s += PN_THREADS) sm.in_src[s] = src[base + s];
+    for (int c0 = lo; c0 < hi; c0 += PN_OUT) {
+      if (tid == 0) sm.n_out = 0;
+      __syncthreads();
+      // out-edges (j -> i), i in [c0, c0 + PN_OUT): edge id and the position of i among j's in-neighbours (d: absent)
+      {
+        const int i = c0 + tid;
+        if (i < hi && i != j) {
+          const int ib = row_ptr[i], di = row_ptr[i + 1] - ib;
+          int a = 0, b = di;
+          while (a < b) { const int mid = (a + b) >> 1; if (src[ib + mid] < j) a = mid + 1; else b = mid; }
+          if (a < di && src[ib + a] == j) {
+            int pa = 0, pb = d;
+            while (pa < pb) { const int mid = (pa + pb) >> 1; if (sm.in_src[mid] < i) pa = mid + 1; else pb = mid; }
+            const int slot = atomicAdd(&sm.n_out, 1);
+            sm.out_e[slot] = ib + a;
+            sm.out_pos[slot] = (pa < d && sm.in_src[pa] == i) ? pa : d;
+          }
+        }
+      }
+      __syncthreads();
+      const int o = sm.n_out;
+      if (o == 0) continue;                    // uniform
+      const int grp = max(1, PN_TRIP / o);     // in-edges per pass (o <= PN_OUT = PN_TRIP, so grp * o <= PN_TRIP)
+      for (int s0 = 0; s0 < d; s0 += grp) {
+        const int ng = min(grp, d - s0);
+        // harmonics of the (in-edge s, out-edge u) pairs of this pass, one triplet per thread
+        for (int p = tid; p < ng * o; p += PN_THREADS) {
+          const int s = s0 + p / o, u = p % o;
+          const int pos_i = sm.out_pos[u];
+          int t = -1;
+          if (pos_i != s) {                    // k == i is not a triplet
+            t = trip_ptr[sm.out_e[u]] + s - ((pos_i < s) ? 1 : 0);
+            const float th = angle[t];
+            float y0[NS];
+            BS::yl0(th, y0);
+#pragma unroll
+            for (int l = 0; l < NS; ++l) sm.y[p][NYT + l] = y0[l];
+            if (TORSION) {
+              float y[NY];
+              BS::ylm(th, torsion[t], y);
+#pragma unroll
+              for (int ab = 0; ab < NY; ++ab) sm.y[p][ab] = y[ab];
+            }
+          }
+          sm.trip[p] = t;
+        }
+        __syncthreads();
+        // contraction: one warp per in-edge, lane = output column q
+        for (int sg = w; sg < ng; sg += PN_THREADS / 32) {
+          const int kj = base + s0 + sg;
+          __syncwarp();
+          for (int c = lane; c < NB; c += 32) sm.bess[w][c] = __ldg(bess + (size_t)kj * NB + c);
+          __syncwarp();
+          float R[NYT], Rs[NS];
+#pragma unroll
+          for (int b = 0; b < NS; ++b) {
+            float rb[NR];
+#pragma unroll
+            for (int r = 0; r < NR; ++r) rb[r] = sm.bess[w][b * NR + r];
+            float acc = 0.f;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) acc = fmaf(rb[r], sm.ws[(b * NR + r) * PRJ_LD + lane], acc);
+            Rs[b] = acc;
+            if (TORSION) {
+#pragma unroll
+              for (int a = 0; a < NS; ++a) {
+                const int ab = a * NS + b;
+                float acc_t = 0.f;
+#pragma unroll
+                for (int r = 0; r < NR; ++r) acc_t = fmaf(rb[r], sm.wt[(ab * NR + r) * PRJ_LD + lane], acc_t);
+                R[ab] = acc_t;
+              }
+            }
+          }
+          for (int u = 0; u < o; ++u) {
+            const int p = sg * o + u;
+            const int tt = sm.trip[p];
+            if (tt < 0) continue;
+            float yv[SM::YLD];
+#pragma unroll
+            for (int i = 0; i < SM::YLD; i += 4) {
+              const float4 q = *reinterpret_cast<const float4*>(&sm.y[p][i]);
+              yv[i] = q.x; yv[i + 1] = q.y; yv[i + 2] = q.z; yv[i + 3] = q.w;
+            }
+            float acc_s = 0.f;
+#pragma unroll
+            for (int l = 0; l < NS; ++l) acc_s = fmaf(yv[NYT + l], Rs[l], acc_s);
+            const size_t oo = ((size_t)(lane >> 3) * n_triplets + tt) * 8 + (lane & 7);
+            sbf_p[oo] = acc_s;
+            if (TORSION) {
+              float acc_t = 0.f;
+#pragma unroll
+              for (int ab = 0; ab < NY; ++ab) acc_t = fmaf(yv[ab], R[ab], acc_t);
+              t_p[oo] = acc_t;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ backward of the fused projection (training path)
 // d(loss)/d(lin_sbf1.weight), d(loss)/d(lin_t1.weight) of up to four layers from d sbf_p[l][T, 8] / d t_p[l][T, 8]:
 //   dW_t1[q][(a*ns+b)*nr + r] = sum_kj ( sum_{t uses kj} d t_p[q][t] * Y_ab(t) ) * bess[kj][b*nr + r]      (q = layer*8 + row)
@@ -741,6 +896,48 @@ int dig3d_triplet_basis_project(const float* bess, const float* angle, const flo
   }
 #undef DIG3D_PRJ_ONE
 #undef DIG3D_PRJ
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_triplet_basis_project_node(const float* bess, const float* angle, const float* torsion, const int32_t* src,
+                                     const int32_t* row_ptr, const int32_t* trip_ptr, const int32_t* graph_ptr,
+                                     const int64_t* batch, int64_t n_nodes, int64_t n_triplets, int32_t cap,
+                                     int32_t basis_id, int32_t n_layers, int32_t basis_emb, const float* w_sbf1,
+                                     const float* w_t1, float* sbf_p, float* t_p, void* stream) {
+  DIG3D_REQUIRE(bess && angle && src && row_ptr && trip_ptr && graph_ptr && batch && w_sbf1 && sbf_p,
+                "triplet_basis_project_node: null pointer");
+  DIG3D_REQUIRE(n_layers * basis_emb == 32, "triplet_basis_project_node: n_layers*basis_emb must be 32, got %d*%d",
+                n_layers, basis_emb);
+  DIG3D_REQUIRE(cap >= 1 && cap <= PN_MAXIN, "triplet_basis_project_node: cap=%d outside [1,%d]", cap, PN_MAXIN);
+  const bool tors = (t_p != nullptr);
+  DIG3D_REQUIRE(!tors || (torsion && w_t1), "triplet_basis_project_node: torsion path needs torsion and w_t1");
+  if (n_nodes == 0 || n_triplets == 0) return DIG3D_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = (int)(n_nodes < 2 * n_sm ? n_nodes : 2 * n_sm);
+#define DIG3D_PRJN_ONE(BS, TORS)                                                                            \
+  {                                                                                                         \
+    auto kfn = triplet_basis_project_node_kernel<BS, TORS>;                                                 \
+    const size_t smem = sizeof(PrjNodeSmem<BS, TORS>);                                                      \
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { \
+      set_error("triplet_basis_project_node: cannot reserve %zu bytes of shared memory", smem);             \
+      return DIG3D_ECUDA;                                                                                   \
+    }                                                                                                       \
+    kfn<<<grid, PN_THREADS, smem, st>>>(bess, angle, torsion, src, row_ptr, trip_ptr, graph_ptr, batch,     \
+                                        (int)n_nodes, (int)n_triplets, w_sbf1, w_t1, sbf_p, t_p);           \
+  }
+#define DIG3D_PRJN(BS) \
+  if (tors) DIG3D_PRJN_ONE(BS, true) else DIG3D_PRJN_ONE(BS, false)
+  switch (basis_id) {
+    case 0: DIG3D_PRJN(B76); break;
+    case 1: DIG3D_PRJN(B36); break;
+    default: set_error("triplet_basis_project_node: unsupported basis_id %d", basis_id); return DIG3D_EUNSUPPORTED;
+  }
+#undef DIG3D_PRJN_ONE
+#undef DIG3D_PRJN
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
 }

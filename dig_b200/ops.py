@@ -157,6 +157,9 @@ def triplet_basis(bess, angle, torsion, idx_kj, basis_id, ns, nr, want_tbf):
     return sbf, tbf
 
 
+PROJECT_MODE = ["node"]      # "node" (one CTA per middle node of the triplets) | "edge" (one warp per (k -> j) edge)
+
+
 def triplet_basis_project(g, bess, basis_id, w_sbf1_rows, w_t1_rows):
     """w_sbf1_rows: [32, ns*nr], w_t1_rows: [32, ns*ns*nr] or None.
     Returns sbf_p [4, T, 8], t_p [4, T, 8] | None (layer-major: layer l's rows are contiguous)."""
@@ -166,7 +169,14 @@ def triplet_basis_project(g, bess, basis_id, w_sbf1_rows, w_t1_rows):
     t_p = torch.empty(4, max(t, 1), 8, dtype=torch.float32, device=dev) if w_t1_rows is not None else None
     if t == 0:
         return sbf_p[:, :0], (t_p[:, :0] if t_p is not None else None)
-    if t and g.n_edges:
+    if t and g.n_edges and PROJECT_MODE[0] == "node":
+        call("dig3d_triplet_basis_project_node", _p(bess, torch.float32), _p(g.angle),
+             _p(g.torsion) if w_t1_rows is not None else None, _p(g.src), _p(g.row_ptr), _p(g.trip_ptr),
+             _p(g.graph_ptr), _p(g.batch, torch.int64), g.n_nodes, t, g.cap, int(basis_id), 4, 8,
+             _p(w_sbf1_rows, torch.float32, "w_sbf1"),
+             _p(w_t1_rows, torch.float32, "w_t1") if w_t1_rows is not None else None,
+             _p(sbf_p), _p(t_p) if t_p is not None else None, _stream())
+    elif t and g.n_edges:
         call("dig3d_triplet_basis_project", _p(bess, torch.float32), _p(g.angle),
              _p(g.torsion) if w_t1_rows is not None else None, _p(g.src), _p(g.dst), _p(g.row_ptr),
              _p(g.trip_ptr), _p(g.graph_ptr), _p(g.batch, torch.int64), g.n_edges, t, int(basis_id), 4, 8,
@@ -977,42 +987,74 @@ def _h16_pack_jobs(jobs):
         call("dig3d_h16_pack_t", wp, ns, ks, ts, op, m, _stream())
 
 
+_H16_BATCHES = {"stamp": -1, "calls": []}      # cached ctypes argument arrays of repack_h16_all (rebuilt when the registry changes)
+_H16_STAMP = [0]                                # bumps whenever an entry is added to / dropped from the registry
+
+
 def _h16_packed(weight, transposed):
     """Packed 3xFP16 copy of W (or W^T) for dig3d_linear_h16, owned by a registry entry that dies with the tensor;
     repacked when the tensor changed (version / generation)."""
     import weakref
     ent = _H16_REGISTRY.get(id(weight))
     if ent is None or ent[0]() is not weight:
-        ent = [weakref.ref(weight, lambda _r, key=id(weight): _H16_REGISTRY.pop(key, None)), {}]
+        def drop(_r, key=id(weight)):
+            _H16_REGISTRY.pop(key, None)
+            _H16_STAMP[0] += 1
+        ent = [weakref.ref(weight, drop), {}]
         _H16_REGISTRY[id(weight)] = ent
+    tr = bool(transposed)
+    hit = ent[1].get(tr)
+    if hit is not None:
+        tag = hit[0]
+        if tag[0] == _PACK_GENERATION[0] and tag[1] == weight._version and tag[2] == weight.data_ptr():
+            return hit[1]
     tag = _h16_tag(weight)
-    hit = ent[1].get(bool(transposed))
-    if hit is not None and hit[0] == tag:
-        return hit[1]
     buf = hit[1] if hit is not None else torch.empty(4 * weight.numel(), dtype=torch.uint8, device=weight.device)
-    _h16_pack_jobs([(weight.detach(), transposed, buf)])
-    ent[1][bool(transposed)] = (tag, buf)
+    _h16_pack_jobs([(weight.detach(), tr, buf)])
+    if hit is None:
+        _H16_STAMP[0] += 1
+    ent[1][tr] = (tag, buf)
     return buf
 
 
 def repack_h16_all():
     """Re-pack every registered weight (both orientations in use) in a few batched launches: called by the optimizer
-    right after it changed the parameters, so the next step's linears find current copies."""
-    jobs, entries = [], []
-    for key, ent in list(_H16_REGISTRY.items()):
-        w = ent[0]()
-        if w is None:
-            _H16_REGISTRY.pop(key, None)
-            continue
-        for tr, (tag, buf) in ent[1].items():
-            new = _h16_tag(w)
-            if tag != new:
-                jobs.append((w.detach(), tr, buf))
-                entries.append((ent, tr, new, buf))
-    if jobs:
-        _h16_pack_jobs(jobs)
-        for ent, tr, new, buf in entries:
-            ent[1][tr] = (new, buf)
+    right after it changed the parameters, so the next step's linears find current copies.  The ctypes argument arrays
+    are cached (parameter and buffer addresses do not move between steps), so a call costs ~len(registry)/16 launches."""
+    cache = _H16_BATCHES
+    if cache["stamp"] != _H16_STAMP[0]:
+        flat, ents = [], []
+        for key, ent in list(_H16_REGISTRY.items()):
+            w = ent[0]()
+            if w is None:
+                continue
+            for tr, (tag, buf) in ent[1].items():
+                off = 0
+                for src_off, n, k, trans in _h16_slices(w, tr):
+                    flat.append((w.data_ptr() + 4 * src_off, n, k, trans, buf.data_ptr() + off))
+                    off += 4 * n * k
+                ents.append((ent, tr, w, buf))
+        calls = []
+        for first in range(0, len(flat), 16):
+            chunk = flat[first:first + 16]
+            m = len(chunk)
+            calls.append(((ctypes.c_void_p * m)(*[c[0] for c in chunk]), (ctypes.c_int32 * m)(*[c[1] for c in chunk]),
+                          (ctypes.c_int32 * m)(*[c[2] for c in chunk]), (ctypes.c_int32 * m)(*[c[3] for c in chunk]),
+                          (ctypes.c_void_p * m)(*[c[4] for c in chunk]), m))
+        cache.update(stamp=_H16_STAMP[0], calls=calls, ents=ents,
+                     ptrs=[(w.data_ptr(), buf.data_ptr()) for _, _, w, buf in ents])
+    ents = cache.get("ents", [])
+    if not ents:
+        return
+    if any(w.data_ptr() != p[0] for (_, _, w, _), p in zip(ents, cache["ptrs"])):     # a parameter moved: rebuild
+        cache["stamp"] = -1
+        return repack_h16_all()
+    st = _stream()
+    for wp, ns, ks, ts, op, m in cache["calls"]:
+        call("dig3d_h16_pack_t", wp, ns, ks, ts, op, m, st)
+    gen = _PACK_GENERATION[0]
+    for ent, tr, w, buf in ents:
+        ent[1][tr] = ((gen, w._version, w.data_ptr(), tuple(w.shape)), buf)
 
 
 def linear_h16(x, weight, bias=None, transposed=False, want_act=False):

@@ -123,6 +123,13 @@ int dig3d_triplet_basis_project(const float* bess, const float* angle, const flo
                                 int64_t n_edges, int64_t n_triplets, int32_t basis_id, int32_t n_layers,
                                 int32_t basis_emb, const float* w_sbf1, const float* w_t1, float* sbf_p,
                                 float* t_p, void* stream);
+/* Same outputs (bit-identical) with one CTA per MIDDLE node j of the triplets: the out-edges of j are found once, the
+ * harmonics of up to 256 triplets are evaluated with all threads busy, then contracted per (k -> j) edge. */
+int dig3d_triplet_basis_project_node(const float* bess, const float* angle, const float* torsion, const int32_t* src,
+                                     const int32_t* row_ptr, const int32_t* trip_ptr, const int32_t* graph_ptr,
+                                     const int64_t* batch, int64_t n_nodes, int64_t n_triplets, int32_t cap,
+                                     int32_t basis_id, int32_t n_layers, int32_t basis_emb, const float* w_sbf1,
+                                     const float* w_t1, float* sbf_p, float* t_p, void* stream);
 
 /* ------------------------------------------------------------------ segmented reductions
  * scatter(src, index, dim=0, dim_size, reduce='sum') with a SORTED index given as CSR pointers

@@ -668,3 +668,35 @@ def test_comenet_ocp_matches_oracle():
         assert rel_err(p.grad.cpu().numpy(), r.cpu().numpy()) < 1e-4, name
     with pytest.raises(NotImplementedError, match="hetero"):
         ComENet(0, 0, hidden_channels=256, num_blocks=1, num_radial=3, num_spherical=2, hetero=True).to(dev)(b)
+
+
+@pytest.mark.parametrize("cls_name", ["SphereNet", "DimeNetPP"])
+def test_node_centred_projection_equals_edge_centred(cls_name):
+    """The fused basis x first-projection kernel organised around the middle node of the triplets writes the same
+    sbf_p / t_p, bit for bit, as the one-warp-per-edge kernel (same FMA order), on a ragged batch with an isolated atom."""
+    from dig_b200 import ops
+    from dig_b200.data import synthetic_batch, collate, Molecule
+    from dig_b200.threedgraph import method
+    dev = torch.device("cuda:0")
+    tors = cls_name == "SphereNet"
+    model = getattr(method, cls_name)()
+    model.load_state_dict(formula_state_dict(model.state_dict(), seed=2))
+    model = model.to(dev)
+    mols = synthetic_batch(12, "qm9", seed=8, variable=True)
+    b = collate([Molecule(mols.z[:9], mols.pos[:9]), Molecule(torch.tensor([6]), torch.tensor([[40.0, 40.0, 40.0]])),
+                 Molecule(mols.z[9:], mols.pos[9:] + 0.0)]).to(dev)
+    b.batch = torch.cat([torch.zeros(9), torch.ones(1), mols.batch[9:].float() + 2]).long().to(dev)
+    g = ops.build_graph(b.pos, b.batch, 5.0)
+    ops.triplet_geometry(g, b.pos, use_torsion=tors, want_idx=False)
+    rbf0, bess = ops.edge_basis(g.dist, 5.0, 5, model.emb.dist_emb.freq, 0, not tors, 6, 42)
+    w_s, w_t = model._projection_rows(0, 4)
+    outs = []
+    for mode in ("edge", "node"):
+        ops.PROJECT_MODE[0] = mode
+        s_p, t_p = ops.triplet_basis_project(g, bess, 0, w_s, w_t)
+        outs.append((s_p.clone(), None if t_p is None else t_p.clone()))
+    ops.PROJECT_MODE[0] = "node"
+    assert g.n_triplets > 1000 and torch.isfinite(outs[1][0]).all()
+    assert torch.equal(outs[0][0], outs[1][0])
+    if tors:
+        assert torch.equal(outs[0][1], outs[1][1])
