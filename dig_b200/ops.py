@@ -157,7 +157,11 @@ def triplet_basis(bess, angle, torsion, idx_kj, basis_id, ns, nr, want_tbf):
     return sbf, tbf
 
 
-PROJECT_MODE = ["node"]      # "node" (one CTA per middle node of the triplets) | "edge" (one warp per (k -> j) edge)
+# "edge" (default): one warp per (k -> j) edge, persistent CTAs.  "node": one CTA per middle node of the triplets -- all
+# threads busy in the harmonics phase and no repeated out-edge search, bit-identical output, but measured SLOWER on the
+# B200 at the headline size (0.226 vs 0.199 ms: three CTA-wide barriers per pass and only ~15 in-edges to spread over the
+# eight contraction warps); kept as the starting point for a version that keeps several nodes in flight per CTA.
+PROJECT_MODE = ["edge"]
 
 
 def triplet_basis_project(g, bess, basis_id, w_sbf1_rows, w_t1_rows):
@@ -950,7 +954,7 @@ _H16_REGISTRY = {}          # id(weight) -> [weakref, {transposed: (tag, buffer)
 
 
 def linear_h16_supported(k, nout):
-    return bool(_lib.load().dig3d_linear_h16_supported(int(k), int(nout)))
+    return k in (64, 128, 256, 384) and 64 <= nout <= 512 and nout % 64 == 0      # == dig3d_linear_h16_supported
 
 
 def _h16_tag(weight):

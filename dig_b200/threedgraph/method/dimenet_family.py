@@ -253,7 +253,11 @@ class _DimeNetFamily(nn.Module):
         g = ops.build_graph(pos, batch, self.cutoff, num_graphs=getattr(batch_data, "num_graphs", None),
                             z=z if with_emb else None, z_rows=self.init_e.emb.num_embeddings if with_emb else 0)
         if wants_grad(self) or self._generic:
-            return self._forward_train(z, pos, g, getattr(batch_data, "node_feature", None))
+            ag.EXACT_BACKWARD[0] = bool(pos.requires_grad)     # forces: keep the input-gradient GEMMs exact
+            try:
+                return self._forward_train(z, pos, g, getattr(batch_data, "node_feature", None))
+            finally:
+                ag.EXACT_BACKWARD[0] = False
         ops.triplet_geometry(g, pos, use_torsion=self._torsion, want_idx=False)
         rbf0, bess = ops.edge_basis(g.dist, self.cutoff, self.envelope_exponent, self.emb.dist_emb.freq,
                                     self._basis_id, envelope_on_bessel=not self._torsion, num_radial=nr,

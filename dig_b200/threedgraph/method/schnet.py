@@ -121,7 +121,11 @@ class SchNet(nn.Module):
         g = ops.build_graph(pos, batch, self.cutoff, num_graphs=getattr(batch_data, "num_graphs", None),
                             want_edge_index=False, z=z, z_rows=self.init_v.num_embeddings)
         if wants_grad(self) or self._generic:
-            return self._forward_train(z, pos, g)
+            ag.EXACT_BACKWARD[0] = bool(pos.requires_grad)     # forces: keep the input-gradient GEMMs exact
+            try:
+                return self._forward_train(z, pos, g)
+            finally:
+                ag.EXACT_BACKWARD[0] = False
         # v = init_v(z): an embedding row gather (torch indexing = plumbing, no arithmetic)
         v = self.init_v.weight.detach()[z].contiguous()
         keep = []

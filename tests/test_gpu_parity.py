@@ -695,7 +695,7 @@ def test_node_centred_projection_equals_edge_centred(cls_name):
         ops.PROJECT_MODE[0] = mode
         s_p, t_p = ops.triplet_basis_project(g, bess, 0, w_s, w_t)
         outs.append((s_p.clone(), None if t_p is None else t_p.clone()))
-    ops.PROJECT_MODE[0] = "node"
+    ops.PROJECT_MODE[0] = "edge"
     assert g.n_triplets > 1000 and torch.isfinite(outs[1][0]).all()
     assert torch.equal(outs[0][0], outs[1][0])
     if tors:

@@ -651,14 +651,15 @@ def test_linear_on_the_two_tile_engine_matches_fp64(k, nout):
         w = torch.nn.Parameter(torch.randn(nout, k, device=dev) / k ** 0.5)
         b = torch.randn(nout, device=dev)
         y, a = ops.linear_h16(x, w, b, want_act=True)
-        ref = x.double() @ w.double().t() + b.double()
+        wd = w.detach().double()
+        ref = x.double() @ wd.t() + b.double()
         assert rel_err(y.cpu().numpy(), ref.cpu().numpy()) < 2e-6
         assert rel_err(a.cpu().numpy(), (ref * torch.sigmoid(ref)).cpu().numpy()) < 2e-6
         dy = torch.randn(rows, nout, device=dev)
         dx = ops.linear_h16(dy, w, None, transposed=True)
-        assert rel_err(dx.cpu().numpy(), (dy.double() @ w.double()).cpu().numpy()) < 2e-6
+        assert rel_err(dx.cpu().numpy(), (dy.double() @ wd).cpu().numpy()) < 2e-6
         with torch.no_grad():
             w.mul_(0.5)                                  # a parameter update must be seen (version-keyed cache)
         y2 = ops.linear_h16(x, w, b)
-        assert rel_err(y2.cpu().numpy(), (x.double() @ w.double().t() + b.double()).cpu().numpy()) < 2e-6
+        assert rel_err(y2.cpu().numpy(), (x.double() @ w.detach().double().t() + b.double()).cpu().numpy()) < 2e-6
     assert ops.tc_timeouts() == 0 and not ops.h16_overflow()
