@@ -257,6 +257,26 @@ def other_configs(dev):
                     return model(b)
             ms = time_ms(torch, infer)
             rec["inference"] = {"ms_per_step": round(ms, 4), "molecules_per_s": round(nmol / (ms * 1e-3), 1)}
+            # whole-forward roofline view (SURVEY 8d flop counts; fp32 work counted once): which pipe would bound it
+            from dig_b200 import ops as _ops
+            if hasattr(b, "pos") and not data_kw.get("protein"):
+                gg = _ops.build_graph(b.pos, b.batch, model.cutoff, num_graphs=nmol)
+                E_, N_ = gg.n_edges, gg.n_nodes
+                fl = None
+                if name.startswith("cfg4"):          # ComENet: 1.70 MFLOP/node + 68.8 kFLOP/edge per block, 4 blocks
+                    fl = 4 * (N_ * 1.70e6 + E_ * 68.8e3)
+                    kind = "fp32 FFMA (fused block kernels, no tensor cores yet)"
+                elif name.startswith("cfg3"):        # DimeNet++: 331 kFLOP/edge + 2.8 kFLOP/triplet per block + node MLPs
+                    _ops.triplet_geometry(gg, b.pos, use_torsion=False, want_idx=False)
+                    fl = 4 * (E_ * 331e3 + gg.n_triplets * 2.8e3) + 5 * N_ * 459e3
+                    kind = "tcgen05 3xFP16 dense chain + FP32 triplet kernels"
+                elif name.startswith("cfg1"):        # SchNet: 2(G F + F^2) + 3F per edge, 2(HF + FH + H^2) per node, 2 layers
+                    fl = 2 * (E_ * (2 * (50 * 32 + 32 * 32) + 96) + N_ * 2 * 3 * 32 * 32)
+                    kind = "fp32 FFMA (launch-latency bound at this size)"
+                if fl:
+                    rec["inference"]["roofline"] = {"flops_per_step": fl, "achieved_tflops": round(fl / (ms * 1e-3) / 1e12, 3),
+                                                    "frac_of_tensor_peak": round(fl / (ms * 1e-3) / 1e12 / peaks()[1], 5),
+                                                    "edges": E_, "nodes": N_, "pipe": kind}
             y = torch.randn(nmol, 1, device=dev)
             opt = torch.optim.Adam(model.parameters(), lr=5e-4)
 

@@ -516,13 +516,15 @@ def sphere_update_e_tc(e1, g, rbf0, sbf_p, t_p, col0, w, hidden, int_emb, v_in=N
     return e1_out, v_in, x_ji, x_down
 
 
-GATHER_MODE = ["node"]       # "node" (source-node CTAs, shared-memory staged rows) | "edge" (one warp per edge)
+# "node": source-node CTAs, shared-memory staged rows, FP32 expansions (exact fp32, bit-equal to "edge");
+# "tc": the same organisation with the 8 -> 64 expansions on tcgen05 (3xFP16 operands); "edge": one warp per edge
+GATHER_MODE = ["node"]
 
 
 def triplet_gather(x_down, sp, tp, g, w_sbf2, w_t2, m_out, st):
     """m[e] = sum_t x_down[kj] * lin_sbf2(sbf_p) * lin_t2(t_p)  (spherenet.py:163-171); sp / tp are layer slices."""
-    if GATHER_MODE[0] == "node":
-        call("dig3d_sphere_triplet_gather_node", _p(x_down), sp, tp, 8, _p(g.src), _p(g.row_ptr), _p(g.trip_ptr),
+    if GATHER_MODE[0] in ("node", "tc"):
+        call("dig3d_sphere_triplet_gather_tc" if GATHER_MODE[0] == "tc" else "dig3d_sphere_triplet_gather_node", _p(x_down), sp, tp, 8, _p(g.src), _p(g.row_ptr), _p(g.trip_ptr),
              _p(g.graph_ptr), _p(g.batch, torch.int64), g.n_nodes, g.cap, w_sbf2, w_t2, _p(m_out), st)
     else:
         call("dig3d_sphere_triplet_gather", _p(x_down), sp, tp, 8, _p(g.src), _p(g.dst), _p(g.row_ptr),

@@ -275,6 +275,14 @@ int dig3d_sphere_update_v_h16_supported(int32_t hidden, int32_t out_emb, int32_t
 int dig3d_sphere_update_v_h16(const float* v_in_all, int64_t n_nodes, int32_t n_blocks, int32_t out_channels,
                               int32_t n_lins, const void* const* packed, const dig3d_update_v_weights* w,
                               float* v_out_all, void* stream);
+/* The triplet gather with the two 8 -> 64 expansions (lin_sbf2, lin_t2) on the tensor cores: one CTA per source node,
+ * x_down rows of its in-edges staged in shared memory, whole out-edges packed into tiles of <= 128 triplet rows, G_s / G_t
+ * in TMEM (3xFP16 operands, K = 16 zero padded), products + per-edge sums in the epilogue.  Same contract as
+ * dig3d_sphere_triplet_gather_node (every edge that has a source is written); fp32-level accuracy (~3e-7), not bit-equal. */
+int dig3d_sphere_triplet_gather_tc(const float* x_down, const float* sbf_p, const float* t_p, int32_t ld_p,
+                                   const int32_t* src, const int32_t* row_ptr, const int32_t* trip_ptr,
+                                   const int32_t* graph_ptr, const int64_t* batch, int64_t n_nodes, int32_t cap,
+                                   const float* w_sbf2, const float* w_t2, float* m, void* stream);
 /* Training-path linears on the same engine: y[rows, nout] = x[rows, k] W^T + bias, optionally also swish(y);
  * dig3d_h16_pack_t: trans[i] = 0 packs weights[i] as a row-major [n, k] matrix; trans[i] = ld > 0 packs the TRANSPOSE of
  * a [k, n] block whose rows are ld floats apart (a column slice of W for the input-gradient GEMM dX = dY W). */
