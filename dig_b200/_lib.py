@@ -140,6 +140,10 @@ SIGNATURES = {
     "dig3d_linear_tc_supported": [c_int32, c_int32],
     "dig3d_linear_tc": [P, c_int64, c_int32, c_int32, P, P, P, P, P],
     "dig3d_act_bwd2": [P, P, P, c_int64, c_int32, P, P],
+    "dig3d_geometry_jvp": [P, P, P, P, P, P, P, c_int64, P, P, P, P],
+    "dig3d_edge_basis_tangent": [P, P, c_int64, c_double, c_int32, P, c_int32, c_int32, P, P, P],
+    "dig3d_rbf_freq_grad_tangent": [P, P, c_int64, c_double, c_int32, P, c_int32, P, P, P],
+    "dig3d_triplet_basis_tangent": [P, P, P, P, P, P, P, c_int64, c_int32, P, P, P],
     "dig3d_edge_dist_bwd2": [P, P, P, P, P, P, c_int64, P, P, P],
     "dig3d_schnet_edge_features_bwd2": [P, c_int64, P, c_int32, c_double, c_double, P, P, P, P, P, P, P],
     "dig3d_pronet_edge_features": [P, P, P, P, P, c_int64, c_int64, c_int32, c_double, c_int32, P, P, P, P, P, P],

@@ -606,6 +606,103 @@ __global__ void edge_basis_bwd_kernel(const float* __restrict__ dist, int n_edge
   }
 }
 
+// ------------------------------------------------------------------ forward-mode basis (force training, autograd_jvp.py)
+// Tangents of the edge bases along a displacement with dist_dot[e] = d(dist_e)/d(eps):
+//   rbf0_dot[e][n] = d(env(x) sin(f_n x))/dx * dist_dot / cutoff,   bess_dot[e][c] = d(bess[e][c])/dx * dist_dot / cutoff.
+template <class BS>
+__global__ void edge_basis_tangent_kernel(const float* __restrict__ dist, const float* __restrict__ dist_dot, int n_edges,
+                                          float inv_cutoff, int p, float ea, float eb, float ec,
+                                          const float* __restrict__ freq, int env_on_bessel,
+                                          float* __restrict__ rbf0_dot, float* __restrict__ bess_dot) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  const float x = __fmul_rn(dist[e], inv_cutoff);
+  const float xd = dist_dot[e] * inv_cutoff;
+  const float env = envelope(x, p, ea, eb, ec), envd = envelope_dx(x, p, ea, eb, ec);
+  if (rbf0_dot) {
+#pragma unroll
+    for (int n = 0; n < BS::NR; ++n) {
+      const float f = __ldg(freq + n);
+      rbf0_dot[(size_t)e * BS::NR + n] = (envd * sinf(f * x) + env * f * cosf(f * x)) * xd;
+    }
+  }
+  if (bess_dot) {
+    float b[BS::NB], bd[BS::NB];
+    BS::bessel(x, b);
+    BS::bessel_dx(x, bd);
+#pragma unroll
+    for (int c = 0; c < BS::NB; ++c)
+      bess_dot[(size_t)e * BS::NB + c] = (env_on_bessel ? fmaf(envd, b[c], env * bd[c]) : bd[c]) * xd;
+  }
+}
+
+// d(loss)/d(freq[n]) through rbf0_dot:  sum_e G[e][n] * xd_e * d/df ( env' sin(f x) + env f cos(f x) )
+//                                     = sum_e G[e][n] * xd_e * ( env' x cos(f x) + env (cos(f x) - f x sin(f x)) )
+__global__ void rbf_freq_grad_tangent_kernel(const float* __restrict__ dist, const float* __restrict__ dist_dot,
+                                             int64_t n_edges, float inv_cutoff, int p, float ea, float eb, float ec,
+                                             const float* __restrict__ freq, int nr, const float* __restrict__ g_dot,
+                                             float* __restrict__ dfreq) {
+  float part[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (int64_t)gridDim.x * blockDim.x) {
+    const float x = __fmul_rn(dist[e], inv_cutoff);
+    const float xd = dist_dot[e] * inv_cutoff;
+    const float env = envelope(x, p, ea, eb, ec), envd = envelope_dx(x, p, ea, eb, ec);
+    for (int n = 0; n < nr; ++n) {
+      const float f = __ldg(freq + n);
+      float sn, cs;
+      sincosf(f * x, &sn, &cs);
+      part[n] = fmaf(g_dot[e * nr + n] * xd, envd * x * cs + env * (cs - f * x * sn), part[n]);
+    }
+  }
+  for (int n = 0; n < nr; ++n) {
+    float v = part[n];
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(dfreq + n, v);
+  }
+}
+
+// Tangents of the materialised triplet bases (layouts of triplet_basis_kernel):
+//   sbf_dot[t][l,n]  = Y_l0'(th) th_dot bess[kj][l,n] + Y_l0(th) bess_dot[kj][l,n]
+//   tbf_dot[t][ab,r] = (dY_ab/dth th_dot + dY_ab/dph ph_dot) bess[kj][b,r] + Y_ab bess_dot[kj][b,r]
+template <class BS>
+__global__ void triplet_basis_tangent_kernel(const float* __restrict__ bess, const float* __restrict__ bess_dot,
+                                             const float* __restrict__ angle, const float* __restrict__ angle_dot,
+                                             const float* __restrict__ torsion, const float* __restrict__ torsion_dot,
+                                             const int32_t* __restrict__ idx_kj, int n_triplets,
+                                             float* __restrict__ sbf_dot, float* __restrict__ tbf_dot) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_triplets) return;
+  const float* rb = bess + (size_t)idx_kj[t] * BS::NB;
+  const float* rd = bess_dot + (size_t)idx_kj[t] * BS::NB;
+  const float th = angle[t], thd = angle_dot[t];
+  if (sbf_dot) {
+    float y0[BS::NS], y0d[BS::NS];
+    BS::yl0(th, y0);
+    BS::yl0_dtheta(th, y0d);
+#pragma unroll
+    for (int l = 0; l < BS::NS; ++l)
+#pragma unroll
+      for (int n = 0; n < BS::NR; ++n)
+        sbf_dot[(size_t)t * BS::NB + l * BS::NR + n] =
+            fmaf(y0d[l] * thd, __ldg(rb + l * BS::NR + n), y0[l] * __ldg(rd + l * BS::NR + n));
+  }
+  if (tbf_dot) {
+    const float ph = torsion[t], phd = torsion_dot[t];
+    float y[BS::NY], yd[BS::NY];
+    BS::ylm_dtheta(th, ph, yd);
+    BS::ylm_dphi(th, ph, y);
+#pragma unroll
+    for (int ab = 0; ab < BS::NY; ++ab) yd[ab] = fmaf(yd[ab], thd, y[ab] * phd);
+    BS::ylm(th, ph, y);
+#pragma unroll
+    for (int ab = 0; ab < BS::NY; ++ab)
+#pragma unroll
+      for (int r = 0; r < BS::NR; ++r)
+        tbf_dot[(size_t)t * (BS::NY * BS::NR) + ab * BS::NR + r] =
+            fmaf(yd[ab], __ldg(rb + (ab % BS::NS) * BS::NR + r), y[ab] * __ldg(rd + (ab % BS::NS) * BS::NR + r));
+  }
+}
+
 // Backward of the fused projection w.r.t. the geometry (forces):
 //   sbf_p[q][t] = sum_l  Y_l0(angle_t)            Rs[q][l],   Rs[q][l]  = sum_r bess[kj][l,r]  w_sbf1[q][l,r]
 //   t_p[q][t]   = sum_ab Y_ab(angle_t, torsion_t) R[q][ab],   R[q][ab]  = sum_r bess[kj][b,r]  w_t1[q][ab,r]
@@ -852,6 +949,58 @@ int dig3d_triplet_basis(const float* bess, const float* angle, const float* tors
     case 0: triplet_basis_kernel<B76><<<grid, 128, 0, st>>>(bess, angle, torsion, idx_kj, (int)n_triplets, sbf, tbf); break;
     case 1: triplet_basis_kernel<B36><<<grid, 128, 0, st>>>(bess, angle, torsion, idx_kj, (int)n_triplets, sbf, tbf); break;
     default: set_error("triplet_basis: unsupported basis_id %d", basis_id); return DIG3D_EUNSUPPORTED;
+  }
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_edge_basis_tangent(const float* dist, const float* dist_dot, int64_t n_edges, double cutoff,
+                             int32_t envelope_exponent, const float* freq, int32_t basis_id, int32_t envelope_on_bessel,
+                             float* rbf0_dot, float* bess_dot, void* stream) {
+  DIG3D_REQUIRE(dist && dist_dot && (rbf0_dot || bess_dot), "edge_basis_tangent: null pointer");
+  DIG3D_REQUIRE(!rbf0_dot || freq, "edge_basis_tangent: rbf0_dot needs freq");
+  if (n_edges == 0) return DIG3D_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int p = envelope_exponent + 1;
+  const float a = -(float)((p + 1) * (p + 2)) / 2.f, b = (float)(p * (p + 2)), c = -(float)(p * (p + 1)) / 2.f;
+  const float inv = 1.0f / (float)cutoff;
+  const int grid = ceil_div(n_edges, 128);
+  switch (basis_id) {
+    case 0: edge_basis_tangent_kernel<B76><<<grid, 128, 0, st>>>(dist, dist_dot, (int)n_edges, inv, p, a, b, c, freq, envelope_on_bessel, rbf0_dot, bess_dot); break;
+    case 1: edge_basis_tangent_kernel<B36><<<grid, 128, 0, st>>>(dist, dist_dot, (int)n_edges, inv, p, a, b, c, freq, envelope_on_bessel, rbf0_dot, bess_dot); break;
+    default: set_error("edge_basis_tangent: unsupported basis_id %d", basis_id); return DIG3D_EUNSUPPORTED;
+  }
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_rbf_freq_grad_tangent(const float* dist, const float* dist_dot, int64_t n_edges, double cutoff,
+                                int32_t envelope_exponent, const float* freq, int32_t nr, const float* g_dot,
+                                float* dfreq, void* stream) {
+  DIG3D_REQUIRE(dist && dist_dot && freq && g_dot && dfreq, "rbf_freq_grad_tangent: null pointer");
+  DIG3D_REQUIRE(nr >= 1 && nr <= 8, "rbf_freq_grad_tangent: num_radial=%d outside [1,8]", nr);
+  if (n_edges == 0) return DIG3D_OK;
+  const int p = envelope_exponent + 1;
+  const float a = -(float)((p + 1) * (p + 2)) / 2.f, b = (float)(p * (p + 2)), c = -(float)(p * (p + 1)) / 2.f;
+  const int grid = (int)(ceil_div(n_edges, 256) < 296 ? ceil_div(n_edges, 256) : 296);
+  rbf_freq_grad_tangent_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dist, dist_dot, n_edges, 1.0f / (float)cutoff, p,
+                                                                      a, b, c, freq, nr, g_dot, dfreq);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_triplet_basis_tangent(const float* bess, const float* bess_dot, const float* angle, const float* angle_dot,
+                                const float* torsion, const float* torsion_dot, const int32_t* idx_kj,
+                                int64_t n_triplets, int32_t basis_id, float* sbf_dot, float* tbf_dot, void* stream) {
+  DIG3D_REQUIRE(bess && bess_dot && angle && angle_dot && idx_kj && (sbf_dot || tbf_dot), "triplet_basis_tangent: null pointer");
+  DIG3D_REQUIRE(!tbf_dot || (torsion && torsion_dot), "triplet_basis_tangent: tbf_dot requested without torsion / torsion_dot");
+  if (n_triplets == 0) return DIG3D_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ceil_div(n_triplets, 128);
+  switch (basis_id) {
+    case 0: triplet_basis_tangent_kernel<B76><<<grid, 128, 0, st>>>(bess, bess_dot, angle, angle_dot, torsion, torsion_dot, idx_kj, (int)n_triplets, sbf_dot, tbf_dot); break;
+    case 1: triplet_basis_tangent_kernel<B36><<<grid, 128, 0, st>>>(bess, bess_dot, angle, angle_dot, torsion, torsion_dot, idx_kj, (int)n_triplets, sbf_dot, tbf_dot); break;
+    default: set_error("triplet_basis_tangent: unsupported basis_id %d", basis_id); return DIG3D_EUNSUPPORTED;
   }
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;

@@ -1372,7 +1372,7 @@ int dig3d_sphere_triplet_gather_tc(const float* x_down, const float* sbf_p, cons
   int dev = 0, n_sm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = (int)(n_nodes < 3 * n_sm ? n_nodes : 3 * n_sm);
+  const int grid = (int)(n_nodes < 2 * n_sm ? n_nodes : 2 * n_sm);   // 79 KB of shared memory per CTA: two per SM
   cudaError_t e;
   if (t_p) {
     e = cudaFuncSetAttribute(sphere_triplet_gather_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GTSmem));

@@ -253,6 +253,129 @@ __global__ void rowdot_kernel(const float* __restrict__ a, const float* __restri
   if (lane == 0) out[r] = acc;
 }
 
+// ---------------------------------------------------------------------------------- forward-mode geometry (force training)
+// Training ON forces (reference run.py:110-123) needs d/d(theta) of  c . dE/dpos  for a fixed per-atom vector c; that is
+// the parameter gradient of the DIRECTIONAL derivative of E along c (dig_b200/autograd_jvp.py).  The geometry side of
+// that derivative is first order: the tangents of dist / angle / torsion along c,
+//   dist_dot[e] = u_hat . (c_i - c_j),   angle_dot[t] = g_u . (c_i - c_j) + g_v . (c_k - c_j),   torsion_dot[t] likewise
+// with exactly the per-triplet gradients g_u, g_v, ... the backward kernels above scatter (so J c and J^T w agree to
+// rounding; tests check <J c, w> = <c, J^T w>).  One thread per edge / one warp per (j -> i) edge, same enumeration.
+__global__ void edge_dist_jvp_kernel(const float* __restrict__ pos, const float* __restrict__ cvec,
+                                     const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+                                     const float* __restrict__ dist, int n_edges, float* __restrict__ dist_dot) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  const float d = dist[e];
+  if (d == 0.f) { dist_dot[e] = 0.f; return; }
+  const int j = src[e], i = dst[e];
+  const f3 u = sub3(load3(pos, i), load3(pos, j)), dc = sub3(load3(cvec, i), load3(cvec, j));
+  dist_dot[e] = (u.x * dc.x + u.y * dc.y + u.z * dc.z) / d;
+}
+
+__device__ __forceinline__ float dot3(const f3 a, const f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+__global__ void __launch_bounds__(256)
+triplet_angle_jvp_kernel(const float* __restrict__ pos, const float* __restrict__ cvec, const int32_t* __restrict__ src,
+                         const int32_t* __restrict__ dst, const int32_t* __restrict__ row_ptr,
+                         const int32_t* __restrict__ trip_ptr, int n_edges, float* __restrict__ angle_dot) {
+  const int lane = threadIdx.x & 31;
+  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (e >= n_edges) return;
+  const int j = src[e], i = dst[e];
+  const int base = row_ptr[j], d = row_ptr[j + 1] - base;
+  int p_i = d;
+  for (int s0 = 0; s0 < d; s0 += 32) {
+    const int sl = s0 + lane;
+    const unsigned hit = __ballot_sync(0xffffffffu, sl < d && src[base + sl] == i);
+    if (hit) p_i = s0 + __ffs(hit) - 1;
+  }
+  const f3 pj = load3(pos, j), cj = load3(cvec, j);
+  const f3 u = sub3(load3(pos, i), pj), cu = sub3(load3(cvec, i), cj);
+  const int t0 = trip_ptr[e];
+  for (int s = lane; s < d; s += 32) {
+    if (s == p_i) continue;
+    const int k = src[base + s];
+    const f3 v = sub3(load3(pos, k), pj), cv = sub3(load3(cvec, k), cj);
+    const float a = dot3(u, v);
+    const f3 w = cross3(u, v);
+    const float b = sqrtf(dot3(w, w));
+    const float den = a * a + b * b;
+    float out = 0.f;
+    if (den != 0.f) {
+      const float ga = -b / den, gb = a / den;
+      f3 gu = scale3(v, ga), gv = scale3(u, ga);
+      if (b > 0.f) {
+        const f3 wh = scale3(w, 1.0f / b);
+        gu = add3(gu, scale3(cross3(v, wh), gb));
+        gv = add3(gv, scale3(cross3(wh, u), gb));
+      }
+      out = dot3(gu, cu) + dot3(gv, cv);
+    }
+    angle_dot[t0 + s - (s > p_i ? 1 : 0)] = out;
+  }
+}
+
+__global__ void __launch_bounds__(TGEO_WARPS * 32)
+triplet_torsion_jvp_kernel(const float* __restrict__ pos, const float* __restrict__ cvec, const int32_t* __restrict__ src,
+                           const int32_t* __restrict__ dst, const int32_t* __restrict__ row_ptr,
+                           const int32_t* __restrict__ trip_ptr, int n_edges, float* __restrict__ torsion_dot) {
+  __shared__ float planes[TGEO_WARPS][TGEO_MAXDEG][3];
+  __shared__ int32_t ks[TGEO_WARPS][TGEO_MAXDEG];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int e = blockIdx.x * TGEO_WARPS + w;
+  if (e >= n_edges) return;
+  const int j = src[e], i = dst[e];
+  const int base = row_ptr[j], d = min(row_ptr[j + 1] - base, TGEO_MAXDEG);
+  const f3 pj = load3(pos, j), cj = load3(cvec, j);
+  const f3 u = sub3(load3(pos, i), pj), cu = sub3(load3(cvec, i), cj);
+  const float n = norm3_aten(u);
+  for (int s = lane; s < d; s += 32) {
+    const int k = src[base + s];
+    ks[w][s] = k;
+    const f3 pl = cross_aten(u, sub3(load3(pos, k), pj));
+    planes[w][s][0] = pl.x; planes[w][s][1] = pl.y; planes[w][s][2] = pl.z;
+  }
+  __syncwarp();
+  int p_i = d;
+  for (int s = 0; s < d; ++s) if (ks[w][s] == i) p_i = s;
+  const int t0 = trip_ptr[e];
+  for (int s = lane; s < d; s += 32) {
+    if (s == p_i) continue;
+    const f3 p1 = {planes[w][s][0], planes[w][s][1], planes[w][s][2]};
+    float best = __int_as_float(0x7f800000), bta = 1.f, btb = 0.f;
+    int bc = -1;
+    for (int c = 0; c < d; ++c) {              // same candidate search (and rounding) as the forward / backward kernels
+      if (c == p_i) continue;
+      const f3 p2 = {planes[w][c][0], planes[w][c][1], planes[w][c][2]};
+      const float ta = sum3_aten(mul3(p1, p2));
+      const float tb = __fdiv_rn(sum3_aten(mul3(cross_aten(p1, p2), u)), n);
+      float tor = atan2f(tb, ta);
+      if (tor <= 0.0f) tor = __fadd_rn(tor, 6.2831855f);
+      if (tor < best) { best = tor; bc = c; bta = ta; btb = tb; }
+    }
+    const float den = bta * bta + btb * btb;
+    float out = 0.f;
+    if (bc >= 0 && den != 0.f) {
+      const float g_ta = -btb / den, g_tb = bta / den;
+      const f3 p2 = {planes[w][bc][0], planes[w][bc][1], planes[w][bc][2]};
+      const f3 q = cross3(p1, p2);
+      const float sq = dot3(q, u);
+      const float g_s = g_tb / n, g_n = -g_tb * sq / (n * n);
+      f3 g_p1 = scale3(p2, g_ta), g_p2 = scale3(p1, g_ta);
+      const f3 g_q = scale3(u, g_s);
+      f3 g_u = add3(scale3(q, g_s), scale3(u, g_n / n));
+      g_p1 = add3(g_p1, cross3(p2, g_q));
+      g_p2 = add3(g_p2, cross3(g_q, p1));
+      const int k = ks[w][s], c = ks[w][bc];
+      const f3 vk = sub3(load3(pos, k), pj), vc = sub3(load3(pos, c), pj);
+      g_u = add3(g_u, add3(cross3(vk, g_p1), cross3(vc, g_p2)));
+      const f3 g_vk = cross3(g_p1, u), g_vc = cross3(g_p2, u);
+      out = dot3(g_u, cu) + dot3(g_vk, sub3(load3(cvec, k), cj)) + dot3(g_vc, sub3(load3(cvec, c), cj));
+    }
+    torsion_dot[t0 + s - (s > p_i ? 1 : 0)] = out;
+  }
+}
+
 }  // namespace dig3d
 
 using namespace dig3d;
@@ -286,6 +409,28 @@ int dig3d_triplet_torsion_bwd(const float* pos, const int32_t* src, const int32_
   triplet_torsion_bwd_kernel<<<ceil_div(n_edges, TGEO_WARPS), TGEO_WARPS * 32, 0, (cudaStream_t)stream>>>(
       pos, src, dst, row_ptr, trip_ptr, dtorsion, (int)n_edges, dpos);
   DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_geometry_jvp(const float* pos, const float* cvec, const int32_t* src, const int32_t* dst,
+                       const int32_t* row_ptr, const int32_t* trip_ptr, const float* dist, int64_t n_edges,
+                       float* dist_dot, float* angle_dot, float* torsion_dot, void* stream) {
+  DIG3D_REQUIRE(pos && cvec && src && dst && dist && dist_dot, "geometry_jvp: null pointer");
+  DIG3D_REQUIRE((!angle_dot && !torsion_dot) || (row_ptr && trip_ptr), "geometry_jvp: triplet tangents need row_ptr / trip_ptr");
+  if (n_edges == 0) return DIG3D_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  edge_dist_jvp_kernel<<<ceil_div(n_edges, 256), 256, 0, st>>>(pos, cvec, src, dst, dist, (int)n_edges, dist_dot);
+  DIG3D_LAUNCH_CHECK();
+  if (angle_dot) {
+    triplet_angle_jvp_kernel<<<ceil_div(n_edges * 32, 256), 256, 0, st>>>(pos, cvec, src, dst, row_ptr, trip_ptr,
+                                                                          (int)n_edges, angle_dot);
+    DIG3D_LAUNCH_CHECK();
+  }
+  if (torsion_dot) {
+    triplet_torsion_jvp_kernel<<<ceil_div(n_edges, TGEO_WARPS), TGEO_WARPS * 32, 0, st>>>(
+        pos, cvec, src, dst, row_ptr, trip_ptr, (int)n_edges, torsion_dot);
+    DIG3D_LAUNCH_CHECK();
+  }
   return DIG3D_OK;
 }
 

@@ -1086,6 +1086,52 @@ def act_bwd2(x, dy, g, mode):
     return out
 
 
+# ------------------------------------------------------------------ forward-mode kernels (force training, autograd_jvp.py)
+def geometry_jvp(pos, cvec, g, want_angle=True, want_torsion=False):
+    """Tangents of dist [E], angle [T], torsion [T] along the per-atom displacement cvec [N, 3]."""
+    dev = pos.device
+    d_dot = torch.zeros(g.n_edges, device=dev, dtype=F32)
+    a_dot = torch.zeros(g.n_triplets, device=dev, dtype=F32) if want_angle else None
+    t_dot = torch.zeros(g.n_triplets, device=dev, dtype=F32) if want_torsion else None
+    if g.n_edges:
+        call("dig3d_geometry_jvp", _p(pos, F32, "pos"), _p(cvec, F32, "cvec"), _p(g.src), _p(g.dst), _p(g.row_ptr),
+             _p(g.trip_ptr), _p(g.dist), g.n_edges, _p(d_dot), _p(a_dot), _p(t_dot), _stream())
+    return d_dot, a_dot, t_dot
+
+
+def edge_basis_tangent(dist, dist_dot, cutoff, envelope_exponent, freq, basis_id, envelope_on_bessel, nr, n_bessel,
+                       want_rbf0=True, want_bess=True):
+    e = dist.numel()
+    r_dot = torch.zeros(e, nr, device=dist.device, dtype=F32) if want_rbf0 else None
+    b_dot = torch.zeros(e, n_bessel, device=dist.device, dtype=F32) if want_bess else None
+    if e:
+        call("dig3d_edge_basis_tangent", _p(dist, F32, "dist"), _p(dist_dot, F32, "dist_dot"), e, float(cutoff),
+             int(envelope_exponent), _p(freq.detach(), F32, "freq") if freq is not None else None, int(basis_id),
+             int(bool(envelope_on_bessel)), _p(r_dot), _p(b_dot), _stream())
+    return r_dot, b_dot
+
+
+def rbf_freq_grad_tangent(dist, dist_dot, cutoff, envelope_exponent, freq, g_dot):
+    dfreq = torch.zeros_like(freq, dtype=F32)
+    if dist.numel():
+        call("dig3d_rbf_freq_grad_tangent", _p(dist, F32, "dist"), _p(dist_dot, F32, "dist_dot"), dist.numel(),
+             float(cutoff), int(envelope_exponent), _p(freq.detach(), F32, "freq"), freq.numel(),
+             _p(g_dot, F32, "g_dot"), _p(dfreq), _stream())
+    return dfreq
+
+
+def triplet_basis_tangent(bess, bess_dot, angle, angle_dot, torsion, torsion_dot, idx_kj, basis_id, ns, nr, want_tbf):
+    t = angle.numel()
+    dev = angle.device
+    s_dot = torch.zeros(t, ns * nr, dtype=F32, device=dev)
+    t_dot = torch.zeros(t, ns * ns * nr, dtype=F32, device=dev) if want_tbf else None
+    if t:
+        call("dig3d_triplet_basis_tangent", _p(bess, F32), _p(bess_dot, F32), _p(angle, F32), _p(angle_dot, F32),
+             _p(torsion, F32) if want_tbf else None, _p(torsion_dot, F32) if want_tbf else None,
+             _p(idx_kj, torch.int32), t, int(basis_id), _p(s_dot), _p(t_dot), _stream())
+    return s_dot, t_dot
+
+
 def edge_dist_bwd2(pos, g, ddist, g_dpos):
     """-> (d_ddist [E], d_pos [N,3]) of edge_dist_bwd given g_dpos = d(loss)/d(dpos)."""
     d_ddist = torch.zeros(g.n_edges, device=pos.device, dtype=F32)

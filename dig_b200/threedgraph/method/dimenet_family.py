@@ -19,6 +19,7 @@ import torch
 from torch import nn
 
 from ... import autograd as ag
+from ... import autograd_jvp as jv
 from ... import ops
 from ...basis import envelope_coefficients  # noqa: F401  (documented dependency)
 from ._common import ResidualLayer, glorot_orthogonal, require_cuda, swish, wants_grad
@@ -253,11 +254,15 @@ class _DimeNetFamily(nn.Module):
         g = ops.build_graph(pos, batch, self.cutoff, num_graphs=getattr(batch_data, "num_graphs", None),
                             z=z if with_emb else None, z_rows=self.init_e.emb.num_embeddings if with_emb else 0)
         if wants_grad(self) or self._generic:
-            ag.EXACT_BACKWARD[0] = bool(pos.requires_grad)     # forces: keep the input-gradient GEMMs exact
-            try:
-                return self._forward_train(z, pos, g, getattr(batch_data, "node_feature", None))
-            finally:
-                ag.EXACT_BACKWARD[0] = False
+            nf = getattr(batch_data, "node_feature", None)
+            if (self.training and torch.is_grad_enabled() and pos.requires_grad
+                    and any(p.requires_grad for p in self.parameters())):
+                # training ON forces (run.py:110-123): grad(out, pos, create_graph=True) must stay differentiable in the
+                # parameters -- reverse over forward mode, dig_b200/autograd_jvp.py
+                return jv.energy_with_force(lambda p: self._exact(self._forward_train, z, p, g, nf),
+                                            lambda p, c: self._exact(self._forward_dual, z, p, c, g, nf),
+                                            pos, tuple(self.parameters()))
+            return self._exact(self._forward_train, z, pos, g, nf, exact=bool(pos.requires_grad))
         ops.triplet_geometry(g, pos, use_torsion=self._torsion, want_idx=False)
         rbf0, bess = ops.edge_basis(g.dist, self.cutoff, self.envelope_exponent, self.emb.dist_emb.freq,
                                     self._basis_id, envelope_on_bessel=not self._torsion, num_radial=nr,
@@ -313,6 +318,15 @@ class _DimeNetFamily(nn.Module):
             ops.sphere_update_v_batched(v_in_all, holders, self.out_channels, v_all)
         return ops.graph_readout(v_all, g.graph_ptr, g.n_graphs, g.n_nodes)
 
+
+    @staticmethod
+    def _exact(fn, *args, exact=True):
+        """Run fn with the input-gradient GEMMs of the recorded graph kept exact (graphs that carry forces)."""
+        ag.EXACT_BACKWARD[0] = exact
+        try:
+            return fn(*args)
+        finally:
+            ag.EXACT_BACKWARD[0] = False
 
     # ------------------------------------------------------------------ training path
     def _update_v_train(self, mods, e2_list, g):
@@ -386,6 +400,83 @@ class _DimeNetFamily(nn.Module):
         for l in range(1, v.size(0)):
             u = ag.add(u, ag.segment_sum(v[l], g.graph_ptr, g.batch))
         return u
+
+
+    # ------------------------------------------------------------------ force-training path (tangent network)
+    def _forward_dual(self, z, pos, cvec, g, node_feature=None):
+        """(E, E_dot): the forward of _forward_train carried together with its directional derivative along the per-atom
+        displacement `cvec` [N, 3] (same reference lines, op for op), built on the first-order primitives so that
+        E_dot is differentiable in the parameters.  Positions are data here: geometry, its tangents and the angular
+        bases are constants; the radial basis is differentiable in dist_emb.freq.  See dig_b200/autograd_jvp.py."""
+        ns, nr = self.num_spherical, self.num_radial
+        tors = self._torsion
+        pos = pos.detach()
+        ops.triplet_geometry(g, pos, use_torsion=tors, want_idx=True)
+        d_dot, a_dot, t_dot = ops.geometry_jvp(pos, cvec, g, want_angle=True, want_torsion=tors)
+        dist, angle, tors_angle = g.dist.view(-1), g.angle.view(-1), (g.torsion.view(-1) if tors else None)
+        freq = self.emb.dist_emb.freq
+        cfg = (self.cutoff, self.envelope_exponent, self._basis_id, not tors, nr, ns * nr)
+        rbf0, bess = ag.edge_basis(freq, dist, *cfg)
+        rbf0_d = jv.edge_basis_tangent(freq, dist, d_dot, *cfg)
+        _, bess_d = ops.edge_basis_tangent(dist, d_dot, self.cutoff, self.envelope_exponent, None, self._basis_id,
+                                           not tors, nr, ns * nr, want_rbf0=False, want_bess=True)
+        sbf_d, tbf_d = ops.triplet_basis_tangent(bess, bess_d, angle, a_dot, tors_angle, t_dot, g.idx_kj,
+                                                 self._basis_id, ns, nr, want_tbf=tors)
+        geo_cfg = (self.cutoff, self.envelope_exponent, not tors, dist)
+        L = self.num_layers
+        sbf_ps, t_ps = [], []
+        for first in range(0, L, 4):
+            es = self.update_es[first:first + 4]
+            s_l, t_l = ag.basis_project(g, bess, dist, angle, tors_angle, geo_cfg, self._basis_id, ns, nr,
+                                        [m.lin_sbf1.weight for m in es],
+                                        [m.lin_t1.weight for m in es] if tors else None)
+            sbf_ps += s_l
+            t_ps += t_l if t_l is not None else [None] * len(s_l)
+        lin, lsd, muld, addd = ag.lin, jv.lin_swish_dual, jv.mul_dual, jv.add_dual
+        # init_e (spherenet.py:79-91): the embedding rows carry no tangent
+        ie = self.init_e
+        if ie.use_node_features:
+            x = ag.gather_rows(ie.emb.weight, z)
+        else:
+            x = ag.gather_rows(ie.node_embedding.view(1, -1), torch.zeros_like(z))
+        if self.use_extra_node_feature and node_feature is not None:
+            x = torch.cat([x, lin(self.extra_emb, node_feature.to(torch.float32).contiguous())], dim=1)
+        r0, r0_d = lsd(ie.lin_rbf_0, rbf0, rbf0_d)
+        xi, xj = ag.gather_rows(x, g.dst, g.row_ptr), ag.gather_rows(x, g.src)
+        cat = torch.cat([xi, xj, r0], dim=-1)                                           # copies only
+        cat_d = torch.cat([torch.zeros_like(xi), torch.zeros_like(xj), r0_d], dim=-1)
+        e1, e1_d = lsd(ie.lin, cat, cat_d)
+        e2, e2_d = muld(*jv.lin_dual(ie.lin_rbf_1, rbf0, rbf0_d), e1, e1_d)
+        e2s = [(e2, e2_d)]
+        for l, ue in enumerate(self.update_es):                                        # spherenet.py:150-182
+            x_ji, x_ji_d = lsd(ue.lin_ji, e1, e1_d)
+            x_kj, x_kj_d = lsd(ue.lin_kj, e1, e1_d)
+            rb, rb_d = jv.lin_dual(ue.lin_rbf2, *jv.lin_dual(ue.lin_rbf1, rbf0, rbf0_d))
+            x_kj, x_kj_d = muld(x_kj, x_kj_d, rb, rb_d)
+            x_kj, x_kj_d = lsd(ue.lin_down, x_kj, x_kj_d)
+            s_d = ag.linear(sbf_d, ue.lin_sbf1.weight, None)                            # tangent of lin_sbf1(sbf)
+            t_d = ag.linear(tbf_d, ue.lin_t1.weight, None) if tors else None
+            x_kj, x_kj_d = jv.triplet_gather_dual(x_kj, x_kj_d, sbf_ps[l], s_d, t_ps[l], t_d, ue.lin_sbf2.weight,
+                                                  ue.lin_t2.weight if tors else None, g)
+            x_kj, x_kj_d = lsd(ue.lin_up, x_kj, x_kj_d)
+            h, h_d = addd(x_ji, x_ji_d, x_kj, x_kj_d)
+            for layer in ue.layers_before_skip:
+                h, h_d = addd(h, h_d, *lsd(layer.lin2, *lsd(layer.lin1, h, h_d)))
+            h, h_d = addd(*lsd(ue.lin, h, h_d), e1, e1_d)
+            for layer in ue.layers_after_skip:
+                h, h_d = addd(h, h_d, *lsd(layer.lin2, *lsd(layer.lin1, h, h_d)))
+            e1, e1_d = h, h_d
+            e2s.append(muld(*jv.lin_dual(ue.lin_rbf, rbf0, rbf0_d), e1, e1_d))
+        u = u_d = None
+        for uv, (e2, e2_d) in zip([self.init_v] + list(self.update_vs), e2s):          # spherenet.py:209-216, :316-318
+            v, v_d = jv.segment_sum_dual(e2, e2_d, g.row_ptr, g.dst)
+            v, v_d = jv.lin_dual(uv.lin_up, v, v_d)
+            for m in uv.lins:
+                v, v_d = lsd(m, v, v_d)
+            v, v_d = jv.lin_dual(uv.lin, v, v_d)
+            uu, uu_d = jv.segment_sum_dual(v, v_d, g.graph_ptr, g.batch)
+            u, u_d = (uu, uu_d) if u is None else addd(u, u_d, uu, uu_d)
+        return u, u_d
 
 
 class SphereNet(_DimeNetFamily):

@@ -466,6 +466,25 @@ int dig3d_triplet_basis_project_bwd_geom(const float* bess, const float* bess_dx
                                          void* stream);
 int dig3d_triplet_torsion_bwd(const float* pos, const int32_t* src, const int32_t* dst, const int32_t* row_ptr,
                               const int32_t* trip_ptr, const float* dtorsion, int64_t n_edges, float* dpos, void* stream);
+/* ---- forward-mode (tangent) kernels of the force-TRAINING path (reference run.py:110-123; dig_b200/autograd_jvp.py) ----
+ * d/d(theta) of  c . dE/dpos  (c = d loss / d force, fixed) is the parameter gradient of the directional derivative of E
+ * along c, so the second-order path of DimeNet++ / SphereNet needs only FIRST-order tangents of the geometry and bases:
+ * geometry_jvp: dist_dot[E], angle_dot[T] (NULL: skip), torsion_dot[T] (NULL: skip) along cvec[N,3]; every row written.
+ * edge_basis_tangent: rbf0_dot[E,nr] / bess_dot[E,ns*nr] (either may be NULL) for dist_dot.
+ * rbf_freq_grad_tangent: dfreq[nr] += d(loss)/d(freq) through rbf0_dot given g_dot = d(loss)/d(rbf0_dot).
+ * triplet_basis_tangent: tangents of dig3d_triplet_basis' sbf [T, ns*nr] / tbf [T, ns*ns*nr] (same layouts). */
+int dig3d_geometry_jvp(const float* pos, const float* cvec, const int32_t* src, const int32_t* dst,
+                       const int32_t* row_ptr, const int32_t* trip_ptr, const float* dist, int64_t n_edges,
+                       float* dist_dot, float* angle_dot, float* torsion_dot, void* stream);
+int dig3d_edge_basis_tangent(const float* dist, const float* dist_dot, int64_t n_edges, double cutoff,
+                             int32_t envelope_exponent, const float* freq, int32_t basis_id, int32_t envelope_on_bessel,
+                             float* rbf0_dot, float* bess_dot, void* stream);
+int dig3d_rbf_freq_grad_tangent(const float* dist, const float* dist_dot, int64_t n_edges, double cutoff,
+                                int32_t envelope_exponent, const float* freq, int32_t nr, const float* g_dot,
+                                float* dfreq, void* stream);
+int dig3d_triplet_basis_tangent(const float* bess, const float* bess_dot, const float* angle, const float* angle_dot,
+                                const float* torsion, const float* torsion_dot, const int32_t* idx_kj,
+                                int64_t n_triplets, int32_t basis_id, float* sbf_dot, float* tbf_dot, void* stream);
 int dig3d_schnet_edge_features_bwd(const float* dist, int64_t n_edges, const float* offset, int32_t n_gauss,
                                    double coeff, double cutoff, const float* dgauss, const float* dcut, float* ddist,
                                    void* stream);

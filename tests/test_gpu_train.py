@@ -319,8 +319,8 @@ def test_force_path_parameter_gradients_still_match():
 
 
 def test_run_val_energy_and_force_and_force_training():
-    """run.val with forces (SchNet); run.train ON forces works for SchNet (twice-differentiable Functions) and raises
-    loudly for the models without a second-order path instead of silently dropping the force term."""
+    """run.val with forces; run.train ON forces (run.py:110-123) lowers the loss for SchNet (twice-differentiable
+    Functions, autograd_dd.py) and for DimeNet++ (tangent network, autograd_jvp.py)."""
     from dig_b200.data import DataLoader, synthetic_molecules
     from dig_b200.threedgraph.evaluation import ThreeDEvaluator
     from dig_b200.threedgraph.method import DimeNetPP, SchNet, run
@@ -334,10 +334,15 @@ def test_run_val_energy_and_force_and_force_training():
     losses = [run().train(model, opt, DataLoader(mols, 4, shuffle=False), True, 100, torch.nn.L1Loss(), dev)
               for _ in range(6)]
     assert np.isfinite(losses).all() and losses[-1] < losses[0], losses
-    dpp = DimeNetPP(energy_and_force=True).to(dev)
-    with pytest.raises(NotImplementedError, match="double"):
-        run().train(dpp, torch.optim.Adam(dpp.parameters(), lr=1e-3), DataLoader(mols, 4, shuffle=False), True, 100,
-                    torch.nn.L1Loss(), dev)
+    # DimeNet++ trains on forces too (round 2: tangent network, dig_b200/autograd_jvp.py)
+    torch.manual_seed(0)
+    dpp = DimeNetPP(energy_and_force=True, num_layers=2, hidden_channels=64, out_emb_channels=64).to(dev)
+    opt = torch.optim.Adam(dpp.parameters(), lr=1e-3)
+    losses = [run().train(dpp, opt, DataLoader(mols, 4, shuffle=False), True, 100, torch.nn.L1Loss(), dev)
+              for _ in range(6)]
+    assert np.isfinite(losses).all() and losses[-1] < losses[0], losses
+    mae = run().val(dpp, DataLoader(mols, 4, shuffle=False), True, 100, ThreeDEvaluator(), dev)
+    assert np.isfinite(mae)
 
 
 def test_schnet_force_training_gradients_match_oracle():
@@ -382,6 +387,59 @@ def test_schnet_force_training_gradients_match_oracle():
         if err > 2e-4:
             bad[name] = err
     assert not bad, bad
+
+
+@pytest.mark.parametrize("name", ["dimenetpp_md17", "spherenet_qm9", "spherenet_ns3"])
+def test_dimenet_family_force_training_gradients_match_oracle(name):
+    """d/d(parameters) of  L1(E, y) + 100 * L1(F, f),  F = -dE/dpos under create_graph=True
+    (reference run.py:110-123), for DimeNet++ and SphereNet.  The product differentiates the directional derivative of E
+    along c = dL/dF (reverse over forward mode, dig_b200/autograd_jvp.py: geometry_jvp, edge_basis_tangent,
+    triplet_basis_tangent, act''); the comparator is torch.autograd's double backward over the oracle restatement on the
+    same GPU.  Every parameter tensor is compared (2e-4 of its largest entry)."""
+    from dig_b200.threedgraph import method
+    from helpers import CASES
+    from oracle import restated
+    dev = torch.device("cuda:0")
+    model_name, ctor, _, wseed = CASES[name]
+    _, z, pos, batch = case_inputs(name, dev)
+    model = getattr(method, model_name)(energy_and_force=True, **ctor)
+    sd = formula_state_dict(model.state_dict(), seed=wseed)
+    model.load_state_dict(sd)
+    model = model.to(dev)
+    n_mol = int(batch.max()) + 1
+    gen = torch.Generator().manual_seed(21)
+    y = torch.randn(n_mol, 1, generator=gen).to(dev)
+    f_t = torch.randn(pos.size(0), 3, generator=gen).to(dev)
+
+    def total_loss(energy, position):
+        force = -torch.autograd.grad(energy, position, grad_outputs=torch.ones_like(energy), create_graph=True,
+                                     retain_graph=True)[0]
+        return torch.nn.functional.l1_loss(energy, y) + 100.0 * torch.nn.functional.l1_loss(force, f_t), force
+
+    b = _batch(z, pos.clone(), batch)
+    out = model(b)
+    loss, force = total_loss(out, b.pos)
+    assert force.requires_grad, "the force must stay differentiable in the parameters"
+    loss.backward()
+    sd_ref = {k: v.to(dev).clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    pos2 = pos.clone().requires_grad_(True)
+    kw = {k: v for k, v in ctor.items() if k in ("cutoff", "num_layers", "num_spherical", "num_radial")}
+    ref = restated.dimenet_family_forward(sd_ref, z, pos2, batch, torsion=(model_name == "SphereNet"), **kw)
+    ref_loss, ref_force = total_loss(ref, pos2)
+    ref_loss.backward()
+    assert rel_err(force.detach().cpu().numpy(), ref_force.detach().cpu().numpy()) < FTOL
+    assert abs(loss.item() - ref_loss.item()) < 1e-5 * abs(ref_loss.item())
+    bad, checked = {}, 0
+    for pname, prm in model.named_parameters():
+        r = sd_ref[pname].grad
+        if r is None:
+            continue
+        assert prm.grad is not None, pname
+        checked += 1
+        err = rel_err(prm.grad.cpu().numpy(), r.cpu().numpy())
+        if err > 2e-4:
+            bad[pname] = err
+    assert checked > 50 and not bad, (checked, bad)
 
 
 @pytest.mark.parametrize("name", ["spherenet_qm9", "spherenet_ns3"])
@@ -589,6 +647,44 @@ def test_node_centred_triplet_gather_equals_edge_centred():
             outs.append(m)
         ops.GATHER_MODE[0] = "node"
         assert torch.isfinite(outs[1]).all() and torch.equal(outs[0], outs[1]), tors
+
+
+def test_tensor_core_triplet_gather_matches_the_exact_one():
+    """ops.GATHER_MODE 'tc' (lin_sbf2 / lin_t2 expansions as 3xFP16 tcgen05 MMAs, out-edges packed into 128-row tiles)
+    against the exact FP32 'node' kernel on the same inputs: fp32-level agreement (the operand split keeps ~22 bits),
+    every edge written, with and without torsion, incl. an isolated atom and the 128-molecule headline batch."""
+    import ctypes
+    from dig_b200 import ops
+    from dig_b200.data import synthetic_batch, collate, Molecule
+    dev = torch.device("cuda:0")
+    mols = synthetic_batch(9, "qm9", seed=4, variable=True)
+    far = torch.tensor([[50.0, 50.0, 50.0]])
+    small = collate([Molecule(mols.z[:7], mols.pos[:7]), Molecule(torch.tensor([6]), far),
+                     Molecule(mols.z[7:40], mols.pos[7:40])]).to(dev)
+    big = synthetic_batch(128, "qm9", seed=5).to(dev)
+    for b, ng in ((small, 3), (big, 128)):
+        g = ops.build_graph(b.pos, b.batch, 5.0, num_graphs=ng)
+        ops.triplet_geometry(g, b.pos, use_torsion=True, want_idx=False)
+        e, t = g.n_edges, g.n_triplets
+        torch.manual_seed(1)
+        x_down = torch.randn(e, 64, device=dev)
+        sbf_p, t_p = torch.randn(t, 8, device=dev), torch.randn(t, 8, device=dev)
+        w_s, w_t = torch.randn(64, 8, device=dev) * 0.3, torch.randn(64, 8, device=dev) * 0.3
+        for tors in (True, False):
+            outs = []
+            for mode in ("node", "tc"):
+                ops.GATHER_MODE[0] = mode
+                m = torch.full((e, 64), float("nan"), device=dev)
+                ops.triplet_gather(x_down, ctypes.c_void_p(sbf_p.data_ptr()),
+                                   ctypes.c_void_p(t_p.data_ptr()) if tors else None, g,
+                                   w_s.data_ptr(), w_t.data_ptr() if tors else None, m, ops._stream())
+                outs.append(m)
+            ops.GATHER_MODE[0] = "node"
+            torch.cuda.synchronize()
+            assert ops.tc_timeouts() == 0
+            assert torch.isfinite(outs[1]).all(), (ng, tors)
+            err = (outs[1] - outs[0]).abs().max().item() / outs[0].abs().max().item()
+            assert err < 2e-6, (ng, tors, err)
 
 
 def test_training_step_parity_at_the_headline_size():
