@@ -289,6 +289,7 @@ def other_configs(dev):
             if forces:
                 fmodel = make(True).to(dev)
                 fmodel.load_state_dict(model.state_dict())
+                fmodel.eval()
 
                 def ef():
                     b.pos.grad = None
@@ -296,6 +297,23 @@ def other_configs(dev):
                     return torch.autograd.grad(o, b.pos, grad_outputs=torch.ones_like(o))[0]
                 ms = time_ms(torch, ef, n=5)
                 rec["energy_and_force"] = {"ms_per_step": round(ms, 4), "molecules_per_s": round(nmol / (ms * 1e-3), 1)}
+                # training ON forces (reference run.py:110-123): loss = L1(E) + 100 L1(F), F = -dE/dpos under create_graph
+                fmodel.train()
+                fopt = torch.optim.Adam(fmodel.parameters(), lr=5e-4)
+                f_t = torch.randn(b.pos.size(0), 3, device=dev)
+
+                def ftrain():
+                    fopt.zero_grad()
+                    b.pos.grad = None
+                    o = fmodel(b)
+                    force = -torch.autograd.grad(o, b.pos, grad_outputs=torch.ones_like(o), create_graph=True,
+                                                 retain_graph=True)[0]
+                    loss = torch.nn.functional.l1_loss(o, y) + 100.0 * torch.nn.functional.l1_loss(force, f_t)
+                    loss.backward()
+                    fopt.step()
+                ms = time_ms(torch, ftrain, n=3)
+                rec["force_train_step"] = {"ms_per_step": round(ms, 4), "molecules_per_s": round(nmol / (ms * 1e-3), 1),
+                                           "what": "energy + force loss, second-order path (tangent network)"}
                 b.pos.requires_grad_(False)
         except Exception as exc:                      # reported, never hidden
             rec["error"] = f"{type(exc).__name__}: {exc}"

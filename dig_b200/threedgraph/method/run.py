@@ -124,8 +124,9 @@ class run():
                 if not force.requires_grad:
                     raise NotImplementedError(
                         "run.train(energy_and_force=True): the force loss needs d(force)/d(parameters), i.e. a double "
-                        "backward through the model; the dig_b200 backward kernels are first order only (forces are "
-                        "available for inference / run.val) -- training on forces would silently ignore the force term")
+                        "backward through the model; this model has no second-order path (SchNet: autograd_dd.py, "
+                        "DimeNet++ / SphereNet: autograd_jvp.py) -- training on forces would silently ignore the force "
+                        "term")
                 e_loss = loss_func(out, batch_data.y.unsqueeze(1))
                 f_loss = loss_func(force, batch_data.force)
                 loss = e_loss + p * f_loss
