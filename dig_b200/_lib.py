@@ -116,6 +116,10 @@ SIGNATURES = {
                             POINTER(ComenetHeadWeights), c_int32, P, P, P, P, P, P, P, P],
     "dig3d_linear": [P, c_int64, c_int32, c_int32, P, P, P, P, c_int32, P],
     "dig3d_wgrad": [P, P, c_int64, c_int32, c_int32, P, P, c_int32, P],
+    "dig3d_wgrad_tc": [P, P, c_int64, c_int32, c_int32, P, P, c_int32, P],
+    "dig3d_wgrad_tc_supported": [c_int64, c_int32, c_int32],
+    "dig3d_wgrad_set_mode": [c_int32],
+    "dig3d_wgrad_tc_timeouts": [],
     "dig3d_act": [P, c_int64, c_int32, P, P],
     "dig3d_act_bwd": [P, P, c_int64, c_int32, P, P],
     "dig3d_adam_step": [P, P, P, P, c_int64, c_double, c_double, c_double, c_double, c_double, c_int64, P],

@@ -440,6 +440,8 @@ int dig3d_wgrad(const float* dy, const float* x, int64_t rows, int32_t nout, int
                 int32_t groups, void* stream) {
   DIG3D_REQUIRE(dy && x && dw && nout > 0 && k > 0 && groups >= 1 && groups <= 64, "wgrad: bad arguments");
   if (rows == 0) return DIG3D_OK;
+  if (dig3d_wgrad_tc_supported(rows, nout, k))         // tcgen05 3xTF32 (train_tc.cu) where the tile shape pays
+    return dig3d_wgrad_tc(dy, x, rows, nout, k, dw, db, groups, stream);
   cudaStream_t st = (cudaStream_t)stream;
   if (nout > 16 && k > 16) launch_wgrad<64, 64>(dy, x, rows, nout, k, dw, db, groups, st);
   else if (nout > 16) launch_wgrad<64, 16>(dy, x, rows, nout, k, dw, db, groups, st);

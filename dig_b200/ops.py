@@ -611,7 +611,12 @@ def tc_timeouts():
     """mbarrier waits that timed out in the tensor-core kernels (they trap, so a non-zero count is only ever seen
     together with a failed launch)."""
     lib = _lib.load()
-    return lib.dig3d_tc_timeouts() + lib.dig3d_h16_timeouts()
+    return lib.dig3d_tc_timeouts() + lib.dig3d_h16_timeouts() + lib.dig3d_wgrad_tc_timeouts()
+
+
+def wgrad_set_mode(tensor_cores):
+    """True (default): weight gradients of >= 64-wide layers on tcgen05 (3xTF32, csrc/train_tc.cu); False: FFMA kernel."""
+    _lib.load().dig3d_wgrad_set_mode(1 if tensor_cores else 0)
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -18,6 +18,7 @@ from torch.optim.lr_scheduler import StepLR
 
 from ... import parallel
 from ...data import DataLoader
+from ...pipeline import InferencePipeline
 
 try:                       # progress bars are optional plumbing (reference run.py:10)
     from tqdm import tqdm
@@ -146,6 +147,19 @@ class run():
         step); values are identical."""
         model.eval()
         preds, targets, preds_force, targets_force = [], [], [], []
+        if not energy_and_force and torch.device(device).type == "cuda":
+            # two batches in flight (dig_b200/pipeline.py): the copy, graph kernels and count readback of batch n+1
+            # overlap the interaction blocks of batch n; values identical to the plain loop below
+            pipe = InferencePipeline(model, device, depth=2)
+
+            def feed():
+                for batch_data in tqdm(data_loader):
+                    targets.append(batch_data.y.unsqueeze(1))
+                    yield batch_data
+            for out in pipe.map(feed()):
+                preds.append(out.clone())
+            input_dict = {"y_true": torch.cat(targets, dim=0).to(device), "y_pred": torch.cat(preds, dim=0).to(device)}
+            return evaluation.eval(input_dict)['mae']
         for step, batch_data in enumerate(tqdm(data_loader)):
             batch_data = batch_data.to(device)
             if energy_and_force:

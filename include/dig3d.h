@@ -395,6 +395,14 @@ int dig3d_linear(const float* x, int64_t rows, int32_t k, int32_t nout, const fl
                  float* act_out /* nullable: also receives swish(y) */, int32_t groups, void* stream);
 int dig3d_wgrad(const float* dy, const float* x, int64_t rows, int32_t nout, int32_t k, float* dw, float* db,
                 int32_t groups, void* stream);
+/* The same contract on the tensor cores (csrc/train_tc.cu): 3xTF32 tcgen05 with the transposed operand tiles built on
+ * the fly, four rotating TMEM accumulators, coalesced red.global of the partial tiles.  dig3d_wgrad routes here when
+ * dig3d_wgrad_tc_supported (nout >= 64, k >= 64, rows >= 1024 and mode 1); dig3d_wgrad_set_mode(0) forces the FFMA kernel. */
+int dig3d_wgrad_tc(const float* dy, const float* x, int64_t rows, int32_t nout, int32_t k, float* dw, float* db,
+                   int32_t groups, void* stream);
+int dig3d_wgrad_tc_supported(int64_t rows, int32_t nout, int32_t k);
+int dig3d_wgrad_set_mode(int32_t mode);
+int dig3d_wgrad_tc_timeouts(void);
 /* tile configuration of the 128 -> 128 linear (tuning / experiments): 0 = 64-row tiles, 1 = 64-row tiles with two CTAs
  * per SM (default), 2 = 128-row tiles */
 int dig3d_linear_set_config(int32_t cfg);

@@ -759,3 +759,37 @@ def test_linear_on_the_two_tile_engine_matches_fp64(k, nout):
         y2 = ops.linear_h16(x, w, b)
         assert rel_err(y2.cpu().numpy(), (x.double() @ w.detach().double().t() + b.double()).cpu().numpy()) < 2e-6
     assert ops.tc_timeouts() == 0 and not ops.h16_overflow()
+
+
+@pytest.mark.parametrize("rows,nout,k,groups", [(39000, 128, 128, 1), (5000, 128, 384, 1), (4097, 64, 128, 1),
+                                                (1031, 128, 64, 1), (2304, 256, 256, 5), (2304, 256, 128, 5),
+                                                (20000, 100, 72, 1)])
+def test_weight_gradient_on_the_tensor_cores_matches_fp64(rows, nout, k, groups):
+    """dig3d_wgrad_tc (3xTF32 tcgen05, transposed operand tiles built on the fly, csrc/train_tc.cu) vs fp64 and vs the
+    FFMA kernel: dW = dY^T X and db = colsum dY, ragged row counts and widths, wide dynamic range of dY, grouped."""
+    from dig_b200 import ops
+    dev = torch.device("cuda:0")
+    torch.manual_seed(rows + nout + k)
+    lead = (groups,) if groups > 1 else ()
+    x = torch.randn(lead + (rows, k), device=dev)
+    dy = torch.randn(lead + (rows, nout), device=dev) * torch.logspace(-9, 0, nout, device=dev)   # gradient-like range
+    shape = lead + (nout, k)
+    assert ops._lib.load().dig3d_wgrad_tc_supported(rows, nout, k) == 1
+    dw, db = ops.wgrad(dy, x, shape, True)
+    ops.wgrad_set_mode(False)
+    try:
+        dw_s, db_s = ops.wgrad(dy, x, shape, True)
+    finally:
+        ops.wgrad_set_mode(True)
+    ref = dy.double().transpose(-1, -2) @ x.double()
+    ref_b = dy.double().sum(-2)
+    torch.cuda.synchronize()
+    assert ops.tc_timeouts() == 0
+    # column-wise comparison: every output row n has its own scale (1e-9 .. 1)
+    scale = ref.abs().amax(-1, keepdim=True)
+    err = ((dw.double() - ref).abs() / scale).max().item()
+    err_s = ((dw_s.double() - ref).abs() / scale).max().item()
+    assert err < 5e-6, (err, err_s)
+    col_scale = dy.double().abs().sum(-2)             # a column sum may cancel: compare against the sum of magnitudes
+    assert ((db.double() - ref_b).abs() / col_scale).max().item() < 1e-6
+    assert rel_err(db.cpu().numpy(), db_s.cpu().numpy()) < 1e-5
