@@ -414,7 +414,8 @@ def main():
     # the same loop with two batches in flight (dig_b200.pipeline.InferencePipeline, what run.val does): every step still
     # copies its inputs from pinned host memory and its energies are still read on the host, one step later
     from dig_b200.pipeline import InferencePipeline
-    depth = max(1, int(os.environ.get("DIG3D_BENCH_STREAMS", "2")))
+    from dig_b200.pipeline import DEFAULT_DEPTH
+    depth = max(1, int(os.environ.get("DIG3D_BENCH_STREAMS", str(DEFAULT_DEPTH))))
     pipe = InferencePipeline(model, dev, depth=depth)
     pipe_r = InferencePipeline(model, dev, depth=depth)
     pending, pending_r = [], []
@@ -443,9 +444,9 @@ def main():
     for s in range(args.warmup):
         step_resident(s)
         step_e2e(s)
-    for s in list(range(max(args.warmup, 3))) + [args.steps - 1]:
+    for s in list(range(max(args.warmup, 3) + 2 * depth)) + [args.steps - 1]:
         step_e2e_pipelined(s)                            # warm the side streams' allocator pools; the last call flushes
-    for s in list(range(max(args.warmup, 3))) + [args.steps - 1]:
+    for s in list(range(max(args.warmup, 3) + 2 * depth)) + [args.steps - 1]:
         step_resident_pipelined(s)
     sampler = ClockSampler(local)
     if rank == 0:

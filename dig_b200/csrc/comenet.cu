@@ -458,6 +458,73 @@ static int smem_attr(K kernel, size_t bytes) {
   return DIG3D_OK;
 }
 
+// ---------------------------------------------------------------------------------- EdgeGraphConv aggregation
+// agg[i][c] = sum_{e = (j -> i)} w[e][c] * x[j][c]       (comenet.py:66-73: message x_j * edge_weight, aggr = 'add')
+// for the tensor-engine forward (ComENet._forward_h16): w = lin_feature(feat) comes out of a GEMM on the dense engine as an
+// [E, W] matrix; one warp per target node streams its (contiguous, CSR-sorted) rows of w and gathers the source rows of x
+// from L2; lanes own float4 columns, the sum stays in registers, one coalesced row store.  No atomics, no zero fill.
+template <int W4>
+__global__ void __launch_bounds__(256)
+edge_weighted_sum_kernel(const float* __restrict__ w, const float* __restrict__ x, const int32_t* __restrict__ src,
+                         const int32_t* __restrict__ row_ptr, int n_nodes, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= n_nodes) return;
+  constexpr int PER = W4 / 32;                      // float4 columns per lane
+  float4 acc[PER];
+#pragma unroll
+  for (int p = 0; p < PER; ++p) acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int e0 = row_ptr[i], e1 = row_ptr[i + 1];
+  for (int e = e0; e < e1; ++e) {
+    const float4* wr = reinterpret_cast<const float4*>(w + (size_t)e * (W4 * 4));
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)__ldg(src + e) * (W4 * 4));
+#pragma unroll
+    for (int p = 0; p < PER; ++p) {
+      const float4 a = __ldg(wr + lane + 32 * p), b = __ldg(xr + lane + 32 * p);
+      acc[p].x = fmaf(a.x, b.x, acc[p].x); acc[p].y = fmaf(a.y, b.y, acc[p].y);
+      acc[p].z = fmaf(a.z, b.z, acc[p].z); acc[p].w = fmaf(a.w, b.w, acc[p].w);
+    }
+  }
+  float4* o = reinterpret_cast<float4*>(out + (size_t)i * (W4 * 4));
+#pragma unroll
+  for (int p = 0; p < PER; ++p) o[lane + 32 * p] = acc[p];
+}
+
+// The same aggregation with the edge filter folded in: TwoLayerLinear(bias=False, act=False) is ONE linear map
+// W_eff = W2 W1 [W, Q] (comenet.py:87-112 without bias / activation), so
+//   agg[i][c] = sum_{e=(j->i)} ( sum_q W_eff[c][q] feat[e][q] ) * x[j][c]
+// costs Q + 1 FMAs per edge and channel instead of 64 + 1 and never materialises an [E, W] filter.  weff_t = W_eff^T
+// [Q, W] (host side: one tiny GEMM per parameter version).  One warp per (node, 128-channel half): a lane keeps its four
+// channels' Q filter coefficients in registers, streams the node's CSR rows of feat (broadcast loads) and gathers x rows.
+template <int Q>
+__global__ void __launch_bounds__(256)
+comenet_filter_sum_kernel(const float* __restrict__ feat, const float* __restrict__ weff_t, const float* __restrict__ x,
+                          const int32_t* __restrict__ src, const int32_t* __restrict__ row_ptr, int n_nodes, int width,
+                          float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int halves = width / 128;
+  const int i = wid / halves, c0 = (wid % halves) * 128 + lane * 4;
+  if (i >= n_nodes) return;
+  float4 wq[Q];
+#pragma unroll
+  for (int q = 0; q < Q; ++q) wq[q] = __ldg(reinterpret_cast<const float4*>(weff_t + (size_t)q * width + c0));
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int e0 = row_ptr[i], e1 = row_ptr[i + 1];
+  for (int e = e0; e < e1; ++e) {
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (size_t)__ldg(src + e) * width + c0));
+    const float* f = feat + (size_t)e * Q;
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const float fq = __ldg(f + q);
+      w.x = fmaf(wq[q].x, fq, w.x); w.y = fmaf(wq[q].y, fq, w.y); w.z = fmaf(wq[q].z, fq, w.z); w.w = fmaf(wq[q].w, fq, w.w);
+    }
+    acc.x = fmaf(w.x, xv.x, acc.x); acc.y = fmaf(w.y, xv.y, acc.y); acc.z = fmaf(w.z, xv.z, acc.z); acc.w = fmaf(w.w, xv.w, acc.w);
+  }
+  *reinterpret_cast<float4*>(out + (size_t)i * width + c0) = acc;
+}
+
 }  // namespace dig3d
 
 using namespace dig3d;
@@ -567,6 +634,35 @@ int dig3d_comenet_block(const float* x_in, const float* feature1, const float* f
   DIG3D_LAUNCH_CHECK();
   comenet_norm_final_kernel<<<ngrid, DT, sizeof(NodeSmem2), st>>>(h, batch, (int)n_nodes, shift, stdv, *w, *head,
                                                                 out_channels, x_out, node_out);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_edge_weighted_sum(const float* w, const float* x, const int32_t* src, const int32_t* row_ptr, int64_t n_nodes,
+                            int32_t width, float* out, void* stream) {
+  DIG3D_REQUIRE(w && x && src && row_ptr && out, "edge_weighted_sum: null pointer");
+  DIG3D_REQUIRE(width == 128 || width == 256, "edge_weighted_sum: width %d is not compiled (128, 256)", width);
+  DIG3D_REQUIRE((((uintptr_t)w | (uintptr_t)x | (uintptr_t)out) & 15) == 0, "edge_weighted_sum: 16-byte alignment");
+  if (n_nodes == 0) return DIG3D_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ceil_div(n_nodes * 32, 256);
+  if (width == 256) edge_weighted_sum_kernel<64><<<grid, 256, 0, st>>>(w, x, src, row_ptr, (int)n_nodes, out);
+  else edge_weighted_sum_kernel<32><<<grid, 256, 0, st>>>(w, x, src, row_ptr, (int)n_nodes, out);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_comenet_filter_sum(const float* feat, int32_t q, const float* weff_t, const float* x, const int32_t* src,
+                             const int32_t* row_ptr, int64_t n_nodes, int32_t width, float* out, void* stream) {
+  DIG3D_REQUIRE(feat && weff_t && x && src && row_ptr && out, "comenet_filter_sum: null pointer");
+  DIG3D_REQUIRE(width % 128 == 0 && width >= 128 && width <= 1024, "comenet_filter_sum: width %d must be a multiple of 128", width);
+  DIG3D_REQUIRE(q == 12 || q == 6, "comenet_filter_sum: feature width %d is not compiled (12 = num_radial*num_spherical^2, 6)", q);
+  DIG3D_REQUIRE((((uintptr_t)weff_t | (uintptr_t)x | (uintptr_t)out) & 15) == 0, "comenet_filter_sum: 16-byte alignment");
+  if (n_nodes == 0) return DIG3D_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ceil_div(n_nodes * (width / 128) * 32, 256);
+  if (q == 12) comenet_filter_sum_kernel<12><<<grid, 256, 0, st>>>(feat, weff_t, x, src, row_ptr, (int)n_nodes, width, out);
+  else comenet_filter_sum_kernel<6><<<grid, 256, 0, st>>>(feat, weff_t, x, src, row_ptr, (int)n_nodes, width, out);
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
 }

@@ -403,6 +403,25 @@ def comenet_block(x, f1, f2, g, w, head, out_channels, last):
     return node_out if last else x_out
 
 
+def edge_weighted_sum(w, x, g):
+    """agg[i] = sum_{e=(j->i)} w[e] * x[j]  (EdgeGraphConv, comenet.py:66-73); w [E, W] in the graph's CSR edge order."""
+    out = torch.empty(g.n_nodes, x.size(1), dtype=torch.float32, device=x.device)
+    if g.n_nodes:
+        call("dig3d_edge_weighted_sum", _p(w, torch.float32, "w", 16), _p(x, torch.float32, "x", 16), _p(g.src),
+             _p(g.row_ptr), g.n_nodes, x.size(1), _p(out, align=16), _stream())
+    return out
+
+
+def comenet_filter_sum(feat, weff_t, x, g):
+    """agg[i] = sum_{e=(j->i)} (feat[e] @ weff_t) * x[j]: EdgeGraphConv aggregation with the TwoLayerLinear filter folded
+    into one [Q, W] matrix (comenet.py:66-73, :87-112)."""
+    out = torch.empty(g.n_nodes, x.size(1), dtype=torch.float32, device=x.device)
+    if g.n_nodes:
+        call("dig3d_comenet_filter_sum", _p(feat, torch.float32, "feat"), feat.size(1), _p(weff_t, torch.float32, "weff_t", 16),
+             _p(x, torch.float32, "x", 16), _p(g.src), _p(g.row_ptr), g.n_nodes, x.size(1), _p(out, align=16), _stream())
+    return out
+
+
 # ----------------------------------------------------------------------------- tcgen05 update_e
 _TC_MATS = ("lin_ji", "lin_kj", "lin_down", "lin_up", "lin")
 

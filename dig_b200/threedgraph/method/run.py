@@ -148,9 +148,9 @@ class run():
         model.eval()
         preds, targets, preds_force, targets_force = [], [], [], []
         if not energy_and_force and torch.device(device).type == "cuda":
-            # two batches in flight (dig_b200/pipeline.py): the copy, graph kernels and count readback of batch n+1
+            # several batches in flight (dig_b200/pipeline.py): the copy, graph kernels and count readback of batch n+1
             # overlap the interaction blocks of batch n; values identical to the plain loop below
-            pipe = InferencePipeline(model, device, depth=2)
+            pipe = InferencePipeline(model, device)
 
             def feed():
                 for batch_data in tqdm(data_loader):

@@ -377,6 +377,14 @@ int dig3d_comenet_block(const float* x_in, const float* feature1, const float* f
                         int64_t n_edges, int64_t n_graphs, const dig3d_comenet_block_weights* w,
                         const dig3d_comenet_head_weights* head, int32_t out_channels, float* xs, float* agg1,
                         float* agg2, float* h, float* stats, float* x_out, float* node_out, void* stream);
+/* EdgeGraphConv aggregation for the tensor-engine forward: agg[i] = sum over the in-edges e = (j -> i) of w[e] * x[j]
+ * (comenet.py:66-73), w [E, width] in CSR (target-sorted) edge order, width 128 or 256; every row of agg is written. */
+int dig3d_edge_weighted_sum(const float* w, const float* x, const int32_t* src, const int32_t* row_ptr, int64_t n_nodes,
+                            int32_t width, float* out, void* stream);
+/* The same with the bias-free, activation-free TwoLayerLinear edge filter folded in (W_eff = W2 W1, weff_t = W_eff^T
+ * [q, width]): agg[i][c] = sum_e (sum_q weff_t[q][c] feat[e][q]) * x[src e][c]; q = 12 or 6; every row written. */
+int dig3d_comenet_filter_sum(const float* feat, int32_t q, const float* weff_t, const float* x, const int32_t* src,
+                             const int32_t* row_ptr, int64_t n_nodes, int32_t width, float* out, void* stream);
 
 /* ------------------------------------------------------------------ training primitives (csrc/train_ops.cu)
  * Forward/backward building blocks of the training path (reference run.py:103-135 = forward + loss.backward();

@@ -247,6 +247,52 @@ def test_comenet_energy_parity():
     # and the oracle's op sequence executed on this GPU is the checker above.
 
 
+def test_comenet_engine_forward_and_its_edge_kernels():
+    """ComENet inference on the tensor engine (linear_h16 for every hidden x hidden linear, folded edge filter,
+    ComENet._forward_h16) vs round 1's exact-fp32 fused block kernel (DIG3D_COMENET_DENSE=simt) and vs the oracle, at the
+    BASELINE configs[3] size; and the two aggregation kernels against their definitions in fp64."""
+    import os
+    from dig_b200 import ops
+    from dig_b200.data import synthetic_batch
+    from dig_b200.threedgraph.method import ComENet
+    from oracle import restated
+    dev = torch.device("cuda:0")
+    model = ComENet(cutoff=6.0)
+    sd = formula_state_dict(model.state_dict(), seed=9)
+    model.load_state_dict(sd)
+    model = model.to(dev)
+    b = synthetic_batch(64, "oc20-is2re", seed=4).to(dev)
+    outs = {}
+    try:
+        for mode in ("h16", "simt"):
+            os.environ["DIG3D_COMENET_DENSE"] = mode
+            with torch.no_grad():
+                outs[mode] = model(b)
+    finally:
+        os.environ.pop("DIG3D_COMENET_DENSE", None)
+    with torch.no_grad():
+        ref = restated.comenet_forward({k: v.to(dev) for k, v in sd.items()}, b.z, b.pos, b.batch, cutoff=6.0)
+    torch.cuda.synchronize()
+    assert ops.tc_timeouts() == 0 and not ops.h16_overflow()
+    assert rel_err(outs["simt"].cpu().numpy(), ref.cpu().numpy()) < TOL
+    assert rel_err(outs["h16"].cpu().numpy(), ref.cpu().numpy()) < TOL
+    # kernel level
+    g = ops.build_graph(b.pos, b.batch, 6.0, num_graphs=64, want_edge_index=False)
+    f1, f2, _ = ops.comenet_geometry(g, b.pos, 6.0)
+    torch.manual_seed(3)
+    x = torch.randn(g.n_nodes, 256, device=dev)
+    blk = model.interaction_blocks[1]
+    src = g.src.long()
+    dst = g.dst.long()
+    for lf, feat in ((blk.lin_feature1, f1), (blk.lin_feature2, f2)):
+        w_ref = (feat.double() @ lf.lin1.weight.double().t()) @ lf.lin2.weight.double().t()          # [E, 256]
+        agg_ref = torch.zeros(g.n_nodes, 256, device=dev, dtype=torch.float64).index_add_(0, dst, w_ref * x.double()[src])
+        agg = ops.comenet_filter_sum(feat, model._filter_t(lf), x, g)
+        assert rel_err(agg.cpu().numpy(), agg_ref.cpu().numpy()) < 2e-6
+        agg2 = ops.edge_weighted_sum(w_ref.float().contiguous(), x, g)
+        assert rel_err(agg2.cpu().numpy(), agg_ref.cpu().numpy()) < 2e-6
+
+
 def test_xyz_to_dat_api_matches_reference_outputs():
     """The utility API with the reference's signature (utils/geometric_computing.py:12) vs the fixture
     written by the real reference and vs the notebook known-answer."""
