@@ -265,7 +265,7 @@ def other_configs(dev):
                 fl = None
                 if name.startswith("cfg4"):          # ComENet: 1.70 MFLOP/node + 68.8 kFLOP/edge per block, 4 blocks
                     fl = 4 * (N_ * 1.70e6 + E_ * 68.8e3)
-                    kind = "fp32 FFMA (fused block kernels, no tensor cores yet)"
+                    kind = "tcgen05 3xFP16 engine for the hidden x hidden linears (dig3d_linear_h16) + FP32 edge-filter aggregation"
                 elif name.startswith("cfg3"):        # DimeNet++: 331 kFLOP/edge + 2.8 kFLOP/triplet per block + node MLPs
                     _ops.triplet_geometry(gg, b.pos, use_torsion=False, want_idx=False)
                     fl = 4 * (E_ * 331e3 + gg.n_triplets * 2.8e3) + 5 * N_ * 459e3

@@ -113,9 +113,9 @@ SIGNATURES = {
     "dig3d_pbc_edge_vectors": [P, P, P, P, P, c_int64, P, P, P],
     "dig3d_comenet_geometry_edges": [P, P, P, P, P, c_int64, c_int64, c_double, P, P, P, P, P, P],
     "dig3d_comenet_block": [P, P, P, P, P, P, P, c_int64, c_int64, c_int64, POINTER(ComenetBlockWeights),
+                            POINTER(ComenetHeadWeights), c_int32, P, P, P, P, P, P, P, P],
     "dig3d_edge_weighted_sum": [P, P, P, P, c_int64, c_int32, P, P],
     "dig3d_comenet_filter_sum": [P, c_int32, P, P, P, P, c_int64, c_int32, P, P],
-                            POINTER(ComenetHeadWeights), c_int32, P, P, P, P, P, P, P, P],
     "dig3d_linear": [P, c_int64, c_int32, c_int32, P, P, P, P, c_int32, P],
     "dig3d_wgrad": [P, P, c_int64, c_int32, c_int32, P, P, c_int32, P],
     "dig3d_wgrad_tc": [P, P, c_int64, c_int32, c_int32, P, P, c_int32, P],

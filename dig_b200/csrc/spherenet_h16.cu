@@ -930,12 +930,24 @@ struct HLinParams { HGemm g[3]; };
 template <int NPANEL, int KU, int N>
 __global__ void __launch_bounds__(H_THREADS, 1)
 linear_h16_kernel(const float* __restrict__ x, int n_rows, int ldx, HLinParams P, const float* __restrict__ bias,
-                  float* __restrict__ y, float* __restrict__ act_out, int ldy) {
+                  float* __restrict__ y, float* __restrict__ act_out, int ldy, int tiles_per_cta, int slice_bytes) {
   extern __shared__ __align__(1024) unsigned char h_raw[];
   HSmem& s = *reinterpret_cast<HSmem*>(h_raw);
   constexpr int NC = N / 2;                                // columns per epilogue thread
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int n_tiles = (n_rows + H_M - 1) / H_M, tile0 = blockIdx.x * 2, ntile = min(2, n_tiles - tile0);
+  // blockIdx.y = 128-column slice of a wider layer (all slices of one launch are N wide): its packed weights follow the
+  // previous slice's, its bias / output columns start at N * slice.  Small row counts run ONE tile per CTA so that the
+  // launch spreads over more SMs (a 4.7 k-row, 256-wide layer is 74 CTAs instead of 19 in two serial launches).
+  {
+    const int slice = blockIdx.y;
+#pragma unroll
+    for (int p = 0; p < NPANEL; ++p) P.g[p].w += (size_t)slice * slice_bytes;
+    if (bias) bias += slice * N;
+    y += slice * N;
+    if (act_out) act_out += slice * N;
+  }
+  const int n_tiles = (n_rows + H_M - 1) / H_M, tile0 = blockIdx.x * tiles_per_cta;
+  const int ntile = min(tiles_per_cta, n_tiles - tile0);
   h_setup(s);
   for (int i = tid; i < N; i += H_THREADS) s.bias[0][i] = bias ? __ldg(bias + i) : 0.f;
   tc_fence_before();
@@ -1214,15 +1226,20 @@ sphere_triplet_gather_tc_kernel(const float* __restrict__ x_down, const float* _
 static int h_smem_attr(const void* fn);
 template <int NPANEL, int KU, int N>
 static int launch_linear_h16(const float* x, int64_t rows, int ldx, const unsigned char* packed, const float* bias,
-                             float* y, float* act_out, int ldy, cudaStream_t st) {
+                             float* y, float* act_out, int ldy, int slices, cudaStream_t st) {
   HLinParams P;
   const size_t panel = (size_t)(KU / 4) * 2 * 4 * N * 16;      // KU/4 slabs of [hi|lo][4][N][8 halves]
   for (int p = 0; p < NPANEL; ++p) P.g[p] = {packed + p * panel, nullptr, KU * 8, N};
   auto kfn = linear_h16_kernel<NPANEL, KU, N>;
   int rc = h_smem_attr((const void*)kfn);
   if (rc) return rc;
-  const int pairs = ceil_div(ceil_div(rows, H_M), 2);
-  kfn<<<pairs, H_THREADS, sizeof(HSmem), st>>>(x, (int)rows, ldx, P, bias, y, act_out, ldy);
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles = ceil_div(rows, H_M);
+  const int tpc = (ceil_div(tiles, 2) * slices < n_sm) ? 1 : 2;        // below one wave of tile pairs: one tile per CTA
+  dim3 grid(ceil_div(tiles, tpc), slices);
+  kfn<<<grid, H_THREADS, sizeof(HSmem), st>>>(x, (int)rows, ldx, P, bias, y, act_out, ldy, tpc, 4 * N * (NPANEL * KU * 8));
   return DIG3D_OK;
 }
 
@@ -1404,22 +1421,25 @@ int dig3d_linear_h16(const float* x, int64_t rows, int32_t k, int32_t nout, cons
   if (rows == 0) return DIG3D_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned char* pw = (const unsigned char*)packed;
-  for (int c0 = 0; c0 < nout; c0 += 128) {
+  // all full 128-column slices in ONE launch (gridDim.y); a trailing 64-column slice gets its own
+  for (int c0 = 0; c0 < nout;) {
     const int n = nout - c0 >= 128 ? 128 : 64;
+    const int slices = n == 128 ? (nout - c0) / 128 : 1;
     const float* b = bias ? bias + c0 : nullptr;
     float* yo = y + c0;
     float* ao = act_out ? act_out + c0 : nullptr;
     int rc;
 #define DIG3D_LIN(NP, KU)                                                                                             \
-    (n == 128 ? launch_linear_h16<NP, KU, 128>(x, rows, k, pw, b, yo, ao, nout, st)                                    \
-              : launch_linear_h16<NP, KU, 64>(x, rows, k, pw, b, yo, ao, nout, st))
+    (n == 128 ? launch_linear_h16<NP, KU, 128>(x, rows, k, pw, b, yo, ao, nout, slices, st)                            \
+              : launch_linear_h16<NP, KU, 64>(x, rows, k, pw, b, yo, ao, nout, slices, st))
     if (k == 64) rc = DIG3D_LIN(1, 8);
     else if (k == 128) rc = DIG3D_LIN(1, 16);
     else if (k == 256) rc = DIG3D_LIN(2, 16);
     else rc = DIG3D_LIN(3, 16);
 #undef DIG3D_LIN
     if (rc) return rc;
-    pw += (size_t)4 * n * k;
+    pw += (size_t)4 * n * k * slices;
+    c0 += n * slices;
   }
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;

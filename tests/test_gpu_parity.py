@@ -285,7 +285,7 @@ def test_comenet_engine_forward_and_its_edge_kernels():
     src = g.src.long()
     dst = g.dst.long()
     for lf, feat in ((blk.lin_feature1, f1), (blk.lin_feature2, f2)):
-        w_ref = (feat.double() @ lf.lin1.weight.double().t()) @ lf.lin2.weight.double().t()          # [E, 256]
+        w_ref = (feat.double() @ lf.lin1.weight.detach().double().t()) @ lf.lin2.weight.detach().double().t()   # [E, 256]
         agg_ref = torch.zeros(g.n_nodes, 256, device=dev, dtype=torch.float64).index_add_(0, dst, w_ref * x.double()[src])
         agg = ops.comenet_filter_sum(feat, model._filter_t(lf), x, g)
         assert rel_err(agg.cpu().numpy(), agg_ref.cpu().numpy()) < 2e-6
