@@ -76,16 +76,35 @@ wgrad_tc_kernel(const float* __restrict__ dy, const float* __restrict__ x, int64
     const float* xc = x + kb + c;
     float bsum = 0.f;
     float av[4][4], bv[4][4];
-    auto fetch = [&](int ch) {                       // this thread's 16 + 16 values of chunk ch (zero beyond the slice)
-      const int64_t r0 = r_lo + (int64_t)ch * WG_RC;
+    // this thread's 16 + 16 values of chunk ch (zero beyond the slice): running pointers, one 64-bit add per load; the
+    // bounds are only tested in the (single) ragged last chunk
+    const size_t step_a = (size_t)nout, step_b = (size_t)k;
+    auto fetch = [&](int ch) {
+      const int64_t r0 = r_lo + (int64_t)ch * WG_RC + half * 4;
+      const float* pa = dyc + r0 * nout;
+      const float* pb = xc + r0 * k;
+      if (r_lo + (int64_t)(ch + 1) * WG_RC <= r_hi) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 4; ++u) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int64_t r = r0 + (half + 2 * u) * 4 + q;
-          const bool in = r < r_hi;
-          av[u][q] = (in && n_ok) ? __ldg(dyc + r * nout) : 0.f;
-          bv[u][q] = (in && k_ok) ? __ldg(xc + r * k) : 0.f;
+          for (int q = 0; q < 4; ++q) {
+            av[u][q] = n_ok ? __ldg(pa) : 0.f;
+            bv[u][q] = k_ok ? __ldg(pb) : 0.f;
+            pa += step_a; pb += step_b;
+          }
+          pa += 4 * step_a; pb += 4 * step_b;
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const bool in = r0 + u * 8 + q < r_hi;
+            av[u][q] = (in && n_ok) ? __ldg(pa) : 0.f;
+            bv[u][q] = (in && k_ok) ? __ldg(pb) : 0.f;
+            pa += step_a; pb += step_b;
+          }
+          pa += 4 * step_a; pb += 4 * step_b;
         }
       }
     };

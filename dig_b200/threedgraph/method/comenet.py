@@ -166,6 +166,24 @@ class ComENet(nn.Module):
         for lin in self.lins:
             lin.reset_parameters()
         self.lin_out.reset_parameters()
+        self.invalidate_packed()
+
+    # The engine forward keeps packed copies of the weights keyed on (generation, data_ptr, tensor._version); writes through
+    # `.data` (reset_parameters, EMA swaps) do not bump the version, so every entry point that may do that bumps the
+    # generation; user code that edits `.data` of an eval-mode model must call invalidate_packed() itself (as for SphereNet).
+    def invalidate_packed(self):
+        self.__dict__.pop("_filter_cache", None)
+        self.__dict__.pop("_cat_cache", None)
+        ops.invalidate_packed()
+
+    def load_state_dict(self, *args, **kw):
+        out = super().load_state_dict(*args, **kw)
+        self.invalidate_packed()
+        return out
+
+    def train(self, mode=True):
+        self.invalidate_packed()
+        return super().train(mode)
 
     def _forward(self, data):
         batch, z, pos = data.batch, data.z.long(), data.pos

@@ -276,6 +276,21 @@ def test_comenet_engine_forward_and_its_edge_kernels():
     assert ops.tc_timeouts() == 0 and not ops.h16_overflow()
     assert rel_err(outs["simt"].cpu().numpy(), ref.cpu().numpy()) < TOL
     assert rel_err(outs["h16"].cpu().numpy(), ref.cpu().numpy()) < TOL
+    # a write through .data + invalidate_packed() is seen by the packed copies (weights, folded filters, lin_cat halves)
+    with torch.no_grad():
+        model.interaction_blocks[0].lin.weight.data.mul_(0.5)
+        model.interaction_blocks[1].lin_feature1.lin2.weight.data.mul_(1.5)
+        model.interaction_blocks[2].lin_cat.weight.data.mul_(0.75)
+    model.invalidate_packed()
+    try:
+        for mode in ("h16", "simt"):
+            os.environ["DIG3D_COMENET_DENSE"] = mode
+            with torch.no_grad():
+                outs[mode + "2"] = model(b)
+    finally:
+        os.environ.pop("DIG3D_COMENET_DENSE", None)
+    assert rel_err(outs["h162"].cpu().numpy(), outs["simt2"].cpu().numpy()) < TOL
+    assert rel_err(outs["simt2"].cpu().numpy(), outs["simt"].cpu().numpy()) > 1e-3
     # kernel level
     g = ops.build_graph(b.pos, b.batch, 6.0, num_graphs=64, want_edge_index=False)
     f1, f2, _ = ops.comenet_geometry(g, b.pos, 6.0)
