@@ -257,6 +257,27 @@ def other_configs(dev):
                     return model(b)
             ms = time_ms(torch, infer)
             rec["inference"] = {"ms_per_step": round(ms, 4), "molecules_per_s": round(nmol / (ms * 1e-3), 1)}
+            if not data_kw.get("protein"):
+                # the same forward with batches in flight (dig_b200.pipeline, what run.val does)
+                from dig_b200.pipeline import InferencePipeline
+                pipe = InferencePipeline(model.eval(), dev)
+                for _ in pipe.map([b] * (2 * pipe.depth)):
+                    pass
+                ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                ea.record()
+                n_rep = 12
+                for _ in pipe.map([b] * n_rep):
+                    pass
+                cur = torch.cuda.current_stream()
+                for st in pipe.streams:
+                    cur.wait_stream(st)
+                eb.record()
+                torch.cuda.synchronize()
+                msp = ea.elapsed_time(eb) / n_rep
+                rec["inference"]["in_flight"] = {"batches": pipe.depth, "ms_per_step": round(msp, 4),
+                                                 "molecules_per_s": round(nmol / (msp * 1e-3), 1)}
+                model.train()
             # whole-forward roofline view (SURVEY 8d flop counts; fp32 work counted once): which pipe would bound it
             from dig_b200 import ops as _ops
             if hasattr(b, "pos") and not data_kw.get("protein"):
@@ -493,10 +514,11 @@ def main():
             topt.step()
 
         train_steps = max(3, min(args.steps, 30))
-        for s in range(3):
-            step_train(s)
-        lt0 = _lib.launch_count
-        tr_dev, _ = windows(step_train, train_steps, n=3)
+        with parallel.PacedGC(every=0):                  # as run.train does: no rank pauses for cycle collection mid-window
+            for s in range(3):
+                step_train(s)
+            lt0 = _lib.launch_count
+            tr_dev, _ = windows(step_train, train_steps, n=3)
         train_launches = (_lib.launch_count - lt0) // 3
         ms_train = statistics.median(tr_dev)
         train = {"value": MOLS_PER_GPU * world * train_steps / (ms_train * 1e-3), "unit": "molecules/s",

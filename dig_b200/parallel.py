@@ -300,3 +300,39 @@ class FlatAdam(torch.optim.Optimizer):
                     st[key] = view
             steps = max(steps, int(float(st["step"])))
         self.steps = steps
+
+
+class PacedGC:
+    """Training-loop garbage-collection pacing for data-parallel runs.
+
+    A step allocates a few thousand short-lived Python objects (tensor wrappers, autograd nodes, ctypes arguments), so
+    CPython's generational collector fires at arbitrary steps, at different steps on different ranks; with a gradient
+    all-reduce every step, each rank's pause becomes everybody's pause (the step time is the slowest rank's).  Inside
+    this context automatic collection is off, the long-lived objects (model, optimizer state, CUDA library handles) are
+    frozen out of the young generations, and `tick()` collects every `every` steps -- the SAME steps on every rank.
+    Reference counting still frees tensors immediately; only cycle collection is paced."""
+
+    def __init__(self, every=64):
+        self.every, self.count, self._was_enabled = int(every), 0, True
+
+    def __enter__(self):
+        import gc
+        self._was_enabled = gc.isenabled()
+        gc.collect()
+        gc.freeze()
+        gc.disable()
+        self.count = 0
+        return self
+
+    def tick(self):
+        self.count += 1
+        if self.every > 0 and self.count % self.every == 0:
+            import gc
+            gc.collect()
+
+    def __exit__(self, *exc):
+        import gc
+        gc.unfreeze()
+        if self._was_enabled:
+            gc.enable()
+        return False

@@ -111,7 +111,16 @@ class run():
         model.train()
         loss_accum = 0
         step = -1
+        with parallel.PacedGC(every=64) as pace:      # cycle collection at the same steps on every rank (no stragglers)
+            step, loss_accum = self._train_steps(model, optimizer, train_loader, energy_and_force, p, loss_func, device, pace)
+        return loss_accum / (step + 1)
+
+    @staticmethod
+    def _train_steps(model, optimizer, train_loader, energy_and_force, p, loss_func, device, pace):
+        loss_accum = 0
+        step = -1
         for step, batch_data in enumerate(tqdm(train_loader)):
+            pace.tick()
             optimizer.zero_grad()
             batch_data = batch_data.to(device)
             out = model(batch_data)
@@ -139,7 +148,7 @@ class run():
             parallel.allreduce_gradients(model.parameters())
             optimizer.step()
             loss_accum += loss.detach().cpu().item()
-        return loss_accum / (step + 1)
+        return step, loss_accum
 
     def val(self, model, data_loader, energy_and_force, p, evaluation, device):
         r"""reference run.py:137-180; returns the MAE (energy MAE + p * force MAE with forces).
