@@ -142,6 +142,21 @@ def emit_function(name, var_names, sources, doc=""):
             f"{body}\n{stores}\n}}\n")
 
 
+def emit_bessel_orders(ns, nr, bessel_sources):
+    """bessel() split by order l: bessel_l<l>(x, out[NR]) evaluates entries l*NR .. l*NR+NR-1 with the same expression
+    trees (so the same roundings) and bessel_order(l, x, out) dispatches on a block-uniform l -- the edge-basis kernel
+    spreads one edge's NS orders over NS threads instead of one thread walking ~80 sinf / cosf calls."""
+    parts = []
+    for l in range(ns):
+        parts.append(emit_function(f"bessel_l{l}", ["x"], bessel_sources[l * nr:(l + 1) * nr],
+                                   f"bessel() entries of order l = {l}"))
+    cases = "\n".join(f"        case {l}: bessel_l{l}(x, out); break;" for l in range(ns))
+    parts.append("// order l of bessel(); l must be uniform over the warp\n"
+                 f"__device__ __forceinline__ void bessel_order(const int l, const float x, float (&out)[{nr}]) {{\n"
+                 f"    switch (l) {{\n{cases}\n        default: break;\n    }}\n}}\n")
+    return "\n".join(parts)
+
+
 def emit_header(tag, flavor, num_spherical, num_radial, sources):
     """Full generated header for one (flavor, ns, nr)."""
     ns, nr = num_spherical, num_radial
@@ -158,6 +173,7 @@ def emit_header(tag, flavor, num_spherical, num_radial, sources):
         f"constexpr int N_YLM = {len(sources['ylm'])};\n",
         emit_function("bessel", ["x"], sources["bessel"],
                       "normalised spherical Bessel j_l(z_ln x); index l*NR + n"),
+        emit_bessel_orders(ns, nr, sources["bessel"]),
         emit_function("yl0", ["theta"], sources["yl0"], "real spherical harmonics Y_l^0(theta)"),
         emit_function("ylm", ["theta", "phi"], sources["ylm"],
                       "real spherical harmonics, reference flat order"),

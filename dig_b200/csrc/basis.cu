@@ -20,6 +20,7 @@ struct B76 {
   static constexpr int NS = basis_dimenet_7_6::NS, NR = basis_dimenet_7_6::NR;
   static constexpr int NB = NS * NR, NY = NS * NS;
   __device__ static void bessel(float x, float (&o)[NB]) { basis_dimenet_7_6::bessel(x, o); }
+  __device__ static void bessel_order(int l, float x, float (&o)[NR]) { basis_dimenet_7_6::bessel_order(l, x, o); }
   __device__ static void yl0(float t, float (&o)[NS]) { basis_dimenet_7_6::yl0(t, o); }
   __device__ static void ylm(float t, float p, float (&o)[NY]) { basis_dimenet_7_6::ylm(t, p, o); }
   __device__ static void bessel_dx(float x, float (&o)[NB]) { basis_dimenet_7_6::bessel_dx(x, o); }
@@ -31,6 +32,7 @@ struct B36 {
   static constexpr int NS = basis_dimenet_3_6::NS, NR = basis_dimenet_3_6::NR;
   static constexpr int NB = NS * NR, NY = NS * NS;
   __device__ static void bessel(float x, float (&o)[NB]) { basis_dimenet_3_6::bessel(x, o); }
+  __device__ static void bessel_order(int l, float x, float (&o)[NR]) { basis_dimenet_3_6::bessel_order(l, x, o); }
   __device__ static void yl0(float t, float (&o)[NS]) { basis_dimenet_3_6::yl0(t, o); }
   __device__ static void ylm(float t, float p, float (&o)[NY]) { basis_dimenet_3_6::ylm(t, p, o); }
   __device__ static void bessel_dx(float x, float (&o)[NB]) { basis_dimenet_3_6::bessel_dx(x, o); }
@@ -42,6 +44,7 @@ struct G23 {
   static constexpr int NS = basis_gemnet_2_3::NS, NR = basis_gemnet_2_3::NR;
   static constexpr int NB = NS * NR, NY = NS * NS;
   __device__ static void bessel(float x, float (&o)[NB]) { basis_gemnet_2_3::bessel(x, o); }
+  __device__ static void bessel_order(int l, float x, float (&o)[NR]) { basis_gemnet_2_3::bessel_order(l, x, o); }
   __device__ static void yl0(float t, float (&o)[NS]) { basis_gemnet_2_3::yl0(t, o); }
   __device__ static void ylm(float t, float p, float (&o)[NY]) { basis_gemnet_2_3::ylm(t, p, o); }
   __device__ static void bessel_dx(float x, float (&o)[NB]) { basis_gemnet_2_3::bessel_dx(x, o); }
@@ -89,6 +92,37 @@ __global__ void edge_basis_kernel(const float* __restrict__ dist, int n_edges, f
     for (int c = 0; c < BS::NB; ++c)
       bess[(size_t)e * BS::NB + c] = env_on_bessel ? __fmul_rn(env, b[c]) : b[c];
   }
+}
+
+
+// The same outputs with one edge's work spread over NS + 1 threads: blockIdx.y = Bessel order l (its NR entries, the
+// same expression trees and roundings as bessel(): codegen.emit_bessel_orders) or NS for the six rbf0 sines.  One thread per
+// edge walks ~80 sinf / cosf calls back to back on ~7 resident warps per SM (latency bound: 50 us for 34 k edges); split by
+// order the launch has 8x the warps and the critical path is the longest single order.  Bit-identical to edge_basis_kernel.
+template <class BS>
+__global__ void __launch_bounds__(128)
+edge_basis_split_kernel(const float* __restrict__ dist, int n_edges, float inv_cutoff, int p, float ea, float eb, float ec,
+                        const float* __restrict__ freq, int env_on_bessel, float* __restrict__ rbf0,
+                        float* __restrict__ bess) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int part = blockIdx.y;
+  if (e >= n_edges) return;
+  const float x = __fmul_rn(dist[e], inv_cutoff);
+  if (part == BS::NS) {
+    if (!rbf0) return;
+    const float env = envelope(x, p, ea, eb, ec);
+#pragma unroll
+    for (int n = 0; n < BS::NR; ++n)
+      rbf0[(size_t)e * BS::NR + n] = __fmul_rn(env, sinf(__fmul_rn(__ldg(freq + n), x)));
+    return;
+  }
+  if (!bess) return;
+  float b[BS::NR];
+  BS::bessel_order(part, x, b);
+  const float env = env_on_bessel ? envelope(x, p, ea, eb, ec) : 1.0f;
+#pragma unroll
+  for (int n = 0; n < BS::NR; ++n)
+    bess[(size_t)e * BS::NB + part * BS::NR + n] = env_on_bessel ? __fmul_rn(env, b[n]) : b[n];
 }
 
 
@@ -889,6 +923,8 @@ triplet_basis_project_bwd_geom_kernel(const float* __restrict__ bess, const floa
   }
 }
 
+static int h_edge_basis_split = 1;   // 1: one thread per (edge, Bessel order); 0: one thread per edge (round 1)
+
 template <class BS>
 static int launch_edge_basis(const float* dist, int64_t n_edges, double cutoff, int exponent,
                              const float* freq, int env_on_bessel, float* rbf0, float* bess,
@@ -896,8 +932,12 @@ static int launch_edge_basis(const float* dist, int64_t n_edges, double cutoff, 
   const int p = exponent + 1;
   const float a = (float)(-(p + 1) * (p + 2) / 2.0), b = (float)(p * (p + 2)), c = (float)(-p * (p + 1) / 2.0);
   const float inv = 1.0f / (float)cutoff;
-  edge_basis_kernel<BS><<<ceil_div(n_edges, 128), 128, 0, st>>>(dist, (int)n_edges, inv, p, a, b, c, freq,
-                                                             env_on_bessel, rbf0, bess);
+  if (h_edge_basis_split)
+    edge_basis_split_kernel<BS><<<dim3(ceil_div(n_edges, 128), BS::NS + 1), 128, 0, st>>>(
+        dist, (int)n_edges, inv, p, a, b, c, freq, env_on_bessel, rbf0, bess);
+  else
+    edge_basis_kernel<BS><<<ceil_div(n_edges, 128), 128, 0, st>>>(dist, (int)n_edges, inv, p, a, b, c, freq,
+                                                               env_on_bessel, rbf0, bess);
   return 0;
 }
 
@@ -921,6 +961,11 @@ int dig3d_edge_basis(const float* dist, int64_t n_edges, double cutoff, int32_t 
     default: set_error("edge_basis: unknown basis_id %d", basis_id); return DIG3D_EUNSUPPORTED;
   }
   DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_edge_basis_set_split(int32_t on) {
+  h_edge_basis_split = on ? 1 : 0;
   return DIG3D_OK;
 }
 

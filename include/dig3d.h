@@ -107,6 +107,9 @@ int dig3d_triplet_geometry(const float* pos, const int32_t* src, const int32_t* 
 int dig3d_edge_basis(const float* dist, int64_t n_edges, double cutoff, int32_t envelope_exponent,
                      const float* freq, int32_t basis_id, int32_t envelope_on_bessel, float* rbf0,
                      float* bess, void* stream);
+/* 1 (default): one thread per (edge, Bessel order) -- 8x the warps of the one-thread-per-edge kernel, bit-identical
+ * output; 0: the round-1 kernel (kept as the comparison twin for tests). */
+int dig3d_edge_basis_set_split(int32_t on);
 
 /* Materialise sbf[T, ns*nr] and (nullable) tbf[T, ns*ns*nr] exactly as the reference's angle_emb /
  * torsion_emb do (test / API-parity path; the fused model path never materialises them). */

@@ -247,6 +247,28 @@ def test_comenet_energy_parity():
     # and the oracle's op sequence executed on this GPU is the checker above.
 
 
+@pytest.mark.parametrize("basis_id,nr,nb,env_on_bessel", [(0, 6, 42, True), (0, 6, 42, False), (1, 6, 18, False), (2, 3, 6, True)])
+def test_edge_basis_split_by_order_is_bit_identical(basis_id, nr, nb, env_on_bessel):
+    """One thread per (edge, Bessel order) (edge_basis_split_kernel, the default) writes exactly the bits of the
+    one-thread-per-edge kernel: rbf0 and all NS * NR Bessel entries, envelope on / off, ragged edge count."""
+    from dig_b200 import ops, _lib
+    dev = torch.device("cuda:0")
+    torch.manual_seed(basis_id)
+    dist = torch.rand(34567, device=dev) * 4.9 + 0.05
+    freq = torch.arange(1, nr + 1, device=dev, dtype=torch.float32) * 3.14159274
+    lib = _lib.load()
+    outs = []
+    try:
+        for split in (0, 1):
+            lib.dig3d_edge_basis_set_split(split)
+            outs.append(ops.edge_basis(dist, 5.0, 5, freq, basis_id, env_on_bessel, nr, nb))
+    finally:
+        lib.dig3d_edge_basis_set_split(1)
+    torch.cuda.synchronize()
+    assert torch.isfinite(outs[1][1]).all()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 def test_comenet_engine_forward_and_its_edge_kernels():
     """ComENet inference on the tensor engine (linear_h16 for every hidden x hidden linear, folded edge filter,
     ComENet._forward_h16) vs round 1's exact-fp32 fused block kernel (DIG3D_COMENET_DENSE=simt) and vs the oracle, at the
