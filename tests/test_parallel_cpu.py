@@ -176,3 +176,26 @@ def test_run_driver_contract_on_cpu(tmp_path, capsys):
     ck = torch.load(str(tmp_path / "ck" / "valid_checkpoint.pt"), weights_only=False)
     assert set(ck) == {'epoch', 'model_state_dict', 'optimizer_state_dict', 'scheduler_state_dict', 'best_valid_mae',
                        'num_params'} and ck['num_params'] == 45
+
+
+def test_paced_gc_disables_and_restores_collection():
+    """parallel.PacedGC: automatic cycle collection is off inside the context, tick() collects every `every` steps (the
+    same steps on every rank), and the previous state comes back on exit."""
+    import gc
+    from dig_b200 import parallel
+    assert gc.isenabled()
+    with parallel.PacedGC(every=3) as pace:
+        assert not gc.isenabled()
+
+        class Node:
+            pass
+        a, b = Node(), Node()
+        a.other, b.other = b, a                 # a reference cycle only the collector can free
+        import weakref
+        probe = weakref.ref(a)
+        del a, b
+        pace.tick(); pace.tick()
+        assert probe() is not None              # nothing collected yet
+        pace.tick()                             # third step: paced collection
+        assert probe() is None
+    assert gc.isenabled()
