@@ -100,7 +100,7 @@ SIGNATURES = {
     "dig3d_sphere_update_v_h16": [P, c_int64, c_int32, c_int32, c_int32, P, P, P, P],
     "dig3d_h16_pack_t": [P, P, P, P, P, c_int32, P],
     "dig3d_linear_h16_supported": [c_int32, c_int32],
-    "dig3d_linear_h16": [P, c_int64, c_int32, c_int32, P, P, P, P, P],
+    "dig3d_linear_h16": [P, c_int64, c_int32, c_int32, P, P, P, P, P, P],
     "dig3d_h16_overflow": [c_int32],
     "dig3d_h16_timeouts": [],
     "dig3d_h16_trace": [c_int32, P],

@@ -365,9 +365,11 @@ __device__ __forceinline__ void h_store_tile_coalesced(HSmem& s, const HCtx& c, 
 }
 
 // Same with an output leading dimension (the tile is a column slice of a wider row-major matrix).
+// `res` (nullable, same leading dimension): added to the tile in the coalesced store phase (fused residual / skip add).
 template <int W>
 __device__ __forceinline__ void h_store_tile_strided(HSmem& s, const HCtx& c, int col0, const float (&v)[W / 2],
-                                                     float* __restrict__ out, int ld, int rows) {
+                                                     float* __restrict__ out, int ld, int rows,
+                                                     const float* __restrict__ res = nullptr) {
   constexpr int LD = W + 1, RPW = 128 / W;
   float* st = reinterpret_cast<float*>(s.a[c.t][0]);
 #pragma unroll
@@ -378,7 +380,12 @@ __device__ __forceinline__ void h_store_tile_strided(HSmem& s, const HCtx& c, in
     const int r = r0 + (RPW == 2 ? (lane >> 4) : 0), c4 = 4 * (RPW == 2 ? (lane & 15) : lane);
     if (r < rows) {
       const float* src = st + r * LD + c4;
-      *reinterpret_cast<float4*>(out + (size_t)r * ld + c4) = make_float4(src[0], src[1], src[2], src[3]);
+      float4 o = make_float4(src[0], src[1], src[2], src[3]);
+      if (res) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(res + (size_t)r * ld + c4));
+        o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+      }
+      *reinterpret_cast<float4*>(out + (size_t)r * ld + c4) = o;
     }
   }
 }
@@ -930,7 +937,8 @@ struct HLinParams { HGemm g[3]; };
 template <int NPANEL, int KU, int N>
 __global__ void __launch_bounds__(H_THREADS, 1)
 linear_h16_kernel(const float* __restrict__ x, int n_rows, int ldx, HLinParams P, const float* __restrict__ bias,
-                  float* __restrict__ y, float* __restrict__ act_out, int ldy, int tiles_per_cta, int slice_bytes) {
+                  float* __restrict__ y, float* __restrict__ act_out, const float* __restrict__ residual, int ldy,
+                  int tiles_per_cta, int slice_bytes) {
   extern __shared__ __align__(1024) unsigned char h_raw[];
   HSmem& s = *reinterpret_cast<HSmem*>(h_raw);
   constexpr int NC = N / 2;                                // columns per epilogue thread
@@ -943,8 +951,9 @@ linear_h16_kernel(const float* __restrict__ x, int n_rows, int ldx, HLinParams P
 #pragma unroll
     for (int p = 0; p < NPANEL; ++p) P.g[p].w += (size_t)slice * slice_bytes;
     if (bias) bias += slice * N;
-    y += slice * N;
+    if (y) y += slice * N;
     if (act_out) act_out += slice * N;
+    if (residual) residual += slice * N;
   }
   const int n_tiles = (n_rows + H_M - 1) / H_M, tile0 = blockIdx.x * tiles_per_cta;
   const int ntile = min(tiles_per_cta, n_tiles - tile0);
@@ -973,12 +982,15 @@ linear_h16_kernel(const float* __restrict__ x, int n_rows, int ldx, HLinParams P
     }
 #pragma unroll
     for (int i = 0; i < NC; ++i) acc[i] = fmaf(acc[i], H_INV, s.bias[0][col0 + i]);
-    h_store_tile_strided<N>(s, c, col0, acc, y + (size_t)r0 * ldy, ldy, rows);
+    // outputs: y = x W^T + b (nullable) and / or act_out = swish(y); `residual` is added to the LAST of them (the skip
+    // connection of a residual layer, or the second GEMM of a sum of two linears), y stays the pre-activation
+    const float* res = residual ? residual + (size_t)r0 * ldy : nullptr;
+    if (y) h_store_tile_strided<N>(s, c, col0, acc, y + (size_t)r0 * ldy, ldy, rows, act_out ? nullptr : res);
     if (act_out) {
 #pragma unroll
       for (int i = 0; i < NC; ++i) acc[i] = hswish<false>(acc[i]);
-      h_tile_bar(c.t);
-      h_store_tile_strided<N>(s, c, col0, acc, act_out + (size_t)r0 * ldy, ldy, rows);
+      if (y) h_tile_bar(c.t);
+      h_store_tile_strided<N>(s, c, col0, acc, act_out + (size_t)r0 * ldy, ldy, rows, res);
     }
   }
   h_finish(s, epi ? &c : nullptr);
@@ -1226,7 +1238,7 @@ sphere_triplet_gather_tc_kernel(const float* __restrict__ x_down, const float* _
 static int h_smem_attr(const void* fn);
 template <int NPANEL, int KU, int N>
 static int launch_linear_h16(const float* x, int64_t rows, int ldx, const unsigned char* packed, const float* bias,
-                             float* y, float* act_out, int ldy, int slices, cudaStream_t st) {
+                             float* y, float* act_out, const float* residual, int ldy, int slices, cudaStream_t st) {
   HLinParams P;
   const size_t panel = (size_t)(KU / 4) * 2 * 4 * N * 16;      // KU/4 slabs of [hi|lo][4][N][8 halves]
   for (int p = 0; p < NPANEL; ++p) P.g[p] = {packed + p * panel, nullptr, KU * 8, N};
@@ -1239,7 +1251,8 @@ static int launch_linear_h16(const float* x, int64_t rows, int ldx, const unsign
   const int tiles = ceil_div(rows, H_M);
   const int tpc = (ceil_div(tiles, 2) * slices < n_sm) ? 1 : 2;        // below one wave of tile pairs: one tile per CTA
   dim3 grid(ceil_div(tiles, tpc), slices);
-  kfn<<<grid, H_THREADS, sizeof(HSmem), st>>>(x, (int)rows, ldx, P, bias, y, act_out, ldy, tpc, 4 * N * (NPANEL * KU * 8));
+  kfn<<<grid, H_THREADS, sizeof(HSmem), st>>>(x, (int)rows, ldx, P, bias, y, act_out, residual, ldy, tpc,
+                                              4 * N * (NPANEL * KU * 8));
   return DIG3D_OK;
 }
 
@@ -1414,10 +1427,11 @@ int dig3d_linear_h16_supported(int32_t k, int32_t nout) {
 /* y = x W^T + bias (+ act_out = swish(y)); packed = dig3d_h16_pack(_t) of W as consecutive [min(128, N - c), K] row
  * slices (one per 128 output columns; a trailing 64-column slice is allowed). */
 int dig3d_linear_h16(const float* x, int64_t rows, int32_t k, int32_t nout, const void* packed, const float* bias,
-                     float* y, float* act_out, void* stream) {
-  DIG3D_REQUIRE(x && packed && y, "linear_h16: null pointer");
+                     float* y, float* act_out, const float* residual, void* stream) {
+  DIG3D_REQUIRE(x && packed && (y || act_out), "linear_h16: null pointer");
   DIG3D_REQUIRE(dig3d_linear_h16_supported(k, nout), "linear_h16: shape %d -> %d is not compiled", k, nout);
-  DIG3D_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)act_out) & 15) == 0, "linear_h16: 16-byte alignment");
+  DIG3D_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)act_out | (uintptr_t)residual) & 15) == 0,
+                "linear_h16: 16-byte alignment");
   if (rows == 0) return DIG3D_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned char* pw = (const unsigned char*)packed;
@@ -1426,12 +1440,13 @@ int dig3d_linear_h16(const float* x, int64_t rows, int32_t k, int32_t nout, cons
     const int n = nout - c0 >= 128 ? 128 : 64;
     const int slices = n == 128 ? (nout - c0) / 128 : 1;
     const float* b = bias ? bias + c0 : nullptr;
-    float* yo = y + c0;
+    float* yo = y ? y + c0 : nullptr;
     float* ao = act_out ? act_out + c0 : nullptr;
+    const float* ro = residual ? residual + c0 : nullptr;
     int rc;
 #define DIG3D_LIN(NP, KU)                                                                                             \
-    (n == 128 ? launch_linear_h16<NP, KU, 128>(x, rows, k, pw, b, yo, ao, nout, slices, st)                            \
-              : launch_linear_h16<NP, KU, 64>(x, rows, k, pw, b, yo, ao, nout, slices, st))
+    (n == 128 ? launch_linear_h16<NP, KU, 128>(x, rows, k, pw, b, yo, ao, ro, nout, slices, st)                        \
+              : launch_linear_h16<NP, KU, 64>(x, rows, k, pw, b, yo, ao, ro, nout, slices, st))
     if (k == 64) rc = DIG3D_LIN(1, 8);
     else if (k == 128) rc = DIG3D_LIN(1, 16);
     else if (k == 256) rc = DIG3D_LIN(2, 16);

@@ -1087,18 +1087,25 @@ def repack_h16_all():
         ent[1][tr] = ((gen, w._version, w.data_ptr(), tuple(w.shape)), buf)
 
 
-def linear_h16(x, weight, bias=None, transposed=False, want_act=False):
+def linear_h16(x, weight, bias=None, transposed=False, want_act=False, residual=None, act_only=False):
     """y = x W^T + b (transposed=False) or y = x W (transposed=True: the input-gradient GEMM) on the two-tile tcgen05
-    engine, 3xFP16 operands (fp32-level accuracy, |x| < 8190); want_act: also return swish(y)."""
+    engine, 3xFP16 operands (fp32-level accuracy, |x| < 8190); want_act: also return swish(y).
+    residual [rows, nout]: added in the epilogue to the last output (swish(y) + r with want_act, else y + r);
+    act_only (with want_act): the pre-activation is not written and only swish(y) (+ r) is returned."""
     k = x.size(-1)
     nout = weight.size(1) if transposed else weight.size(0)
     rows = x.numel() // k
     packed = _h16_packed(weight, transposed)
-    y = torch.empty(x.shape[:-1] + (nout,), device=x.device, dtype=F32)
-    act_out = torch.empty_like(y) if want_act else None
+    shape = x.shape[:-1] + (nout,)
+    y = None if (want_act and act_only) else torch.empty(shape, device=x.device, dtype=F32)
+    act_out = torch.empty(shape, device=x.device, dtype=F32) if want_act else None
+    if residual is not None and tuple(residual.shape) != tuple(shape):
+        raise ValueError(f"linear_h16: residual {tuple(residual.shape)} does not match the output {tuple(shape)}")
     call("dig3d_linear_h16", _p(x, F32, "x", 16), rows, k, nout, _p(packed), _p(bias, F32, "bias"), _p(y, align=16),
-         _p(act_out, align=16), _stream())
-    return (y, act_out) if want_act else y
+         _p(act_out, align=16), _p(residual, F32, "residual", 16), _stream())
+    if want_act:
+        return act_out if act_only else (y, act_out)
+    return y
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -242,22 +242,24 @@ class ComENet(nn.Module):
         lin = ops.linear_h16
         x = ops.comenet_embed(z, self.emb.emb.weight)                               # swish(emb[z])
         for blk in self.interaction_blocks:
-            _, x = lin(x, blk.lin.weight, blk.lin.bias, want_act=True)
+            x = lin(x, blk.lin.weight, blk.lin.bias, want_act=True, act_only=True)
             hs = []
             for conv, lf, l, feat in ((blk.conv1, blk.lin_feature1, blk.lin1, f1),
                                       (blk.conv2, blk.lin_feature2, blk.lin2, f2)):
                 agg = ops.comenet_filter_sum(feat, self._filter_t(lf), x, g)
-                h = ops.ewise(lin(agg, conv.lin_rel.weight, conv.lin_rel.bias), lin(x, conv.lin_root.weight, None), 1)
-                hs.append(lin(h, l.weight, l.bias, want_act=True)[1])
+                # GraphConv: lin_rel(agg) + lin_root(x) -- the second GEMM adds the first in its epilogue
+                h = lin(agg, conv.lin_rel.weight, conv.lin_rel.bias, residual=lin(x, conv.lin_root.weight, None))
+                hs.append(lin(h, l.weight, l.bias, want_act=True, act_only=True))
             wa, wb = self._cat_halves(blk)
-            h = ops.ewise(ops.ewise(lin(hs[0], wa, blk.lin_cat.bias), lin(hs[1], wb, None), 1), x, 1)
+            # lin_cat(cat[h1, h2]) + x = h1 Wa^T + b + (h2 Wb^T + x)
+            h = lin(hs[0], wa, blk.lin_cat.bias, residual=lin(hs[1], wb, None, residual=x))
             for l in blk.lins:
-                h = ops.ewise(lin(h, l.weight, l.bias, want_act=True)[1], h, 1)
+                h = lin(h, l.weight, l.bias, want_act=True, act_only=True, residual=h)      # swish(l(h)) + h
             h, _, _ = ops.graphnorm(h, g.graph_ptr, blk.norm.weight.detach(), blk.norm.bias.detach(),
                                     blk.norm.mean_scale.detach(), blk.norm.eps)
             x = lin(h, blk.final.weight, blk.final.bias)
         for l in self.lins:
-            _, x = lin(x, l.weight, l.bias, want_act=True)
+            x = lin(x, l.weight, l.bias, want_act=True, act_only=True)
         x = ops.linear(x, self.lin_out.weight.detach(), self.lin_out.bias.detach())
         return ops.segment_sum(x, g.graph_ptr)
 

@@ -292,8 +292,11 @@ int dig3d_sphere_triplet_gather_tc(const float* x_down, const float* sbf_p, cons
 int dig3d_h16_pack_t(const float* const* weights, const int32_t* n, const int32_t* k, const int32_t* trans,
                      void* const* outs, int32_t count, void* stream);
 int dig3d_linear_h16_supported(int32_t k, int32_t nout);
+/* y (pre-activation) and act_out (swish(y)) may each be NULL (not both); residual [rows, nout] (nullable) is added to the
+ * last output written (act_out if given, else y): swish(x W^T + b) + r is a residual layer in one launch, x W^T + b + r the
+ * sum of two linears.  All 128-column slices of a wide layer run in one launch; small row counts use one tile per CTA. */
 int dig3d_linear_h16(const float* x, int64_t rows, int32_t k, int32_t nout, const void* packed, const float* bias,
-                     float* y, float* act_out, void* stream);
+                     float* y, float* act_out, const float* residual, void* stream);
 /* 1 if an operand left the fp16 range since the flag was last cleared (synchronises the device). */
 int dig3d_h16_overflow(int32_t clear);
 int dig3d_h16_timeouts(void);

@@ -751,6 +751,13 @@ def test_linear_on_the_two_tile_engine_matches_fp64(k, nout):
         ref = x.double() @ wd.t() + b.double()
         assert rel_err(y.cpu().numpy(), ref.cpu().numpy()) < 2e-6
         assert rel_err(a.cpu().numpy(), (ref * torch.sigmoid(ref)).cpu().numpy()) < 2e-6
+        res = torch.randn(rows, nout, device=dev)
+        a_r = ops.linear_h16(x, w, b, want_act=True, act_only=True, residual=res)      # swish(y) + r, y not written
+        assert rel_err(a_r.cpu().numpy(), (ref * torch.sigmoid(ref) + res.double()).cpu().numpy()) < 2e-6
+        y_r = ops.linear_h16(x, w, b, residual=res)                                    # y + r
+        assert rel_err(y_r.cpu().numpy(), (ref + res.double()).cpu().numpy()) < 2e-6
+        y_p, a_p = ops.linear_h16(x, w, b, want_act=True, residual=res)                # pre-activation untouched
+        assert torch.equal(y_p, y) and torch.equal(a_p, a_r)
         dy = torch.randn(rows, nout, device=dev)
         dx = ops.linear_h16(dy, w, None, transposed=True)
         assert rel_err(dx.cpu().numpy(), (dy.double() @ wd).cpu().numpy()) < 2e-6

@@ -1,7 +1,8 @@
 #!/bin/bash
-# round 2, call Q: split edge basis, leaner wgrad producer, ComENet invalidation; quick bench + train step
+# round 2, call Q: split edge basis, leaner wgrad producer, ComENet invalidation + fused residual epilogues; quick bench + train step
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_train.py -x -q -k "edge_basis or basis_bit_exact or comenet or weight_gradient or energy_parity" > gpurun_out/r2q_pytest.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/r2q_pytest.log
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_train.py -x -q -k "edge_basis or basis_bit_exact or comenet or weight_gradient or energy_parity or two_tile_engine or baseline_configs" > gpurun_out/r2q_pytest.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/r2q_pytest.log
+timeout 600 python tools/gpu_comenet.py > gpurun_out/r2q_comenet.log 2>&1; echo "comenet rc=$?"; tail -8 gpurun_out/r2q_comenet.log | cut -c1-900
 timeout 600 python bench.py --steps 20 --warmup 5 --quick > gpurun_out/r2q_bench_quick.json 2> gpurun_out/r2q_bench_quick.err; echo "bench rc=$?"; tail -3 gpurun_out/r2q_bench_quick.err
 python -c "
 import json
