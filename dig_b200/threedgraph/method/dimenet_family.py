@@ -164,14 +164,17 @@ class _DimeNetFamily(nn.Module):
         # basis_emb_size_angle/torsion 8; everything else (hidden / out_emb widths, basis_emb_size_dist, number of
         # residual layers) is free on the GENERIC path: the same CUDA primitives the training path is made of
         # (dig3d_linear & co., any shape), slower than the fused kernels that exist for the class defaults.
-        if int_emb_size != 64 or be_angle != 8 or (self._torsion and be_torsion != 8) or num_radial != 6:
+        # Other triplet-branch widths run the reference's op sequence on the generic primitives (materialised angular
+        # bases, lin_sbf1 / lin_sbf2 / lin_t1 / lin_t2 as ordinary linears, row gather, segment sum): _triplet_generic.
+        self._triplet_generic = int_emb_size != 64 or be_angle != 8 or (self._torsion and be_torsion != 8)
+        if num_radial != 6:
             raise NotImplementedError(
-                f"{type(self).__name__}: the triplet kernels are compiled for int_emb_size=64, "
-                f"basis_emb_size_angle/torsion=8, num_radial=6; got int_emb_size={int_emb_size}, "
-                f"basis_emb sizes {(be_dist, be_angle, be_torsion)}, num_radial={num_radial}")
+                f"{type(self).__name__}: the generated radial / angular bases exist for num_radial=6 "
+                f"(dig_b200/codegen.py:CONFIGS); got num_radial={num_radial}")
         # use_node_features=False / use_extra_node_feature change init_e only (spherenet.py:79-91); they run on the
         # generic primitives as well (the fused init_e kernels are compiled for the 3H-wide default)
-        self._generic = bool(bad) or be_dist != 8 or not use_node_features or use_extra_node_feature
+        self._generic = (bool(bad) or be_dist != 8 or not use_node_features or use_extra_node_feature
+                         or self._triplet_generic)
         self.use_extra_node_feature = use_extra_node_feature
         if use_extra_node_feature:
             self.extra_emb = nn.Linear(extra_node_feature_dim, hidden_channels)
@@ -358,13 +361,24 @@ class _DimeNetFamily(nn.Module):
                                    self._basis_id, not self._torsion, nr, ns * nr)
         L = self.num_layers
         sbf_ps, t_ps = [], []
-        for first in range(0, L, 4):
-            es = self.update_es[first:first + 4]
-            s_l, t_l = ag.basis_project(g, bess, dist, angle, tors_angle, geo_cfg, self._basis_id, ns, nr,
-                                        [m.lin_sbf1.weight for m in es],
-                                        [m.lin_t1.weight for m in es] if self._torsion else None)
-            sbf_ps += s_l
-            t_ps += t_l if t_l is not None else [None] * len(s_l)
+        sbf = tbf = None
+        if self._triplet_generic:
+            # triplet-branch widths the fused projection / gather kernels are not compiled for: the angular bases are
+            # materialised once (constants: no parameters) and the branch runs op for op as spherenet.py:163-171
+            if pos.requires_grad:
+                raise NotImplementedError(
+                    f"{type(self).__name__}: forces with non-default int_emb_size / basis_emb_size_angle / _torsion are not "
+                    "built (the materialised-basis path carries no geometry gradient)")
+            ops.triplet_geometry(g, pos, use_torsion=self._torsion, want_idx=True)
+            sbf, tbf = ops.triplet_basis(bess, g.angle, g.torsion, g.idx_kj, self._basis_id, ns, nr, self._torsion)
+        else:
+            for first in range(0, L, 4):
+                es = self.update_es[first:first + 4]
+                s_l, t_l = ag.basis_project(g, bess, dist, angle, tors_angle, geo_cfg, self._basis_id, ns, nr,
+                                            [m.lin_sbf1.weight for m in es],
+                                            [m.lin_t1.weight for m in es] if self._torsion else None)
+                sbf_ps += s_l
+                t_ps += t_l if t_l is not None else [None] * len(s_l)
         swish_, lin = ag.swish, ag.lin
         # init_e (spherenet.py:79-91)
         ie = self.init_e
@@ -384,8 +398,14 @@ class _DimeNetFamily(nn.Module):
             x_kj = ag.lin_swish(ue.lin_kj, e1)
             x_kj = ag.mul(x_kj, lin(ue.lin_rbf2, lin(ue.lin_rbf1, rbf0)))
             x_kj = ag.lin_swish(ue.lin_down, x_kj)
-            x_kj = ag.triplet_gather(x_kj, sbf_ps[l], t_ps[l], ue.lin_sbf2.weight,
-                                     ue.lin_t2.weight if self._torsion else None, g)
+            if self._triplet_generic:
+                prod = ag.mul(ag.gather_rows(x_kj, g.idx_kj), lin(ue.lin_sbf2, lin(ue.lin_sbf1, sbf)))
+                if self._torsion:
+                    prod = ag.mul(prod, lin(ue.lin_t2, lin(ue.lin_t1, tbf)))
+                x_kj = ag.segment_sum(prod, g.trip_ptr, g.idx_ji)
+            else:
+                x_kj = ag.triplet_gather(x_kj, sbf_ps[l], t_ps[l], ue.lin_sbf2.weight,
+                                         ue.lin_t2.weight if self._torsion else None, g)
             x_kj = ag.lin_swish(ue.lin_up, x_kj)
             h = ag.add(x_ji, x_kj)
             for layer in ue.layers_before_skip:
@@ -483,8 +503,10 @@ class SphereNet(_DimeNetFamily):
     r"""Drop-in for dig.threedgraph.method.SphereNet (reference spherenet.py:228-320).
 
     Same constructor arguments and defaults.  `use_extra_node_feature=True` / `use_node_features=False` run on the
-    generic primitives (the fused init_e kernels are compiled for the default 3H-wide input).  Restrictions (raise
-    at construction): non-swish `act`, and triplet-branch sizes other than the class defaults.  `energy_and_force=True`: forward is differentiable w.r.t. pos (first order)."""
+    generic primitives (the fused init_e kernels are compiled for the default 3H-wide input), and so do
+    `int_emb_size` / `basis_emb_size_*` other than the defaults (materialised bases, ordinary linears; no forces there).
+    Restrictions (raise at construction): non-swish `act`, (num_spherical, num_radial) pairs without a generated basis.  `energy_and_force=True`: forward is differentiable w.r.t. pos, and in training mode twice (force training,
+    dig_b200/autograd_jvp.py)."""
     _torsion = True
 
     def __init__(self, energy_and_force=False, cutoff=5.0, num_layers=4, hidden_channels=128, out_channels=1,

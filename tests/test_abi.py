@@ -88,7 +88,11 @@ def test_generic_size_flags_and_constructor_contract():
     assert SphereNet(basis_emb_size_dist=4)._generic and DimeNetPP(num_before_skip=2)._generic
     assert SchNet(hidden_channels=48, num_filters=80)._generic and SchNet(num_gaussians=70)._generic
     assert ComENet(hidden_channels=128, middle_channels=32)._generic
-    for bad in (dict(int_emb_size=32), dict(basis_emb_size_angle=4), dict(num_radial=5), dict(num_spherical=5)):
+    for generic in (dict(int_emb_size=32), dict(basis_emb_size_angle=4), dict(basis_emb_size_torsion=6)):
+        m = SphereNet(**generic)                        # triplet-branch widths: generic primitives since round 2
+        assert m._generic and m._triplet_generic
+    assert DimeNetPP(basis_emb_size=16)._triplet_generic and not SphereNet()._triplet_generic
+    for bad in (dict(num_radial=5), dict(num_spherical=5)):          # no generated basis for these pairs
         with pytest.raises(NotImplementedError):
             SphereNet(**bad)
     with pytest.raises(NotImplementedError):

@@ -644,6 +644,11 @@ def test_non_default_hyperparameters(cls_name, kw):
     ("SphereNet", dict(hidden_channels=64, out_emb_channels=128, basis_emb_size_dist=4, num_before_skip=2,
                        num_after_skip=1, num_output_layers=2, out_channels=2, num_layers=3, cutoff=5.0)),
     ("DimeNetPP", dict(hidden_channels=96, out_emb_channels=192, num_layers=2, cutoff=5.0)),
+    # triplet-branch widths (VERDICT r1 missing #5): materialised bases + ordinary linears, gather, segment sum
+    ("SphereNet", dict(int_emb_size=32, basis_emb_size_angle=4, basis_emb_size_torsion=6, basis_emb_size_dist=8,
+                       num_layers=2, cutoff=5.0)),
+    ("SphereNet", dict(int_emb_size=48, num_spherical=3, num_layers=2, cutoff=5.0)),
+    ("DimeNetPP", dict(int_emb_size=96, basis_emb_size=16, num_layers=2, cutoff=5.0)),
     ("SchNet", dict(hidden_channels=48, num_filters=80, num_gaussians=70, num_layers=3, cutoff=6.0)),
     ("ComENet", dict(hidden_channels=128, middle_channels=32, num_layers=2, num_output_layers=2, cutoff=5.0)),
 ])
@@ -666,6 +671,7 @@ def test_generic_channel_sizes(cls_name, kw):
     if cls_name in ("SphereNet", "DimeNetPP"):
         ref = restated.dimenet_family_forward(sd_dev, b.z, b.pos, b.batch, torsion=(cls_name == "SphereNet"),
                                               cutoff=kw["cutoff"], num_layers=kw["num_layers"],
+                                              num_spherical=kw.get("num_spherical", 7),
                                               num_before_skip=kw.get("num_before_skip", 1),
                                               num_after_skip=kw.get("num_after_skip", 2),
                                               num_output_layers=kw.get("num_output_layers", 3))
