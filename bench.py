@@ -682,9 +682,9 @@ def main():
             "e2e": {"value": e2e, "unit": "molecules/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": wall_e2e / args.steps, "ms_per_step_min": e2e_pipe_wall_w[0] / args.steps,
                     "ms_per_step_max": e2e_pipe_wall_w[-1] / args.steps,
-                    "api": "dig_b200.pipeline.InferencePipeline (the loop of run.val): two batches in flight on alternating "
-                           "streams; every step copies its inputs from pinned host memory and its energies are read on "
-                           "the host one step later",
+                    "api": f"dig_b200.pipeline.InferencePipeline (the loop of run.val): {depth} batches in flight on "
+                           "alternating streams; every step copies its inputs from pinned host memory and its energies are "
+                           "read on the host a step or two later",
                     "serial": {"value": total_mols / (wall_e2e_serial * 1e-3), "ms_per_step": wall_e2e_serial / args.steps,
                                "api": "model(batch.to(device)) + .copy_ to a pinned buffer + stream sync every step"},
                     "timing": "host wall clock over exactly K steps (barrier + synchronize on both sides), median of the windows"},

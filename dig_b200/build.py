@@ -69,10 +69,12 @@ def build(force=False, verbose=False):
                 raise RuntimeError(f"nvcc failed on {src}:\n" + res.stdout + res.stderr)
             if verbose:
                 print(res.stderr)
-    res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT]
+    tmp = os.path.join(CSRC, "_obj", "libdig3d.so.tmp")     # link beside the objects, then move into place atomically:
+    res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp]
                          + [_obj(s) for s in sources()], capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
+    os.replace(tmp, OUT)                                     # a reader (or a repo snapshot) never sees a half-written library
     return OUT
 
 

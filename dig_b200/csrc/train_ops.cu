@@ -235,6 +235,47 @@ __global__ void rowscale_kernel(const float* __restrict__ a, const float* __rest
   if (i < rows * width) y[i] = __fmul_rn(a[i], s[i / width]);
 }
 
+// float4 forms of the streaming element-wise kernels above: the same per-element arithmetic (so the same bits), 16-byte
+// accesses, four elements per thread.  A 34 k x 128 activation is 17.6 MB: the scalar kernels ran at ~40 % of the HBM rate
+// (one 4-byte access per thread and instruction), these are bound by it.  Used when n % 4 == 0 and all pointers are
+// 16-byte aligned; the scalar kernels remain for the rest.
+__device__ __forceinline__ float act_fwd_one(float v, int mode) {
+  return mode == 0 ? __fmul_rn(v, sigmoid_f(v))
+         : mode == 1 ? __fsub_rn(v > 20.0f ? v : log1pf(expf(v)), 0.693147182464599609375f)
+                     : fmaxf(v, 0.0f);
+}
+__device__ __forceinline__ float act_bwd_one(float v, float dy, int mode) {
+  const float s = sigmoid_f(v);
+  const float d = mode == 0 ? s * (1.0f + v * (1.0f - s)) : mode == 1 ? s : (v > 0.0f ? 1.0f : 0.0f);
+  return dy * d;
+}
+__global__ void act_fwd4_kernel(const float4* __restrict__ x, int64_t n4, int mode, float4* __restrict__ y) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = x[i];
+  y[i] = make_float4(act_fwd_one(v.x, mode), act_fwd_one(v.y, mode), act_fwd_one(v.z, mode), act_fwd_one(v.w, mode));
+}
+__global__ void act_bwd4_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, int64_t n4, int mode,
+                                float4* __restrict__ dx) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = x[i], g = dy[i];
+  dx[i] = make_float4(act_bwd_one(v.x, g.x, mode), act_bwd_one(v.y, g.y, mode), act_bwd_one(v.z, g.z, mode),
+                      act_bwd_one(v.w, g.w, mode));
+}
+template <int OP>
+__global__ void ewise4_kernel(const float4* __restrict__ a, const float4* __restrict__ b, int64_t n4,
+                              float4* __restrict__ y) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 p = a[i], q = b[i];
+  y[i] = OP == 0 ? make_float4(__fmul_rn(p.x, q.x), __fmul_rn(p.y, q.y), __fmul_rn(p.z, q.z), __fmul_rn(p.w, q.w))
+                 : make_float4(__fadd_rn(p.x, q.x), __fadd_rn(p.y, q.y), __fadd_rn(p.z, q.z), __fadd_rn(p.w, q.w));
+}
+static inline bool vec4_ok(int64_t n, const void* a, const void* b, const void* c) {
+  return n % 4 == 0 && (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15) == 0;
+}
+
 // ------------------------------------------------------------------ row gather / scatter-add
 template <typename IDX>
 __global__ void gather_rows_kernel(const float* __restrict__ x, const IDX* __restrict__ idx, int64_t rows, int width,
@@ -454,7 +495,10 @@ int dig3d_wgrad(const float* dy, const float* x, int64_t rows, int32_t nout, int
 int dig3d_act(const float* x, int64_t n, int32_t mode, float* y, void* stream) {
   DIG3D_REQUIRE(x && y && mode >= 0 && mode <= 2, "act: bad arguments");
   if (n == 0) return DIG3D_OK;
-  act_fwd_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, mode, y);
+  if (vec4_ok(n, x, y, y))
+    act_fwd4_kernel<<<ceil_div(n / 4, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)x, n / 4, mode, (float4*)y);
+  else
+    act_fwd_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, mode, y);
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
 }
@@ -462,7 +506,11 @@ int dig3d_act(const float* x, int64_t n, int32_t mode, float* y, void* stream) {
 int dig3d_act_bwd(const float* x, const float* dy, int64_t n, int32_t mode, float* dx, void* stream) {
   DIG3D_REQUIRE(x && dy && dx && mode >= 0 && mode <= 2, "act_bwd: bad arguments");
   if (n == 0) return DIG3D_OK;
-  act_bwd_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(x, dy, n, mode, dx);
+  if (vec4_ok(n, x, dy, dx))
+    act_bwd4_kernel<<<ceil_div(n / 4, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)x, (const float4*)dy, n / 4, mode,
+                                                                          (float4*)dx);
+  else
+    act_bwd_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(x, dy, n, mode, dx);
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
 }
@@ -492,7 +540,10 @@ int dig3d_adam_step(float* param, const float* grad, float* exp_avg, float* exp_
 int dig3d_ewise(const float* a, const float* b, int64_t n, int32_t op, float* y, void* stream) {
   DIG3D_REQUIRE(a && b && y && (op == 0 || op == 1), "ewise: bad arguments");
   if (n == 0) return DIG3D_OK;
-  if (op == 0) mul_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, n, y);
+  if (vec4_ok(n, a, b, y)) {
+    if (op == 0) ewise4_kernel<0><<<ceil_div(n / 4, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)a, (const float4*)b, n / 4, (float4*)y);
+    else ewise4_kernel<1><<<ceil_div(n / 4, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)a, (const float4*)b, n / 4, (float4*)y);
+  } else if (op == 0) mul_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, n, y);
   else add_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, n, y);
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
