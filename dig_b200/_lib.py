@@ -68,6 +68,7 @@ SIGNATURES = {
     "dig3d_triplet_geometry": [P, P, P, P, P, c_int64, c_int32, P, P, P, P, P, P, P],
     "dig3d_edge_basis": [P, c_int64, c_double, c_int32, P, c_int32, c_int32, P, P, P],
     "dig3d_edge_basis_set_split": [c_int32],
+    "dig3d_triplet_basis_project_set_mode": [c_int32],
     "dig3d_triplet_basis": [P, P, P, P, c_int64, c_int32, P, P, P],
     "dig3d_triplet_basis_project": [P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int32, c_int32,
                                     c_int32, P, P, P, P, P],

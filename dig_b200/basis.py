@@ -296,3 +296,47 @@ def envelope_coefficients(exponent):
     (reference Envelope, features.py:151-164)."""
     p = exponent + 1
     return p, -(p + 1) * (p + 2) / 2, p * (p + 2), -p * (p + 1) / 2
+
+
+def harmonics_recurrence(theta, phi, num_spherical, dtype=np.float64):
+    """numpy twin of csrc/harmonics.cuh `ylm_recurrence`: the L*L real harmonics in the reference's flat order (per l:
+    m = 0, +1..+l, -l..-1) from the recurrences the reference's symbolic construction starts from (features.py:74-148),
+    evaluated numerically instead of through the simplified closed forms.  The fused projection kernel uses this form;
+    tests/test_basis.py pins it against the closed forms."""
+    L = num_spherical
+    theta = np.asarray(theta, dtype=dtype)
+    phi = np.asarray(phi, dtype=dtype)
+    f = dtype
+
+    def norm(l, m):
+        v = math.sqrt((2 * l + 1) * math.factorial(l - m) / (4 * math.pi * math.factorial(l + m)))
+        return f(v * (math.sqrt(2.0) if m else 1.0))
+
+    st, ct, sp, cp = np.sin(theta), np.cos(theta), np.sin(phi), np.cos(phi)
+    x, y, z = st * cp, st * sp, ct
+    out = np.zeros(theta.shape + (L * L,), dtype=dtype)
+    p2, p1 = np.ones_like(z), z
+    out[..., 0] = norm(0, 0)
+    if L > 1:
+        out[..., 1] = norm(1, 0) * z
+    for l in range(2, L):
+        p = (f((2.0 * l - 1.0) / l) * z) * p1 - f((l - 1.0) / l) * p2
+        out[..., l * l] = norm(l, 0) * p
+        p2, p1 = p1, p
+    s, c, pmm = np.zeros_like(z), np.ones_like(z), np.ones_like(z)
+    for m in range(1, L):
+        s, c = x * s + y * c, x * c - y * s
+        pmm = f(1 - 2 * m) * pmm
+        p2, p1 = np.zeros_like(z), pmm
+        for l in range(m, L):
+            if l == m:
+                p = pmm
+            elif l == m + 1:
+                p = (f(2 * m + 1) * z) * pmm
+            else:
+                p = (f((2.0 * l - 1.0) / (l - m)) * z) * p1 - f((l + m - 1) / (l - m)) * p2
+            n_p = norm(l, m) * p
+            out[..., l * l + m] = n_p * c
+            out[..., l * l + 2 * l + 1 - m] = n_p * s
+            p2, p1 = p1, p
+    return out

@@ -10,6 +10,7 @@
 // sbf / tbf: dig3d_triplet_basis_project contracts them with lin_sbf1 / lin_t1 of ALL layers at
 // once, grouped by the (k->j) edge so the radial half of the contraction is done once per edge.
 #include "common.cuh"
+#include "harmonics.cuh"
 #include "generated/basis_dimenet_7_6.cuh"
 #include "generated/basis_dimenet_3_6.cuh"
 #include "generated/basis_gemnet_2_3.cuh"
@@ -306,6 +307,151 @@ triplet_basis_project_kernel(const float* __restrict__ bess, const float* __rest
           for (int ab = 0; ab < NY; ++ab) acc_t = fmaf(yv[ab], R[ab], acc_t);
           t_p[o] = acc_t;
         }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// ------------------------------------------------------------------ fused projection, packed (round 2, default)
+// Same traversal and outputs as triplet_basis_project_kernel (torsion models), rebuilt around the FP32 issue rate
+// (that kernel: 140 M warp instructions per launch at the headline size, 60 % issue-active,
+// profiles/r01_project_ncu_summary.txt):
+//   * per-edge radial contraction: for a Bessel order b the NS + 1 outputs Rs[b], R[a*NS + b] share their NR Bessel
+//     values, so they run as (NS + 1) / 2 FFMA2 chains on pairs of OUTPUTS -- the weights of a pair sit side by side in
+//     shared memory (one LDS.64 per FFMA2 instead of one LDS.32 per FFMA), the Bessel values are staged duplicated;
+//     every half is the r-ascending chain of the scalar kernel;
+//   * the harmonics of a triplet are stored in that pair order ({Y_b0, Y[0*NS+b]}, {Y[1*NS+b], Y[2*NS+b]}, ...; row
+//     stride 60 floats: the 16-byte stores of eight lanes fall into eight different bank groups), so the per-triplet
+//     contraction is NS * (NS+1) / 2 FFMA2 on natural register pairs; sbf_p keeps the scalar kernel's summation order,
+//     t_p is summed as (NS+1)/2 interleaved partial sums;
+//   * RECURRENCE: the harmonics come from the recurrences of harmonics.cuh (two sincosf + ~250 multiply-adds) instead
+//     of the node-by-node closed forms (~1200 instructions); the radial contraction runs AFTER the harmonics so that
+//     its 56 result registers are not live while they are evaluated.
+template <class BS>
+struct PrjPackSmem {
+  static constexpr int NP = (BS::NS + 1) / 2;                       // output pairs per Bessel order
+  static constexpr int ROW = BS::NS * NP * 2;                       // harmonics per triplet in pair order
+  static constexpr int YLD = (ROW / 4) % 2 ? ROW : ROW + 4;         // odd number of 16-byte chunks per row
+  float2 wp[BS::NS * NP * BS::NR * 32];                             // [(b, p, r)][lane]
+  float2 bess2[PRJ_WARPS][BS::NB];                                  // {v, v}
+  alignas(16) float y[PRJ_WARPS][32][YLD];
+  int32_t trip[PRJ_WARPS][32];
+};
+
+template <class BS, bool RECURRENCE>
+__global__ void __launch_bounds__(PRJ_WARPS * 32, 2)
+triplet_basis_project_packed_kernel(const float* __restrict__ bess, const float* __restrict__ angle,
+                                    const float* __restrict__ torsion, const int32_t* __restrict__ src,
+                                    const int32_t* __restrict__ dst, const int32_t* __restrict__ row_ptr,
+                                    const int32_t* __restrict__ trip_ptr, const int32_t* __restrict__ graph_ptr,
+                                    const int64_t* __restrict__ batch, int n_edges, int n_triplets,
+                                    const float* __restrict__ w_sbf1, const float* __restrict__ w_t1,
+                                    float* __restrict__ sbf_p, float* __restrict__ t_p) {
+  constexpr int NS = BS::NS, NR = BS::NR, NB = BS::NB, NY = BS::NY;
+  using SM = PrjPackSmem<BS>;
+  constexpr int NP = SM::NP, ROW = SM::ROW;
+  static_assert((NS + 1) % 2 == 0 && ROW % 4 == 0, "packed projection: NS must be odd");
+  extern __shared__ __align__(16) unsigned char prj_smem_raw[];
+  SM& sm = *reinterpret_cast<SM*>(prj_smem_raw);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  // output o of order b: o = 0 -> Rs[b] (lin_sbf1 column b*NR + r), o >= 1 -> R[(o-1)*NS + b] (lin_t1 column ...)
+  for (int id = threadIdx.x; id < NS * NP * NR * 32; id += PRJ_WARPS * 32) {
+    const int q = id & 31, r = (id >> 5) % NR, p = ((id >> 5) / NR) % NP, b = (id >> 5) / (NR * NP);
+    float v[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int o = 2 * p + h;
+      v[h] = o == 0 ? __ldg(w_sbf1 + q * NB + b * NR + r) : __ldg(w_t1 + q * (NY * NR) + ((o - 1) * NS + b) * NR + r);
+    }
+    sm.wp[id] = make_float2(v[0], v[1]);
+  }
+  __syncthreads();
+  for (int kj = blockIdx.x * PRJ_WARPS + w; kj < n_edges; kj += gridDim.x * PRJ_WARPS) {
+    const int k = src[kj], j = dst[kj];
+    __syncwarp();
+    for (int c = lane; c < NB; c += 32) {
+      const float v = __ldg(bess + (size_t)kj * NB + c);
+      sm.bess2[w][c] = make_float2(v, v);
+    }
+    const int jbase = row_ptr[j], dj = row_ptr[j + 1] - jbase;
+    const int rank_k = kj - jbase;  // position of k among j's in-neighbours
+    const int g = (int)batch[j];
+    const int lo = graph_ptr[g], hi = graph_ptr[g + 1];
+    for (int c0 = lo; c0 < hi; c0 += 32) {
+      // out-edges e = (j -> i), i != k, among the nodes c0 .. c0 + 31 of j's graph (as in the scalar kernel)
+      const int i = c0 + lane;
+      int t = -1;
+      if (i < hi && i != k && i != j) {
+        const int ib = row_ptr[i], di = row_ptr[i + 1] - ib;
+        int a = 0, b = di;
+        while (a < b) { int mid = (a + b) >> 1; if (src[ib + mid] < j) a = mid + 1; else b = mid; }
+        if (a < di && src[ib + a] == j) {
+          const int e = ib + a;
+          int a2 = 0, b2 = dj;
+          while (a2 < b2) { int mid = (a2 + b2) >> 1; if (src[jbase + mid] < i) a2 = mid + 1; else b2 = mid; }
+          const bool i_in = (a2 < dj && src[jbase + a2] == i);
+          t = trip_ptr[e] + rank_k - ((i_in && a2 < rank_k) ? 1 : 0);
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, t >= 0);
+      const int cnt = __popc(m);
+      if (cnt == 0) continue;
+      if (t >= 0) {
+        const int slot = __popc(m & ((1u << lane) - 1));
+        sm.trip[w][slot] = t;
+        float y[NY], y0[NS];
+        if (RECURRENCE) {
+          ylm_recurrence<NS>(angle[t], torsion[t], y, y0);
+        } else {
+          BS::yl0(angle[t], y0);
+          BS::ylm(angle[t], torsion[t], y);
+        }
+        float yp[ROW];
+#pragma unroll
+        for (int b = 0; b < NS; ++b)
+#pragma unroll
+          for (int o = 0; o <= NS; ++o) yp[(b * NP + (o >> 1)) * 2 + (o & 1)] = o == 0 ? y0[b] : y[(o - 1) * NS + b];
+        float4* row = reinterpret_cast<float4*>(&sm.y[w][slot][0]);
+#pragma unroll
+        for (int c = 0; c < ROW / 4; ++c) row[c] = make_float4(yp[4 * c], yp[4 * c + 1], yp[4 * c + 2], yp[4 * c + 3]);
+      }
+      __syncwarp();
+      // per-edge radial contraction, lane = output column q (4 layers x 8)
+      float2 R[NS][NP];
+#pragma unroll
+      for (int b = 0; b < NS; ++b) {
+        float2 rb[NR];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) rb[r] = sm.bess2[w][b * NR + r];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int r = 0; r < NR; ++r) acc = ffma2(rb[r], sm.wp[((b * NP + p) * NR + r) * 32 + lane], acc);
+          R[b][p] = acc;
+        }
+      }
+      for (int s = 0; s < cnt; ++s) {
+        const int tt = sm.trip[w][s];
+        const float4* row = reinterpret_cast<const float4*>(&sm.y[w][s][0]);
+        float2 acc[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) acc[p] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < ROW / 4; ++c) {
+          const float4 v = row[c];                     // pairs 2c, 2c + 1 of the row = (b, p) in b-major order
+          const int i0 = 2 * c, i1 = 2 * c + 1;
+          acc[i0 % NP] = ffma2(make_float2(v.x, v.y), R[i0 / NP][i0 % NP], acc[i0 % NP]);
+          acc[i1 % NP] = ffma2(make_float2(v.z, v.w), R[i1 / NP][i1 % NP], acc[i1 % NP]);
+        }
+        // acc[0].x = sum_b Y_b0 Rs[b] (b ascending, as the scalar kernel); everything else belongs to t_p
+        float2 rest = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int p = 1; p < NP; ++p) rest = fadd2(rest, acc[p]);
+        const size_t o = ((size_t)(lane >> 3) * n_triplets + tt) * 8 + (lane & 7);
+        sbf_p[o] = acc[0].x;
+        t_p[o] = (acc[0].y + rest.x) + rest.y;
       }
       __syncwarp();
     }
@@ -923,6 +1069,9 @@ triplet_basis_project_bwd_geom_kernel(const float* __restrict__ bess, const floa
   }
 }
 
+// fused projection of the torsion models: 0 = scalar kernel (round 1), 1 = packed kernel with the closed-form
+// harmonics, 2 = packed kernel with the recurrence harmonics (default)
+static int h_project_mode = 2;
 static int h_edge_basis_split = 1;   // 1: one thread per (edge, Bessel order); 0: one thread per edge (round 1)
 
 template <class BS>
@@ -1081,16 +1230,37 @@ int dig3d_triplet_basis_project(const float* bess, const float* angle, const flo
     kfn<<<grid, PRJ_WARPS * 32, smem, st>>>(bess, angle, torsion, src, dst, row_ptr, trip_ptr, graph_ptr,   \
                                             batch, (int)n_edges, (int)n_triplets, w_sbf1, w_t1, sbf_p, t_p);\
   }
-#define DIG3D_PRJ(BS) \
-  if (tors) DIG3D_PRJ_ONE(BS, true) else DIG3D_PRJ_ONE(BS, false)
+#define DIG3D_PRJP_ONE(BS, REC)                                                                            \
+  {                                                                                                         \
+    auto kfn = triplet_basis_project_packed_kernel<BS, REC>;                                                \
+    const size_t smem = sizeof(PrjPackSmem<BS>);                                                            \
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { \
+      set_error("triplet_basis_project: cannot reserve %zu bytes of shared memory", smem);                  \
+      return DIG3D_ECUDA;                                                                                   \
+    }                                                                                                       \
+    kfn<<<grid, PRJ_WARPS * 32, smem, st>>>(bess, angle, torsion, src, dst, row_ptr, trip_ptr, graph_ptr,   \
+                                            batch, (int)n_edges, (int)n_triplets, w_sbf1, w_t1, sbf_p, t_p);\
+  }
+#define DIG3D_PRJ(BS)                                                  \
+  if (tors && h_project_mode == 2) DIG3D_PRJP_ONE(BS, true)            \
+  else if (tors && h_project_mode == 1) DIG3D_PRJP_ONE(BS, false)      \
+  else if (tors) DIG3D_PRJ_ONE(BS, true)                               \
+  else DIG3D_PRJ_ONE(BS, false)
   switch (basis_id) {
     case 0: DIG3D_PRJ(B76); break;
     case 1: DIG3D_PRJ(B36); break;
     default: set_error("triplet_basis_project: unsupported basis_id %d", basis_id); return DIG3D_EUNSUPPORTED;
   }
 #undef DIG3D_PRJ_ONE
+#undef DIG3D_PRJP_ONE
 #undef DIG3D_PRJ
   DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_triplet_basis_project_set_mode(int32_t mode) {
+  DIG3D_REQUIRE(mode >= 0 && mode <= 2, "triplet_basis_project_set_mode: mode must be 0, 1 or 2");
+  h_project_mode = mode;
   return DIG3D_OK;
 }
 

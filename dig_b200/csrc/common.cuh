@@ -60,6 +60,30 @@ __device__ __forceinline__ f3 load3(const float* __restrict__ p, int n) {
   return {__ldg(p + 3 * n), __ldg(p + 3 * n + 1), __ldg(p + 3 * n + 2)};
 }
 
+// ---- packed fp32 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2 on 64-bit register pairs) ----------------------------
+// Each half is an ordinary round-to-nearest fp32 operation, so a packed chain is bit-identical to the two scalar
+// chains it replaces; the FP32 pipe issues one packed instruction in the slot of one scalar FFMA
+// (tools/ffma_rate.cu, profiles/r02_ffma2_rate.txt).
+__device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c) {
+  unsigned long long ra = *reinterpret_cast<const unsigned long long*>(&a);
+  unsigned long long rb = *reinterpret_cast<const unsigned long long*>(&b);
+  unsigned long long rc = *reinterpret_cast<const unsigned long long*>(&c), rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 fmul2(const float2 a, const float2 b) {
+  unsigned long long ra = *reinterpret_cast<const unsigned long long*>(&a);
+  unsigned long long rb = *reinterpret_cast<const unsigned long long*>(&b), rd;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 fadd2(const float2 a, const float2 b) {
+  unsigned long long ra = *reinterpret_cast<const unsigned long long*>(&a);
+  unsigned long long rb = *reinterpret_cast<const unsigned long long*>(&b), rd;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+
 __device__ __forceinline__ float swish(float x) {
   // x * sigmoid(x); ATen sigmoid = 1 / (1 + exp(-x)) in fp32
   return __fmul_rn(x, __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))));

@@ -211,6 +211,87 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"
 
 // ---------------------------------------------------------------------------------- triplet gather (SIMT)
 // m[e] = sum_{t in trip(e)} x_down[kj(t)] * lin_sbf2(sbf_p[t]) * lin_t2(t_p[t])      spherenet.py:163-171
+// ---- packed inner loop shared by the edge-centred and the node-centred gather ------------------------------------
+// A lane owns channels `lane` and `lane + 32`.  Per triplet and channel the work is two 8-term expansions
+// (lin_sbf2, lin_t2) and three products; the expansions run as FFMA2 chains (common.cuh):
+//   TORSION   : the halves of a pair are the sbf and the t expansion of the SAME triplet and channel -- weights
+//               {w_sbf2[c][q], w_t2[c][q]} and staged values {sbf_p[t][q], t_p[t][q]} pair up naturally;
+//   !TORSION  : the halves are the sbf expansions of two CONSECUTIVE triplets (weights duplicated, staged values
+//               interleaved pairwise).
+// Every half is the same k-ascending fmaf chain as before, so the results are bit-identical to the scalar loops.
+template <bool TORSION>
+__device__ __forceinline__ void tg_load_weights(float2 (&w)[2][8], const float* __restrict__ w_sbf2,
+                                                const float* __restrict__ w_t2, int lane) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float a = __ldg(w_sbf2 + (lane + 32 * h) * 8 + q);
+      w[h][q] = make_float2(a, TORSION ? __ldg(w_t2 + (lane + 32 * h) * 8 + q) : a);
+    }
+}
+
+// st: the warp's 64 x float2 staging area.  Lane l holds element (triplet l / 8, q = l % 8) of the chunk's first four
+// triplets in (sa, ta) and of the last four in (sb, tb).
+template <bool TORSION>
+__device__ __forceinline__ void tg_stage(float2* st, int lane, float sa, float sb, float ta, float tb) {
+  if (TORSION) {
+    st[lane] = make_float2(sa, ta);
+    st[lane + 32] = make_float2(sb, tb);
+  } else {
+    float* f = reinterpret_cast<float*>(st);
+    const int q = lane & 7, u = lane >> 3;                 // (u, q) -> pair (u >> 1), half (u & 1)
+    f[((u >> 1) * 8 + q) * 2 + (u & 1)] = sa;
+    f[(((u >> 1) + 2) * 8 + q) * 2 + (u & 1)] = sb;
+  }
+}
+
+template <bool TORSION, class XRow>
+__device__ __forceinline__ void tg_accumulate(const float2* st, int n8, const float2 (&w)[2][8], XRow xrow, float& a0,
+                                              float& a1) {
+  if (TORSION) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (u < n8) {
+        float2 gh0 = make_float2(0.f, 0.f), gh1 = make_float2(0.f, 0.f);      // {lin_sbf2, lin_t2} of channel 0 / 1
+#pragma unroll
+        for (int q = 0; q < 8; q += 2) {
+          const float4 v = *reinterpret_cast<const float4*>(st + u * 8 + q);
+          const float2 v0 = make_float2(v.x, v.y), v1 = make_float2(v.z, v.w);
+          gh0 = ffma2(w[0][q], v0, gh0); gh1 = ffma2(w[1][q], v0, gh1);
+          gh0 = ffma2(w[0][q + 1], v1, gh0); gh1 = ffma2(w[1][q + 1], v1, gh1);
+        }
+        float x0, x1;
+        xrow(u, x0, x1);
+        float m0 = __fmul_rn(x0, gh0.x), m1 = __fmul_rn(x1, gh1.x);
+        m0 = __fmul_rn(m0, gh0.y); m1 = __fmul_rn(m1, gh1.y);
+        a0 += m0; a1 += m1;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int up = 0; up < 4; ++up) {
+      if (2 * up < n8) {
+        float2 g0 = make_float2(0.f, 0.f), g1 = make_float2(0.f, 0.f);        // triplets 2 up, 2 up + 1
+#pragma unroll
+        for (int q = 0; q < 8; q += 2) {
+          const float4 v = *reinterpret_cast<const float4*>(st + up * 8 + q);
+          const float2 v0 = make_float2(v.x, v.y), v1 = make_float2(v.z, v.w);
+          g0 = ffma2(w[0][q], v0, g0); g1 = ffma2(w[1][q], v0, g1);
+          g0 = ffma2(w[0][q + 1], v1, g0); g1 = ffma2(w[1][q + 1], v1, g1);
+        }
+        float x0, x1;
+        xrow(2 * up, x0, x1);
+        a0 += __fmul_rn(x0, g0.x); a1 += __fmul_rn(x1, g1.x);
+        if (2 * up + 1 < n8) {
+          xrow(2 * up + 1, x0, x1);
+          a0 += __fmul_rn(x0, g0.y); a1 += __fmul_rn(x1, g1.y);
+        }
+      }
+    }
+  }
+}
+
 template <bool TORSION>
 __global__ void __launch_bounds__(256, 3)
 sphere_triplet_gather_kernel(const float* __restrict__ x_down, const float* __restrict__ sbf_p,
@@ -220,18 +301,12 @@ sphere_triplet_gather_kernel(const float* __restrict__ x_down, const float* __re
                              const float* __restrict__ w_t2, float* __restrict__ m) {
   // per warp: the projected basis rows of 8 consecutive triplets (8 x 8 floats each for sbf and t), loaded
   // with two coalesced 256-byte reads instead of 32 broadcast loads, then re-read as warp broadcasts
-  __shared__ __align__(16) float stage[8][2][64];
+  __shared__ __align__(16) float2 stage[8][64];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (e >= n_edges) return;
-  float ws2[2][8], wt2[2][8];
-#pragma unroll
-  for (int h = 0; h < 2; ++h)
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      ws2[h][q] = __ldg(w_sbf2 + (lane + 32 * h) * 8 + q);
-      wt2[h][q] = TORSION ? __ldg(w_t2 + (lane + 32 * h) * 8 + q) : 0.f;
-    }
+  float2 wq[2][8];
+  tg_load_weights<TORSION>(wq, w_sbf2, w_t2, lane);
   const int j = src[e], i = dst[e];
   const int base = row_ptr[j], d = row_ptr[j + 1] - base;
   // position of i among j's in-neighbours (d if absent): triplet r of this edge uses slot r + (r >= p_i)
@@ -261,31 +336,9 @@ sphere_triplet_gather_kernel(const float* __restrict__ x_down, const float* __re
       x1[u] = __ldg(x_down + (size_t)kj * 64 + lane + 32);
     }
     __syncwarp();
-    stage[w][0][lane] = sa; stage[w][0][lane + 32] = sb;
-    if (TORSION) { stage[w][1][lane] = ta; stage[w][1][lane + 32] = tb; }
+    tg_stage<TORSION>(stage[w], lane, sa, sb, ta, tb);
     __syncwarp();
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      if (u < n8) {
-        const float4 s0 = *reinterpret_cast<const float4*>(&stage[w][0][u * 8]);
-        const float4 s1 = *reinterpret_cast<const float4*>(&stage[w][0][u * 8 + 4]);
-        const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-        float g0 = 0.f, g1 = 0.f;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) { g0 = fmaf(ws2[0][q], sv[q], g0); g1 = fmaf(ws2[1][q], sv[q], g1); }
-        float m0 = __fmul_rn(x0[u], g0), m1 = __fmul_rn(x1[u], g1);
-        if (TORSION) {
-          const float4 q0 = *reinterpret_cast<const float4*>(&stage[w][1][u * 8]);
-          const float4 q1 = *reinterpret_cast<const float4*>(&stage[w][1][u * 8 + 4]);
-          const float tv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-          float h0 = 0.f, h1 = 0.f;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) { h0 = fmaf(wt2[0][q], tv[q], h0); h1 = fmaf(wt2[1][q], tv[q], h1); }
-          m0 = __fmul_rn(m0, h0); m1 = __fmul_rn(m1, h1);
-        }
-        a0 += m0; a1 += m1;
-      }
-    }
+    tg_accumulate<TORSION>(stage[w], n8, wq, [&](int u, float& xa, float& xb) { xa = x0[u]; xb = x1[u]; }, a0, a1);
   }
   m[(size_t)e * 64 + lane] = a0;
   m[(size_t)e * 64 + lane + 32] = a1;
@@ -313,7 +366,7 @@ sphere_triplet_gather_node_kernel(const float* __restrict__ x_down, const float*
                                   float* __restrict__ m) {
   extern __shared__ __align__(128) float tgn_rows[];          // [cap][64]: x_down rows of j's in-edges
   float (*rows)[64] = reinterpret_cast<float (*)[64]>(tgn_rows);
-  __shared__ __align__(16) float stage[TGN_THREADS / 32][2][64];
+  __shared__ __align__(16) float2 stage[TGN_THREADS / 32][64];
   __shared__ int in_src[TGN_MAXIN];
   __shared__ int out_e[TGN_LIST], out_p[TGN_LIST];
   __shared__ int n_out;
@@ -333,14 +386,8 @@ sphere_triplet_gather_node_kernel(const float* __restrict__ x_down, const float*
     bulk_g2s(&rows[0][0], x_down + (size_t)base * 64, (uint32_t)d * 256u, &bar);
   }
   for (int k = tid; k < d; k += TGN_THREADS) in_src[k] = src[base + k];
-  float ws2[2][8], wt2[2][8];
-#pragma unroll
-  for (int h = 0; h < 2; ++h)
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      ws2[h][q] = __ldg(w_sbf2 + (lane + 32 * h) * 8 + q);
-      wt2[h][q] = TORSION ? __ldg(w_t2 + (lane + 32 * h) * 8 + q) : 0.f;
-    }
+  float2 wq[2][8];
+  tg_load_weights<TORSION>(wq, w_sbf2, w_t2, lane);
   __syncthreads();
   bool staged = false;
   for (int c0 = lo; c0 < hi; c0 += TGN_LIST) {
@@ -361,50 +408,44 @@ sphere_triplet_gather_node_kernel(const float* __restrict__ x_down, const float*
     __syncthreads();
     const int no = n_out;
     if (!staged && no > 0 && d > 0) { mbar_wait(&bar, 0); staged = true; }
-    for (int idx = w; idx < no; idx += TGN_THREADS / 32) {
-      const int e = out_e[idx], p_i = out_p[idx];
-      const int t0 = trip_ptr[e], nt = d - (p_i < d ? 1 : 0);
+    // The projected-basis values of a chunk (8 triplets) are fetched one chunk AHEAD of their use -- the next chunk of
+    // this edge, or the first chunk of the warp's next edge -- so the L2 latency hides under the FFMA2 chains.
+    auto fetch = [&](int t_first, int left, float& sa, float& sb, float& ta, float& tb) {
+      const int lim = min(8, left) * 8;
+      const float* sp = sbf_p + (size_t)t_first * 8;
+      sa = lane < lim ? __ldg(sp + lane) : 0.f; sb = lane + 32 < lim ? __ldg(sp + lane + 32) : 0.f;
+      ta = 0.f; tb = 0.f;
+      if (TORSION) {
+        const float* tp = t_p + (size_t)t_first * 8;
+        ta = lane < lim ? __ldg(tp + lane) : 0.f; tb = lane + 32 < lim ? __ldg(tp + lane + 32) : 0.f;
+      }
+    };
+    int idx = w, e = 0, p_i = 0, t0 = 0, nt = 0;
+    float sa = 0.f, sb = 0.f, ta = 0.f, tb = 0.f;
+    bool fetched = false;
+    if (idx < no) { e = out_e[idx]; p_i = out_p[idx]; t0 = trip_ptr[e]; nt = d - (p_i < d ? 1 : 0); }
+    while (idx < no) {
+      const int idx_n = idx + TGN_THREADS / 32;
+      int e_n = 0, p_n = 0, t0_n = 0, nt_n = 0;
+      if (idx_n < no) { e_n = out_e[idx_n]; p_n = out_p[idx_n]; t0_n = trip_ptr[e_n]; nt_n = d - (p_n < d ? 1 : 0); }
+      if (!fetched && nt > 0) fetch(t0, nt, sa, sb, ta, tb);
+      fetched = false;
       float a0 = 0.f, a1 = 0.f;
       for (int r0 = 0; r0 < nt; r0 += 8) {
-        const int n8 = min(8, nt - r0), lim = n8 * 8;
-        const float* sp = sbf_p + (size_t)(t0 + r0) * 8;
-        const float sa = lane < lim ? __ldg(sp + lane) : 0.f, sb = lane + 32 < lim ? __ldg(sp + lane + 32) : 0.f;
-        float ta = 0.f, tb = 0.f;
-        if (TORSION) {
-          const float* tp = t_p + (size_t)(t0 + r0) * 8;
-          ta = lane < lim ? __ldg(tp + lane) : 0.f; tb = lane + 32 < lim ? __ldg(tp + lane + 32) : 0.f;
-        }
+        const int n8 = min(8, nt - r0);
         __syncwarp();
-        stage[w][0][lane] = sa; stage[w][0][lane + 32] = sb;
-        if (TORSION) { stage[w][1][lane] = ta; stage[w][1][lane + 32] = tb; }
+        tg_stage<TORSION>(stage[w], lane, sa, sb, ta, tb);
         __syncwarp();
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          if (u < n8) {
-            const int r = r0 + u, row = r + (r >= p_i ? 1 : 0);
-            const float x0 = rows[row][lane], x1 = rows[row][lane + 32];
-            const float4 s0 = *reinterpret_cast<const float4*>(&stage[w][0][u * 8]);
-            const float4 s1 = *reinterpret_cast<const float4*>(&stage[w][0][u * 8 + 4]);
-            const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-            float g0 = 0.f, g1 = 0.f;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) { g0 = fmaf(ws2[0][q], sv[q], g0); g1 = fmaf(ws2[1][q], sv[q], g1); }
-            float m0 = __fmul_rn(x0, g0), m1 = __fmul_rn(x1, g1);
-            if (TORSION) {
-              const float4 q0 = *reinterpret_cast<const float4*>(&stage[w][1][u * 8]);
-              const float4 q1 = *reinterpret_cast<const float4*>(&stage[w][1][u * 8 + 4]);
-              const float tv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-              float h0 = 0.f, h1 = 0.f;
-#pragma unroll
-              for (int q = 0; q < 8; ++q) { h0 = fmaf(wt2[0][q], tv[q], h0); h1 = fmaf(wt2[1][q], tv[q], h1); }
-              m0 = __fmul_rn(m0, h0); m1 = __fmul_rn(m1, h1);
-            }
-            a0 += m0; a1 += m1;
-          }
-        }
+        if (r0 + 8 < nt) fetch(t0 + r0 + 8, nt - r0 - 8, sa, sb, ta, tb);
+        else if (idx_n < no && nt_n > 0) { fetch(t0_n, nt_n, sa, sb, ta, tb); fetched = true; }
+        tg_accumulate<TORSION>(stage[w], n8, wq, [=](int u, float& xa, float& xb) {
+          const int r = r0 + u, row = r + (r >= p_i ? 1 : 0);
+          xa = rows[row][lane]; xb = rows[row][lane + 32];
+        }, a0, a1);
       }
       m[(size_t)e * 64 + lane] = a0;
       m[(size_t)e * 64 + lane + 32] = a1;
+      idx = idx_n; e = e_n; p_i = p_n; t0 = t0_n; nt = nt_n;
     }
     __syncthreads();
     if (tid == 0) n_out = 0;

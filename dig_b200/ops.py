@@ -177,6 +177,16 @@ def triplet_basis(bess, angle, torsion, idx_kj, basis_id, ns, nr, want_tbf):
 # eight contraction warps); kept as the starting point for a version that keeps several nodes in flight per CTA.
 PROJECT_MODE = ["edge"]
 
+# Kernel behind the "edge" mode for the torsion models (dig3d_triplet_basis_project_set_mode, process-wide):
+# "scalar" = round 1's kernel (reference-rounded closed-form harmonics, scalar FMA chains), "packed" = FFMA2 chains on
+# pairs of outputs with the same closed forms, "recurrence" (default) = packed + harmonics from the Legendre / angle-addition
+# recurrences (csrc/harmonics.cuh).
+PROJECT_KERNELS = {"scalar": 0, "packed": 1, "recurrence": 2}
+
+
+def set_project_kernel(name):
+    call("dig3d_triplet_basis_project_set_mode", PROJECT_KERNELS[name])
+
 
 def triplet_basis_project(g, bess, basis_id, w_sbf1_rows, w_t1_rows):
     """w_sbf1_rows: [32, ns*nr], w_t1_rows: [32, ns*ns*nr] or None.

@@ -126,7 +126,12 @@ int dig3d_triplet_basis_project(const float* bess, const float* angle, const flo
                                 int64_t n_edges, int64_t n_triplets, int32_t basis_id, int32_t n_layers,
                                 int32_t basis_emb, const float* w_sbf1, const float* w_t1, float* sbf_p,
                                 float* t_p, void* stream);
-/* Same outputs (bit-identical) with one CTA per MIDDLE node j of the triplets: the out-edges of j are found once, the
+/* Process-wide experiment switch for the torsion models' projection (spherenet.py:163,167): 0 = scalar kernel with the
+ * reference-rounded closed-form harmonics (round 1), 1 = packed (FFMA2) kernel with the same closed forms, 2 (default) =
+ * packed kernel with the harmonics evaluated from the recurrences the reference derives its closed forms from
+ * (features.py:74-148; csrc/harmonics.cuh).  DimeNet++ (no torsion) always takes the scalar kernel. */
+int dig3d_triplet_basis_project_set_mode(int32_t mode);
+/* Same outputs (bit-identical to mode 0) with one CTA per MIDDLE node j of the triplets: the out-edges of j are found once, the
  * harmonics of up to 256 triplets are evaluated with all threads busy, then contracted per (k -> j) edge. */
 int dig3d_triplet_basis_project_node(const float* bess, const float* angle, const float* torsion, const int32_t* src,
                                      const int32_t* row_ptr, const int32_t* trip_ptr, const int32_t* graph_ptr,

@@ -107,3 +107,28 @@ def test_second_order_sources_match_finite_differences():
             fd = (ev(d1, theta=th + h) - ev(d1, theta=th - h)) / (2 * h)
             assert abs(ev(d2, theta=th) - fd) <= 1e-6 * max(1.0, abs(fd))
     assert len(second["bessel_dxx"]) == 18 and len(second["yl0_dtheta2"]) == 3
+
+
+@pytest.mark.parametrize("ns", [7, 3])
+def test_recurrence_harmonics_equal_the_closed_forms(ns):
+    """csrc/harmonics.cuh (numpy twin: basis.harmonics_recurrence) evaluates the harmonics of the fused projection from
+    the recurrences the reference's symbolic construction starts from; in exact arithmetic they ARE the reference's
+    simplified closed forms (flat order included), and in fp32 they are at least as close to the fp64 values."""
+    import math
+    src = basis.basis_sources("dimenet", ns, 6)
+    rng = np.random.default_rng(0)
+    th, ph = rng.uniform(0, math.pi, 2000), rng.uniform(0, 2 * math.pi, 2000)
+    env = {"sin": np.sin, "cos": np.cos, "sqrt": np.sqrt, "pi": math.pi}
+    ref = np.stack([np.broadcast_to(eval("lambda theta, phi: " + s, env)(th, ph), th.shape) for s in src["ylm"]], -1)
+    got = basis.harmonics_recurrence(th, ph, ns)
+    assert got.shape == ref.shape == (2000, ns * ns)
+    assert np.abs(got - ref).max() < 1e-12
+    y0 = np.stack([np.broadcast_to(eval("lambda theta: " + s, env)(th), th.shape) for s in src["yl0"]], -1)
+    assert np.abs(y0 - got[:, [l * l for l in range(ns)]]).max() < 1e-12       # the zonal entries double as yl0
+    got32 = basis.harmonics_recurrence(th, ph, ns, np.float32)
+    env32 = dict(env, pi=np.float32(math.pi))
+    th32, ph32 = th.astype(np.float32), ph.astype(np.float32)
+    ref32 = np.stack([np.broadcast_to(eval("lambda theta, phi: " + s, env32)(th32, ph32), th.shape)
+                      for s in src["ylm"]], -1)
+    assert np.abs(got32 - ref).max() < 3e-6
+    assert np.abs(got32 - ref).max() <= 1.5 * np.abs(ref32.astype(np.float64) - ref).max() + 5e-7

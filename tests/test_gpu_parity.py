@@ -83,12 +83,27 @@ def test_basis_bit_exact(name):
         assert torch.equal(tbf, it["tbf"])
     # fused projection (never materialises sbf/tbf) vs explicit fp32 matmul on the same values
     w_s, w_t = model._projection_rows(0, 4)
-    sbf_p, t_p = ops.triplet_basis_project(gr, bess, bid, w_s, w_t)        # layer-major [4, T, 8]
-    sbf_p = sbf_p.permute(1, 0, 2).reshape(-1, 32)
-    t_p = t_p.permute(1, 0, 2).reshape(-1, 32) if t_p is not None else None
-    assert rel_err(sbf_p.cpu().numpy(), (it["sbf"].double() @ w_s.double().t()).cpu().numpy()) < 2e-6
-    if tors:
-        assert rel_err(t_p.cpu().numpy(), (it["tbf"].double() @ w_t.double().t()).cpu().numpy()) < 2e-6
+    ref_s = (it["sbf"].double() @ w_s.double().t()).cpu().numpy()
+    ref_t = (it["tbf"].double() @ w_t.double().t()).cpu().numpy() if tors else None
+    # "scalar" / "packed": the reference-rounded closed-form harmonics (2e-6 = fp32 summation noise of the 294-term
+    # contraction).  "recurrence" (default): the same functions from their recurrences -- the reference's own fp32
+    # closed forms sit up to 4e-6 from the fp64 values (tests/test_basis.py), so the bound is 5e-6 against a matmul of
+    # the reference-rounded basis.
+    got = {}
+    try:
+        for kernel, tol in (("scalar", 2e-6), ("packed", 2e-6), ("recurrence", 5e-6)):
+            ops.set_project_kernel(kernel)
+            sbf_p, t_p = ops.triplet_basis_project(gr, bess, bid, w_s, w_t)        # layer-major [4, T, 8]
+            sbf_p = sbf_p.permute(1, 0, 2).reshape(-1, 32)
+            t_p = t_p.permute(1, 0, 2).reshape(-1, 32) if t_p is not None else None
+            got[kernel] = (sbf_p.clone(), t_p)
+            assert rel_err(sbf_p.cpu().numpy(), ref_s) < tol, kernel
+            if tors:
+                assert rel_err(t_p.cpu().numpy(), ref_t) < tol, kernel
+    finally:
+        ops.set_project_kernel("recurrence")
+    if tors:    # the packed kernel keeps the scalar kernel's summation order for sbf_p (same harmonics, same chains)
+        assert torch.equal(got["scalar"][0], got["packed"][0])
 
 
 @pytest.mark.parametrize("name", ["spherenet_qm9", "dimenetpp_md17", "spherenet_ns3"])
@@ -780,11 +795,15 @@ def test_node_centred_projection_equals_edge_centred(cls_name):
     rbf0, bess = ops.edge_basis(g.dist, 5.0, 5, model.emb.dist_emb.freq, 0, not tors, 6, 42)
     w_s, w_t = model._projection_rows(0, 4)
     outs = []
-    for mode in ("edge", "node"):
-        ops.PROJECT_MODE[0] = mode
-        s_p, t_p = ops.triplet_basis_project(g, bess, 0, w_s, w_t)
-        outs.append((s_p.clone(), None if t_p is None else t_p.clone()))
-    ops.PROJECT_MODE[0] = "edge"
+    ops.set_project_kernel("scalar")          # the node-centred kernel is the twin of the scalar edge-centred one
+    try:
+        for mode in ("edge", "node"):
+            ops.PROJECT_MODE[0] = mode
+            s_p, t_p = ops.triplet_basis_project(g, bess, 0, w_s, w_t)
+            outs.append((s_p.clone(), None if t_p is None else t_p.clone()))
+    finally:
+        ops.PROJECT_MODE[0] = "edge"
+        ops.set_project_kernel("recurrence")
     assert g.n_triplets > 1000 and torch.isfinite(outs[1][0]).all()
     assert torch.equal(outs[0][0], outs[1][0])
     if tors:
