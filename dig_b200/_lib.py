@@ -89,6 +89,7 @@ SIGNATURES = {
     "dig3d_sphere_update_e_a_tc": [P, P, c_int64, POINTER(TcUpdateE), P, P, P],
     "dig3d_sphere_triplet_gather": [P, P, P, c_int32, P, P, P, P, c_int64, P, P, P, P],
     "dig3d_sphere_triplet_gather_node": [P, P, P, c_int32, P, P, P, P, P, c_int64, c_int32, P, P, P, P],
+    "dig3d_sphere_triplet_gather_warp": [P, P, P, c_int32, P, P, P, P, P, c_int64, c_int32, c_int32, P, P, P, P],
     "dig3d_sphere_triplet_gather_tc": [P, P, P, c_int32, P, P, P, P, P, c_int64, c_int32, P, P, P, P],
     "dig3d_sphere_update_e_b_tc": [P, P, P, P, P, c_int64, POINTER(TcUpdateE), P, P, P],
     "dig3d_tc_set_fast_swish": [c_int32],

@@ -128,17 +128,23 @@ __device__ __forceinline__ int find_sorted(const int32_t* __restrict__ list, int
 }
 
 // ------------------------------------------------------------------ triplet count per node
+// One WARP per node, lane = in-neighbour slot: the per-neighbour binary searches (six dependent L2 round trips each) run
+// side by side instead of one after the other in a single thread (round 1: one thread per node, 23 us at 2 304 nodes --
+// pure latency).
 __global__ void triplet_count_kernel(const int32_t* __restrict__ nbr, const int32_t* __restrict__ deg,
                                      int n_nodes, int cap, int32_t* __restrict__ tcnt) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= n_nodes) return;
-  int d = deg[i], cnt = 0;
-  for (int s = 0; s < d; ++s) {
-    int j = nbr[(size_t)i * cap + s];
-    int dj = deg[j];
+  const int d = deg[i];
+  int cnt = 0;
+  for (int s = lane; s < d; s += 32) {
+    const int j = nbr[(size_t)i * cap + s];
+    const int dj = deg[j];
     cnt += dj - (find_sorted(nbr + (size_t)j * cap, dj, i) >= 0 ? 1 : 0);
   }
-  tcnt[i] = cnt;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) tcnt[i] = cnt;
 }
 
 // ------------------------------------------------------------------ single-CTA dual exclusive scan
@@ -189,33 +195,47 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t* __rest
 }
 
 // ------------------------------------------------------------------ edge fill
+// One WARP per target node, lane = in-neighbour slot (round 1: one thread per node walking its <= 33 edges, 28 us of
+// dependent loads).  The triplet offsets of the node's edges are a warp prefix sum of the per-edge counts.
 __global__ void edge_fill_kernel(const float* __restrict__ pos, const int32_t* __restrict__ nbr,
                                  const int32_t* __restrict__ deg, const int32_t* __restrict__ row_ptr,
                                  const int32_t* __restrict__ node_trip_ptr, int n_nodes, int cap,
                                  int64_t n_edges, int64_t* __restrict__ edge_index, int32_t* __restrict__ src,
                                  int32_t* __restrict__ dst, float* __restrict__ dist, float* __restrict__ vec,
                                  int32_t* __restrict__ trip_ptr) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= n_nodes) return;
-  int d = deg[i], e0 = row_ptr[i], t = node_trip_ptr[i];
-  f3 pi = load3(pos, i);
-  for (int s = 0; s < d; ++s) {
-    int j = nbr[(size_t)i * cap + s];
-    int e = e0 + s;
-    src[e] = j; dst[e] = i;
-    if (edge_index) { edge_index[e] = j; edge_index[n_edges + e] = i; }
-    f3 pj = load3(pos, j);
-    // (pos[i]-pos[j]).pow(2).sum(-1).sqrt()   geometric_computing.py:25
-    dist[e] = norm3_aten(sub3(pi, pj));
-    if (vec) {  // vecs = pos[j] - pos[i]       comenet.py:297
-      f3 v = sub3(pj, pi);
-      vec[3 * (size_t)e] = v.x; vec[3 * (size_t)e + 1] = v.y; vec[3 * (size_t)e + 2] = v.z;
+  const int d = deg[i], e0 = row_ptr[i];
+  int t = node_trip_ptr[i];
+  const f3 pi = load3(pos, i);
+  for (int s0 = 0; s0 < d; s0 += 32) {
+    const int s = s0 + lane;
+    int c = 0;
+    if (s < d) {
+      const int j = nbr[(size_t)i * cap + s];
+      const int e = e0 + s;
+      src[e] = j; dst[e] = i;
+      if (edge_index) { edge_index[e] = j; edge_index[n_edges + e] = i; }
+      const f3 pj = load3(pos, j);
+      // (pos[i]-pos[j]).pow(2).sum(-1).sqrt()   geometric_computing.py:25
+      dist[e] = norm3_aten(sub3(pi, pj));
+      if (vec) {  // vecs = pos[j] - pos[i]       comenet.py:297
+        const f3 v = sub3(pj, pi);
+        vec[3 * (size_t)e] = v.x; vec[3 * (size_t)e + 1] = v.y; vec[3 * (size_t)e + 2] = v.z;
+      }
+      const int dj = deg[j];
+      c = dj - (find_sorted(nbr + (size_t)j * cap, dj, i) >= 0 ? 1 : 0);
     }
-    trip_ptr[e] = t;
-    int dj = deg[j];
-    t += dj - (find_sorted(nbr + (size_t)j * cap, dj, i) >= 0 ? 1 : 0);
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (s < d) trip_ptr[e0 + s] = t + incl - c;
+    t += __shfl_sync(0xffffffffu, incl, 31);
   }
-  if (i == n_nodes - 1) trip_ptr[n_edges] = t;
+  if (i == n_nodes - 1 && lane == 0) trip_ptr[n_edges] = t;
 }
 
 // ------------------------------------------------------------------ CSR from a caller-supplied edge_index
@@ -435,7 +455,7 @@ int dig3d_triplet_count(const int32_t* nbr, const int32_t* deg, int64_t n_nodes,
                         void* stream) {
   DIG3D_REQUIRE(nbr && deg && tcnt, "triplet_count: null pointer");
   if (n_nodes == 0) return DIG3D_OK;
-  triplet_count_kernel<<<ceil_div(n_nodes, 128), 128, 0, (cudaStream_t)stream>>>(nbr, deg, (int)n_nodes, cap,
+  triplet_count_kernel<<<ceil_div(n_nodes * 32, 128), 128, 0, (cudaStream_t)stream>>>(nbr, deg, (int)n_nodes, cap,
                                                                              tcnt);
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
@@ -457,7 +477,7 @@ int dig3d_edge_fill(const float* pos, const int32_t* nbr, const int32_t* deg, co
   DIG3D_REQUIRE(pos && nbr && deg && row_ptr && node_trip_ptr && src && dst && dist && trip_ptr,
                 "edge_fill: null pointer");
   if (n_nodes == 0) return DIG3D_OK;
-  edge_fill_kernel<<<ceil_div(n_nodes, 128), 128, 0, (cudaStream_t)stream>>>(
+  edge_fill_kernel<<<ceil_div(n_nodes * 32, 128), 128, 0, (cudaStream_t)stream>>>(
       pos, nbr, deg, row_ptr, node_trip_ptr, (int)n_nodes, cap, n_edges, edge_index, src, dst, dist, vec,
       trip_ptr);
   DIG3D_LAUNCH_CHECK();

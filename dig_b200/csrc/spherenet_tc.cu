@@ -250,22 +250,37 @@ template <bool TORSION, class XRow>
 __device__ __forceinline__ void tg_accumulate(const float2* st, int n8, const float2 (&w)[2][8], XRow xrow, float& a0,
                                               float& a1) {
   if (TORSION) {
+    // two triplets per step: four independent FFMA2 chains, all eight broadcast loads in flight before the first use
+    // (one triplet at a time, the chain latency and the shared-memory round trip were exposed: short-scoreboard 3.1 and
+    // wait 2.1 stalls per issue, profiles/r02_gather_node_packed_ncu_summary.txt).  The staged values of a triplet past
+    // the end of the chunk are zero, its row is not read, so it adds an exact 0.
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      if (u < n8) {
-        float2 gh0 = make_float2(0.f, 0.f), gh1 = make_float2(0.f, 0.f);      // {lin_sbf2, lin_t2} of channel 0 / 1
+    for (int up = 0; up < 4; ++up) {
+      if (2 * up < n8) {
+        const int u = 2 * up;
+        const bool two = u + 1 < n8;
+        float4 v[8];
 #pragma unroll
-        for (int q = 0; q < 8; q += 2) {
-          const float4 v = *reinterpret_cast<const float4*>(st + u * 8 + q);
-          const float2 v0 = make_float2(v.x, v.y), v1 = make_float2(v.z, v.w);
-          gh0 = ffma2(w[0][q], v0, gh0); gh1 = ffma2(w[1][q], v0, gh1);
-          gh0 = ffma2(w[0][q + 1], v1, gh0); gh1 = ffma2(w[1][q + 1], v1, gh1);
+        for (int q = 0; q < 8; ++q) v[q] = *reinterpret_cast<const float4*>(st + u * 8 + 2 * q);
+        float xa0, xb0, xa1 = 0.f, xb1 = 0.f;
+        xrow(u, xa0, xb0);
+        if (two) xrow(u + 1, xa1, xb1);
+        float2 g0 = make_float2(0.f, 0.f), g1 = g0, k0 = g0, k1 = g0;   // {lin_sbf2, lin_t2}: channel 0 / 1 of u, u + 1
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 a0q = make_float2(v[q].x, v[q].y), a1q = make_float2(v[q].z, v[q].w);
+          const float2 b0q = make_float2(v[4 + q].x, v[4 + q].y), b1q = make_float2(v[4 + q].z, v[4 + q].w);
+          g0 = ffma2(w[0][2 * q], a0q, g0); g1 = ffma2(w[1][2 * q], a0q, g1);
+          k0 = ffma2(w[0][2 * q], b0q, k0); k1 = ffma2(w[1][2 * q], b0q, k1);
+          g0 = ffma2(w[0][2 * q + 1], a1q, g0); g1 = ffma2(w[1][2 * q + 1], a1q, g1);
+          k0 = ffma2(w[0][2 * q + 1], b1q, k0); k1 = ffma2(w[1][2 * q + 1], b1q, k1);
         }
-        float x0, x1;
-        xrow(u, x0, x1);
-        float m0 = __fmul_rn(x0, gh0.x), m1 = __fmul_rn(x1, gh1.x);
-        m0 = __fmul_rn(m0, gh0.y); m1 = __fmul_rn(m1, gh1.y);
+        float m0 = __fmul_rn(xa0, g0.x), m1 = __fmul_rn(xb0, g1.x);
+        float n0 = __fmul_rn(xa1, k0.x), n1 = __fmul_rn(xb1, k1.x);
+        m0 = __fmul_rn(m0, g0.y); m1 = __fmul_rn(m1, g1.y);
+        n0 = __fmul_rn(n0, k0.y); n1 = __fmul_rn(n1, k1.y);
         a0 += m0; a1 += m1;
+        a0 += n0; a1 += n1;
       }
     }
   } else {
@@ -450,6 +465,120 @@ sphere_triplet_gather_node_kernel(const float* __restrict__ x_down, const float*
     __syncthreads();
     if (tid == 0) n_out = 0;
     __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------- triplet gather, one WARP per node
+// The node-centred kernel above spends a quarter of its warp time in CTA barriers (one warp searches the out-edges
+// while three wait; the four warps finish their 3-4 out-edges at different times) and pays the CTA set-up once per
+// node.  Here every warp is independent: it owns (node j, share `sub` of `split`), stages the rows of j's in-edges in
+// its OWN shared-memory buffer with one bulk copy (own mbarrier), finds the out-edges with lane = candidate atom,
+// keeps the in-neighbour list in two registers per lane (position look-ups are ballots) and walks its out-edges with the
+// same chunk pipeline.  No __syncthreads after the set-up.  split > 1 spreads a heavy node over several warps (each
+// stages its own copy of the rows; out-edge r of the node goes to share r % split).
+constexpr int TGW_WARPS = 4;
+
+template <bool TORSION>
+__global__ void __launch_bounds__(TGW_WARPS * 32)
+sphere_triplet_gather_warp_kernel(const float* __restrict__ x_down, const float* __restrict__ sbf_p,
+                                  const float* __restrict__ t_p, const int32_t* __restrict__ src,
+                                  const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ trip_ptr,
+                                  const int32_t* __restrict__ graph_ptr, const int64_t* __restrict__ batch,
+                                  int n_nodes, int split, int cap, const float* __restrict__ w_sbf2,
+                                  const float* __restrict__ w_t2, float* __restrict__ m) {
+  extern __shared__ __align__(128) unsigned char tgw_smem[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const size_t per_warp = (size_t)cap * 256 + 512 + 128;
+  unsigned char* mine = tgw_smem + (size_t)w * per_warp;
+  float (*rows)[64] = reinterpret_cast<float (*)[64]>(mine);
+  float2* stage = reinterpret_cast<float2*>(mine + (size_t)cap * 256);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(mine + (size_t)cap * 256 + 512);
+  const int task = blockIdx.x * TGW_WARPS + w;
+  if (task >= n_nodes * split) return;
+  const int j = task / split, sub = task - j * split;
+  const int base = row_ptr[j], d = row_ptr[j + 1] - base;
+  const int g = (int)batch[j], lo = graph_ptr[g], hi = graph_ptr[g + 1];
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+    if (d > 0) {
+      mbar_arrive_expect_tx(bar, (uint32_t)d * 256u);
+      bulk_g2s(&rows[0][0], x_down + (size_t)base * 64, (uint32_t)d * 256u, bar);
+    }
+  }
+  const int in_a = lane < d ? src[base + lane] : -1, in_b = lane + 32 < d ? src[base + lane + 32] : -1;
+  float2 wq[2][8];
+  tg_load_weights<TORSION>(wq, w_sbf2, w_t2, lane);
+  __syncwarp();
+  auto fetch = [&](int t_first, int left, float& sa, float& sb, float& ta, float& tb) {
+    const int lim = min(8, left) * 8;
+    const float* sp = sbf_p + (size_t)t_first * 8;
+    sa = lane < lim ? __ldg(sp + lane) : 0.f; sb = lane + 32 < lim ? __ldg(sp + lane + 32) : 0.f;
+    ta = 0.f; tb = 0.f;
+    if (TORSION) {
+      const float* tp = t_p + (size_t)t_first * 8;
+      ta = lane < lim ? __ldg(tp + lane) : 0.f; tb = lane + 32 < lim ? __ldg(tp + lane + 32) : 0.f;
+    }
+  };
+  // position of node i among j's in-neighbours (d if absent)
+  auto position = [&](int i) {
+    const unsigned ha = __ballot_sync(0xffffffffu, in_a == i), hb = __ballot_sync(0xffffffffu, in_b == i);
+    return ha ? __ffs(ha) - 1 : (hb ? 32 + __ffs(hb) - 1 : d);
+  };
+  bool staged = false;
+  int seen = 0;                      // out-edges of j met so far (all shares)
+  for (int c0 = lo; c0 < hi; c0 += 32) {
+    const int i = c0 + lane;
+    int e_l = -1;
+    if (i < hi && i != j) {
+      const int ib = row_ptr[i], di = row_ptr[i + 1] - ib;
+      int a = 0, b = di;
+      while (a < b) { const int mid = (a + b) >> 1; if (src[ib + mid] < j) a = mid + 1; else b = mid; }
+      if (a < di && src[ib + a] == j) e_l = ib + a;
+    }
+    const unsigned found = __ballot_sync(0xffffffffu, e_l >= 0);
+    const int rank = seen + __popc(found & ((1u << lane) - 1));
+    unsigned sel = __ballot_sync(0xffffffffu, e_l >= 0 && rank % split == sub);
+    seen += __popc(found);
+    if (!sel) continue;
+    if (!staged && d > 0) { mbar_wait(bar, 0); staged = true; }
+    // walk the selected out-edges; the projected-basis values of a chunk are fetched one chunk ahead (next chunk of the
+    // edge, or the first chunk of the next selected edge)
+    int bit = __ffs(sel) - 1;
+    sel &= sel - 1;
+    int e = __shfl_sync(0xffffffffu, e_l, bit), p_i = position(c0 + bit);
+    int t0 = trip_ptr[e], nt = d - (p_i < d ? 1 : 0);
+    float sa = 0.f, sb = 0.f, ta = 0.f, tb = 0.f;
+    bool fetched = false;
+    for (;;) {
+      int e_n = -1, p_n = 0, t0_n = 0, nt_n = 0;
+      if (sel) {
+        const int bn = __ffs(sel) - 1;
+        sel &= sel - 1;
+        e_n = __shfl_sync(0xffffffffu, e_l, bn);
+        p_n = position(c0 + bn);
+        t0_n = trip_ptr[e_n]; nt_n = d - (p_n < d ? 1 : 0);
+      }
+      if (!fetched && nt > 0) fetch(t0, nt, sa, sb, ta, tb);
+      fetched = false;
+      float a0 = 0.f, a1 = 0.f;
+      for (int r0 = 0; r0 < nt; r0 += 8) {
+        const int n8 = min(8, nt - r0);
+        __syncwarp();
+        tg_stage<TORSION>(stage, lane, sa, sb, ta, tb);
+        __syncwarp();
+        if (r0 + 8 < nt) fetch(t0 + r0 + 8, nt - r0 - 8, sa, sb, ta, tb);
+        else if (e_n >= 0 && nt_n > 0) { fetch(t0_n, nt_n, sa, sb, ta, tb); fetched = true; }
+        tg_accumulate<TORSION>(stage, n8, wq, [=](int u, float& xa, float& xb) {
+          const int r = r0 + u, row = r + (r >= p_i ? 1 : 0);
+          xa = rows[row][lane]; xb = rows[row][lane + 32];
+        }, a0, a1);
+      }
+      m[(size_t)e * 64 + lane] = a0;
+      m[(size_t)e * 64 + lane + 32] = a1;
+      if (e_n < 0) break;
+      e = e_n; p_i = p_n; t0 = t0_n; nt = nt_n;
+    }
   }
 }
 
@@ -1109,6 +1238,32 @@ int dig3d_sphere_triplet_gather_node(const float* x_down, const float* sbf_p, co
   else
     sphere_triplet_gather_node_kernel<false><<<(int)n_nodes, TGN_THREADS, (size_t)cap * 256, st>>>(
         x_down, sbf_p, t_p, src, row_ptr, trip_ptr, graph_ptr, batch, (int)n_nodes, w_sbf2, w_t2, m);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_sphere_triplet_gather_warp(const float* x_down, const float* sbf_p, const float* t_p, int32_t ld_p,
+                                     const int32_t* src, const int32_t* row_ptr, const int32_t* trip_ptr,
+                                     const int32_t* graph_ptr, const int64_t* batch, int64_t n_nodes, int32_t cap,
+                                     int32_t split, const float* w_sbf2, const float* w_t2, float* m, void* stream) {
+  DIG3D_REQUIRE(x_down && sbf_p && src && row_ptr && trip_ptr && graph_ptr && batch && w_sbf2 && m,
+                "sphere_triplet_gather_warp: null pointer");
+  DIG3D_REQUIRE((t_p != nullptr) == (w_t2 != nullptr), "sphere_triplet_gather_warp: t_p and w_t2 must agree");
+  DIG3D_REQUIRE(ld_p == 8, "sphere_triplet_gather_warp: expects the layer-major [T, 8] slices (ld_p == 8), got %d", ld_p);
+  DIG3D_REQUIRE(cap >= 1 && cap <= TGN_MAXIN, "sphere_triplet_gather_warp: cap=%d outside [1,%d]", cap, TGN_MAXIN);
+  DIG3D_REQUIRE(split >= 1 && split <= 32, "sphere_triplet_gather_warp: split=%d outside [1,32]", split);
+  DIG3D_REQUIRE(((uintptr_t)x_down & 15) == 0, "sphere_triplet_gather_warp: x_down must be 16-byte aligned");
+  if (n_nodes == 0) return DIG3D_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (size_t)TGW_WARPS * ((size_t)cap * 256 + 512 + 128);
+  const int grid = ceil_div(n_nodes * split, TGW_WARPS);
+  auto kfn = t_p ? sphere_triplet_gather_warp_kernel<true> : sphere_triplet_gather_warp_kernel<false>;
+  if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    set_error("sphere_triplet_gather_warp: cannot reserve %zu bytes of shared memory", smem);
+    return DIG3D_ECUDA;
+  }
+  kfn<<<grid, TGW_WARPS * 32, smem, st>>>(x_down, sbf_p, t_p, src, row_ptr, trip_ptr, graph_ptr, batch, (int)n_nodes,
+                                          (int)split, (int)cap, w_sbf2, w_t2, m);
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
 }

@@ -559,16 +559,32 @@ def sphere_update_e_tc(e1, g, rbf0, sbf_p, t_p, col0, w, hidden, int_emb, v_in=N
     return e1_out, v_in, x_ji, x_down
 
 
-# "node": source-node CTAs, shared-memory staged rows, FP32 expansions (exact fp32, bit-equal to "edge");
-# "tc": the same organisation with the 8 -> 64 expansions on tcgen05 (3xFP16 operands); "edge": one warp per edge
-GATHER_MODE = ["node"]
+# "warp" (default): one warp per (source node, share) -- rows staged in the warp's own shared memory by one bulk copy, no
+# CTA-wide barrier; "node": one CTA per source node (round 2's first node-centred kernel); "tc": the node organisation
+# with the 8 -> 64 expansions on tcgen05 (3xFP16 operands); "edge": one warp per edge.  "warp" / "node" / "edge" are
+# bit-identical.
+GATHER_MODE = ["warp"]
+# warps sharing one node in "warp" mode; None = by the average number of triplets per node
+GATHER_SPLIT = [None]
+
+
+def gather_split(g):
+    if GATHER_SPLIT[0] is not None:
+        return int(GATHER_SPLIT[0])
+    per_node = g.n_triplets / max(g.n_nodes, 1)
+    return max(1, min(8, int(per_node // 384) + 1))
 
 
 def triplet_gather(x_down, sp, tp, g, w_sbf2, w_t2, m_out, st):
     """m[e] = sum_t x_down[kj] * lin_sbf2(sbf_p) * lin_t2(t_p)  (spherenet.py:163-171); sp / tp are layer slices."""
-    if GATHER_MODE[0] in ("node", "tc"):
-        call("dig3d_sphere_triplet_gather_tc" if GATHER_MODE[0] == "tc" else "dig3d_sphere_triplet_gather_node", _p(x_down), sp, tp, 8, _p(g.src), _p(g.row_ptr), _p(g.trip_ptr),
-             _p(g.graph_ptr), _p(g.batch, torch.int64), g.n_nodes, g.cap, w_sbf2, w_t2, _p(m_out), st)
+    mode = GATHER_MODE[0]
+    if mode == "warp":
+        call("dig3d_sphere_triplet_gather_warp", _p(x_down), sp, tp, 8, _p(g.src), _p(g.row_ptr), _p(g.trip_ptr),
+             _p(g.graph_ptr), _p(g.batch, torch.int64), g.n_nodes, g.cap, gather_split(g), w_sbf2, w_t2, _p(m_out), st)
+    elif mode in ("node", "tc"):
+        call("dig3d_sphere_triplet_gather_tc" if mode == "tc" else "dig3d_sphere_triplet_gather_node", _p(x_down), sp, tp,
+             8, _p(g.src), _p(g.row_ptr), _p(g.trip_ptr), _p(g.graph_ptr), _p(g.batch, torch.int64), g.n_nodes, g.cap,
+             w_sbf2, w_t2, _p(m_out), st)
     else:
         call("dig3d_sphere_triplet_gather", _p(x_down), sp, tp, 8, _p(g.src), _p(g.dst), _p(g.row_ptr),
              _p(g.trip_ptr), g.n_edges, w_sbf2, w_t2, _p(m_out), st)

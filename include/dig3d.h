@@ -249,6 +249,13 @@ int dig3d_sphere_triplet_gather_node(const float* x_down, const float* sbf_p, co
                                      const int32_t* src, const int32_t* row_ptr, const int32_t* trip_ptr,
                                      const int32_t* graph_ptr, const int64_t* batch, int64_t n_nodes, int32_t cap,
                                      const float* w_sbf2, const float* w_t2, float* m, void* stream);
+/* Same result (bit-identical) with one WARP per (source node, share): no CTA-wide barrier, the warp's own bulk copy /
+ * mbarrier, in-neighbour positions by ballot.  split >= 1 warps share a node (out-edge r of the node goes to share
+ * r % split); cap = max in-degree + 1 <= 64. */
+int dig3d_sphere_triplet_gather_warp(const float* x_down, const float* sbf_p, const float* t_p, int32_t ld_p,
+                                     const int32_t* src, const int32_t* row_ptr, const int32_t* trip_ptr,
+                                     const int32_t* graph_ptr, const int64_t* batch, int64_t n_nodes, int32_t cap,
+                                     int32_t split, const float* w_sbf2, const float* w_t2, float* m, void* stream);
 /* lin_up + residual stack + lin (spherenet.py:172-180) on tcgen05; writes e1_out, ACCUMULATES e2 into v_in. */
 int dig3d_sphere_update_e_b_tc(const float* m, const float* e1_in, const float* x_ji, const float* rbf0,
                                const int32_t* dst, int64_t n_edges, const dig3d_tc_update_e* w, float* e1_out,

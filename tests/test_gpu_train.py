@@ -636,17 +636,21 @@ def test_node_centred_triplet_gather_equals_edge_centred():
     x_down = torch.randn(e, 64, device=dev)
     sbf_p, t_p = torch.randn(t, 8, device=dev), torch.randn(t, 8, device=dev)
     w_s, w_t = torch.randn(64, 8, device=dev), torch.randn(64, 8, device=dev)
-    for tors in (True, False):
-        outs = []
-        for mode in ("edge", "node"):
-            ops.GATHER_MODE[0] = mode
-            m = torch.full((e, 64), float("nan"), device=dev)
-            ops.triplet_gather(x_down, ctypes.c_void_p(sbf_p.data_ptr()),
-                               ctypes.c_void_p(t_p.data_ptr()) if tors else None, g,
-                               w_s.data_ptr(), w_t.data_ptr() if tors else None, m, ops._stream())
-            outs.append(m)
-        ops.GATHER_MODE[0] = "node"
-        assert torch.isfinite(outs[1]).all() and torch.equal(outs[0], outs[1]), tors
+    default_mode = ops.GATHER_MODE[0]
+    try:
+        for tors in (True, False):
+            outs = {}
+            for mode, split in (("edge", None), ("node", None), ("warp", 1), ("warp", 2), ("warp", 3), ("warp", None)):
+                ops.GATHER_MODE[0], ops.GATHER_SPLIT[0] = mode, split
+                m = torch.full((e, 64), float("nan"), device=dev)
+                ops.triplet_gather(x_down, ctypes.c_void_p(sbf_p.data_ptr()),
+                                   ctypes.c_void_p(t_p.data_ptr()) if tors else None, g,
+                                   w_s.data_ptr(), w_t.data_ptr() if tors else None, m, ops._stream())
+                outs[(mode, split)] = m
+            for key, m in outs.items():
+                assert torch.isfinite(m).all() and torch.equal(outs[("edge", None)], m), (tors, key)
+    finally:
+        ops.GATHER_MODE[0], ops.GATHER_SPLIT[0] = default_mode, None
 
 
 def test_tensor_core_triplet_gather_matches_the_exact_one():
@@ -679,7 +683,7 @@ def test_tensor_core_triplet_gather_matches_the_exact_one():
                                    ctypes.c_void_p(t_p.data_ptr()) if tors else None, g,
                                    w_s.data_ptr(), w_t.data_ptr() if tors else None, m, ops._stream())
                 outs.append(m)
-            ops.GATHER_MODE[0] = "node"
+            ops.GATHER_MODE[0] = "warp"
             torch.cuda.synchronize()
             assert ops.tc_timeouts() == 0
             assert torch.isfinite(outs[1]).all(), (ng, tors)

@@ -1,5 +1,5 @@
 """Triplet gather organisations at the headline size: energy error vs the oracle and per-kernel time for
-ops.GATHER_MODE in (node, tc) -- test infrastructure."""
+ops.GATHER_MODE in (node, warp x split) -- test infrastructure."""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -16,8 +16,8 @@ for name, cls, tors in (("spherenet", SphereNet, True), ("dimenetpp", DimeNetPP,
     b = synthetic_batch(128, "qm9", seed=2).to(dev)
     with torch.no_grad():
         ref = restated.dimenet_family_forward({k: v.to(dev) for k, v in sd.items()}, b.z, b.pos, b.batch, torsion=tors)
-    for mode in ("node", "tc"):
-        ops.GATHER_MODE[0] = mode
+    for mode, split in (("node", None), ("warp", 1), ("warp", 2), ("warp", 4)):
+        ops.GATHER_MODE[0], ops.GATHER_SPLIT[0] = mode, split
         with torch.no_grad():
             for _ in range(3): u = model(b)
             _lib.start_timing()
@@ -28,6 +28,6 @@ for name, cls, tors in (("spherenet", SphereNet, True), ("dimenetpp", DimeNetPP,
             for _ in range(20): model(b)
             e.record(); torch.cuda.synchronize()
         gk = {k.replace("dig3d_", ""): round(sum(v) / len(v), 4) for k, v in per.items() if "gather" in k}
-        print(f"{name} gather={mode}: step {a.elapsed_time(e) / 20:.4f} ms, {gk}, rel(energy, oracle) "
+        print(f"{name} gather={mode} split={split}: step {a.elapsed_time(e) / 20:.4f} ms, {gk}, rel(energy, oracle) "
               f"{rel_err(u.cpu().numpy(), ref.cpu().numpy()):.3e}, timeouts {ops.tc_timeouts()}", flush=True)
-ops.GATHER_MODE[0] = "node"
+ops.GATHER_MODE[0], ops.GATHER_SPLIT[0] = "warp", None
