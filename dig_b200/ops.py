@@ -575,19 +575,25 @@ def gather_split(g):
     return max(1, min(8, int(per_node // 384) + 1))
 
 
+def _ptr(x):
+    """Device pointer argument: a raw address (int, internal workspace of the lean inference path) or a validated tensor."""
+    return x if type(x) is int else _p(x)
+
+
 def triplet_gather(x_down, sp, tp, g, w_sbf2, w_t2, m_out, st):
-    """m[e] = sum_t x_down[kj] * lin_sbf2(sbf_p) * lin_t2(t_p)  (spherenet.py:163-171); sp / tp are layer slices."""
+    """m[e] = sum_t x_down[kj] * lin_sbf2(sbf_p) * lin_t2(t_p)  (spherenet.py:163-171); sp / tp are layer slices.
+    x_down / m_out: tensors or raw device addresses."""
     mode = GATHER_MODE[0]
     if mode == "warp":
-        call("dig3d_sphere_triplet_gather_warp", _p(x_down), sp, tp, 8, _p(g.src), _p(g.row_ptr), _p(g.trip_ptr),
-             _p(g.graph_ptr), _p(g.batch, torch.int64), g.n_nodes, g.cap, gather_split(g), w_sbf2, w_t2, _p(m_out), st)
+        call("dig3d_sphere_triplet_gather_warp", _ptr(x_down), sp, tp, 8, _p(g.src), _p(g.row_ptr), _p(g.trip_ptr),
+             _p(g.graph_ptr), _p(g.batch, torch.int64), g.n_nodes, g.cap, gather_split(g), w_sbf2, w_t2, _ptr(m_out), st)
     elif mode in ("node", "tc"):
-        call("dig3d_sphere_triplet_gather_tc" if mode == "tc" else "dig3d_sphere_triplet_gather_node", _p(x_down), sp, tp,
-             8, _p(g.src), _p(g.row_ptr), _p(g.trip_ptr), _p(g.graph_ptr), _p(g.batch, torch.int64), g.n_nodes, g.cap,
-             w_sbf2, w_t2, _p(m_out), st)
+        call("dig3d_sphere_triplet_gather_tc" if mode == "tc" else "dig3d_sphere_triplet_gather_node", _ptr(x_down), sp,
+             tp, 8, _p(g.src), _p(g.row_ptr), _p(g.trip_ptr), _p(g.graph_ptr), _p(g.batch, torch.int64), g.n_nodes, g.cap,
+             w_sbf2, w_t2, _ptr(m_out), st)
     else:
-        call("dig3d_sphere_triplet_gather", _p(x_down), sp, tp, 8, _p(g.src), _p(g.dst), _p(g.row_ptr),
-             _p(g.trip_ptr), g.n_edges, w_sbf2, w_t2, _p(m_out), st)
+        call("dig3d_sphere_triplet_gather", _ptr(x_down), sp, tp, 8, _p(g.src), _p(g.dst), _p(g.row_ptr),
+             _p(g.trip_ptr), g.n_edges, w_sbf2, w_t2, _ptr(m_out), st)
 
 
 def sphere_init_e_h16(z, g, rbf0, w, packed_lin, hidden, v_in=None):
@@ -626,10 +632,9 @@ def update_v_h16_supported(holder, out_channels):
         holder.lin_up.weight.size(1), holder.lin_up.weight.size(0), int(out_channels), len(holder.lins)))
 
 
-def sphere_update_v_h16(v_in_all, holders, out_channels, v_out_all, cache):
-    """All node MLPs of a forward in one launch on the two-tile tensor-core engine (3xFP16 operands).
-    v_in_all [NB, N, 128], holders: NB update_v modules (128 -> 256 -> ... -> out_channels)."""
-    nb, n, _ = v_in_all.shape
+def pack_update_v_h16(holders, cache):
+    """(packed-weight pointer array, UpdateVWeights array, n_lins) of the node MLPs for dig3d_sphere_update_v_h16; the
+    packed buffers live in `cache` (same invalidation rules as tc_pack_update_e)."""
     n_lins = len(holders[0].lins)
     ptrs = []
     for h in holders:
@@ -646,7 +651,15 @@ def sphere_update_v_h16(v_in_all, holders, out_channels, v_out_all, cache):
         _, buf, offs = hit
         ptrs += [buf.data_ptr() + offs[2 * l] for l in range(n_lins + 1)]
     parr = (ctypes.c_void_p * len(ptrs))(*ptrs)
-    arr = (_lib.UpdateVWeights * nb)(*[pack_update_v(h) for h in holders])
+    arr = (_lib.UpdateVWeights * len(holders))(*[pack_update_v(h) for h in holders])
+    return parr, arr, n_lins
+
+
+def sphere_update_v_h16(v_in_all, holders, out_channels, v_out_all, cache):
+    """All node MLPs of a forward in one launch on the two-tile tensor-core engine (3xFP16 operands).
+    v_in_all [NB, N, 128], holders: NB update_v modules (128 -> 256 -> ... -> out_channels)."""
+    nb, n, _ = v_in_all.shape
+    parr, arr, n_lins = pack_update_v_h16(holders, cache)
     if n:
         call("dig3d_sphere_update_v_h16", _p(v_in_all, torch.float32, "v_in_all", 16), n, nb, int(out_channels), n_lins,
              parr, arr, _p(v_out_all, align=4), _stream())

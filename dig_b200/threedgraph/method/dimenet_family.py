@@ -225,7 +225,16 @@ class _DimeNetFamily(nn.Module):
     # model must call invalidate_packed() itself.
     def invalidate_packed(self):
         self.__dict__.setdefault("_tc_cache", {}).clear()
+        self.__dict__.pop("_plan", None)
+        self.__dict__.pop("_plan_params", None)
         ops.invalidate_packed()
+
+    def __getstate__(self):
+        # the packed-weight caches / inference plan hold device pointers (ctypes): rebuilt on demand, never copied or pickled
+        state = self.__dict__.copy()
+        for k in ("_tc_cache", "_plan", "_plan_params"):
+            state.pop(k, None)
+        return state
 
     def load_state_dict(self, *args, **kw):
         out = super().load_state_dict(*args, **kw)
@@ -266,6 +275,11 @@ class _DimeNetFamily(nn.Module):
                                             lambda p, c: self._exact(self._forward_dual, z, p, c, g, nf),
                                             pos, tuple(self.parameters()))
             return self._exact(self._forward_train, z, pos, g, nf, exact=bool(pos.requires_grad))
+        if (os.environ.get("DIG3D_DENSE", "h16") == "h16" and g.n_edges and self.num_layers <= 4
+                and os.environ.get("DIG3D_LEAN", "1") != "0"):
+            plan = self._inference_plan()
+            if plan is not None:
+                return self._forward_lean(plan, z, pos, g)
         ops.triplet_geometry(g, pos, use_torsion=self._torsion, want_idx=False)
         rbf0, bess = ops.edge_basis(g.dist, self.cutoff, self.envelope_exponent, self.emb.dist_emb.freq,
                                     self._basis_id, envelope_on_bessel=not self._torsion, num_radial=nr,
@@ -321,6 +335,95 @@ class _DimeNetFamily(nn.Module):
             ops.sphere_update_v_batched(v_in_all, holders, self.out_channels, v_all)
         return ops.graph_readout(v_all, g.graph_ptr, g.n_graphs, g.n_nodes)
 
+
+    # ------------------------------------------------------------------ lean inference path (host overhead)
+    # The launch sequence above spends ~0.85 ms of Python per forward (weight-pointer structs rebuilt and validated for
+    # every layer, ~35 allocations, ~240 pointer validations; profiles/r02_infer_host_profile.txt) -- more than the GPU
+    # needs for the batch once three batches are in flight.  Everything that depends only on the PARAMETERS lives in a
+    # plan that is rebuilt when a parameter changes (same rules as the packed-weight caches: tensor._version / storage
+    # address / invalidate_packed()); per forward the host then allocates one workspace and makes the ~25 C calls with
+    # raw addresses.  Same kernels, same arguments, same order: the energies are bit-identical to the path above
+    # (DIG3D_LEAN=0 selects it; tests/test_gpu_parity.py::test_lean_inference_path_is_bit_identical).
+    def _inference_plan(self):
+        params = self.__dict__.get("_plan_params")
+        if params is None:
+            params = self.__dict__["_plan_params"] = list(self.parameters())
+        key = (ops._PACK_GENERATION[0], sum(p._version for p in params), tuple(p.data_ptr() for p in params))
+        plan = self.__dict__.get("_plan")
+        if plan is not None and plan["key"] == key:
+            return plan
+        holders = [self.init_v] + list(self.update_vs)
+        if not ops.update_v_h16_supported(self.init_v, self.out_channels):
+            return None
+        tc_cache = self.__dict__.setdefault("_tc_cache", {})
+        L = self.num_layers
+        w_s, w_t = self._projection_rows(0, L)
+        parr, varr, n_lins = ops.pack_update_v_h16(holders, tc_cache)
+        plan = {
+            "key": key,
+            "init_w": ops.pack_init_e(self.init_e),
+            "init_packed": ops.tc_pack_matrix(self.init_e.lin.weight, tc_cache, "init_e.lin", kind="h16"),
+            "layers": [ops.tc_pack_update_e(self.update_es[l], self._torsion, tc_cache, kind="h16") for l in range(L)],
+            "w_s": w_s, "w_t": w_t, "parr": parr, "varr": varr, "n_lins": n_lins,
+            "freq": self.emb.dist_emb.freq.detach(),
+            "emb_rows": self.init_e.emb.num_embeddings if self.init_e.use_node_features else 0,
+        }
+        self.__dict__["_plan"] = plan
+        return plan
+
+    def _forward_lean(self, plan, z, pos, g):
+        import ctypes
+        call, byref = ops.call, ctypes.byref
+        tors = self._torsion
+        E, T, N, L = g.n_edges, g.n_triplets, g.n_nodes, self.num_layers
+        H, I, O = self.hidden_channels, self.int_emb_size, self.out_channels
+        nb_s = self.num_spherical * self.num_radial
+        dev = pos.device
+        # one workspace (floats), every buffer on a 256-byte boundary
+        sizes = (("angle", T), ("torsion", T if tors else 0), ("rbf0", E * self.num_radial), ("bess", E * nb_s),
+                 ("sbf_p", 32 * T), ("t_p", 32 * T if tors else 0), ("e1a", E * H), ("e1b", E * H), ("x_ji", E * H),
+                 ("x_down", E * I), ("m", E * I), ("v_all", (L + 1) * N * O))
+        off, total = {}, 0
+        for name, n in sizes:
+            off[name] = total
+            total += (n + 63) & ~63
+        ws = torch.empty(total + 64, dtype=torch.float32, device=dev)
+        base = (ws.data_ptr() + 255) & ~255
+        a = {name: base + 4 * o for name, o in off.items()}
+        v_in_all = torch.zeros(L + 1, N, H, dtype=torch.float32, device=dev)
+        v_in = v_in_all.data_ptr()
+        st = ops._stream()
+        src, dst, row_ptr, trip_ptr = g.src.data_ptr(), g.dst.data_ptr(), g.row_ptr.data_ptr(), g.trip_ptr.data_ptr()
+        graph_ptr, batch = g.graph_ptr.data_ptr(), ops._p(g.batch, torch.int64, "batch")
+        pos_p = ops._p(pos.detach(), torch.float32, "pos")
+        if T:
+            call("dig3d_triplet_geometry", pos_p, src, dst, row_ptr, trip_ptr, E, int(tors), a["angle"],
+                 a["torsion"] if tors else None, None, None, None, None, st)
+        call("dig3d_edge_basis", g.dist.data_ptr(), E, float(self.cutoff), int(self.envelope_exponent),
+             ops._p(plan["freq"], torch.float32, "freq"), int(self._basis_id), int(not tors), a["rbf0"], a["bess"], st)
+        if T:
+            call("dig3d_triplet_basis_project", a["bess"], a["angle"], a["torsion"] if tors else None, src, dst, row_ptr,
+                 trip_ptr, graph_ptr, batch, E, T, int(self._basis_id), 4, 8, plan["w_s"].data_ptr(),
+                 plan["w_t"].data_ptr() if tors else None, a["sbf_p"], a["t_p"] if tors else None, st)
+        call("dig3d_sphere_init_e_h16", ops._p(z, torch.int64, "z"), src, dst, a["rbf0"], E, byref(plan["init_w"]),
+             plan["init_packed"].data_ptr(), a["e1a"], v_in, st)
+        e1, e1_next = a["e1a"], a["e1b"]
+        for l in range(L):
+            w = plan["layers"][l]
+            call("dig3d_sphere_update_e_a_h16", e1, a["rbf0"], E, byref(w), a["x_ji"], a["x_down"], st)
+            sp = ctypes.c_void_p(a["sbf_p"] + 4 * 8 * T * l)
+            tp = ctypes.c_void_p(a["t_p"] + 4 * 8 * T * l) if tors else None
+            ops.triplet_gather(a["x_down"], sp, tp, g, w.w_sbf2, w.w_t2, a["m"], st)
+            call("dig3d_sphere_update_e_b_h16", a["m"], e1, a["x_ji"], a["rbf0"], dst, E, byref(w), e1_next,
+                 v_in + 4 * (l + 1) * N * H, st)
+            e1, e1_next = e1_next, e1
+        call("dig3d_sphere_update_v_h16", v_in, N, L + 1, int(O), plan["n_lins"], plan["parr"], plan["varr"], a["v_all"], st)
+        u = torch.empty(g.n_graphs, O, dtype=torch.float32, device=dev)
+        if g.n_graphs:
+            call("dig3d_graph_readout", a["v_all"], graph_ptr, g.n_graphs, N, L + 1, O, u.data_ptr(), st)
+        # ws / v_in_all are released here: the caching allocator hands them out again in stream order, after the kernels
+        # above, exactly like the per-tensor buffers of the general path
+        return u
 
     @staticmethod
     def _exact(fn, *args, exact=True):

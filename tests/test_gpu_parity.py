@@ -133,6 +133,50 @@ def test_forward_is_deterministic():
     assert torch.equal(a, b)          # segmented reductions, no order-dependent atomics
 
 
+@pytest.mark.parametrize("cls_name", ["SphereNet", "DimeNetPP"])
+def test_lean_inference_path_is_bit_identical(cls_name, monkeypatch):
+    """The inference forward runs from a cached plan (parameter-only state: weight-pointer structs, packed weights,
+    projection rows) with raw workspace addresses; DIG3D_LEAN=0 selects the general op-by-op path.  Same kernels, same
+    arguments: bit-identical energies -- and the plan follows the parameters (in-place update, .data write +
+    invalidate_packed(), load_state_dict), and survives copy.deepcopy of the model."""
+    import copy
+    from dig_b200.data import synthetic_batch
+    from dig_b200.threedgraph import method
+    dev = torch.device("cuda:0")
+    model = getattr(method, cls_name)()
+    model.load_state_dict(formula_state_dict(model.state_dict(), seed=3))
+    model = model.to(dev).eval()
+    b = synthetic_batch(19, "qm9", seed=6, variable=True).to(dev)
+
+    def both():
+        with torch.no_grad():
+            monkeypatch.setenv("DIG3D_LEAN", "1")
+            lean = model(b)
+            lean2 = model(b)                      # second call: the cached plan
+            monkeypatch.setenv("DIG3D_LEAN", "0")
+            general = model(b)
+        assert "_plan" in model.__dict__
+        assert torch.equal(lean, general) and torch.equal(lean, lean2)
+        return lean
+
+    u0 = both()
+    with torch.no_grad():
+        model.update_es[1].lin_up.weight.mul_(1.5)            # in-place: bumps tensor._version
+    u1 = both()
+    assert not torch.equal(u0, u1)
+    model.update_es[2].lin_sbf1.weight.data.mul_(0.5)         # behind autograd's back: explicit invalidation
+    model.invalidate_packed()
+    u2 = both()
+    assert not torch.equal(u1, u2)
+    model.load_state_dict(formula_state_dict(model.state_dict(), seed=3))
+    assert torch.equal(both(), u0)
+    clone = copy.deepcopy(model)                              # plan / packed caches are not copied (device pointers)
+    assert "_plan" not in clone.__dict__
+    with torch.no_grad():
+        monkeypatch.setenv("DIG3D_LEAN", "1")
+        assert torch.equal(clone(b), u0)
+
+
 def test_segment_sum_against_index_add():
     from dig_b200 import ops
     torch.manual_seed(0)
