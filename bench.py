@@ -560,7 +560,9 @@ def main():
         # triplet gather: x_down rows once per edge (staged), 16 projected-basis floats per triplet, m out
         "dig3d_sphere_triplet_gather_node": (T * (2 * 2 * 8 * I + 3 * I), 4 * (E * I + T * 16 + E * I), "hbm"),
         "dig3d_sphere_triplet_gather": (T * (2 * 2 * 8 * I + 3 * I), 4 * (E * I + T * 16 + E * I), "hbm"),
+        "dig3d_sphere_triplet_gather_warp": (T * (2 * 2 * 8 * I + 3 * I), 4 * (E * I + T * 16 + E * I), "hbm"),
         "dig3d_triplet_basis_project": (2 * (E * 336 * 32 + T * 56 * 32), 4 * (E * 42 + 2 * T + 64 * T), "hbm"),
+        "dig3d_triplet_basis_project_lists": (2 * (E * 336 * 32 + T * 56 * 32), 4 * (E * 42 + 2 * T + 64 * T), "hbm"),
         "dig3d_sphere_update_v_batched": (5 * 2 * N * (128 * 256 + 3 * 256 * 256 + 256), 4 * 5 * N * (H + 1), "tensor"),
         "dig3d_sphere_update_v_h16": (5 * 2 * N * (128 * 256 + 3 * 256 * 256 + 256), 4 * 5 * N * (H + 1), "tensor"),
     }

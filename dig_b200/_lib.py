@@ -62,6 +62,9 @@ SIGNATURES = {
     "dig3d_knn2": [P, P, P, c_int64, c_int64, P, P, P],
     "dig3d_triplet_geometry_knn": [P, P, P, P, P, c_int64, P, P, P, P, P, P, P],
     "dig3d_triplet_count": [P, P, c_int64, c_int32, P, P],
+    "dig3d_triplet_count_out": [P, P, c_int64, c_int32, P, P, P],
+    "dig3d_scan_counts3": [P, P, P, c_int64, P, P, P, P, P],
+    "dig3d_edge_fill_out": [P, P, P, P, P, c_int64, c_int32, c_int64, P, P, P, P, P, P, P, P, P, P, P, P],
     "dig3d_scan_counts": [P, P, c_int64, P, P, P, P],
     "dig3d_edge_fill": [P, P, P, P, P, c_int64, c_int32, c_int64, P, P, P, P, P, P, P],
     "dig3d_edges_to_csr": [P, P, c_int64, c_int64, P, P, P, P, P, P, P, P],
@@ -72,6 +75,8 @@ SIGNATURES = {
     "dig3d_triplet_basis": [P, P, P, P, c_int64, c_int32, P, P, P],
     "dig3d_triplet_basis_project": [P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int32, c_int32,
                                     c_int32, P, P, P, P, P],
+    "dig3d_triplet_basis_project_lists": [P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int32, c_int32,
+                                    c_int32, P, P, P, P, P, P, P, P],
     "dig3d_triplet_basis_project_node": [P, P, P, P, P, P, P, P, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32,
                                          P, P, P, P, P],
     "dig3d_segment_sum": [P, P, c_int64, c_int64, P, P],
@@ -89,7 +94,8 @@ SIGNATURES = {
     "dig3d_sphere_update_e_a_tc": [P, P, c_int64, POINTER(TcUpdateE), P, P, P],
     "dig3d_sphere_triplet_gather": [P, P, P, c_int32, P, P, P, P, c_int64, P, P, P, P],
     "dig3d_sphere_triplet_gather_node": [P, P, P, c_int32, P, P, P, P, P, c_int64, c_int32, P, P, P, P],
-    "dig3d_sphere_triplet_gather_warp": [P, P, P, c_int32, P, P, P, P, P, c_int64, c_int32, c_int32, P, P, P, P],
+    "dig3d_sphere_triplet_gather_warp": [P, P, P, c_int32, P, P, P, P, P, c_int64, c_int32, c_int32, P, P, P, P, P,
+                                         P, P],
     "dig3d_sphere_triplet_gather_tc": [P, P, P, c_int32, P, P, P, P, P, c_int64, c_int32, P, P, P, P],
     "dig3d_sphere_update_e_b_tc": [P, P, P, P, P, c_int64, POINTER(TcUpdateE), P, P, P],
     "dig3d_tc_set_fast_swish": [c_int32],

@@ -347,7 +347,9 @@ triplet_basis_project_packed_kernel(const float* __restrict__ bess, const float*
                                     const int32_t* __restrict__ trip_ptr, const int32_t* __restrict__ graph_ptr,
                                     const int64_t* __restrict__ batch, int n_edges, int n_triplets,
                                     const float* __restrict__ w_sbf1, const float* __restrict__ w_t1,
-                                    float* __restrict__ sbf_p, float* __restrict__ t_p) {
+                                    float* __restrict__ sbf_p, float* __restrict__ t_p,
+                                    const int32_t* __restrict__ out_ptr, const int32_t* __restrict__ out_list,
+                                    const int32_t* __restrict__ pos_in) {
   constexpr int NS = BS::NS, NR = BS::NR, NB = BS::NB, NY = BS::NY;
   using SM = PrjPackSmem<BS>;
   constexpr int NP = SM::NP, ROW = SM::ROW;
@@ -376,13 +378,21 @@ triplet_basis_project_packed_kernel(const float* __restrict__ bess, const float*
     }
     const int jbase = row_ptr[j], dj = row_ptr[j + 1] - jbase;
     const int rank_k = kj - jbase;  // position of k among j's in-neighbours
-    const int g = (int)batch[j];
-    const int lo = graph_ptr[g], hi = graph_ptr[g + 1];
+    const bool lists = out_ptr != nullptr;
+    int lo, hi;
+    if (lists) { lo = out_ptr[j]; hi = out_ptr[j + 1]; }
+    else { const int g = (int)batch[j]; lo = graph_ptr[g]; hi = graph_ptr[g + 1]; }
     for (int c0 = lo; c0 < hi; c0 += 32) {
-      // out-edges e = (j -> i), i != k, among the nodes c0 .. c0 + 31 of j's graph (as in the scalar kernel)
+      // out-edges e = (j -> i), i != k: from the list of the graph build (entry c0 + lane; the position of i among j's
+      // in-neighbours comes with it, i == k <=> that position is rank_k), or searched among the nodes of j's graph
       const int i = c0 + lane;
       int t = -1;
-      if (i < hi && i != k && i != j) {
+      if (lists) {
+        if (i < hi) {
+          const int e = out_list[i], p = pos_in[e];
+          if (p != rank_k) t = trip_ptr[e] + rank_k - (p < rank_k ? 1 : 0);
+        }
+      } else if (i < hi && i != k && i != j) {
         const int ib = row_ptr[i], di = row_ptr[i + 1] - ib;
         int a = 0, b = di;
         while (a < b) { int mid = (a + b) >> 1; if (src[ib + mid] < j) a = mid + 1; else b = mid; }
@@ -1206,8 +1216,22 @@ int dig3d_triplet_basis_project(const float* bess, const float* angle, const flo
                                 int64_t n_edges, int64_t n_triplets, int32_t basis_id, int32_t n_layers,
                                 int32_t basis_emb, const float* w_sbf1, const float* w_t1, float* sbf_p,
                                 float* t_p, void* stream) {
+  return dig3d_triplet_basis_project_lists(bess, angle, torsion, src, dst, row_ptr, trip_ptr, graph_ptr, batch, n_edges,
+                                           n_triplets, basis_id, n_layers, basis_emb, w_sbf1, w_t1, sbf_p, t_p, nullptr,
+                                           nullptr, nullptr, stream);
+}
+
+int dig3d_triplet_basis_project_lists(const float* bess, const float* angle, const float* torsion,
+                                      const int32_t* src, const int32_t* dst, const int32_t* row_ptr,
+                                      const int32_t* trip_ptr, const int32_t* graph_ptr, const int64_t* batch,
+                                      int64_t n_edges, int64_t n_triplets, int32_t basis_id, int32_t n_layers,
+                                      int32_t basis_emb, const float* w_sbf1, const float* w_t1, float* sbf_p,
+                                      float* t_p, const int32_t* out_ptr, const int32_t* out_list,
+                                      const int32_t* pos_in, void* stream) {
   DIG3D_REQUIRE(bess && angle && src && dst && row_ptr && trip_ptr && graph_ptr && batch && w_sbf1 && sbf_p,
                 "triplet_basis_project: null pointer");
+  DIG3D_REQUIRE((out_ptr != nullptr) == (out_list != nullptr) && (out_ptr != nullptr) == (pos_in != nullptr),
+                "triplet_basis_project: out_ptr, out_list and pos_in come together");
   DIG3D_REQUIRE(n_layers * basis_emb == 32, "triplet_basis_project: n_layers*basis_emb must be 32, got %d*%d",
                 n_layers, basis_emb);
   const bool tors = (t_p != nullptr);
@@ -1239,7 +1263,8 @@ int dig3d_triplet_basis_project(const float* bess, const float* angle, const flo
       return DIG3D_ECUDA;                                                                                   \
     }                                                                                                       \
     kfn<<<grid, PRJ_WARPS * 32, smem, st>>>(bess, angle, torsion, src, dst, row_ptr, trip_ptr, graph_ptr,   \
-                                            batch, (int)n_edges, (int)n_triplets, w_sbf1, w_t1, sbf_p, t_p);\
+                                            batch, (int)n_edges, (int)n_triplets, w_sbf1, w_t1, sbf_p, t_p, \
+                                            out_ptr, out_list, pos_in);                                     \
   }
 #define DIG3D_PRJ(BS)                                                  \
   if (tors && h_project_mode == 2) DIG3D_PRJP_ONE(BS, true)            \

@@ -132,7 +132,7 @@ __device__ __forceinline__ int find_sorted(const int32_t* __restrict__ list, int
 // side by side instead of one after the other in a single thread (round 1: one thread per node, 23 us at 2 304 nodes --
 // pure latency).
 __global__ void triplet_count_kernel(const int32_t* __restrict__ nbr, const int32_t* __restrict__ deg,
-                                     int n_nodes, int cap, int32_t* __restrict__ tcnt) {
+                                     int n_nodes, int cap, int32_t* __restrict__ tcnt, int32_t* __restrict__ out_cnt) {
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= n_nodes) return;
   const int d = deg[i];
@@ -141,6 +141,7 @@ __global__ void triplet_count_kernel(const int32_t* __restrict__ nbr, const int3
     const int j = nbr[(size_t)i * cap + s];
     const int dj = deg[j];
     cnt += dj - (find_sorted(nbr + (size_t)j * cap, dj, i) >= 0 ? 1 : 0);
+    if (out_cnt) atomicAdd(out_cnt + j, 1);           // out-degree of the source (zero-initialised by the caller)
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
@@ -149,47 +150,52 @@ __global__ void triplet_count_kernel(const int32_t* __restrict__ nbr, const int3
 
 // ------------------------------------------------------------------ single-CTA dual exclusive scan
 __global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t* __restrict__ a,
-                                                          const int32_t* __restrict__ b, int n,
+                                                          const int32_t* __restrict__ b,
+                                                          const int32_t* __restrict__ c3, int n,
                                                           int32_t* __restrict__ pa, int32_t* __restrict__ pb,
-                                                          int32_t* __restrict__ totals) {
-  __shared__ int2 warp_tot[32];
-  __shared__ int2 carry;
+                                                          int32_t* __restrict__ pc, int32_t* __restrict__ totals) {
+  __shared__ int3 warp_tot[32];
+  __shared__ int3 carry;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid == 0) carry = make_int2(0, 0);
+  if (tid == 0) carry = make_int3(0, 0, 0);
   __syncthreads();
   for (int base = 0; base < n; base += 1024) {
     int idx = base + tid;
-    int2 v = (idx < n) ? make_int2(a[idx], b[idx]) : make_int2(0, 0);
-    int2 s = v;
+    int3 v = (idx < n) ? make_int3(a[idx], b[idx], c3 ? c3[idx] : 0) : make_int3(0, 0, 0);
+    int3 s = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      int tx = __shfl_up_sync(0xffffffffu, s.x, o), ty = __shfl_up_sync(0xffffffffu, s.y, o);
-      if (lane >= o) { s.x += tx; s.y += ty; }
+      int tx = __shfl_up_sync(0xffffffffu, s.x, o), ty = __shfl_up_sync(0xffffffffu, s.y, o),
+          tz = __shfl_up_sync(0xffffffffu, s.z, o);
+      if (lane >= o) { s.x += tx; s.y += ty; s.z += tz; }
     }
     if (lane == 31) warp_tot[wid] = s;
     __syncthreads();
     if (wid == 0) {
-      int2 w = warp_tot[lane];
+      int3 w = warp_tot[lane];
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        int tx = __shfl_up_sync(0xffffffffu, w.x, o), ty = __shfl_up_sync(0xffffffffu, w.y, o);
-        if (lane >= o) { w.x += tx; w.y += ty; }
+        int tx = __shfl_up_sync(0xffffffffu, w.x, o), ty = __shfl_up_sync(0xffffffffu, w.y, o),
+            tz = __shfl_up_sync(0xffffffffu, w.z, o);
+        if (lane >= o) { w.x += tx; w.y += ty; w.z += tz; }
       }
       warp_tot[lane] = w;
     }
     __syncthreads();
-    int2 c = carry;
-    int2 wofs = (wid == 0) ? make_int2(0, 0) : warp_tot[wid - 1];
+    int3 c = carry;
+    int3 wofs = (wid == 0) ? make_int3(0, 0, 0) : warp_tot[wid - 1];
     if (idx < n) {
       pa[idx] = c.x + wofs.x + s.x - v.x;
       pb[idx] = c.y + wofs.y + s.y - v.y;
+      if (pc) pc[idx] = c.z + wofs.z + s.z - v.z;
     }
     __syncthreads();
-    if (tid == 0) { carry.x = c.x + warp_tot[31].x; carry.y = c.y + warp_tot[31].y; }
+    if (tid == 0) { carry.x = c.x + warp_tot[31].x; carry.y = c.y + warp_tot[31].y; carry.z = c.z + warp_tot[31].z; }
     __syncthreads();
   }
   if (tid == 0) {
     pa[n] = carry.x; pb[n] = carry.y;
+    if (pc) pc[n] = carry.z;
     totals[0] = carry.x; totals[1] = carry.y;
   }
 }
@@ -202,9 +208,38 @@ __global__ void edge_fill_kernel(const float* __restrict__ pos, const int32_t* _
                                  const int32_t* __restrict__ node_trip_ptr, int n_nodes, int cap,
                                  int64_t n_edges, int64_t* __restrict__ edge_index, int32_t* __restrict__ src,
                                  int32_t* __restrict__ dst, float* __restrict__ dist, float* __restrict__ vec,
-                                 int32_t* __restrict__ trip_ptr) {
+                                 int32_t* __restrict__ trip_ptr, const int32_t* __restrict__ graph_ptr,
+                                 const int64_t* __restrict__ batch, const int32_t* __restrict__ out_ptr,
+                                 int32_t* __restrict__ out_list, int32_t* __restrict__ pos_in) {
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= n_nodes) return;
+  if (out_list) {
+    // Node i as a SOURCE: its out-edges (i -> c), c ascending over the nodes of its graph, with the position of c
+    // among i's own in-neighbours (deg[i] if absent).  The triplet kernels used to rediscover this list -- one binary
+    // search per candidate node -- once per in-edge (projection) and once per layer (gather).
+    const int g = (int)batch[i];
+    const int lo = graph_ptr[g], hi = graph_ptr[g + 1], di = deg[i];
+    int w = out_ptr[i];
+    for (int c0 = lo; c0 < hi; c0 += 32) {
+      const int c = c0 + lane;
+      int e = -1, p = 0;
+      if (c < hi && c != i) {
+        const int dc = deg[c];
+        const int q = find_sorted(nbr + (size_t)c * cap, dc, i);       // slot of i among c's in-neighbours
+        if (q >= 0) {
+          e = row_ptr[c] + q;
+          const int r = find_sorted(nbr + (size_t)i * cap, di, c);
+          p = r >= 0 ? r : di;
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, e >= 0);
+      if (e >= 0) {
+        out_list[w + __popc(m & ((1u << lane) - 1))] = e;
+        pos_in[e] = p;
+      }
+      w += __popc(m);
+    }
+  }
   const int d = deg[i], e0 = row_ptr[i];
   int t = node_trip_ptr[i];
   const f3 pi = load3(pos, i);
@@ -419,7 +454,7 @@ using namespace dig3d;
 extern "C" {
 
 const char* dig3d_last_error(void) { return g_err; }
-int dig3d_abi_version(void) { return 1; }
+int dig3d_abi_version(void) { return 2; }
 
 int dig3d_graph_ptr(const int64_t* batch, int64_t n_nodes, int64_t n_graphs, int32_t* ptr, void* stream) {
   DIG3D_REQUIRE(batch && ptr && n_nodes >= 0 && n_graphs >= 0, "graph_ptr: bad arguments");
@@ -451,21 +486,49 @@ int dig3d_radius_neighbors(const float* pos, const int64_t* batch, const int32_t
   return DIG3D_OK;
 }
 
-int dig3d_triplet_count(const int32_t* nbr, const int32_t* deg, int64_t n_nodes, int32_t cap, int32_t* tcnt,
-                        void* stream) {
+int dig3d_triplet_count_out(const int32_t* nbr, const int32_t* deg, int64_t n_nodes, int32_t cap, int32_t* tcnt,
+                            int32_t* out_cnt, void* stream) {
   DIG3D_REQUIRE(nbr && deg && tcnt, "triplet_count: null pointer");
   if (n_nodes == 0) return DIG3D_OK;
   triplet_count_kernel<<<ceil_div(n_nodes * 32, 128), 128, 0, (cudaStream_t)stream>>>(nbr, deg, (int)n_nodes, cap,
-                                                                             tcnt);
+                                                                                   tcnt, out_cnt);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_triplet_count(const int32_t* nbr, const int32_t* deg, int64_t n_nodes, int32_t cap, int32_t* tcnt,
+                        void* stream) {
+  return dig3d_triplet_count_out(nbr, deg, n_nodes, cap, tcnt, nullptr, stream);
+}
+
+int dig3d_scan_counts3(const int32_t* deg, const int32_t* tcnt, const int32_t* out_cnt, int64_t n_nodes,
+                       int32_t* row_ptr, int32_t* node_trip_ptr, int32_t* out_ptr, int32_t* totals, void* stream) {
+  DIG3D_REQUIRE(deg && tcnt && row_ptr && node_trip_ptr && totals, "scan_counts: null pointer");
+  DIG3D_REQUIRE((out_cnt != nullptr) == (out_ptr != nullptr), "scan_counts: out_cnt and out_ptr must agree");
+  scan_counts_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(deg, tcnt, out_cnt, (int)n_nodes, row_ptr, node_trip_ptr,
+                                                         out_ptr, totals);
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
 }
 
 int dig3d_scan_counts(const int32_t* deg, const int32_t* tcnt, int64_t n_nodes, int32_t* row_ptr,
                       int32_t* node_trip_ptr, int32_t* totals, void* stream) {
-  DIG3D_REQUIRE(deg && tcnt && row_ptr && node_trip_ptr && totals, "scan_counts: null pointer");
-  scan_counts_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(deg, tcnt, (int)n_nodes, row_ptr, node_trip_ptr,
-                                                         totals);
+  return dig3d_scan_counts3(deg, tcnt, nullptr, n_nodes, row_ptr, node_trip_ptr, nullptr, totals, stream);
+}
+
+int dig3d_edge_fill_out(const float* pos, const int32_t* nbr, const int32_t* deg, const int32_t* row_ptr,
+                        const int32_t* node_trip_ptr, int64_t n_nodes, int32_t cap, int64_t n_edges,
+                        int64_t* edge_index, int32_t* src, int32_t* dst, float* dist, float* vec,
+                        int32_t* trip_ptr, const int32_t* graph_ptr, const int64_t* batch, const int32_t* out_ptr,
+                        int32_t* out_list, int32_t* pos_in, void* stream) {
+  DIG3D_REQUIRE(pos && nbr && deg && row_ptr && node_trip_ptr && src && dst && dist && trip_ptr,
+                "edge_fill: null pointer");
+  DIG3D_REQUIRE(!out_list || (graph_ptr && batch && out_ptr && pos_in),
+                "edge_fill: the out-edge lists need graph_ptr, batch, out_ptr and pos_in");
+  if (n_nodes == 0) return DIG3D_OK;
+  edge_fill_kernel<<<ceil_div(n_nodes * 32, 128), 128, 0, (cudaStream_t)stream>>>(
+      pos, nbr, deg, row_ptr, node_trip_ptr, (int)n_nodes, cap, n_edges, edge_index, src, dst, dist, vec,
+      trip_ptr, graph_ptr, batch, out_ptr, out_list, pos_in);
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
 }
@@ -474,14 +537,8 @@ int dig3d_edge_fill(const float* pos, const int32_t* nbr, const int32_t* deg, co
                     const int32_t* node_trip_ptr, int64_t n_nodes, int32_t cap, int64_t n_edges,
                     int64_t* edge_index, int32_t* src, int32_t* dst, float* dist, float* vec,
                     int32_t* trip_ptr, void* stream) {
-  DIG3D_REQUIRE(pos && nbr && deg && row_ptr && node_trip_ptr && src && dst && dist && trip_ptr,
-                "edge_fill: null pointer");
-  if (n_nodes == 0) return DIG3D_OK;
-  edge_fill_kernel<<<ceil_div(n_nodes * 32, 128), 128, 0, (cudaStream_t)stream>>>(
-      pos, nbr, deg, row_ptr, node_trip_ptr, (int)n_nodes, cap, n_edges, edge_index, src, dst, dist, vec,
-      trip_ptr);
-  DIG3D_LAUNCH_CHECK();
-  return DIG3D_OK;
+  return dig3d_edge_fill_out(pos, nbr, deg, row_ptr, node_trip_ptr, n_nodes, cap, n_edges, edge_index, src, dst, dist,
+                             vec, trip_ptr, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
 }
 
 int dig3d_triplet_geometry(const float* pos, const int32_t* src, const int32_t* dst, const int32_t* row_ptr,
@@ -539,7 +596,8 @@ int dig3d_edges_to_csr(const float* pos, const int64_t* edge_index, int64_t n_ed
                                                                     GEO_MAXDEG, cnt_ws, dist, flags);
     DIG3D_LAUNCH_CHECK();
   }
-  scan_counts_kernel<<<1, 1024, 0, st>>>(cnt_ws, cnt_ws, (int)n_edges, trip_ptr, cnt_ws + n_edges + 1, flags + 2);
+  scan_counts_kernel<<<1, 1024, 0, st>>>(cnt_ws, cnt_ws, nullptr, (int)n_edges, trip_ptr, cnt_ws + n_edges + 1, nullptr,
+                                         flags + 2);
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
 }

@@ -485,7 +485,9 @@ sphere_triplet_gather_warp_kernel(const float* __restrict__ x_down, const float*
                                   const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ trip_ptr,
                                   const int32_t* __restrict__ graph_ptr, const int64_t* __restrict__ batch,
                                   int n_nodes, int split, int cap, const float* __restrict__ w_sbf2,
-                                  const float* __restrict__ w_t2, float* __restrict__ m) {
+                                  const float* __restrict__ w_t2, float* __restrict__ m,
+                                  const int32_t* __restrict__ out_ptr, const int32_t* __restrict__ out_list,
+                                  const int32_t* __restrict__ pos_in) {
   extern __shared__ __align__(128) unsigned char tgw_smem[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const size_t per_warp = (size_t)cap * 256 + 512 + 128;
@@ -497,7 +499,12 @@ sphere_triplet_gather_warp_kernel(const float* __restrict__ x_down, const float*
   if (task >= n_nodes * split) return;
   const int j = task / split, sub = task - j * split;
   const int base = row_ptr[j], d = row_ptr[j + 1] - base;
-  const int g = (int)batch[j], lo = graph_ptr[g], hi = graph_ptr[g + 1];
+  // out-edges of j: the list the graph build left (out_ptr / out_list / pos_in), or -- for graphs that came without it
+  // (caller-supplied edge_index) -- a search over the nodes of j's graph
+  const bool lists = out_ptr != nullptr;
+  int lo, hi;
+  if (lists) { lo = out_ptr[j]; hi = out_ptr[j + 1]; }
+  else { const int g = (int)batch[j]; lo = graph_ptr[g]; hi = graph_ptr[g + 1]; }
   if (lane == 0) {
     mbar_init(bar, 1);
     mbar_fence_init();
@@ -506,7 +513,7 @@ sphere_triplet_gather_warp_kernel(const float* __restrict__ x_down, const float*
       bulk_g2s(&rows[0][0], x_down + (size_t)base * 64, (uint32_t)d * 256u, bar);
     }
   }
-  const int in_a = lane < d ? src[base + lane] : -1, in_b = lane + 32 < d ? src[base + lane + 32] : -1;
+  const int in_a = !lists && lane < d ? src[base + lane] : -1, in_b = !lists && lane + 32 < d ? src[base + lane + 32] : -1;
   float2 wq[2][8];
   tg_load_weights<TORSION>(wq, w_sbf2, w_t2, lane);
   __syncwarp();
@@ -529,8 +536,10 @@ sphere_triplet_gather_warp_kernel(const float* __restrict__ x_down, const float*
   int seen = 0;                      // out-edges of j met so far (all shares)
   for (int c0 = lo; c0 < hi; c0 += 32) {
     const int i = c0 + lane;
-    int e_l = -1;
-    if (i < hi && i != j) {
+    int e_l = -1, p_l = d;
+    if (lists) {
+      if (i < hi) { e_l = out_list[i]; p_l = pos_in[e_l]; }
+    } else if (i < hi && i != j) {
       const int ib = row_ptr[i], di = row_ptr[i + 1] - ib;
       int a = 0, b = di;
       while (a < b) { const int mid = (a + b) >> 1; if (src[ib + mid] < j) a = mid + 1; else b = mid; }
@@ -546,7 +555,7 @@ sphere_triplet_gather_warp_kernel(const float* __restrict__ x_down, const float*
     // edge, or the first chunk of the next selected edge)
     int bit = __ffs(sel) - 1;
     sel &= sel - 1;
-    int e = __shfl_sync(0xffffffffu, e_l, bit), p_i = position(c0 + bit);
+    int e = __shfl_sync(0xffffffffu, e_l, bit), p_i = lists ? __shfl_sync(0xffffffffu, p_l, bit) : position(c0 + bit);
     int t0 = trip_ptr[e], nt = d - (p_i < d ? 1 : 0);
     float sa = 0.f, sb = 0.f, ta = 0.f, tb = 0.f;
     bool fetched = false;
@@ -556,7 +565,7 @@ sphere_triplet_gather_warp_kernel(const float* __restrict__ x_down, const float*
         const int bn = __ffs(sel) - 1;
         sel &= sel - 1;
         e_n = __shfl_sync(0xffffffffu, e_l, bn);
-        p_n = position(c0 + bn);
+        p_n = lists ? __shfl_sync(0xffffffffu, p_l, bn) : position(c0 + bn);
         t0_n = trip_ptr[e_n]; nt_n = d - (p_n < d ? 1 : 0);
       }
       if (!fetched && nt > 0) fetch(t0, nt, sa, sb, ta, tb);
@@ -1245,9 +1254,13 @@ int dig3d_sphere_triplet_gather_node(const float* x_down, const float* sbf_p, co
 int dig3d_sphere_triplet_gather_warp(const float* x_down, const float* sbf_p, const float* t_p, int32_t ld_p,
                                      const int32_t* src, const int32_t* row_ptr, const int32_t* trip_ptr,
                                      const int32_t* graph_ptr, const int64_t* batch, int64_t n_nodes, int32_t cap,
-                                     int32_t split, const float* w_sbf2, const float* w_t2, float* m, void* stream) {
+                                     int32_t split, const float* w_sbf2, const float* w_t2, float* m,
+                                     const int32_t* out_ptr, const int32_t* out_list, const int32_t* pos_in,
+                                     void* stream) {
   DIG3D_REQUIRE(x_down && sbf_p && src && row_ptr && trip_ptr && graph_ptr && batch && w_sbf2 && m,
                 "sphere_triplet_gather_warp: null pointer");
+  DIG3D_REQUIRE((out_ptr != nullptr) == (out_list != nullptr) && (out_ptr != nullptr) == (pos_in != nullptr),
+                "sphere_triplet_gather_warp: out_ptr, out_list and pos_in come together");
   DIG3D_REQUIRE((t_p != nullptr) == (w_t2 != nullptr), "sphere_triplet_gather_warp: t_p and w_t2 must agree");
   DIG3D_REQUIRE(ld_p == 8, "sphere_triplet_gather_warp: expects the layer-major [T, 8] slices (ld_p == 8), got %d", ld_p);
   DIG3D_REQUIRE(cap >= 1 && cap <= TGN_MAXIN, "sphere_triplet_gather_warp: cap=%d outside [1,%d]", cap, TGN_MAXIN);
@@ -1263,7 +1276,7 @@ int dig3d_sphere_triplet_gather_warp(const float* x_down, const float* sbf_p, co
     return DIG3D_ECUDA;
   }
   kfn<<<grid, TGW_WARPS * 32, smem, st>>>(x_down, sbf_p, t_p, src, row_ptr, trip_ptr, graph_ptr, batch, (int)n_nodes,
-                                          (int)split, (int)cap, w_sbf2, w_t2, m);
+                                          (int)split, (int)cap, w_sbf2, w_t2, m, out_ptr, out_list, pos_in);
   DIG3D_LAUNCH_CHECK();
   return DIG3D_OK;
 }

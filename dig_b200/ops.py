@@ -55,7 +55,8 @@ class Graph3D:
     """Radius graph in CSR-by-target form plus the implicit triplet structure."""
     __slots__ = ("n_nodes", "n_graphs", "n_edges", "n_triplets", "cap", "graph_ptr", "batch",
                  "row_ptr", "src", "dst", "edge_index", "dist", "vec", "trip_ptr",
-                 "angle", "torsion", "idx_kj", "idx_ji", "idx_kj64", "idx_ji64")
+                 "angle", "torsion", "idx_kj", "idx_ji", "idx_kj64", "idx_ji64",
+                 "out_ptr", "out_list", "pos_in")      # out-edge lists (CSR by source), None for graphs built without them
 
     def __init__(self):
         for s in self.__slots__:
@@ -99,10 +100,13 @@ def build_graph(pos, batch, cutoff, num_graphs=None, max_num_neighbors=32, want_
          ctypes.c_void_p(totals.data_ptr() + 8), st)
     call("dig3d_radius_neighbors", _p(pos, torch.float32, "pos"), _p(batch), _p(g.graph_ptr), n, g.n_graphs,
          float(cutoff), cap, _p(nbr), _p(deg), st)
-    call("dig3d_triplet_count", _p(nbr), _p(deg), n, cap, _p(tcnt), st)
+    out_cnt = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
+    call("dig3d_triplet_count_out", _p(nbr), _p(deg), n, cap, _p(tcnt), _p(out_cnt), st)
     g.row_ptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
     node_trip_ptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
-    call("dig3d_scan_counts", _p(deg), _p(tcnt), n, _p(g.row_ptr), _p(node_trip_ptr), _p(totals), st)
+    g.out_ptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    call("dig3d_scan_counts3", _p(deg), _p(tcnt), _p(out_cnt), n, _p(g.row_ptr), _p(node_trip_ptr), _p(g.out_ptr),
+         _p(totals), st)
     tot = totals[:3].tolist()                      # the one sync of the forward pass
     if tot[2]:
         what = [msg for bit, msg in ((1, f"batch ids outside [0, {g.n_graphs})"), (2, "batch is not sorted ascending"),
@@ -116,11 +120,21 @@ def build_graph(pos, batch, cutoff, num_graphs=None, max_num_neighbors=32, want_
     g.trip_ptr = torch.zeros(e + 1, dtype=torch.int32, device=dev)
     g.edge_index = torch.empty(2, e, dtype=torch.int64, device=dev) if want_edge_index else None
     g.vec = torch.empty(e, 3, dtype=torch.float32, device=dev) if want_vec else None
+    g.out_list = torch.empty(max(e, 1), dtype=torch.int32, device=dev)[:e]
+    g.pos_in = torch.empty(max(e, 1), dtype=torch.int32, device=dev)[:e]
     if e:
-        call("dig3d_edge_fill", _p(pos), _p(nbr), _p(deg), _p(g.row_ptr), _p(node_trip_ptr), n, cap, e,
+        call("dig3d_edge_fill_out", _p(pos), _p(nbr), _p(deg), _p(g.row_ptr), _p(node_trip_ptr), n, cap, e,
              _p(g.edge_index) if want_edge_index else None, _p(g.src), _p(g.dst), _p(g.dist),
-             _p(g.vec) if want_vec else None, _p(g.trip_ptr), st)
+             _p(g.vec) if want_vec else None, _p(g.trip_ptr), _p(g.graph_ptr), _p(batch), _p(g.out_ptr), _p(g.out_list),
+             _p(g.pos_in), st)
     return g
+
+
+def _out_lists(g):
+    """(out_ptr, out_list, pos_in) device addresses of a graph's out-edge lists, or three NULLs."""
+    if getattr(g, "out_ptr", None) is None or g.out_list is None or g.pos_in is None:
+        return None, None, None
+    return g.out_ptr.data_ptr(), g.out_list.data_ptr(), g.pos_in.data_ptr()
 
 
 def triplet_geometry(g, pos, use_torsion, want_idx=True, want_idx64=False):
@@ -205,12 +219,12 @@ def triplet_basis_project(g, bess, basis_id, w_sbf1_rows, w_t1_rows):
              _p(w_t1_rows, torch.float32, "w_t1") if w_t1_rows is not None else None,
              _p(sbf_p), _p(t_p) if t_p is not None else None, _stream())
     elif t and g.n_edges:
-        call("dig3d_triplet_basis_project", _p(bess, torch.float32), _p(g.angle),
+        call("dig3d_triplet_basis_project_lists", _p(bess, torch.float32), _p(g.angle),
              _p(g.torsion) if w_t1_rows is not None else None, _p(g.src), _p(g.dst), _p(g.row_ptr),
              _p(g.trip_ptr), _p(g.graph_ptr), _p(g.batch, torch.int64), g.n_edges, t, int(basis_id), 4, 8,
              _p(w_sbf1_rows, torch.float32, "w_sbf1"),
              _p(w_t1_rows, torch.float32, "w_t1") if w_t1_rows is not None else None,
-             _p(sbf_p), _p(t_p) if t_p is not None else None, _stream())
+             _p(sbf_p), _p(t_p) if t_p is not None else None, *_out_lists(g), _stream())
     return sbf_p, t_p
 
 
@@ -586,7 +600,8 @@ def triplet_gather(x_down, sp, tp, g, w_sbf2, w_t2, m_out, st):
     mode = GATHER_MODE[0]
     if mode == "warp":
         call("dig3d_sphere_triplet_gather_warp", _ptr(x_down), sp, tp, 8, _p(g.src), _p(g.row_ptr), _p(g.trip_ptr),
-             _p(g.graph_ptr), _p(g.batch, torch.int64), g.n_nodes, g.cap, gather_split(g), w_sbf2, w_t2, _ptr(m_out), st)
+             _p(g.graph_ptr), _p(g.batch, torch.int64), g.n_nodes, g.cap, gather_split(g), w_sbf2, w_t2, _ptr(m_out),
+             *_out_lists(g), st)
     elif mode in ("node", "tc"):
         call("dig3d_sphere_triplet_gather_tc" if mode == "tc" else "dig3d_sphere_triplet_gather_node", _ptr(x_down), sp,
              tp, 8, _p(g.src), _p(g.row_ptr), _p(g.trip_ptr), _p(g.graph_ptr), _p(g.batch, torch.int64), g.n_nodes, g.cap,

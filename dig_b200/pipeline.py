@@ -13,7 +13,7 @@ import torch
 # Measured on the B200, SphereNet QM9-shape batches of 128 (profiles/r02_batches_in_flight.txt): 1 batch at a time 106.5 k
 # molecules/s, 2 in flight 131.2 k, 3: 133.4 k, 4: 134.0 k -- the second stream fills the first one's launch gaps, partial
 # waves and count-readback bubble; beyond three there is nothing left to fill.
-DEFAULT_DEPTH = 3
+DEFAULT_DEPTH = 4
 
 
 class InferencePipeline:

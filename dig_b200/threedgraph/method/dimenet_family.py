@@ -402,9 +402,9 @@ class _DimeNetFamily(nn.Module):
         call("dig3d_edge_basis", g.dist.data_ptr(), E, float(self.cutoff), int(self.envelope_exponent),
              ops._p(plan["freq"], torch.float32, "freq"), int(self._basis_id), int(not tors), a["rbf0"], a["bess"], st)
         if T:
-            call("dig3d_triplet_basis_project", a["bess"], a["angle"], a["torsion"] if tors else None, src, dst, row_ptr,
-                 trip_ptr, graph_ptr, batch, E, T, int(self._basis_id), 4, 8, plan["w_s"].data_ptr(),
-                 plan["w_t"].data_ptr() if tors else None, a["sbf_p"], a["t_p"] if tors else None, st)
+            call("dig3d_triplet_basis_project_lists", a["bess"], a["angle"], a["torsion"] if tors else None, src, dst,
+                 row_ptr, trip_ptr, graph_ptr, batch, E, T, int(self._basis_id), 4, 8, plan["w_s"].data_ptr(),
+                 plan["w_t"].data_ptr() if tors else None, a["sbf_p"], a["t_p"] if tors else None, *ops._out_lists(g), st)
         call("dig3d_sphere_init_e_h16", ops._p(z, torch.int64, "z"), src, dst, a["rbf0"], E, byref(plan["init_w"]),
              plan["init_packed"].data_ptr(), a["e1a"], v_in, st)
         e1, e1_next = a["e1a"], a["e1b"]

@@ -66,9 +66,18 @@ int dig3d_validate_nodes(const int64_t* batch, const int64_t* z, int64_t n_nodes
 int dig3d_triplet_count(const int32_t* nbr, const int32_t* deg, int64_t n_nodes, int32_t cap,
                         int32_t* tcnt, void* stream);
 
+/* The same, also counting the OUT-degree of every node into out_cnt[n_nodes] (zero-initialised by the caller, nullable):
+ * the radius graph caps the in-degree only, so the out-degree is not the in-degree. */
+int dig3d_triplet_count_out(const int32_t* nbr, const int32_t* deg, int64_t n_nodes, int32_t cap, int32_t* tcnt,
+                            int32_t* out_cnt, void* stream);
+
 /* Exclusive scans: row_ptr[0..n] of deg, node_trip_ptr[0..n] of tcnt; totals[0]=E, totals[1]=T. */
 int dig3d_scan_counts(const int32_t* deg, const int32_t* tcnt, int64_t n_nodes, int32_t* row_ptr,
                       int32_t* node_trip_ptr, int32_t* totals, void* stream);
+
+/* dig3d_scan_counts plus out_ptr[0..n] = exclusive scan of out_cnt (both nullable together). */
+int dig3d_scan_counts3(const int32_t* deg, const int32_t* tcnt, const int32_t* out_cnt, int64_t n_nodes,
+                       int32_t* row_ptr, int32_t* node_trip_ptr, int32_t* out_ptr, int32_t* totals, void* stream);
 
 /* Per-edge arrays, edges sorted by (target i, source j):
  *   edge_index[2,E] int64 (row 0 = source j, row 1 = target i), src/dst int32, dist[E],
@@ -78,6 +87,16 @@ int dig3d_edge_fill(const float* pos, const int32_t* nbr, const int32_t* deg, co
                     const int32_t* node_trip_ptr, int64_t n_nodes, int32_t cap, int64_t n_edges,
                     int64_t* edge_index, int32_t* src, int32_t* dst, float* dist, float* vec,
                     int32_t* trip_ptr, void* stream);
+
+/* dig3d_edge_fill plus the OUT-edge lists (CSR by source; all three nullable together): out_list[out_ptr[j] ..
+ * out_ptr[j+1]) = the edges (j -> i) in ascending i, pos_in[e] for e = (j -> i) = position of i among j's own
+ * in-neighbours (deg[j] if i is not one).  The triplet kernels (projection: per (k -> j) edge; gather: per node and
+ * layer) read them instead of searching the nodes of j's graph for j's out-edges. */
+int dig3d_edge_fill_out(const float* pos, const int32_t* nbr, const int32_t* deg, const int32_t* row_ptr,
+                        const int32_t* node_trip_ptr, int64_t n_nodes, int32_t cap, int64_t n_edges,
+                        int64_t* edge_index, int32_t* src, int32_t* dst, float* dist, float* vec,
+                        int32_t* trip_ptr, const int32_t* graph_ptr, const int64_t* batch, const int32_t* out_ptr,
+                        int32_t* out_list, int32_t* pos_in, void* stream);
 
 /* CSR / triplet offsets / distances for a CALLER-SUPPLIED edge_index [2,E] int64 sorted by (target, source)
  * (the entry of xyz_to_dat(pos, edge_index, num_nodes, ...), utils/geometric_computing.py:12).
@@ -126,6 +145,14 @@ int dig3d_triplet_basis_project(const float* bess, const float* angle, const flo
                                 int64_t n_edges, int64_t n_triplets, int32_t basis_id, int32_t n_layers,
                                 int32_t basis_emb, const float* w_sbf1, const float* w_t1, float* sbf_p,
                                 float* t_p, void* stream);
+/* The same with the out-edge lists of dig3d_edge_fill_out (nullable together; used by the packed torsion kernels). */
+int dig3d_triplet_basis_project_lists(const float* bess, const float* angle, const float* torsion,
+                                      const int32_t* src, const int32_t* dst, const int32_t* row_ptr,
+                                      const int32_t* trip_ptr, const int32_t* graph_ptr, const int64_t* batch,
+                                      int64_t n_edges, int64_t n_triplets, int32_t basis_id, int32_t n_layers,
+                                      int32_t basis_emb, const float* w_sbf1, const float* w_t1, float* sbf_p,
+                                      float* t_p, const int32_t* out_ptr, const int32_t* out_list,
+                                      const int32_t* pos_in, void* stream);
 /* Process-wide experiment switch for the torsion models' projection (spherenet.py:163,167): 0 = scalar kernel with the
  * reference-rounded closed-form harmonics (round 1), 1 = packed (FFMA2) kernel with the same closed forms, 2 (default) =
  * packed kernel with the harmonics evaluated from the recurrences the reference derives its closed forms from
@@ -251,11 +278,14 @@ int dig3d_sphere_triplet_gather_node(const float* x_down, const float* sbf_p, co
                                      const float* w_sbf2, const float* w_t2, float* m, void* stream);
 /* Same result (bit-identical) with one WARP per (source node, share): no CTA-wide barrier, the warp's own bulk copy /
  * mbarrier, in-neighbour positions by ballot.  split >= 1 warps share a node (out-edge r of the node goes to share
- * r % split); cap = max in-degree + 1 <= 64. */
+ * r % split); cap = max in-degree + 1 <= 64.  out_ptr / out_list / pos_in: the out-edge lists of dig3d_edge_fill_out
+ * (nullable together: without them the warp searches the nodes of the graph). */
 int dig3d_sphere_triplet_gather_warp(const float* x_down, const float* sbf_p, const float* t_p, int32_t ld_p,
                                      const int32_t* src, const int32_t* row_ptr, const int32_t* trip_ptr,
                                      const int32_t* graph_ptr, const int64_t* batch, int64_t n_nodes, int32_t cap,
-                                     int32_t split, const float* w_sbf2, const float* w_t2, float* m, void* stream);
+                                     int32_t split, const float* w_sbf2, const float* w_t2, float* m,
+                                     const int32_t* out_ptr, const int32_t* out_list, const int32_t* pos_in,
+                                     void* stream);
 /* lin_up + residual stack + lin (spherenet.py:172-180) on tcgen05; writes e1_out, ACCUMULATES e2 into v_in. */
 int dig3d_sphere_update_e_b_tc(const float* m, const float* e1_in, const float* x_ji, const float* rbf0,
                                const int32_t* dst, int64_t n_edges, const dig3d_tc_update_e* w, float* e1_out,

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"libdig3d.so lacks {name}"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
     assert set(_lib.SIGNATURES) == set(declared)
-    assert lib.dig3d_abi_version() == 1
+    assert lib.dig3d_abi_version() == 2
 
 
 def test_library_is_sm100a():

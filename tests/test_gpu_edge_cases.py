@@ -152,3 +152,53 @@ def test_out_of_range_indices_raise_instead_of_reading_out_of_bounds():
         ops.build_graph(b.pos, unsorted, 5.0, num_graphs=3)
     g = ops.build_graph(b.pos, b.batch, 5.0, num_graphs=3)       # the context is still healthy afterwards
     assert g.n_edges > 0
+
+
+def test_out_edge_lists_of_the_graph_build():
+    """out_ptr / out_list / pos_in (CSR by SOURCE, left by the graph build for the triplet kernels) against their
+    definition computed from edge_index: capped dense graph (out-degree != in-degree), isolated atom, > 32 atoms per
+    molecule -- and the triplet gather / projection are bit-identical with and without the lists."""
+    import ctypes
+    from dig_b200 import ops
+    from dig_b200.data import synthetic_batch, collate, Molecule
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    dense = (torch.rand(70, 3) * 3.0)
+    mols = synthetic_batch(6, "qm9", seed=9, variable=True)
+    b = collate([Molecule(torch.full((70,), 6), dense), Molecule(torch.tensor([8]), torch.tensor([[90.0, 0, 0]])),
+                 Molecule(mols.z, mols.pos + 200.0)]).to(dev)
+    b.batch = torch.cat([torch.zeros(70), torch.ones(1), torch.full((mols.z.numel(),), 2.0)]).long().to(dev)
+    g = ops.build_graph(b.pos, b.batch, 5.0, num_graphs=3)
+    src, dst = g.edge_index[0].cpu().numpy(), g.edge_index[1].cpu().numpy()
+    n, e = g.n_nodes, g.n_edges
+    out_ptr, out_list, pos_in = g.out_ptr.cpu().numpy(), g.out_list.cpu().numpy(), g.pos_in.cpu().numpy()
+    row_ptr = g.row_ptr.cpu().numpy()
+    assert np.array_equal(out_ptr, np.concatenate([[0], np.cumsum(np.bincount(src, minlength=n))]))
+    assert not np.array_equal(np.diff(out_ptr), np.diff(row_ptr))           # the cap broke the symmetry somewhere
+    order = np.lexsort((dst, src))                                           # by source, then target
+    assert np.array_equal(out_list, order)
+    for ed in range(e):
+        j, i = src[ed], dst[ed]
+        ins = src[row_ptr[j]:row_ptr[j + 1]]
+        hit = np.nonzero(ins == i)[0]
+        assert pos_in[ed] == (hit[0] if hit.size else ins.size)
+    # consumers: lists vs search
+    ops.triplet_geometry(g, b.pos, use_torsion=True, want_idx=False)
+    t = g.n_triplets
+    x_down = torch.randn(e, 64, device=dev)
+    sbf_p, t_p = torch.randn(t, 8, device=dev), torch.randn(t, 8, device=dev)
+    w_s, w_t = torch.randn(64, 8, device=dev), torch.randn(64, 8, device=dev)
+    bess = torch.randn(e, 42, device=dev)
+    w1s, w1t = torch.randn(32, 42, device=dev), torch.randn(32, 294, device=dev)
+    lists = (g.out_ptr, g.out_list, g.pos_in)
+    outs = []
+    for use in (True, False):
+        g.out_ptr, g.out_list, g.pos_in = lists if use else (None, None, None)
+        m = torch.full((e, 64), float("nan"), device=dev)
+        ops.triplet_gather(x_down, ctypes.c_void_p(sbf_p.data_ptr()), ctypes.c_void_p(t_p.data_ptr()), g,
+                           w_s.data_ptr(), w_t.data_ptr(), m, ops._stream())
+        sp, tp = ops.triplet_basis_project(g, bess, 0, w1s, w1t)
+        outs.append((m, sp.clone(), tp.clone()))
+    g.out_ptr, g.out_list, g.pos_in = lists
+    for a, c in zip(outs[0], outs[1]):
+        assert torch.isfinite(a).all() and torch.equal(a, c)

@@ -32,6 +32,19 @@ for rep in range(3):
     run(200)
     torch.cuda.synchronize()
     print(f"pipeline (depth {pipe.depth}): {1e3 * (time.perf_counter() - t0) / 200:.4f} ms/batch wall", flush=True)
+for depth in (1, 2, 3, 4, 6):
+    pd = InferencePipeline(model, dev, depth=depth)
+    for out in pd.map(host[i % 8] for i in range(24)):
+        pass
+    torch.cuda.synchronize()
+    best = 1e9
+    for rep in range(3):
+        t0 = time.perf_counter()
+        for out in pd.map(host[i % 8] for i in range(200)):
+            pass
+        torch.cuda.synchronize()
+        best = min(best, 1e3 * (time.perf_counter() - t0) / 200)
+    print(f"depth {depth}: {best:.4f} ms/batch wall = {128e3 / best:.0f} molecules/s", flush=True)
 pr = cProfile.Profile()
 pr.enable()
 run(200)
