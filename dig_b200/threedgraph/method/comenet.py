@@ -174,7 +174,16 @@ class ComENet(nn.Module):
     def invalidate_packed(self):
         self.__dict__.pop("_filter_cache", None)
         self.__dict__.pop("_cat_cache", None)
+        self.__dict__.pop("_plan", None)
+        self.__dict__.pop("_plan_params", None)
         ops.invalidate_packed()
+
+    def __getstate__(self):
+        # caches hold device addresses / packed copies: rebuilt on demand, never copied or pickled
+        state = self.__dict__.copy()
+        for k in ("_filter_cache", "_cat_cache", "_plan", "_plan_params"):
+            state.pop(k, None)
+        return state
 
     def load_state_dict(self, *args, **kw):
         out = super().load_state_dict(*args, **kw)
@@ -197,6 +206,8 @@ class ComENet(nn.Module):
         if dense not in ("h16", "simt"):
             raise ValueError(f"DIG3D_COMENET_DENSE={dense!r}: expected h16 or simt")
         if dense == "h16":
+            if os.environ.get("DIG3D_LEAN", "1") != "0" and g.n_nodes and g.n_edges:
+                return self._forward_lean(self._inference_plan(), z, g, f1, f2)
             return self._forward_h16(z, g, f1, f2)
         x = ops.comenet_embed(z, self.emb.emb.weight)
         no_head = ops.pack_comenet_head([], None)
@@ -262,6 +273,112 @@ class ComENet(nn.Module):
             x = lin(x, l.weight, l.bias, want_act=True, act_only=True)
         x = ops.linear(x, self.lin_out.weight.detach(), self.lin_out.bias.detach())
         return ops.segment_sum(x, g.graph_ptr)
+
+    # ------------------------------------------------------------------ lean inference path (host overhead)
+    # `_forward_h16` is 77 launches of ~20 us kernels behind ~18 us of Python each (module attribute walks, packed-weight
+    # registry look-ups, one or two allocations and six pointer validations per linear): host-bound.  As for the DimeNet
+    # family everything that depends only on the parameters is resolved once into a plan -- per linear
+    # (packed weight address, bias address, K, N) -- and a forward is the same launch sequence over 256-wide slots of one
+    # workspace with raw addresses.  Bit-identical to `_forward_h16` (DIG3D_LEAN=0;
+    # tests/test_gpu_parity.py::test_comenet_lean_inference_path_is_bit_identical).
+    def _inference_plan(self):
+        params = self.__dict__.get("_plan_params")
+        if params is None:
+            params = self.__dict__["_plan_params"] = list(self.parameters())
+        key = (ops._PACK_GENERATION[0], sum(p._version for p in params), tuple(p.data_ptr() for p in params))
+        plan = self.__dict__.get("_plan")
+        if plan is not None and plan["key"] == key:
+            return plan
+        keep = []                                   # tensors the addresses below point into
+
+        def lin(weight, bias):
+            packed = ops._h16_packed(weight, False)          # the registry entry `ops.linear_h16` uses for this tensor
+            keep.extend((weight, packed, bias))
+            return (packed.data_ptr(), bias.data_ptr() if bias is not None else None, weight.size(1), weight.size(0))
+
+        def raw(t):
+            t = t.detach().contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        blocks = []
+        for blk in self.interaction_blocks:
+            wa, wb = self._cat_halves(blk)
+            convs = []
+            for conv, lf, l in ((blk.conv1, blk.lin_feature1, blk.lin1), (blk.conv2, blk.lin_feature2, blk.lin2)):
+                ft = self._filter_t(lf)
+                keep.append(ft)
+                convs.append({"filt": ft.data_ptr(), "q": ft.size(0), "root": lin(conv.lin_root.weight, None),
+                              "rel": lin(conv.lin_rel.weight, conv.lin_rel.bias), "l": lin(l.weight, l.bias)})
+            blocks.append({"lin": lin(blk.lin.weight, blk.lin.bias), "convs": convs, "wa": lin(wa, blk.lin_cat.bias),
+                           "wb": lin(wb, None), "lins": [lin(l.weight, l.bias) for l in blk.lins],
+                           "norm": (raw(blk.norm.weight), raw(blk.norm.bias), raw(blk.norm.mean_scale), float(blk.norm.eps)),
+                           "final": lin(blk.final.weight, blk.final.bias)})
+        plan = {"key": key, "keep": keep, "emb": raw(self.emb.emb.weight), "blocks": blocks,
+                "head": [lin(l.weight, l.bias) for l in self.lins],
+                "out": (raw(self.lin_out.weight), raw(self.lin_out.bias) if self.lin_out.bias is not None else None)}
+        self.__dict__["_plan"] = plan
+        return plan
+
+    def _forward_lean(self, plan, z, g, f1, f2):
+        call = ops.call
+        n, hdim, dev = g.n_nodes, self.emb.emb.weight.size(1), z.device
+        ng, oc = g.n_graphs, self.out_channels
+        slot_f = (n * hdim + 63) & ~63
+        n_slots = 8
+        ws = torch.empty(n_slots * slot_f + 2 * ng * hdim + n * oc + 256, dtype=torch.float32, device=dev)
+        base = (ws.data_ptr() + 255) & ~255
+        free = [base + 4 * slot_f * i for i in range(n_slots)]
+        shift = base + 4 * slot_f * n_slots
+        std = shift + 4 * ng * hdim
+        y_out = (std + 4 * ng * hdim + 255) & ~255
+        st = ops._stream()
+        f1p, f2p = f1.data_ptr(), f2.data_ptr()
+        src, row_ptr, graph_ptr = g.src.data_ptr(), g.row_ptr.data_ptr(), g.graph_ptr.data_ptr()
+
+        def lin(x, w, want_act=False, residual=None):
+            """One dig3d_linear_h16 into a fresh slot: swish(x W^T + b) (+ residual) with want_act, else x W^T + b (+ residual)."""
+            out = free.pop()
+            call("dig3d_linear_h16", x, n, w[2], w[3], w[0], w[1], None if want_act else out, out if want_act else None,
+                 residual, st)
+            return out
+
+        x = free.pop()
+        call("dig3d_comenet_embed", ops._p(z, torch.int64, "z"), plan["emb"], n, x, st)
+        for blk in plan["blocks"]:
+            x1 = lin(x, blk["lin"], want_act=True)
+            free.append(x)
+            hs = []
+            for conv, feat in zip(blk["convs"], (f1p, f2p)):
+                agg = free.pop()
+                call("dig3d_comenet_filter_sum", feat, conv["q"], conv["filt"], x1, src, row_ptr, n, hdim, agg, st)
+                root = lin(x1, conv["root"])
+                h = lin(agg, conv["rel"], residual=root)           # GraphConv: lin_rel(agg) + lin_root(x)
+                free += [agg, root]
+                hs.append(lin(h, conv["l"], want_act=True))
+                free.append(h)
+            t = lin(hs[1], blk["wb"], residual=x1)                 # lin_cat(cat[h1, h2]) + x = h1 Wa^T + b + (h2 Wb^T + x)
+            h = lin(hs[0], blk["wa"], residual=t)
+            free += [hs[0], hs[1], t, x1]
+            for w in blk["lins"]:
+                h2 = lin(h, w, want_act=True, residual=h)          # swish(l(h)) + h
+                free.append(h)
+                h = h2
+            nw, nb_, nms, eps = blk["norm"]
+            hn = free.pop()
+            call("dig3d_graphnorm", h, graph_ptr, ng, hdim, nw, nb_, nms, eps, hn, shift, std, st)
+            free.append(h)
+            x = lin(hn, blk["final"])
+            free.append(hn)
+        for w in plan["head"]:
+            x2 = lin(x, w, want_act=True)
+            free.append(x)
+            x = x2
+        call("dig3d_linear", x, n, hdim, oc, plan["out"][0], plan["out"][1], y_out, None, 1, st)
+        u = torch.empty(ng, oc, dtype=torch.float32, device=dev)
+        if ng:
+            call("dig3d_segment_sum", y_out, graph_ptr, ng, oc, u.data_ptr(), st)
+        return u
 
     def _forward_train(self, z, g, f1, f2):
         """Differentiable forward (reference comenet.py:386-399 and SimpleInteractionBlock.forward :195-215, op for op)

@@ -177,6 +177,36 @@ def test_lean_inference_path_is_bit_identical(cls_name, monkeypatch):
         assert torch.equal(clone(b), u0)
 
 
+def test_comenet_lean_inference_path_is_bit_identical(monkeypatch):
+    """ComENet's engine forward from the cached plan (one workspace, raw addresses) vs the op-by-op `_forward_h16`
+    (DIG3D_LEAN=0): same launches, bit-identical energies; the plan follows parameter updates."""
+    from dig_b200.data import synthetic_batch
+    from dig_b200.threedgraph.method import ComENet
+    dev = torch.device("cuda:0")
+    model = ComENet(cutoff=6.0)
+    model.load_state_dict(formula_state_dict(model.state_dict(), seed=5))
+    model = model.to(dev).eval()
+    b = synthetic_batch(5, "oc20-is2re", seed=3).to(dev)
+
+    def both():
+        with torch.no_grad():
+            monkeypatch.setenv("DIG3D_LEAN", "1")
+            lean, lean2 = model(b), model(b)
+            monkeypatch.setenv("DIG3D_LEAN", "0")
+            general = model(b)
+        assert "_plan" in model.__dict__ and torch.isfinite(lean).all()
+        assert torch.equal(lean, general) and torch.equal(lean, lean2)
+        return lean
+
+    u0 = both()
+    with torch.no_grad():
+        model.interaction_blocks[1].lin_cat.weight.mul_(1.25)
+    u1 = both()
+    assert not torch.equal(u0, u1)
+    model.load_state_dict(formula_state_dict(model.state_dict(), seed=5))
+    assert torch.equal(both(), u0)
+
+
 def test_segment_sum_against_index_add():
     from dig_b200 import ops
     torch.manual_seed(0)
