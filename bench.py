@@ -554,6 +554,9 @@ def main():
         # chain B: lin_up + 7 (128x128) linears; reads m, x_ji, e1_in, rbf0, dst; writes e1_out, v_in
         "dig3d_sphere_update_e_b_h16": (E * (2 * I * H + 7 * 2 * H * H), 4 * (E * (I + 3 * H + 6 + 1) + N * H), "tensor"),
         "dig3d_sphere_update_e_b_tc": (E * (2 * I * H + 7 * 2 * H * H), 4 * (E * (I + 3 * H + 6 + 1) + N * H), "tensor"),
+        # chain B of block l + part A of block l + 1 in one launch (e1 stays on chip between them)
+        "dig3d_sphere_update_e_ba_h16": (E * (2 * I * H + 7 * 2 * H * H) + E * (2 * 2 * H * H + 2 * H * I),
+                                         4 * (E * (I + 3 * H + 6 + 1) + N * H) + 4 * E * (H + I), "tensor"),
         "dig3d_sphere_update_e_a_h16": (E * (2 * 2 * H * H + 2 * H * I), 4 * E * (H + H + I + 6), "tensor"),
         "dig3d_sphere_update_e_a_tc": (E * (2 * 2 * H * H + 2 * H * I), 4 * E * (H + H + I + 6), "tensor"),
         "dig3d_sphere_init_e_h16": (E * 2 * 3 * H * H, 4 * (E * (H + 6 + 2) + N * H), "tensor"),

@@ -57,6 +57,8 @@ struct HSmem {
   float bias[8][128];
   float wr[128 * 8];
   float wr1[64];
+  float wr2[128 * 8];                              // fused B + A(next block): lin_rbf2 of the NEXT block (wr is still lin_rbf of this one for the other tile)
+  float bias2[2][128];                             //                          b_ji (x 1), b_kj (x H_SA) of the next block
   int dst[2][H_M];
   int aux[2][2][H_M];                              // init_e: atomic numbers of the target / source node of each row
   // d_ready / d_free are indexed [tile][accumulator]: each barrier has ONE waiter that sees every phase in order
@@ -435,11 +437,18 @@ __global__ void h16_pack_kernel(HPackJobs jobs) {
 
 // ---------------------------------------------------------------------------------- update_e part B
 struct HBParams {
-  HGemm g[8];                  // lin_up, res0.lin1, res0.lin2, lin, res1.lin1, res1.lin2, res2.lin1, res2.lin2
+  HGemm g[11];                 // lin_up, res0.lin1, res0.lin2, lin, res1.lin1, res1.lin2, res2.lin1, res2.lin2
+                               // FUSE: + lin_ji, lin_kj, lin_down of the NEXT block
   const float* w_rbf;          // [128, 6]
+  const float *n_w_rbf1, *n_w_rbf2;     // FUSE: lin_rbf1 [8, 6], lin_rbf2 [128, 8] of the next block
+  float *n_x_ji, *n_x_down;             // FUSE: part-A outputs of the next block
 };
 
-template <bool FAST>
+// FUSE: part A of the NEXT interaction block (x_ji = act(lin_ji(e1)), x_kj = act(lin_kj(e1)) * gate,
+// x_down = act(lin_down(x_kj)); spherenet.py:154-161) is appended to this block's chain: its operand is the e1 tile
+// this kernel has just produced, so the three extra jobs continue on the same tiles -- one launch, one set-up and
+// one e1 read less per block (part A alone is 34 us for 2.5 layers, two thirds of it set-up and tail).
+template <bool FAST, bool FUSE>
 __global__ void __launch_bounds__(H_THREADS, 1)
 sphere_update_e_b_h16_kernel(const float* __restrict__ m, const float* __restrict__ x_ji,
                              const float* __restrict__ e1_in, const float* __restrict__ rbf0,
@@ -466,16 +475,23 @@ sphere_update_e_b_h16_kernel(const float* __restrict__ m, const float* __restric
     const int e = (tile0 + i / H_M) * H_M + i % H_M;
     s.dst[i / H_M][i % H_M] = (e < n_edges) ? dst[e] : -1;
   }
+  if (FUSE) {
+    for (int i = tid; i < 2 * 128; i += H_THREADS)     // lin_ji's output leaves unscaled, lin_kj's feeds an operand (x H_SA)
+      s.bias2[i / 128][i % 128] = (i / 128 ? H_SA : 1.0f) * __ldg(P.g[8 + i / 128].bias + i % 128);
+    for (int i = tid; i < 128 * 8; i += H_THREADS) s.wr2[i] = __ldg(P.n_w_rbf2 + i);      // [128][8]
+    for (int i = tid; i < 64; i += H_THREADS) s.wr1[i] = (i % 8 < 6) ? __ldg(P.n_w_rbf1 + (i / 8) * 6 + i % 8) : 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   if (tid == 0 && g_h16_trace_on && blockIdx.x == 0) g_h16_trace[104] = clock64();
   HCtx c;
   bool epi = false;
+  constexpr int NG = FUSE ? 11 : 8;
   if (warp < H_CTRL_WARPS) {
     h_regs_ctrl();
-    if (tid == 0) h_producer(s, P.g, ntile);
-    else if (tid == 32) h_mma<8, true>(s, P.g, ntile, s.tmem_base);
+    if (tid == 0) h_producer_n(s, P.g, NG, ntile);
+    else if (tid == 32) h_mma_n<true, false>(s, P.g, NG, ntile, s.tmem_base);
   } else if (h_regs_epi(), (c = h_ctx(s, ntile)).t < ntile) {
     epi = true;
     constexpr bool TRACE = true;
@@ -589,6 +605,73 @@ sphere_update_e_b_h16_kernel(const float* __restrict__ m, const float* __restric
     h_tile_bar(c.t);
     h_store_tile_coalesced<128>(s, c, col0, acc_final, e1_out + (size_t)e0 * 128, rows);
     if (probe) H_TRACE(96 + c.t);
+    if (FUSE) {
+      // ---- part A of the next block on the e1 tile still in this thread's registers
+      h_tile_bar(c.t);                               // every thread of the tile has read the staging overlay
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        float v16[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v16[i] = acc_final[16 * p + i] * H_SA;
+        h_store_a16(s, c, col0 + 16 * p, v16);
+      }
+      float r8[8];                                   // gate coefficients of this row: lin_rbf1(rbf0[row])   spherenet.py:157
+      {
+        float rb[6];
+#pragma unroll
+        for (int n = 0; n < 6; ++n) rb[n] = valid ? __ldg(rbf0 + ge * 6 + n) : 0.f;
+#pragma unroll
+        for (int mm = 0; mm < 8; ++mm) {
+          float a = 0.f;
+#pragma unroll
+          for (int n = 0; n < 6; ++n) a = fmaf(s.wr1[mm * 8 + n], rb[n], a);
+          r8[mm] = a;
+        }
+      }
+      h_epi_done(s, c.t);
+      float (&acc)[64] = acc_final;
+      // G0: x_ji = act(lin_ji(e1))                                                spherenet.py:154
+      h_drain<4, true>(s, c, col0, 2, acc);
+      h_epi_done(s, c.t);   // the operand (= e1) is reused unchanged by lin_kj
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < 64; i += 4) {
+          const float4 b = *reinterpret_cast<const float4*>(&s.bias2[0][col0 + i]);
+          float4 o;
+          o.x = hswish<FAST>(fmaf(acc[i], H_INV, b.x));
+          o.y = hswish<FAST>(fmaf(acc[i + 1], H_INV, b.y));
+          o.z = hswish<FAST>(fmaf(acc[i + 2], H_INV, b.z));
+          o.w = hswish<FAST>(fmaf(acc[i + 3], H_INV, b.w));
+          *reinterpret_cast<float4*>(P.n_x_ji + ge * 128 + col0 + i) = o;
+        }
+      }
+      // G1: x_kj = act(lin_kj(e1)) * lin_rbf2(r8)                                 spherenet.py:155-159
+      h_drain<4, true>(s, c, col0, 2, acc);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int col = col0 + 16 * p + i;
+          const float4 w0 = *reinterpret_cast<const float4*>(s.wr2 + col * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(s.wr2 + col * 8 + 4);
+          const float gate = fmaf(w1.w, r8[7], fmaf(w1.z, r8[6], fmaf(w1.y, r8[5], fmaf(w1.x, r8[4],
+                             fmaf(w0.w, r8[3], fmaf(w0.z, r8[2], fmaf(w0.y, r8[1], w0.x * r8[0])))))));
+          v[i] = hswish8<FAST>(fmaf(acc[16 * p + i], H_SA * H_INV, s.bias2[1][col])) * gate;
+        }
+        h_store_a16(s, c, col0 + 16 * p, v);
+      }
+      h_epi_done(s, c.t);
+      // G2: x_down = act(lin_down(x_kj)), N = 64                                  spherenet.py:161
+      {
+        const int col = c.half * 32;
+        float a32[32];
+        h_drain<2, true>(s, c, col, 2, a32);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) a32[i] = hswish<FAST>(a32[i] * H_INV);
+        h_store_tile_coalesced<64>(s, c, col, a32, P.n_x_down + (size_t)e0 * 64, rows);   // all MMAs of the tile are done
+      }
+    }
   }
   h_finish(s, epi ? &c : nullptr);
   if (tid == 0 && g_h16_trace_on && blockIdx.x == 0) { g_h16_trace[102] = clock64(); g_h16_trace[103] = (long long)global_ns(); }
@@ -1377,7 +1460,37 @@ int dig3d_sphere_update_e_b_h16(const float* m, const float* e1_in, const float*
   P.g[3] = {(const unsigned char*)w->p_lin, w->b_lin, 128, 128};
   for (int i = 2; i < 6; ++i) P.g[2 + i] = {(const unsigned char*)w->p_res[i], w->b_res[i], 128, 128};
   P.w_rbf = w->w_rbf;
-  auto kfn = h16_fast_swish ? sphere_update_e_b_h16_kernel<true> : sphere_update_e_b_h16_kernel<false>;
+  P.n_w_rbf1 = P.n_w_rbf2 = nullptr; P.n_x_ji = P.n_x_down = nullptr;
+  auto kfn = h16_fast_swish ? sphere_update_e_b_h16_kernel<true, false> : sphere_update_e_b_h16_kernel<false, false>;
+  int rc = h_smem_attr((const void*)kfn);
+  if (rc) return rc;
+  const int pairs = ceil_div(ceil_div(n_edges, H_M), 2);
+  kfn<<<pairs, H_THREADS, sizeof(HSmem), (cudaStream_t)stream>>>(m, x_ji, e1_in, rbf0, dst, (int)n_edges, P, e1_out,
+                                                                 v_in);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_sphere_update_e_ba_h16(const float* m, const float* e1_in, const float* x_ji, const float* rbf0,
+                                 const int32_t* dst, int64_t n_edges, const dig3d_tc_update_e* w,
+                                 const dig3d_tc_update_e* w_next, float* e1_out, float* v_in, float* x_ji_next,
+                                 float* x_down_next, void* stream) {
+  DIG3D_REQUIRE(m && e1_in && x_ji && rbf0 && dst && w && w_next && e1_out && v_in && x_ji_next && x_down_next,
+                "sphere_update_e_ba_h16: null pointer");
+  DIG3D_REQUIRE(x_ji_next != x_ji, "sphere_update_e_ba_h16: x_ji_next must not alias x_ji (other tiles still read it)");
+  if (n_edges == 0) return DIG3D_OK;
+  HBParams P;
+  P.g[0] = {(const unsigned char*)w->p_up, nullptr, 64, 128};
+  for (int i = 0; i < 2; ++i) P.g[1 + i] = {(const unsigned char*)w->p_res[i], w->b_res[i], 128, 128};
+  P.g[3] = {(const unsigned char*)w->p_lin, w->b_lin, 128, 128};
+  for (int i = 2; i < 6; ++i) P.g[2 + i] = {(const unsigned char*)w->p_res[i], w->b_res[i], 128, 128};
+  P.g[8] = {(const unsigned char*)w_next->p_ji, w_next->b_ji, 128, 128};
+  P.g[9] = {(const unsigned char*)w_next->p_kj, w_next->b_kj, 128, 128};
+  P.g[10] = {(const unsigned char*)w_next->p_down, nullptr, 128, 64};
+  P.w_rbf = w->w_rbf;
+  P.n_w_rbf1 = w_next->w_rbf1; P.n_w_rbf2 = w_next->w_rbf2;
+  P.n_x_ji = x_ji_next; P.n_x_down = x_down_next;
+  auto kfn = h16_fast_swish ? sphere_update_e_b_h16_kernel<true, true> : sphere_update_e_b_h16_kernel<false, true>;
   int rc = h_smem_attr((const void*)kfn);
   if (rc) return rc;
   const int pairs = ceil_div(ceil_div(n_edges, H_M), 2);

@@ -382,7 +382,7 @@ class _DimeNetFamily(nn.Module):
         # one workspace (floats), every buffer on a 256-byte boundary
         sizes = (("angle", T), ("torsion", T if tors else 0), ("rbf0", E * self.num_radial), ("bess", E * nb_s),
                  ("sbf_p", 32 * T), ("t_p", 32 * T if tors else 0), ("e1a", E * H), ("e1b", E * H), ("x_ji", E * H),
-                 ("x_down", E * I), ("m", E * I), ("v_all", (L + 1) * N * O))
+                 ("x_ji2", E * H), ("x_down", E * I), ("m", E * I), ("v_all", (L + 1) * N * O))
         off, total = {}, 0
         for name, n in sizes:
             off[name] = total
@@ -407,15 +407,25 @@ class _DimeNetFamily(nn.Module):
                  plan["w_t"].data_ptr() if tors else None, a["sbf_p"], a["t_p"] if tors else None, *ops._out_lists(g), st)
         call("dig3d_sphere_init_e_h16", ops._p(z, torch.int64, "z"), src, dst, a["rbf0"], E, byref(plan["init_w"]),
              plan["init_packed"].data_ptr(), a["e1a"], v_in, st)
+        # Part A of block l + 1 rides on the tile chain of part B of block l (dig3d_sphere_update_e_ba_h16): two launches per
+        # interaction block (gather, dense chain) instead of three; DIG3D_FUSE_BA=0 keeps them apart (same results).
+        fuse = os.environ.get("DIG3D_FUSE_BA", "1") != "0"
         e1, e1_next = a["e1a"], a["e1b"]
+        x_ji, x_ji_next = a["x_ji"], a["x_ji2"]
         for l in range(L):
             w = plan["layers"][l]
-            call("dig3d_sphere_update_e_a_h16", e1, a["rbf0"], E, byref(w), a["x_ji"], a["x_down"], st)
+            if l == 0 or not fuse:
+                call("dig3d_sphere_update_e_a_h16", e1, a["rbf0"], E, byref(w), x_ji, a["x_down"], st)
             sp = ctypes.c_void_p(a["sbf_p"] + 4 * 8 * T * l)
             tp = ctypes.c_void_p(a["t_p"] + 4 * 8 * T * l) if tors else None
             ops.triplet_gather(a["x_down"], sp, tp, g, w.w_sbf2, w.w_t2, a["m"], st)
-            call("dig3d_sphere_update_e_b_h16", a["m"], e1, a["x_ji"], a["rbf0"], dst, E, byref(w), e1_next,
-                 v_in + 4 * (l + 1) * N * H, st)
+            if fuse and l + 1 < L:        # x_down is free again: the gather that read it has completed (stream order)
+                call("dig3d_sphere_update_e_ba_h16", a["m"], e1, x_ji, a["rbf0"], dst, E, byref(w),
+                     byref(plan["layers"][l + 1]), e1_next, v_in + 4 * (l + 1) * N * H, x_ji_next, a["x_down"], st)
+                x_ji, x_ji_next = x_ji_next, x_ji
+            else:
+                call("dig3d_sphere_update_e_b_h16", a["m"], e1, x_ji, a["rbf0"], dst, E, byref(w), e1_next,
+                     v_in + 4 * (l + 1) * N * H, st)
             e1, e1_next = e1_next, e1
         call("dig3d_sphere_update_v_h16", v_in, N, L + 1, int(O), plan["n_lins"], plan["parr"], plan["varr"], a["v_all"], st)
         u = torch.empty(g.n_graphs, O, dtype=torch.float32, device=dev)

@@ -312,6 +312,14 @@ int dig3d_sphere_update_e_a_h16(const float* e1, const float* rbf0, int64_t n_ed
 int dig3d_sphere_update_e_b_h16(const float* m, const float* e1_in, const float* x_ji, const float* rbf0,
                                 const int32_t* dst, int64_t n_edges, const dig3d_tc_update_e* w, float* e1_out,
                                 float* v_in, void* stream);
+/* dig3d_sphere_update_e_b_h16 of block l with part A of block l + 1 (dig3d_sphere_update_e_a_h16 on the e1 this kernel
+ * produces) appended to the same tile chain: one launch, one set-up and one read of e1 less per block; bit-identical to
+ * the two separate launches.  w_next: the next block's weights; x_ji_next [E, 128] (must not alias x_ji), x_down_next
+ * [E, 64]: its part-A outputs.                                                  spherenet.py:150-182 */
+int dig3d_sphere_update_e_ba_h16(const float* m, const float* e1_in, const float* x_ji, const float* rbf0,
+                                 const int32_t* dst, int64_t n_edges, const dig3d_tc_update_e* w,
+                                 const dig3d_tc_update_e* w_next, float* e1_out, float* v_in, float* x_ji_next,
+                                 float* x_down_next, void* stream);
 /* update_v.forward after the scatter (spherenet.py:212-215) for ALL blocks of a forward on the same engine (one
  * 128-node tile per CTA, the two 128-column halves of every 256-wide layer in flight); H = 128, O = 256,
  * out_channels <= 4.  packed[b * (n_lins + 1) + l] = dig3d_h16_pack of block b's lin_up (l = 0) / lins[l - 1]

@@ -151,12 +151,15 @@ def test_lean_inference_path_is_bit_identical(cls_name, monkeypatch):
     def both():
         with torch.no_grad():
             monkeypatch.setenv("DIG3D_LEAN", "1")
-            lean = model(b)
+            monkeypatch.setenv("DIG3D_FUSE_BA", "1")
+            lean = model(b)                       # part A of block l + 1 fused into the chain of part B of block l
             lean2 = model(b)                      # second call: the cached plan
+            monkeypatch.setenv("DIG3D_FUSE_BA", "0")
+            apart = model(b)
             monkeypatch.setenv("DIG3D_LEAN", "0")
             general = model(b)
         assert "_plan" in model.__dict__
-        assert torch.equal(lean, general) and torch.equal(lean, lean2)
+        assert torch.equal(lean, general) and torch.equal(lean, lean2) and torch.equal(lean, apart)
         return lean
 
     u0 = both()
