@@ -102,6 +102,7 @@ SIGNATURES = {
     "dig3d_h16_packed_bytes": [c_int32, c_int32],
     "dig3d_h16_pack": [P, P, P, P, c_int32, P],
     "dig3d_sphere_init_e_h16": [P, P, P, P, c_int64, POINTER(InitEWeights), P, P, P, P],
+    "dig3d_sphere_init_e_h16_tab": [P, P, P, P, c_int64, POINTER(InitEWeights), P, P, P, P, P, P],
     "dig3d_sphere_update_e_a_h16": [P, P, c_int64, POINTER(TcUpdateE), P, P, P],
     "dig3d_sphere_update_e_b_h16": [P, P, P, P, P, c_int64, POINTER(TcUpdateE), P, P, P],
     "dig3d_sphere_update_e_ba_h16": [P, P, P, P, P, c_int64, POINTER(TcUpdateE), POINTER(TcUpdateE), P, P, P, P, P],

@@ -782,9 +782,14 @@ sphere_update_e_a_h16_kernel(const float* __restrict__ e1, const float* __restri
 struct HInitParams {
   HGemm g[3];
   const float *emb, *w_rbf0, *b_rbf0, *b_lin, *w_rbf1;
+  const float *tab_i, *tab_j;   // TABLE: [emb rows, 128] = emb W[:, 0:128]^T and emb W[:, 128:256]^T
 };
 
-template <bool FAST>
+// TABLE: lin(cat[x_i, x_j, rbf0]) = W_i emb[z_i] + W_j emb[z_j] + W_r rbf0 + b, and the first two terms depend on the
+// ATOMIC NUMBER only: they are two [emb rows, 128] tables computed once per parameter version in exact fp32
+// (ops.init_e_tables), gathered into the TMEM stash while the single remaining K = 128 panel (the rbf part) runs, and
+// added in the final epilogue -- one job per tile instead of three (a job of the two-tile chain is ~10 us, §4.5).
+template <bool FAST, bool TABLE>
 __global__ void __launch_bounds__(H_THREADS, 1)
 sphere_init_e_h16_kernel(const int64_t* __restrict__ z, const int32_t* __restrict__ src,
                          const int32_t* __restrict__ dst, const float* __restrict__ rbf0, int n_edges, HInitParams P,
@@ -812,14 +817,15 @@ sphere_init_e_h16_kernel(const int64_t* __restrict__ z, const int32_t* __restric
   bool epi = false;
   if (warp < H_CTRL_WARPS) {
     h_regs_ctrl();
-    if (tid == 0) h_producer(s, P.g, ntile);
-    else if (tid == 32) h_mma(s, P.g, ntile, s.tmem_base);
+    if (tid == 0) h_producer_n(s, P.g, TABLE ? 1 : 3, ntile);
+    else if (tid == 32) h_mma_n<false, false>(s, P.g, TABLE ? 1 : 3, ntile, s.tmem_base);
   } else if (h_regs_epi(), (c = h_ctx(s, ntile)).t < ntile) {
     epi = true;
     const int e0 = (tile0 + c.t) * H_M, rows = min(H_M, n_edges - e0);
     const bool valid = c.row < rows;
     const size_t ge = (size_t)(e0 + c.row);
     const int col0 = c.half * 64;
+    const uint32_t stash = c.tl + 256u + 128u * c.t + col0;      // TABLE: the row's table sums wait here
     float rb[6];
 #pragma unroll
     for (int n = 0; n < 6; ++n) rb[n] = valid ? __ldg(rbf0 + ge * 6 + n) : 0.f;
@@ -842,12 +848,14 @@ sphere_init_e_h16_kernel(const int64_t* __restrict__ z, const int32_t* __restric
       }
     };
     float acc[64];
-    fill_embedding(s.aux[c.t][0]);                  // panel 0: x_i
-    h_epi_done(s, c.t);
-    h_drain<4, true>(s, c, col0, 2, acc);
-    fill_embedding(s.aux[c.t][1]);                  // panel 1: x_j
-    h_epi_done(s, c.t);
-    h_drain<4, false>(s, c, col0, 2, acc);
+    if (!TABLE) {
+      fill_embedding(s.aux[c.t][0]);                  // panel 0: x_i
+      h_epi_done(s, c.t);
+      h_drain<4, true>(s, c, col0, 2, acc);
+      fill_embedding(s.aux[c.t][1]);                  // panel 1: x_j
+      h_epi_done(s, c.t);
+      h_drain<4, false>(s, c, col0, 2, acc);
+    }
 #pragma unroll
     for (int p = 0; p < 4; ++p) {                   // panel 2: act(lin_rbf_0(rbf))        spherenet.py:87
       float v[16];
@@ -862,7 +870,35 @@ sphere_init_e_h16_kernel(const int64_t* __restrict__ z, const int32_t* __restric
       h_store_a16(s, c, col0 + 16 * p, v);
     }
     h_epi_done(s, c.t);
-    h_drain<4, false>(s, c, col0, 2, acc);
+    if (TABLE) {
+      // W_i emb[z_i] + W_j emb[z_j] of this row (L2-resident tables) -> stash, under the panel's MMAs
+      const float* ti = P.tab_i + (size_t)s.aux[c.t][0][c.row] * 128 + col0;
+      const float* tj = P.tab_j + (size_t)s.aux[c.t][1][c.row] * 128 + col0;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        uint32_t r[16];
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(ti + 16 * p + i));
+          const float4 b = __ldg(reinterpret_cast<const float4*>(tj + 16 * p + i));
+          r[i] = __float_as_uint(a.x + b.x); r[i + 1] = __float_as_uint(a.y + b.y);
+          r[i + 2] = __float_as_uint(a.z + b.z); r[i + 3] = __float_as_uint(a.w + b.w);
+        }
+        tmem_st16(stash + 16 * p, r);
+      }
+      tmem_st_wait();
+      h_drain<4, true>(s, c, col0, 2, acc);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        uint32_t r[16];
+        tmem_ld16(stash + 16 * p, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[16 * p + i] = fmaf(acc[16 * p + i], H_INV, __uint_as_float(r[i])) * (H_SA * H_SW);
+      }
+    } else {
+      h_drain<4, false>(s, c, col0, 2, acc);
+    }
     // e1 = act(. + b), e2 = lin_rbf_1(rbf) * e1 (tile staged over the planes), edge -> node sums, coalesced e1 store
     float* e2t = reinterpret_cast<float*>(s.a[c.t][0]);
 #pragma unroll
@@ -1422,7 +1458,30 @@ int dig3d_sphere_init_e_h16(const int64_t* z, const int32_t* src, const int32_t*
   const size_t panel = (size_t)4 * 2 * 4 * 128 * 16;   // four K=32 slabs
   for (int p = 0; p < 3; ++p) P.g[p] = {(const unsigned char*)packed_lin + p * panel, nullptr, 128, 128};
   P.emb = w->emb; P.w_rbf0 = w->w_rbf0; P.b_rbf0 = w->b_rbf0; P.b_lin = w->b_lin; P.w_rbf1 = w->w_rbf1;
-  auto kfn = h16_fast_swish ? sphere_init_e_h16_kernel<true> : sphere_init_e_h16_kernel<false>;
+  P.tab_i = P.tab_j = nullptr;
+  auto kfn = h16_fast_swish ? sphere_init_e_h16_kernel<true, false> : sphere_init_e_h16_kernel<false, false>;
+  int rc = h_smem_attr((const void*)kfn);
+  if (rc) return rc;
+  const int pairs = ceil_div(ceil_div(n_edges, H_M), 2);
+  kfn<<<pairs, H_THREADS, sizeof(HSmem), (cudaStream_t)stream>>>(z, src, dst, rbf0, (int)n_edges, P, e1, v_in);
+  DIG3D_LAUNCH_CHECK();
+  return DIG3D_OK;
+}
+
+int dig3d_sphere_init_e_h16_tab(const int64_t* z, const int32_t* src, const int32_t* dst, const float* rbf0,
+                                int64_t n_edges, const dig3d_init_e_weights* w, const void* packed_rbf_panel,
+                                const float* tab_i, const float* tab_j, float* e1, float* v_in, void* stream) {
+  DIG3D_REQUIRE(z && src && dst && rbf0 && w && packed_rbf_panel && tab_i && tab_j && e1 && v_in,
+                "sphere_init_e_h16_tab: null pointer");
+  DIG3D_REQUIRE(w->w_rbf0 && w->b_rbf0 && w->b_lin && w->w_rbf1, "sphere_init_e_h16_tab: null weight");
+  DIG3D_REQUIRE((((uintptr_t)tab_i | (uintptr_t)tab_j) & 15) == 0, "sphere_init_e_h16_tab: tables must be 16-byte aligned");
+  if (n_edges == 0) return DIG3D_OK;
+  HInitParams P;
+  P.g[0] = {(const unsigned char*)packed_rbf_panel, nullptr, 128, 128};
+  P.g[1] = P.g[2] = P.g[0];
+  P.emb = w->emb; P.w_rbf0 = w->w_rbf0; P.b_rbf0 = w->b_rbf0; P.b_lin = w->b_lin; P.w_rbf1 = w->w_rbf1;
+  P.tab_i = tab_i; P.tab_j = tab_j;
+  auto kfn = h16_fast_swish ? sphere_init_e_h16_kernel<true, true> : sphere_init_e_h16_kernel<false, true>;
   int rc = h_smem_attr((const void*)kfn);
   if (rc) return rc;
   const int pairs = ceil_div(ceil_div(n_edges, H_M), 2);

@@ -93,14 +93,14 @@ def build_graph(pos, batch, cutoff, num_graphs=None, max_num_neighbors=32, want_
     nbr = torch.empty(max(n, 1) * cap, dtype=torch.int32, device=dev)
     deg = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
     tcnt = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
-    totals = torch.zeros(4, dtype=torch.int32, device=dev)
+    zeroed = torch.zeros(4 + max(n, 1), dtype=torch.int32, device=dev)     # one fill: totals [4] + out-degree counters [n]
+    totals, out_cnt = zeroed[:4], zeroed[4:]
     if z is not None and z.shape != (n,):
         raise ValueError("z must be [N]")
     call("dig3d_validate_nodes", _p(batch), _p(z, torch.int64, "z"), n, g.n_graphs, int(z_rows),
          ctypes.c_void_p(totals.data_ptr() + 8), st)
     call("dig3d_radius_neighbors", _p(pos, torch.float32, "pos"), _p(batch), _p(g.graph_ptr), n, g.n_graphs,
          float(cutoff), cap, _p(nbr), _p(deg), st)
-    out_cnt = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
     call("dig3d_triplet_count_out", _p(nbr), _p(deg), n, cap, _p(tcnt), _p(out_cnt), st)
     g.row_ptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
     node_trip_ptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
@@ -117,7 +117,7 @@ def build_graph(pos, batch, cutoff, num_graphs=None, max_num_neighbors=32, want_
     g.src = torch.empty(max(e, 1), dtype=torch.int32, device=dev)[:e]
     g.dst = torch.empty(max(e, 1), dtype=torch.int32, device=dev)[:e]
     g.dist = torch.empty(max(e, 1), dtype=torch.float32, device=dev)[:e]
-    g.trip_ptr = torch.zeros(e + 1, dtype=torch.int32, device=dev)
+    g.trip_ptr = (torch.empty if e else torch.zeros)(e + 1, dtype=torch.int32, device=dev)   # edge_fill writes all e + 1 entries
     g.edge_index = torch.empty(2, e, dtype=torch.int64, device=dev) if want_edge_index else None
     g.vec = torch.empty(e, 3, dtype=torch.float32, device=dev) if want_vec else None
     g.out_list = torch.empty(max(e, 1), dtype=torch.int32, device=dev)[:e]
@@ -611,11 +611,34 @@ def triplet_gather(x_down, sp, tp, g, w_sbf2, w_t2, m_out, st):
              _p(g.trip_ptr), g.n_edges, w_sbf2, w_t2, _ptr(m_out), st)
 
 
-def sphere_init_e_h16(z, g, rbf0, w, packed_lin, hidden, v_in=None):
+def init_e_tables(init_e, cache):
+    """(tab_i, tab_j, packed rbf panel) of an init_e block for dig3d_sphere_init_e_h16_tab: the first two K = 128 panels of
+    lin(cat[x_i, x_j, rbf0]) only depend on the atomic number, so they become two [emb rows, 128] tables (exact fp32
+    FFMA GEMMs); the third panel is packed for the tensor engine.  Cached in `cache` per parameter version."""
+    w, emb = init_e.lin.weight, init_e.emb.weight
+    key = (_PACK_GENERATION[0], w.data_ptr(), w._version, emb.data_ptr(), emb._version)
+    hit = cache.get("init_e.tables")
+    if hit is None or hit[0] != key:
+        wd, ed = w.detach(), emb.detach().contiguous()
+        tab_i = linear(ed, wd[:, :128].contiguous())
+        tab_j = linear(ed, wd[:, 128:256].contiguous())
+        packed, _ = _pack_matrices([wd[:, 256:384].contiguous()], "h16")
+        hit = (key, tab_i, tab_j, packed)
+        cache["init_e.tables"] = hit
+    return hit[1], hit[2], hit[3]
+
+
+def sphere_init_e_h16(z, g, rbf0, w, packed_lin, hidden, v_in=None, tables=None):
+    """tables = init_e_tables(...): the table form (one K = 128 job per tile); else three K = 128 panels of packed_lin."""
     e1 = torch.empty(max(g.n_edges, 1), hidden, dtype=torch.float32, device=rbf0.device)[:g.n_edges]
     if v_in is None:
         v_in = torch.zeros(g.n_nodes, hidden, dtype=torch.float32, device=rbf0.device)
-    if g.n_edges:
+    if g.n_edges and tables is not None:
+        tab_i, tab_j, packed = tables
+        call("dig3d_sphere_init_e_h16_tab", _p(z, torch.int64, "z"), _p(g.src), _p(g.dst), _p(rbf0), g.n_edges,
+             ctypes.byref(w), _p(packed), _p(tab_i, torch.float32, "tab_i", 16), _p(tab_j, torch.float32, "tab_j", 16),
+             _p(e1), _p(v_in), _stream())
+    elif g.n_edges:
         call("dig3d_sphere_init_e_h16", _p(z, torch.int64, "z"), _p(g.src), _p(g.dst), _p(rbf0), g.n_edges,
              ctypes.byref(w), _p(packed_lin), _p(e1), _p(v_in), _stream())
     return e1, v_in

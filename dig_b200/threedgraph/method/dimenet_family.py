@@ -305,8 +305,10 @@ class _DimeNetFamily(nn.Module):
         tc_cache = self.__dict__.setdefault("_tc_cache", {})
         if dense == "h16":
             packed = ops.tc_pack_matrix(self.init_e.lin.weight, tc_cache, "init_e.lin", kind="h16")
+            tables = (ops.init_e_tables(self.init_e, tc_cache)
+                      if os.environ.get("DIG3D_INIT_TABLES", "1") != "0" and self.hidden_channels == 128 else None)
             e1, _ = ops.sphere_init_e_h16(z, g, rbf0, ops.pack_init_e(self.init_e), packed, self.hidden_channels,
-                                          v_in=v_in_all[0])
+                                          v_in=v_in_all[0], tables=tables)
         elif dense == "tc":
             packed = ops.tc_pack_matrix(self.init_e.lin.weight, tc_cache, "init_e.lin")
             e1, _ = ops.sphere_init_e_tc(z, g, rbf0, ops.pack_init_e(self.init_e), packed, self.hidden_channels,
@@ -348,7 +350,8 @@ class _DimeNetFamily(nn.Module):
         params = self.__dict__.get("_plan_params")
         if params is None:
             params = self.__dict__["_plan_params"] = list(self.parameters())
-        key = (ops._PACK_GENERATION[0], sum(p._version for p in params), tuple(p.data_ptr() for p in params))
+        key = (ops._PACK_GENERATION[0], sum(p._version for p in params), tuple(p.data_ptr() for p in params),
+               os.environ.get("DIG3D_INIT_TABLES", "1"))
         plan = self.__dict__.get("_plan")
         if plan is not None and plan["key"] == key:
             return plan
@@ -363,6 +366,8 @@ class _DimeNetFamily(nn.Module):
             "key": key,
             "init_w": ops.pack_init_e(self.init_e),
             "init_packed": ops.tc_pack_matrix(self.init_e.lin.weight, tc_cache, "init_e.lin", kind="h16"),
+            "init_tables": (ops.init_e_tables(self.init_e, tc_cache)
+                            if os.environ.get("DIG3D_INIT_TABLES", "1") != "0" and self.hidden_channels == 128 else None),
             "layers": [ops.tc_pack_update_e(self.update_es[l], self._torsion, tc_cache, kind="h16") for l in range(L)],
             "w_s": w_s, "w_t": w_t, "parr": parr, "varr": varr, "n_lins": n_lins,
             "freq": self.emb.dist_emb.freq.detach(),
@@ -405,8 +410,13 @@ class _DimeNetFamily(nn.Module):
             call("dig3d_triplet_basis_project_lists", a["bess"], a["angle"], a["torsion"] if tors else None, src, dst,
                  row_ptr, trip_ptr, graph_ptr, batch, E, T, int(self._basis_id), 4, 8, plan["w_s"].data_ptr(),
                  plan["w_t"].data_ptr() if tors else None, a["sbf_p"], a["t_p"] if tors else None, *ops._out_lists(g), st)
-        call("dig3d_sphere_init_e_h16", ops._p(z, torch.int64, "z"), src, dst, a["rbf0"], E, byref(plan["init_w"]),
-             plan["init_packed"].data_ptr(), a["e1a"], v_in, st)
+        if plan["init_tables"] is not None:
+            tab_i, tab_j, packed_rbf = plan["init_tables"]
+            call("dig3d_sphere_init_e_h16_tab", ops._p(z, torch.int64, "z"), src, dst, a["rbf0"], E, byref(plan["init_w"]),
+                 packed_rbf.data_ptr(), tab_i.data_ptr(), tab_j.data_ptr(), a["e1a"], v_in, st)
+        else:
+            call("dig3d_sphere_init_e_h16", ops._p(z, torch.int64, "z"), src, dst, a["rbf0"], E, byref(plan["init_w"]),
+                 plan["init_packed"].data_ptr(), a["e1a"], v_in, st)
         # Part A of block l + 1 rides on the tile chain of part B of block l (dig3d_sphere_update_e_ba_h16): two launches per
         # interaction block (gather, dense chain) instead of three; DIG3D_FUSE_BA=0 keeps them apart (same results).
         fuse = os.environ.get("DIG3D_FUSE_BA", "1") != "0"

@@ -307,6 +307,13 @@ int dig3d_h16_pack(const float* const* weights, const int32_t* n, const int32_t*
 int dig3d_sphere_init_e_h16(const int64_t* z, const int32_t* src, const int32_t* dst, const float* rbf0,
                             int64_t n_edges, const dig3d_init_e_weights* w, const void* packed_lin, float* e1,
                             float* v_in, void* stream);
+/* The same with the embedding panels folded into two tables: lin(cat[x_i, x_j, rbf0]) = tab_i[z_i] + tab_j[z_j] +
+ * W[:, 256:384] rbf0 + b, tab_i = emb W[:, 0:128]^T, tab_j = emb W[:, 128:256]^T ([emb rows, 128] fp32, computed once per
+ * parameter version with dig3d_linear); packed_rbf_panel: dig3d_h16_pack of W[:, 256:384].  One K = 128 job per tile
+ * instead of three.                                                          spherenet.py:86-90 */
+int dig3d_sphere_init_e_h16_tab(const int64_t* z, const int32_t* src, const int32_t* dst, const float* rbf0,
+                                int64_t n_edges, const dig3d_init_e_weights* w, const void* packed_rbf_panel,
+                                const float* tab_i, const float* tab_j, float* e1, float* v_in, void* stream);
 int dig3d_sphere_update_e_a_h16(const float* e1, const float* rbf0, int64_t n_edges, const dig3d_tc_update_e* w,
                                 float* x_ji, float* x_down, void* stream);
 int dig3d_sphere_update_e_b_h16(const float* m, const float* e1_in, const float* x_ji, const float* rbf0,

@@ -564,6 +564,11 @@ def test_two_tile_fp16_chain_matches_fp32_twin(cls_name):
         e1_t, v_t = ops.sphere_init_e_h16(b.z, g, rbf0, ops.pack_init_e(model.init_e), packed, 128)
         assert rel_err(e1_t.cpu().numpy(), e1_s.cpu().numpy()) < TOL, nmol
         assert rel_err(v_t.cpu().numpy(), v_s.cpu().numpy()) < TOL, nmol
+        # table form: the two embedding panels folded into per-atomic-number tables (one job per tile instead of three)
+        e1_b, v_b = ops.sphere_init_e_h16(b.z, g, rbf0, ops.pack_init_e(model.init_e), packed, 128,
+                                          tables=ops.init_e_tables(model.init_e, cache))
+        assert rel_err(e1_b.cpu().numpy(), e1_s.cpu().numpy()) < TOL, nmol
+        assert rel_err(v_b.cpu().numpy(), v_s.cpu().numpy()) < TOL, nmol
         ue = model.update_es[1]
         e_ref, v_ref = ops.sphere_update_e(e1_s, g, rbf0, sbf_p, t_p, 8, ops.pack_update_e(ue, tors), 128, 64)
         e_h, v_h, _, _ = ops.sphere_update_e_h16(e1_s, g, rbf0, sbf_p, t_p, 8,
