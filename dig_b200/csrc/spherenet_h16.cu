@@ -79,6 +79,7 @@ struct HGemm {
 
 static __device__ unsigned int g_h16_overflow = 0;
 static int h16_fast_swish = 1;
+static int h16_wide_epilogue = 0;   // update_e part B (+ A): 0 = eight epilogue warps per tile, 1 = all sixteen on the ready tile
 // optional timeline probe: CTA 0 of update_e part B records clock64() at protocol points (tools/gpu_h16_timeline.py)
 static __device__ long long g_h16_trace[128];
 static __device__ int g_h16_trace_on = 0;
@@ -327,12 +328,12 @@ __device__ __forceinline__ void h_drain(HSmem& s, HCtx& c, int col0, int chunks,
   }
   if (c.t == 0 && c.ntile == 2) c.ch += chunks;
 }
-__device__ __forceinline__ void h_setup(HSmem& s, int a_ready_warps = H_TILE_WARPS) {
+__device__ __forceinline__ void h_setup(HSmem& s, int a_ready_warps = H_TILE_WARPS, int d_free_warps = H_TILE_WARPS) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < H_STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s.a_ready[i], a_ready_warps);
-      for (int j = 0; j < 2; ++j) { mbar_init(&s.d_ready[i][j], 1); mbar_init(&s.d_free[i][j], H_TILE_WARPS); }
+      for (int j = 0; j < 2; ++j) { mbar_init(&s.d_ready[i][j], 1); mbar_init(&s.d_free[i][j], d_free_warps); }
     }
     mbar_init(&s.l_done, 1);
     mbar_fence_init();
@@ -675,6 +676,381 @@ sphere_update_e_b_h16_kernel(const float* __restrict__ m, const float* __restric
   }
   h_finish(s, epi ? &c : nullptr);
   if (tid == 0 && g_h16_trace_on && blockIdx.x == 0) { g_h16_trace[102] = clock64(); g_h16_trace[103] = (long long)global_ns(); }
+}
+
+// ---------------------------------------------------------------------------------- update_e part B (+ A), wide epilogue
+// Same chain, same jobs, same barriers as sphere_update_e_b_h16_kernel; the difference is WHO runs an epilogue.  There,
+// eight warps own a tile (64 columns per thread) and a tile's job cycle is its MMAs (~3.6 k cycles) PLUS its epilogue
+// (~5 k: 2 k of MUFU and 1.8 k of FP32 pipe per scheduler on two warps) -- the other tile fills the gaps and the tensor
+// pipe still idles a quarter of the time.  Here all SIXTEEN epilogue warps serve the tile whose
+// accumulators are ready (32 columns per thread, four warps per scheduler), then the other tile: an epilogue takes about
+// half as long, MMA(X, q+1) can follow MMA(Y, q) immediately, and the cycle becomes MMA-issue bound.  A thread walks the
+// jobs in the issuer's order (q, tile 0), (q, tile 1), (q + 1, tile 0), ...; nothing but barrier phases is kept per tile.
+constexpr int X_WARPS = 2 * H_TILE_WARPS;         // epilogue warps, all on one tile at a time
+constexpr int X_THREADS = X_WARPS * 32;
+
+struct XCtx {
+  int e, row, slice;        // index among the 512 epilogue threads, row of the tile (= TMEM lane), 32-column slice
+  uint32_t tl;              // TMEM address of this warp's lane quarter, column 0
+  int ch;                   // accumulator-chunk counter (the issuer's sequence: q major, tile minor)
+  int use[2][2];            // chunks drained so far per [tile][accumulator]: barrier phases
+  bool bad;
+};
+__device__ __forceinline__ void x_bar() { asm volatile("bar.sync 1, %0;" ::"n"(X_THREADS) : "memory"); }
+__device__ __forceinline__ void x_epi_done(HSmem& s, int t) {
+  fence_async_smem();
+  tc_fence_before();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(&s.a_ready[t]);
+}
+// one k-unit (8 consecutive K elements, already x H_SA) of row `row` of tile t -> fp16 hi / lo planes
+__device__ __forceinline__ void x_store_ku(HSmem& s, int t, int row, int ku, const float (&x)[8]) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 hh = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+    const float2 hf = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(x[2 * i] - hf.x, x[2 * i + 1] - hf.y);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  const int o = (ku * H_AKU + row) * 16;
+  *reinterpret_cast<uint4*>(s.a[t][0] + o) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(s.a[t][1] + o) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+__device__ __forceinline__ void x_store_a16(HSmem& s, const XCtx& c, int t, int col, const float (&v8)[16]) {
+  float x[8];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = v8[8 * u + i];
+    x_store_ku(s, t, c.row, (col >> 3) + u, x);
+  }
+}
+// chunks of job (q, t) -> fp32 registers (round-to-nearest adds), NP 16-column pieces from column col0
+template <int NP>
+__device__ __forceinline__ void x_drain(HSmem& s, XCtx& c, int t, int col0, int chunks, float (&acc)[NP * 16]) {
+  for (int k = 0; k < chunks; ++k, ++c.ch) {
+    const int ab = c.ch & 1;
+    mbar_wait(&s.d_ready[t][ab], c.use[t][ab] & 1);
+    ++c.use[t][ab];
+    tc_fence_after();
+    const uint32_t ta = c.tl + 128u * ab + col0;
+    if (k == 0) {
+#pragma unroll
+      for (int p = 0; p < NP; ++p) tmem_ld16f(ta + 16 * p, &acc[p * 16]);
+      tmem_ld_wait();
+    } else {
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        uint32_t r[16];
+        tmem_ld16(ta + 16 * p, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[p * 16 + i] = __fadd_rn(acc[p * 16 + i], __uint_as_float(r[i]));
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&s.d_free[t][ab]);
+  }
+}
+// [rows x W] fp32 tile of tile t (every thread holds W / 4 values of its row from column col0) -> full-line stores
+template <int W>
+__device__ __forceinline__ void x_store_tile_coalesced(HSmem& s, const XCtx& c, int t, int col0, const float (&v)[W / 4],
+                                                       float* __restrict__ out, int rows) {
+  constexpr int LD = W + 1, RPW = 128 / W;
+  float* st = reinterpret_cast<float*>(s.a[t][0]);
+#pragma unroll
+  for (int i = 0; i < W / 4; ++i) st[c.row * LD + col0 + i] = v[i];
+  x_bar();
+  const int w = c.e >> 5, lane = c.e & 31;
+  for (int r0 = w * RPW; r0 < rows; r0 += X_WARPS * RPW) {
+    const int r = r0 + (RPW == 2 ? (lane >> 4) : 0), c4 = 4 * (RPW == 2 ? (lane & 15) : lane);
+    if (r < rows) {
+      const float* src = st + r * LD + c4;
+      *reinterpret_cast<float4*>(out + (size_t)r * W + c4) = make_float4(src[0], src[1], src[2], src[3]);
+    }
+  }
+}
+// e2 tile of tile t (staged [128][H_LDS] over its planes) -> edge -> node sums: one column and one 32-row quarter per thread
+__device__ __forceinline__ void x_segment_sums(const HSmem& s, const XCtx& c, int t, int rows, float* __restrict__ v_in) {
+  const int col = c.e & 127, r0 = (c.e >> 7) * 32, r1 = min(rows, r0 + 32);
+  if (r0 >= r1) return;
+  const float* e2t = reinterpret_cast<const float*>(s.a[t][0]);
+  const int* dst = s.dst[t];
+  float run = 0.f;
+  int cur = dst[r0];
+  bool first = true;
+  for (int r = r0; r < r1; ++r) {
+    const int d = dst[r];
+    if (d != cur) {
+      if (first) atomicAdd(v_in + (size_t)cur * 128 + col, run);
+      else v_in[(size_t)cur * 128 + col] = run;
+      first = false; run = 0.f; cur = d;
+    }
+    run += e2t[r * H_LDS + col];
+  }
+  atomicAdd(v_in + (size_t)cur * 128 + col, run);
+}
+
+template <bool FAST, bool FUSE>
+__global__ void __launch_bounds__(H_THREADS, 1)
+sphere_update_e_b_x16_kernel(const float* __restrict__ m, const float* __restrict__ x_ji,
+                             const float* __restrict__ e1_in, const float* __restrict__ rbf0,
+                             const int32_t* __restrict__ dst, int n_edges, HBParams P, float* __restrict__ e1_out,
+                             float* __restrict__ v_in) {
+  extern __shared__ __align__(1024) unsigned char h_raw[];
+  HSmem& s = *reinterpret_cast<HSmem*>(h_raw);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int n_tiles = (n_edges + H_M - 1) / H_M, tile0 = blockIdx.x * 2, ntile = min(2, n_tiles - tile0);
+  // the m tiles (K = 64: 8 k-units per row) of both tiles, in flight during the set-up: 2 (row, k-unit) items per tile
+  float4 mreg[2][2][2];
+  if (warp >= H_CTRL_WARPS) {
+    const int e = tid - H_CTRL_THREADS;
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int f = e + k * X_THREADS, row = f >> 3, ku = f & 7;
+        const int e0 = (tile0 + t) * H_M, rows = min(H_M, n_edges - e0);
+        if (t < ntile && row < rows) {
+          const float* g = m + (size_t)(e0 + row) * 64 + ku * 8;
+          mreg[t][k][0] = __ldg(reinterpret_cast<const float4*>(g));
+          mreg[t][k][1] = __ldg(reinterpret_cast<const float4*>(g + 4));
+        } else {
+          mreg[t][k][0] = mreg[t][k][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+  }
+  h_setup(s, X_WARPS, X_WARPS);
+  for (int i = tid; i < 8 * 128; i += H_THREADS) {
+    const float* b = P.g[i / 128].bias;
+    s.bias[i / 128][i % 128] = b ? H_SA * __ldg(b + i % 128) : 0.f;          // the chain runs pre-scaled by H_SA
+  }
+  for (int i = tid; i < 128 * 8; i += H_THREADS) s.wr[i] = (i % 8 < 6) ? __ldg(P.w_rbf + (i / 8) * 6 + i % 8) : 0.f;
+  for (int i = tid; i < 2 * H_M; i += H_THREADS) {
+    const int e = (tile0 + i / H_M) * H_M + i % H_M;
+    s.dst[i / H_M][i % H_M] = (e < n_edges) ? dst[e] : -1;
+  }
+  if (FUSE) {
+    for (int i = tid; i < 2 * 128; i += H_THREADS)     // lin_ji's output leaves unscaled, lin_kj's feeds an operand (x H_SA)
+      s.bias2[i / 128][i % 128] = (i / 128 ? H_SA : 1.0f) * __ldg(P.g[8 + i / 128].bias + i % 128);
+    for (int i = tid; i < 128 * 8; i += H_THREADS) s.wr2[i] = __ldg(P.n_w_rbf2 + i);      // [128][8]
+    for (int i = tid; i < 64; i += H_THREADS) s.wr1[i] = (i % 8 < 6) ? __ldg(P.n_w_rbf1 + (i / 8) * 6 + i % 8) : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  constexpr int NG = FUSE ? 11 : 8;
+  XCtx c;
+  bool epi = false;
+  if (warp < H_CTRL_WARPS) {
+    h_regs_ctrl();
+    if (tid == 0) h_producer_n(s, P.g, NG, ntile);
+    else if (tid == 32) h_mma_n<false, false>(s, P.g, NG, ntile, s.tmem_base);
+  } else {
+    h_regs_epi();
+    epi = true;
+    const int lane = tid & 31, ew = warp - H_CTRL_WARPS, quarter = warp & 3;
+    c.e = tid - H_CTRL_THREADS; c.row = 32 * quarter + lane; c.slice = ew >> 2;
+    c.tl = s.tmem_base + ((uint32_t)(32 * quarter) << 16);
+    c.ch = 0; c.use[0][0] = c.use[0][1] = c.use[1][0] = c.use[1][1] = 0; c.bad = false;
+    const int col0 = 32 * c.slice;
+    // skip rows (x_ji for q = 0, e1_in for q = 3) -> TMEM stash of tile t, x H_SA
+    auto prefetch_skip = [&](const float* __restrict__ src, int t) {
+      const int e0 = (tile0 + t) * H_M;
+      const bool valid = c.row < min(H_M, n_edges - e0);
+      const float* gsrc = src + (size_t)(e0 + c.row) * 128 + col0;
+      const uint32_t stash = c.tl + 256u + 128u * t + col0;
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        uint32_t r[16];
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const float4 x = valid ? __ldg(reinterpret_cast<const float4*>(gsrc + 16 * p + i)) : make_float4(0, 0, 0, 0);
+          r[i] = __float_as_uint(x.x * H_SA); r[i + 1] = __float_as_uint(x.y * H_SA);
+          r[i + 2] = __float_as_uint(x.z * H_SA); r[i + 3] = __float_as_uint(x.w * H_SA);
+        }
+        tmem_st16(stash + 16 * p, r);
+      }
+      tmem_st_wait();
+    };
+    // A0 = the m tiles
+    for (int t = 0; t < ntile; ++t) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int f = c.e + k * X_THREADS, row = f >> 3, ku = f & 7;
+        const float4 p0 = mreg[t][k][0], p1 = mreg[t][k][1];
+        const float x[8] = {p0.x * H_SA, p0.y * H_SA, p0.z * H_SA, p0.w * H_SA, p1.x * H_SA, p1.y * H_SA, p1.z * H_SA, p1.w * H_SA};
+        x_store_ku(s, t, row, ku, x);
+      }
+      x_epi_done(s, t);
+    }
+    for (int t = 0; t < ntile; ++t) prefetch_skip(x_ji, t);
+    float acc[32];
+#pragma unroll 1
+    for (int q = 0; q < 8; ++q) {
+      const bool add_stash = (q == 0 || q == 2 || q == 3 || q == 5 || q == 7);
+      const bool to_stash = (q == 0 || q == 3 || q == 5);
+#pragma unroll 1
+      for (int t = 0; t < ntile; ++t) {
+        const int e0 = (tile0 + t) * H_M, rows = min(H_M, n_edges - e0);
+        const bool valid = c.row < rows;
+        const size_t ge = (size_t)(e0 + c.row);
+        const uint32_t stash = c.tl + 256u + 128u * t + col0;
+        x_drain<2>(s, c, t, col0, q == 0 ? 1 : 2, acc);
+        float rb[6];
+        if (q == 7) {
+#pragma unroll
+          for (int n = 0; n < 6; ++n) rb[n] = valid ? __ldg(rbf0 + ge * 6 + n) : 0.f;
+        }
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          const int col = col0 + 16 * p;
+          uint32_t r[16];
+          if (add_stash) tmem_ld16(stash + 16 * p, r);           // in flight under the 16 activations below
+          float* v = &acc[16 * p];                               // in place: v8 = H_SA * act(.)
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(&s.bias[q][col + i]);
+            v[i] = hswish8<FAST>(fmaf(v[i], H_SA * H_INV, b.x));
+            v[i + 1] = hswish8<FAST>(fmaf(v[i + 1], H_SA * H_INV, b.y));
+            v[i + 2] = hswish8<FAST>(fmaf(v[i + 2], H_SA * H_INV, b.z));
+            v[i + 3] = hswish8<FAST>(fmaf(v[i + 3], H_SA * H_INV, b.w));
+          }
+          if (add_stash) {
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += __uint_as_float(r[i]);
+          }
+          if (q < 7) {
+            if (to_stash) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(v[i]);
+              tmem_st16(stash + 16 * p, r);
+            }
+            float v16[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v16[i] = v[i];
+            x_store_a16(s, c, t, col, v16);
+          } else {
+            // e1 (unscaled, kept in the accumulator registers for the coalesced store below) and e2 = lin_rbf(rbf0) * e1,
+            // staged as a [128][H_LDS] tile over this tile's planes (all its MMAs of part B are done)
+            float* e2t = reinterpret_cast<float*>(s.a[t][0]);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float o = v[i] * (1.0f / H_SA);
+              c.bad |= !h_finite(o);
+              const float4 w0 = *reinterpret_cast<const float4*>(s.wr + (col + i) * 8);
+              const float2 w1 = *reinterpret_cast<const float2*>(s.wr + (col + i) * 8 + 4);
+              const float gsum = fmaf(w1.y, rb[5], fmaf(w1.x, rb[4], fmaf(w0.w, rb[3], fmaf(w0.z, rb[2],
+                                 fmaf(w0.y, rb[1], w0.x * rb[0])))));
+              e2t[c.row * H_LDS + col + i] = gsum * o;
+              v[i] = o;
+            }
+          }
+        }
+        if (q < 7) {
+          if (to_stash) tmem_st_wait();
+          x_epi_done(s, t);
+          if (q == 2) prefetch_skip(e1_in, t);    // the stash was consumed above; q = 3 adds e1_in from it
+        } else {
+          x_bar();
+          x_segment_sums(s, c, t, rows, v_in);    // spherenet.py:211
+          x_bar();
+          x_store_tile_coalesced<128>(s, c, t, col0, acc, e1_out + (size_t)e0 * 128, rows);
+          if (FUSE) {
+            // operand of part A of the next block: H_SA * e1, from the registers
+            x_bar();                              // every thread has read the staging overlay
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+              float v16[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v16[i] = acc[16 * p + i] * H_SA;
+              x_store_a16(s, c, t, col0 + 16 * p, v16);
+            }
+            x_epi_done(s, t);
+          }
+        }
+      }
+    }
+    if (FUSE) {
+      // ---- part A of the next block (spherenet.py:154-161): three more jobs per tile
+      // G0: x_ji = act(lin_ji(e1))
+#pragma unroll 1
+      for (int t = 0; t < ntile; ++t) {
+        const int e0 = (tile0 + t) * H_M, rows = min(H_M, n_edges - e0);
+        const bool valid = c.row < rows;
+        const size_t ge = (size_t)(e0 + c.row);
+        x_drain<2>(s, c, t, col0, 2, acc);
+        x_epi_done(s, t);     // the operand (= e1) is reused unchanged by lin_kj
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(&s.bias2[0][col0 + i]);
+            float4 o;
+            o.x = hswish<FAST>(fmaf(acc[i], H_INV, b.x));
+            o.y = hswish<FAST>(fmaf(acc[i + 1], H_INV, b.y));
+            o.z = hswish<FAST>(fmaf(acc[i + 2], H_INV, b.z));
+            o.w = hswish<FAST>(fmaf(acc[i + 3], H_INV, b.w));
+            *reinterpret_cast<float4*>(P.n_x_ji + ge * 128 + col0 + i) = o;
+          }
+        }
+      }
+      // G1: x_kj = act(lin_kj(e1)) * lin_rbf2(lin_rbf1(rbf0))
+#pragma unroll 1
+      for (int t = 0; t < ntile; ++t) {
+        const int e0 = (tile0 + t) * H_M, rows = min(H_M, n_edges - e0);
+        const bool valid = c.row < rows;
+        const size_t ge = (size_t)(e0 + c.row);
+        float r8[8];
+        {
+          float rb[6];
+#pragma unroll
+          for (int n = 0; n < 6; ++n) rb[n] = valid ? __ldg(rbf0 + ge * 6 + n) : 0.f;
+#pragma unroll
+          for (int mm = 0; mm < 8; ++mm) {
+            float a = 0.f;
+#pragma unroll
+            for (int n = 0; n < 6; ++n) a = fmaf(s.wr1[mm * 8 + n], rb[n], a);
+            r8[mm] = a;
+          }
+        }
+        x_drain<2>(s, c, t, col0, 2, acc);
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int col = col0 + 16 * p + i;
+            const float4 w0 = *reinterpret_cast<const float4*>(s.wr2 + col * 8);
+            const float4 w1 = *reinterpret_cast<const float4*>(s.wr2 + col * 8 + 4);
+            const float gate = fmaf(w1.w, r8[7], fmaf(w1.z, r8[6], fmaf(w1.y, r8[5], fmaf(w1.x, r8[4],
+                               fmaf(w0.w, r8[3], fmaf(w0.z, r8[2], fmaf(w0.y, r8[1], w0.x * r8[0])))))));
+            v[i] = hswish8<FAST>(fmaf(acc[16 * p + i], H_SA * H_INV, s.bias2[1][col])) * gate;
+          }
+          x_store_a16(s, c, t, col0 + 16 * p, v);
+        }
+        x_epi_done(s, t);
+      }
+      // G2: x_down = act(lin_down(x_kj)), N = 64: 16 columns per thread
+#pragma unroll 1
+      for (int t = 0; t < ntile; ++t) {
+        const int e0 = (tile0 + t) * H_M, rows = min(H_M, n_edges - e0);
+        const int col = 16 * c.slice;
+        float a16[16];
+        x_drain<1>(s, c, t, col, 2, a16);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a16[i] = hswish<FAST>(a16[i] * H_INV);
+        x_store_tile_coalesced<64>(s, c, t, col, a16, P.n_x_down + (size_t)e0 * 64, rows);   // all MMAs of the tile are done
+        x_bar();              // the staging overlay of tile t is read before anything else may touch shared memory
+      }
+    }
+    if (c.bad) atomicOr(&g_h16_overflow, 1u);
+  }
+  (void)epi;
+  h_finish(s, nullptr);
 }
 
 // ---------------------------------------------------------------------------------- update_e part A
@@ -1425,6 +1801,11 @@ int dig3d_h16_set_fast_swish(int32_t on) {
   return DIG3D_OK;
 }
 
+int dig3d_h16_set_wide_epilogue(int32_t on) {
+  h16_wide_epilogue = on ? 1 : 0;
+  return DIG3D_OK;
+}
+
 int dig3d_h16_overflow(int32_t clear) {
   unsigned int v = 0;
   cudaMemcpyFromSymbol(&v, g_h16_overflow, sizeof(v));
@@ -1520,7 +1901,9 @@ int dig3d_sphere_update_e_b_h16(const float* m, const float* e1_in, const float*
   for (int i = 2; i < 6; ++i) P.g[2 + i] = {(const unsigned char*)w->p_res[i], w->b_res[i], 128, 128};
   P.w_rbf = w->w_rbf;
   P.n_w_rbf1 = P.n_w_rbf2 = nullptr; P.n_x_ji = P.n_x_down = nullptr;
-  auto kfn = h16_fast_swish ? sphere_update_e_b_h16_kernel<true, false> : sphere_update_e_b_h16_kernel<false, false>;
+  auto kfn = h16_wide_epilogue
+                 ? (h16_fast_swish ? sphere_update_e_b_x16_kernel<true, false> : sphere_update_e_b_x16_kernel<false, false>)
+                 : (h16_fast_swish ? sphere_update_e_b_h16_kernel<true, false> : sphere_update_e_b_h16_kernel<false, false>);
   int rc = h_smem_attr((const void*)kfn);
   if (rc) return rc;
   const int pairs = ceil_div(ceil_div(n_edges, H_M), 2);
@@ -1549,7 +1932,9 @@ int dig3d_sphere_update_e_ba_h16(const float* m, const float* e1_in, const float
   P.w_rbf = w->w_rbf;
   P.n_w_rbf1 = w_next->w_rbf1; P.n_w_rbf2 = w_next->w_rbf2;
   P.n_x_ji = x_ji_next; P.n_x_down = x_down_next;
-  auto kfn = h16_fast_swish ? sphere_update_e_b_h16_kernel<true, true> : sphere_update_e_b_h16_kernel<false, true>;
+  auto kfn = h16_wide_epilogue
+                 ? (h16_fast_swish ? sphere_update_e_b_x16_kernel<true, true> : sphere_update_e_b_x16_kernel<false, true>)
+                 : (h16_fast_swish ? sphere_update_e_b_h16_kernel<true, true> : sphere_update_e_b_h16_kernel<false, true>);
   int rc = h_smem_attr((const void*)kfn);
   if (rc) return rc;
   const int pairs = ceil_div(ceil_div(n_edges, H_M), 2);

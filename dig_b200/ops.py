@@ -713,6 +713,23 @@ def h16_set_fast_swish(on):
     call("dig3d_h16_set_fast_swish", int(bool(on)))
 
 
+_H16_WIDE = [None]
+
+
+def h16_set_wide_epilogue(on):
+    """update_e part B (+ A): all sixteen epilogue warps on the ready tile (True) or eight per tile (False)."""
+    call("dig3d_h16_set_wide_epilogue", int(bool(on)))
+    _H16_WIDE[0] = bool(on)
+
+
+def h16_wide_from_env():
+    """Apply DIG3D_H16_WIDE (default 1) once per change; called by the model forwards."""
+    import os
+    want = os.environ.get("DIG3D_H16_WIDE", "1") != "0"
+    if _H16_WIDE[0] is not want:
+        h16_set_wide_epilogue(want)
+
+
 def tc_set_fast_swish(on):
     call("dig3d_tc_set_fast_swish", int(bool(on)))
 

@@ -275,6 +275,7 @@ class _DimeNetFamily(nn.Module):
                                             lambda p, c: self._exact(self._forward_dual, z, p, c, g, nf),
                                             pos, tuple(self.parameters()))
             return self._exact(self._forward_train, z, pos, g, nf, exact=bool(pos.requires_grad))
+        ops.h16_wide_from_env()
         if (os.environ.get("DIG3D_DENSE", "h16") == "h16" and g.n_edges and self.num_layers <= 4
                 and os.environ.get("DIG3D_LEAN", "1") != "0"):
             plan = self._inference_plan()

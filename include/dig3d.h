@@ -360,6 +360,11 @@ int dig3d_h16_timeouts(void);
 /* debugging probe: enable / read the clock64() timeline CTA 0 of update_e part B records (host buffer, 128 x i64) */
 int dig3d_h16_trace(int32_t on, long long* out128);
 int dig3d_h16_set_fast_swish(int32_t on);
+/* Process-wide switch of dig3d_sphere_update_e_b_h16 / _ba_h16: 0 = eight epilogue warps per tile (64 columns per
+ * thread), 1 = all sixteen epilogue warps on the tile whose accumulators are ready (32 columns per thread): a shorter
+ * epilogue per tile, so that the chain's cycle is bound by MMA issue.  Same jobs, same barriers; the edge -> node sums
+ * are grouped in 32-row instead of 64-row parts (fp32 summation order only). */
+int dig3d_h16_set_wide_epilogue(int32_t on);
 
 /* ------------------------------------------------------------------ SchNet
  * One interaction (update_e + update_v, schnet.py:29-35,53-59) for hidden_channels == num_filters in

@@ -210,6 +210,46 @@ def test_comenet_lean_inference_path_is_bit_identical(monkeypatch):
     assert torch.equal(both(), u0)
 
 
+@pytest.mark.parametrize("cls_name", ["SphereNet", "DimeNetPP"])
+def test_wide_epilogue_chain_matches_the_eight_warp_chain(cls_name, monkeypatch):
+    """update_e part B (+ the next block's part A) with all sixteen epilogue warps on the ready tile (DIG3D_H16_WIDE=1,
+    default) against the eight-warps-per-tile kernel: same jobs and operands, only the edge -> node sums are grouped
+    differently -- energies agree to fp32 summation noise and both sit within 1e-5 of the oracle.  Ragged last tile, odd
+    tile count, a single tile; fused and separate part A."""
+    from dig_b200 import ops
+    from dig_b200.data import synthetic_batch
+    from dig_b200.threedgraph import method
+    from oracle import restated
+    dev = torch.device("cuda:0")
+    tors = cls_name == "SphereNet"
+    model = getattr(method, cls_name)()
+    sd = formula_state_dict(model.state_dict(), seed=4)
+    model.load_state_dict(sd)
+    model = model.to(dev).eval()
+    sd = {k: v.to(dev) for k, v in sd.items()}
+    try:
+        for nmol in (24, 11, 1):
+            b = synthetic_batch(nmol, "qm9", seed=7, variable=True).to(dev)
+            with torch.no_grad():
+                ref = restated.dimenet_family_forward(sd, b.z, b.pos, b.batch, torsion=tors)
+                outs = {}
+                for wide in ("0", "1"):
+                    for fuse in ("0", "1"):
+                        monkeypatch.setenv("DIG3D_H16_WIDE", wide)
+                        monkeypatch.setenv("DIG3D_FUSE_BA", fuse)
+                        outs[(wide, fuse)] = model(b)
+            torch.cuda.synchronize()
+            assert ops.tc_timeouts() == 0 and not ops.h16_overflow()
+            assert torch.equal(outs[("1", "0")], outs[("1", "1")]), nmol           # fusion is exact in both layouts
+            assert torch.equal(outs[("0", "0")], outs[("0", "1")]), nmol
+            assert rel_err(outs[("1", "1")].cpu().numpy(), outs[("0", "1")].cpu().numpy()) < 2e-6, nmol
+            for k, u in outs.items():
+                assert rel_err(u.cpu().numpy(), ref.cpu().numpy()) < TOL, (nmol, k)
+    finally:
+        monkeypatch.setenv("DIG3D_H16_WIDE", "1")
+        ops.h16_wide_from_env()
+
+
 def test_segment_sum_against_index_add():
     from dig_b200 import ops
     torch.manual_seed(0)
