@@ -202,3 +202,38 @@ def test_out_edge_lists_of_the_graph_build():
     g.out_ptr, g.out_list, g.pos_in = lists
     for a, c in zip(outs[0], outs[1]):
         assert torch.isfinite(a).all() and torch.equal(a, c)
+
+
+@pytest.mark.parametrize("cls_name", ["SphereNet", "DimeNetPP"])
+def test_inference_paths_with_isolated_atoms_and_an_empty_graph_slot(cls_name, monkeypatch):
+    """The lean inference path (cached plan, fused chain, wide epilogue, out-edge lists) on a batch with an isolated atom, a
+    two-atom molecule without triplets and an empty graph slot: bit-identical to the general path and within 1e-5 of the
+    oracle."""
+    from dig_b200 import ops
+    from dig_b200.data import synthetic_molecules, collate, Molecule
+    from dig_b200.threedgraph import method
+    from helpers import formula_state_dict, rel_err
+    from oracle import restated
+    dev = torch.device("cuda:0")
+    m0, m1 = synthetic_molecules(2, "qm9", seed=11, variable=True)
+    items = [Molecule(m0.z, m0.pos), Molecule(torch.tensor([8]), torch.tensor([[60.0, 0.0, 0.0]])),
+             Molecule(torch.tensor([6, 1]), torch.tensor([[0.0, 0.0, 0.0], [1.1, 0.0, 0.0]])), Molecule(m1.z, m1.pos)]
+    b = collate(items).to(dev)
+    b.batch = torch.where(b.batch >= 3, b.batch + 1, b.batch)            # graph 3 is an empty slot
+    b.num_graphs = 5
+    model = getattr(method, cls_name)()
+    sd = formula_state_dict(model.state_dict(), seed=6)
+    model.load_state_dict(sd)
+    model = model.to(dev).eval()
+    with torch.no_grad():
+        monkeypatch.setenv("DIG3D_LEAN", "1")
+        lean = model(b)
+        monkeypatch.setenv("DIG3D_LEAN", "0")
+        general = model(b)
+        ref = restated.dimenet_family_forward({k: v.to(dev) for k, v in sd.items()}, b.z, b.pos, b.batch,
+                                              torsion=cls_name == "SphereNet", num_graphs=5)
+    assert not ops.h16_overflow()
+    assert lean.shape == (5, 1) and torch.isfinite(lean).all()
+    assert torch.equal(lean, general)
+    assert float(lean[3].abs().max()) == 0.0                              # the empty slot sums nothing
+    assert rel_err(lean.cpu().numpy(), ref.cpu().numpy()) < 1e-5
