@@ -897,6 +897,12 @@ def sphere_triplet_gather(x_down, sbf_p, t_p, g, w_sbf2, w_t2):
     if e == 0 or g.n_triplets == 0:
         return torch.zeros(e, x_down.size(1), device=x_down.device, dtype=F32)
     m = torch.empty(e, x_down.size(1), device=x_down.device, dtype=F32)
+    if (x_down.size(1) == 64 and g.cap is not None and g.cap <= 64 and g.graph_ptr is not None and g.batch is not None
+            and (x_down.data_ptr() & 15) == 0 and GATHER_MODE[0] != "edge"):
+        # the inference organisation (warp per source node, out-edge lists): bit-identical to the edge-centred kernel
+        triplet_gather(_p(x_down, F32, "x_down").value, _p(sbf_p, F32, "sbf_p"), _p(t_p, F32, "t_p"), g,
+                       _p(w_sbf2, F32, "w_sbf2"), _p(w_t2, F32, "w_t2"), _p(m).value, _stream())
+        return m
     call("dig3d_sphere_triplet_gather", _p(x_down, F32, "x_down"), _p(sbf_p, F32, "sbf_p"), _p(t_p, F32, "t_p"), 8,
          _p(g.src), _p(g.dst), _p(g.row_ptr), _p(g.trip_ptr), e, _p(w_sbf2, F32, "w_sbf2"), _p(w_t2, F32, "w_t2"),
          _p(m), _stream())
