@@ -432,7 +432,7 @@ def main():
             out_host.copy_(u, non_blocking=True)
         torch.cuda.current_stream().synchronize()      # the user reads the energies every step
 
-    # the same loop with two batches in flight (dig_b200.pipeline.InferencePipeline, what run.val does): every step still
+    # the same loop with `depth` batches in flight (dig_b200.pipeline.InferencePipeline, what run.val does): every step still
     # copies its inputs from pinned host memory and its energies are still read on the host, one step later
     from dig_b200.pipeline import InferencePipeline
     from dig_b200.pipeline import DEFAULT_DEPTH

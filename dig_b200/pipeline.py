@@ -1,4 +1,4 @@
-"""Host-fed inference with two batches in flight (the loop of reference run.py:137-180 `run.val`, non-force branch).
+"""Host-fed inference with several batches in flight (the loop of reference run.py:137-180 `run.val`, non-force branch).
 
 `model(batch)` has one host synchronisation (the edge / triplet counts size the buffers of the interaction kernels).
 In a plain loop the GPU idles from that point of batch n+1 back to the end of batch n's readback.  Here consecutive
@@ -10,9 +10,10 @@ kernels, same inputs; the streams share nothing but the read-only weights).
 """
 import torch
 
-# Measured on the B200, SphereNet QM9-shape batches of 128 (profiles/r02_batches_in_flight.txt): 1 batch at a time 106.5 k
-# molecules/s, 2 in flight 131.2 k, 3: 133.4 k, 4: 134.0 k -- the second stream fills the first one's launch gaps, partial
-# waves and count-readback bubble; beyond three there is nothing left to fill.
+# Measured on the B200, SphereNet QM9-shape batches of 128 (profiles/r02_batches_in_flight_final.txt): 1 batch at a time
+# 109.5 k molecules/s, 2 in flight 152.0 k, 3: 162.8 k, 4: 163.9 k, 6: 164.1 k -- the other streams fill one stream's launch
+# gaps, partial waves and count-readback bubble; beyond four there is nothing left to fill.  (Before the host work per
+# forward was cut, profiles/r02_batches_in_flight.txt, the loop was host-bound and three were enough: 133.4 k.)
 DEFAULT_DEPTH = 4
 
 
