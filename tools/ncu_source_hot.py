@@ -4,7 +4,6 @@ instructions aggregated per CUDA source line.
     python tools/ncu_source_hot.py gpurun_out/x.ncu-rep [top]
 """
 import csv
-import io
 import subprocess
 import sys
 from collections import defaultdict
