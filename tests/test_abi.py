@@ -27,6 +27,35 @@ def test_library_exports_every_declared_symbol():
     assert lib.dig3d_abi_version() == 2
 
 
+def test_ctypes_signatures_match_the_header_declarations():
+    """Every `int dig3d_x(...)` declaration of include/dig3d.h has as many parameters as its ctypes argtypes entry, pointers
+    where the header has pointers and integers / doubles where it has scalars -- a mismatch would only show as a crash
+    (or garbage arguments) on the GPU box."""
+    import ctypes
+    from dig_b200 import _lib
+    with open(os.path.join(ROOT, "include", "dig3d.h")) as fh:
+        text = re.sub(r"/\*.*?\*/", " ", fh.read(), flags=re.S)
+    text = re.sub(r"//[^\n]*", " ", text)
+    decls = dict(re.findall(r"\b(dig3d_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S))
+    assert set(decls) == set(_lib.SIGNATURES)
+    for name, params in decls.items():
+        params = " ".join(params.split())
+        plist = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+        sig = _lib.SIGNATURES[name]
+        assert len(plist) == len(sig), f"{name}: header has {len(plist)} parameters, ctypes {len(sig)}"
+        for decl, ct in zip(plist, sig):
+            is_ptr_decl = "*" in decl
+            is_ptr_ct = ct is ctypes.c_void_p or ct is ctypes.c_char_p or hasattr(ct, "contents") or hasattr(ct, "_type_") and isinstance(ct._type_, type)
+            if is_ptr_decl:
+                assert is_ptr_ct, f"{name}: `{decl}` is a pointer, ctypes has {ct}"
+            elif "double" in decl:
+                assert ct is ctypes.c_double, f"{name}: `{decl}` vs {ct}"
+            elif "int64_t" in decl:
+                assert ct is ctypes.c_int64, f"{name}: `{decl}` vs {ct}"
+            elif "int32_t" in decl or decl.startswith("int "):
+                assert ct is ctypes.c_int32, f"{name}: `{decl}` vs {ct}"
+
+
 def test_library_is_sm100a():
     import subprocess
     from dig_b200 import _lib
