@@ -474,6 +474,32 @@ def invalidate_packed():
     _PACK_GENERATION[0] += 1
 
 
+# A parameter object that is REPLACED (module.weight = nn.Parameter(...)) is invisible to caches keyed on the old
+# object's version / address: every parameter registration in the process bumps the generation (cheap; model
+# construction bumps it a few hundred times, nothing is cached yet).
+try:
+    from torch.nn.modules.module import register_module_parameter_registration_hook as _reg_hook
+    _reg_hook(lambda _module, _name, _param: invalidate_packed())
+except ImportError:          # older torch: replaced parameters need an explicit model.invalidate_packed()
+    pass
+
+
+def plan_key(model, *extra):
+    """(cached parameter list, key) of a model's inference plan: pack generation, sum of tensor._version, every parameter's
+    storage address, plus `extra`.  The list is cached on the model and refreshed by plan_key_refresh() on a miss."""
+    params = model.__dict__.get("_plan_params")
+    if params is None:
+        params = model.__dict__["_plan_params"] = list(model.parameters())
+    return (_PACK_GENERATION[0], sum(p._version for p in params), tuple(p.data_ptr() for p in params)) + tuple(extra)
+
+
+def plan_key_refresh(model, *extra):
+    """On a plan miss: re-read the parameter list (parameters may have been replaced or moved) and return the key the new
+    plan is stored under."""
+    model.__dict__.pop("_plan_params", None)
+    return plan_key(model, *extra)
+
+
 def _pack_matrices(mats, kind):
     """One device buffer holding the packed copies of `mats` ([N, K] fp32 weights) + their byte offsets.
     kind 'tc': TF32 hi/lo planes (dig3d_tc_pack, 8*N*K bytes); kind 'h16': FP16 hi/lo slabs (dig3d_h16_pack, 4*N*K)."""

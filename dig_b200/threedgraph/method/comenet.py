@@ -282,13 +282,11 @@ class ComENet(nn.Module):
     # workspace with raw addresses.  Bit-identical to `_forward_h16` (DIG3D_LEAN=0;
     # tests/test_gpu_parity.py::test_comenet_lean_inference_path_is_bit_identical).
     def _inference_plan(self):
-        params = self.__dict__.get("_plan_params")
-        if params is None:
-            params = self.__dict__["_plan_params"] = list(self.parameters())
-        key = (ops._PACK_GENERATION[0], sum(p._version for p in params), tuple(p.data_ptr() for p in params))
+        key = ops.plan_key(self)
         plan = self.__dict__.get("_plan")
         if plan is not None and plan["key"] == key:
             return plan
+        key = ops.plan_key_refresh(self)
         keep = []                                   # tensors the addresses below point into
 
         def lin(weight, bias):

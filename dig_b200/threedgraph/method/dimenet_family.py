@@ -348,14 +348,12 @@ class _DimeNetFamily(nn.Module):
     # raw addresses.  Same kernels, same arguments, same order: the energies are bit-identical to the path above
     # (DIG3D_LEAN=0 selects it; tests/test_gpu_parity.py::test_lean_inference_path_is_bit_identical).
     def _inference_plan(self):
-        params = self.__dict__.get("_plan_params")
-        if params is None:
-            params = self.__dict__["_plan_params"] = list(self.parameters())
-        key = (ops._PACK_GENERATION[0], sum(p._version for p in params), tuple(p.data_ptr() for p in params),
-               os.environ.get("DIG3D_INIT_TABLES", "1"))
+        tables = os.environ.get("DIG3D_INIT_TABLES", "1")
+        key = ops.plan_key(self, tables)
         plan = self.__dict__.get("_plan")
         if plan is not None and plan["key"] == key:
             return plan
+        key = ops.plan_key_refresh(self, tables)
         holders = [self.init_v] + list(self.update_vs)
         if not ops.update_v_h16_supported(self.init_v, self.out_channels):
             return None

@@ -199,3 +199,57 @@ def test_paced_gc_disables_and_restores_collection():
         pace.tick()                             # third step: paced collection
         assert probe() is None
     assert gc.isenabled()
+
+
+def test_inference_plan_follows_the_parameters(monkeypatch):
+    """Host logic of the cached inference plan with the packing ops stubbed out (no GPU): the plan is
+    reused while nothing changed and rebuilt after an in-place update (tensor._version), a `.data` write followed by
+    invalidate_packed(), load_state_dict, and a REPLACED parameter object (parameter-registration hook); copies of the
+    model do not carry it."""
+    import copy
+    import torch
+    from torch import nn
+    from dig_b200 import ops
+    from dig_b200.threedgraph.method import SphereNet, ComENet
+
+    built = []
+    monkeypatch.setattr(ops, "update_v_h16_supported", lambda *a, **k: True)
+    monkeypatch.setattr(ops, "pack_update_v_h16", lambda holders, cache: ("parr", "varr", len(holders[0].lins)))
+    monkeypatch.setattr(ops, "pack_init_e", lambda m: "init_w")
+    monkeypatch.setattr(ops, "tc_pack_matrix", lambda w, cache, key, kind="tc": torch.zeros(1))
+    monkeypatch.setattr(ops, "init_e_tables", lambda m, cache: ("ti", "tj", "packed"))
+    monkeypatch.setattr(ops, "tc_pack_update_e", lambda m, tors, cache, kind="tc": built.append(m.lin_up.weight) or "layer")
+    model = SphereNet()
+    p1 = model._inference_plan()
+    assert p1 is model._inference_plan() and len(built) == 4
+    with torch.no_grad():
+        model.update_es[2].lin.weight.add_(1.0)                    # in place: version bump
+    p2 = model._inference_plan()
+    assert p2 is not p1 and p2 is model._inference_plan()
+    model.update_es[1].lin_kj.weight.data.mul_(2.0)                # behind autograd's back: the version does not move
+    assert model._inference_plan() is p2
+    model.invalidate_packed()
+    p3 = model._inference_plan()
+    assert p3 is not p2
+    model.load_state_dict(model.state_dict())
+    p4 = model._inference_plan()
+    assert p4 is not p3
+    fresh = nn.Parameter(torch.zeros_like(model.update_es[0].lin_up.weight))
+    model.update_es[0].lin_up.weight = fresh                       # a NEW parameter object
+    built.clear()
+    p5 = model._inference_plan()
+    assert p5 is not p4 and built[0] is fresh
+    assert any(p is fresh for p in model.__dict__["_plan_params"])
+    with torch.no_grad():
+        fresh.add_(1.0)                                            # ... whose later updates are tracked too
+    assert model._inference_plan() is not p5
+    clone = copy.deepcopy(model)
+    assert "_plan" not in clone.__dict__ and "_plan_params" not in clone.__dict__ and "_plan" in model.__dict__
+
+    # ComENet: same key logic (ops.plan_key); its plan builder needs the packed-weight registry, only the key is checked
+    cm = ComENet(cutoff=6.0)
+    k1 = ops.plan_key(cm)
+    assert k1 == ops.plan_key(cm)
+    with torch.no_grad():
+        cm.lin_out.weight.mul_(0.5)
+    assert ops.plan_key(cm) != k1
